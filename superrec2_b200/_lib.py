@@ -1,0 +1,200 @@
+"""ctypes binding of ``libsr2.so`` (C ABI in ``include/sr2.h``).
+
+The library is built in-tree by ``superrec2_b200/csrc/build.sh`` (or
+``__graft_entry__.build()``).  Nothing here falls back to another
+implementation: a missing library or GPU raises :class:`Sr2Error`.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+
+import numpy as np
+
+SR2_INF = 0x3FFFFFFF
+SR2_KEEP_TABLES = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsr2.so")
+
+
+class Sr2Error(RuntimeError):
+    """An ``sr2_*`` call failed; ``code`` is the negative ``sr2_status``."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libsr2 error {code}: {message}")
+        self.code = code
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [
+        ("upload_ms", c_float),
+        ("solve_ms", c_float),
+        ("waves_ms", c_float),
+        ("results_ms", c_float),
+        ("n_waves", c_int32),
+        ("n_launches", c_int32),
+        ("n_cells", c_int64),
+    ]
+
+
+_I32P = POINTER(c_int32)
+_I64P = POINTER(c_int64)
+
+#: every symbol declared in include/sr2.h: name -> (restype, argtypes)
+SIGNATURES = {
+    "sr2_version": (c_int, []),
+    "sr2_create": (c_int, [c_int, POINTER(c_void_p)]),
+    "sr2_destroy": (None, [c_void_p]),
+    "sr2_last_error": (c_char_p, [c_void_p]),
+    "sr2_set_stream": (c_int, [c_void_p, c_void_p]),
+    "sr2_synchronize": (c_int, [c_void_p]),
+    "sr2_set_species": (c_int, [c_void_p, c_int32, _I32P, _I32P, _I32P]),
+    "sr2_dtl_upload": (c_int, [c_void_p, c_int32, _I64P, _I32P, _I32P, _I32P, _I32P, c_uint32]),
+    "sr2_dtl_solve": (c_int, [c_void_p]),
+    "sr2_dtl_results": (c_int, [c_void_p, _I32P, _I32P, _I32P]),
+    "sr2_dtl_run": (c_int, [c_void_p, c_int32, _I64P, _I32P, _I32P, _I32P, _I32P, c_uint32,
+                            _I32P, _I32P, _I32P]),
+    "sr2_dtl_tables": (c_int, [c_void_p, c_int32, _I32P, _I32P]),
+    "sr2_last_timing": (c_int, [c_void_p, POINTER(Timing)]),
+}
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load ``libsr2.so`` (once) and declare its prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Sr2Error(-2, f"{LIB_PATH} is missing: build it with superrec2_b200/csrc/build.sh "
+                           "(there is no CPU implementation to fall back to)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def i32(array) -> np.ndarray:
+    return np.ascontiguousarray(array, dtype=np.int32)
+
+
+def i64(array) -> np.ndarray:
+    return np.ascontiguousarray(array, dtype=np.int64)
+
+
+def p32(array: np.ndarray):
+    return array.ctypes.data_as(_I32P)
+
+
+def p64(array: np.ndarray):
+    return array.ctypes.data_as(_I64P)
+
+
+class Context:
+    """One ``sr2_ctx``: a device, a stream, a species tree and at most one batch."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        handle = c_void_p()
+        code = self._lib.sr2_create(device, ctypes.byref(handle))
+        if code != 0:
+            message = self._lib.sr2_last_error(None).decode()
+            raise Sr2Error(code, message)
+        self._handle = handle
+        self.device = device
+        self.n_species = 0
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.sr2_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # interpreter shutdown
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def _check(self, code: int):
+        if code != 0:
+            raise Sr2Error(code, self._lib.sr2_last_error(self._handle).decode())
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self._lib.sr2_set_stream(self._handle, c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._check(self._lib.sr2_synchronize(self._handle))
+
+    def set_species(self, parent, child0, child1):
+        parent, child0, child1 = i32(parent), i32(child0), i32(child1)
+        self._check(self._lib.sr2_set_species(
+            self._handle, len(parent), p32(parent), p32(child0), p32(child1)))
+        self.n_species = len(parent)
+
+    # ------------------------------------------------------------------ dtl
+    def dtl_upload(self, node_off, left, right, leaf_species, costs, flags=0):
+        node_off, left, right = i64(node_off), i32(left), i32(right)
+        leaf_species, costs = i32(leaf_species), i32(costs)
+        self._batch = (len(node_off) - 1, int(node_off[-1]))
+        self._check(self._lib.sr2_dtl_upload(
+            self._handle, len(node_off) - 1, p64(node_off), p32(left), p32(right),
+            p32(leaf_species), p32(costs), flags))
+
+    def dtl_solve(self):
+        self._check(self._lib.sr2_dtl_solve(self._handle))
+
+    def dtl_results(self):
+        n_inst, n_nodes = self._batch
+        min_cost = np.empty(n_inst, np.int32)
+        root = np.empty(n_inst, np.int32)
+        mapping = np.empty(n_nodes, np.int32)
+        self._check(self._lib.sr2_dtl_results(self._handle, p32(min_cost), p32(root), p32(mapping)))
+        return min_cost, root, mapping
+
+    def dtl_run(self, node_off, left, right, leaf_species, costs, flags=0):
+        """upload + solve + results with host buffers (the e2e path)."""
+        node_off, left, right = i64(node_off), i32(left), i32(right)
+        leaf_species, costs = i32(leaf_species), i32(costs)
+        n_inst, n_nodes = len(node_off) - 1, int(node_off[-1])
+        self._batch = (n_inst, n_nodes)
+        min_cost = np.empty(n_inst, np.int32)
+        root = np.empty(n_inst, np.int32)
+        mapping = np.empty(n_nodes, np.int32)
+        self._check(self._lib.sr2_dtl_run(
+            self._handle, n_inst, p64(node_off), p32(left), p32(right), p32(leaf_species),
+            p32(costs), flags, p32(min_cost), p32(root), p32(mapping)))
+        return min_cost, root, mapping
+
+    def dtl_tables(self, instance: int, n_nodes: int):
+        values = np.empty((n_nodes, self.n_species), np.int32)
+        tags = np.empty((n_nodes, self.n_species, 2), np.int32)
+        self._check(self._lib.sr2_dtl_tables(self._handle, instance, p32(values), p32(tags)))
+        return values, tags
+
+    def timing(self) -> Timing:
+        out = Timing()
+        self._check(self._lib.sr2_last_timing(self._handle, ctypes.byref(out)))
+        return out
+
+
+_contexts = {}
+
+
+def default_context(device: int = 0) -> Context:
+    """Process-wide context per device (created on first use)."""
+    ctx = _contexts.get(device)
+    if ctx is None:
+        ctx = _contexts[device] = Context(device)
+    return ctx

@@ -1,0 +1,211 @@
+// sr2_context.cu -- context, error reporting and the species-tree layout.
+//
+// The species tree replaces the reference's LowestCommonAncestor oracle
+// (/root/reference/src/superrec2/utils/trees.py:31-142): instead of an Euler
+// tour + sparse table queried per candidate, every node gets its depth and a
+// preorder [tin, tout) interval once, and the DP kernels only use look-ups.
+#include <cstdio>
+#include <cstring>
+
+#include "sr2_internal.cuh"
+
+int sr2_fail(sr2_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+int sr2_cuda_fail(sr2_ctx* ctx, cudaError_t e, const char* what) {
+    std::string msg = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    cudaGetLastError();  // clear the sticky flag where possible
+    return sr2_fail(ctx, SR2_ERR_CUDA, msg);
+}
+
+static std::string g_create_error;
+
+extern "C" int sr2_version(void) { return 100; }
+
+extern "C" int sr2_create(int device, sr2_ctx** out) {
+    if (!out) return SR2_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device available (") +
+                         (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                         "); libsr2 has no CPU path";
+        cudaGetLastError();
+        return SR2_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "device index out of range";
+        return SR2_ERR_ARG;
+    }
+    sr2_ctx* ctx = new sr2_ctx();
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        delete ctx;
+        return SR2_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+        delete ctx;
+        return SR2_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+        g_create_error = "libsr2 is built for sm_100a (B200) only; found sm_" +
+                         std::to_string(prop.major) + std::to_string(prop.minor);
+        delete ctx;
+        return SR2_ERR_CUDA;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+        delete ctx;
+        return SR2_ERR_CUDA;
+    }
+    ctx->own_stream = true;
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return SR2_OK;
+}
+
+extern "C" void sr2_destroy(sr2_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    sr2_free_dtl(ctx);
+    sr2_free_super(ctx);
+    if (ctx->d_species_slab) cudaFree(ctx->d_species_slab);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* sr2_last_error(const sr2_ctx* ctx) {
+    return ctx ? ctx->err.c_str() : g_create_error.c_str();
+}
+
+extern "C" int sr2_set_stream(sr2_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return SR2_ERR_ARG;
+    if (ctx->own_stream && ctx->stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+    }
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return SR2_OK;
+}
+
+extern "C" int sr2_synchronize(sr2_ctx* ctx) {
+    if (!ctx) return SR2_ERR_ARG;
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SR2_OK;
+}
+
+extern "C" int sr2_last_timing(const sr2_ctx* ctx, sr2_timing* out) {
+    if (!ctx || !out) return SR2_ERR_ARG;
+    *out = ctx->timing;
+    return SR2_OK;
+}
+
+extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
+                               const int32_t* child0, const int32_t* child1) {
+    if (!ctx) return SR2_ERR_ARG;
+    if (S < 1 || !parent || !child0 || !child1)
+        return sr2_fail(ctx, SR2_ERR_ARG, "sr2_set_species: empty species tree or null array");
+    if (S > 65535)
+        return sr2_fail(ctx, SR2_ERR_RANGE,
+                        "sr2_set_species: more than 65535 species nodes (arg-min keys hold 16-bit ranks)");
+    if (parent[0] != -1)
+        return sr2_fail(ctx, SR2_ERR_ARG, "sr2_set_species: node 0 must be the root (parent -1)");
+    // BFS numbering <=> the i-th internal node (in rank order) has children 2i+1, 2i+2.
+    std::vector<int32_t> int_list;
+    int next = 1;
+    for (int y = 0; y < S; ++y) {
+        bool leaf = child0[y] < 0;
+        if (leaf != (child1[y] < 0))
+            return sr2_fail(ctx, SR2_ERR_ARG, "sr2_set_species: node " + std::to_string(y) +
+                                                  " has exactly one child (tree must be binary)");
+        if (leaf) continue;
+        if (child0[y] != next || child1[y] != next + 1 || next + 1 >= S)
+            return sr2_fail(ctx, SR2_ERR_ARG,
+                            "sr2_set_species: nodes are not numbered in level order at node " +
+                                std::to_string(y));
+        if (parent[next] != y || parent[next + 1] != y)
+            return sr2_fail(ctx, SR2_ERR_ARG, "sr2_set_species: parent[] disagrees with child arrays at node " +
+                                                  std::to_string(y));
+        int_list.push_back(y);
+        next += 2;
+    }
+    if (next != S)
+        return sr2_fail(ctx, SR2_ERR_ARG, "sr2_set_species: child arrays do not cover all nodes");
+
+    ctx->S = S;
+    ctx->pitch = (S + 31) / 32 * 32;
+    ctx->n_internal = (int)int_list.size();
+    ctx->h_parent.assign(parent, parent + S);
+    ctx->h_child0.assign(child0, child0 + S);
+    ctx->h_depth.assign(S, 0);
+    for (int y = 1; y < S; ++y) ctx->h_depth[y] = ctx->h_depth[parent[y]] + 1;
+    ctx->D = ctx->h_depth[S - 1] + 1;
+    if (ctx->D > 32767)
+        return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_set_species: species tree deeper than 32767 levels");
+    // preorder entry/exit times, iteratively
+    ctx->h_tin.assign(S, 0);
+    ctx->h_tout.assign(S, 0);
+    {
+        std::vector<int32_t> size(S, 1);
+        for (int y = S - 1; y >= 1; --y) size[parent[y]] += size[y];
+        ctx->h_tin[0] = 0;
+        for (int y = 0; y < S; ++y) {
+            ctx->h_tout[y] = ctx->h_tin[y] + size[y];
+            if (child0[y] >= 0) {
+                ctx->h_tin[child0[y]] = ctx->h_tin[y] + 1;
+                ctx->h_tin[child1[y]] = ctx->h_tin[y] + 1 + size[child0[y]];
+            }
+        }
+    }
+    ctx->h_int_list = int_list;
+    ctx->h_int_lvl_off.assign(ctx->D + 1, 0);
+    for (int y : int_list) ctx->h_int_lvl_off[ctx->h_depth[y] + 1]++;
+    for (int d = 0; d < ctx->D; ++d) ctx->h_int_lvl_off[d + 1] += ctx->h_int_lvl_off[d];
+
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    sr2_free_dtl(ctx);
+    sr2_free_super(ctx);
+    if (ctx->d_species_slab) {
+        cudaFree(ctx->d_species_slab);
+        ctx->d_species_slab = nullptr;
+    }
+    size_t n_int = int_list.size();
+    size_t total = (size_t)S * 5 + (n_int ? n_int : 1) + (size_t)ctx->D + 1;
+    SR2_CUDA(ctx, cudaMalloc(&ctx->d_species_slab, total * sizeof(int32_t)));
+    std::vector<int32_t> slab(total, 0);
+    int32_t* h = slab.data();
+    int32_t* d = ctx->d_species_slab;
+    size_t off = 0;
+    auto put = [&](const std::vector<int32_t>& v, size_t n) {
+        if (!v.empty()) memcpy(h + off, v.data(), v.size() * sizeof(int32_t));
+        const int32_t* p = d + off;
+        off += n;
+        return p;
+    };
+    ctx->dsp.S = S;
+    ctx->dsp.pitch = ctx->pitch;
+    ctx->dsp.D = ctx->D;
+    ctx->dsp.n_internal = ctx->n_internal;
+    ctx->dsp.child0 = put(ctx->h_child0, S);
+    ctx->dsp.depth = put(ctx->h_depth, S);
+    ctx->dsp.tin = put(ctx->h_tin, S);
+    ctx->dsp.tout = put(ctx->h_tout, S);
+    ctx->dsp.parent = put(ctx->h_parent, S);
+    ctx->dsp.int_list = put(ctx->h_int_list, n_int ? n_int : 1);
+    ctx->dsp.int_lvl_off = put(ctx->h_int_lvl_off, (size_t)ctx->D + 1);
+    SR2_CUDA(ctx, cudaMemcpyAsync(d, h, total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SR2_OK;
+}

@@ -1,0 +1,763 @@
+// sr2_dtl.cu -- the `dtl` (Tofigh-Hallett-Lagergren) reconciliation DP on sm_100a.
+//
+// Replaces /root/reference/src/superrec2/compute/reconciliation.py:
+//   _compute_thl_try_speciation            :60-113   (candidates 1-2 below)
+//   _compute_thl_try_duplication_transfer  :116-189  (candidates 3-5 below)
+//   _compute_thl_table                     :192-225  (the wavefront driver)
+//   _decode_thl_table + reconcile_thl      :228-294  (selection + traceback)
+//
+// The reference evaluates every (object node u, species x) cell by scanning all
+// species (O(|G| |S|^2)).  Here one launch handles one HEIGHT of the object
+// trees of a whole batch; each object node is one "row" of |S| cells owned by a
+// warp (or by a CTA for large |S|).  Per row the two child rows are staged in
+// shared memory as 64-bit keys (value, BFS rank, depth) and two sweeps over the
+// BFS-indexed species tree give every cell what it needs in O(1):
+//   up-sweep   M[y] = min over subtree(y)            (SUBMIN, reverse BFS levels)
+//   down-sweep P[x] = min over species incomparable  (SEPMIN, forward BFS levels)
+//              to x  = min(P[parent x], M[sibling x])
+// Lexicographic key order == the reference's first-candidate-wins rule
+// (utils/dynamic_programming.py:228-238) because candidates are offered in BFS
+// order.  The loss term is added AFTER the arg-min, as the reference does
+// (reconciliation.py:97-108,153-183), so cell values depend on that tie-break.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <omp.h>
+
+#include "sr2_internal.cuh"
+
+// ---------------------------------------------------------------------------
+// device-resident problem
+// ---------------------------------------------------------------------------
+struct DtlChunk {
+    int32_t inst_begin = 0, inst_end = 0;
+    int64_t row_begin = 0, row_end = 0;   // global row range of the chunk
+    std::vector<int64_t> wave_off;        // [H+1] global row offsets per height (1-based waves)
+};
+
+struct DtlProblem {
+    int32_t B = 0;
+    int64_t N = 0, R = 0;
+    uint32_t flags = 0;
+    int32_t costs[5] = {0, 0, 0, 0, 0};
+    bool need_decoded_cost = false;
+    std::vector<int64_t> node_off;  // [B+1]
+    std::vector<DtlChunk> chunks;
+    int64_t max_chunk_rows = 0;
+    // device
+    int32_t* d_rows_slab = nullptr;  // row_cl,row_cr,row_node,row_left,row_right [5*R]
+    int32_t *row_cl = nullptr, *row_cr = nullptr, *row_node = nullptr, *row_left = nullptr,
+            *row_right = nullptr;
+    int64_t* d_root_row = nullptr;   // [B] global row of the root, or -1-leaf_species
+    int32_t* d_root_node = nullptr;  // [B] global node id of the root
+    int32_t* d_T = nullptr;          // [max_chunk_rows * pitch]
+    uint32_t* d_tag = nullptr;       // [max_chunk_rows * pitch]
+    int32_t* d_C = nullptr;          // decoded cost rows (only if need_decoded_cost)
+    int32_t* d_min_cost = nullptr;   // [B]
+    int32_t* d_root_species = nullptr;  // [B]
+    int32_t* d_map = nullptr;        // [N]
+    // host copies for the test hook
+    std::vector<int32_t> h_left, h_right, h_leaf;
+    std::vector<int64_t> h_node_row;  // [N] global row of a node or -1 (only with KEEP_TABLES)
+    bool solved = false;
+    // wave launch configuration (fixed per upload)
+    int spad = 0, wave_warps = 0;
+    size_t wave_smem = 0;
+    bool cta_per_row = false;
+};
+
+void sr2_free_dtl(sr2_ctx* ctx) {
+    DtlProblem* p = ctx->dtl;
+    if (!p) return;
+    cudaFree(p->d_rows_slab);
+    cudaFree(p->d_root_row);
+    cudaFree(p->d_root_node);
+    cudaFree(p->d_T);
+    cudaFree(p->d_tag);
+    cudaFree(p->d_C);
+    cudaFree(p->d_min_cost);
+    cudaFree(p->d_root_species);
+    cudaFree(p->d_map);
+    delete p;
+    ctx->dtl = nullptr;
+}
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+struct DtlCosts {
+    int spe, dup, hgt, loss;
+};
+
+template <int TPR>
+__device__ __forceinline__ void group_sync() {
+    if (TPR == 32)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
+// One candidate of a cell: children placed at the species held by keys a (left
+// child) and b (right child); `extra` is event cost + loss * (sum of distances).
+__device__ __forceinline__ void dtl_offer(u64 a, u64 b, int extra, int& best, unsigned& tag) {
+    unsigned va = (unsigned)key_value(a), vb = (unsigned)key_value(b);
+    if (va < (unsigned)SR2_INF && vb < (unsigned)SR2_INF) {
+        int v = (int)(va + vb) + extra;
+        if (v < best) {
+            best = v;
+            tag = (unsigned)key_rank(a) | ((unsigned)key_rank(b) << 16);
+        }
+    }
+}
+
+// Cell (u, x).  Ml/Mr: SUBMIN keys at x; Pl/Pr: SEPMIN keys at x (unused for the
+// root); Sl/Sr: slot arrays, still holding SUBMIN at the children of x.
+// Candidate order = reference update order (reconciliation.py:110-113,185-189).
+__device__ __forceinline__ void dtl_cell(int x, int dx, int cx, bool is_root, u64 Ml, u64 Mr,
+                                         u64 Pl, u64 Pr, const u64* Sl, const u64* Sr,
+                                         const DtlCosts& cs, int& best, unsigned& tag) {
+    best = SR2_INF;
+    tag = SR2_NO_TAG;
+    if (cx >= 0) {
+        u64 l0 = Sl[cx], l1 = Sl[cx + 1], r0 = Sr[cx], r1 = Sr[cx + 1];
+        // 1. speciation, left child below x's first child, right below the second
+        dtl_offer(l0, r1, cs.loss * (key_depth(l0) + key_depth(r1) - 2 * dx - 2), best, tag);
+        // 2. speciation, the other way round
+        dtl_offer(l1, r0, cs.loss * (key_depth(l1) + key_depth(r0) - 2 * dx - 2), best, tag);
+    }
+    // 3. duplication: both children anywhere below (or at) x
+    dtl_offer(Ml, Mr, cs.dup + cs.loss * (key_depth(Ml) + key_depth(Mr) - 2 * dx), best, tag);
+    if (!is_root) {
+        // 4. transfer of the left child to a species incomparable to x
+        dtl_offer(Pl, Mr, cs.hgt + cs.loss * (key_depth(Mr) - dx), best, tag);
+        // 5. transfer of the right child
+        dtl_offer(Ml, Pr, cs.hgt + cs.loss * (key_depth(Ml) - dx), best, tag);
+    }
+}
+
+// TPR = threads per row: 32 (one warp per row, several rows per CTA) or the CTA
+// size (one row per CTA, for species trees too large for a warp's share of smem).
+template <int TPR>
+__global__ void __launch_bounds__(TPR == 32 ? 256 : TPR)
+dtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
+                const int32_t* __restrict__ row_cr, int64_t row_begin, int64_t chunk_row0,
+                int n_rows, int32_t* __restrict__ T, uint32_t* __restrict__ tags, DtlCosts cs,
+                int spad) {
+    extern __shared__ u64 smem[];
+    const int S = sp.S;
+    int group, lane, groups_per_cta;
+    if (TPR == 32) {
+        group = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        groups_per_cta = blockDim.x >> 5;
+    } else {
+        group = 0;
+        lane = threadIdx.x;
+        groups_per_cta = 1;
+    }
+    int local = blockIdx.x * groups_per_cta + group;
+    if (local >= n_rows) return;  // uniform per group
+    const int64_t gr = row_begin + local;              // global row
+    const size_t slot = (size_t)(gr - chunk_row0);     // row inside the chunk's tables
+    u64* Sl = smem + (size_t)group * 2 * spad;
+    u64* Sr = Sl + spad;
+    const int cl = row_cl[gr], cr = row_cr[gr];
+    const int32_t* __restrict__ Tl = cl >= 0 ? T + (size_t)cl * sp.pitch : nullptr;
+    const int32_t* __restrict__ Tr = cr >= 0 ? T + (size_t)cr * sp.pitch : nullptr;
+
+    // stage the two child rows as keys
+    for (int y = lane; y < S; y += TPR) {
+        int d = __ldg(sp.depth + y);
+        int vl = Tl ? Tl[y] : (y == -1 - cl ? 0 : SR2_INF);
+        int vr = Tr ? Tr[y] : (y == -1 - cr ? 0 : SR2_INF);
+        Sl[y] = key_make(vl, y, d);
+        Sr[y] = key_make(vr, y, d);
+    }
+    group_sync<TPR>();
+
+    // up-sweep: slot[y] <- min over subtree(y); deepest level has leaves only
+    for (int d = sp.D - 2; d >= 0; --d) {
+        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
+        for (int i = b + lane; i < e; i += TPR) {
+            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+            Sl[p] = key_min(Sl[p], key_min(Sl[c], Sl[c + 1]));
+            Sr[p] = key_min(Sr[p], key_min(Sr[c], Sr[c + 1]));
+        }
+        group_sync<TPR>();
+    }
+
+    int32_t* __restrict__ Tout = T + slot * sp.pitch;
+    uint32_t* __restrict__ Gout = tags + slot * sp.pitch;
+
+    // root cell; afterwards slot[0] holds P[root] = "nothing is incomparable to the root"
+    if (lane == 0) {
+        int best;
+        unsigned tag;
+        dtl_cell(0, 0, __ldg(sp.child0), true, Sl[0], Sr[0], SR2_KEY_NONE, SR2_KEY_NONE, Sl, Sr, cs,
+                 best, tag);
+        Tout[0] = best;
+        Gout[0] = tag;
+        Sl[0] = SR2_KEY_NONE;
+        Sr[0] = SR2_KEY_NONE;
+    }
+    group_sync<TPR>();
+
+    // down-sweep: each internal species p finishes the cells of its two children
+    // and leaves their P keys in their slots for the next level.
+    for (int d = 0; d < sp.D - 1; ++d) {
+        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
+        for (int i = b + lane; i < e; i += TPR) {
+            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+            u64 Ppl = Sl[p], Ppr = Sr[p];
+            u64 m0l = Sl[c], m1l = Sl[c + 1], m0r = Sr[c], m1r = Sr[c + 1];
+            u64 P0l = key_min(Ppl, m1l), P1l = key_min(Ppl, m0l);
+            u64 P0r = key_min(Ppr, m1r), P1r = key_min(Ppr, m0r);
+            int best0, best1;
+            unsigned tag0, tag1;
+            dtl_cell(c, d + 1, __ldg(sp.child0 + c), false, m0l, m0r, P0l, P0r, Sl, Sr, cs, best0, tag0);
+            dtl_cell(c + 1, d + 1, __ldg(sp.child0 + c + 1), false, m1l, m1r, P1l, P1r, Sl, Sr, cs, best1,
+                     tag1);
+            Tout[c] = best0;
+            Tout[c + 1] = best1;
+            Gout[c] = tag0;
+            Gout[c + 1] = tag1;
+            Sl[c] = P0l;
+            Sl[c + 1] = P1l;
+            Sr[c] = P0r;
+            Sr[c + 1] = P1r;
+        }
+        group_sync<TPR>();
+    }
+}
+
+// Event cost of node (x; children at a, b) as ReconciliationOutput.cost() sees it
+// (/root/reference/src/superrec2/model/reconciliation.py:273-365).  SR2_INF = INVALID.
+__device__ __forceinline__ int dtl_event_cost(const DevSpecies& sp, int x, int a, int b,
+                                              const DtlCosts& cs) {
+    int tx = __ldg(sp.tin + x), ox = __ldg(sp.tout + x), dx = __ldg(sp.depth + x);
+    int ta = __ldg(sp.tin + a), oa = __ldg(sp.tout + a), da = __ldg(sp.depth + a);
+    int tb = __ldg(sp.tin + b), ob = __ldg(sp.tout + b), db = __ldg(sp.depth + b);
+    bool x_anc_a = tx <= ta && ta < ox, x_anc_b = tx <= tb && tb < ox;
+    bool a_sanc_x = a != x && ta <= tx && tx < oa, b_sanc_x = b != x && tb <= tx && tx < ob;
+    if (a_sanc_x || b_sanc_x) return SR2_INF;
+    if (x_anc_a && x_anc_b) {
+        // speciation iff a and b sit below different children of x
+        int c = __ldg(sp.child0 + x);
+        bool spec = false;
+        if (c >= 0 && a != x && b != x) {
+            int t1 = __ldg(sp.tin + c + 1);  // subtree(c) = [tx+1, t1), subtree(c+1) = [t1, ox)
+            spec = (ta < t1) != (tb < t1);
+        }
+        int dist = da + db - 2 * dx;
+        return spec ? cs.spe + cs.loss * (dist - 2) : cs.dup + cs.loss * dist;
+    }
+    if (x_anc_a) return cs.hgt + cs.loss * (da - dx);
+    if (x_anc_b) return cs.hgt + cs.loss * (db - dx);
+    return SR2_INF;
+}
+
+// Decoded-cost rows: C[u][x] = cost() of the solution decoded from (u, x)
+//   = event(x, sl, sr) + C[l][sl] + C[r][sr]      with (sl, sr) = tag[u][x].
+// Only needed when cost() can differ from the table value (speciation cost != 0,
+// see DESIGN.md "selection"); one warp per row.
+__global__ void __launch_bounds__(256)
+dtl_decoded_cost_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
+                        const int32_t* __restrict__ row_cr, int64_t row_begin, int64_t chunk_row0,
+                        int n_rows, const uint32_t* __restrict__ tags, int32_t* __restrict__ C,
+                        DtlCosts cs) {
+    int local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (local >= n_rows) return;
+    const int64_t gr = row_begin + local;
+    const size_t slot = (size_t)(gr - chunk_row0);
+    const int cl = row_cl[gr], cr = row_cr[gr];
+    for (int x = lane; x < sp.S; x += 32) {
+        unsigned tag = tags[slot * sp.pitch + x];
+        int out = SR2_INF;
+        if (tag != SR2_NO_TAG) {
+            int a = tag & 0xffffu, b = tag >> 16;
+            int ca = cl >= 0 ? C[(size_t)cl * sp.pitch + a] : (a == -1 - cl ? 0 : SR2_INF);
+            int cb = cr >= 0 ? C[(size_t)cr * sp.pitch + b] : (b == -1 - cr ? 0 : SR2_INF);
+            int ev = dtl_event_cost(sp, x, a, b, cs);
+            if (ca < SR2_INF && cb < SR2_INF && ev < SR2_INF) out = ev + ca + cb;
+        }
+        C[slot * sp.pitch + x] = out;
+    }
+}
+
+// Selection (reconcile_thl:284-294): roots are tried in BFS order and the first
+// strict minimum of cost() wins.  One warp per instance.
+__global__ void __launch_bounds__(256)
+dtl_select_kernel(DevSpecies sp, const int64_t* __restrict__ root_row,
+                  const int32_t* __restrict__ root_node, int inst_begin, int n_inst,
+                  int64_t chunk_row0, const int32_t* __restrict__ T, const int32_t* __restrict__ C,
+                  int32_t* __restrict__ min_cost, int32_t* __restrict__ root_species,
+                  int32_t* __restrict__ map) {
+    int local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (local >= n_inst) return;
+    int b = inst_begin + local;
+    int64_t gr = root_row[b];
+    if (gr < 0) {  // single-leaf object tree: the leaf sits at its own species at cost 0
+        if (lane == 0) {
+            int s = (int)(-1 - gr);
+            min_cost[b] = 0;
+            root_species[b] = s;
+            map[root_node[b]] = s;
+        }
+        return;
+    }
+    size_t slot = (size_t)(gr - chunk_row0);
+    u64 best = SR2_KEY_NONE;
+    for (int x = lane; x < sp.S; x += 32) {
+        int t = T[slot * sp.pitch + x];
+        if (t < SR2_INF) {  // roots without an entry are skipped (Hazard B)
+            int c = C ? C[slot * sp.pitch + x] : t;
+            best = key_min(best, ((u64)(unsigned)c << 32) | (unsigned)x);
+        }
+    }
+    for (int off = 16; off; off >>= 1) best = key_min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if (lane == 0) {
+        bool none = best == SR2_KEY_NONE;
+        int x = none ? -1 : (int)(best & 0xffffffffu);
+        min_cost[b] = none ? SR2_INF : (int)(best >> 32);
+        root_species[b] = x;
+        map[root_node[b]] = x;
+    }
+}
+
+// Traceback, one height per launch from the top down: a node of height h reads its
+// own species (set by its parent, which is higher) and assigns its two children.
+__global__ void __launch_bounds__(256)
+dtl_traceback_kernel(DevSpecies sp, const int32_t* __restrict__ row_node,
+                     const int32_t* __restrict__ row_left, const int32_t* __restrict__ row_right,
+                     int64_t row_begin, int64_t chunk_row0, int n_rows,
+                     const uint32_t* __restrict__ tags, int32_t* __restrict__ map) {
+    int local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= n_rows) return;
+    int64_t gr = row_begin + local;
+    size_t slot = (size_t)(gr - chunk_row0);
+    int x = map[row_node[gr]];
+    int a = -1, b = -1;
+    if (x >= 0) {
+        unsigned tag = tags[slot * sp.pitch + x];
+        if (tag != SR2_NO_TAG) {
+            a = tag & 0xffffu;
+            b = tag >> 16;
+        }
+    }
+    map[row_left[gr]] = a;
+    map[row_right[gr]] = b;
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
+                              const int32_t* left, const int32_t* right,
+                              const int32_t* leaf_species, const int32_t costs[5], uint32_t flags) {
+    if (!ctx) return SR2_ERR_ARG;
+    double t0 = now_ms();
+    if (ctx->S == 0) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_upload: call sr2_set_species first");
+    if (B < 0 || !node_off || !costs || (B > 0 && (!left || !right || !leaf_species)))
+        return sr2_fail(ctx, SR2_ERR_ARG, "sr2_dtl_upload: null array");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    sr2_free_dtl(ctx);
+    const int S = ctx->S;
+    const int64_t N = B ? node_off[B] : 0;
+    if (N >= (int64_t)1 << 31)
+        return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_dtl_upload: more than 2^31 object nodes in one batch");
+    for (int k = 0; k < 5; ++k)
+        if (costs[k] < 0 || costs[k] > (1 << 20))
+            return sr2_fail(ctx, SR2_ERR_RANGE,
+                            "sr2_dtl_upload: event costs must be integers in [0, 2^20]");
+
+    DtlProblem* p = new DtlProblem();
+    ctx->dtl = p;
+    p->B = B;
+    p->N = N;
+    p->flags = flags;
+    memcpy(p->costs, costs, sizeof(p->costs));
+    // cost() == table value unless speciations are charged: the table never adds the
+    // speciation cost (reconciliation.py:97-108) but cost() does (DESIGN.md "selection").
+    p->need_decoded_cost = costs[0] != 0;
+    p->node_off.assign(node_off, node_off + B + 1);
+
+    // ---- pass 1: validate, heights, per-instance histogram of heights -------
+    std::vector<uint16_t> height(N);
+    int bad_inst = -1;
+    std::string bad_msg;
+    int64_t max_finite_bound = 0;
+    int Hmax = 0;
+    std::vector<int32_t> inst_H(B, 0);
+#pragma omp parallel for schedule(dynamic, 64) reduction(max : Hmax)
+    for (int b = 0; b < B; ++b) {
+        int64_t off = node_off[b];
+        int64_t G = node_off[b + 1] - off;
+        const char* why = nullptr;
+        if (G < 1) why = "empty object tree";
+        std::vector<uint8_t> refs;
+        if (!why) refs.assign(G, 0);
+        for (int64_t u = G - 1; u >= 0 && !why; --u) {
+            int l = left[off + u], r = right[off + u];
+            if (l < 0 && r < 0) {
+                int s = leaf_species[off + u];
+                if (s < 0 || s >= S) why = "leaf species out of range";
+                height[off + u] = 0;
+            } else if (l <= u || r <= u || l >= G || r >= G || l == r) {
+                why = "children must be two distinct nodes numbered after their parent";
+            } else {
+                if (++refs[l] > 1 || ++refs[r] > 1) why = "a node has two parents";
+                int h = 1 + std::max(height[off + l], height[off + r]);
+                if (h > 65535) why = "object tree higher than 65535";
+                height[off + u] = (uint16_t)h;
+            }
+        }
+        if (!why)
+            for (int64_t u = 1; u < G; ++u)
+                if (refs[u] != 1) {
+                    why = "a node other than node 0 has no parent";
+                    break;
+                }
+        if (why) {
+#pragma omp critical
+            if (bad_inst < 0 || b < bad_inst) {
+                bad_inst = b;
+                bad_msg = why;
+            }
+            continue;
+        }
+        inst_H[b] = height[off];
+        Hmax = std::max(Hmax, (int)height[off]);
+    }
+    if (bad_inst >= 0)
+        return sr2_fail(ctx, SR2_ERR_ARG,
+                        "sr2_dtl_upload: instance " + std::to_string(bad_inst) + ": " + bad_msg);
+    // finite table values are bounded by (#internal nodes) * (largest event term)
+    {
+        int64_t maxG = 0;
+        for (int b = 0; b < B; ++b) maxG = std::max(maxG, node_off[b + 1] - node_off[b]);
+        int64_t ev = std::max<int64_t>({std::abs((int64_t)costs[0]), std::abs((int64_t)costs[1]),
+                                        std::abs((int64_t)costs[2])}) +
+                     2 * std::abs((int64_t)costs[3]) * (int64_t)ctx->D;
+        max_finite_bound = maxG * ev;
+        if (max_finite_bound >= (1 << 29))
+            return sr2_fail(ctx, SR2_ERR_RANGE,
+                            "sr2_dtl_upload: costs x tree size may overflow the int32 DP table");
+    }
+
+    // ---- chunking by device memory ------------------------------------------
+    size_t free_b = 0, total_b = 0;
+    SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t per_row = (size_t)ctx->pitch * (p->need_decoded_cost ? 12 : 8);
+    size_t fixed = (size_t)N * 4 * 7 + (size_t)B * 32 + (64u << 20);
+    if (free_b < fixed + per_row * 4)
+        return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: batch does not fit in device memory");
+    int64_t rows_budget = (int64_t)(((free_b - fixed) / 10 * 9) / per_row);
+    std::vector<int64_t> inst_rows(B);
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b) inst_rows[b] = (node_off[b + 1] - node_off[b] - 1) / 2;
+    {
+        DtlChunk c;
+        int64_t rows = 0, total_rows = 0;
+        for (int b = 0; b < B; ++b) {
+            if (inst_rows[b] > rows_budget)
+                return sr2_fail(ctx, SR2_ERR_NOMEM,
+                                "sr2_dtl_upload: one instance alone exceeds device memory");
+            if (rows + inst_rows[b] > rows_budget) {
+                c.inst_end = b;
+                c.row_end = total_rows;
+                p->chunks.push_back(c);
+                c = DtlChunk();
+                c.inst_begin = b;
+                c.row_begin = total_rows;
+                rows = 0;
+            }
+            rows += inst_rows[b];
+            total_rows += inst_rows[b];
+        }
+        c.inst_end = B;
+        c.row_end = total_rows;
+        p->chunks.push_back(c);
+        p->R = total_rows;
+    }
+    if ((flags & SR2_KEEP_TABLES) && p->chunks.size() > 1)
+        return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: SR2_KEEP_TABLES needs the batch to fit in one chunk");
+    const int64_t R = p->R;
+
+    // ---- pass 2: rows in (chunk, height, instance, node) order ---------------
+    std::vector<int32_t> rows_slab((size_t)std::max<int64_t>(R, 1) * 5);
+    int32_t* h_cl = rows_slab.data();
+    int32_t* h_cr = h_cl + R;
+    int32_t* h_node = h_cr + R;
+    int32_t* h_left = h_node + R;
+    int32_t* h_right = h_left + R;
+    std::vector<int64_t> h_root_row(B);
+    std::vector<int32_t> h_root_node(B);
+    std::vector<int64_t> node_row;  // global row of each node (internal) -- scratch
+    node_row.assign(N, -1);
+    const int W = Hmax + 1;
+    for (auto& c : p->chunks) {
+        int nb = c.inst_end - c.inst_begin;
+        // cnt[(b - inst_begin) * W + h]
+        std::vector<int64_t> cnt((size_t)nb * W, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int b = c.inst_begin; b < c.inst_end; ++b) {
+            int64_t off = node_off[b], G = node_off[b + 1] - off;
+            int64_t* mine = cnt.data() + (size_t)(b - c.inst_begin) * W;
+            for (int64_t u = 0; u < G; ++u) mine[height[off + u]]++;
+        }
+        // exclusive prefix over (h, b): rows of one height are contiguous
+        c.wave_off.assign(W + 1, 0);
+        int64_t run = c.row_begin;
+        c.wave_off[0] = run;
+        for (int h = 1; h < W; ++h) {
+            c.wave_off[h] = run;  // wave h covers [wave_off[h], wave_off[h+1])
+            for (int i = 0; i < nb; ++i) {
+                int64_t k = cnt[(size_t)i * W + h];
+                cnt[(size_t)i * W + h] = run;
+                run += k;
+            }
+        }
+        c.wave_off[W] = run;
+        p->max_chunk_rows = std::max(p->max_chunk_rows, c.row_end - c.row_begin);
+#pragma omp parallel for schedule(dynamic, 64)
+        for (int b = c.inst_begin; b < c.inst_end; ++b) {
+            int64_t off = node_off[b], G = node_off[b + 1] - off;
+            int64_t* cursor = cnt.data() + (size_t)(b - c.inst_begin) * W;
+            for (int64_t u = 0; u < G; ++u) {
+                int h = height[off + u];
+                if (h > 0) node_row[off + u] = cursor[h]++;
+            }
+            for (int64_t u = 0; u < G; ++u) {
+                int64_t gr = node_row[off + u];
+                if (gr < 0) continue;
+                int l = left[off + u], r = right[off + u];
+                int64_t rl = node_row[off + l], rr = node_row[off + r];
+                h_cl[gr] = rl >= 0 ? (int32_t)(rl - c.row_begin) : -1 - leaf_species[off + l];
+                h_cr[gr] = rr >= 0 ? (int32_t)(rr - c.row_begin) : -1 - leaf_species[off + r];
+                h_node[gr] = (int32_t)(off + u);
+                h_left[gr] = (int32_t)(off + l);
+                h_right[gr] = (int32_t)(off + r);
+            }
+            h_root_node[b] = (int32_t)off;
+            h_root_row[b] = node_row[off] >= 0 ? node_row[off] : -1 - (int64_t)leaf_species[off];
+        }
+    }
+
+    // ---- device allocations + H2D ---------------------------------------------
+    SR2_CUDA(ctx, cudaMalloc(&p->d_rows_slab, rows_slab.size() * sizeof(int32_t)));
+    p->row_cl = p->d_rows_slab;
+    p->row_cr = p->row_cl + R;
+    p->row_node = p->row_cr + R;
+    p->row_left = p->row_node + R;
+    p->row_right = p->row_left + R;
+    SR2_CUDA(ctx, cudaMalloc(&p->d_root_row, std::max<size_t>(B, 1) * sizeof(int64_t)));
+    SR2_CUDA(ctx, cudaMalloc(&p->d_root_node, std::max<size_t>(B, 1) * sizeof(int32_t)));
+    SR2_CUDA(ctx, cudaMalloc(&p->d_min_cost, std::max<size_t>(B, 1) * sizeof(int32_t)));
+    SR2_CUDA(ctx, cudaMalloc(&p->d_root_species, std::max<size_t>(B, 1) * sizeof(int32_t)));
+    SR2_CUDA(ctx, cudaMalloc(&p->d_map, std::max<size_t>(N, 1) * sizeof(int32_t)));
+    size_t table_elems = (size_t)std::max<int64_t>(p->max_chunk_rows, 1) * ctx->pitch;
+    SR2_CUDA(ctx, cudaMalloc(&p->d_T, table_elems * sizeof(int32_t)));
+    SR2_CUDA(ctx, cudaMalloc(&p->d_tag, table_elems * sizeof(uint32_t)));
+    if (p->need_decoded_cost) SR2_CUDA(ctx, cudaMalloc(&p->d_C, table_elems * sizeof(int32_t)));
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_rows_slab, rows_slab.data(), rows_slab.size() * sizeof(int32_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_root_row, h_root_row.data(), (size_t)B * sizeof(int64_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_root_node, h_root_node.data(), (size_t)B * sizeof(int32_t),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (flags & SR2_KEEP_TABLES) {
+        p->h_left.assign(left, left + N);
+        p->h_right.assign(right, right + N);
+        p->h_leaf.assign(leaf_species, leaf_species + N);
+        p->h_node_row.swap(node_row);
+    }
+    ctx->timing.upload_ms = (float)(now_ms() - t0);
+    return SR2_OK;
+}
+
+static int dtl_configure_waves(sr2_ctx* ctx, DtlProblem* p) {
+    const int S = ctx->S;
+    p->spad = (S + 1) & ~1;
+    const size_t per_row = (size_t)2 * p->spad * sizeof(u64);
+    if (S <= 1024) {
+        p->cta_per_row = false;
+        p->wave_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx->smem_optin - 1024) / per_row));
+        p->wave_smem = per_row * p->wave_warps;
+        SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
+    } else {
+        if (per_row > ctx->smem_optin)
+            return sr2_fail(ctx, SR2_ERR_RANGE, "dtl: species tree too large for one CTA's shared memory");
+        p->cta_per_row = true;
+        p->wave_warps = 16;
+        p->wave_smem = per_row;
+        SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
+    }
+    return SR2_OK;
+}
+
+static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const DtlChunk& c, int64_t row_begin,
+                           int64_t n_rows, const DtlCosts& cs) {
+    if (n_rows <= 0) return SR2_OK;
+    if (!p->cta_per_row) {
+        int64_t grid = (n_rows + p->wave_warps - 1) / p->wave_warps;
+        dtl_wave_kernel<32><<<(unsigned)grid, p->wave_warps * 32, p->wave_smem, ctx->stream>>>(
+            ctx->dsp, p->row_cl, p->row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
+            p->spad);
+    } else {
+        dtl_wave_kernel<512><<<(unsigned)n_rows, 512, p->wave_smem, ctx->stream>>>(
+            ctx->dsp, p->row_cl, p->row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
+            p->spad);
+    }
+    SR2_CUDA(ctx, cudaGetLastError());
+    return SR2_OK;
+}
+
+extern "C" int sr2_dtl_solve(sr2_ctx* ctx) {
+    if (!ctx) return SR2_ERR_ARG;
+    DtlProblem* p = ctx->dtl;
+    if (!p) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_solve: nothing uploaded");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    {
+        int rc = dtl_configure_waves(ctx, p);
+        if (rc) return rc;
+    }
+    cudaStream_t st = ctx->stream;
+    DtlCosts cs{p->costs[0], p->costs[1], p->costs[2], p->costs[3]};
+    int n_waves = 0, n_launch = 0;
+    float waves_ms = 0.f;
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    for (const DtlChunk& c : p->chunks) {
+        const int H = (int)c.wave_off.size() - 2;  // highest wave
+        SR2_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+        for (int h = 1; h <= H; ++h) {
+            int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+            if (n <= 0) continue;
+            int rc = dtl_launch_wave(ctx, p, c, c.wave_off[h], n, cs);
+            if (rc) return rc;
+            ++n_waves;
+            ++n_launch;
+        }
+        SR2_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+        if (p->need_decoded_cost) {
+            for (int h = 1; h <= H; ++h) {
+                int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+                if (n <= 0) continue;
+                dtl_decoded_cost_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(
+                    ctx->dsp, p->row_cl, p->row_cr, c.wave_off[h], c.row_begin, (int)n, p->d_tag, p->d_C, cs);
+                ++n_launch;
+            }
+        }
+        int n_inst = c.inst_end - c.inst_begin;
+        if (n_inst > 0) {
+            dtl_select_kernel<<<(n_inst + 7) / 8, 256, 0, st>>>(
+                ctx->dsp, p->d_root_row, p->d_root_node, c.inst_begin, n_inst, c.row_begin, p->d_T,
+                p->need_decoded_cost ? p->d_C : nullptr, p->d_min_cost, p->d_root_species, p->d_map);
+            ++n_launch;
+        }
+        for (int h = H; h >= 1; --h) {
+            int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+            if (n <= 0) continue;
+            dtl_traceback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+                ctx->dsp, p->row_node, p->row_left, p->row_right, c.wave_off[h], c.row_begin, (int)n,
+                p->d_tag, p->d_map);
+            ++n_launch;
+        }
+        SR2_CUDA(ctx, cudaGetLastError());
+        if (p->chunks.size() > 1) {
+            // the next chunk reuses the table buffers: account the wave time now
+            SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+            waves_ms += ms;
+        }
+    }
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+    if (p->chunks.size() == 1) cudaEventElapsedTime(&waves_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->timing.solve_ms, ctx->ev[0], ctx->ev[1]);
+    ctx->timing.waves_ms = waves_ms;
+    ctx->timing.n_waves = n_waves;
+    ctx->timing.n_launches = n_launch;
+    ctx->timing.n_cells = p->R * (int64_t)ctx->S;
+    p->solved = true;
+    return SR2_OK;
+}
+
+extern "C" int sr2_dtl_results(sr2_ctx* ctx, int32_t* out_min_cost, int32_t* out_root_species,
+                               int32_t* out_map_species) {
+    if (!ctx) return SR2_ERR_ARG;
+    DtlProblem* p = ctx->dtl;
+    if (!p || !p->solved) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_results: solve first");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    double t0 = now_ms();
+    if (out_min_cost)
+        SR2_CUDA(ctx, cudaMemcpyAsync(out_min_cost, p->d_min_cost, (size_t)p->B * 4, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    if (out_root_species)
+        SR2_CUDA(ctx, cudaMemcpyAsync(out_root_species, p->d_root_species, (size_t)p->B * 4,
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_map_species)
+        SR2_CUDA(ctx, cudaMemcpyAsync(out_map_species, p->d_map, (size_t)p->N * 4, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+    SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing.results_ms = (float)(now_ms() - t0);
+    return SR2_OK;
+}
+
+extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, const int32_t* left,
+                           const int32_t* right, const int32_t* leaf_species, const int32_t costs[5],
+                           uint32_t flags, int32_t* out_min_cost, int32_t* out_root_species,
+                           int32_t* out_map_species) {
+    int rc = sr2_dtl_upload(ctx, B, node_off, left, right, leaf_species, costs, flags);
+    if (rc) return rc;
+    rc = sr2_dtl_solve(ctx);
+    if (rc) return rc;
+    return sr2_dtl_results(ctx, out_min_cost, out_root_species, out_map_species);
+}
+
+extern "C" int sr2_dtl_tables(sr2_ctx* ctx, int32_t instance, int32_t* out_value, int32_t* out_tag) {
+    if (!ctx) return SR2_ERR_ARG;
+    DtlProblem* p = ctx->dtl;
+    if (!p || !p->solved) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_tables: solve first");
+    if (!(p->flags & SR2_KEEP_TABLES))
+        return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_tables: upload with SR2_KEEP_TABLES");
+    if (instance < 0 || instance >= p->B) return sr2_fail(ctx, SR2_ERR_ARG, "sr2_dtl_tables: bad instance");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int S = ctx->S, pitch = ctx->pitch;
+    int64_t off = p->node_off[instance], G = p->node_off[instance + 1] - off;
+    std::vector<int32_t> rowT(pitch);
+    std::vector<uint32_t> rowG(pitch);
+    for (int64_t u = 0; u < G; ++u) {
+        int64_t gr = p->h_node_row[off + u];
+        int32_t* ov = out_value ? out_value + (size_t)u * S : nullptr;
+        int32_t* ot = out_tag ? out_tag + (size_t)u * S * 2 : nullptr;
+        if (gr < 0) {
+            for (int x = 0; x < S; ++x) {
+                if (ov) ov[x] = x == p->h_leaf[off + u] ? 0 : SR2_INF;
+                if (ot) ot[2 * x] = ot[2 * x + 1] = -1;
+            }
+            continue;
+        }
+        SR2_CUDA(ctx, cudaMemcpy(rowT.data(), p->d_T + (size_t)gr * pitch, (size_t)pitch * 4, cudaMemcpyDeviceToHost));
+        SR2_CUDA(ctx, cudaMemcpy(rowG.data(), p->d_tag + (size_t)gr * pitch, (size_t)pitch * 4, cudaMemcpyDeviceToHost));
+        for (int x = 0; x < S; ++x) {
+            if (ov) ov[x] = rowT[x];
+            if (ot) {
+                bool none = rowG[x] == SR2_NO_TAG;
+                ot[2 * x] = none ? -1 : (int32_t)(rowG[x] & 0xffffu);
+                ot[2 * x + 1] = none ? -1 : (int32_t)(rowG[x] >> 16);
+            }
+        }
+    }
+    return SR2_OK;
+}

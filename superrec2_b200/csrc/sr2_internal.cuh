@@ -1,0 +1,92 @@
+// sr2_internal.cuh -- shared declarations of libsr2 (not part of the C ABI).
+//
+// Data layout in HBM:
+//   species tree  : int32 arrays indexed by BFS rank (parent, child0, depth,
+//                   preorder entry/exit times) + the list of internal nodes in
+//                   BFS order with per-level offsets; the i-th internal node of
+//                   that list has children 2i+1 and 2i+2.
+//   DP tables     : one row of `pitch` int32 per INTERNAL object node ("row"),
+//                   rows ordered by wave (= height of the node), so one wave
+//                   reads rows written by earlier launches and writes a
+//                   contiguous block.  Leaf rows are never stored: a leaf row is
+//                   0 at its species and INF elsewhere and is synthesised on load.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/sr2.h"
+
+#define SR2_NO_TAG 0xffffffffu
+
+typedef unsigned long long u64;
+
+// Device view of the species tree (all pointers are device memory).
+struct DevSpecies {
+    int S;           // number of species nodes
+    int pitch;       // row pitch of the DP tables (int32 elements, multiple of 32)
+    int D;           // number of levels (max depth + 1)
+    int n_internal;  // number of internal species nodes
+    const int32_t* child0;      // [S]  rank of the first child, -1 for leaves
+    const int32_t* depth;       // [S]
+    const int32_t* tin;         // [S]  preorder entry time
+    const int32_t* tout;        // [S]  preorder exit time (exclusive)
+    const int32_t* parent;      // [S]
+    const int32_t* int_list;    // [n_internal] BFS ranks of the internal nodes, BFS order
+    const int32_t* int_lvl_off; // [D+1] offsets into int_list per depth
+};
+
+struct DtlProblem;
+struct SuperProblem;
+
+struct sr2_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+
+    // species tree (host copies + one device slab)
+    int S = 0, pitch = 0, D = 0, n_internal = 0;
+    std::vector<int32_t> h_parent, h_child0, h_depth, h_tin, h_tout, h_int_list, h_int_lvl_off;
+    int32_t* d_species_slab = nullptr;
+    DevSpecies dsp{};
+
+    DtlProblem* dtl = nullptr;
+    SuperProblem* super = nullptr;
+    sr2_timing timing{};
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+int sr2_fail(sr2_ctx* ctx, int code, const std::string& msg);
+int sr2_cuda_fail(sr2_ctx* ctx, cudaError_t e, const char* what);
+void sr2_free_dtl(sr2_ctx* ctx);
+void sr2_free_super(sr2_ctx* ctx);
+
+#define SR2_CUDA(ctx, call)                                        \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return sr2_cuda_fail(ctx, e__, #call); \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// 64-bit arg-min keys.  Lexicographic order (value, BFS rank[, kind]) is the
+// reference's "first candidate that reaches the minimum wins"
+// (utils/dynamic_programming.py:228-238): candidates are offered in BFS order.
+// The low 16 bits carry the depth of the species so that the loss term
+// loss * distance needs no second look-up; they never decide a comparison
+// because the rank above them is unique.
+//   dtl      : value[63:32] | rank[31:16]          | depth[15:0]
+//   superdtl : value[63:32] | rank[31:16] | kind[15] | depth[14:0]
+// ---------------------------------------------------------------------------
+#define SR2_KEY_NONE 0xffffffffffffffffull
+
+__device__ __forceinline__ u64 key_make(int value, int rank, int depth) {
+    return ((u64)(unsigned)value << 32) | ((u64)(unsigned)rank << 16) | (unsigned)depth;
+}
+__device__ __forceinline__ int key_value(u64 k) { return (int)(k >> 32); }
+__device__ __forceinline__ int key_rank(u64 k) { return (int)((k >> 16) & 0xffffu); }
+__device__ __forceinline__ int key_depth(u64 k) { return (int)(k & 0xffffu); }
+__device__ __forceinline__ u64 key_min(u64 a, u64 b) { return a < b ? a : b; }

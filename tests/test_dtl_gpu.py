@@ -1,0 +1,156 @@
+"""Parity of the CUDA dtl path (through the C ABI) with the CPU oracle and with
+the fixtures produced by the unmodified reference.  Bit-exact: integer costs,
+same tags, same returned mapping."""
+import numpy as np
+import pytest
+
+from oracle import binding as oracle
+from superrec2_b200 import _lib, synth
+from superrec2_b200.compute.reconciliation import reconcile_thl, reconcile_thl_batch
+from superrec2_b200.model.reconciliation import ReconciliationInput
+from superrec2_b200.utils.dynamic_programming import RetentionPolicy
+from tests.helpers import FlatDtl
+
+pytestmark = pytest.mark.gpu
+INF = _lib.SR2_INF
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return _lib.default_context(0)
+
+
+def _gpu_tables(ctx, flat):
+    ctx.set_species(*flat.species_args)
+    node_off = np.array([0, len(flat.objects.left)], np.int64)
+    min_cost, root, mapping = ctx.dtl_run(node_off, *flat.object_args, flat.costs,
+                                          flags=_lib.SR2_KEEP_TABLES)
+    value, tag = ctx.dtl_tables(0, len(flat.objects.left))
+    return int(min_cost[0]), int(root[0]), mapping, value, tag
+
+
+def test_golden_small_tables(ctx, golden):
+    """Cell by cell (value and tag) against the reference's own tables."""
+    for fixture in golden("thl_small.json.gz") + golden("thl_reference_tests.json.gz"):
+        flat = FlatDtl(fixture["input"])
+        min_cost, root, mapping, value, tag = _gpu_tables(ctx, flat)
+        assert flat.table_by_name(value, tag) == fixture["table"]
+        if fixture.get("error") == "KeyError":
+            # the reference crashes here (a root without an entry); the library skips such
+            # roots -- same answer as the oracle's non-strict mode
+            ref = oracle.dtl(*flat.species_args, *flat.object_args, flat.costs, strict=False)
+            assert (min_cost, root) == (ref["min_cost"], ref["root_species"])
+            assert (mapping == ref["mapping"]).all()
+            continue
+        assert min_cost == fixture["min_cost"]
+        assert flat.mapping_by_name(mapping) == fixture["result"]["object_species"]
+
+
+def test_golden_results_through_entry_point(golden):
+    """reconcile_thl(...).to_dict() equals the reference's output JSON."""
+    for fixture in golden("thl_medium.json.gz") + golden("thl_small.json.gz")[:40]:
+        if fixture.get("error"):
+            continue
+        rec_input = ReconciliationInput.from_dict(fixture["input"])
+        (result,) = reconcile_thl(rec_input, RetentionPolicy.ANY)
+        assert result.to_dict() == fixture["result"]
+        assert list(result.to_dict()["object_species"]) == list(fixture["result"]["object_species"])
+        assert result.cost() == fixture["min_cost"]
+
+
+@pytest.mark.parametrize("n_s,n_o,costs", [
+    (8, 12, (0, 1, 1, 1, 1)),
+    (20, 33, (0, 1, 1, 1, 1)),
+    (20, 33, (0, 0, 0, 0, 0)),
+    (33, 40, (2, 3, 1, 2, 0)),
+    (64, 64, (0, 2, 3, 1, 1)),
+    (100, 150, (1, 1, 1, 1, 1)),
+])
+def test_random_batches_against_oracle(ctx, n_s, n_o, costs):
+    """Ragged-free batches of random trees: tables, min cost, root and mapping."""
+    batch = synth.make_batch(n_s, n_o, 6, seed=1000 + n_s, costs=costs)
+    ctx.set_species(batch.parent, batch.child0, batch.child1)
+    min_cost, root, mapping = ctx.dtl_run(batch.node_off, batch.left, batch.right,
+                                          batch.leaf_species, batch.costs, flags=_lib.SR2_KEEP_TABLES)
+    for b in range(batch.n_instances):
+        left, right, leaf = batch.instance(b)
+        ref = oracle.dtl(batch.parent, batch.child0, batch.child1, left, right, leaf, batch.costs,
+                         strict=False)
+        value, tag = ctx.dtl_tables(b, len(left))
+        assert (value == ref["value"]).all()
+        # the reference creates no tag for cells without an entry
+        assert (tag == ref["tag"]).all()
+        assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"]
+        lo, hi = batch.node_off[b], batch.node_off[b + 1]
+        assert (mapping[lo:hi] == ref["mapping"]).all()
+
+
+def test_ragged_batch_and_single_leaf(ctx):
+    """Instances of different sizes in one batch, including a one-node object tree."""
+    species = synth.make_batch(6, 6, 1, seed=5)
+    parts = [synth.make_batch(6, n, 1, seed=5) for n in (6, 9, 17)]
+    lefts = [p.left for p in parts] + [np.array([-1], np.int32)]
+    rights = [p.right for p in parts] + [np.array([-1], np.int32)]
+    leaves = [p.leaf_species for p in parts] + [np.array([3], np.int32)]
+    node_off = np.cumsum([0] + [len(x) for x in lefts]).astype(np.int64)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    min_cost, root, mapping = ctx.dtl_run(node_off, np.concatenate(lefts), np.concatenate(rights),
+                                          np.concatenate(leaves), species.costs)
+    for b in range(4):
+        ref = oracle.dtl(species.parent, species.child0, species.child1, lefts[b], rights[b], leaves[b],
+                         species.costs, strict=False, tables=False)
+        assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"]
+        assert (mapping[node_off[b]:node_off[b + 1]] == ref["mapping"]).all()
+    assert min_cost[3] == 0 and root[3] == 3
+
+
+def test_large_species_tree_uses_cta_per_row(ctx):
+    """|S| > 1024 switches to one CTA per row; checked against the oracle."""
+    batch = synth.make_batch(600, 610, 1, seed=77)
+    ctx.set_species(batch.parent, batch.child0, batch.child1)
+    min_cost, root, mapping = ctx.dtl_run(batch.node_off, batch.left, batch.right,
+                                          batch.leaf_species, batch.costs, flags=_lib.SR2_KEEP_TABLES)
+    ref = oracle.dtl(batch.parent, batch.child0, batch.child1, batch.left, batch.right,
+                     batch.leaf_species, batch.costs, strict=False)
+    value, tag = ctx.dtl_tables(0, len(batch.left))
+    assert (value == ref["value"]).all() and (tag == ref["tag"]).all()
+    assert min_cost[0] == ref["min_cost"] and (mapping == ref["mapping"]).all()
+
+
+def test_full_size_single_instance_properties(ctx):
+    """BASELINE config #3 (5,000-leaf object tree x 2,000-leaf species tree): too large for
+    the O(G S^2) oracle, so check size-independent properties: the host-side cost() of the
+    returned mapping equals the reported minimum, every leaf sits at its species, and the
+    result is reproducible."""
+    batch = synth.make_batch(2000, 5000, 1, seed=3000)
+    ctx.set_species(batch.parent, batch.child0, batch.child1)
+    args = (batch.node_off, batch.left, batch.right, batch.leaf_species, batch.costs)
+    min_cost, root, mapping = ctx.dtl_run(*args)
+    assert 0 < min_cost[0] < INF
+    leaf = batch.left < 0
+    assert (mapping[leaf] == batch.leaf_species[leaf]).all()
+    from tests.helpers import flat_cost
+    assert flat_cost(batch, 0, mapping) == min_cost[0]
+    again = ctx.dtl_run(*args)
+    assert again[0][0] == min_cost[0] and (again[2] == mapping).all()
+
+
+def test_batch_entry_point_matches_single(golden):
+    fixture = golden("thl_medium.json.gz")[0]
+    rec_input = ReconciliationInput.from_dict(fixture["input"])
+    outs = reconcile_thl_batch([rec_input, rec_input], RetentionPolicy.ANY)
+    for out in outs:
+        (result,) = out
+        assert result.to_dict() == fixture["result"]
+
+
+def test_bad_input_is_rejected(ctx):
+    batch = synth.make_batch(4, 5, 1, seed=1)
+    ctx.set_species(batch.parent, batch.child0, batch.child1)
+    left = batch.left.copy()
+    left[0] = 0  # a node cannot be its own child
+    with pytest.raises(_lib.Sr2Error):
+        ctx.dtl_run(batch.node_off, left, batch.right, batch.leaf_species, batch.costs)
+    with pytest.raises(_lib.Sr2Error):
+        ctx.dtl_run(batch.node_off, batch.left, batch.right, batch.leaf_species,
+                    np.array([0, -1, 1, 1, 1], np.int32))
