@@ -73,3 +73,30 @@ def dtl_batch(parent, child0, child1, node_off, left, right, leaf_species, costs
     if rc:
         raise RuntimeError(f"oracle_dtl_batch failed with {rc}")
     return min_cost, root, mapping
+
+
+def superdtl(parent, child0, child1, left, right, leaf_species, leaf_bits, costs, tables=True):
+    """One binary resolution.  leaf_bits: uint32 [G, W].  Returns a dict with gain/lca sets,
+    value[G,S,2], tag[G,S,2,4], min_cost, root_species, mapping, kind, syn[G,W]."""
+    lib = load()
+    parent, child0, child1 = _a32(parent), _a32(child0), _a32(child1)
+    left, right, leaf_species, costs = _a32(left), _a32(right), _a32(leaf_species), _a32(costs)
+    leaf_bits = np.ascontiguousarray(leaf_bits, dtype=np.uint32)
+    S, G, W = len(parent), len(left), leaf_bits.shape[1]
+    gain = np.zeros((G, W), np.uint32)
+    lca = np.zeros((G, W), np.uint32)
+    value = np.empty((G, S, 2), np.int32) if tables else None
+    tag = np.empty((G, S, 2, 4), np.int32) if tables else None
+    min_cost, root = c_int32(0), c_int32(0)
+    mapping = np.full(G, -1, np.int32)
+    kind = np.full(G, -1, np.int32)
+    syn = np.zeros((G, W), np.uint32)
+    u32 = POINTER(ctypes.c_uint32)
+    lib.oracle_superdtl.restype = c_int
+    rc = lib.oracle_superdtl(
+        c_int(S), _p(parent), _p(child0), _p(child1), c_int(G), _p(left), _p(right), _p(leaf_species),
+        c_int(W), leaf_bits.ctypes.data_as(u32), _p(costs), gain.ctypes.data_as(u32),
+        lca.ctypes.data_as(u32), _p(value), _p(tag), ctypes.byref(min_cost), ctypes.byref(root),
+        _p(mapping), _p(kind), syn.ctypes.data_as(u32))
+    return dict(rc=rc, gain=gain, lca=lca, value=value, tag=tag, min_cost=min_cost.value,
+                root_species=root.value, mapping=mapping, kind=kind, syn=syn)

@@ -325,3 +325,276 @@ int oracle_dtl_batch(int S, const int* parent, const int* c0, const int* c1, int
     }
     return rc_all;
 }
+
+/* =================================================================================
+ * superdtl = usreconcile_extended_uspfs,
+ * /root/reference/src/superrec2/compute/unordered_super_reconciliation.py:85-542
+ * One call = one binary resolution.  Syntenies are bitsets of W 32-bit words; bit i
+ * is the i-th family in sort_synteny order (model/synteny.py:21-33).
+ * ================================================================================= */
+enum { K_LCA = 0, K_INH = 1 };
+enum { M_LEFT, M_RIGHT, M_CONSERVED, M_SEGMENT, M_SEPARATE, M_COUNT }; /* MappingChoices :62-79 */
+
+static int bits_subset(const uint32_t* a, const uint32_t* b, int W) { /* a <= b */
+    for (int w = 0; w < W; ++w)
+        if (a[w] & ~b[w]) return 0;
+    return 1;
+}
+
+/* two-candidate update: (value, (species, kind)) */
+static void upd2(entry_t* e, int v_lca, int v_inh, int s) {
+    entry_update(e, v_lca, s, K_LCA);
+    entry_update(e, v_inh, s, K_INH);
+}
+
+typedef struct {
+    int value, has_tag;
+    int sl, kl, sr, kr;
+} cell_t;
+
+static void cell_offer(cell_t* c, int value, const entry_t* l, const entry_t* r) {
+    /* Entry.update (ANY) on a cell whose tag is a ChildrenAssignment */
+    if (value > INF) value = INF;
+    if (c->value == value) {
+        if (!c->has_tag) {
+            c->has_tag = 1;
+            c->sl = l->a, c->kl = l->b, c->sr = r->a, c->kr = r->b;
+        }
+    }
+    if (c->value > value) {
+        c->has_tag = 1;
+        c->sl = l->a, c->kl = l->b, c->sr = r->a, c->kr = r->b;
+        c->value = value;
+    }
+}
+
+/* out_gain/out_lca: [G*W]; out_value: [G*S*2]; out_tag: [G*S*2*4] = (sl,kl,sr,kr) or -1;
+ * out_map/out_kind: [G]; out_syn: [G*W] (decoded, i.e. possibly polluted, syntenies). */
+int oracle_superdtl(int S, const int* parent, const int* c0, const int* c1, int G, const int* left,
+                    const int* right, const int* leaf_species, int W, const uint32_t* leaf_bits,
+                    const int* costs, uint32_t* out_gain, uint32_t* out_lca, int* out_value, int* out_tag,
+                    int* out_min_cost, int* out_root_species, int* out_map, int* out_kind,
+                    uint32_t* out_syn) {
+    species_t sp;
+    if (species_init(&sp, S, parent, c0, c1)) return -1;
+    const int spe = costs[0], dup = costs[1], hgt = costs[2], floss = costs[3], sloss = costs[4];
+
+    /* object-tree parents and depths (for the object LCA of _compute_gain_sets :96) */
+    int* opar = (int*)malloc(sizeof(int) * G);
+    int* odep = (int*)malloc(sizeof(int) * G);
+    uint32_t* gain = (uint32_t*)calloc((size_t)G * W, sizeof(uint32_t));
+    uint32_t* L = (uint32_t*)calloc((size_t)G * W, sizeof(uint32_t));
+    cell_t* T = (cell_t*)malloc(sizeof(cell_t) * (size_t)G * S * 2);
+    if (!opar || !odep || !gain || !L || !T) return -1;
+    opar[0] = -1;
+    odep[0] = 0;
+    for (int u = 0; u < G; ++u)
+        if (left[u] >= 0) {
+            opar[left[u]] = opar[right[u]] = u;
+            odep[left[u]] = odep[right[u]] = odep[u] + 1;
+        }
+    /* _compute_gain_sets (:85-109): each family is gained at the LCA of the leaves carrying it */
+    for (int f = 0; f < W * 32; ++f) {
+        int node = -1;
+        for (int u = 0; u < G; ++u) {
+            if (left[u] >= 0 || !(leaf_bits[(size_t)u * W + f / 32] >> (f % 32) & 1)) continue;
+            if (node < 0) {
+                node = u;
+                continue;
+            }
+            int a = node, b = u;
+            while (a != b) {
+                if (odep[a] >= odep[b])
+                    a = opar[a];
+                else
+                    b = opar[b];
+            }
+            node = a;
+        }
+        if (node >= 0) gain[(size_t)node * W + f / 32] |= 1u << (f % 32);
+    }
+    /* _compute_lca_sets (:112-136), postorder = descending index */
+    for (int u = G - 1; u >= 0; --u) {
+        for (int w = 0; w < W; ++w) {
+            if (left[u] < 0)
+                L[(size_t)u * W + w] = leaf_bits[(size_t)u * W + w];
+            else
+                L[(size_t)u * W + w] = (L[(size_t)left[u] * W + w] | L[(size_t)right[u] * W + w]) &
+                                       ~(gain[(size_t)left[u] * W + w] | gain[(size_t)right[u] * W + w]);
+        }
+    }
+    if (out_gain) memcpy(out_gain, gain, sizeof(uint32_t) * (size_t)G * W);
+    if (out_lca) memcpy(out_lca, L, sizeof(uint32_t) * (size_t)G * W);
+
+    /* _compute_uspfs_table (:300-358) */
+    for (size_t i = 0; i < (size_t)G * S * 2; ++i) {
+        T[i].value = INF;
+        T[i].has_tag = 0;
+        T[i].sl = T[i].kl = T[i].sr = T[i].kr = -1;
+    }
+#define CELL(u, x, k) T[((size_t)(u) * S + (x)) * 2 + (k)]
+    for (int u = G - 1; u >= 0; --u) {
+        if (left[u] < 0) {
+            CELL(u, leaf_species[u], K_LCA).value = 0; /* Candidate(0): value only */
+            continue;
+        }
+        for (int x = 0; x < S; ++x) {
+            /* _compute_uspfs_entry (:147-297) */
+            entry_t sub[2][2][M_COUNT];
+            for (int i = 0; i < 2; ++i)
+                for (int k = 0; k < 2; ++k)
+                    for (int m = 0; m < M_COUNT; ++m) entry_init(&sub[i][k][m]);
+            for (int i = 0; i < 2; ++i) {
+                int child = i == 0 ? left[u] : right[u];
+                int lca_lca_dist, lca_inh_dist;
+                if (bits_subset(L + (size_t)u * W, L + (size_t)child * W, W)) {
+                    lca_lca_dist = 0;
+                    lca_inh_dist = INF;
+                } else {
+                    lca_lca_dist = sloss;
+                    lca_inh_dist = 0;
+                }
+                for (int s = 0; s < S; ++s) { /* level order */
+                    int lca_cost = CELL(child, s, K_LCA).value;
+                    int inh_cost = CELL(child, s, K_INH).value;
+                    if (anc(&sp, x, s)) {
+                        int above = dist(&sp, x, s) * floss;
+                        upd2(&sub[i][K_INH][M_CONSERVED], sat_add(sat_add(above, lca_cost), sloss),
+                             sat_add(above, inh_cost), s);
+                        upd2(&sub[i][K_LCA][M_CONSERVED], sat_add(sat_add(above, lca_cost), lca_lca_dist),
+                             sat_add(sat_add(above, inh_cost), lca_inh_dist), s);
+                        upd2(&sub[i][K_INH][M_SEGMENT], sat_add(above, lca_cost), sat_add(above, inh_cost), s);
+                        upd2(&sub[i][K_LCA][M_SEGMENT], sat_add(above, lca_cost),
+                             sat_add(sat_add(above, inh_cost), lca_inh_dist), s);
+                        if (c0[x] >= 0) {
+                            int sd = above - floss;
+                            int which = anc(&sp, c0[x], s) ? M_LEFT : (anc(&sp, c1[x], s) ? M_RIGHT : -1);
+                            if (which >= 0) {
+                                upd2(&sub[i][K_INH][which], sat_add(sat_add(sd, lca_cost), sloss),
+                                     sat_add(sd, inh_cost), s);
+                                upd2(&sub[i][K_LCA][which], sat_add(sat_add(sd, lca_cost), lca_lca_dist),
+                                     sat_add(sat_add(sd, inh_cost), lca_inh_dist), s);
+                            }
+                        }
+                    } else if (!anc(&sp, s, x)) {
+                        upd2(&sub[i][K_INH][M_SEPARATE], lca_cost, inh_cost, s);
+                        upd2(&sub[i][K_LCA][M_SEPARATE], lca_cost, sat_add(inh_cost, lca_inh_dist), s);
+                    }
+                }
+            }
+            for (int k = 0; k < 2; ++k) { /* :289-297 */
+                static const int pair[6][2] = {{M_LEFT, M_RIGHT},       {M_RIGHT, M_LEFT},
+                                               {M_CONSERVED, M_SEGMENT}, {M_SEGMENT, M_CONSERVED},
+                                               {M_CONSERVED, M_SEPARATE}, {M_SEPARATE, M_CONSERVED}};
+                const int ev[6] = {spe, spe, dup, dup, hgt, hgt};
+                int val[6], n = 0, any = 0;
+                const entry_t *el[6], *er[6];
+                for (int c = 0; c < 6; ++c) {
+                    const entry_t* a = &sub[0][k][pair[c][0]];
+                    const entry_t* b = &sub[1][k][pair[c][1]];
+                    if (!a->has_tag || !b->has_tag) continue; /* combine() of an empty entry */
+                    val[n] = sat_add(ev[c], sat_add(a->value, b->value));
+                    el[n] = a, er[n] = b;
+                    if (val[n] < INF) any = 1;
+                    ++n;
+                }
+                if (any) /* EntryProxy.update */
+                    for (int c = 0; c < n; ++c) cell_offer(&CELL(u, x, k), val[c], el[c], er[c]);
+            }
+        }
+    }
+    if (out_value || out_tag)
+        for (size_t i = 0; i < (size_t)G * S * 2; ++i) {
+            if (out_value) out_value[i] = T[i].value;
+            if (out_tag) {
+                out_tag[4 * i + 0] = T[i].has_tag ? T[i].sl : -1;
+                out_tag[4 * i + 1] = T[i].has_tag ? T[i].kl : -1;
+                out_tag[4 * i + 2] = T[i].has_tag ? T[i].sr : -1;
+                out_tag[4 * i + 3] = T[i].has_tag ? T[i].kr : -1;
+            }
+        }
+
+    /* _uspfs (:474-497) + _decode_uspfs_table (:361-446): decode every root species in level
+     * order with kind LCA; L is LIVE -- INHERIT nodes union their gain set into the set of
+     * their nearest LCA-kind ancestor IN PLACE (:386-391), and that persists across roots. */
+    int* map = (int*)malloc(sizeof(int) * G);
+    int* kind = (int*)malloc(sizeof(int) * G);
+    int* ancref = (int*)malloc(sizeof(int) * G);
+    int* stack = (int*)malloc(sizeof(int) * (G + 1));
+    uint32_t* syn = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)G * W);
+    entry_t results;
+    entry_init(&results);
+    int rc = 0;
+    for (int x = 0; x < S; ++x) {
+        const cell_t* root = &CELL(0, x, K_LCA);
+        if (left[0] >= 0 ? !root->has_tag : root->value >= INF) continue; /* yields nothing */
+        map[0] = x;
+        kind[0] = K_LCA;
+        ancref[0] = 0;
+        int top = 0, ok = 1;
+        stack[top++] = 0;
+        while (top) {
+            int n = stack[--top];
+            if (kind[n] == K_LCA) {
+                ancref[n] = n;
+            } else {
+                for (int w = 0; w < W; ++w) L[(size_t)ancref[n] * W + w] |= gain[(size_t)n * W + w];
+            }
+            memcpy(syn + (size_t)n * W, L + (size_t)ancref[n] * W, sizeof(uint32_t) * W);
+            if (left[n] < 0) {
+                if (CELL(n, map[n], kind[n]).value >= INF) ok = 0;
+                continue;
+            }
+            const cell_t* c = &CELL(n, map[n], kind[n]);
+            if (!c->has_tag) {
+                ok = 0;
+                continue;
+            }
+            map[left[n]] = c->sl, kind[left[n]] = c->kl, ancref[left[n]] = ancref[n];
+            map[right[n]] = c->sr, kind[right[n]] = c->kr, ancref[right[n]] = ancref[n];
+            stack[top++] = right[n];
+            stack[top++] = left[n];
+        }
+        if (!ok) { /* cannot happen from a root that has an entry */
+            rc = -2;
+            break;
+        }
+        /* SuperReconciliationOutput.cost() (model/reconciliation.py:511-554) */
+        int c = rec_cost(&sp, G, left, right, leaf_species, map, costs);
+        if (c < INF) {
+            long long lab = 0;
+            for (int n = 0; n < G; ++n) {
+                if (left[n] < 0) continue;
+                int lc = bits_subset(syn + (size_t)n * W, syn + (size_t)left[n] * W, W) ? 0 : sloss;
+                int rcst = bits_subset(syn + (size_t)n * W, syn + (size_t)right[n] * W, W) ? 0 : sloss;
+                int ev = node_event(&sp, map[n], map[left[n]], map[right[n]]);
+                if (ev == EV_SPE)
+                    lab += lc + rcst;
+                else if (ev == EV_DUP)
+                    lab += lc < rcst ? lc : rcst;
+                else
+                    lab += (anc(&sp, map[n], map[left[n]]) || anc(&sp, map[left[n]], map[n])) ? lc : rcst;
+            }
+            c = (c + lab >= INF) ? INF : (int)(c + lab);
+        }
+        int before_tag = results.has_tag, before_val = results.value;
+        entry_update(&results, c, x, -1);
+        if (results.has_tag && (!before_tag || results.value < before_val)) {
+            if (out_map) memcpy(out_map, map, sizeof(int) * G);
+            if (out_kind) memcpy(out_kind, kind, sizeof(int) * G);
+            if (out_syn) memcpy(out_syn, syn, sizeof(uint32_t) * (size_t)G * W);
+        }
+    }
+#undef CELL
+    if (results.has_tag) {
+        *out_min_cost = results.value;
+        *out_root_species = results.a;
+    } else {
+        *out_min_cost = INF;
+        *out_root_species = -1;
+    }
+    free(map), free(kind), free(ancref), free(stack), free(syn);
+    free(opar), free(odep), free(gain), free(L), free(T);
+    species_free(&sp);
+    return rc;
+}

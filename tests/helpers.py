@@ -90,3 +90,74 @@ def flat_cost(batch, b, mapping):
                      np.where(both, dup + floss * (da + db),
                               np.where(pa, hgt + floss * da, hgt + floss * db)))
     return int(total.sum())
+
+
+KINDS = ("LCA", "INHERIT")
+
+
+class FlatSuper:
+    """One BINARY super-reconciliation input (already labelled) as flat arrays."""
+
+    def __init__(self, srec_input):
+        from superrec2_b200.compute.unordered_super_reconciliation import family_index, leaf_bitsets
+        self.srec_input = srec_input
+        self.species = flatten_species(srec_input.species_lca.tree)
+        self.objects = flatten_objects(
+            srec_input.object_tree, srec_input.leaf_object_species, self.species.rank)
+        self.costs = cost_vector(srec_input.costs)
+        self.families = family_index(srec_input.leaf_syntenies)
+        self.leaf_bits = leaf_bitsets(self.objects.nodes, srec_input.leaf_syntenies, self.families)
+
+    @classmethod
+    def from_dict(cls, data):
+        srec_input = SuperReconciliationInput.from_dict(data)
+        (binary,) = list(srec_input.binarize())
+        binary.label_internal()
+        return cls(binary)
+
+    @property
+    def species_args(self):
+        return self.species.parent, self.species.child0, self.species.child1
+
+    @property
+    def object_args(self):
+        return self.objects.left, self.objects.right, self.objects.leaf_species
+
+    def bits_to_names(self, bits):
+        names = list(self.families)
+        return [names[f] for f in range(len(names)) if bits[f // 32] >> (f % 32) & 1]
+
+    def sets_by_name(self, bitsets):
+        return {node.name: sorted(self.bits_to_names(bitsets[u]))
+                for u, node in enumerate(self.objects.nodes)}
+
+    def table_by_name(self, value, tag):
+        out = {}
+        sp = self.species.nodes
+        for u, node in enumerate(self.objects.nodes):
+            row = {}
+            for x in range(len(sp)):
+                cell = {}
+                for k, kname in enumerate(KINDS):
+                    v = int(value[u, x, k])
+                    t = tag[u, x, k]
+                    has_tag = t[0] >= 0
+                    if v < INF or has_tag:
+                        names = ([[sp[t[0]].name, KINDS[t[1]]], [sp[t[2]].name, KINDS[t[3]]]]
+                                 if has_tag else None)
+                        cell[kname] = [None if v >= INF else v, names]
+                if cell:
+                    row[sp[x].name] = cell
+            out[node.name] = row
+        return out
+
+    def result_dict(self, mapping, syn):
+        """The reference's output JSON for this (labelled) input."""
+        from superrec2_b200.model.reconciliation import SuperReconciliationOutput
+        nodes = self.objects.nodes
+        output = SuperReconciliationOutput(
+            input=self.srec_input,
+            object_species={node: self.species.nodes[int(mapping[u])] for u, node in enumerate(nodes)},
+            syntenies={node: self.bits_to_names(syn[u]) for u, node in enumerate(nodes)},
+            ordered=False)
+        return output.to_dict()
