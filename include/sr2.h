@@ -106,6 +106,52 @@ int sr2_dtl_run(sr2_ctx* ctx, int32_t n_instances, const int64_t* node_off,
  * left/right child (MappingInfo, reconciliation.py:47-54), -1 if absent. */
 int sr2_dtl_tables(sr2_ctx* ctx, int32_t instance, int32_t* out_value, int32_t* out_tag);
 
+/* ---- superdtl (usreconcile_extended_uspfs) -----------------------------------
+ * One instance = one BINARY object tree with leaf syntenies (a batch of independent
+ * super-reconciliations, or the enumerated resolutions of one multifurcating tree).
+ * Syntenies are bitsets of n_words 32-bit words per node: bit i = the i-th gene
+ * family of the problem in sort_synteny order
+ * (/root/reference/src/superrec2/model/synteny.py:21-33); leaf_bits[(node)*n_words + w],
+ * rows of internal nodes are ignored.
+ *
+ * Per instance the device computes the gain and LCA sets (:85-136), fills the
+ * (object, species, kind) table (:147-358), decodes the solution from every root
+ * species in level order reproducing the reference's in-place synteny unions
+ * (:361-446, SURVEY.md Hazard A), evaluates SuperReconciliationOutput.cost()
+ * (model/reconciliation.py:511-554) on each decode and keeps the first strict
+ * minimum (:474-495).
+ *
+ * index_base: global number of instance 0 (the resolution index when the batch is a
+ * shard of an enumeration); sr2_superdtl_best returns the lexicographic minimum of
+ * (cost, index_base + instance, root species) over the batch -- the reference's
+ * running minimum over resolutions (:454) -- and its packed 64-bit key
+ * (cost << 40 | instance << 16 | root) for a cross-GPU min-reduce.
+ *
+ * out_map_kind[node]: 0 = LCA synteny, 1 = INHERIT (SyntenyAssignment, :37-45).
+ * out_synteny_bits[node*n_words + w]: the synteny the reference reports for the node.
+ */
+int sr2_superdtl_upload(sr2_ctx* ctx, int32_t n_instances, const int64_t* node_off,
+                        const int32_t* left, const int32_t* right, const int32_t* leaf_species,
+                        int32_t n_words, const uint32_t* leaf_bits, const int32_t costs[5],
+                        int64_t index_base, uint32_t flags);
+int sr2_superdtl_solve(sr2_ctx* ctx);
+int sr2_superdtl_results(sr2_ctx* ctx, int32_t* out_min_cost, int32_t* out_root_species,
+                         int32_t* out_map_species, int32_t* out_map_kind, uint32_t* out_synteny_bits);
+int sr2_superdtl_best(sr2_ctx* ctx, int32_t* out_min_cost, int64_t* out_instance,
+                      int32_t* out_root_species, uint64_t* out_key);
+int sr2_superdtl_result_one(sr2_ctx* ctx, int32_t instance, int32_t* out_map_species,
+                            int32_t* out_map_kind, uint32_t* out_synteny_bits);
+int sr2_superdtl_run(sr2_ctx* ctx, int32_t n_instances, const int64_t* node_off,
+                     const int32_t* left, const int32_t* right, const int32_t* leaf_species,
+                     int32_t n_words, const uint32_t* leaf_bits, const int32_t costs[5], uint32_t flags,
+                     int32_t* out_min_cost, int32_t* out_root_species, int32_t* out_map_species,
+                     int32_t* out_map_kind, uint32_t* out_synteny_bits);
+/* Test hook (needs SR2_KEEP_TABLES).  out_value[(u*S + x)*2 + kind];
+ * out_tag[((u*S + x)*2 + kind)*4 + {0..3}] = (left species, left kind, right species,
+ * right kind) = ChildrenAssignment (:55-59), -1 if absent; out_gain/out_lca[u*n_words + w]. */
+int sr2_superdtl_tables(sr2_ctx* ctx, int32_t instance, int32_t* out_value, int32_t* out_tag,
+                        uint32_t* out_gain, uint32_t* out_lca);
+
 /* ---- timing of the last solve (CUDA events on the context's stream) ------ */
 typedef struct sr2_timing {
     float upload_ms;     /* host prep + H2D of the last upload */

@@ -8,7 +8,8 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+from ctypes import (POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64,
+                    c_void_p)
 
 import numpy as np
 
@@ -41,6 +42,7 @@ class Timing(ctypes.Structure):
 
 _I32P = POINTER(c_int32)
 _I64P = POINTER(c_int64)
+_U32P = POINTER(c_uint32)
 
 #: every symbol declared in include/sr2.h: name -> (restype, argtypes)
 SIGNATURES = {
@@ -57,6 +59,15 @@ SIGNATURES = {
     "sr2_dtl_run": (c_int, [c_void_p, c_int32, _I64P, _I32P, _I32P, _I32P, _I32P, c_uint32,
                             _I32P, _I32P, _I32P]),
     "sr2_dtl_tables": (c_int, [c_void_p, c_int32, _I32P, _I32P]),
+    "sr2_superdtl_upload": (c_int, [c_void_p, c_int32, _I64P, _I32P, _I32P, _I32P, c_int32, _U32P, _I32P,
+                                    c_int64, c_uint32]),
+    "sr2_superdtl_solve": (c_int, [c_void_p]),
+    "sr2_superdtl_results": (c_int, [c_void_p, _I32P, _I32P, _I32P, _I32P, _U32P]),
+    "sr2_superdtl_best": (c_int, [c_void_p, _I32P, _I64P, _I32P, POINTER(c_uint64)]),
+    "sr2_superdtl_result_one": (c_int, [c_void_p, c_int32, _I32P, _I32P, _U32P]),
+    "sr2_superdtl_run": (c_int, [c_void_p, c_int32, _I64P, _I32P, _I32P, _I32P, c_int32, _U32P, _I32P,
+                                 c_uint32, _I32P, _I32P, _I32P, _I32P, _U32P]),
+    "sr2_superdtl_tables": (c_int, [c_void_p, c_int32, _I32P, _I32P, _U32P, _U32P]),
     "sr2_last_timing": (c_int, [c_void_p, POINTER(Timing)]),
 }
 
@@ -182,6 +193,65 @@ class Context:
         tags = np.empty((n_nodes, self.n_species, 2), np.int32)
         self._check(self._lib.sr2_dtl_tables(self._handle, instance, p32(values), p32(tags)))
         return values, tags
+
+    # ------------------------------------------------------------- superdtl
+    def superdtl_upload(self, node_off, left, right, leaf_species, leaf_bits, costs,
+                        index_base=0, flags=0):
+        node_off, left, right = i64(node_off), i32(left), i32(right)
+        leaf_species, costs = i32(leaf_species), i32(costs)
+        leaf_bits = np.ascontiguousarray(leaf_bits, dtype=np.uint32).reshape(len(left), -1)
+        self._sbatch = (len(node_off) - 1, int(node_off[-1]), leaf_bits.shape[1], node_off.copy())
+        self._check(self._lib.sr2_superdtl_upload(
+            self._handle, len(node_off) - 1, p64(node_off), p32(left), p32(right), p32(leaf_species),
+            leaf_bits.shape[1], leaf_bits.ctypes.data_as(_U32P), p32(costs), index_base, flags))
+
+    def superdtl_solve(self):
+        self._check(self._lib.sr2_superdtl_solve(self._handle))
+
+    def superdtl_results(self):
+        n_inst, n_nodes, words, _ = self._sbatch
+        min_cost = np.empty(n_inst, np.int32)
+        root = np.empty(n_inst, np.int32)
+        mapping = np.empty(n_nodes, np.int32)
+        kind = np.empty(n_nodes, np.int32)
+        syn = np.empty((n_nodes, words), np.uint32)
+        self._check(self._lib.sr2_superdtl_results(
+            self._handle, p32(min_cost), p32(root), p32(mapping), p32(kind), syn.ctypes.data_as(_U32P)))
+        return min_cost, root, mapping, kind, syn
+
+    def superdtl_best(self):
+        """(min cost, global instance number, root species, packed key) of the batch."""
+        cost, inst, root, key = c_int32(0), c_int64(0), c_int32(0), c_uint64(0)
+        self._check(self._lib.sr2_superdtl_best(
+            self._handle, ctypes.byref(cost), ctypes.byref(inst), ctypes.byref(root), ctypes.byref(key)))
+        return cost.value, inst.value, root.value, key.value
+
+    def superdtl_result_one(self, instance: int):
+        _, _, words, node_off = self._sbatch
+        n_nodes = int(node_off[instance + 1] - node_off[instance])
+        mapping = np.empty(n_nodes, np.int32)
+        kind = np.empty(n_nodes, np.int32)
+        syn = np.empty((n_nodes, words), np.uint32)
+        self._check(self._lib.sr2_superdtl_result_one(
+            self._handle, instance, p32(mapping), p32(kind), syn.ctypes.data_as(_U32P)))
+        return mapping, kind, syn
+
+    def superdtl_run(self, node_off, left, right, leaf_species, leaf_bits, costs, flags=0):
+        self.superdtl_upload(node_off, left, right, leaf_species, leaf_bits, costs, 0, flags)
+        self.superdtl_solve()
+        return self.superdtl_results()
+
+    def superdtl_tables(self, instance: int):
+        _, _, words, node_off = self._sbatch
+        n_nodes = int(node_off[instance + 1] - node_off[instance])
+        values = np.empty((n_nodes, self.n_species, 2), np.int32)
+        tags = np.empty((n_nodes, self.n_species, 2, 4), np.int32)
+        gain = np.empty((n_nodes, words), np.uint32)
+        lca = np.empty((n_nodes, words), np.uint32)
+        self._check(self._lib.sr2_superdtl_tables(
+            self._handle, instance, p32(values), p32(tags), gain.ctypes.data_as(_U32P),
+            lca.ctypes.data_as(_U32P)))
+        return values, tags, gain, lca
 
     def timing(self) -> Timing:
         out = Timing()

@@ -39,3 +39,128 @@ def leaf_bitsets(nodes: List, leaf_syntenies, families: Dict[str, int]) -> np.nd
 
 def bits_to_families(bits: Iterable[int], names: List[str]) -> List[str]:
     return [names[f] for f in range(len(names)) if int(bits[f // 32]) >> (f % 32) & 1]
+
+
+# ---------------------------------------------------------------------------
+# entry point
+# ---------------------------------------------------------------------------
+from typing import Set  # noqa: E402
+
+from .. import _lib  # noqa: E402
+from ..model.reconciliation import (  # noqa: E402
+    SuperReconciliationInput,
+    SuperReconciliationOutput,
+)
+from ..utils.dynamic_programming import RetentionPolicy  # noqa: E402
+from .flatten import flatten_objects, flatten_species  # noqa: E402
+from .reconciliation import cost_vector  # noqa: E402
+
+#: resolutions flattened and sent to the device per batch by the Python driver
+RESOLUTION_BATCH = 4096
+
+
+def flatten_super(srec_input: SuperReconciliationInput, species=None, families=None):
+    """(species layout, object layout, family index, leaf bitsets) of one BINARY input."""
+    if species is None:
+        species = flatten_species(srec_input.species_lca.tree)
+    objects = flatten_objects(srec_input.object_tree, srec_input.leaf_object_species, species.rank)
+    if families is None:
+        families = family_index(srec_input.leaf_syntenies)
+    bits = leaf_bitsets(objects.nodes, srec_input.leaf_syntenies, families)
+    return species, objects, families, bits
+
+
+def usreconcile_extended_uspfs(
+    srec_input: SuperReconciliationInput,
+    policy: RetentionPolicy,
+) -> Set[SuperReconciliationOutput]:
+    """
+    Compute a minimum-cost unordered super-reconciliation using the
+    SuperDTL algorithm on an NVIDIA B200 GPU.  This is an extension of the
+    Unordered Small-Phylogeny-for-Syntenies (EUSPFS) algorithm that can handle
+    all kinds of events (including transfers) and non-negative integer cost
+    values.  Multifurcations of the object tree are resolved by trying every
+    binary resolution; the solution returned is the one the reference
+    implementation returns (same tie-breaking, same synteny labelling).
+
+    :param srec_input: objects of the super-reconciliation
+    :param policy: ``RetentionPolicy.ANY`` (one solution)
+    :returns: any minimum-cost super-reconciliation, if there is one
+    """
+    return usreconcile_extended_uspfs_sharded(srec_input, policy)
+
+
+def usreconcile_extended_uspfs_sharded(
+    srec_input: SuperReconciliationInput,
+    policy: RetentionPolicy = RetentionPolicy.ANY,
+    device: int = 0,
+    shard: int = 0,
+    n_shards: int = 1,
+    reduce_key=None,
+) -> Set[SuperReconciliationOutput]:
+    """
+    ``usreconcile_extended_uspfs`` over the resolutions ``shard::n_shards`` ... in
+    contiguous blocks: shard ``i`` of ``n`` handles resolution numbers
+    ``[i*R/n, (i+1)*R/n)``.  ``reduce_key(key) -> key`` is the cross-shard
+    min-reduce of the packed ``(cost, resolution, root)`` key (an NCCL all-reduce
+    in ``superrec2_b200.dist``); the shard that owns the winning resolution
+    returns the solution, the others return an empty set.
+    """
+    if policy is not RetentionPolicy.ANY:
+        raise NotImplementedError(
+            "only RetentionPolicy.ANY is implemented on the GPU path so far "
+            "(SURVEY.md section 8f item 1)")
+    total = srec_input.count_resolutions()
+    lo, hi = total * shard // n_shards, total * (shard + 1) // n_shards
+    costs = cost_vector(srec_input.costs)
+    ctx = _lib.default_context(device)
+    families = family_index(srec_input.leaf_syntenies)
+    names = list(families)
+    n_species_res = 1
+    from ..utils.trees import count_resolutions
+    n_species_res = count_resolutions(srec_input.species_lca.tree)
+
+    best_key = (1 << 64) - 1
+    best = None   # (key, resolution index, mapping, kind, syn)
+    start = lo
+    while start < hi:
+        # resolutions are object-major: a run with one species resolution shares the species tree
+        stop = min(hi, start + RESOLUTION_BATCH, (start // n_species_res + 1) * n_species_res
+                   if n_species_res > 1 else hi)
+        if n_species_res > 1:
+            stop = start + 1  # species polytomies: one (object, species) pair per batch
+        inputs = [srec_input.resolution(index) for index in range(start, stop)]
+        species = flatten_species(inputs[0].species_lca.tree)
+        layouts = []
+        for item in inputs:
+            rank = species.rank if item.species_lca is inputs[0].species_lca else \
+                flatten_species(item.species_lca.tree).rank
+            objects = flatten_objects(item.object_tree, item.leaf_object_species, rank)
+            layouts.append((objects, leaf_bitsets(objects.nodes, item.leaf_syntenies, families)))
+        node_off = np.zeros(len(layouts) + 1, np.int64)
+        np.cumsum([len(objects.nodes) for objects, _ in layouts], out=node_off[1:])
+        ctx.set_species(species.parent, species.child0, species.child1)
+        ctx.superdtl_upload(
+            node_off,
+            np.concatenate([objects.left for objects, _ in layouts]),
+            np.concatenate([objects.right for objects, _ in layouts]),
+            np.concatenate([objects.leaf_species for objects, _ in layouts]),
+            np.concatenate([bits for _, bits in layouts]),
+            costs, index_base=start)
+        ctx.superdtl_solve()
+        cost, index, root, key = ctx.superdtl_best()
+        if index >= 0 and key < best_key:
+            best_key = key
+            mapping, kind, syn = ctx.superdtl_result_one(index - start)
+            best = (key, index, inputs[index - start], layouts[index - start][0], species, mapping, syn)
+        start = stop
+
+    global_key = reduce_key(best_key) if reduce_key is not None else best_key
+    if best is None or global_key != best_key:
+        return set()
+    _, index, winner, objects, species, mapping, syn = best
+    winner.label_internal()
+    object_species = {node: species.nodes[int(mapping[u])] for u, node in enumerate(objects.nodes)}
+    syntenies = {node: bits_to_families(syn[u], names) for u, node in enumerate(objects.nodes)}
+    return {SuperReconciliationOutput(
+        input=winner, object_species=object_species, syntenies=syntenies, ordered=False)}

@@ -24,41 +24,23 @@
 #include <cstring>
 #include <omp.h>
 
-#include "sr2_internal.cuh"
+#include "sr2_rows.cuh"
 
 // ---------------------------------------------------------------------------
 // device-resident problem
 // ---------------------------------------------------------------------------
-struct DtlChunk {
-    int32_t inst_begin = 0, inst_end = 0;
-    int64_t row_begin = 0, row_end = 0;   // global row range of the chunk
-    std::vector<int64_t> wave_off;        // [H+1] global row offsets per height (1-based waves)
-};
-
 struct DtlProblem {
-    int32_t B = 0;
-    int64_t N = 0, R = 0;
+    RowLayout rows;
     uint32_t flags = 0;
     int32_t costs[5] = {0, 0, 0, 0, 0};
     bool need_decoded_cost = false;
-    std::vector<int64_t> node_off;  // [B+1]
-    std::vector<DtlChunk> chunks;
-    int64_t max_chunk_rows = 0;
     // device
-    int32_t* d_rows_slab = nullptr;  // row_cl,row_cr,row_node,row_left,row_right [5*R]
-    int32_t *row_cl = nullptr, *row_cr = nullptr, *row_node = nullptr, *row_left = nullptr,
-            *row_right = nullptr;
-    int64_t* d_root_row = nullptr;   // [B] global row of the root, or -1-leaf_species
-    int32_t* d_root_node = nullptr;  // [B] global node id of the root
     int32_t* d_T = nullptr;          // [max_chunk_rows * pitch]
     uint32_t* d_tag = nullptr;       // [max_chunk_rows * pitch]
     int32_t* d_C = nullptr;          // decoded cost rows (only if need_decoded_cost)
     int32_t* d_min_cost = nullptr;   // [B]
     int32_t* d_root_species = nullptr;  // [B]
     int32_t* d_map = nullptr;        // [N]
-    // host copies for the test hook
-    std::vector<int32_t> h_left, h_right, h_leaf;
-    std::vector<int64_t> h_node_row;  // [N] global row of a node or -1 (only with KEEP_TABLES)
     bool solved = false;
     // wave launch configuration (fixed per upload)
     int spad = 0, wave_warps = 0;
@@ -69,9 +51,7 @@ struct DtlProblem {
 void sr2_free_dtl(sr2_ctx* ctx) {
     DtlProblem* p = ctx->dtl;
     if (!p) return;
-    cudaFree(p->d_rows_slab);
-    cudaFree(p->d_root_row);
-    cudaFree(p->d_root_node);
+    p->rows.release();
     cudaFree(p->d_T);
     cudaFree(p->d_tag);
     cudaFree(p->d_C);
@@ -358,6 +338,18 @@ static double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64_t max_nodes) {
+    for (int k = 0; k < 5; ++k)
+        if (costs[k] < 0 || costs[k] > (1 << 20))
+            return sr2_fail(ctx, SR2_ERR_RANGE, std::string(who) + ": event costs must be integers in [0, 2^20]");
+    // finite table values are bounded by (#internal nodes) * (largest event term)
+    int64_t ev = std::max<int64_t>({costs[0], costs[1], costs[2]}) + 2 * (int64_t)costs[3] * ctx->D +
+                 2 * (int64_t)costs[4];
+    if (max_nodes * ev >= (1 << 29))
+        return sr2_fail(ctx, SR2_ERR_RANGE, std::string(who) + ": costs x tree size may overflow the int32 DP table");
+    return SR2_OK;
+}
+
 extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
                               const int32_t* left, const int32_t* right,
                               const int32_t* leaf_species, const int32_t costs[5], uint32_t flags) {
@@ -368,90 +360,16 @@ extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
         return sr2_fail(ctx, SR2_ERR_ARG, "sr2_dtl_upload: null array");
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
     sr2_free_dtl(ctx);
-    const int S = ctx->S;
     const int64_t N = B ? node_off[B] : 0;
-    if (N >= (int64_t)1 << 31)
-        return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_dtl_upload: more than 2^31 object nodes in one batch");
-    for (int k = 0; k < 5; ++k)
-        if (costs[k] < 0 || costs[k] > (1 << 20))
-            return sr2_fail(ctx, SR2_ERR_RANGE,
-                            "sr2_dtl_upload: event costs must be integers in [0, 2^20]");
 
     DtlProblem* p = new DtlProblem();
     ctx->dtl = p;
-    p->B = B;
-    p->N = N;
     p->flags = flags;
     memcpy(p->costs, costs, sizeof(p->costs));
     // cost() == table value unless speciations are charged: the table never adds the
     // speciation cost (reconciliation.py:97-108) but cost() does (DESIGN.md "selection").
     p->need_decoded_cost = costs[0] != 0;
-    p->node_off.assign(node_off, node_off + B + 1);
 
-    // ---- pass 1: validate, heights, per-instance histogram of heights -------
-    std::vector<uint16_t> height(N);
-    int bad_inst = -1;
-    std::string bad_msg;
-    int64_t max_finite_bound = 0;
-    int Hmax = 0;
-    std::vector<int32_t> inst_H(B, 0);
-#pragma omp parallel for schedule(dynamic, 64) reduction(max : Hmax)
-    for (int b = 0; b < B; ++b) {
-        int64_t off = node_off[b];
-        int64_t G = node_off[b + 1] - off;
-        const char* why = nullptr;
-        if (G < 1) why = "empty object tree";
-        std::vector<uint8_t> refs;
-        if (!why) refs.assign(G, 0);
-        for (int64_t u = G - 1; u >= 0 && !why; --u) {
-            int l = left[off + u], r = right[off + u];
-            if (l < 0 && r < 0) {
-                int s = leaf_species[off + u];
-                if (s < 0 || s >= S) why = "leaf species out of range";
-                height[off + u] = 0;
-            } else if (l <= u || r <= u || l >= G || r >= G || l == r) {
-                why = "children must be two distinct nodes numbered after their parent";
-            } else {
-                if (++refs[l] > 1 || ++refs[r] > 1) why = "a node has two parents";
-                int h = 1 + std::max(height[off + l], height[off + r]);
-                if (h > 65535) why = "object tree higher than 65535";
-                height[off + u] = (uint16_t)h;
-            }
-        }
-        if (!why)
-            for (int64_t u = 1; u < G; ++u)
-                if (refs[u] != 1) {
-                    why = "a node other than node 0 has no parent";
-                    break;
-                }
-        if (why) {
-#pragma omp critical
-            if (bad_inst < 0 || b < bad_inst) {
-                bad_inst = b;
-                bad_msg = why;
-            }
-            continue;
-        }
-        inst_H[b] = height[off];
-        Hmax = std::max(Hmax, (int)height[off]);
-    }
-    if (bad_inst >= 0)
-        return sr2_fail(ctx, SR2_ERR_ARG,
-                        "sr2_dtl_upload: instance " + std::to_string(bad_inst) + ": " + bad_msg);
-    // finite table values are bounded by (#internal nodes) * (largest event term)
-    {
-        int64_t maxG = 0;
-        for (int b = 0; b < B; ++b) maxG = std::max(maxG, node_off[b + 1] - node_off[b]);
-        int64_t ev = std::max<int64_t>({std::abs((int64_t)costs[0]), std::abs((int64_t)costs[1]),
-                                        std::abs((int64_t)costs[2])}) +
-                     2 * std::abs((int64_t)costs[3]) * (int64_t)ctx->D;
-        max_finite_bound = maxG * ev;
-        if (max_finite_bound >= (1 << 29))
-            return sr2_fail(ctx, SR2_ERR_RANGE,
-                            "sr2_dtl_upload: costs x tree size may overflow the int32 DP table");
-    }
-
-    // ---- chunking by device memory ------------------------------------------
     size_t free_b = 0, total_b = 0;
     SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     size_t per_row = (size_t)ctx->pitch * (p->need_decoded_cost ? 12 : 8);
@@ -459,126 +377,21 @@ extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
     if (free_b < fixed + per_row * 4)
         return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: batch does not fit in device memory");
     int64_t rows_budget = (int64_t)(((free_b - fixed) / 10 * 9) / per_row);
-    std::vector<int64_t> inst_rows(B);
-#pragma omp parallel for schedule(static)
-    for (int b = 0; b < B; ++b) inst_rows[b] = (node_off[b + 1] - node_off[b] - 1) / 2;
-    {
-        DtlChunk c;
-        int64_t rows = 0, total_rows = 0;
-        for (int b = 0; b < B; ++b) {
-            if (inst_rows[b] > rows_budget)
-                return sr2_fail(ctx, SR2_ERR_NOMEM,
-                                "sr2_dtl_upload: one instance alone exceeds device memory");
-            if (rows + inst_rows[b] > rows_budget) {
-                c.inst_end = b;
-                c.row_end = total_rows;
-                p->chunks.push_back(c);
-                c = DtlChunk();
-                c.inst_begin = b;
-                c.row_begin = total_rows;
-                rows = 0;
-            }
-            rows += inst_rows[b];
-            total_rows += inst_rows[b];
-        }
-        c.inst_end = B;
-        c.row_end = total_rows;
-        p->chunks.push_back(c);
-        p->R = total_rows;
-    }
-    if ((flags & SR2_KEEP_TABLES) && p->chunks.size() > 1)
+    int rc = sr2_build_rows(ctx, "sr2_dtl_upload", B, node_off, left, right, leaf_species, rows_budget,
+                            (flags & SR2_KEEP_TABLES) != 0, false, &p->rows);
+    if (rc) return rc;
+    rc = sr2_check_costs(ctx, "sr2_dtl_upload", costs, p->rows.max_nodes);
+    if (rc) return rc;
+    if ((flags & SR2_KEEP_TABLES) && p->rows.chunks.size() > 1)
         return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: SR2_KEEP_TABLES needs the batch to fit in one chunk");
-    const int64_t R = p->R;
 
-    // ---- pass 2: rows in (chunk, height, instance, node) order ---------------
-    std::vector<int32_t> rows_slab((size_t)std::max<int64_t>(R, 1) * 5);
-    int32_t* h_cl = rows_slab.data();
-    int32_t* h_cr = h_cl + R;
-    int32_t* h_node = h_cr + R;
-    int32_t* h_left = h_node + R;
-    int32_t* h_right = h_left + R;
-    std::vector<int64_t> h_root_row(B);
-    std::vector<int32_t> h_root_node(B);
-    std::vector<int64_t> node_row;  // global row of each node (internal) -- scratch
-    node_row.assign(N, -1);
-    const int W = Hmax + 1;
-    for (auto& c : p->chunks) {
-        int nb = c.inst_end - c.inst_begin;
-        // cnt[(b - inst_begin) * W + h]
-        std::vector<int64_t> cnt((size_t)nb * W, 0);
-#pragma omp parallel for schedule(dynamic, 64)
-        for (int b = c.inst_begin; b < c.inst_end; ++b) {
-            int64_t off = node_off[b], G = node_off[b + 1] - off;
-            int64_t* mine = cnt.data() + (size_t)(b - c.inst_begin) * W;
-            for (int64_t u = 0; u < G; ++u) mine[height[off + u]]++;
-        }
-        // exclusive prefix over (h, b): rows of one height are contiguous
-        c.wave_off.assign(W + 1, 0);
-        int64_t run = c.row_begin;
-        c.wave_off[0] = run;
-        for (int h = 1; h < W; ++h) {
-            c.wave_off[h] = run;  // wave h covers [wave_off[h], wave_off[h+1])
-            for (int i = 0; i < nb; ++i) {
-                int64_t k = cnt[(size_t)i * W + h];
-                cnt[(size_t)i * W + h] = run;
-                run += k;
-            }
-        }
-        c.wave_off[W] = run;
-        p->max_chunk_rows = std::max(p->max_chunk_rows, c.row_end - c.row_begin);
-#pragma omp parallel for schedule(dynamic, 64)
-        for (int b = c.inst_begin; b < c.inst_end; ++b) {
-            int64_t off = node_off[b], G = node_off[b + 1] - off;
-            int64_t* cursor = cnt.data() + (size_t)(b - c.inst_begin) * W;
-            for (int64_t u = 0; u < G; ++u) {
-                int h = height[off + u];
-                if (h > 0) node_row[off + u] = cursor[h]++;
-            }
-            for (int64_t u = 0; u < G; ++u) {
-                int64_t gr = node_row[off + u];
-                if (gr < 0) continue;
-                int l = left[off + u], r = right[off + u];
-                int64_t rl = node_row[off + l], rr = node_row[off + r];
-                h_cl[gr] = rl >= 0 ? (int32_t)(rl - c.row_begin) : -1 - leaf_species[off + l];
-                h_cr[gr] = rr >= 0 ? (int32_t)(rr - c.row_begin) : -1 - leaf_species[off + r];
-                h_node[gr] = (int32_t)(off + u);
-                h_left[gr] = (int32_t)(off + l);
-                h_right[gr] = (int32_t)(off + r);
-            }
-            h_root_node[b] = (int32_t)off;
-            h_root_row[b] = node_row[off] >= 0 ? node_row[off] : -1 - (int64_t)leaf_species[off];
-        }
-    }
-
-    // ---- device allocations + H2D ---------------------------------------------
-    SR2_CUDA(ctx, cudaMalloc(&p->d_rows_slab, rows_slab.size() * sizeof(int32_t)));
-    p->row_cl = p->d_rows_slab;
-    p->row_cr = p->row_cl + R;
-    p->row_node = p->row_cr + R;
-    p->row_left = p->row_node + R;
-    p->row_right = p->row_left + R;
-    SR2_CUDA(ctx, cudaMalloc(&p->d_root_row, std::max<size_t>(B, 1) * sizeof(int64_t)));
-    SR2_CUDA(ctx, cudaMalloc(&p->d_root_node, std::max<size_t>(B, 1) * sizeof(int32_t)));
     SR2_CUDA(ctx, cudaMalloc(&p->d_min_cost, std::max<size_t>(B, 1) * sizeof(int32_t)));
     SR2_CUDA(ctx, cudaMalloc(&p->d_root_species, std::max<size_t>(B, 1) * sizeof(int32_t)));
     SR2_CUDA(ctx, cudaMalloc(&p->d_map, std::max<size_t>(N, 1) * sizeof(int32_t)));
-    size_t table_elems = (size_t)std::max<int64_t>(p->max_chunk_rows, 1) * ctx->pitch;
+    size_t table_elems = (size_t)std::max<int64_t>(p->rows.max_chunk_rows, 1) * ctx->pitch;
     SR2_CUDA(ctx, cudaMalloc(&p->d_T, table_elems * sizeof(int32_t)));
     SR2_CUDA(ctx, cudaMalloc(&p->d_tag, table_elems * sizeof(uint32_t)));
     if (p->need_decoded_cost) SR2_CUDA(ctx, cudaMalloc(&p->d_C, table_elems * sizeof(int32_t)));
-    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_rows_slab, rows_slab.data(), rows_slab.size() * sizeof(int32_t),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_root_row, h_root_row.data(), (size_t)B * sizeof(int64_t),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_root_node, h_root_node.data(), (size_t)B * sizeof(int32_t),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (flags & SR2_KEEP_TABLES) {
-        p->h_left.assign(left, left + N);
-        p->h_right.assign(right, right + N);
-        p->h_leaf.assign(leaf_species, leaf_species + N);
-        p->h_node_row.swap(node_row);
-    }
     ctx->timing.upload_ms = (float)(now_ms() - t0);
     return SR2_OK;
 }
@@ -605,17 +418,17 @@ static int dtl_configure_waves(sr2_ctx* ctx, DtlProblem* p) {
     return SR2_OK;
 }
 
-static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const DtlChunk& c, int64_t row_begin,
+static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int64_t row_begin,
                            int64_t n_rows, const DtlCosts& cs) {
     if (n_rows <= 0) return SR2_OK;
     if (!p->cta_per_row) {
         int64_t grid = (n_rows + p->wave_warps - 1) / p->wave_warps;
         dtl_wave_kernel<32><<<(unsigned)grid, p->wave_warps * 32, p->wave_smem, ctx->stream>>>(
-            ctx->dsp, p->row_cl, p->row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
             p->spad);
     } else {
         dtl_wave_kernel<512><<<(unsigned)n_rows, 512, p->wave_smem, ctx->stream>>>(
-            ctx->dsp, p->row_cl, p->row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
             p->spad);
     }
     SR2_CUDA(ctx, cudaGetLastError());
@@ -636,7 +449,7 @@ extern "C" int sr2_dtl_solve(sr2_ctx* ctx) {
     int n_waves = 0, n_launch = 0;
     float waves_ms = 0.f;
     SR2_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-    for (const DtlChunk& c : p->chunks) {
+    for (const RowChunk& c : p->rows.chunks) {
         const int H = (int)c.wave_off.size() - 2;  // highest wave
         SR2_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
         for (int h = 1; h <= H; ++h) {
@@ -653,14 +466,14 @@ extern "C" int sr2_dtl_solve(sr2_ctx* ctx) {
                 int64_t n = c.wave_off[h + 1] - c.wave_off[h];
                 if (n <= 0) continue;
                 dtl_decoded_cost_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(
-                    ctx->dsp, p->row_cl, p->row_cr, c.wave_off[h], c.row_begin, (int)n, p->d_tag, p->d_C, cs);
+                    ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->d_tag, p->d_C, cs);
                 ++n_launch;
             }
         }
         int n_inst = c.inst_end - c.inst_begin;
         if (n_inst > 0) {
             dtl_select_kernel<<<(n_inst + 7) / 8, 256, 0, st>>>(
-                ctx->dsp, p->d_root_row, p->d_root_node, c.inst_begin, n_inst, c.row_begin, p->d_T,
+                ctx->dsp, p->rows.d_root_row, p->rows.d_root_node, c.inst_begin, n_inst, c.row_begin, p->d_T,
                 p->need_decoded_cost ? p->d_C : nullptr, p->d_min_cost, p->d_root_species, p->d_map);
             ++n_launch;
         }
@@ -668,12 +481,12 @@ extern "C" int sr2_dtl_solve(sr2_ctx* ctx) {
             int64_t n = c.wave_off[h + 1] - c.wave_off[h];
             if (n <= 0) continue;
             dtl_traceback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-                ctx->dsp, p->row_node, p->row_left, p->row_right, c.wave_off[h], c.row_begin, (int)n,
+                ctx->dsp, p->rows.row_node, p->rows.row_left, p->rows.row_right, c.wave_off[h], c.row_begin, (int)n,
                 p->d_tag, p->d_map);
             ++n_launch;
         }
         SR2_CUDA(ctx, cudaGetLastError());
-        if (p->chunks.size() > 1) {
+        if (p->rows.chunks.size() > 1) {
             // the next chunk reuses the table buffers: account the wave time now
             SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
             float ms = 0.f;
@@ -683,12 +496,12 @@ extern "C" int sr2_dtl_solve(sr2_ctx* ctx) {
     }
     SR2_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
-    if (p->chunks.size() == 1) cudaEventElapsedTime(&waves_ms, ctx->ev[2], ctx->ev[3]);
+    if (p->rows.chunks.size() == 1) cudaEventElapsedTime(&waves_ms, ctx->ev[2], ctx->ev[3]);
     cudaEventElapsedTime(&ctx->timing.solve_ms, ctx->ev[0], ctx->ev[1]);
     ctx->timing.waves_ms = waves_ms;
     ctx->timing.n_waves = n_waves;
     ctx->timing.n_launches = n_launch;
-    ctx->timing.n_cells = p->R * (int64_t)ctx->S;
+    ctx->timing.n_cells = p->rows.R * (int64_t)ctx->S;
     p->solved = true;
     return SR2_OK;
 }
@@ -701,13 +514,13 @@ extern "C" int sr2_dtl_results(sr2_ctx* ctx, int32_t* out_min_cost, int32_t* out
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
     double t0 = now_ms();
     if (out_min_cost)
-        SR2_CUDA(ctx, cudaMemcpyAsync(out_min_cost, p->d_min_cost, (size_t)p->B * 4, cudaMemcpyDeviceToHost,
+        SR2_CUDA(ctx, cudaMemcpyAsync(out_min_cost, p->d_min_cost, (size_t)p->rows.B * 4, cudaMemcpyDeviceToHost,
                                       ctx->stream));
     if (out_root_species)
-        SR2_CUDA(ctx, cudaMemcpyAsync(out_root_species, p->d_root_species, (size_t)p->B * 4,
+        SR2_CUDA(ctx, cudaMemcpyAsync(out_root_species, p->d_root_species, (size_t)p->rows.B * 4,
                                       cudaMemcpyDeviceToHost, ctx->stream));
     if (out_map_species)
-        SR2_CUDA(ctx, cudaMemcpyAsync(out_map_species, p->d_map, (size_t)p->N * 4, cudaMemcpyDeviceToHost,
+        SR2_CUDA(ctx, cudaMemcpyAsync(out_map_species, p->d_map, (size_t)p->rows.N * 4, cudaMemcpyDeviceToHost,
                                       ctx->stream));
     SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->timing.results_ms = (float)(now_ms() - t0);
@@ -731,19 +544,19 @@ extern "C" int sr2_dtl_tables(sr2_ctx* ctx, int32_t instance, int32_t* out_value
     if (!p || !p->solved) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_tables: solve first");
     if (!(p->flags & SR2_KEEP_TABLES))
         return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_tables: upload with SR2_KEEP_TABLES");
-    if (instance < 0 || instance >= p->B) return sr2_fail(ctx, SR2_ERR_ARG, "sr2_dtl_tables: bad instance");
+    if (instance < 0 || instance >= p->rows.B) return sr2_fail(ctx, SR2_ERR_ARG, "sr2_dtl_tables: bad instance");
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
     const int S = ctx->S, pitch = ctx->pitch;
-    int64_t off = p->node_off[instance], G = p->node_off[instance + 1] - off;
+    int64_t off = p->rows.node_off[instance], G = p->rows.node_off[instance + 1] - off;
     std::vector<int32_t> rowT(pitch);
     std::vector<uint32_t> rowG(pitch);
     for (int64_t u = 0; u < G; ++u) {
-        int64_t gr = p->h_node_row[off + u];
+        int64_t gr = p->rows.h_node_row[off + u];
         int32_t* ov = out_value ? out_value + (size_t)u * S : nullptr;
         int32_t* ot = out_tag ? out_tag + (size_t)u * S * 2 : nullptr;
         if (gr < 0) {
             for (int x = 0; x < S; ++x) {
-                if (ov) ov[x] = x == p->h_leaf[off + u] ? 0 : SR2_INF;
+                if (ov) ov[x] = x == p->rows.h_leaf[off + u] ? 0 : SR2_INF;
                 if (ot) ot[2 * x] = ot[2 * x + 1] = -1;
             }
             continue;

@@ -1,9 +1,892 @@
-// sr2_superdtl.cu -- the `superdtl` DP (filled in below).
-#include "sr2_internal.cuh"
+// sr2_superdtl.cu -- the `superdtl` (unordered super-reconciliation) DP on sm_100a.
+//
+// Replaces /root/reference/src/superrec2/compute/unordered_super_reconciliation.py:
+//   _compute_gain_sets / _compute_lca_sets   :85-136   (bitset kernels syn_*)
+//   _compute_uspfs_entry                     :147-297  (superdtl_wave_kernel)
+//   _compute_uspfs_table                     :300-358  (the wavefront driver)
+//   _decode_uspfs_table                      :361-446  (sdecode_*, incl. the in-place
+//                                                        set union of :386-391)
+//   _uspfs selection                         :449-497  (scost_kernel, sselect_kernel,
+//                                                        sbest_kernel)
+// and SuperReconciliationOutput.cost() (model/reconciliation.py:511-554), the
+// objective the reference actually minimises when it picks the returned solution.
+//
+// Table state per (object node u, species x): two values, kind LCA (0) and kind
+// INHERIT (1).  For each child i and each parent kind K three rows of keys are
+// built from the child's two value rows:
+//   cons = "conserved" (subtree of x, synteny kept)     -> SUBMIN
+//   seg  = "segment"   (subtree of x, segment lost)      -> SUBMIN
+//   sep  = "separate"  (species incomparable to x)       -> SEPMIN
+// cons/seg carry floss * depth so that a subtree minimum is valid for every
+// ancestor x; the cell subtracts floss * depth[x] again ("rel").  The `left` /
+// `right` choices of the reference are cons at the two children of x.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
 
-struct SuperProblem {};
+#include "sr2_rows.cuh"
+
+int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64_t max_nodes);
+
+struct SuperProblem {
+    RowLayout rows;
+    uint32_t flags = 0;
+    int32_t costs[5] = {0, 0, 0, 0, 0};
+    int W = 1;                 // 32-bit words per synteny bitset
+    int64_t index_base = 0;    // global number of instance 0 (resolution sharding)
+    // device
+    int32_t *d_left = nullptr, *d_right = nullptr;       // [N] global node ids, -1 for leaves
+    int64_t* d_node_off = nullptr;                       // [B+1]
+    uint32_t *d_bits = nullptr, *d_present = nullptr, *d_outside = nullptr, *d_gain = nullptr,
+             *d_L = nullptr;                             // [N*W]
+    uint8_t* d_row_flags = nullptr;                      // [R]
+    int32_t* d_T = nullptr;                              // [rows*2*pitch]
+    uint32_t* d_tag = nullptr;                           // [rows*2*pitch]
+    uint16_t *d_dec = nullptr, *d_anc = nullptr;         // [N*S] (species<<1|kind), local index of the set owner
+    uint32_t *d_tau = nullptr, *d_taumin = nullptr;      // [N*W*32], [N]
+    int32_t* d_cost = nullptr;                           // [B*S] cost() of the decode from each root
+    int32_t *d_min_cost = nullptr, *d_root_species = nullptr;  // [B]
+    int32_t *d_map = nullptr, *d_kind = nullptr;         // [N]
+    uint32_t* d_syn = nullptr;                           // [N*W]
+    unsigned long long* d_best = nullptr;                // packed (cost, instance, root)
+    bool solved = false;
+    int spad = 0, wave_warps = 0;
+    size_t wave_smem = 0;
+    bool cta_per_row = false;
+};
 
 void sr2_free_super(sr2_ctx* ctx) {
-    delete ctx->super;
+    SuperProblem* p = ctx->super;
+    if (!p) return;
+    p->rows.release();
+    cudaFree(p->d_left);
+    cudaFree(p->d_right);
+    cudaFree(p->d_node_off);
+    cudaFree(p->d_bits);
+    cudaFree(p->d_present);
+    cudaFree(p->d_outside);
+    cudaFree(p->d_gain);
+    cudaFree(p->d_L);
+    cudaFree(p->d_row_flags);
+    cudaFree(p->d_T);
+    cudaFree(p->d_tag);
+    cudaFree(p->d_dec);
+    cudaFree(p->d_anc);
+    cudaFree(p->d_tau);
+    cudaFree(p->d_taumin);
+    cudaFree(p->d_cost);
+    cudaFree(p->d_min_cost);
+    cudaFree(p->d_root_species);
+    cudaFree(p->d_map);
+    cudaFree(p->d_kind);
+    cudaFree(p->d_syn);
+    cudaFree(p->d_best);
+    delete p;
     ctx->super = nullptr;
+}
+
+struct SuperCosts {
+    int spe, dup, hgt, floss, sloss;
+};
+
+#define DEC_NONE 0xffffu
+
+// ---------------------------------------------------------------------------
+// synteny bitsets (gain sets and LCA sets)
+// ---------------------------------------------------------------------------
+// present[u] = families carried by some leaf below u (starts as a copy of the leaf bits)
+__global__ void syn_present_wave(const int32_t* __restrict__ row_node, const int32_t* __restrict__ row_left,
+                                 const int32_t* __restrict__ row_right, int64_t row_begin, int n_rows, int W,
+                                 uint32_t* __restrict__ present) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * W) return;
+    int64_t gr = row_begin + i / W;
+    int w = i % W;
+    present[(size_t)row_node[gr] * W + w] =
+        present[(size_t)row_left[gr] * W + w] | present[(size_t)row_right[gr] * W + w];
+}
+
+// outside[u] = families carried by some leaf NOT below u (top-down; zero at the roots)
+__global__ void syn_outside_wave(const int32_t* __restrict__ row_node, const int32_t* __restrict__ row_left,
+                                 const int32_t* __restrict__ row_right, int64_t row_begin, int n_rows, int W,
+                                 const uint32_t* __restrict__ present, uint32_t* __restrict__ outside) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows * W) return;
+    int64_t gr = row_begin + i / W;
+    int w = i % W;
+    uint32_t mine = outside[(size_t)row_node[gr] * W + w];
+    size_t l = (size_t)row_left[gr] * W + w, r = (size_t)row_right[gr] * W + w;
+    outside[l] = mine | present[r];
+    outside[r] = mine | present[l];
+}
+
+// A family is gained at the LCA of the leaves that carry it (:98-107): the node where it
+// is "complete" (present and not outside) while complete in neither child.
+__global__ void syn_gain_kernel(const int32_t* __restrict__ left, const int32_t* __restrict__ right, int64_t N,
+                                int W, const uint32_t* __restrict__ present,
+                                const uint32_t* __restrict__ outside, uint32_t* __restrict__ gain) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N * W) return;
+    int64_t u = i / W;
+    int w = (int)(i % W);
+    uint32_t full = present[i] & ~outside[i];
+    int l = left[u];
+    if (l >= 0) {
+        size_t li = (size_t)l * W + w, ri = (size_t)right[u] * W + w;
+        full &= ~((present[li] & ~outside[li]) | (present[ri] & ~outside[ri]));
+    }
+    gain[i] = full;
+}
+
+// L[u] = (L[l] | L[r]) - (gain[l] | gain[r]) (:126-134); also the two subset flags that
+// _compute_uspfs_entry tests per child (:182).  L starts as a copy of the leaf bits.
+__global__ void syn_lca_wave(const int32_t* __restrict__ row_node, const int32_t* __restrict__ row_left,
+                             const int32_t* __restrict__ row_right, int64_t row_begin, int n_rows, int W,
+                             const uint32_t* __restrict__ gain, uint32_t* __restrict__ L,
+                             uint8_t* __restrict__ row_flags) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    int64_t gr = row_begin + i;
+    size_t u = (size_t)row_node[gr] * W, l = (size_t)row_left[gr] * W, r = (size_t)row_right[gr] * W;
+    bool sub0 = true, sub1 = true;
+    for (int w = 0; w < W; ++w) {
+        uint32_t Ll = L[l + w], Lr = L[r + w];
+        uint32_t mine = (Ll | Lr) & ~(gain[l + w] | gain[r + w]);
+        L[u + w] = mine;
+        sub0 &= (mine & ~Ll) == 0;
+        sub1 &= (mine & ~Lr) == 0;
+    }
+    row_flags[gr] = (uint8_t)((sub0 ? 1 : 0) | (sub1 ? 2 : 0));
+}
+
+// ---------------------------------------------------------------------------
+// the table
+// ---------------------------------------------------------------------------
+// superdtl keys: value[63:32] | rank[31:16] | kind[15] | depth[14:0]; order (value, rank, kind)
+__device__ __forceinline__ u64 skey(int value, int rank, int kind, int depth) {
+    return ((u64)(unsigned)value << 32) | ((u64)(unsigned)rank << 16) | ((unsigned)kind << 15) | (unsigned)depth;
+}
+__device__ __forceinline__ int sat_add(int a, int b) { return (a >= SR2_INF || b >= SR2_INF) ? SR2_INF : a + b; }
+
+template <int TPR>
+__device__ __forceinline__ void sgroup_sync() {
+    if (TPR == 32)
+        __syncwarp();
+    else
+        __syncthreads();
+}
+
+// one candidate: children at keys a / b; da, db = depth the cons/seg value is relative to,
+// or -1 for a "separate" key (raw value, no distance term).
+__device__ __forceinline__ void super_offer(u64 a, int da, u64 b, int db, int event, int floss, int& best,
+                                            unsigned& tag) {
+    unsigned va = (unsigned)(a >> 32), vb = (unsigned)(b >> 32);
+    if (va < (unsigned)SR2_INF && vb < (unsigned)SR2_INF) {
+        int v = event + (int)va + (int)vb - floss * ((da < 0 ? 0 : da) + (db < 0 ? 0 : db));
+        if (v < best) {
+            best = v;
+            tag = (unsigned)((a >> 15) & 0xffffu) | ((unsigned)((b >> 15) & 0xffffu) << 16);
+        }
+    }
+}
+
+// arrays of one row in shared memory: [child i][parent kind K][cons, seg, sep]
+#define SARR(base, spad, i, K, t) ((base) + (size_t)((((i) * 2 + (K)) * 3) + (t)) * (spad))
+enum { T_CONS = 0, T_SEG = 1, T_SEP = 2 };
+
+// Cell (u, x, K).  P0/P1: SEPMIN keys of child 0/1 at x.  Candidate order = :289-297.
+__device__ __forceinline__ void super_cell(const u64* base, int spad, int K, int x, int dx, int cx, bool is_root,
+                                           u64 P0, u64 P1, const SuperCosts& cs, int& best, unsigned& tag) {
+    const u64* C0 = SARR(base, spad, 0, K, T_CONS);
+    const u64* C1 = SARR(base, spad, 1, K, T_CONS);
+    const u64* G0 = SARR(base, spad, 0, K, T_SEG);
+    const u64* G1 = SARR(base, spad, 1, K, T_SEG);
+    best = SR2_INF;
+    tag = SR2_NO_TAG;
+    if (cx >= 0) {
+        super_offer(C0[cx], dx + 1, C1[cx + 1], dx + 1, cs.spe, cs.floss, best, tag);  // left x right
+        super_offer(C0[cx + 1], dx + 1, C1[cx], dx + 1, cs.spe, cs.floss, best, tag);  // right x left
+    }
+    u64 c0 = C0[x], c1 = C1[x];
+    super_offer(c0, dx, G1[x], dx, cs.dup, cs.floss, best, tag);  // conserved x segment
+    super_offer(G0[x], dx, c1, dx, cs.dup, cs.floss, best, tag);  // segment x conserved
+    if (!is_root) {
+        super_offer(c0, dx, P1, -1, cs.hgt, cs.floss, best, tag);  // conserved x separate
+        super_offer(P0, -1, c1, dx, cs.hgt, cs.floss, best, tag);  // separate x conserved
+    }
+}
+
+template <int TPR>
+__global__ void __launch_bounds__(TPR == 32 ? 256 : TPR)
+superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                     const uint8_t* __restrict__ row_flags, int64_t row_begin, int64_t chunk_row0, int n_rows,
+                     int32_t* __restrict__ T, uint32_t* __restrict__ tags, SuperCosts cs, int spad) {
+    extern __shared__ u64 smem[];
+    const int S = sp.S;
+    int group, lane, groups_per_cta;
+    if (TPR == 32) {
+        group = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        groups_per_cta = blockDim.x >> 5;
+    } else {
+        group = 0;
+        lane = threadIdx.x;
+        groups_per_cta = 1;
+    }
+    int local = blockIdx.x * groups_per_cta + group;
+    if (local >= n_rows) return;
+    const int64_t gr = row_begin + local;
+    const size_t slot = (size_t)(gr - chunk_row0);
+    u64* base = smem + (size_t)group * 12 * spad;
+    const int flags = row_flags[gr];
+
+    // stage the child rows as the 12 key rows
+    for (int i = 0; i < 2; ++i) {
+        const int c = i == 0 ? row_cl[gr] : row_cr[gr];
+        const bool sub = (flags >> i) & 1;               // L[u] <= L[child]  (:182)
+        const int ll = sub ? 0 : cs.sloss;               // lca_lca_dist
+        const int li = sub ? SR2_INF : 0;                // lca_inh_dist
+        const int32_t* __restrict__ TA = c >= 0 ? T + ((size_t)c * 2 + 0) * sp.pitch : nullptr;
+        const int32_t* __restrict__ TB = c >= 0 ? T + ((size_t)c * 2 + 1) * sp.pitch : nullptr;
+        for (int y = lane; y < S; y += TPR) {
+            int d = __ldg(sp.depth + y);
+            int Araw = TA ? TA[y] : (y == -1 - c ? 0 : SR2_INF);
+            int Braw = TB ? TB[y] : SR2_INF;
+            int A = sat_add(Araw, cs.floss * d), B = sat_add(Braw, cs.floss * d);
+            // parent kind INHERIT: (sloss, 0, 0)
+            SARR(base, spad, i, 1, T_CONS)[y] = key_min(skey(sat_add(A, cs.sloss), y, 0, d), skey(B, y, 1, d));
+            SARR(base, spad, i, 1, T_SEG)[y] = key_min(skey(A, y, 0, d), skey(B, y, 1, d));
+            SARR(base, spad, i, 1, T_SEP)[y] = key_min(skey(Araw, y, 0, d), skey(Braw, y, 1, d));
+            // parent kind LCA: (lca_lca_dist, lca_inh_dist, lca_inh_dist)
+            SARR(base, spad, i, 0, T_CONS)[y] =
+                key_min(skey(sat_add(A, ll), y, 0, d), skey(sat_add(B, li), y, 1, d));
+            SARR(base, spad, i, 0, T_SEG)[y] = key_min(skey(A, y, 0, d), skey(sat_add(B, li), y, 1, d));
+            SARR(base, spad, i, 0, T_SEP)[y] = key_min(skey(Araw, y, 0, d), skey(sat_add(Braw, li), y, 1, d));
+        }
+    }
+    sgroup_sync<TPR>();
+
+    // up-sweep of all 12 rows
+    for (int d = sp.D - 2; d >= 0; --d) {
+        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
+        for (int i = b + lane; i < e; i += TPR) {
+            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+#pragma unroll
+            for (int a = 0; a < 12; ++a) {
+                u64* arr = base + (size_t)a * spad;
+                arr[p] = key_min(arr[p], key_min(arr[c], arr[c + 1]));
+            }
+        }
+        sgroup_sync<TPR>();
+    }
+
+    int32_t* __restrict__ Tout0 = T + (slot * 2 + 0) * sp.pitch;
+    int32_t* __restrict__ Tout1 = T + (slot * 2 + 1) * sp.pitch;
+    uint32_t* __restrict__ Gout0 = tags + (slot * 2 + 0) * sp.pitch;
+    uint32_t* __restrict__ Gout1 = tags + (slot * 2 + 1) * sp.pitch;
+
+    if (lane == 0) {
+        int cx = __ldg(sp.child0);
+        int best;
+        unsigned tag;
+        super_cell(base, spad, 0, 0, 0, cx, true, SR2_KEY_NONE, SR2_KEY_NONE, cs, best, tag);
+        Tout0[0] = best;
+        Gout0[0] = tag;
+        super_cell(base, spad, 1, 0, 0, cx, true, SR2_KEY_NONE, SR2_KEY_NONE, cs, best, tag);
+        Tout1[0] = best;
+        Gout1[0] = tag;
+        for (int i = 0; i < 2; ++i)
+            for (int K = 0; K < 2; ++K) SARR(base, spad, i, K, T_SEP)[0] = SR2_KEY_NONE;
+    }
+    sgroup_sync<TPR>();
+
+    for (int d = 0; d < sp.D - 1; ++d) {
+        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
+        for (int i = b + lane; i < e; i += TPR) {
+            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+            int cx0 = __ldg(sp.child0 + c), cx1 = __ldg(sp.child0 + c + 1);
+#pragma unroll
+            for (int K = 0; K < 2; ++K) {
+                u64* E0 = SARR(base, spad, 0, K, T_SEP);
+                u64* E1 = SARR(base, spad, 1, K, T_SEP);
+                u64 Pp0 = E0[p], Pp1 = E1[p];
+                u64 m00 = E0[c], m01 = E0[c + 1], m10 = E1[c], m11 = E1[c + 1];
+                // species c: incomparable = parent's incomparable + subtree of the sibling c+1
+                u64 Pc_0 = key_min(Pp0, m01), Pc_1 = key_min(Pp1, m11);
+                u64 Pd_0 = key_min(Pp0, m00), Pd_1 = key_min(Pp1, m10);
+                int best;
+                unsigned tag;
+                super_cell(base, spad, K, c, d + 1, cx0, false, Pc_0, Pc_1, cs, best, tag);
+                (K ? Tout1 : Tout0)[c] = best;
+                (K ? Gout1 : Gout0)[c] = tag;
+                super_cell(base, spad, K, c + 1, d + 1, cx1, false, Pd_0, Pd_1, cs, best, tag);
+                (K ? Tout1 : Tout0)[c + 1] = best;
+                (K ? Gout1 : Gout0)[c + 1] = tag;
+                E0[c] = Pc_0;
+                E0[c + 1] = Pd_0;
+                E1[c] = Pc_1;
+                E1[c + 1] = Pd_1;
+            }
+        }
+        sgroup_sync<TPR>();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// decode from every root species, Hazard-A time stamps, cost(), selection
+// ---------------------------------------------------------------------------
+// dec[node*S + k] = (species << 1 | kind) of `node` in the decode that starts at root
+// species k; anc[node*S + k] = instance-local index of the node whose lca-set the node
+// labels itself with (itself for kind LCA, else its nearest LCA-kind ancestor).
+__global__ void sdecode_root_kernel(DevSpecies sp, const int64_t* __restrict__ root_row,
+                                    const int32_t* __restrict__ root_node, int inst_begin, int n_inst,
+                                    int64_t chunk_row0, const uint32_t* __restrict__ tags,
+                                    uint16_t* __restrict__ dec, uint16_t* __restrict__ anc) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_inst * sp.S) return;
+    int b = inst_begin + (int)(i / sp.S), k = (int)(i % sp.S);
+    int64_t gr = root_row[b];
+    bool ok;
+    if (gr < 0)
+        ok = k == (int)(-1 - gr);  // one-node tree: only its own species has an entry (:393-404)
+    else
+        ok = tags[((size_t)(gr - chunk_row0) * 2 + 0) * sp.pitch + k] != SR2_NO_TAG;  // kind LCA (:487)
+    size_t at = (size_t)root_node[b] * sp.S + k;
+    dec[at] = ok ? (uint16_t)(k << 1) : (uint16_t)DEC_NONE;
+    anc[at] = 0;
+}
+
+__global__ void sdecode_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_node,
+                                    const int32_t* __restrict__ row_left, const int32_t* __restrict__ row_right,
+                                    const int64_t* __restrict__ node_off, const int32_t* __restrict__ node_inst,
+                                    const int32_t* __restrict__ node_pre, int64_t row_begin, int64_t chunk_row0,
+                                    int n_rows, const uint32_t* __restrict__ tags, int W,
+                                    const uint32_t* __restrict__ gain, uint16_t* __restrict__ dec,
+                                    uint16_t* __restrict__ anc, uint32_t* __restrict__ tau,
+                                    uint32_t* __restrict__ taumin) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_rows * sp.S) return;
+    int64_t gr = row_begin + i / sp.S;
+    int k = (int)(i % sp.S);
+    size_t slot = (size_t)(gr - chunk_row0);
+    int node = row_node[gr], l = row_left[gr], r = row_right[gr];
+    unsigned e = dec[(size_t)node * sp.S + k];
+    unsigned el = DEC_NONE, er = DEC_NONE;
+    unsigned al = 0, ar = 0;
+    if (e != DEC_NONE) {
+        int x = e >> 1, kd = e & 1;
+        unsigned tag = tags[(slot * 2 + kd) * sp.pitch + x];
+        if (tag != SR2_NO_TAG) {
+            el = tag & 0xffffu;
+            er = tag >> 16;
+            int64_t off = node_off[node_inst[node]];
+            unsigned mine = anc[(size_t)node * sp.S + k];
+            al = (el & 1) ? mine : (unsigned)(l - off);
+            ar = (er & 1) ? mine : (unsigned)(r - off);
+            // kind INHERIT: the node's gains are merged, in place, into the set of its owner at
+            // time (root k, preorder position) and stay there for every later decode (:390)
+#pragma unroll 1
+            for (int side = 0; side < 2; ++side) {
+                unsigned ec = side ? er : el;
+                if (!(ec & 1)) continue;
+                int child = side ? r : l;
+                unsigned owner = side ? ar : al;
+                unsigned stamp = ((unsigned)k << 16) | (unsigned)node_pre[child];
+                bool any = false;
+                for (int w = 0; w < W; ++w) {
+                    uint32_t g = gain[(size_t)child * W + w];
+                    while (g) {
+                        int f = __ffs(g) - 1;
+                        g &= g - 1;
+                        atomicMin(&tau[((size_t)(off + owner) * W + w) * 32 + f], stamp);
+                        any = true;
+                    }
+                }
+                if (any) atomicMin(&taumin[off + owner], stamp);
+            }
+        }
+    }
+    dec[(size_t)l * sp.S + k] = (uint16_t)el;
+    dec[(size_t)r * sp.S + k] = (uint16_t)er;
+    anc[(size_t)l * sp.S + k] = (uint16_t)al;
+    anc[(size_t)r * sp.S + k] = (uint16_t)ar;
+}
+
+// the synteny a node is labelled with at time `stamp`: clean lca-set of its owner plus
+// every family merged into that set at or before `stamp`
+__device__ __forceinline__ uint32_t syn_word(const uint32_t* __restrict__ L, const uint32_t* __restrict__ tau,
+                                             const uint32_t* __restrict__ taumin, size_t owner, int W, int w,
+                                             unsigned stamp) {
+    uint32_t bits = L[owner * W + w];
+    if (taumin[owner] <= stamp) {
+        const uint32_t* t = tau + (owner * W + w) * 32;
+        for (int f = 0; f < 32; ++f)
+            if (t[f] <= stamp) bits |= 1u << f;
+    }
+    return bits;
+}
+
+__device__ __forceinline__ bool sp_anc(const DevSpecies& sp, int a, int b) {  // a is b or above b
+    int ta = __ldg(sp.tin + a), tb = __ldg(sp.tin + b);
+    return ta <= tb && tb < __ldg(sp.tout + a);
+}
+
+// cost() of the decode from root species k of instance b (one thread each)
+__global__ void scost_kernel(DevSpecies sp, const int64_t* __restrict__ node_off, const int32_t* __restrict__ left,
+                             const int32_t* __restrict__ right, const int32_t* __restrict__ node_pre,
+                             int inst_begin, int n_inst, int W, const uint32_t* __restrict__ L,
+                             const uint32_t* __restrict__ tau, const uint32_t* __restrict__ taumin,
+                             const uint16_t* __restrict__ dec, const uint16_t* __restrict__ anc, SuperCosts cs,
+                             int32_t* __restrict__ cost) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_inst * sp.S) return;
+    int b = inst_begin + (int)(i / sp.S), k = (int)(i % sp.S);
+    int64_t off = node_off[b], end = node_off[b + 1];
+    int total = SR2_INF;
+    if (dec[(size_t)off * sp.S + k] != DEC_NONE) {
+        total = 0;
+        for (int64_t u = off; u < end; ++u) {
+            int l = left[u];
+            if (l < 0) continue;
+            int r = right[u];
+            unsigned eu = dec[(size_t)u * sp.S + k], el = dec[(size_t)l * sp.S + k], er = dec[(size_t)r * sp.S + k];
+            int p = eu >> 1, a = el >> 1, c = er >> 1;
+            int dp = __ldg(sp.depth + p), da = __ldg(sp.depth + a), dc = __ldg(sp.depth + c);
+            bool pa = sp_anc(sp, p, a), pc = sp_anc(sp, p, c);
+            // labelling cost (model/reconciliation.py:511-543)
+            size_t ou = (size_t)off + anc[(size_t)u * sp.S + k], ol = (size_t)off + anc[(size_t)l * sp.S + k],
+                   orr = (size_t)off + anc[(size_t)r * sp.S + k];
+            unsigned su = ((unsigned)k << 16) | (unsigned)node_pre[u], sl = ((unsigned)k << 16) | (unsigned)node_pre[l],
+                     sr = ((unsigned)k << 16) | (unsigned)node_pre[r];
+            bool in_l = true, in_r = true;
+            for (int w = 0; w < W; ++w) {
+                uint32_t mine = syn_word(L, tau, taumin, ou, W, w, su);
+                in_l &= (mine & ~syn_word(L, tau, taumin, ol, W, w, sl)) == 0;
+                in_r &= (mine & ~syn_word(L, tau, taumin, orr, W, w, sr)) == 0;
+            }
+            int lc = in_l ? 0 : cs.sloss, rc = in_r ? 0 : cs.sloss;
+            // event (model/reconciliation.py:273-365); decodes of finite entries are never INVALID
+            if (pa && pc) {
+                int cx = __ldg(sp.child0 + p);
+                bool spec = false;
+                if (cx >= 0 && a != p && c != p) {
+                    int t1 = __ldg(sp.tin + cx + 1);
+                    spec = (__ldg(sp.tin + a) < t1) != (__ldg(sp.tin + c) < t1);
+                }
+                if (spec)
+                    total += cs.spe + cs.floss * (da + dc - 2 * dp - 2) + lc + rc;
+                else
+                    total += cs.dup + cs.floss * (da + dc - 2 * dp) + min(lc, rc);
+            } else if (pa) {
+                total += cs.hgt + cs.floss * (da - dp) + lc;  // left child kept (comparable)
+            } else {
+                // transfer with the right child kept; the left child's species is comparable
+                // with p only if it is an ancestor of p, which a decode never produces
+                total += cs.hgt + cs.floss * (dc - dp) + (sp_anc(sp, a, p) ? lc : rc);
+            }
+        }
+    }
+    cost[(size_t)b * sp.S + k] = total;
+}
+
+// first strict minimum over the root species in level order (_uspfs :474-495), one warp per instance
+__global__ void __launch_bounds__(256)
+sselect_kernel(DevSpecies sp, int inst_begin, int n_inst, const int32_t* __restrict__ cost,
+               const uint16_t* __restrict__ dec, const int64_t* __restrict__ node_off,
+               int32_t* __restrict__ min_cost, int32_t* __restrict__ root_species) {
+    int local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (local >= n_inst) return;
+    int b = inst_begin + local;
+    u64 best = SR2_KEY_NONE;
+    for (int k = lane; k < sp.S; k += 32)
+        if (dec[(size_t)node_off[b] * sp.S + k] != DEC_NONE)
+            best = key_min(best, ((u64)(unsigned)cost[(size_t)b * sp.S + k] << 32) | (unsigned)k);
+    for (int off = 16; off; off >>= 1) best = key_min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if (lane == 0) {
+        bool none = best == SR2_KEY_NONE;
+        min_cost[b] = none ? SR2_INF : (int)(best >> 32);
+        root_species[b] = none ? -1 : (int)(best & 0xffffffffu);
+    }
+}
+
+// species, kind and synteny of every node in the decode chosen for its instance
+__global__ void smaterialise_kernel(DevSpecies sp, int64_t node_begin, int64_t n_nodes,
+                                    const int32_t* __restrict__ node_inst, const int64_t* __restrict__ node_off,
+                                    const int32_t* __restrict__ node_pre, const int32_t* __restrict__ root_species,
+                                    int W, const uint32_t* __restrict__ L, const uint32_t* __restrict__ tau,
+                                    const uint32_t* __restrict__ taumin, const uint16_t* __restrict__ dec,
+                                    const uint16_t* __restrict__ anc, int32_t* __restrict__ map,
+                                    int32_t* __restrict__ kind, uint32_t* __restrict__ syn) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    int64_t u = node_begin + i;
+    int b = node_inst[u];
+    int k = root_species[b];
+    if (k < 0) {
+        map[u] = -1;
+        kind[u] = -1;
+        for (int w = 0; w < W; ++w) syn[(size_t)u * W + w] = 0;
+        return;
+    }
+    unsigned e = dec[(size_t)u * sp.S + k];
+    map[u] = e >> 1;
+    kind[u] = e & 1;
+    size_t owner = (size_t)node_off[b] + anc[(size_t)u * sp.S + k];
+    unsigned stamp = ((unsigned)k << 16) | (unsigned)node_pre[u];
+    for (int w = 0; w < W; ++w) syn[(size_t)u * W + w] = syn_word(L, tau, taumin, owner, W, w, stamp);
+}
+
+// lexicographic minimum of (cost, global instance number, root species) over the batch:
+// the reference's running Entry(MIN, ANY) over resolutions (_uspfs :454, :481-495)
+__global__ void sbest_kernel(int n_inst, int64_t index_base, const int32_t* __restrict__ min_cost,
+                             const int32_t* __restrict__ root_species, unsigned long long* __restrict__ best) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    u64 key = SR2_KEY_NONE;
+    if (i < n_inst && root_species[i] >= 0)
+        key = ((u64)(unsigned)min_cost[i] << 40) | ((u64)(index_base + i) << 16) | (unsigned)root_species[i];
+    for (int off = 16; off; off >>= 1) key = key_min(key, __shfl_xor_sync(0xffffffffu, key, off));
+    if ((threadIdx.x & 31) == 0 && key != SR2_KEY_NONE) atomicMin(best, key);
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static double snow_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off, const int32_t* left,
+                                   const int32_t* right, const int32_t* leaf_species, int32_t n_words,
+                                   const uint32_t* leaf_bits, const int32_t costs[5], int64_t index_base,
+                                   uint32_t flags) {
+    if (!ctx) return SR2_ERR_ARG;
+    double t0 = snow_ms();
+    if (ctx->S == 0) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_upload: call sr2_set_species first");
+    if (B < 0 || !node_off || !costs || n_words < 1 || (B > 0 && (!left || !right || !leaf_species || !leaf_bits)))
+        return sr2_fail(ctx, SR2_ERR_ARG, "sr2_superdtl_upload: null array or n_words < 1");
+    if (ctx->S > 32767)
+        return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_superdtl_upload: more than 32767 species nodes");
+    if (index_base < 0 || index_base + B >= (1 << 24))
+        return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_superdtl_upload: instance numbers must stay below 2^24");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    sr2_free_super(ctx);
+    const int64_t N = B ? node_off[B] : 0;
+    const int S = ctx->S, W = n_words;
+    SuperProblem* p = new SuperProblem();
+    ctx->super = p;
+    p->flags = flags;
+    p->W = W;
+    p->index_base = index_base;
+    memcpy(p->costs, costs, sizeof(p->costs));
+
+    size_t free_b = 0, total_b = 0;
+    SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t per_row = (size_t)ctx->pitch * 16 + 1;
+    size_t fixed = (size_t)N * (4 * 9 + (size_t)W * 4 * 6 + (size_t)W * 128 + (size_t)S * 4) +
+                   (size_t)B * ((size_t)S * 4 + 32) + (64u << 20);
+    if (free_b < fixed + per_row * 4)
+        return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_superdtl_upload: batch does not fit in device memory");
+    int64_t rows_budget = (int64_t)(((free_b - fixed) / 10 * 9) / per_row);
+    int rc = sr2_build_rows(ctx, "sr2_superdtl_upload", B, node_off, left, right, leaf_species, rows_budget,
+                            (flags & SR2_KEEP_TABLES) != 0, true, &p->rows);
+    if (rc) return rc;
+    if (p->rows.chunks.size() > 1)
+        return sr2_fail(ctx, SR2_ERR_NOMEM,
+                        "sr2_superdtl_upload: batch does not fit in device memory (split it into smaller batches)");
+    if (p->rows.max_nodes > 65535)
+        return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_superdtl_upload: more than 65535 nodes in one object tree");
+    rc = sr2_check_costs(ctx, "sr2_superdtl_upload", costs, p->rows.max_nodes);
+    if (rc) return rc;
+
+    const int64_t R = p->rows.R;
+    // global-id child arrays for the per-instance kernels
+    std::vector<int32_t> gl(std::max<int64_t>(N, 1)), grt(std::max<int64_t>(N, 1));
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < B; ++b)
+        for (int64_t u = node_off[b]; u < node_off[b + 1]; ++u) {
+            gl[u] = left[u] < 0 ? -1 : (int32_t)(node_off[b] + left[u]);
+            grt[u] = right[u] < 0 ? -1 : (int32_t)(node_off[b] + right[u]);
+        }
+    auto alloc = [&](void** ptr, size_t bytes) { return cudaMalloc(ptr, std::max<size_t>(bytes, 16)); };
+    size_t nw = (size_t)N * W;
+    SR2_CUDA(ctx, alloc((void**)&p->d_left, (size_t)N * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_right, (size_t)N * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_node_off, (size_t)(B + 1) * 8));
+    SR2_CUDA(ctx, alloc((void**)&p->d_bits, nw * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_present, nw * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_outside, nw * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_gain, nw * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_L, nw * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_row_flags, (size_t)R));
+    SR2_CUDA(ctx, alloc((void**)&p->d_T, (size_t)R * 2 * ctx->pitch * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_tag, (size_t)R * 2 * ctx->pitch * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_dec, (size_t)N * S * 2));
+    SR2_CUDA(ctx, alloc((void**)&p->d_anc, (size_t)N * S * 2));
+    SR2_CUDA(ctx, alloc((void**)&p->d_tau, nw * 32 * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_taumin, (size_t)N * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_cost, (size_t)B * S * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_min_cost, (size_t)B * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_root_species, (size_t)B * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_map, (size_t)N * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_kind, (size_t)N * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_syn, nw * 4));
+    SR2_CUDA(ctx, alloc((void**)&p->d_best, 8));
+    cudaStream_t st = ctx->stream;
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_left, gl.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_right, grt.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_node_off, node_off, (size_t)(B + 1) * 8, cudaMemcpyHostToDevice, st));
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_bits, leaf_bits, nw * 4, cudaMemcpyHostToDevice, st));
+    SR2_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->timing.upload_ms = (float)(snow_ms() - t0);
+    return SR2_OK;
+}
+
+static int super_configure(sr2_ctx* ctx, SuperProblem* p) {
+    const int S = ctx->S;
+    p->spad = (S + 1) & ~1;
+    const size_t per_row = (size_t)12 * p->spad * sizeof(u64);
+    if (per_row > ctx->smem_optin)
+        return sr2_fail(ctx, SR2_ERR_RANGE, "superdtl: species tree too large for one CTA's shared memory");
+    if (S <= 256) {
+        p->cta_per_row = false;
+        p->wave_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx->smem_optin - 1024) / per_row));
+        p->wave_smem = per_row * p->wave_warps;
+        SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
+    } else {
+        p->cta_per_row = true;
+        p->wave_smem = per_row;
+        SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
+    }
+    return SR2_OK;
+}
+
+static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
+
+extern "C" int sr2_superdtl_solve(sr2_ctx* ctx) {
+    if (!ctx) return SR2_ERR_ARG;
+    SuperProblem* p = ctx->super;
+    if (!p) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_solve: nothing uploaded");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = super_configure(ctx, p);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream;
+    const RowLayout& rows = p->rows;
+    const RowChunk& c = rows.chunks[0];
+    const int H = c.height(), W = p->W, S = ctx->S;
+    const int64_t N = rows.N;
+    const int B = rows.B;
+    SuperCosts cs{p->costs[0], p->costs[1], p->costs[2], p->costs[3], p->costs[4]};
+    int n_launch = 0, n_waves = 0;
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    size_t nw = (size_t)N * W;
+    // ---- gain sets and lca sets ------------------------------------------------------
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_present, p->d_bits, nw * 4, cudaMemcpyDeviceToDevice, st));
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_L, p->d_bits, nw * 4, cudaMemcpyDeviceToDevice, st));
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_outside, 0, std::max<size_t>(nw * 4, 4), st));
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_tau, 0xff, std::max<size_t>(nw * 128, 4), st));
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_taumin, 0xff, std::max<size_t>((size_t)N * 4, 4), st));
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_best, 0xff, 8, st));
+    for (int h = 1; h <= H; ++h) {
+        int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+        if (n <= 0) continue;
+        syn_present_wave<<<grid_for(n * W, 256), 256, 0, st>>>(rows.row_node, rows.row_left, rows.row_right,
+                                                               c.wave_off[h], (int)n, W, p->d_present);
+        ++n_launch;
+    }
+    for (int h = H; h >= 1; --h) {
+        int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+        if (n <= 0) continue;
+        syn_outside_wave<<<grid_for(n * W, 256), 256, 0, st>>>(rows.row_node, rows.row_left, rows.row_right,
+                                                               c.wave_off[h], (int)n, W, p->d_present, p->d_outside);
+        ++n_launch;
+    }
+    if (N > 0) {
+        syn_gain_kernel<<<grid_for(N * W, 256), 256, 0, st>>>(p->d_left, p->d_right, N, W, p->d_present,
+                                                              p->d_outside, p->d_gain);
+        ++n_launch;
+    }
+    for (int h = 1; h <= H; ++h) {
+        int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+        if (n <= 0) continue;
+        syn_lca_wave<<<grid_for(n, 256), 256, 0, st>>>(rows.row_node, rows.row_left, rows.row_right, c.wave_off[h],
+                                                       (int)n, W, p->d_gain, p->d_L, p->d_row_flags);
+        ++n_launch;
+    }
+    // ---- the table ---------------------------------------------------------------------
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    for (int h = 1; h <= H; ++h) {
+        int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+        if (n <= 0) continue;
+        if (!p->cta_per_row) {
+            superdtl_wave_kernel<32><<<grid_for(n, p->wave_warps), p->wave_warps * 32, p->wave_smem, st>>>(
+                ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, c.wave_off[h], c.row_begin, (int)n, p->d_T,
+                p->d_tag, cs, p->spad);
+        } else {
+            superdtl_wave_kernel<256><<<(unsigned)n, 256, p->wave_smem, st>>>(
+                ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, c.wave_off[h], c.row_begin, (int)n, p->d_T,
+                p->d_tag, cs, p->spad);
+        }
+        ++n_launch;
+        ++n_waves;
+    }
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    SR2_CUDA(ctx, cudaGetLastError());
+    // ---- decode every root, cost(), selection --------------------------------------------
+    if (B > 0) {
+        sdecode_root_kernel<<<grid_for((int64_t)B * S, 256), 256, 0, st>>>(
+            ctx->dsp, rows.d_root_row, rows.d_root_node, 0, B, c.row_begin, p->d_tag, p->d_dec, p->d_anc);
+        ++n_launch;
+        for (int h = H; h >= 1; --h) {
+            int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+            if (n <= 0) continue;
+            sdecode_wave_kernel<<<grid_for(n * S, 256), 256, 0, st>>>(
+                ctx->dsp, rows.row_node, rows.row_left, rows.row_right, p->d_node_off, rows.d_node_inst,
+                rows.d_node_pre, c.wave_off[h], c.row_begin, (int)n, p->d_tag, W, p->d_gain, p->d_dec, p->d_anc,
+                p->d_tau, p->d_taumin);
+            ++n_launch;
+        }
+        scost_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
+            ctx->dsp, p->d_node_off, p->d_left, p->d_right, rows.d_node_pre, 0, B, W, p->d_L, p->d_tau, p->d_taumin,
+            p->d_dec, p->d_anc, cs, p->d_cost);
+        sselect_kernel<<<grid_for(B, 8), 256, 0, st>>>(ctx->dsp, 0, B, p->d_cost, p->d_dec, p->d_node_off,
+                                                       p->d_min_cost, p->d_root_species);
+        smaterialise_kernel<<<grid_for(N, 256), 256, 0, st>>>(
+            ctx->dsp, 0, N, rows.d_node_inst, p->d_node_off, rows.d_node_pre, p->d_root_species, W, p->d_L,
+            p->d_tau, p->d_taumin, p->d_dec, p->d_anc, p->d_map, p->d_kind, p->d_syn);
+        sbest_kernel<<<grid_for(B, 256), 256, 0, st>>>(B, p->index_base, p->d_min_cost, p->d_root_species,
+                                                       p->d_best);
+        n_launch += 4;
+    }
+    SR2_CUDA(ctx, cudaGetLastError());
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+    cudaEventElapsedTime(&ctx->timing.waves_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->timing.solve_ms, ctx->ev[0], ctx->ev[1]);
+    ctx->timing.n_waves = n_waves;
+    ctx->timing.n_launches = n_launch;
+    ctx->timing.n_cells = rows.R * (int64_t)S * 2;
+    p->solved = true;
+    return SR2_OK;
+}
+
+extern "C" int sr2_superdtl_results(sr2_ctx* ctx, int32_t* out_min_cost, int32_t* out_root_species,
+                                    int32_t* out_map_species, int32_t* out_map_kind, uint32_t* out_synteny_bits) {
+    if (!ctx) return SR2_ERR_ARG;
+    SuperProblem* p = ctx->super;
+    if (!p || !p->solved) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_results: solve first");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    double t0 = snow_ms();
+    cudaStream_t st = ctx->stream;
+    size_t B = p->rows.B, N = p->rows.N;
+    if (out_min_cost) SR2_CUDA(ctx, cudaMemcpyAsync(out_min_cost, p->d_min_cost, B * 4, cudaMemcpyDeviceToHost, st));
+    if (out_root_species)
+        SR2_CUDA(ctx, cudaMemcpyAsync(out_root_species, p->d_root_species, B * 4, cudaMemcpyDeviceToHost, st));
+    if (out_map_species) SR2_CUDA(ctx, cudaMemcpyAsync(out_map_species, p->d_map, N * 4, cudaMemcpyDeviceToHost, st));
+    if (out_map_kind) SR2_CUDA(ctx, cudaMemcpyAsync(out_map_kind, p->d_kind, N * 4, cudaMemcpyDeviceToHost, st));
+    if (out_synteny_bits)
+        SR2_CUDA(ctx, cudaMemcpyAsync(out_synteny_bits, p->d_syn, N * p->W * 4, cudaMemcpyDeviceToHost, st));
+    SR2_CUDA(ctx, cudaStreamSynchronize(st));
+    ctx->timing.results_ms = (float)(snow_ms() - t0);
+    return SR2_OK;
+}
+
+extern "C" int sr2_superdtl_best(sr2_ctx* ctx, int32_t* out_min_cost, int64_t* out_instance,
+                                 int32_t* out_root_species, uint64_t* out_key) {
+    if (!ctx) return SR2_ERR_ARG;
+    SuperProblem* p = ctx->super;
+    if (!p || !p->solved) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_best: solve first");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    unsigned long long key = 0;
+    SR2_CUDA(ctx, cudaMemcpyAsync(&key, p->d_best, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    bool none = key == SR2_KEY_NONE;
+    if (out_key) *out_key = key;
+    if (out_min_cost) *out_min_cost = none ? SR2_INF : (int32_t)(key >> 40);
+    if (out_instance) *out_instance = none ? -1 : (int64_t)((key >> 16) & 0xffffffu);
+    if (out_root_species) *out_root_species = none ? -1 : (int32_t)(key & 0xffffu);
+    return SR2_OK;
+}
+
+extern "C" int sr2_superdtl_result_one(sr2_ctx* ctx, int32_t instance, int32_t* out_map_species,
+                                       int32_t* out_map_kind, uint32_t* out_synteny_bits) {
+    if (!ctx) return SR2_ERR_ARG;
+    SuperProblem* p = ctx->super;
+    if (!p || !p->solved) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_result_one: solve first");
+    if (instance < 0 || instance >= p->rows.B)
+        return sr2_fail(ctx, SR2_ERR_ARG, "sr2_superdtl_result_one: bad instance");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    size_t off = p->rows.node_off[instance], G = p->rows.node_off[instance + 1] - off;
+    if (out_map_species)
+        SR2_CUDA(ctx, cudaMemcpyAsync(out_map_species, p->d_map + off, G * 4, cudaMemcpyDeviceToHost, st));
+    if (out_map_kind) SR2_CUDA(ctx, cudaMemcpyAsync(out_map_kind, p->d_kind + off, G * 4, cudaMemcpyDeviceToHost, st));
+    if (out_synteny_bits)
+        SR2_CUDA(ctx, cudaMemcpyAsync(out_synteny_bits, p->d_syn + off * p->W, G * p->W * 4, cudaMemcpyDeviceToHost, st));
+    SR2_CUDA(ctx, cudaStreamSynchronize(st));
+    return SR2_OK;
+}
+
+extern "C" int sr2_superdtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, const int32_t* left,
+                                const int32_t* right, const int32_t* leaf_species, int32_t n_words,
+                                const uint32_t* leaf_bits, const int32_t costs[5], uint32_t flags,
+                                int32_t* out_min_cost, int32_t* out_root_species, int32_t* out_map_species,
+                                int32_t* out_map_kind, uint32_t* out_synteny_bits) {
+    int rc = sr2_superdtl_upload(ctx, B, node_off, left, right, leaf_species, n_words, leaf_bits, costs, 0, flags);
+    if (rc) return rc;
+    rc = sr2_superdtl_solve(ctx);
+    if (rc) return rc;
+    return sr2_superdtl_results(ctx, out_min_cost, out_root_species, out_map_species, out_map_kind,
+                                out_synteny_bits);
+}
+
+extern "C" int sr2_superdtl_tables(sr2_ctx* ctx, int32_t instance, int32_t* out_value, int32_t* out_tag,
+                                   uint32_t* out_gain, uint32_t* out_lca) {
+    if (!ctx) return SR2_ERR_ARG;
+    SuperProblem* p = ctx->super;
+    if (!p || !p->solved) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_tables: solve first");
+    if (!(p->flags & SR2_KEEP_TABLES))
+        return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_tables: upload with SR2_KEEP_TABLES");
+    if (instance < 0 || instance >= p->rows.B) return sr2_fail(ctx, SR2_ERR_ARG, "sr2_superdtl_tables: bad instance");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int S = ctx->S, pitch = ctx->pitch, W = p->W;
+    int64_t off = p->rows.node_off[instance], G = p->rows.node_off[instance + 1] - off;
+    if (out_gain) SR2_CUDA(ctx, cudaMemcpy(out_gain, p->d_gain + off * W, (size_t)G * W * 4, cudaMemcpyDeviceToHost));
+    if (out_lca) SR2_CUDA(ctx, cudaMemcpy(out_lca, p->d_L + off * W, (size_t)G * W * 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> rowT(2 * pitch);
+    std::vector<uint32_t> rowG(2 * pitch);
+    for (int64_t u = 0; u < G && (out_value || out_tag); ++u) {
+        int64_t gr = p->rows.h_node_row[off + u];
+        int32_t* ov = out_value ? out_value + (size_t)u * S * 2 : nullptr;
+        int32_t* ot = out_tag ? out_tag + (size_t)u * S * 8 : nullptr;
+        if (gr < 0) {
+            for (int x = 0; x < S; ++x)
+                for (int k = 0; k < 2; ++k) {
+                    if (ov) ov[x * 2 + k] = (k == 0 && x == p->rows.h_leaf[off + u]) ? 0 : SR2_INF;
+                    if (ot)
+                        for (int j = 0; j < 4; ++j) ot[(x * 2 + k) * 4 + j] = -1;
+                }
+            continue;
+        }
+        SR2_CUDA(ctx, cudaMemcpy(rowT.data(), p->d_T + (size_t)gr * 2 * pitch, (size_t)pitch * 8, cudaMemcpyDeviceToHost));
+        SR2_CUDA(ctx, cudaMemcpy(rowG.data(), p->d_tag + (size_t)gr * 2 * pitch, (size_t)pitch * 8, cudaMemcpyDeviceToHost));
+        for (int x = 0; x < S; ++x)
+            for (int k = 0; k < 2; ++k) {
+                if (ov) ov[x * 2 + k] = rowT[k * pitch + x];
+                if (ot) {
+                    uint32_t t = rowG[k * pitch + x];
+                    bool none = t == SR2_NO_TAG;
+                    int32_t* o = ot + (x * 2 + k) * 4;
+                    o[0] = none ? -1 : (int32_t)((t & 0xffffu) >> 1);
+                    o[1] = none ? -1 : (int32_t)(t & 1u);
+                    o[2] = none ? -1 : (int32_t)((t >> 16) >> 1);
+                    o[3] = none ? -1 : (int32_t)((t >> 16) & 1u);
+                }
+            }
+    }
+    return SR2_OK;
 }
