@@ -158,8 +158,9 @@ def usreconcile_extended_uspfs_sharded(
     global_key = reduce_key(best_key) if reduce_key is not None else best_key
     if best is None or global_key != best_key:
         return set()
-    _, index, winner, objects, species, mapping, syn = best
+    _, index, winner, objects, _, mapping, syn = best
     winner.label_internal()
+    species = flatten_species(winner.species_lca.tree)  # each resolution re-parses its trees
     object_species = {node: species.nodes[int(mapping[u])] for u, node in enumerate(objects.nodes)}
     syntenies = {node: bits_to_families(syn[u], names) for u, node in enumerate(objects.nodes)}
     return {SuperReconciliationOutput(
