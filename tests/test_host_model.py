@@ -1,0 +1,109 @@
+"""Host-side model (no GPU): newick/JSON round trips, label_internal, resolution order,
+cost() -- against the fixtures produced by the unmodified reference."""
+import json
+
+import pytest
+
+from superrec2_b200.model.reconciliation import (
+    ReconciliationInput,
+    ReconciliationOutput,
+    SuperReconciliationInput,
+    SuperReconciliationOutput,
+)
+from superrec2_b200.model.synteny import sort_synteny
+from superrec2_b200.model.tree import Tree, TreeError
+from superrec2_b200.model.tree_mapping import get_species_mapping
+from superrec2_b200.utils.trees import LowestCommonAncestor, count_resolutions, is_binary
+
+
+def test_newick_roundtrip_with_nhx_and_odd_names():
+    text = ("((A b,(C+d,E)F g)H[&&NHX:color=0037DB],I-1)R;")
+    tree = Tree(text, format=1)
+    assert [n.name for n in tree.traverse()] == ["R", "H", "I-1", "A b", "F g", "C+d", "E"]
+    assert (tree & "H").color == "0037DB"
+    assert tree.write(format=8, format_root_node=True, features=["color"]) == text
+    assert tree.write(format=9) == "((A b,(C+d,E)),I-1);"
+    with pytest.raises(TreeError):
+        Tree("((a,b);", format=1)
+
+
+def test_multiline_newick_and_leaf_iteration():
+    tree = Tree("""
+        (
+            ((x_1,z_1)3,(w_1,w_2)4)2,
+            (y_1, t_1)5
+        )1;
+    """, format=1)
+    assert [leaf.name for leaf in tree] == ["x_1", "z_1", "w_1", "w_2", "y_1", "t_1"]
+    assert len(tree) == 6 and "4" in tree and "nope" not in tree
+
+
+def test_natural_sort_of_families():
+    assert sort_synteny({"10", "2", "3'", "3\"", "1", "11"}) == ["1", "2", "3\"", "3'", "10", "11"]
+    assert sort_synteny(["f10", "f2", "f1"]) == ["f1", "f2", "f10"]
+
+
+def test_species_mapping_from_names():
+    objects = Tree("((x_1,xy_2),Y_3,z);", format=1)
+    species = Tree("(X,(Y,X_Y)P);", format=1)
+    mapping = get_species_mapping(objects, species)
+    assert {k.name: v.name for k, v in mapping.items()} == {"x_1": "X", "Y_3": "Y"}
+
+
+def test_lca_queries():
+    tree = Tree("(((X,Y)XY,Z)XYZ,(W,T)WT)R;", format=1)
+    lca = LowestCommonAncestor(tree)
+    node = lambda name: tree & name  # noqa: E731
+    assert lca(node("X"), node("Z")) is node("XYZ")
+    assert lca(node("X"), node("Y"), node("T")) is tree
+    assert lca.is_ancestor_of(node("XYZ"), node("Y")) and lca.is_ancestor_of(node("Y"), node("Y"))
+    assert not lca.is_strict_ancestor_of(node("Y"), node("Y"))
+    assert lca.is_comparable(node("X"), node("XYZ")) and not lca.is_comparable(node("X"), node("W"))
+    assert lca.level(node("X")) == 3 and lca.distance(node("X"), node("W")) == 5
+
+
+def test_resolution_order_matches_reference_binarize(golden):
+    """Resolution number r of unrank_resolution == r-th element of the reference's binarize()."""
+    for fixture in golden("binarize.json.gz"):
+        data = {
+            "object_tree": fixture["object_tree"],
+            "species_tree": "(X,Y)R;",
+            "leaf_object_species": {leaf.name: "X" for leaf in Tree(fixture["object_tree"], format=1)},
+        }
+        rec_input = ReconciliationInput.from_dict(data)
+        assert rec_input.count_resolutions() == len(fixture["resolutions"])
+        got = []
+        for item in rec_input.binarize():
+            assert is_binary(item.object_tree)
+            item.label_internal()
+            got.append(item.object_tree.write(format=8, format_root_node=True))
+        assert got == fixture["resolutions"]
+    assert count_resolutions(Tree("((a,b,c,d,e),(f,g,h,i,j,k));", format=1)) == 105 * 945
+
+
+def test_cost_and_json_of_reference_results(golden):
+    """Re-reading the reference's output JSON gives the same JSON back and the same cost()."""
+    for fixture in golden("thl_small.json.gz") + golden("thl_medium.json.gz"):
+        if fixture.get("error"):
+            continue
+        out = ReconciliationOutput.from_dict(fixture["result"])
+        assert out.to_dict() == fixture["result"]
+        assert out.cost() == fixture["min_cost"]
+    for name in ("superdtl_small.json.gz", "superdtl_poly.json.gz", "crispr.json.gz"):
+        for fixture in golden(name):
+            out = SuperReconciliationOutput.from_dict(fixture["result"])
+            assert json.dumps(out.to_dict()) == json.dumps(fixture["result"])
+            assert out.cost() == fixture["min_cost"]
+
+
+def test_label_internal_skips_used_names():
+    data = {
+        "object_tree": "((a,b),(O0,c)O1);",
+        "species_tree": "(X,Y);",
+        "leaf_object_species": {"a": "X", "b": "X", "O0": "Y", "c": "Y"},
+        "leaf_syntenies": {"a": ["g"], "b": ["g"], "O0": ["g"], "c": ["g"]},
+    }
+    item = SuperReconciliationInput.from_dict(data)
+    item.label_internal()
+    assert item.object_tree.write() == "((a,b)O3,(O0,c)O1)O2;"
+    assert item.species_lca.tree.write() == "(X,Y)S0;"
