@@ -152,6 +152,29 @@ int sr2_superdtl_run(sr2_ctx* ctx, int32_t n_instances, const int64_t* node_off,
 int sr2_superdtl_tables(sr2_ctx* ctx, int32_t instance, int32_t* out_value, int32_t* out_tag,
                         uint32_t* out_gain, uint32_t* out_lca);
 
+/* ---- polytomy resolutions (ReconciliationInput.binarize) -------------------------
+ * The multifurcating object tree is given in CSR form: nodes 0..n_nodes-1 with the root
+ * at 0 and parents before children, children of v = child_idx[child_off[v] .. child_off[v+1])
+ * in order (0 or 2..16 children).  Resolution numbers follow the reference's enumeration
+ * order (model/reconciliation.py:161-190, utils/trees.py:377-446).
+ *
+ * sr2_resolutions_count : number of resolutions (capped at 2^40) and nodes of a resolved tree
+ * sr2_resolutions_tree  : resolution `index` as flat left/right arrays in the library's
+ *                         numbering; out_origin[id] = original node of leaves and of the roots
+ *                         of resolved polytomies, -1 for the joints created by the resolution
+ * sr2_resolutions_upload: unrank resolutions [first, first+count) and upload them as a
+ *                         superdtl batch with index_base = first (then sr2_superdtl_solve,
+ *                         sr2_superdtl_best, ...).  leaf_species / leaf_bits are indexed by the
+ *                         nodes of the multifurcating tree (internal entries ignored). */
+int sr2_resolutions_count(int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx,
+                          int64_t* out_count, int32_t* out_binary_nodes);
+int sr2_resolutions_tree(int32_t n_nodes, const int32_t* child_off, const int32_t* child_idx,
+                         int64_t index, int32_t* out_left, int32_t* out_right, int32_t* out_origin);
+int sr2_resolutions_upload(sr2_ctx* ctx, int32_t n_nodes, const int32_t* child_off,
+                           const int32_t* child_idx, const int32_t* leaf_species, int32_t n_words,
+                           const uint32_t* leaf_bits, const int32_t costs[5], int64_t first,
+                           int64_t count, uint32_t flags);
+
 /* ---- timing of the last solve (CUDA events on the context's stream) ------ */
 typedef struct sr2_timing {
     float upload_ms;     /* host prep + H2D of the last upload */

@@ -68,6 +68,10 @@ SIGNATURES = {
     "sr2_superdtl_run": (c_int, [c_void_p, c_int32, _I64P, _I32P, _I32P, _I32P, c_int32, _U32P, _I32P,
                                  c_uint32, _I32P, _I32P, _I32P, _I32P, _U32P]),
     "sr2_superdtl_tables": (c_int, [c_void_p, c_int32, _I32P, _I32P, _U32P, _U32P]),
+    "sr2_resolutions_count": (c_int, [c_int32, _I32P, _I32P, _I64P, _I32P]),
+    "sr2_resolutions_tree": (c_int, [c_int32, _I32P, _I32P, c_int64, _I32P, _I32P, _I32P]),
+    "sr2_resolutions_upload": (c_int, [c_void_p, c_int32, _I32P, _I32P, _I32P, c_int32, _U32P, _I32P,
+                                       c_int64, c_int64, c_uint32]),
     "sr2_last_timing": (c_int, [c_void_p, POINTER(Timing)]),
 }
 
@@ -253,10 +257,50 @@ class Context:
             lca.ctypes.data_as(_U32P)))
         return values, tags, gain, lca
 
+    def resolutions_upload(self, child_off, child_idx, leaf_species, leaf_bits, costs, first, count,
+                           flags=0):
+        """Unrank resolutions [first, first+count) of a multifurcating tree into a superdtl batch."""
+        child_off, child_idx = i32(child_off), i32(child_idx)
+        leaf_species, costs = i32(leaf_species), i32(costs)
+        leaf_bits = np.ascontiguousarray(leaf_bits, dtype=np.uint32).reshape(len(leaf_species), -1)
+        _, binary_nodes = resolutions_count(child_off, child_idx)
+        node_off = np.arange(count + 1, dtype=np.int64) * binary_nodes
+        self._sbatch = (count, int(node_off[-1]), leaf_bits.shape[1], node_off)
+        self._check(self._lib.sr2_resolutions_upload(
+            self._handle, len(child_off) - 1, p32(child_off), p32(child_idx), p32(leaf_species),
+            leaf_bits.shape[1], leaf_bits.ctypes.data_as(_U32P), p32(costs), first, count, flags))
+
     def timing(self) -> Timing:
         out = Timing()
         self._check(self._lib.sr2_last_timing(self._handle, ctypes.byref(out)))
         return out
+
+
+def resolutions_count(child_off, child_idx):
+    """(number of resolutions, nodes of one resolved tree) of a multifurcating tree (host only)."""
+    lib = load()
+    child_off, child_idx = i32(child_off), i32(child_idx)
+    count, nodes = c_int64(0), c_int32(0)
+    code = lib.sr2_resolutions_count(len(child_off) - 1, p32(child_off), p32(child_idx),
+                                     ctypes.byref(count), ctypes.byref(nodes))
+    if code:
+        raise Sr2Error(code, "malformed multifurcating tree")
+    return count.value, nodes.value
+
+
+def resolutions_tree(child_off, child_idx, index):
+    """(left, right, origin) of resolution ``index`` in the library's numbering (host only)."""
+    lib = load()
+    child_off, child_idx = i32(child_off), i32(child_idx)
+    _, nodes = resolutions_count(child_off, child_idx)
+    left = np.empty(nodes, np.int32)
+    right = np.empty(nodes, np.int32)
+    origin = np.empty(nodes, np.int32)
+    code = lib.sr2_resolutions_tree(len(child_off) - 1, p32(child_off), p32(child_idx), index,
+                                    p32(left), p32(right), p32(origin))
+    if code:
+        raise Sr2Error(code, "bad resolution index or tree")
+    return left, right, origin
 
 
 _contexts = {}

@@ -85,3 +85,32 @@ def flatten_objects(tree, leaf_object_species, species_rank) -> ObjectLayout:
             except KeyError:
                 raise KeyError(f"leaf {node.name!r} has no species in leaf_object_species") from None
     return ObjectLayout(nodes, index, left, right, leaf_species)
+
+
+@dataclass
+class PolytomyLayout:
+    """A (possibly multifurcating) object tree in the CSR form of ``sr2_resolutions_*``."""
+
+    nodes: List          # node objects in preorder
+    child_off: np.ndarray
+    child_idx: np.ndarray
+    leaf_species: np.ndarray
+
+
+def flatten_polytomies(tree, leaf_object_species, species_rank) -> PolytomyLayout:
+    nodes = []
+    stack = [tree]
+    while stack:
+        node = stack.pop()
+        nodes.append(node)
+        stack.extend(reversed(node.children))
+    index = {node: i for i, node in enumerate(nodes)}
+    child_off = np.zeros(len(nodes) + 1, np.int32)
+    child_idx = []
+    leaf_species = np.full(len(nodes), -1, np.int32)
+    for i, node in enumerate(nodes):
+        child_idx.extend(index[kid] for kid in node.children)
+        child_off[i + 1] = len(child_idx)
+        if not node.children:
+            leaf_species[i] = species_rank[leaf_object_species[node]]
+    return PolytomyLayout(nodes, child_off, np.asarray(child_idx, np.int32), leaf_species)

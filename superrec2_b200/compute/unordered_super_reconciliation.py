@@ -99,68 +99,81 @@ def usreconcile_extended_uspfs_sharded(
     reduce_key=None,
 ) -> Set[SuperReconciliationOutput]:
     """
-    ``usreconcile_extended_uspfs`` over the resolutions ``shard::n_shards`` ... in
-    contiguous blocks: shard ``i`` of ``n`` handles resolution numbers
-    ``[i*R/n, (i+1)*R/n)``.  ``reduce_key(key) -> key`` is the cross-shard
-    min-reduce of the packed ``(cost, resolution, root)`` key (an NCCL all-reduce
-    in ``superrec2_b200.dist``); the shard that owns the winning resolution
+    ``usreconcile_extended_uspfs`` restricted to one contiguous block of resolution
+    numbers: shard ``i`` of ``n`` handles ``[i*R/n, (i+1)*R/n)``.  ``reduce_key(key) -> key``
+    is the cross-shard min-reduce of the packed ``(cost, resolution, root)`` key (an NCCL
+    all-reduce in ``superrec2_b200.dist``); the shard that owns the winning resolution
     returns the solution, the others return an empty set.
     """
     if policy is not RetentionPolicy.ANY:
         raise NotImplementedError(
             "only RetentionPolicy.ANY is implemented on the GPU path so far "
             "(SURVEY.md section 8f item 1)")
+    from ..utils.trees import count_resolutions, is_binary
     total = srec_input.count_resolutions()
     lo, hi = total * shard // n_shards, total * (shard + 1) // n_shards
     costs = cost_vector(srec_input.costs)
     ctx = _lib.default_context(device)
     families = family_index(srec_input.leaf_syntenies)
     names = list(families)
-    n_species_res = 1
-    from ..utils.trees import count_resolutions
-    n_species_res = count_resolutions(srec_input.species_lca.tree)
+    no_key = (1 << 64) - 1
+    best_key = no_key
 
-    best_key = (1 << 64) - 1
-    best = None   # (key, resolution index, mapping, kind, syn)
-    start = lo
-    while start < hi:
-        # resolutions are object-major: a run with one species resolution shares the species tree
-        stop = min(hi, start + RESOLUTION_BATCH, (start // n_species_res + 1) * n_species_res
-                   if n_species_res > 1 else hi)
-        if n_species_res > 1:
-            stop = start + 1  # species polytomies: one (object, species) pair per batch
-        inputs = [srec_input.resolution(index) for index in range(start, stop)]
-        species = flatten_species(inputs[0].species_lca.tree)
-        layouts = []
-        for item in inputs:
-            rank = species.rank if item.species_lca is inputs[0].species_lca else \
-                flatten_species(item.species_lca.tree).rank
-            objects = flatten_objects(item.object_tree, item.leaf_object_species, rank)
-            layouts.append((objects, leaf_bitsets(objects.nodes, item.leaf_syntenies, families)))
-        node_off = np.zeros(len(layouts) + 1, np.int64)
-        np.cumsum([len(objects.nodes) for objects, _ in layouts], out=node_off[1:])
+    if is_binary(srec_input.species_lca.tree):
+        # one species tree for every resolution: unranking happens inside the library
+        species = flatten_species(srec_input.species_lca.tree)
         ctx.set_species(species.parent, species.child0, species.child1)
-        ctx.superdtl_upload(
-            node_off,
-            np.concatenate([objects.left for objects, _ in layouts]),
-            np.concatenate([objects.right for objects, _ in layouts]),
-            np.concatenate([objects.leaf_species for objects, _ in layouts]),
-            np.concatenate([bits for _, bits in layouts]),
-            costs, index_base=start)
-        ctx.superdtl_solve()
-        cost, index, root, key = ctx.superdtl_best()
-        if index >= 0 and key < best_key:
-            best_key = key
-            mapping, kind, syn = ctx.superdtl_result_one(index - start)
-            best = (key, index, inputs[index - start], layouts[index - start][0], species, mapping, syn)
-        start = stop
+        if total == 1:
+            if hi > lo:
+                _, objects, _, bits = flatten_super(srec_input, species, families)
+                ctx.superdtl_upload([0, len(objects.nodes)], objects.left, objects.right,
+                                    objects.leaf_species, bits, costs)
+                ctx.superdtl_solve()
+                best_key = ctx.superdtl_best()[3]
+        else:
+            from .flatten import flatten_polytomies
+            poly = flatten_polytomies(srec_input.object_tree, srec_input.leaf_object_species,
+                                      species.rank)
+            bits = leaf_bitsets(poly.nodes, srec_input.leaf_syntenies, families)
+            start, step = lo, max(1, hi - lo)
+            while start < hi:
+                count = min(step, hi - start)
+                try:
+                    ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits,
+                                           costs, start, count)
+                except _lib.Sr2Error as err:
+                    if err.code != -4 or count == 1:   # SR2_ERR_NOMEM: halve the batch
+                        raise
+                    step = (count + 1) // 2
+                    continue
+                ctx.superdtl_solve()
+                best_key = min(best_key, ctx.superdtl_best()[3])
+                start += count
+    else:
+        # species polytomies: each (object, species) resolution pair has its own species tree
+        for index in range(lo, hi):
+            item = srec_input.resolution(index)
+            species, objects, _, bits = flatten_super(item, None, families)
+            ctx.set_species(species.parent, species.child0, species.child1)
+            ctx.superdtl_upload([0, len(objects.nodes)], objects.left, objects.right,
+                                objects.leaf_species, bits, costs, index_base=index)
+            ctx.superdtl_solve()
+            best_key = min(best_key, ctx.superdtl_best()[3])
 
     global_key = reduce_key(best_key) if reduce_key is not None else best_key
-    if best is None or global_key != best_key:
+    if global_key == no_key or global_key != best_key:
         return set()
-    _, index, winner, objects, _, mapping, syn = best
+    # materialise the winner: rebuild that one resolution exactly as the reference does
+    # (re-parsed trees, O#/S# labels) and decode it in its own preorder numbering
+    index = (global_key >> 16) & 0xFFFFFF
+    winner = srec_input.resolution(index)
     winner.label_internal()
-    species = flatten_species(winner.species_lca.tree)  # each resolution re-parses its trees
+    species, objects, _, bits = flatten_super(winner, None, families)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    min_cost, root, mapping, _, syn = ctx.superdtl_run(
+        [0, len(objects.nodes)], objects.left, objects.right, objects.leaf_species, bits, costs)
+    if (int(min_cost[0]), int(root[0])) != (global_key >> 40, global_key & 0xFFFF):
+        raise _lib.Sr2Error(-5, "winning resolution does not reproduce its key")
     object_species = {node: species.nodes[int(mapping[u])] for u, node in enumerate(objects.nodes)}
     syntenies = {node: bits_to_families(syn[u], names) for u, node in enumerate(objects.nodes)}
     return {SuperReconciliationOutput(

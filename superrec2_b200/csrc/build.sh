@@ -7,6 +7,6 @@ nvcc -O3 -std=c++17 -lineinfo \
   -gencode arch=compute_100a,code=sm_100a \
   -Xcompiler -fPIC,-fopenmp,-Wall,-Wno-unknown-pragmas \
   ${SR2_NVCC_EXTRA:-} \
-  -shared -o "$out" "$here"/sr2_context.cu "$here"/sr2_rows.cu "$here"/sr2_dtl.cu "$here"/sr2_superdtl.cu \
+  -shared -o "$out" "$here"/sr2_context.cu "$here"/sr2_rows.cu "$here"/sr2_dtl.cu "$here"/sr2_superdtl.cu "$here"/sr2_resolve.cu \
   -lgomp -lcudart_static -ldl -lrt -lpthread
 echo "built $out"

@@ -203,3 +203,57 @@ def make_batch(n_species_leaves: int, n_object_leaves: int, batch: int, seed: in
         result.leaf_family_bits = bits.reshape(-1, words)
         result.n_families = n_families
     return result
+
+
+def make_polytomy_input(n_species_leaves: int = 30, arities=(5, 6), subtree_leaves: int = 3,
+                        n_families: int = 32, seed: int = 5000, costs=(0, 1, 1, 1, 1)) -> Dict:
+    """
+    BASELINE config #5: a binary root over one node per entry of
+    ``arities``; every child of those nodes is a ``subtree_leaves``-leaf random-join subtree.
+    The defaults give 33 leaves and 105 x 945 = 99,225 binary resolutions.  Returned in the
+    reference's input JSON form (only leaves are named, as in data/crispr-class1.in.json).
+    """
+    species = make_batch(n_species_leaves, n_species_leaves, 1, seed)
+    rng = np.random.default_rng(seed + 1)
+    n_sub = sum(arities)
+    subs_left, subs_right = random_join_batch(subtree_leaves, n_sub, seed + 1)
+    leaf_counter = 0
+    leaf_names: List[str] = []
+
+    def subtree_newick(k):
+        nonlocal leaf_counter
+        size = 2 * subtree_leaves - 1
+        names = [""] * size
+        for u in range(size):
+            if subs_left[k][u] < 0:
+                names[u] = f"g{leaf_counter}"
+                leaf_names.append(names[u])
+                leaf_counter += 1
+        return to_newick(subs_left[k], subs_right[k], names)[:-1]
+
+    groups, k = [], 0
+    for arity in arities:
+        groups.append("(" + ",".join(subtree_newick(k + i) for i in range(arity)) + ")")
+        k += arity
+    if len(groups) != 2:
+        raise ValueError("the root is binary: give exactly two arities")
+    object_tree = "(" + ",".join(groups) + ");"
+    species_leaves = [species.species_names[r] for r in np.flatnonzero(species.child0 < 0)]
+    perm = list(rng.permutation(len(species_leaves)))
+    leaf_map = {}
+    for i, name in enumerate(leaf_names):
+        pick = perm[i] if i < len(perm) else int(rng.integers(0, len(species_leaves)))
+        leaf_map[name] = species_leaves[pick]
+    syn = {}
+    for name in leaf_names:
+        keep = [f"f{f}" for f in range(n_families) if rng.random() < 0.6]
+        syn[name] = keep or [f"f{int(rng.integers(0, n_families))}"]
+    return {
+        "object_tree": object_tree,
+        "species_tree": to_newick(species.child0, species.child1, species.species_names),
+        "leaf_object_species": leaf_map,
+        "leaf_syntenies": syn,
+        "costs": dict(zip(
+            ["SPECIATION", "DUPLICATION", "HORIZONTAL_TRANSFER", "FULL_LOSS", "SEGMENTAL_LOSS"],
+            (int(c) for c in costs))),
+    }

@@ -107,3 +107,34 @@ def test_label_internal_skips_used_names():
     item.label_internal()
     assert item.object_tree.write() == "((a,b)O3,(O0,c)O1)O2;"
     assert item.species_lca.tree.write() == "(X,Y)S0;"
+
+
+def test_library_unranking_equals_host_unranking(golden):
+    """sr2_resolutions_tree (C++, what the GPU batches are built from) builds the same trees,
+    with the same child order, as the Python unranker that is pinned to the reference order."""
+    from superrec2_b200 import _lib
+    from superrec2_b200.compute.flatten import flatten_polytomies
+    from superrec2_b200.utils.trees import unrank_resolution
+
+    def nested_host(node):
+        return node.name if node.is_leaf() else tuple(nested_host(kid) for kid in node.children)
+
+    def nested_lib(left, right, origin, names, at=0):
+        if left[at] < 0:
+            return names[origin[at]]
+        return (nested_lib(left, right, origin, names, left[at]),
+                nested_lib(left, right, origin, names, right[at]))
+
+    trees = [f["object_tree"] for f in golden("binarize.json.gz")] + ["((a,b,c,d,e)p,(f,g,h)q,(i,j));"]
+    for newick in trees:
+        tree = Tree(newick, format=1)
+        layout = flatten_polytomies(tree, {leaf: 0 for leaf in tree}, {0: 0})
+        names = [node.name for node in layout.nodes]
+        total, binary_nodes = _lib.resolutions_count(layout.child_off, layout.child_idx)
+        assert total == count_resolutions(tree) and binary_nodes == 2 * len(tree) - 1
+        step = max(1, total // 400)
+        for index in list(range(0, total, step)) + [total - 1]:
+            left, right, origin = _lib.resolutions_tree(layout.child_off, layout.child_idx, index)
+            assert nested_lib(left, right, origin, names) == nested_host(unrank_resolution(tree, index))
+            # ABI numbering rule: parents before children
+            assert all(left[u] < 0 or (left[u] > u and right[u] > u) for u in range(len(left)))

@@ -109,3 +109,80 @@ def test_best_key_orders_by_cost_then_instance(ctx):
     first = int(np.flatnonzero(min_cost == min_cost.min())[0])
     assert (cost, index, root_species) == (int(min_cost.min()), 1000 + first, int(root[first]))
     assert key == (cost << 40) | (index << 16) | root_species
+
+
+# ------------------------------------------------------------------ resolutions at scale
+def _poly_setup(ctx, data):
+    from superrec2_b200.compute.flatten import flatten_polytomies, flatten_species
+    from superrec2_b200.compute.reconciliation import cost_vector
+    from superrec2_b200.compute.unordered_super_reconciliation import family_index, leaf_bitsets
+    srec_input = SuperReconciliationInput.from_dict(data)
+    species = flatten_species(srec_input.species_lca.tree)
+    poly = flatten_polytomies(srec_input.object_tree, srec_input.leaf_object_species, species.rank)
+    families = family_index(srec_input.leaf_syntenies)
+    bits = leaf_bitsets(poly.nodes, srec_input.leaf_syntenies, families)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    return srec_input, species, poly, bits, cost_vector(srec_input.costs)
+
+
+def test_resolution_batches_against_oracle_per_resolution(ctx):
+    """A 7,875-resolution input (5-ary x 4-ary... of 2-leaf subtrees): every 37th resolution is
+    re-solved alone by the CPU oracle through the host-side unranker (pinned to the reference's
+    enumeration order) and must give the same (cost, root) as the library-side unranked batch."""
+    data = synth.make_polytomy_input(8, (5, 4), 2, 6, seed=77)
+    srec_input, species, poly, bits, costs = _poly_setup(ctx, data)
+    total = srec_input.count_resolutions()
+    assert total == 105 * 15
+    ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits, costs, 0, total)
+    ctx.superdtl_solve()
+    min_cost, root, *_ = ctx.superdtl_results()
+    for index in list(range(0, total, 37)) + [total - 1]:
+        flat = FlatSuper(srec_input.resolution(index))
+        ref = oracle.superdtl(*flat.species_args, *flat.object_args, flat.leaf_bits, flat.costs, tables=False)
+        assert (min_cost[index], root[index]) == (ref["min_cost"], ref["root_species"]), index
+    cost, index, root_species, key = ctx.superdtl_best()
+    first = int(np.flatnonzero(min_cost == min_cost.min())[0])
+    assert (cost, index, root_species) == (int(min_cost.min()), first, int(root[first]))
+
+
+def test_sharded_ranges_agree_with_single_range(ctx):
+    """Sharding property: min over shards of the per-shard key == key of the unsharded run, for
+    2, 3 and 8 shards (what the NCCL min-reduce computes across GPUs)."""
+    from superrec2_b200.dist import shard_range
+    data = synth.make_polytomy_input(10, (4, 5), 2, 8, seed=5)
+    srec_input, species, poly, bits, costs = _poly_setup(ctx, data)
+    total = srec_input.count_resolutions()
+    ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits, costs, 0, total)
+    ctx.superdtl_solve()
+    whole = ctx.superdtl_best()[3]
+    for world in (2, 3, 8):
+        keys = []
+        for rank in range(world):
+            lo, hi = shard_range(total, rank, world)
+            ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits, costs, lo, hi - lo)
+            ctx.superdtl_solve()
+            keys.append(ctx.superdtl_best()[3])
+        assert min(keys) == whole
+
+
+def test_config5_full_enumeration_properties(ctx):
+    """BASELINE config #5: 99,225 resolutions of a 33-leaf tree, 59 species, 32 families.  Too many
+    for the oracle, so: the entry point's answer must (1) have the cost the host-side cost()
+    computes from the returned mapping and syntenies, (2) be the resolution the packed key names,
+    (3) be reproduced by the oracle on that one resolution, and (4) a sample of other resolutions
+    must not beat it."""
+    data = synth.make_polytomy_input()
+    srec_input = SuperReconciliationInput.from_dict(data)
+    assert srec_input.count_resolutions() == 99225
+    (result,) = usreconcile_extended_uspfs(srec_input, RetentionPolicy.ANY)
+    best_cost = result.cost()
+    flat = FlatSuper(result.input)
+    ref = oracle.superdtl(*flat.species_args, *flat.object_args, flat.leaf_bits, flat.costs, tables=False)
+    assert ref["min_cost"] == best_cost
+    assert flat.result_dict(ref["mapping"], ref["syn"]) == result.to_dict()
+    rng = np.random.default_rng(0)
+    for index in rng.integers(0, 99225, 40):
+        other = FlatSuper(srec_input.resolution(int(index)))
+        out = oracle.superdtl(*other.species_args, *other.object_args, other.leaf_bits, other.costs,
+                              tables=False)
+        assert out["min_cost"] >= best_cost
