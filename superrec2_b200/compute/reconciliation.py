@@ -7,7 +7,6 @@ selection by ``cost()`` and the traceback run in ``libsr2.so``
 (``csrc/sr2_dtl.cu``); this module only flattens the trees and rebuilds the
 ``ReconciliationOutput``.
 """
-from __future__ import annotations
 
 from typing import List, Sequence, Set
 

@@ -7,7 +7,6 @@ Syntenies travel to the device as bitsets: bit *i* of a node's words is the
 (``model/synteny.py:21-33``), so a bitset reads back directly as the sorted list
 the reference stores in its output.
 """
-from __future__ import annotations
 
 from typing import Dict, Iterable, List
 

@@ -138,3 +138,17 @@ def test_library_unranking_equals_host_unranking(golden):
             assert nested_lib(left, right, origin, names) == nested_host(unrank_resolution(tree, index))
             # ABI numbering rule: parents before children
             assert all(left[u] < 0 or (left[u] > u and right[u] > u) for u in range(len(left)))
+
+
+def test_entry_point_signatures_satisfy_the_cli_introspection():
+    """cli/reconcile.py:79-100 of the reference compares the ANNOTATIONS of the callable with the
+    input class and RetentionPolicy and dedents its docstring: they must be real objects."""
+    import inspect
+    from superrec2_b200.compute.reconciliation import reconcile_thl
+    from superrec2_b200.compute.unordered_super_reconciliation import usreconcile_extended_uspfs
+    from superrec2_b200.utils.dynamic_programming import RetentionPolicy
+    for fn, cls in ((reconcile_thl, ReconciliationInput), (usreconcile_extended_uspfs, SuperReconciliationInput)):
+        params = list(inspect.signature(fn).parameters.values())
+        assert len(params) == 2
+        assert params[0].annotation is cls and params[1].annotation is RetentionPolicy
+        assert fn.__doc__ and fn.__doc__.strip()
