@@ -21,6 +21,7 @@
 // (reconciliation.py:97-108,153-183), so cell values depend on that tie-break.
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <omp.h>
 
@@ -46,6 +47,13 @@ struct DtlProblem {
     int spad = 0, wave_warps = 0;
     size_t wave_smem = 0;
     bool cta_per_row = false;
+    // SIMD-across-rows kernel for big waves (32-bit keys)
+    bool simd_ok = false;
+    size_t simd_smem = 0;
+    int rank_bits = 0, depth_bits = 0;
+    int64_t max_finite = 0;
+    int64_t simd_min_rows = 0;
+    int simd_arr_words = 0, simd_thresh = 0;
 };
 
 void sr2_free_dtl(sr2_ctx* ctx) {
@@ -210,6 +218,197 @@ dtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// Wave 1: rows whose two children are leaves ("cherries").  Every cell has a closed
+// form: with the children at species a and b, each SUBMIN/SEPMIN key is either
+// (0, a|b) or infinite, so the five candidates reduce to interval tests.  One warp
+// per row, lanes over species, fully coalesced stores.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dtl_cherry_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                  int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
+                  uint32_t* __restrict__ tags, DtlCosts cs) {
+    int local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (local >= n_rows) return;
+    const int64_t gr = row_begin + local;
+    const size_t slot = (size_t)(gr - chunk_row0);
+    const int a = -1 - row_cl[gr], b = -1 - row_cr[gr];
+    const int ta = __ldg(sp.tin + a), oa = __ldg(sp.tout + a), da = __ldg(sp.depth + a);
+    const int tb = __ldg(sp.tin + b), ob = __ldg(sp.tout + b), db = __ldg(sp.depth + b);
+    const unsigned tag_ab = (unsigned)a | ((unsigned)b << 16);
+    int32_t* __restrict__ Tout = T + slot * sp.pitch;
+    uint32_t* __restrict__ Gout = tags + slot * sp.pitch;
+    for (int x = lane; x < sp.S; x += 32) {
+        int tx = __ldg(sp.tin + x), ox = __ldg(sp.tout + x), dx = __ldg(sp.depth + x);
+        int cx = __ldg(sp.child0 + x);
+        bool in_a = tx <= ta && ta < ox, in_b = tx <= tb && tb < ox;
+        int best = SR2_INF;
+        if (cx >= 0 && in_a && in_b && ta > tx && tb > tx) {
+            int t1 = __ldg(sp.tin + cx + 1);  // subtree(cx) = [tx+1, t1), subtree(cx+1) = [t1, ox)
+            if ((ta < t1) != (tb < t1)) best = cs.loss * (da + db - 2 * dx - 2);  // candidates 1 / 2
+        }
+        if (in_a && in_b) {  // 3. duplication
+            int v = cs.dup + cs.loss * (da + db - 2 * dx);
+            if (v < best) best = v;
+        }
+        bool sep_a = !in_a && !(ta <= tx && tx < oa), sep_b = !in_b && !(tb <= tx && tx < ob);
+        if (sep_a && in_b) {  // 4. left child transferred
+            int v = cs.hgt + cs.loss * (db - dx);
+            if (v < best) best = v;
+        }
+        if (in_a && sep_b) {  // 5. right child transferred
+            int v = cs.hgt + cs.loss * (da - dx);
+            if (v < best) best = v;
+        }
+        Tout[x] = best;
+        Gout[x] = best < SR2_INF ? tag_ab : SR2_NO_TAG;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Batched waves: SIMD across rows.  A CTA owns 16 rows of the wave; lane = (row j,
+// half h).  All lanes of a warp work on the SAME species node (two sibling cells, or the
+// l / r child row of one node), so species-tree look-ups are warp-uniform, every lane is
+// busy and no lane ever waits for another row.  The 16 x |S| slot arrays and the output
+// staging live in shared memory, transposed ([species][row], XOR-swizzled) so that both
+// the compute phase (fixed species, 16 rows) and the coalesced row loads / stores (fixed
+// row, 32 species) are free of bank conflicts.  Keys are 32 bits:
+//   value[31:sh] | rank[sh-1:db] | depth[db-1:0]
+// which the host only selects when every finite table value fits the value field.
+// ---------------------------------------------------------------------------
+struct Key32 {
+    int sh, db;            // value shift (= rank bits + depth bits), depth bits
+    unsigned rm, dm;       // rank mask (after >> db), depth mask
+    unsigned inf32;        // the infinite value: top bit of the value field
+    int thresh;            // sums below this are finite (inf32 minus the largest correction)
+};
+
+#define SIMD_ROWS 16
+#define SIMD_LD 17  // row stride in words: odd, so transposed row loads/stores hit 32 banks
+__device__ __forceinline__ int simd_at(int y, int j) { return y * SIMD_LD + j; }
+
+// value + loss * depth of a key: what a candidate adds for a child placed at that key
+__device__ __forceinline__ int key_q(unsigned k, int loss, const Key32& kp) {
+    return (int)(k >> kp.sh) + loss * (int)(k & kp.dm);
+}
+
+__global__ void __launch_bounds__(512, 2)
+dtl_wave_simd16_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                       int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
+                       uint32_t* __restrict__ tags, DtlCosts cs, int arr_words, Key32 kp) {
+    extern __shared__ unsigned smem32[];
+    const int S = sp.S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int j = lane & 15, h = lane >> 4;
+    // four arrays of arr_words (a multiple of 32); SR and OG are shifted by 16 words so that the
+    // two halves of a warp (same species, other array) use opposite halves of the 32 banks
+    unsigned* SL = smem32;
+    unsigned* SR = smem32 + arr_words + 16;
+    unsigned* OT = smem32 + 2 * arr_words + 32;
+    unsigned* OG = smem32 + 3 * arr_words + 48;
+    const int row0 = blockIdx.x * SIMD_ROWS;
+    const int rows_here = min(SIMD_ROWS, n_rows - row0);
+
+    // ---- load: 32 (row, side) child rows, transposed into the slot arrays ----------------
+    for (int pair = warp; pair < 2 * SIMD_ROWS; pair += nwarps) {
+        int jj = pair >> 1, side = pair & 1;
+        int64_t gr = row_begin + row0 + min(jj, rows_here - 1);  // pad the last group with a copy
+        int c = side ? row_cr[gr] : row_cl[gr];
+        unsigned* dst = (side ? SR : SL) + jj;
+        const int32_t* __restrict__ src = c >= 0 ? T + (size_t)c * sp.pitch : nullptr;
+        for (int y = lane; y < S; y += 32) {
+            int v = src ? src[y] : (y == -1 - c ? 0 : SR2_INF);
+            unsigned val = v >= SR2_INF ? kp.inf32 : (unsigned)v;
+            dst[y * SIMD_LD] = (val << kp.sh) | ((unsigned)y << kp.db) | (unsigned)__ldg(sp.depth + y);
+        }
+    }
+    __syncthreads();
+
+    // ---- up-sweep: half 0 sweeps the left-child array, half 1 the right-child array -------
+    {
+        unsigned* arr = (h ? SR : SL) + j;
+        for (int d = sp.D - 2; d >= 0; --d) {
+            int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
+            for (int i = b + warp; i < e; i += nwarps) {
+                int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+                unsigned k = min(arr[p * SIMD_LD], min(arr[c * SIMD_LD], arr[(c + 1) * SIMD_LD]));
+                arr[p * SIMD_LD] = k;
+            }
+            __syncthreads();
+        }
+    }
+
+    const int loss = cs.loss;
+    const int NONE = 0x7fffffff;
+    // ---- down-sweep: a warp takes one internal species p; its halves finish the two sibling
+    //      cells x = c + h and leave P[x] in the slots for the next level.  The root cell is
+    //      folded in as iteration -1 of level 0 (half 0 of warp 0). ----------------------------
+    for (int d = -1; d < sp.D - 1; ++d) {
+        int b = d < 0 ? 0 : __ldg(sp.int_lvl_off + d), e = d < 0 ? 1 : __ldg(sp.int_lvl_off + d + 1);
+        const int dx = d + 1;
+        for (int i = b + warp; i < e; i += nwarps) {
+            int x, cx;
+            unsigned Ml, Mr, Pl, Pr;
+            if (d < 0) {
+                if (h) break;  // only half 0 of warp 0 handles the root
+                x = 0;
+                Ml = SL[simd_at(0, j)];
+                Mr = SR[simd_at(0, j)];
+                Pl = Pr = 0xffffffffu;  // nothing is incomparable to the root
+            } else {
+                int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+                x = c + h;
+                unsigned Ppl = SL[simd_at(p, j)], Ppr = SR[simd_at(p, j)];
+                Ml = SL[simd_at(x, j)];
+                Mr = SR[simd_at(x, j)];
+                unsigned sibl = SL[simd_at(c + 1 - h, j)], sibr = SR[simd_at(c + 1 - h, j)];
+                Pl = min(Ppl, sibl);
+                Pr = min(Ppr, sibr);
+            }
+            cx = __ldg(sp.child0 + x);
+            const int qMl = key_q(Ml, loss, kp), qMr = key_q(Mr, loss, kp);
+            int w1 = NONE, w2 = NONE, w4 = NONE, w5 = NONE;
+            unsigned l0 = 0, l1 = 0, r0 = 0, r1 = 0;
+            if (cx >= 0) {
+                l0 = SL[simd_at(cx, j)];
+                l1 = SL[simd_at(cx + 1, j)];
+                r0 = SR[simd_at(cx, j)];
+                r1 = SR[simd_at(cx + 1, j)];
+                int b12 = -2 * loss * (dx + 1);
+                w1 = ((key_q(l0, loss, kp) + key_q(r1, loss, kp) + b12) << 3) | 0;   // 1. spe, l|r
+                w2 = ((key_q(l1, loss, kp) + key_q(r0, loss, kp) + b12) << 3) | 1;   // 2. spe, r|l
+            }
+            int w3 = ((qMl + qMr + cs.dup - 2 * loss * dx) << 3) | 2;                  // 3. dup
+            if (d >= 0) {
+                w4 = (((int)(Pl >> kp.sh) + qMr + cs.hgt - loss * dx) << 3) | 3;       // 4. hgt, left away
+                w5 = ((qMl + (int)(Pr >> kp.sh) + cs.hgt - loss * dx) << 3) | 4;       // 5. hgt, right away
+            }
+            int w = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
+            int best = w >> 3, which = w & 7;
+            unsigned ka = which == 0 ? l0 : which == 1 ? l1 : which == 3 ? Pl : Ml;
+            unsigned kb = which == 0 ? r1 : which == 1 ? r0 : which == 4 ? Pr : Mr;
+            bool finite = best < kp.thresh;
+            OT[simd_at(x, j)] = finite ? (unsigned)best : (unsigned)SR2_INF;
+            OG[simd_at(x, j)] =
+                finite ? (((ka >> kp.db) & kp.rm) | (((kb >> kp.db) & kp.rm) << 16)) : SR2_NO_TAG;
+            SL[simd_at(x, j)] = Pl;
+            SR[simd_at(x, j)] = Pr;
+        }
+        __syncthreads();
+    }
+
+    // ---- store: rows back to global memory, coalesced -----------------------------------------
+    for (int pair = warp; pair < 2 * rows_here; pair += nwarps) {
+        int jj = pair >> 1, which = pair & 1;
+        size_t slot = (size_t)(row_begin + row0 + jj - chunk_row0);
+        const unsigned* src = (which ? OG : OT) + jj;
+        unsigned* dst = which ? tags + slot * sp.pitch : reinterpret_cast<unsigned*>(T) + slot * sp.pitch;
+        for (int y = lane; y < S; y += 32) dst[y] = src[y * SIMD_LD];
+    }
+}
+
 // Event cost of node (x; children at a, b) as ReconciliationOutput.cost() sees it
 // (/root/reference/src/superrec2/model/reconciliation.py:273-365).  SR2_INF = INVALID.
 __device__ __forceinline__ int dtl_event_cost(const DevSpecies& sp, int x, int a, int b,
@@ -338,7 +537,8 @@ static double now_ms() {
     return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
-int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64_t max_nodes) {
+int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64_t max_nodes,
+                    int64_t* out_bound) {
     for (int k = 0; k < 5; ++k)
         if (costs[k] < 0 || costs[k] > (1 << 20))
             return sr2_fail(ctx, SR2_ERR_RANGE, std::string(who) + ": event costs must be integers in [0, 2^20]");
@@ -347,6 +547,7 @@ int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64
                  2 * (int64_t)costs[4];
     if (max_nodes * ev >= (1 << 29))
         return sr2_fail(ctx, SR2_ERR_RANGE, std::string(who) + ": costs x tree size may overflow the int32 DP table");
+    if (out_bound) *out_bound = max_nodes * ev;
     return SR2_OK;
 }
 
@@ -380,7 +581,7 @@ extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
     int rc = sr2_build_rows(ctx, "sr2_dtl_upload", B, node_off, left, right, leaf_species, rows_budget,
                             (flags & SR2_KEEP_TABLES) != 0, false, &p->rows);
     if (rc) return rc;
-    rc = sr2_check_costs(ctx, "sr2_dtl_upload", costs, p->rows.max_nodes);
+    rc = sr2_check_costs(ctx, "sr2_dtl_upload", costs, p->rows.max_nodes, &p->max_finite);
     if (rc) return rc;
     if ((flags & SR2_KEEP_TABLES) && p->rows.chunks.size() > 1)
         return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: SR2_KEEP_TABLES needs the batch to fit in one chunk");
@@ -418,9 +619,59 @@ static int dtl_configure_waves(sr2_ctx* ctx, DtlProblem* p) {
     return SR2_OK;
 }
 
-static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int64_t row_begin,
+static int ceil_log2(int v) {
+    int bits = 0;
+    while ((1 << bits) < v) ++bits;
+    return bits;
+}
+
+static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
+    const int S = ctx->S;
+    p->rank_bits = std::max(1, ceil_log2(S));
+    p->depth_bits = std::max(1, ceil_log2(ctx->D));
+    int value_bits = 32 - p->rank_bits - p->depth_bits;
+    p->simd_arr_words = (S * SIMD_LD + 31) / 32 * 32;
+    p->simd_smem = ((size_t)4 * p->simd_arr_words + 64) * sizeof(unsigned);
+    // finite sums stay below inf32 minus the largest correction a candidate subtracts
+    int64_t inf32 = value_bits >= 2 ? (int64_t)1 << (value_bits - 1) : 0;
+    int64_t slack = 4 * (int64_t)p->costs[3] * (ctx->D + 2);
+    const char* off = getenv("SR2_DTL_NO_SIMD");
+    p->simd_ok = !(off && off[0] == '1') && S >= 2 && value_bits >= 8 && value_bits <= 27 &&
+                 p->max_finite + slack < inf32 - slack && p->simd_smem <= ctx->smem_optin;
+    p->simd_thresh = (int)(inf32 - slack);
+    // small waves keep the row-per-warp kernel (more parallelism inside a row); the
+    // threshold can be overridden for tests (SR2_DTL_SIMD_MIN_ROWS)
+    p->simd_min_rows = SIMD_ROWS * (int64_t)ctx->sm_count;
+    if (const char* min_rows = getenv("SR2_DTL_SIMD_MIN_ROWS")) p->simd_min_rows = atoll(min_rows);
+    if (p->simd_ok)
+        SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_simd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->simd_smem));
+    return SR2_OK;
+}
+
+static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h, int64_t row_begin,
                            int64_t n_rows, const DtlCosts& cs) {
     if (n_rows <= 0) return SR2_OK;
+    if (h == 1) {  // both children of a height-1 node are leaves
+        dtl_cherry_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, ctx->stream>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs);
+        SR2_CUDA(ctx, cudaGetLastError());
+        return SR2_OK;
+    }
+    if (p->simd_ok && n_rows >= 16 * (int64_t)ctx->sm_count) {
+        Key32 kp;
+        kp.db = p->depth_bits;
+        kp.sh = p->rank_bits + p->depth_bits;
+        kp.rm = (1u << p->rank_bits) - 1;
+        kp.dm = (1u << p->depth_bits) - 1;
+        kp.inf32 = 1u << (32 - kp.sh - 1);
+        kp.thresh = p->simd_thresh;
+        dtl_wave_simd16_kernel<<<(unsigned)((n_rows + SIMD_ROWS - 1) / SIMD_ROWS), 512, p->simd_smem, ctx->stream>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
+            p->simd_arr_words, kp);
+        SR2_CUDA(ctx, cudaGetLastError());
+        return SR2_OK;
+    }
     if (!p->cta_per_row) {
         int64_t grid = (n_rows + p->wave_warps - 1) / p->wave_warps;
         dtl_wave_kernel<32><<<(unsigned)grid, p->wave_warps * 32, p->wave_smem, ctx->stream>>>(
@@ -443,6 +694,8 @@ extern "C" int sr2_dtl_solve(sr2_ctx* ctx) {
     {
         int rc = dtl_configure_waves(ctx, p);
         if (rc) return rc;
+        rc = dtl_configure_simd(ctx, p);
+        if (rc) return rc;
     }
     cudaStream_t st = ctx->stream;
     DtlCosts cs{p->costs[0], p->costs[1], p->costs[2], p->costs[3]};
@@ -455,7 +708,7 @@ extern "C" int sr2_dtl_solve(sr2_ctx* ctx) {
         for (int h = 1; h <= H; ++h) {
             int64_t n = c.wave_off[h + 1] - c.wave_off[h];
             if (n <= 0) continue;
-            int rc = dtl_launch_wave(ctx, p, c, c.wave_off[h], n, cs);
+            int rc = dtl_launch_wave(ctx, p, c, h, c.wave_off[h], n, cs);
             if (rc) return rc;
             ++n_waves;
             ++n_launch;

@@ -26,7 +26,8 @@
 
 #include "sr2_rows.cuh"
 
-int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64_t max_nodes);
+int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64_t max_nodes,
+                    int64_t* out_bound);
 
 struct SuperProblem {
     RowLayout rows;
@@ -597,7 +598,7 @@ extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_
                         "sr2_superdtl_upload: batch does not fit in device memory (split it into smaller batches)");
     if (p->rows.max_nodes > 65535)
         return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_superdtl_upload: more than 65535 nodes in one object tree");
-    rc = sr2_check_costs(ctx, "sr2_superdtl_upload", costs, p->rows.max_nodes);
+    rc = sr2_check_costs(ctx, "sr2_superdtl_upload", costs, p->rows.max_nodes, nullptr);
     if (rc) return rc;
 
     const int64_t R = p->rows.R;
