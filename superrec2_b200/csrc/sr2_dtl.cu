@@ -54,6 +54,8 @@ struct DtlProblem {
     int64_t max_finite = 0;
     int64_t simd_min_rows = 0;
     int simd_arr_words = 0, simd_thresh = 0;
+    int multi_rpw = 4, multi_rs = 0;
+    size_t multi_smem = 0;
 };
 
 void sr2_free_dtl(sr2_ctx* ctx) {
@@ -409,6 +411,141 @@ dtl_wave_simd16_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Batched waves, second form: several rows per warp.  A warp owns RPW rows and gives each
+// 32/RPW lanes, so thin levels of the species tree still fill the warp, while everything
+// stays warp-synchronous (no block barrier, rows are loaded and stored row-major and
+// coalesced).  32-bit keys as above; cells are written straight to global memory (the
+// lanes of one row cover consecutive species, i.e. whole 32-byte sectors).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cell32(int x, int dx, int cx, bool is_root, unsigned Ml, unsigned Mr,
+                                       unsigned Pl, unsigned Pr, const unsigned* sl, const unsigned* sr,
+                                       const DtlCosts& cs, const Key32& kp, int& out_t, unsigned& out_g) {
+    const int loss = cs.loss, NONE = 0x7fffffff;
+    const int qMl = key_q(Ml, loss, kp), qMr = key_q(Mr, loss, kp);
+    int w1 = NONE, w2 = NONE, w4 = NONE, w5 = NONE;
+    unsigned l0 = 0, l1 = 0, r0 = 0, r1 = 0;
+    if (cx >= 0) {
+        l0 = sl[cx];
+        l1 = sl[cx + 1];
+        r0 = sr[cx];
+        r1 = sr[cx + 1];
+        int b12 = -2 * loss * (dx + 1);
+        w1 = ((key_q(l0, loss, kp) + key_q(r1, loss, kp) + b12) << 3) | 0;
+        w2 = ((key_q(l1, loss, kp) + key_q(r0, loss, kp) + b12) << 3) | 1;
+    }
+    int w3 = ((qMl + qMr + cs.dup - 2 * loss * dx) << 3) | 2;
+    if (!is_root) {
+        w4 = (((int)(Pl >> kp.sh) + qMr + cs.hgt - loss * dx) << 3) | 3;
+        w5 = ((qMl + (int)(Pr >> kp.sh) + cs.hgt - loss * dx) << 3) | 4;
+    }
+    int w = min(min(min(w1, w2), w3), min(w4, w5));
+    int best = w >> 3, which = w & 7;
+    unsigned ka = Ml, kb = Mr;
+    ka = which == 0 ? l0 : ka;
+    ka = which == 1 ? l1 : ka;
+    ka = which == 3 ? Pl : ka;
+    kb = which == 0 ? r1 : kb;
+    kb = which == 1 ? r0 : kb;
+    kb = which == 4 ? Pr : kb;
+    bool finite = best < kp.thresh;
+    out_t = finite ? best : SR2_INF;
+    out_g = finite ? (((ka >> kp.db) & kp.rm) | (((kb >> kp.db) & kp.rm) << 16)) : SR2_NO_TAG;
+}
+
+template <int RPW>
+__global__ void __launch_bounds__(256)
+dtl_wave_multi_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                      int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
+                      uint32_t* __restrict__ tags, DtlCosts cs, int rs, Key32 kp) {
+    extern __shared__ unsigned smem32[];
+    constexpr int LPR = 32 / RPW;  // lanes per row
+    const int S = sp.S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int g = lane / LPR, t = lane % LPR;
+    const int wrow0 = (blockIdx.x * nwarps + warp) * RPW;  // first row of this warp inside the wave
+    if (wrow0 >= n_rows) return;
+    const int rows_here = min(RPW, n_rows - wrow0);
+    unsigned* wbase = smem32 + (size_t)warp * RPW * 2 * rs;
+
+    // ---- load the 2*RPW child rows, row-major, whole warp per row ---------------------------
+#pragma unroll 1
+    for (int r = 0; r < RPW; ++r) {
+        int64_t gr = row_begin + wrow0 + min(r, rows_here - 1);
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            int c = side ? row_cr[gr] : row_cl[gr];
+            unsigned* dst = wbase + (size_t)(r * 2 + side) * rs;
+            const int32_t* __restrict__ src = c >= 0 ? T + (size_t)c * sp.pitch : nullptr;
+            for (int y = lane; y < S; y += 32) {
+                int v = src ? src[y] : (y == -1 - c ? 0 : SR2_INF);
+                unsigned val = v >= SR2_INF ? kp.inf32 : (unsigned)v;
+                dst[y] = (val << kp.sh) | ((unsigned)y << kp.db) | (unsigned)__ldg(sp.depth + y);
+            }
+        }
+    }
+    __syncwarp();
+
+    unsigned* sl = wbase + (size_t)(g * 2) * rs;
+    unsigned* sr = sl + rs;
+    // ---- up-sweep -----------------------------------------------------------------------------
+    for (int d = sp.D - 2; d >= 0; --d) {
+        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
+        for (int i = b + t; i < e; i += LPR) {
+            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+            sl[p] = min(sl[p], min(sl[c], sl[c + 1]));
+            sr[p] = min(sr[p], min(sr[c], sr[c + 1]));
+        }
+        __syncwarp();
+    }
+
+    const bool live = g < rows_here;
+    const size_t slot = (size_t)(row_begin + wrow0 + min(g, rows_here - 1) - chunk_row0);
+    int32_t* __restrict__ Tout = T + slot * sp.pitch;
+    uint32_t* __restrict__ Gout = tags + slot * sp.pitch;
+
+    // ---- root cell ------------------------------------------------------------------------------
+    if (t == 0) {
+        int ot;
+        unsigned og;
+        cell32(0, 0, __ldg(sp.child0), true, sl[0], sr[0], 0xffffffffu, 0xffffffffu, sl, sr, cs, kp, ot, og);
+        if (live) {
+            Tout[0] = ot;
+            Gout[0] = og;
+        }
+        sl[0] = 0xffffffffu;  // nothing is incomparable to the root
+        sr[0] = 0xffffffffu;
+    }
+    __syncwarp();
+
+    // ---- down-sweep -------------------------------------------------------------------------------
+    for (int d = 0; d < sp.D - 1; ++d) {
+        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
+        for (int i = b + t; i < e; i += LPR) {
+            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+            unsigned Ppl = sl[p], Ppr = sr[p];
+            unsigned m0l = sl[c], m1l = sl[c + 1], m0r = sr[c], m1r = sr[c + 1];
+            unsigned P0l = min(Ppl, m1l), P1l = min(Ppl, m0l);
+            unsigned P0r = min(Ppr, m1r), P1r = min(Ppr, m0r);
+            int t0, t1;
+            unsigned g0, g1;
+            cell32(c, d + 1, __ldg(sp.child0 + c), false, m0l, m0r, P0l, P0r, sl, sr, cs, kp, t0, g0);
+            cell32(c + 1, d + 1, __ldg(sp.child0 + c + 1), false, m1l, m1r, P1l, P1r, sl, sr, cs, kp, t1, g1);
+            if (live) {
+                Tout[c] = t0;
+                Tout[c + 1] = t1;
+                Gout[c] = g0;
+                Gout[c + 1] = g1;
+            }
+            sl[c] = P0l;
+            sl[c + 1] = P1l;
+            sr[c] = P0r;
+            sr[c + 1] = P1r;
+        }
+        __syncwarp();
+    }
+}
+
 // Event cost of node (x; children at a, b) as ReconciliationOutput.cost() sees it
 // (/root/reference/src/superrec2/model/reconciliation.py:273-365).  SR2_INF = INVALID.
 __device__ __forceinline__ int dtl_event_cost(const DevSpecies& sp, int x, int a, int b,
@@ -646,6 +783,23 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
     if (p->simd_ok)
         SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_simd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->simd_smem));
+    // rows-per-warp variant: 0 = use the 16-rows-per-CTA kernel instead
+    p->multi_rpw = 4;
+    if (const char* v = getenv("SR2_DTL_ROWS_PER_WARP")) p->multi_rpw = atoi(v);
+    if (p->multi_rpw != 0 && p->multi_rpw != 1 && p->multi_rpw != 2 && p->multi_rpw != 4 && p->multi_rpw != 8)
+        p->multi_rpw = 4;
+    // row stride = 4 mod 32 words: the rows of one warp start in different banks
+    p->multi_rs = (S + 31) / 32 * 32 + 4;
+    while (p->multi_rpw > 1 && (size_t)8 * p->multi_rpw * 2 * p->multi_rs * 4 > ctx->smem_optin) p->multi_rpw /= 2;
+    p->multi_smem = (size_t)8 * std::max(p->multi_rpw, 1) * 2 * p->multi_rs * sizeof(unsigned);
+    if (p->multi_smem > ctx->smem_optin) p->multi_rpw = 0;
+    if (p->simd_ok && p->multi_rpw) {
+        const void* fn = p->multi_rpw == 1 ? (const void*)dtl_wave_multi_kernel<1>
+                         : p->multi_rpw == 2 ? (const void*)dtl_wave_multi_kernel<2>
+                         : p->multi_rpw == 4 ? (const void*)dtl_wave_multi_kernel<4>
+                                             : (const void*)dtl_wave_multi_kernel<8>;
+        SR2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->multi_smem));
+    }
     return SR2_OK;
 }
 
@@ -666,6 +820,21 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         kp.dm = (1u << p->depth_bits) - 1;
         kp.inf32 = 1u << (32 - kp.sh - 1);
         kp.thresh = p->simd_thresh;
+        if (p->multi_rpw) {
+            int rows_per_cta = 8 * p->multi_rpw;
+            unsigned grid = (unsigned)((n_rows + rows_per_cta - 1) / rows_per_cta);
+#define SR2_LAUNCH_MULTI(R)                                                                              \
+    dtl_wave_multi_kernel<R><<<grid, 256, p->multi_smem, ctx->stream>>>(                                 \
+        ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, \
+        cs, p->multi_rs, kp)
+            if (p->multi_rpw == 1) SR2_LAUNCH_MULTI(1);
+            else if (p->multi_rpw == 2) SR2_LAUNCH_MULTI(2);
+            else if (p->multi_rpw == 4) SR2_LAUNCH_MULTI(4);
+            else SR2_LAUNCH_MULTI(8);
+#undef SR2_LAUNCH_MULTI
+            SR2_CUDA(ctx, cudaGetLastError());
+            return SR2_OK;
+        }
         dtl_wave_simd16_kernel<<<(unsigned)((n_rows + SIMD_ROWS - 1) / SIMD_ROWS), 512, p->simd_smem, ctx->stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
             p->simd_arr_words, kp);
