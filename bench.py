@@ -238,8 +238,13 @@ def main():
     barrier()
     e2e_start = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 3))
+    e2e_parts = [0.0, 0.0, 0.0]
     for _ in range(e2e_steps):
         out = ctx.dtl_run(*inputs)
+        t = ctx.timing()
+        e2e_parts[0] += t.upload_ms
+        e2e_parts[1] += t.solve_ms
+        e2e_parts[2] += t.results_ms
     barrier()
     e2e_s = time.perf_counter() - e2e_start
     assert int(out[0].astype(np.int64).sum()) == checksum
@@ -283,7 +288,9 @@ def main():
             "e2e": {"value": all_cells * e2e_steps / (e2e_ms * 1e-3), "unit": "cells/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "api": "sr2_dtl_run (upload + solve + results, host buffers)"},
+                    "api": "sr2_dtl_run (upload + solve + results, host buffers)",
+                    "upload_ms": e2e_parts[0] / e2e_steps, "solve_ms": e2e_parts[1] / e2e_steps,
+                    "results_ms": e2e_parts[2] / e2e_steps},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

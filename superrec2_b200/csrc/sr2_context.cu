@@ -4,7 +4,9 @@
 // (/root/reference/src/superrec2/utils/trees.py:31-142): instead of an Euler
 // tour + sparse table queried per candidate, every node gets its depth and a
 // preorder [tin, tout) interval once, and the DP kernels only use look-ups.
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "sr2_internal.cuh"
@@ -19,6 +21,60 @@ int sr2_cuda_fail(sr2_ctx* ctx, cudaError_t e, const char* what) {
     cudaGetLastError();  // clear the sticky flag where possible
     return sr2_fail(ctx, SR2_ERR_CUDA, msg);
 }
+
+int sr2_dev_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out) {
+    Sr2Pool& pool = ctx->dev[id];
+    bytes = std::max<size_t>(bytes, 256);
+    if (pool.cap < bytes) {
+        if (pool.ptr) cudaFree(pool.ptr);
+        pool.ptr = nullptr;
+        pool.cap = 0;
+        cudaError_t e = cudaMalloc(&pool.ptr, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return sr2_fail(ctx, SR2_ERR_NOMEM, std::string("device allocation of ") + std::to_string(bytes) +
+                                                    " bytes failed: " + cudaGetErrorString(e));
+        }
+        pool.cap = bytes;
+    }
+    *out = pool.ptr;
+    return SR2_OK;
+}
+
+int sr2_pin_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out) {
+    Sr2Pool& pool = ctx->pin[id];
+    bytes = std::max<size_t>(bytes, 256);
+    if (pool.cap < bytes) {
+        if (pool.ptr) cudaFreeHost(pool.ptr);
+        pool.ptr = nullptr;
+        pool.cap = 0;
+        size_t want = bytes + bytes / 8;  // a little head-room: batches of similar size reuse it
+        cudaError_t e = cudaHostAlloc(&pool.ptr, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return sr2_fail(ctx, SR2_ERR_NOMEM, std::string("pinned host allocation failed: ") + cudaGetErrorString(e));
+        }
+        pool.cap = want;
+    }
+    *out = pool.ptr;
+    return SR2_OK;
+}
+
+int sr2_host_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out) {
+    Sr2Pool& pool = ctx->host[id];
+    bytes = std::max<size_t>(bytes, 256);
+    if (pool.cap < bytes) {
+        free(pool.ptr);
+        size_t want = bytes + bytes / 8;
+        pool.ptr = malloc(want);
+        pool.cap = pool.ptr ? want : 0;
+        if (!pool.ptr) return sr2_fail(ctx, SR2_ERR_NOMEM, "host allocation failed");
+    }
+    *out = pool.ptr;
+    return SR2_OK;
+}
+
+size_t sr2_dev_pooled(const sr2_ctx* ctx, int id) { return ctx->dev[id].cap; }
 
 static std::string g_create_error;
 
@@ -78,6 +134,11 @@ extern "C" void sr2_destroy(sr2_ctx* ctx) {
     sr2_free_dtl(ctx);
     sr2_free_super(ctx);
     if (ctx->d_species_slab) cudaFree(ctx->d_species_slab);
+    for (auto& pool : ctx->dev)
+        if (pool.ptr) cudaFree(pool.ptr);
+    for (auto& pool : ctx->pin)
+        if (pool.ptr) cudaFreeHost(pool.ptr);
+    for (auto& pool : ctx->host) free(pool.ptr);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

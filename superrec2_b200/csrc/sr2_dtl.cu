@@ -54,21 +54,14 @@ struct DtlProblem {
     int64_t max_finite = 0;
     int64_t simd_min_rows = 0;
     int simd_arr_words = 0, simd_thresh = 0;
-    int multi_rpw = 4, multi_rs = 0;
+    int multi_rpw = 2, multi_rs = 0;
     size_t multi_smem = 0;
 };
 
 void sr2_free_dtl(sr2_ctx* ctx) {
     DtlProblem* p = ctx->dtl;
     if (!p) return;
-    p->rows.release();
-    cudaFree(p->d_T);
-    cudaFree(p->d_tag);
-    cudaFree(p->d_C);
-    cudaFree(p->d_min_cost);
-    cudaFree(p->d_root_species);
-    cudaFree(p->d_map);
-    delete p;
+    delete p;  // device buffers live in the context's pools
     ctx->dtl = nullptr;
 }
 
@@ -710,6 +703,8 @@ extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
 
     size_t free_b = 0, total_b = 0;
     SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    // buffers this context already holds are reused, so they count as available
+    for (int id : {DP_ROWS_SLAB, DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MAP}) free_b += sr2_dev_pooled(ctx, id);
     size_t per_row = (size_t)ctx->pitch * (p->need_decoded_cost ? 12 : 8);
     size_t fixed = (size_t)N * 4 * 7 + (size_t)B * 32 + (64u << 20);
     if (free_b < fixed + per_row * 4)
@@ -723,13 +718,24 @@ extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
     if ((flags & SR2_KEEP_TABLES) && p->rows.chunks.size() > 1)
         return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: SR2_KEEP_TABLES needs the batch to fit in one chunk");
 
-    SR2_CUDA(ctx, cudaMalloc(&p->d_min_cost, std::max<size_t>(B, 1) * sizeof(int32_t)));
-    SR2_CUDA(ctx, cudaMalloc(&p->d_root_species, std::max<size_t>(B, 1) * sizeof(int32_t)));
-    SR2_CUDA(ctx, cudaMalloc(&p->d_map, std::max<size_t>(N, 1) * sizeof(int32_t)));
     size_t table_elems = (size_t)std::max<int64_t>(p->rows.max_chunk_rows, 1) * ctx->pitch;
-    SR2_CUDA(ctx, cudaMalloc(&p->d_T, table_elems * sizeof(int32_t)));
-    SR2_CUDA(ctx, cudaMalloc(&p->d_tag, table_elems * sizeof(uint32_t)));
-    if (p->need_decoded_cost) SR2_CUDA(ctx, cudaMalloc(&p->d_C, table_elems * sizeof(int32_t)));
+    {
+        void* ptr = nullptr;
+        if ((rc = sr2_dev_reserve(ctx, DP_DTL_MINCOST, std::max<size_t>(B, 1) * sizeof(int32_t), &ptr))) return rc;
+        p->d_min_cost = (int32_t*)ptr;
+        if ((rc = sr2_dev_reserve(ctx, DP_DTL_ROOTSP, std::max<size_t>(B, 1) * sizeof(int32_t), &ptr))) return rc;
+        p->d_root_species = (int32_t*)ptr;
+        if ((rc = sr2_dev_reserve(ctx, DP_DTL_MAP, std::max<size_t>(N, 1) * sizeof(int32_t), &ptr))) return rc;
+        p->d_map = (int32_t*)ptr;
+        if ((rc = sr2_dev_reserve(ctx, DP_DTL_T, table_elems * sizeof(int32_t), &ptr))) return rc;
+        p->d_T = (int32_t*)ptr;
+        if ((rc = sr2_dev_reserve(ctx, DP_DTL_TAG, table_elems * sizeof(uint32_t), &ptr))) return rc;
+        p->d_tag = (uint32_t*)ptr;
+        if (p->need_decoded_cost) {
+            if ((rc = sr2_dev_reserve(ctx, DP_DTL_C, table_elems * sizeof(int32_t), &ptr))) return rc;
+            p->d_C = (int32_t*)ptr;
+        }
+    }
     ctx->timing.upload_ms = (float)(now_ms() - t0);
     return SR2_OK;
 }
@@ -784,10 +790,10 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
         SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_simd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->simd_smem));
     // rows-per-warp variant: 0 = use the 16-rows-per-CTA kernel instead
-    p->multi_rpw = 4;
+    p->multi_rpw = 2;  // measured best on B200 for |S| = 399 (profiles/README.md)
     if (const char* v = getenv("SR2_DTL_ROWS_PER_WARP")) p->multi_rpw = atoi(v);
     if (p->multi_rpw != 0 && p->multi_rpw != 1 && p->multi_rpw != 2 && p->multi_rpw != 4 && p->multi_rpw != 8)
-        p->multi_rpw = 4;
+        p->multi_rpw = 2;
     // row stride = 4 mod 32 words: the rows of one warp start in different banks
     p->multi_rs = (S + 31) / 32 * 32 + 4;
     while (p->multi_rpw > 1 && (size_t)8 * p->multi_rpw * 2 * p->multi_rs * 4 > ctx->smem_optin) p->multi_rpw /= 2;
@@ -935,16 +941,30 @@ extern "C" int sr2_dtl_results(sr2_ctx* ctx, int32_t* out_min_cost, int32_t* out
     if (!p || !p->solved) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_results: solve first");
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
     double t0 = now_ms();
+    const size_t B = p->rows.B, N = p->rows.N;
+    // D2H into pinned staging (full PCIe speed), then a parallel copy into the caller's buffers
+    void* ptr = nullptr;
+    int rc = sr2_pin_reserve(ctx, HP_RESULTS, (2 * B + N + 16) * sizeof(int32_t), &ptr);
+    if (rc) return rc;
+    int32_t* stage = (int32_t*)ptr;
     if (out_min_cost)
-        SR2_CUDA(ctx, cudaMemcpyAsync(out_min_cost, p->d_min_cost, (size_t)p->rows.B * 4, cudaMemcpyDeviceToHost,
-                                      ctx->stream));
+        SR2_CUDA(ctx, cudaMemcpyAsync(stage, p->d_min_cost, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_root_species)
-        SR2_CUDA(ctx, cudaMemcpyAsync(out_root_species, p->d_root_species, (size_t)p->rows.B * 4,
-                                      cudaMemcpyDeviceToHost, ctx->stream));
+        SR2_CUDA(ctx, cudaMemcpyAsync(stage + B, p->d_root_species, B * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (out_map_species)
-        SR2_CUDA(ctx, cudaMemcpyAsync(out_map_species, p->d_map, (size_t)p->rows.N * 4, cudaMemcpyDeviceToHost,
-                                      ctx->stream));
+        SR2_CUDA(ctx, cudaMemcpyAsync(stage + 2 * B, p->d_map, N * 4, cudaMemcpyDeviceToHost, ctx->stream));
     SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (out_min_cost) memcpy(out_min_cost, stage, B * 4);
+    if (out_root_species) memcpy(out_root_species, stage + B, B * 4);
+    if (out_map_species) {
+        const int64_t block = 1 << 18;
+        const int64_t n_blocks = ((int64_t)N + block - 1) / block;
+#pragma omp parallel for schedule(static)
+        for (int64_t k = 0; k < n_blocks; ++k) {
+            int64_t lo = k * block, hi = std::min<int64_t>((int64_t)N, lo + block);
+            memcpy(out_map_species + lo, stage + 2 * B + lo, (size_t)(hi - lo) * 4);
+        }
+    }
     ctx->timing.results_ms = (float)(now_ms() - t0);
     return SR2_OK;
 }

@@ -40,6 +40,19 @@ struct DevSpecies {
 struct DtlProblem;
 struct SuperProblem;
 
+// Grow-only buffer pools owned by the context: repeated uploads reuse device buffers and
+// pinned host staging instead of paying cudaMalloc/cudaFree and first-touch page faults.
+struct Sr2Pool {
+    void* ptr = nullptr;
+    size_t cap = 0;
+};
+enum Sr2DevPool {
+    DP_ROWS_SLAB, DP_ROOT_ROW, DP_ROOT_NODE, DP_NODE_PRE, DP_NODE_INST,
+    DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MINCOST, DP_DTL_ROOTSP, DP_DTL_MAP, DP_COUNT
+};
+enum Sr2PinPool { HP_ROWS_SLAB, HP_ROOT_ROW, HP_ROOT_NODE, HP_NODE_PRE, HP_NODE_INST, HP_RESULTS, HP_COUNT };
+enum Sr2HostPool { MP_HEIGHT, MP_NODE_ROW, MP_CNT, MP_COUNT };
+
 struct sr2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -54,6 +67,8 @@ struct sr2_ctx {
     int32_t* d_species_slab = nullptr;
     DevSpecies dsp{};
 
+    Sr2Pool dev[DP_COUNT], pin[HP_COUNT], host[MP_COUNT];
+
     DtlProblem* dtl = nullptr;
     SuperProblem* super = nullptr;
     sr2_timing timing{};
@@ -62,6 +77,10 @@ struct sr2_ctx {
 
 int sr2_fail(sr2_ctx* ctx, int code, const std::string& msg);
 int sr2_cuda_fail(sr2_ctx* ctx, cudaError_t e, const char* what);
+int sr2_dev_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out);   // device memory
+int sr2_pin_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out);   // pinned host memory
+int sr2_host_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out);  // plain host scratch
+size_t sr2_dev_pooled(const sr2_ctx* ctx, int id);
 void sr2_free_dtl(sr2_ctx* ctx);
 void sr2_free_super(sr2_ctx* ctx);
 

@@ -10,12 +10,8 @@
 #include "sr2_rows.cuh"
 
 void RowLayout::release() {
-    cudaFree(d_slab);
-    cudaFree(d_root_row);
-    cudaFree(d_root_node);
-    cudaFree(d_node_pre);
-    cudaFree(d_node_inst);
     d_slab = nullptr;
+    row_cl = row_cr = row_node = row_left = row_right = nullptr;
     d_root_row = nullptr;
     d_root_node = nullptr;
     d_node_pre = nullptr;
@@ -35,7 +31,13 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
     out->node_off.assign(node_off, node_off + B + 1);
 
     // ---- pass 1: validate, heights ------------------------------------------------
-    std::vector<uint16_t> height(N);
+    uint16_t* height = nullptr;
+    {
+        void* ptr = nullptr;
+        int rc = sr2_host_reserve(ctx, MP_HEIGHT, (size_t)std::max<int64_t>(N, 1) * sizeof(uint16_t), &ptr);
+        if (rc) return rc;
+        height = (uint16_t*)ptr;
+    }
     int bad_inst = -1;
     std::string bad_msg;
     int Hmax = 0;
@@ -114,24 +116,47 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
     const int64_t R = out->R;
 
     // ---- pass 2: rows in (chunk, height, instance, node) order ---------------------------
-    std::vector<int32_t> slab((size_t)std::max<int64_t>(R, 1) * 5);
-    int32_t* h_cl = slab.data();
+    // staging in pinned host memory (reused across uploads): full-speed H2D, no page faults
+    const size_t slab_elems = (size_t)std::max<int64_t>(R, 1) * 5;
+    int32_t* h_cl = nullptr;
+    int64_t* h_root_row = nullptr;
+    int32_t* h_root_node = nullptr;
+    int32_t* node_row = nullptr;
+    {
+        void* ptr = nullptr;
+        int rc = sr2_pin_reserve(ctx, HP_ROWS_SLAB, slab_elems * sizeof(int32_t), &ptr);
+        if (rc) return rc;
+        h_cl = (int32_t*)ptr;
+        rc = sr2_pin_reserve(ctx, HP_ROOT_ROW, (size_t)std::max(B, 1) * sizeof(int64_t), &ptr);
+        if (rc) return rc;
+        h_root_row = (int64_t*)ptr;
+        rc = sr2_pin_reserve(ctx, HP_ROOT_NODE, (size_t)std::max(B, 1) * sizeof(int32_t), &ptr);
+        if (rc) return rc;
+        h_root_node = (int32_t*)ptr;
+        rc = sr2_host_reserve(ctx, MP_NODE_ROW, (size_t)std::max<int64_t>(N, 1) * sizeof(int32_t), &ptr);
+        if (rc) return rc;
+        node_row = (int32_t*)ptr;
+    }
     int32_t* h_cr = h_cl + R;
     int32_t* h_node = h_cr + R;
     int32_t* h_left = h_node + R;
     int32_t* h_right = h_left + R;
-    std::vector<int64_t> h_root_row(std::max(B, 1));
-    std::vector<int32_t> h_root_node(std::max(B, 1));
-    std::vector<int64_t> node_row(N, -1);
     const int W = Hmax + 1;
     out->max_chunk_rows = 0;
     for (auto& c : out->chunks) {
         int nb = c.inst_end - c.inst_begin;
-        std::vector<int64_t> cnt((size_t)std::max(nb, 1) * W, 0);
-#pragma omp parallel for schedule(dynamic, 64)
+        int32_t* cnt = nullptr;
+        {
+            void* ptr = nullptr;
+            int rc = sr2_host_reserve(ctx, MP_CNT, (size_t)std::max(nb, 1) * W * sizeof(int32_t), &ptr);
+            if (rc) return rc;
+            cnt = (int32_t*)ptr;
+        }
+#pragma omp parallel for schedule(static)
         for (int b = c.inst_begin; b < c.inst_end; ++b) {
             int64_t off = node_off[b], G = node_off[b + 1] - off;
-            int64_t* mine = cnt.data() + (size_t)(b - c.inst_begin) * W;
+            int32_t* mine = cnt + (size_t)(b - c.inst_begin) * W;
+            for (int h = 0; h < W; ++h) mine[h] = 0;
             for (int64_t u = 0; u < G; ++u) mine[height[off + u]]++;
         }
         c.wave_off.assign(W + 1, 0);
@@ -140,8 +165,8 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
         for (int h = 1; h < W; ++h) {
             c.wave_off[h] = run;
             for (int i = 0; i < nb; ++i) {
-                int64_t k = cnt[(size_t)i * W + h];
-                cnt[(size_t)i * W + h] = run;
+                int32_t k = cnt[(size_t)i * W + h];
+                cnt[(size_t)i * W + h] = (int32_t)run;
                 run += k;
             }
         }
@@ -150,10 +175,10 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
 #pragma omp parallel for schedule(dynamic, 64)
         for (int b = c.inst_begin; b < c.inst_end; ++b) {
             int64_t off = node_off[b], G = node_off[b + 1] - off;
-            int64_t* cursor = cnt.data() + (size_t)(b - c.inst_begin) * W;
+            int32_t* cursor = cnt + (size_t)(b - c.inst_begin) * W;
             for (int64_t u = 0; u < G; ++u) {
                 int h = height[off + u];
-                if (h > 0) node_row[off + u] = cursor[h]++;
+                node_row[off + u] = h > 0 ? cursor[h]++ : -1;
             }
             for (int64_t u = 0; u < G; ++u) {
                 int64_t gr = node_row[off + u];
@@ -171,26 +196,49 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
         }
     }
 
-    // ---- device copies -----------------------------------------------------------------
+    // ---- device copies (pooled buffers) ---------------------------------------------------
     out->release();
-    SR2_CUDA(ctx, cudaMalloc(&out->d_slab, slab.size() * sizeof(int32_t)));
+    {
+        void* ptr = nullptr;
+        int rc = sr2_dev_reserve(ctx, DP_ROWS_SLAB, slab_elems * sizeof(int32_t), &ptr);
+        if (rc) return rc;
+        out->d_slab = (int32_t*)ptr;
+        rc = sr2_dev_reserve(ctx, DP_ROOT_ROW, (size_t)std::max(B, 1) * sizeof(int64_t), &ptr);
+        if (rc) return rc;
+        out->d_root_row = (int64_t*)ptr;
+        rc = sr2_dev_reserve(ctx, DP_ROOT_NODE, (size_t)std::max(B, 1) * sizeof(int32_t), &ptr);
+        if (rc) return rc;
+        out->d_root_node = (int32_t*)ptr;
+    }
     out->row_cl = out->d_slab;
     out->row_cr = out->row_cl + R;
     out->row_node = out->row_cr + R;
     out->row_left = out->row_node + R;
     out->row_right = out->row_left + R;
-    SR2_CUDA(ctx, cudaMalloc(&out->d_root_row, h_root_row.size() * sizeof(int64_t)));
-    SR2_CUDA(ctx, cudaMalloc(&out->d_root_node, h_root_node.size() * sizeof(int32_t)));
-    SR2_CUDA(ctx, cudaMemcpyAsync(out->d_slab, slab.data(), slab.size() * sizeof(int32_t),
+    SR2_CUDA(ctx, cudaMemcpyAsync(out->d_slab, h_cl, slab_elems * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    SR2_CUDA(ctx, cudaMemcpyAsync(out->d_root_row, h_root_row, (size_t)std::max(B, 1) * sizeof(int64_t),
                                   cudaMemcpyHostToDevice, ctx->stream));
-    SR2_CUDA(ctx, cudaMemcpyAsync(out->d_root_row, h_root_row.data(), h_root_row.size() * sizeof(int64_t),
+    SR2_CUDA(ctx, cudaMemcpyAsync(out->d_root_node, h_root_node, (size_t)std::max(B, 1) * sizeof(int32_t),
                                   cudaMemcpyHostToDevice, ctx->stream));
-    SR2_CUDA(ctx, cudaMemcpyAsync(out->d_root_node, h_root_node.data(), h_root_node.size() * sizeof(int32_t),
-                                  cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<int32_t> pre, inst;
     if (want_preorder) {
-        pre.assign(std::max<int64_t>(N, 1), 0);
-        inst.assign(std::max<int64_t>(N, 1), 0);
+        int32_t *pre = nullptr, *inst = nullptr;
+        {
+            void* ptr = nullptr;
+            size_t bytes = (size_t)std::max<int64_t>(N, 1) * sizeof(int32_t);
+            int rc = sr2_pin_reserve(ctx, HP_NODE_PRE, bytes, &ptr);
+            if (rc) return rc;
+            pre = (int32_t*)ptr;
+            rc = sr2_pin_reserve(ctx, HP_NODE_INST, bytes, &ptr);
+            if (rc) return rc;
+            inst = (int32_t*)ptr;
+            rc = sr2_dev_reserve(ctx, DP_NODE_PRE, bytes, &ptr);
+            if (rc) return rc;
+            out->d_node_pre = (int32_t*)ptr;
+            rc = sr2_dev_reserve(ctx, DP_NODE_INST, bytes, &ptr);
+            if (rc) return rc;
+            out->d_node_inst = (int32_t*)ptr;
+        }
 #pragma omp parallel for schedule(dynamic, 64)
         for (int b = 0; b < B; ++b) {
             int64_t off = node_off[b], G = node_off[b + 1] - off;
@@ -209,16 +257,14 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
             }
             
         }
-        SR2_CUDA(ctx, cudaMalloc(&out->d_node_pre, pre.size() * sizeof(int32_t)));
-        SR2_CUDA(ctx, cudaMalloc(&out->d_node_inst, inst.size() * sizeof(int32_t)));
-        SR2_CUDA(ctx, cudaMemcpyAsync(out->d_node_pre, pre.data(), pre.size() * sizeof(int32_t),
+        SR2_CUDA(ctx, cudaMemcpyAsync(out->d_node_pre, pre, (size_t)std::max<int64_t>(N, 1) * sizeof(int32_t),
                                       cudaMemcpyHostToDevice, ctx->stream));
-        SR2_CUDA(ctx, cudaMemcpyAsync(out->d_node_inst, inst.data(), inst.size() * sizeof(int32_t),
+        SR2_CUDA(ctx, cudaMemcpyAsync(out->d_node_inst, inst, (size_t)std::max<int64_t>(N, 1) * sizeof(int32_t),
                                       cudaMemcpyHostToDevice, ctx->stream));
     }
     SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (keep_host) {
-        out->h_node_row.swap(node_row);
+        out->h_node_row.assign(node_row, node_row + N);
         out->h_leaf.assign(leaf_species, leaf_species + N);
     }
     return SR2_OK;

@@ -23,7 +23,7 @@ struct RowLayout {
     int64_t max_chunk_rows = 0;
     int max_height = 0;
     int64_t max_nodes = 0;          // largest instance
-    // device (one slab): per row child descriptors and node ids
+    // device (pooled in the context, not owned): per row child descriptors and node ids
     int32_t* d_slab = nullptr;
     int32_t *row_cl = nullptr, *row_cr = nullptr;      // >=0: child's row inside the chunk; <0: -1-leaf species
     int32_t *row_node = nullptr, *row_left = nullptr, *row_right = nullptr;  // global node ids
@@ -32,10 +32,10 @@ struct RowLayout {
     // optional
     int32_t* d_node_pre = nullptr;   // [N] preorder position of each node inside its instance
     int32_t* d_node_inst = nullptr;  // [N] instance of each node
-    std::vector<int64_t> h_node_row; // [N] global row of a node, -1 for leaves (kept on request)
+    std::vector<int32_t> h_node_row; // [N] global row of a node, -1 for leaves (kept on request)
     std::vector<int32_t> h_leaf;     // [N] leaf species (kept on request)
 
-    void release();
+    void release();  // forgets the pooled pointers (the context keeps the memory)
 };
 
 // Validates the batch (ABI numbering rules), computes heights, splits into chunks
