@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "sr2_internal.cuh"
 
@@ -114,6 +115,18 @@ extern "C" int sr2_create(int device, sr2_ctx** out) {
                          std::to_string(prop.major) + std::to_string(prop.minor);
         delete ctx;
         return SR2_ERR_CUDA;
+    }
+    // Host threads for bucketing/unranking.  Launchers such as torchrun export
+    // OMP_NUM_THREADS=1, which would serialise the host side of every upload, so the library
+    // sizes its own team: SR2_HOST_THREADS, else the cores of this box divided by the ranks
+    // sharing it (LOCAL_WORLD_SIZE).
+    {
+        int cores = (int)std::thread::hardware_concurrency();
+        if (cores < 1) cores = 1;
+        int ranks = 1;
+        if (const char* lws = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(lws));
+        ctx->host_threads = std::max(1, cores / ranks);
+        if (const char* t = getenv("SR2_HOST_THREADS")) ctx->host_threads = std::max(1, atoi(t));
     }
     ctx->sm_count = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;

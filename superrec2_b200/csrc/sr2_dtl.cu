@@ -56,6 +56,9 @@ struct DtlProblem {
     int simd_arr_words = 0, simd_thresh = 0;
     int multi_rpw = 2, multi_rs = 0;
     size_t multi_smem = 0;
+    bool flat = true;
+    int flat_rs = 0;
+    size_t flat_smem = 0;
 };
 
 void sr2_free_dtl(sr2_ctx* ctx) {
@@ -539,6 +542,119 @@ dtl_wave_multi_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     }
 }
 
+// ---------------------------------------------------------------------------
+// Batched waves, third form ("flat"): one warp per row, 32-bit keys, and BOTH sweeps
+// materialised in shared memory before any cell is evaluated:
+//   ML/MR = SUBMIN of the two child rows (up-sweep, in place)
+//   PL/PR = SEPMIN of the two child rows (top-down sweep into two more arrays)
+// The cells are then an element-wise pass with lanes over consecutive species: every lane
+// is busy, child-row loads and the T / tag stores are coalesced, and the level structure
+// of the species tree only costs the two cheap sweeps.  Arrays are shifted by one word so
+// that the keys of the two children of a species (ranks 2i+1, 2i+2) are one aligned
+// 64-bit shared-memory load.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+dtl_wave_flat_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                     int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
+                     uint32_t* __restrict__ tags, DtlCosts cs, int rs, Key32 kp) {
+    extern __shared__ unsigned smem32[];
+    const int S = sp.S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int local = blockIdx.x * nwarps + warp;
+    if (local >= n_rows) return;
+    const int64_t gr = row_begin + local;
+    const size_t slot = (size_t)(gr - chunk_row0);
+    // element y of an array lives at word y + 1
+    unsigned* ML = smem32 + (size_t)warp * 4 * rs + 1;
+    unsigned* MR = ML + rs;
+    unsigned* PL = MR + rs;
+    unsigned* PR = PL + rs;
+    const int cl = row_cl[gr], cr = row_cr[gr];
+
+    // ---- load both child rows as keys (leaf children are synthesised) -------------------------
+    {
+        const int32_t* __restrict__ Tl = cl >= 0 ? T + (size_t)cl * sp.pitch : nullptr;
+        const int32_t* __restrict__ Tr = cr >= 0 ? T + (size_t)cr * sp.pitch : nullptr;
+        const int al = -1 - cl, ar = -1 - cr;
+        for (int y = lane; y < S; y += 32) {
+            unsigned low = ((unsigned)y << kp.db) | (unsigned)__ldg(sp.depth + y);
+            int vl = Tl ? Tl[y] : (y == al ? 0 : SR2_INF);
+            int vr = Tr ? Tr[y] : (y == ar ? 0 : SR2_INF);
+            ML[y] = ((vl >= SR2_INF ? kp.inf32 : (unsigned)vl) << kp.sh) | low;
+            MR[y] = ((vr >= SR2_INF ? kp.inf32 : (unsigned)vr) << kp.sh) | low;
+        }
+    }
+    __syncwarp();
+
+    // ---- up-sweep: SUBMIN in place -------------------------------------------------------------
+    for (int d = sp.D - 2; d >= 0; --d) {
+        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
+        for (int i = b + lane; i < e; i += 32) {
+            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+            uint2 kl = *reinterpret_cast<const uint2*>(ML + c);
+            uint2 kr = *reinterpret_cast<const uint2*>(MR + c);
+            ML[p] = min(ML[p], min(kl.x, kl.y));
+            MR[p] = min(MR[p], min(kr.x, kr.y));
+        }
+        __syncwarp();
+    }
+
+    // ---- top-down sweep: SEPMIN into PL/PR -------------------------------------------------------
+    if (lane == 0) {
+        PL[0] = 0xffffffffu;  // nothing is incomparable to the root
+        PR[0] = 0xffffffffu;
+    }
+    __syncwarp();
+    for (int d = 0; d < sp.D - 1; ++d) {
+        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
+        for (int i = b + lane; i < e; i += 32) {
+            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+            uint2 kl = *reinterpret_cast<const uint2*>(ML + c);
+            uint2 kr = *reinterpret_cast<const uint2*>(MR + c);
+            unsigned ppl = PL[p], ppr = PR[p];
+            *reinterpret_cast<uint2*>(PL + c) = make_uint2(min(ppl, kl.y), min(ppl, kl.x));
+            *reinterpret_cast<uint2*>(PR + c) = make_uint2(min(ppr, kr.y), min(ppr, kr.x));
+        }
+        __syncwarp();
+    }
+
+    // ---- cells: element-wise over species ----------------------------------------------------------
+    int32_t* __restrict__ Tout = T + slot * sp.pitch;
+    uint32_t* __restrict__ Gout = tags + slot * sp.pitch;
+    const int loss = cs.loss, NONE = 0x7fffffff;
+    for (int x = lane; x < S; x += 32) {
+        const int dx = __ldg(sp.depth + x), cx = __ldg(sp.child0 + x);
+        const unsigned Ml = ML[x], Mr = MR[x], Pl = PL[x], Pr = PR[x];
+        const int qMl = key_q(Ml, loss, kp), qMr = key_q(Mr, loss, kp);
+        int w1 = NONE, w2 = NONE, w4 = NONE, w5 = NONE;
+        uint2 kl = make_uint2(0, 0), kr = make_uint2(0, 0);
+        if (cx >= 0) {
+            kl = *reinterpret_cast<const uint2*>(ML + cx);
+            kr = *reinterpret_cast<const uint2*>(MR + cx);
+            int b12 = -2 * loss * (dx + 1);
+            w1 = ((key_q(kl.x, loss, kp) + key_q(kr.y, loss, kp) + b12) << 3) | 0;  // 1. spe, l | r
+            w2 = ((key_q(kl.y, loss, kp) + key_q(kr.x, loss, kp) + b12) << 3) | 1;  // 2. spe, r | l
+        }
+        int w3 = ((qMl + qMr + cs.dup - 2 * loss * dx) << 3) | 2;                    // 3. dup
+        if (x != 0) {
+            w4 = (((int)(Pl >> kp.sh) + qMr + cs.hgt - loss * dx) << 3) | 3;         // 4. hgt, left away
+            w5 = ((qMl + (int)(Pr >> kp.sh) + cs.hgt - loss * dx) << 3) | 4;         // 5. hgt, right away
+        }
+        int w = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
+        int best = w >> 3, which = w & 7;
+        unsigned ka = Ml, kb = Mr;
+        ka = which == 0 ? kl.x : ka;
+        ka = which == 1 ? kl.y : ka;
+        ka = which == 3 ? Pl : ka;
+        kb = which == 0 ? kr.y : kb;
+        kb = which == 1 ? kr.x : kb;
+        kb = which == 4 ? Pr : kb;
+        bool finite = best < kp.thresh;
+        Tout[x] = finite ? best : SR2_INF;
+        Gout[x] = finite ? (((ka >> kp.db) & kp.rm) | (((kb >> kp.db) & kp.rm) << 16)) : SR2_NO_TAG;
+    }
+}
+
 // Event cost of node (x; children at a, b) as ReconciliationOutput.cost() sees it
 // (/root/reference/src/superrec2/model/reconciliation.py:273-365).  SR2_INF = INVALID.
 __device__ __forceinline__ int dtl_event_cost(const DevSpecies& sp, int x, int a, int b,
@@ -789,6 +905,16 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
     if (p->simd_ok)
         SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_simd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->simd_smem));
+    // default batched kernel: "flat" (element-wise cells); SR2_DTL_VARIANT=multi|simd16 selects
+    // the two earlier forms (kept for comparison and as cross-checks in the tests)
+    p->flat = true;
+    if (const char* v = getenv("SR2_DTL_VARIANT")) p->flat = strcmp(v, "flat") == 0;
+    p->flat_rs = (S + 2 + 31) / 32 * 32 + 2;   // even (aligned uint2), = 2 mod 32 (rows in different banks)
+    p->flat_smem = (size_t)8 * 4 * p->flat_rs * sizeof(unsigned);
+    if (p->flat_smem > ctx->smem_optin) p->flat = false;
+    if (p->simd_ok && p->flat)
+        SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->flat_smem));
     // rows-per-warp variant: 0 = use the 16-rows-per-CTA kernel instead
     p->multi_rpw = 2;  // measured best on B200 for |S| = 399 (profiles/README.md)
     if (const char* v = getenv("SR2_DTL_ROWS_PER_WARP")) p->multi_rpw = atoi(v);
@@ -826,6 +952,13 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         kp.dm = (1u << p->depth_bits) - 1;
         kp.inf32 = 1u << (32 - kp.sh - 1);
         kp.thresh = p->simd_thresh;
+        if (p->flat) {
+            dtl_wave_flat_kernel<<<(unsigned)((n_rows + 7) / 8), 256, p->flat_smem, ctx->stream>>>(
+                ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
+                p->flat_rs, kp);
+            SR2_CUDA(ctx, cudaGetLastError());
+            return SR2_OK;
+        }
         if (p->multi_rpw) {
             int rows_per_cta = 8 * p->multi_rpw;
             unsigned grid = (unsigned)((n_rows + rows_per_cta - 1) / rows_per_cta);
@@ -959,7 +1092,7 @@ extern "C" int sr2_dtl_results(sr2_ctx* ctx, int32_t* out_min_cost, int32_t* out
     if (out_map_species) {
         const int64_t block = 1 << 18;
         const int64_t n_blocks = ((int64_t)N + block - 1) / block;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static)
         for (int64_t k = 0; k < n_blocks; ++k) {
             int64_t lo = k * block, hi = std::min<int64_t>((int64_t)N, lo + block);
             memcpy(out_map_species + lo, stage + 2 * B + lo, (size_t)(hi - lo) * 4);

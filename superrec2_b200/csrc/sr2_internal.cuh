@@ -59,6 +59,7 @@ struct sr2_ctx {
     bool own_stream = false;
     std::string err;
     int sm_count = 148;
+    int host_threads = 1;  // OpenMP threads of the host-side bucketing (see sr2_create)
     size_t smem_optin = 0;
 
     // species tree (host copies + one device slab)

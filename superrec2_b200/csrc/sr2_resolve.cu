@@ -251,7 +251,7 @@ extern "C" int sr2_resolutions_upload(sr2_ctx* ctx, int32_t n_nodes, const int32
             tmpl_leaf[t.base[v]] = leaf_species[v];
             memcpy(&tmpl_bits[(size_t)t.base[v] * W], leaf_bits + (size_t)v * W, sizeof(uint32_t) * W);
         }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static)
     for (int64_t i = 0; i < count; ++i) {
         unrank(t, first + i, left.data() + i * Gb, right.data() + i * Gb, nullptr);
         memcpy(leaf.data() + i * Gb, tmpl_leaf.data(), sizeof(int32_t) * Gb);

@@ -42,7 +42,7 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
     std::string bad_msg;
     int Hmax = 0;
     int64_t maxG = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(max : Hmax) reduction(max : maxG)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(dynamic, 64) reduction(max : Hmax) reduction(max : maxG)
     for (int b = 0; b < B; ++b) {
         int64_t off = node_off[b];
         int64_t G = node_off[b + 1] - off;
@@ -152,7 +152,7 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
             if (rc) return rc;
             cnt = (int32_t*)ptr;
         }
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static)
         for (int b = c.inst_begin; b < c.inst_end; ++b) {
             int64_t off = node_off[b], G = node_off[b + 1] - off;
             int32_t* mine = cnt + (size_t)(b - c.inst_begin) * W;
@@ -172,7 +172,7 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
         }
         c.wave_off[W] = run;
         out->max_chunk_rows = std::max(out->max_chunk_rows, c.row_end - c.row_begin);
-#pragma omp parallel for schedule(dynamic, 64)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(dynamic, 64)
         for (int b = c.inst_begin; b < c.inst_end; ++b) {
             int64_t off = node_off[b], G = node_off[b + 1] - off;
             int32_t* cursor = cnt + (size_t)(b - c.inst_begin) * W;
@@ -239,7 +239,7 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
             if (rc) return rc;
             out->d_node_inst = (int32_t*)ptr;
         }
-#pragma omp parallel for schedule(dynamic, 64)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(dynamic, 64)
         for (int b = 0; b < B; ++b) {
             int64_t off = node_off[b], G = node_off[b + 1] - off;
             std::vector<int32_t> stack;

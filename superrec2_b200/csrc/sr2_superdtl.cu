@@ -604,7 +604,7 @@ extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_
     const int64_t R = p->rows.R;
     // global-id child arrays for the per-instance kernels
     std::vector<int32_t> gl(std::max<int64_t>(N, 1)), grt(std::max<int64_t>(N, 1));
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static)
     for (int b = 0; b < B; ++b)
         for (int64_t u = node_off[b]; u < node_off[b + 1]; ++u) {
             gl[u] = left[u] < 0 ? -1 : (int32_t)(node_off[b] + left[u]);
