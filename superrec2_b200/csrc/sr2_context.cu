@@ -256,7 +256,18 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
         ctx->d_species_slab = nullptr;
     }
     size_t n_int = int_list.size();
-    size_t total = (size_t)S * 5 + (n_int ? n_int : 1) + (size_t)ctx->D + 1;
+    // sweep schedule (see DevSpecies::sweep_sched)
+    std::vector<int32_t> sched;
+    for (int d = 0; d + 1 < ctx->D; ++d) {
+        int b = ctx->h_int_lvl_off[d], e = ctx->h_int_lvl_off[d + 1];
+        for (int i = b; i < e; i += 32)
+            for (int l = 0; l < 32; ++l) {
+                int k = i + l;
+                sched.push_back(k < e ? (int32_t)(((uint32_t)(2 * k + 1) << 16) | (uint32_t)int_list[k])
+                                      : (int32_t)0xffffffffu);
+            }
+    }
+    size_t total = (size_t)S * 7 + (n_int ? n_int : 1) + (size_t)ctx->D + 1 + std::max<size_t>(sched.size(), 32);
     SR2_CUDA(ctx, cudaMalloc(&ctx->d_species_slab, total * sizeof(int32_t)));
     std::vector<int32_t> slab(total, 0);
     int32_t* h = slab.data();
@@ -279,6 +290,22 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
     ctx->dsp.parent = put(ctx->h_parent, S);
     ctx->dsp.int_list = put(ctx->h_int_list, n_int ? n_int : 1);
     ctx->dsp.int_lvl_off = put(ctx->h_int_lvl_off, (size_t)ctx->D + 1);
+    {
+        int rank_bits = 1, depth_bits = 1;
+        while ((1 << rank_bits) < S) ++rank_bits;
+        while ((1 << depth_bits) < ctx->D) ++depth_bits;
+        ctx->dsp.rank_bits = rank_bits;
+        ctx->dsp.depth_bits = depth_bits;
+        std::vector<int32_t> keylow(S), meta(S);
+        for (int y = 0; y < S; ++y) {
+            keylow[y] = (int32_t)(((uint32_t)y << depth_bits) | (uint32_t)ctx->h_depth[y]);
+            meta[y] = (int32_t)(((uint32_t)(child0[y] + 1) << 16) | (uint32_t)ctx->h_depth[y]);
+        }
+        ctx->dsp.keylow = (const uint32_t*)put(keylow, S);
+        ctx->dsp.meta = (const uint32_t*)put(meta, S);
+        ctx->dsp.n_steps = (int)(sched.size() / 32);
+        ctx->dsp.sweep_sched = (const uint32_t*)put(sched, std::max<size_t>(sched.size(), 32));
+    }
     SR2_CUDA(ctx, cudaMemcpyAsync(d, h, total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SR2_OK;

@@ -570,60 +570,89 @@ dtl_wave_flat_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     unsigned* PL = MR + rs;
     unsigned* PR = PL + rs;
     const int cl = row_cl[gr], cr = row_cr[gr];
+    const unsigned inf32 = kp.inf32, vmul = 1u << kp.sh;
 
-    // ---- load both child rows as keys (leaf children are synthesised) -------------------------
-    {
-        const int32_t* __restrict__ Tl = cl >= 0 ? T + (size_t)cl * sp.pitch : nullptr;
-        const int32_t* __restrict__ Tr = cr >= 0 ? T + (size_t)cr * sp.pitch : nullptr;
-        const int al = -1 - cl, ar = -1 - cr;
-        for (int y = lane; y < S; y += 32) {
-            unsigned low = ((unsigned)y << kp.db) | (unsigned)__ldg(sp.depth + y);
-            int vl = Tl ? Tl[y] : (y == al ? 0 : SR2_INF);
-            int vr = Tr ? Tr[y] : (y == ar ? 0 : SR2_INF);
-            ML[y] = ((vl >= SR2_INF ? kp.inf32 : (unsigned)vl) << kp.sh) | low;
-            MR[y] = ((vr >= SR2_INF ? kp.inf32 : (unsigned)vr) << kp.sh) | low;
+    // ---- load both child rows as keys: key = min(value, inf) * 2^sh + (rank, depth) ------------
+    // Global loads are issued four species-chunks at a time per side (8 in flight per lane)
+    // before any of them is consumed; a leaf child's row (0 at one species, infinite elsewhere)
+    // is synthesised without touching memory.
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const int c = side ? cr : cl;
+        unsigned* dst = side ? MR : ML;
+        if (c >= 0) {
+            const int32_t* __restrict__ src = T + (size_t)c * sp.pitch;
+#pragma unroll 1
+            for (int y0 = 0; y0 < S; y0 += 128) {
+                unsigned v[4], low[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int y = y0 + k * 32 + lane;
+                    v[k] = y < S ? (unsigned)src[y] : 0u;
+                    low[k] = y < S ? __ldg(sp.keylow + y) : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int y = y0 + k * 32 + lane;
+                    if (y < S) dst[y] = min(v[k], inf32) * vmul + low[k];
+                }
+            }
+        } else {
+            const int a = -1 - c;
+#pragma unroll 1
+            for (int y = lane; y < S; y += 32) dst[y] = (y == a ? 0u : inf32 * vmul) + __ldg(sp.keylow + y);
         }
     }
     __syncwarp();
 
-    // ---- up-sweep: SUBMIN in place -------------------------------------------------------------
-    for (int d = sp.D - 2; d >= 0; --d) {
-        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
-        for (int i = b + lane; i < e; i += 32) {
-            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
-            uint2 kl = *reinterpret_cast<const uint2*>(ML + c);
-            uint2 kr = *reinterpret_cast<const uint2*>(MR + c);
-            ML[p] = min(ML[p], min(kl.x, kl.y));
-            MR[p] = min(MR[p], min(kr.x, kr.y));
+    // ---- up-sweep: SUBMIN in place, following the precomputed schedule bottom-up -----------------
+    {
+        const uint32_t* __restrict__ sched = sp.sweep_sched + lane;
+#pragma unroll 1
+        for (int step = sp.n_steps - 1; step >= 0; --step) {
+            const unsigned w = __ldg(sched + step * 32);
+            if (w != 0xffffffffu) {
+                const int p = (int)(w & 0xffffu), c = (int)(w >> 16);
+                const uint2 kl = *reinterpret_cast<const uint2*>(ML + c);
+                const uint2 kr = *reinterpret_cast<const uint2*>(MR + c);
+                ML[p] = min(ML[p], min(kl.x, kl.y));
+                MR[p] = min(MR[p], min(kr.x, kr.y));
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 
-    // ---- top-down sweep: SEPMIN into PL/PR -------------------------------------------------------
+    // ---- top-down sweep: SEPMIN into PL/PR ---------------------------------------------------------
     if (lane == 0) {
         PL[0] = 0xffffffffu;  // nothing is incomparable to the root
         PR[0] = 0xffffffffu;
     }
     __syncwarp();
-    for (int d = 0; d < sp.D - 1; ++d) {
-        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
-        for (int i = b + lane; i < e; i += 32) {
-            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
-            uint2 kl = *reinterpret_cast<const uint2*>(ML + c);
-            uint2 kr = *reinterpret_cast<const uint2*>(MR + c);
-            unsigned ppl = PL[p], ppr = PR[p];
-            *reinterpret_cast<uint2*>(PL + c) = make_uint2(min(ppl, kl.y), min(ppl, kl.x));
-            *reinterpret_cast<uint2*>(PR + c) = make_uint2(min(ppr, kr.y), min(ppr, kr.x));
+    {
+        const uint32_t* __restrict__ sched = sp.sweep_sched + lane;
+#pragma unroll 1
+        for (int step = 0; step < sp.n_steps; ++step) {
+            const unsigned w = __ldg(sched + step * 32);
+            if (w != 0xffffffffu) {
+                const int p = (int)(w & 0xffffu), c = (int)(w >> 16);
+                const uint2 kl = *reinterpret_cast<const uint2*>(ML + c);
+                const uint2 kr = *reinterpret_cast<const uint2*>(MR + c);
+                const unsigned ppl = PL[p], ppr = PR[p];
+                *reinterpret_cast<uint2*>(PL + c) = make_uint2(min(ppl, kl.y), min(ppl, kl.x));
+                *reinterpret_cast<uint2*>(PR + c) = make_uint2(min(ppr, kr.y), min(ppr, kr.x));
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 
-    // ---- cells: element-wise over species ----------------------------------------------------------
+    // ---- cells: element-wise over species -------------------------------------------------------------
     int32_t* __restrict__ Tout = T + slot * sp.pitch;
     uint32_t* __restrict__ Gout = tags + slot * sp.pitch;
     const int loss = cs.loss, NONE = 0x7fffffff;
+#pragma unroll 1
     for (int x = lane; x < S; x += 32) {
-        const int dx = __ldg(sp.depth + x), cx = __ldg(sp.child0 + x);
+        const unsigned meta = __ldg(sp.meta + x);
+        const int dx = (int)(meta & 0xffffu), cx = (int)(meta >> 16) - 1;
         const unsigned Ml = ML[x], Mr = MR[x], Pl = PL[x], Pr = PR[x];
         const int qMl = key_q(Ml, loss, kp), qMr = key_q(Mr, loss, kp);
         int w1 = NONE, w2 = NONE, w4 = NONE, w5 = NONE;
@@ -886,8 +915,8 @@ static int ceil_log2(int v) {
 
 static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
     const int S = ctx->S;
-    p->rank_bits = std::max(1, ceil_log2(S));
-    p->depth_bits = std::max(1, ceil_log2(ctx->D));
+    p->rank_bits = ctx->dsp.rank_bits;
+    p->depth_bits = ctx->dsp.depth_bits;
     int value_bits = 32 - p->rank_bits - p->depth_bits;
     p->simd_arr_words = (S * SIMD_LD + 31) / 32 * 32;
     p->simd_smem = ((size_t)4 * p->simd_arr_words + 64) * sizeof(unsigned);

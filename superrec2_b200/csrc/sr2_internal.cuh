@@ -35,6 +35,17 @@ struct DevSpecies {
     const int32_t* parent;      // [S]
     const int32_t* int_list;    // [n_internal] BFS ranks of the internal nodes, BFS order
     const int32_t* int_lvl_off; // [D+1] offsets into int_list per depth
+    // packed per-species words for the 32-bit-key kernels (rank_bits = ceil log2 S,
+    // depth_bits = ceil log2 D):
+    const uint32_t* keylow;     // [S]  rank << depth_bits | depth  (low part of a 32-bit key)
+    const uint32_t* meta;       // [S]  (child0 + 1) << 16 | depth  (0 in the high half for leaves)
+    int rank_bits, depth_bits;
+    // sweep schedule for the warp-per-row kernels: n_steps rows of 32 words, step k word l =
+    // (first child rank c) << 16 | (rank p) of the internal species handled by lane l, or
+    // 0xffffffff when the lane idles; steps are in top-down level order and one level never
+    // shares a step with another (levels wider than 32 take several steps)
+    const uint32_t* sweep_sched;
+    int n_steps;
 };
 
 struct DtlProblem;
