@@ -267,7 +267,8 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
                                       : (int32_t)0xffffffffu);
             }
     }
-    size_t total = (size_t)S * 7 + (n_int ? n_int : 1) + (size_t)ctx->D + 1 + std::max<size_t>(sched.size(), 32);
+    size_t total = (size_t)S * 7 + (n_int ? n_int : 1) + (size_t)ctx->D + 1 + std::max<size_t>(sched.size(), 32) +
+                   (size_t)S * 4 + 8;
     SR2_CUDA(ctx, cudaMalloc(&ctx->d_species_slab, total * sizeof(int32_t)));
     std::vector<int32_t> slab(total, 0);
     int32_t* h = slab.data();
@@ -305,6 +306,15 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
         ctx->dsp.meta = (const uint32_t*)put(meta, S);
         ctx->dsp.n_steps = (int)(sched.size() / 32);
         ctx->dsp.sweep_sched = (const uint32_t*)put(sched, std::max<size_t>(sched.size(), 32));
+        off = (off + 3) / 4 * 4;  // 16-byte alignment (the slab itself is 256-byte aligned)
+        std::vector<int32_t> span(4 * (size_t)S);
+        for (int y = 0; y < S; ++y) {
+            span[4 * y + 0] = ctx->h_tin[y];
+            span[4 * y + 1] = ctx->h_tout[y];
+            span[4 * y + 2] = meta[y];
+            span[4 * y + 3] = child0[y] >= 0 ? ctx->h_tin[child0[y] + 1] : ctx->h_tout[y];
+        }
+        ctx->dsp.span4 = (const uint4*)put(span, 4 * (size_t)S);
     }
     SR2_CUDA(ctx, cudaMemcpyAsync(d, h, total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

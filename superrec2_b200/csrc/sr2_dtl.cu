@@ -239,14 +239,14 @@ dtl_cherry_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32
     int32_t* __restrict__ Tout = T + slot * sp.pitch;
     uint32_t* __restrict__ Gout = tags + slot * sp.pitch;
     for (int x = lane; x < sp.S; x += 32) {
-        int tx = __ldg(sp.tin + x), ox = __ldg(sp.tout + x), dx = __ldg(sp.depth + x);
-        int cx = __ldg(sp.child0 + x);
+        const uint4 sx = __ldg(sp.span4 + x);
+        const int tx = (int)sx.x, ox = (int)sx.y, dx = (int)(sx.z & 0xffffu), t1 = (int)sx.w;
+        const bool internal = (sx.z >> 16) != 0;
         bool in_a = tx <= ta && ta < ox, in_b = tx <= tb && tb < ox;
         int best = SR2_INF;
-        if (cx >= 0 && in_a && in_b && ta > tx && tb > tx) {
-            int t1 = __ldg(sp.tin + cx + 1);  // subtree(cx) = [tx+1, t1), subtree(cx+1) = [t1, ox)
-            if ((ta < t1) != (tb < t1)) best = cs.loss * (da + db - 2 * dx - 2);  // candidates 1 / 2
-        }
+        // candidates 1 / 2: subtree(first child) = [tx+1, t1), subtree(second child) = [t1, ox)
+        if (internal && in_a && in_b && ta > tx && tb > tx && ((ta < t1) != (tb < t1)))
+            best = cs.loss * (da + db - 2 * dx - 2);
         if (in_a && in_b) {  // 3. duplication
             int v = cs.dup + cs.loss * (da + db - 2 * dx);
             if (v < best) best = v;
@@ -557,90 +557,87 @@ __global__ void __launch_bounds__(256)
 dtl_wave_flat_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                      int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
                      uint32_t* __restrict__ tags, DtlCosts cs, int rs, Key32 kp) {
-    extern __shared__ unsigned smem32[];
+    extern __shared__ uint2 smem64[];
     const int S = sp.S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int local = blockIdx.x * nwarps + warp;
     if (local >= n_rows) return;
     const int64_t gr = row_begin + local;
     const size_t slot = (size_t)(gr - chunk_row0);
-    // element y of an array lives at word y + 1
-    unsigned* ML = smem32 + (size_t)warp * 4 * rs + 1;
-    unsigned* MR = ML + rs;
-    unsigned* PL = MR + rs;
-    unsigned* PR = PL + rs;
+    // Per row two arrays of (left-child key, right-child key) pairs: M (SUBMIN) and P (SEPMIN).
+    // Element y lives at index y + 1, so the pair of children (2i+1, 2i+2) of a species is one
+    // aligned 16-byte word.
+    uint2* M = smem64 + (size_t)warp * 2 * rs + 1;
+    uint2* P = M + rs;
     const int cl = row_cl[gr], cr = row_cr[gr];
     const unsigned inf32 = kp.inf32, vmul = 1u << kp.sh;
 
     // ---- load both child rows as keys: key = min(value, inf) * 2^sh + (rank, depth) ------------
-    // Global loads are issued four species-chunks at a time per side (8 in flight per lane)
-    // before any of them is consumed; a leaf child's row (0 at one species, infinite elsewhere)
-    // is synthesised without touching memory.
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        const int c = side ? cr : cl;
-        unsigned* dst = side ? MR : ML;
-        if (c >= 0) {
-            const int32_t* __restrict__ src = T + (size_t)c * sp.pitch;
+    // All global loads of a 128-species chunk (both children + the shared low key words, up to
+    // 12 per lane) are issued before any is consumed; a leaf child's row (0 at one species,
+    // infinite elsewhere) is synthesised without touching memory.
+    {
+        const int32_t* __restrict__ Tl = T + (size_t)(cl >= 0 ? cl : 0) * sp.pitch;
+        const int32_t* __restrict__ Tr = T + (size_t)(cr >= 0 ? cr : 0) * sp.pitch;
+        const bool il = cl >= 0, ir = cr >= 0;
+        const int al = -1 - cl, ar = -1 - cr;
 #pragma unroll 1
-            for (int y0 = 0; y0 < S; y0 += 128) {
-                unsigned v[4], low[4];
+        for (int y0 = 0; y0 < S; y0 += 128) {
+            unsigned vl[4], vr[4], low[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int y = y0 + k * 32 + lane;
-                    v[k] = y < S ? (unsigned)src[y] : 0u;
-                    low[k] = y < S ? __ldg(sp.keylow + y) : 0u;
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int y = y0 + k * 32 + lane;
-                    if (y < S) dst[y] = min(v[k], inf32) * vmul + low[k];
-                }
+            for (int k = 0; k < 4; ++k) {
+                const int y = y0 + k * 32 + lane;
+                const bool ok = y < S;
+                low[k] = ok ? __ldg(sp.keylow + y) : 0u;
+                vl[k] = (ok && il) ? (unsigned)Tl[y] : (y == al ? 0u : inf32);
+                vr[k] = (ok && ir) ? (unsigned)Tr[y] : (y == ar ? 0u : inf32);
             }
-        } else {
-            const int a = -1 - c;
-#pragma unroll 1
-            for (int y = lane; y < S; y += 32) dst[y] = (y == a ? 0u : inf32 * vmul) + __ldg(sp.keylow + y);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int y = y0 + k * 32 + lane;
+                if (y < S) M[y] = make_uint2(min(vl[k], inf32) * vmul + low[k], min(vr[k], inf32) * vmul + low[k]);
+            }
         }
     }
     __syncwarp();
 
-    // ---- up-sweep: SUBMIN in place, following the precomputed schedule bottom-up -----------------
+    // ---- up-sweep: SUBMIN in place, following the precomputed schedule bottom-up; the next
+    //      step's schedule word is fetched while the current step runs -----------------------------
     {
         const uint32_t* __restrict__ sched = sp.sweep_sched + lane;
+        unsigned w = sp.n_steps > 0 ? __ldg(sched + (sp.n_steps - 1) * 32) : 0xffffffffu;
 #pragma unroll 1
         for (int step = sp.n_steps - 1; step >= 0; --step) {
-            const unsigned w = __ldg(sched + step * 32);
+            const unsigned next = step > 0 ? __ldg(sched + (step - 1) * 32) : 0xffffffffu;
             if (w != 0xffffffffu) {
                 const int p = (int)(w & 0xffffu), c = (int)(w >> 16);
-                const uint2 kl = *reinterpret_cast<const uint2*>(ML + c);
-                const uint2 kr = *reinterpret_cast<const uint2*>(MR + c);
-                ML[p] = min(ML[p], min(kl.x, kl.y));
-                MR[p] = min(MR[p], min(kr.x, kr.y));
+                const uint4 k = *reinterpret_cast<const uint4*>(M + c);  // (l,r) of c and of c+1
+                const uint2 own = M[p];
+                M[p] = make_uint2(min(own.x, min(k.x, k.z)), min(own.y, min(k.y, k.w)));
             }
+            w = next;
             __syncwarp();
         }
     }
 
-    // ---- top-down sweep: SEPMIN into PL/PR ---------------------------------------------------------
-    if (lane == 0) {
-        PL[0] = 0xffffffffu;  // nothing is incomparable to the root
-        PR[0] = 0xffffffffu;
-    }
+    // ---- top-down sweep: SEPMIN into P ------------------------------------------------------------
+    if (lane == 0) P[0] = make_uint2(0xffffffffu, 0xffffffffu);  // nothing is incomparable to the root
     __syncwarp();
     {
         const uint32_t* __restrict__ sched = sp.sweep_sched + lane;
+        unsigned w = sp.n_steps > 0 ? __ldg(sched) : 0xffffffffu;
 #pragma unroll 1
         for (int step = 0; step < sp.n_steps; ++step) {
-            const unsigned w = __ldg(sched + step * 32);
+            const unsigned next = step + 1 < sp.n_steps ? __ldg(sched + (step + 1) * 32) : 0xffffffffu;
             if (w != 0xffffffffu) {
                 const int p = (int)(w & 0xffffu), c = (int)(w >> 16);
-                const uint2 kl = *reinterpret_cast<const uint2*>(ML + c);
-                const uint2 kr = *reinterpret_cast<const uint2*>(MR + c);
-                const unsigned ppl = PL[p], ppr = PR[p];
-                *reinterpret_cast<uint2*>(PL + c) = make_uint2(min(ppl, kl.y), min(ppl, kl.x));
-                *reinterpret_cast<uint2*>(PR + c) = make_uint2(min(ppr, kr.y), min(ppr, kr.x));
+                const uint4 k = *reinterpret_cast<const uint4*>(M + c);
+                const uint2 pp = P[p];
+                // incomparable(c) = incomparable(p) + subtree(c+1), and the other way round
+                *reinterpret_cast<uint4*>(P + c) =
+                    make_uint4(min(pp.x, k.z), min(pp.y, k.w), min(pp.x, k.x), min(pp.y, k.y));
             }
+            w = next;
             __syncwarp();
         }
     }
@@ -649,38 +646,41 @@ dtl_wave_flat_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     int32_t* __restrict__ Tout = T + slot * sp.pitch;
     uint32_t* __restrict__ Gout = tags + slot * sp.pitch;
     const int loss = cs.loss, NONE = 0x7fffffff;
+    const int sh = kp.sh, db = kp.db, thresh = kp.thresh;
+    const unsigned dm = kp.dm, rm = kp.rm;
 #pragma unroll 1
     for (int x = lane; x < S; x += 32) {
         const unsigned meta = __ldg(sp.meta + x);
         const int dx = (int)(meta & 0xffffu), cx = (int)(meta >> 16) - 1;
-        const unsigned Ml = ML[x], Mr = MR[x], Pl = PL[x], Pr = PR[x];
-        const int qMl = key_q(Ml, loss, kp), qMr = key_q(Mr, loss, kp);
+        const uint2 m = M[x], pq = P[x];
+        const int qMl = (int)(m.x >> sh) + loss * (int)(m.x & dm), qMr = (int)(m.y >> sh) + loss * (int)(m.y & dm);
         int w1 = NONE, w2 = NONE, w4 = NONE, w5 = NONE;
-        uint2 kl = make_uint2(0, 0), kr = make_uint2(0, 0);
+        uint4 k = make_uint4(0, 0, 0, 0);  // (l0, r0, l1, r1): keys of the two children of x
         if (cx >= 0) {
-            kl = *reinterpret_cast<const uint2*>(ML + cx);
-            kr = *reinterpret_cast<const uint2*>(MR + cx);
-            int b12 = -2 * loss * (dx + 1);
-            w1 = ((key_q(kl.x, loss, kp) + key_q(kr.y, loss, kp) + b12) << 3) | 0;  // 1. spe, l | r
-            w2 = ((key_q(kl.y, loss, kp) + key_q(kr.x, loss, kp) + b12) << 3) | 1;  // 2. spe, r | l
+            k = *reinterpret_cast<const uint4*>(M + cx);
+            const int b12 = -2 * loss * (dx + 1);
+            const int ql0 = (int)(k.x >> sh) + loss * (int)(k.x & dm), qr0 = (int)(k.y >> sh) + loss * (int)(k.y & dm);
+            const int ql1 = (int)(k.z >> sh) + loss * (int)(k.z & dm), qr1 = (int)(k.w >> sh) + loss * (int)(k.w & dm);
+            w1 = ((ql0 + qr1 + b12) << 3) | 0;  // 1. speciation, left child below x0, right below x1
+            w2 = ((ql1 + qr0 + b12) << 3) | 1;  // 2. speciation, the other way round
         }
-        int w3 = ((qMl + qMr + cs.dup - 2 * loss * dx) << 3) | 2;                    // 3. dup
+        const int w3 = ((qMl + qMr + cs.dup - 2 * loss * dx) << 3) | 2;  // 3. duplication
         if (x != 0) {
-            w4 = (((int)(Pl >> kp.sh) + qMr + cs.hgt - loss * dx) << 3) | 3;         // 4. hgt, left away
-            w5 = ((qMl + (int)(Pr >> kp.sh) + cs.hgt - loss * dx) << 3) | 4;         // 5. hgt, right away
+            w4 = (((int)(pq.x >> sh) + qMr + cs.hgt - loss * dx) << 3) | 3;  // 4. transfer, left child away
+            w5 = ((qMl + (int)(pq.y >> sh) + cs.hgt - loss * dx) << 3) | 4;  // 5. transfer, right child away
         }
-        int w = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
-        int best = w >> 3, which = w & 7;
-        unsigned ka = Ml, kb = Mr;
-        ka = which == 0 ? kl.x : ka;
-        ka = which == 1 ? kl.y : ka;
-        ka = which == 3 ? Pl : ka;
-        kb = which == 0 ? kr.y : kb;
-        kb = which == 1 ? kr.x : kb;
-        kb = which == 4 ? Pr : kb;
-        bool finite = best < kp.thresh;
+        const int w = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
+        const int best = w >> 3, which = w & 7;
+        unsigned ka = m.x, kb = m.y;
+        ka = which == 0 ? k.x : ka;
+        ka = which == 1 ? k.z : ka;
+        ka = which == 3 ? pq.x : ka;
+        kb = which == 0 ? k.w : kb;
+        kb = which == 1 ? k.y : kb;
+        kb = which == 4 ? pq.y : kb;
+        const bool finite = best < thresh;
         Tout[x] = finite ? best : SR2_INF;
-        Gout[x] = finite ? (((ka >> kp.db) & kp.rm) | (((kb >> kp.db) & kp.rm) << 16)) : SR2_NO_TAG;
+        Gout[x] = finite ? (((ka >> db) & rm) | (((kb >> db) & rm) << 16)) : SR2_NO_TAG;
     }
 }
 
@@ -938,8 +938,8 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
     // the two earlier forms (kept for comparison and as cross-checks in the tests)
     p->flat = true;
     if (const char* v = getenv("SR2_DTL_VARIANT")) p->flat = strcmp(v, "flat") == 0;
-    p->flat_rs = (S + 2 + 31) / 32 * 32 + 2;   // even (aligned uint2), = 2 mod 32 (rows in different banks)
-    p->flat_smem = (size_t)8 * 4 * p->flat_rs * sizeof(unsigned);
+    p->flat_rs = (S + 2 + 15) / 16 * 16 + 2;   // uint2 elements per array; even (aligned uint4 pairs)
+    p->flat_smem = (size_t)8 * 2 * p->flat_rs * sizeof(uint2);
     if (p->flat_smem > ctx->smem_optin) p->flat = false;
     if (p->simd_ok && p->flat)
         SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -46,6 +46,9 @@ struct DevSpecies {
     // shares a step with another (levels wider than 32 take several steps)
     const uint32_t* sweep_sched;
     int n_steps;
+    // [S] x 4 words: tin, tout, (child0 + 1) << 16 | depth, tin of the second child (or tout):
+    // everything the closed-form cherry cells need about a species in one 16-byte load
+    const uint4* span4;
 };
 
 struct DtlProblem;
