@@ -229,7 +229,7 @@ def main():
 
     # ---- dtl ----------------------------------------------------------------
     small = []
-    for i in range(160):
+    for i in range(420):
         n_s = rng.randint(1, 7)
         n_o = rng.randint(1, 9)
         mode = ["default", "zero", "spe", "random"][i % 4]
@@ -259,7 +259,7 @@ def main():
 
     # ---- superdtl -------------------------------------------------------------
     ssmall = []
-    for i in range(140):
+    for i in range(380):
         n_s = rng.randint(1, 6)
         n_o = rng.randint(1, 8)
         mode = ["default", "zero", "spe", "random"][i % 4]
@@ -270,7 +270,7 @@ def main():
     write("superdtl_small.json.gz", ssmall)
 
     spoly = []
-    for i in range(24):
+    for i in range(60):
         n_s = rng.randint(2, 5)
         n_o = rng.randint(3, 7)
         mode = ["default", "random", "spe"][i % 3]
