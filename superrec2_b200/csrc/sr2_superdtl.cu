@@ -59,30 +59,7 @@ struct SuperProblem {
 void sr2_free_super(sr2_ctx* ctx) {
     SuperProblem* p = ctx->super;
     if (!p) return;
-    p->rows.release();
-    cudaFree(p->d_left);
-    cudaFree(p->d_right);
-    cudaFree(p->d_node_off);
-    cudaFree(p->d_bits);
-    cudaFree(p->d_present);
-    cudaFree(p->d_outside);
-    cudaFree(p->d_gain);
-    cudaFree(p->d_L);
-    cudaFree(p->d_row_flags);
-    cudaFree(p->d_T);
-    cudaFree(p->d_tag);
-    cudaFree(p->d_dec);
-    cudaFree(p->d_anc);
-    cudaFree(p->d_tau);
-    cudaFree(p->d_taumin);
-    cudaFree(p->d_cost);
-    cudaFree(p->d_min_cost);
-    cudaFree(p->d_root_species);
-    cudaFree(p->d_map);
-    cudaFree(p->d_kind);
-    cudaFree(p->d_syn);
-    cudaFree(p->d_best);
-    delete p;
+    delete p;  // device buffers live in the context's pools
     ctx->super = nullptr;
 }
 
@@ -584,6 +561,8 @@ extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_
 
     size_t free_b = 0, total_b = 0;
     SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    for (int id = DP_S_LEFT; id <= DP_S_BEST; ++id) free_b += sr2_dev_pooled(ctx, id);
+    free_b += sr2_dev_pooled(ctx, DP_ROWS_SLAB);
     size_t per_row = (size_t)ctx->pitch * 16 + 1;
     size_t fixed = (size_t)N * (4 * 9 + (size_t)W * 4 * 6 + (size_t)W * 128 + (size_t)S * 4) +
                    (size_t)B * ((size_t)S * 4 + 32) + (64u << 20);
@@ -610,30 +589,37 @@ extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_
             gl[u] = left[u] < 0 ? -1 : (int32_t)(node_off[b] + left[u]);
             grt[u] = right[u] < 0 ? -1 : (int32_t)(node_off[b] + right[u]);
         }
-    auto alloc = [&](void** ptr, size_t bytes) { return cudaMalloc(ptr, std::max<size_t>(bytes, 16)); };
     size_t nw = (size_t)N * W;
-    SR2_CUDA(ctx, alloc((void**)&p->d_left, (size_t)N * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_right, (size_t)N * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_node_off, (size_t)(B + 1) * 8));
-    SR2_CUDA(ctx, alloc((void**)&p->d_bits, nw * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_present, nw * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_outside, nw * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_gain, nw * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_L, nw * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_row_flags, (size_t)R));
-    SR2_CUDA(ctx, alloc((void**)&p->d_T, (size_t)R * 2 * ctx->pitch * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_tag, (size_t)R * 2 * ctx->pitch * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_dec, (size_t)N * S * 2));
-    SR2_CUDA(ctx, alloc((void**)&p->d_anc, (size_t)N * S * 2));
-    SR2_CUDA(ctx, alloc((void**)&p->d_tau, nw * 32 * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_taumin, (size_t)N * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_cost, (size_t)B * S * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_min_cost, (size_t)B * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_root_species, (size_t)B * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_map, (size_t)N * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_kind, (size_t)N * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_syn, nw * 4));
-    SR2_CUDA(ctx, alloc((void**)&p->d_best, 8));
+#define SR2_RESERVE(id, field, bytes)                                   \
+    do {                                                                \
+        void* ptr__ = nullptr;                                          \
+        int rc__ = sr2_dev_reserve(ctx, id, (bytes), &ptr__);           \
+        if (rc__) return rc__;                                          \
+        p->field = (decltype(p->field))ptr__;                           \
+    } while (0)
+    SR2_RESERVE(DP_S_LEFT, d_left, (size_t)N * 4);
+    SR2_RESERVE(DP_S_RIGHT, d_right, (size_t)N * 4);
+    SR2_RESERVE(DP_S_NODEOFF, d_node_off, (size_t)(B + 1) * 8);
+    SR2_RESERVE(DP_S_BITS, d_bits, nw * 4);
+    SR2_RESERVE(DP_S_PRESENT, d_present, nw * 4);
+    SR2_RESERVE(DP_S_OUTSIDE, d_outside, nw * 4);
+    SR2_RESERVE(DP_S_GAIN, d_gain, nw * 4);
+    SR2_RESERVE(DP_S_L, d_L, nw * 4);
+    SR2_RESERVE(DP_S_FLAGS, d_row_flags, (size_t)R);
+    SR2_RESERVE(DP_S_T, d_T, (size_t)R * 2 * ctx->pitch * 4);
+    SR2_RESERVE(DP_S_TAG, d_tag, (size_t)R * 2 * ctx->pitch * 4);
+    SR2_RESERVE(DP_S_DEC, d_dec, (size_t)N * S * 2);
+    SR2_RESERVE(DP_S_ANC, d_anc, (size_t)N * S * 2);
+    SR2_RESERVE(DP_S_TAU, d_tau, nw * 32 * 4);
+    SR2_RESERVE(DP_S_TAUMIN, d_taumin, (size_t)N * 4);
+    SR2_RESERVE(DP_S_COST, d_cost, (size_t)B * S * 4);
+    SR2_RESERVE(DP_S_MINCOST, d_min_cost, (size_t)B * 4);
+    SR2_RESERVE(DP_S_ROOTSP, d_root_species, (size_t)B * 4);
+    SR2_RESERVE(DP_S_MAP, d_map, (size_t)N * 4);
+    SR2_RESERVE(DP_S_KIND, d_kind, (size_t)N * 4);
+    SR2_RESERVE(DP_S_SYN, d_syn, nw * 4);
+    SR2_RESERVE(DP_S_BEST, d_best, 8);
+#undef SR2_RESERVE
     cudaStream_t st = ctx->stream;
     SR2_CUDA(ctx, cudaMemcpyAsync(p->d_left, gl.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
     SR2_CUDA(ctx, cudaMemcpyAsync(p->d_right, grt.data(), (size_t)N * 4, cudaMemcpyHostToDevice, st));
