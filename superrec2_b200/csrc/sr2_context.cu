@@ -267,8 +267,18 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
                                       : (int32_t)0xffffffffu);
             }
     }
-    size_t total = (size_t)S * 7 + (n_int ? n_int : 1) + (size_t)ctx->D + 1 + std::max<size_t>(sched.size(), 32) +
-                   (size_t)S * 4 + 8;
+    // the same schedule for dtl_wave_flat2_kernel: byte offsets into a row's M array
+    // (element y at index y + 1, 8 bytes each); idle lanes work on dummy slots behind the row
+    const int flat_rs = ctx->pitch + 8;
+    std::vector<int32_t> sched2(std::max<size_t>(sched.size(), 32 * 32));  // padded to 32 steps with idle words
+    for (size_t i = 0; i < sched2.size(); ++i) {
+        uint32_t w = i < sched.size() ? (uint32_t)sched[i] : 0xffffffffu;
+        uint32_t p_idx = w == 0xffffffffu ? (uint32_t)ctx->pitch + 6 : (w & 0xffffu) + 1;
+        uint32_t c_idx = w == 0xffffffffu ? (uint32_t)ctx->pitch + 4 : (w >> 16) + 1;
+        sched2[i] = (int32_t)((c_idx * 8) << 16 | (p_idx * 8));
+    }
+    size_t total = (size_t)S * 7 + (n_int ? n_int : 1) + (size_t)ctx->D + 1 + std::max<size_t>(sched.size(), 32) + sched2.size() +
+                   (size_t)S * 4 + 2 * (size_t)ctx->pitch + 16;
     SR2_CUDA(ctx, cudaMalloc(&ctx->d_species_slab, total * sizeof(int32_t)));
     std::vector<int32_t> slab(total, 0);
     int32_t* h = slab.data();
@@ -306,6 +316,18 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
         ctx->dsp.meta = (const uint32_t*)put(meta, S);
         ctx->dsp.n_steps = (int)(sched.size() / 32);
         ctx->dsp.sweep_sched = (const uint32_t*)put(sched, std::max<size_t>(sched.size(), 32));
+        ctx->dsp.flat_rs = (size_t)flat_rs * 8 * 2 <= 65535 ? flat_rs : 0;  // 16-bit byte offsets
+        ctx->dsp.flat_sched = (const uint32_t*)put(sched2, sched2.size());
+        // per-species words padded to the row pitch (the flat2 kernel runs over whole pitches)
+        std::vector<int32_t> keylow_p(ctx->pitch, 0), cmeta(ctx->pitch, 0);
+        for (int y = 0; y < ctx->pitch; ++y) {
+            int depth = y < S ? ctx->h_depth[y] : 0;
+            int pair_idx = (y < S && child0[y] >= 0) ? child0[y] + 1 : ctx->pitch + 2;  // leaves: the infinite pair
+            keylow_p[y] = (int32_t)(((uint32_t)y << depth_bits) | (uint32_t)depth);
+            cmeta[y] = (int32_t)(((uint32_t)(pair_idx * 8) << 16) | (uint32_t)depth);
+        }
+        ctx->dsp.keylow_p = (const uint32_t*)put(keylow_p, ctx->pitch);
+        ctx->dsp.cmeta = (const uint32_t*)put(cmeta, ctx->pitch);
         off = (off + 3) / 4 * 4;  // 16-byte alignment (the slab itself is 256-byte aligned)
         std::vector<int32_t> span(4 * (size_t)S);
         for (int y = 0; y < S; ++y) {

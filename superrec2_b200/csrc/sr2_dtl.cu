@@ -30,6 +30,8 @@
 // ---------------------------------------------------------------------------
 // device-resident problem
 // ---------------------------------------------------------------------------
+struct DtlCosts;
+struct Key32;
 struct DtlProblem {
     RowLayout rows;
     uint32_t flags = 0;
@@ -59,6 +61,11 @@ struct DtlProblem {
     bool flat = true;
     int flat_rs = 0;
     size_t flat_smem = 0;
+    bool flat2 = false;          // the default batched kernel when its preconditions hold
+    size_t flat2_smem = 0;
+    int flat2_sh = 0, flat2_thresh = 0;
+    void (*flat2_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
+                     Key32) = nullptr;
 };
 
 void sr2_free_dtl(sr2_ctx* ctx) {
@@ -684,6 +691,206 @@ dtl_wave_flat_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     }
 }
 
+// ---------------------------------------------------------------------------
+// Batched waves, fourth form ("flat2"): the flat kernel with its three phases put on an
+// instruction diet (the flat kernel is issue-bound, profiles/README.md r1j):
+//   * everything runs over whole row pitches (multiples of 32 species) -- no bounds tests;
+//     pad cells hold garbage that nothing reads;
+//   * child rows become keys with ONE multiply-add: value * 2^sh + (rank, depth).  The stored
+//     infinity 0x3fffffff wraps to an all-ones value field, which is the infinite key;
+//   * the sweep schedule (DevSpecies::flat_sched) lives in registers as absolute shared-memory
+//     addresses (child pair << 16 | parent, CTA shared memory < 64 KB), so a sweep step is
+//     2 address ops + 2 loads + min + store; idle lanes work on dummy slots, not on predicates;
+//   * cells: per-species words come from shared memory; leaves point their "child pair" at an
+//     always-infinite pair and the root's SEPMIN is the infinite key, so there is no branch.
+// Row layout in shared memory: M[0..rs) and P[0..rs) of (left key, right key) pairs, species
+// y at index y + 1 so that the children (2i+1, 2i+2) of a species are one aligned 16-byte word.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint2 lds64(unsigned a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds128(unsigned a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, unsigned x, unsigned y) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void sts128(unsigned a, unsigned x, unsigned y, unsigned z, unsigned w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+
+#define FLAT2_NS 32   // sweep steps held in registers
+#define FLAT2_NCH 16  // row chunks of 32 species held in registers (pitch <= 512)
+
+// Child rows -> keys.  Every global load of the row (up to 2 x n_chunks per lane) is issued
+// before the first one is consumed: one DRAM round trip per row.
+template <bool IL, bool IR>
+__device__ __forceinline__ void flat2_load(const int32_t* __restrict__ Tl, const int32_t* __restrict__ Tr,
+                                           const uint32_t* __restrict__ keylow, uint2* __restrict__ M,
+                                           int n_chunks, unsigned vmul, unsigned infkey) {
+    unsigned vl[FLAT2_NCH], vr[FLAT2_NCH];
+#pragma unroll
+    for (int j = 0; j < FLAT2_NCH; ++j) {
+        vl[j] = vr[j] = 0u;
+        if (j < n_chunks) {
+            if (IL) vl[j] = (unsigned)Tl[j * 32];
+            if (IR) vr[j] = (unsigned)Tr[j * 32];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < FLAT2_NCH; ++j) {
+        if (j < n_chunks) {
+            const unsigned low = __ldg(keylow + j * 32);
+            const unsigned a = IL ? vl[j] * vmul + low : infkey + low;
+            const unsigned b = IR ? vr[j] * vmul + low : infkey + low;
+            M[j * 32] = make_uint2(a, b);
+        }
+    }
+}
+
+// value + loss * depth of a key, on the FMA pipe where possible (the ALU pipe is the busy one):
+// hi32(k * 2^(32-sh)) = k >> sh
+__device__ __forceinline__ int flat2_q(unsigned k, unsigned hi_mul, unsigned dm, int loss) {
+    const int ld = loss * (int)(k & dm);
+    unsigned q;
+    asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(q) : "r"(k), "r"(hi_mul), "r"((unsigned)ld));
+    return (int)q;
+}
+__device__ __forceinline__ int flat2_pack(int sum, int idx) {  // sum * 8 + idx, as an IMAD
+    int w;
+    asm("mad.lo.s32 %0, %1, 8, %2;" : "=r"(w) : "r"(sum), "r"(idx));
+    return w;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(256, 4)
+dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                      int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
+                      uint32_t* __restrict__ tags, DtlCosts cs, Key32 kp) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int pitch = sp.pitch, rs = sp.flat_rs, n_chunks = pitch >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int local = blockIdx.x * 8 + warp;
+    if (local >= n_rows) return;
+    const int64_t gr = row_begin + local;
+    const size_t slot = (size_t)(gr - chunk_row0);
+    uint2* Mrow = reinterpret_cast<uint2*>(smem_raw) + (size_t)warp * 2 * rs;
+    uint2* M = Mrow + 1;
+    uint2* P = M + rs;
+    const unsigned Mb = (unsigned)__cvta_generic_to_shared(Mrow);
+    const unsigned pofs = (unsigned)rs * 8u;
+
+    // ---- child rows -> keys ------------------------------------------------------------------
+    const int cl = row_cl[gr], cr = row_cr[gr];
+    const unsigned vmul = 1u << kp.sh, infkey = 0xffffffffu << kp.sh;
+    {
+        const int32_t* __restrict__ Tl = T + (size_t)(cl >= 0 ? cl : 0) * pitch + lane;
+        const int32_t* __restrict__ Tr = T + (size_t)(cr >= 0 ? cr : 0) * pitch + lane;
+        const uint32_t* __restrict__ kl = sp.keylow_p + lane;
+        if (cl >= 0 && cr >= 0) flat2_load<true, true>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        else if (cl >= 0) flat2_load<true, false>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        else if (cr >= 0) flat2_load<false, true>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        else flat2_load<false, false>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+    }
+    // sweep schedule -> registers, as absolute shared-memory addresses of this warp's row
+    // (the table is padded to NS steps with idle words)
+    unsigned sw[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) sw[i] = __ldg(sp.flat_sched + i * 32 + lane) + Mb * 0x10001u;
+    // per-species words of the cells this lane will evaluate
+    unsigned meta[FLAT2_NCH];
+#pragma unroll
+    for (int j = 0; j < FLAT2_NCH; ++j) meta[j] = j < n_chunks ? __ldg(sp.cmeta + j * 32 + lane) : 0u;
+    __syncwarp();
+    if (lane == 0) {
+        // a leaf child: 0 at its own species
+        if (cl < 0) M[-1 - cl].x = __ldg(sp.keylow_p + (-1 - cl));
+        if (cr < 0) M[-1 - cr].y = __ldg(sp.keylow_p + (-1 - cr));
+        const uint2 none = make_uint2(0xffffffffu, 0xffffffffu);
+        Mrow[pitch + 2] = none;  // the "children" of a leaf species
+        Mrow[pitch + 3] = none;
+        P[0] = none;             // nothing is incomparable to the root
+    }
+    __syncwarp();
+
+    // ---- up-sweep: SUBMIN in place, deepest level first ------------------------------------------
+#pragma unroll
+    for (int i = NS - 1; i >= 0; --i) {
+        const unsigned pa = sw[i] & 0xffffu, ca = sw[i] >> 16;
+        const uint4 k = lds128(ca);
+        const uint2 own = lds64(pa);
+        sts64(pa, min(own.x, min(k.x, k.z)), min(own.y, min(k.y, k.w)));
+        __syncwarp();
+    }
+    // ---- top-down sweep: SEPMIN into P ------------------------------------------------------------
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const unsigned pa = sw[i] & 0xffffu, ca = sw[i] >> 16;
+        const uint4 k = lds128(ca);
+        const uint2 pp = lds64(pa + pofs);
+        // incomparable(c) = incomparable(p) + subtree(c+1), and the other way round
+        sts128(ca + pofs, min(pp.x, k.z), min(pp.y, k.w), min(pp.x, k.x), min(pp.y, k.y));
+        __syncwarp();
+    }
+
+    // ---- cells: element-wise over the pitch ----------------------------------------------------------
+    int32_t* __restrict__ Tout = T + slot * pitch + lane;
+    uint32_t* __restrict__ Gout = tags + slot * pitch + lane;
+    const unsigned char* Mbytes = reinterpret_cast<const unsigned char*>(Mrow);
+    const uint2* Mx = M + lane;
+    const uint2* Px = P + lane;
+    const int loss = cs.loss, db = kp.db, thresh = kp.thresh;
+    const unsigned dm = kp.dm, rm = kp.rm, hi_mul = 1u << (32 - kp.sh);
+    const int c12 = -2 * loss, c3 = cs.dup, c45 = cs.hgt;
+#pragma unroll
+    for (int j = 0; j < FLAT2_NCH; ++j) {
+        if (j < n_chunks) {
+            const uint2 m = Mx[j * 32], pq = Px[j * 32];
+            const uint4 k = *reinterpret_cast<const uint4*>(Mbytes + (meta[j] >> 16));  // (l0, r0, l1, r1)
+            const int nld = -loss * (int)(meta[j] & 0xffffu);
+            const int qMl = flat2_q(m.x, hi_mul, dm, loss), qMr = flat2_q(m.y, hi_mul, dm, loss);
+            const int ql0 = flat2_q(k.x, hi_mul, dm, loss), qr0 = flat2_q(k.y, hi_mul, dm, loss);
+            const int ql1 = flat2_q(k.z, hi_mul, dm, loss), qr1 = flat2_q(k.w, hi_mul, dm, loss);
+            const int pl = (int)__umulhi(pq.x, hi_mul), pr = (int)__umulhi(pq.y, hi_mul);
+            const int b12 = 2 * nld + c12, b3 = 2 * nld + c3, b45 = nld + c45;
+            const int w1 = flat2_pack(ql0 + qr1 + b12, 0);  // 1. speciation, left below x0, right below x1
+            const int w2 = flat2_pack(ql1 + qr0 + b12, 1);  // 2. the other way round
+            const int w3 = flat2_pack(qMl + qMr + b3, 2);   // 3. duplication
+            const int w4 = flat2_pack(pl + qMr + b45, 3);   // 4. transfer, left child away
+            const int w5 = flat2_pack(qMl + pr + b45, 4);   // 5. transfer, right child away
+            const int w = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
+            const int best = w >> 3, which = w & 7;
+            unsigned ka = m.x, kb = m.y;
+            ka = which == 0 ? k.x : ka;
+            ka = which == 1 ? k.z : ka;
+            ka = which == 3 ? pq.x : ka;
+            kb = which == 0 ? k.w : kb;
+            kb = which == 1 ? k.y : kb;
+            kb = which == 4 ? pq.y : kb;
+            const bool finite = best < thresh;
+            Tout[j * 32] = finite ? best : SR2_INF;
+            Gout[j * 32] = finite ? (((ka >> db) & rm) | (((kb >> db) & rm) << 16)) : SR2_NO_TAG;
+        }
+    }
+}
+
+// the instantiation whose register-resident schedule is the shortest that holds n_steps
+typedef void (*Flat2Fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*,
+                        DtlCosts, Key32);
+static Flat2Fn flat2_pick(int n_steps) {
+    if (n_steps <= 12) return dtl_wave_flat2_kernel<12>;
+    if (n_steps <= 16) return dtl_wave_flat2_kernel<16>;
+    if (n_steps <= 20) return dtl_wave_flat2_kernel<20>;
+    if (n_steps <= 24) return dtl_wave_flat2_kernel<24>;
+    if (n_steps <= 28) return dtl_wave_flat2_kernel<28>;
+    return dtl_wave_flat2_kernel<32>;
+}
+
 // Event cost of node (x; children at a, b) as ReconciliationOutput.cost() sees it
 // (/root/reference/src/superrec2/model/reconciliation.py:273-365).  SR2_INF = INVALID.
 __device__ __forceinline__ int dtl_event_cost(const DevSpecies& sp, int x, int a, int b,
@@ -944,6 +1151,24 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
     if (p->simd_ok && p->flat)
         SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->flat_smem));
+    // flat2 (default): needs the schedule in FLAT2_NS registers, 16-bit shared-memory addresses and
+    // at most 26 value bits (two infinite keys plus corrections, times 8, must fit an int)
+    {
+        const char* v = getenv("SR2_DTL_VARIANT");
+        int vb = std::min(32 - p->rank_bits - p->depth_bits, 26);
+        int64_t inf = vb >= 2 ? (int64_t)1 << (vb - 1) : 0;
+        p->flat2_sh = 32 - vb;
+        p->flat2_thresh = (int)(inf - slack);
+        p->flat2_smem = (size_t)8 * 2 * ctx->dsp.flat_rs * sizeof(uint2);
+        p->flat2 = (!v || strcmp(v, "flat2") == 0) && !(off && off[0] == '1') && S >= 2 && vb >= 8 &&
+                   p->max_finite + slack < inf - slack && ctx->dsp.flat_rs > 0 && ctx->dsp.n_steps <= FLAT2_NS && ctx->pitch <= 32 * FLAT2_NCH &&
+                   p->flat2_smem <= std::min<size_t>(ctx->smem_optin, 65535);
+        if (p->flat2) {
+            p->flat2_fn = flat2_pick(ctx->dsp.n_steps);
+            SR2_CUDA(ctx, cudaFuncSetAttribute((const void*)p->flat2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)p->flat2_smem));
+        }
+    }
     // rows-per-warp variant: 0 = use the 16-rows-per-CTA kernel instead
     p->multi_rpw = 2;  // measured best on B200 for |S| = 399 (profiles/README.md)
     if (const char* v = getenv("SR2_DTL_ROWS_PER_WARP")) p->multi_rpw = atoi(v);
@@ -973,7 +1198,20 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
-    if (p->simd_ok && n_rows >= 16 * (int64_t)ctx->sm_count) {
+    if (p->flat2 && n_rows >= p->simd_min_rows) {
+        Key32 kp;
+        kp.db = p->depth_bits;
+        kp.sh = p->flat2_sh;
+        kp.rm = (1u << p->rank_bits) - 1;
+        kp.dm = (1u << p->depth_bits) - 1;
+        kp.inf32 = 1u << (32 - kp.sh - 1);
+        kp.thresh = p->flat2_thresh;
+        p->flat2_fn<<<(unsigned)((n_rows + 7) / 8), 256, p->flat2_smem, ctx->stream>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs, kp);
+        SR2_CUDA(ctx, cudaGetLastError());
+        return SR2_OK;
+    }
+    if (p->simd_ok && n_rows >= p->simd_min_rows) {
         Key32 kp;
         kp.db = p->depth_bits;
         kp.sh = p->rank_bits + p->depth_bits;

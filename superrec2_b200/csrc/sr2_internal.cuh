@@ -46,6 +46,15 @@ struct DevSpecies {
     // shares a step with another (levels wider than 32 take several steps)
     const uint32_t* sweep_sched;
     int n_steps;
+    // dtl_wave_flat2_kernel: the same schedule as byte offsets (child pair << 16 | parent) into a
+    // row's shared-memory array of flat_rs 8-byte elements (element y at index y + 1; behind the
+    // pitch: index pitch+2,+3 = an always-infinite pair, +4,+5 / +6 = dummies for idle lanes);
+    // flat_rs == 0: offsets do not fit 16 bits.  keylow_p / cmeta: [pitch] padded per-species words,
+    // cmeta = (byte offset of the child pair, or of the infinite pair for leaves) << 16 | depth
+    const uint32_t* flat_sched;
+    int flat_rs;
+    const uint32_t* keylow_p;
+    const uint32_t* cmeta;
     // [S] x 4 words: tin, tout, (child0 + 1) << 16 | depth, tin of the second child (or tout):
     // everything the closed-form cherry cells need about a species in one 16-byte load
     const uint4* span4;

@@ -164,7 +164,7 @@ def test_bad_input_is_rejected(ctx):
     (200, 210, 3, (0, 1, 1, 1, 1)),
 ])
 @pytest.mark.parametrize("variant,rows_per_warp", [
-    ("flat", 0), ("multi", 0), ("multi", 1), ("multi", 2), ("multi", 4), ("multi", 8)])
+    ("flat2", 0), ("flat", 0), ("multi", 0), ("multi", 1), ("multi", 2), ("multi", 4), ("multi", 8)])
 def test_batched_wave_kernels_against_oracle(ctx, monkeypatch, n_s, n_o, n_trees, costs, variant,
                                              rows_per_warp):
     """Force the batched-wave kernels (32-bit keys) on small batches, including partial last
