@@ -154,6 +154,10 @@ extern "C" void sr2_destroy(sr2_ctx* ctx) {
     for (auto& pool : ctx->host) free(pool.ptr);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -21,6 +21,7 @@
 // (reconciliation.py:97-108,153-183), so cell values depend on that tie-break.
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <omp.h>
@@ -45,6 +46,15 @@ struct DtlProblem {
     int32_t* d_root_species = nullptr;  // [B]
     int32_t* d_map = nullptr;        // [N]
     bool solved = false;
+    bool prepared = false;           // buffers reserved, kernels configured
+    bool wait_rows = false;          // sr2_dtl_run: row arrays arrive chunk by chunk on the upload stream
+    bool two_streams = false;        // pipelined run: chunks alternate between two streams / table sets
+    cudaStream_t cur_stream = nullptr;  // the chunk being enqueued: its stream and tables
+    int32_t* cur_T = nullptr;
+    uint32_t* cur_tag = nullptr;
+    int32_t* cur_C = nullptr;
+    std::vector<cudaEvent_t> ev_w0, ev_w1, ev_done;  // per chunk: waves begin / end, chunk finished
+    int n_waves = 0, n_launch = 0;
     // wave launch configuration (fixed per upload)
     int spad = 0, wave_warps = 0;
     size_t wave_smem = 0;
@@ -71,6 +81,8 @@ struct DtlProblem {
 void sr2_free_dtl(sr2_ctx* ctx) {
     DtlProblem* p = ctx->dtl;
     if (!p) return;
+    for (auto* list : {&p->ev_w0, &p->ev_w1, &p->ev_done})
+        for (cudaEvent_t e : *list) cudaEventDestroy(e);
     delete p;  // device buffers live in the context's pools
     ctx->dtl = nullptr;
 }
@@ -1033,9 +1045,51 @@ int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64
     return SR2_OK;
 }
 
-extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
-                              const int32_t* left, const int32_t* right,
-                              const int32_t* leaf_species, const int32_t costs[5], uint32_t flags) {
+// Everything of an upload that needs the plan of the batch (chunks, sizes) but not its rows:
+// cost range check, table buffers.  Runs as the on_plan hook of sr2_build_rows.
+static int dtl_prepare(void* user) {
+    sr2_ctx* ctx = (sr2_ctx*)user;
+    DtlProblem* p = ctx->dtl;
+    const size_t B = p->rows.B, N = p->rows.N;
+    int rc = sr2_check_costs(ctx, "sr2_dtl_upload", p->costs, p->rows.max_nodes, &p->max_finite);
+    if (rc) return rc;
+    if ((p->flags & SR2_KEEP_TABLES) && p->rows.chunks.size() > 1)
+        return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: SR2_KEEP_TABLES needs the batch to fit in one chunk");
+    size_t table_elems = (size_t)std::max<int64_t>(p->rows.max_chunk_rows, 1) * ctx->pitch;
+    if (p->two_streams) {
+        table_elems *= 2;
+        if (!ctx->stream2) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    }
+    void* ptr = nullptr;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_MINCOST, std::max<size_t>(B, 1) * sizeof(int32_t), &ptr))) return rc;
+    p->d_min_cost = (int32_t*)ptr;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_ROOTSP, std::max<size_t>(B, 1) * sizeof(int32_t), &ptr))) return rc;
+    p->d_root_species = (int32_t*)ptr;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_MAP, std::max<size_t>(N, 1) * sizeof(int32_t), &ptr))) return rc;
+    p->d_map = (int32_t*)ptr;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_T, table_elems * sizeof(int32_t), &ptr))) return rc;
+    p->d_T = (int32_t*)ptr;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_TAG, table_elems * sizeof(uint32_t), &ptr))) return rc;
+    p->d_tag = (uint32_t*)ptr;
+    if (p->need_decoded_cost) {
+        if ((rc = sr2_dev_reserve(ctx, DP_DTL_C, table_elems * sizeof(int32_t), &ptr))) return rc;
+        p->d_C = (int32_t*)ptr;
+    }
+    for (auto* list : {&p->ev_w0, &p->ev_w1, &p->ev_done})
+        while (list->size() < p->rows.chunks.size()) {
+            cudaEvent_t e;
+            SR2_CUDA(ctx, cudaEventCreate(&e));
+            list->push_back(e);
+        }
+    p->prepared = true;
+    return SR2_OK;
+}
+
+// pipeline_chunks > 1: split the batch into about that many instance chunks even when it would fit
+// in one, so that sr2_dtl_run can solve chunk k on the device while the host buckets chunk k+1.
+static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, const int32_t* left,
+                           const int32_t* right, const int32_t* leaf_species, const int32_t costs[5],
+                           uint32_t flags, int pipeline_chunks, const RowHooks* hooks) {
     if (!ctx) return SR2_ERR_ARG;
     double t0 = now_ms();
     if (ctx->S == 0) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_upload: call sr2_set_species first");
@@ -1062,34 +1116,32 @@ extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
     if (free_b < fixed + per_row * 4)
         return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: batch does not fit in device memory");
     int64_t rows_budget = (int64_t)(((free_b - fixed) / 10 * 9) / per_row);
-    int rc = sr2_build_rows(ctx, "sr2_dtl_upload", B, node_off, left, right, leaf_species, rows_budget,
-                            (flags & SR2_KEEP_TABLES) != 0, false, &p->rows);
-    if (rc) return rc;
-    rc = sr2_check_costs(ctx, "sr2_dtl_upload", costs, p->rows.max_nodes, &p->max_finite);
-    if (rc) return rc;
-    if ((flags & SR2_KEEP_TABLES) && p->rows.chunks.size() > 1)
-        return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: SR2_KEEP_TABLES needs the batch to fit in one chunk");
-
-    size_t table_elems = (size_t)std::max<int64_t>(p->rows.max_chunk_rows, 1) * ctx->pitch;
-    {
-        void* ptr = nullptr;
-        if ((rc = sr2_dev_reserve(ctx, DP_DTL_MINCOST, std::max<size_t>(B, 1) * sizeof(int32_t), &ptr))) return rc;
-        p->d_min_cost = (int32_t*)ptr;
-        if ((rc = sr2_dev_reserve(ctx, DP_DTL_ROOTSP, std::max<size_t>(B, 1) * sizeof(int32_t), &ptr))) return rc;
-        p->d_root_species = (int32_t*)ptr;
-        if ((rc = sr2_dev_reserve(ctx, DP_DTL_MAP, std::max<size_t>(N, 1) * sizeof(int32_t), &ptr))) return rc;
-        p->d_map = (int32_t*)ptr;
-        if ((rc = sr2_dev_reserve(ctx, DP_DTL_T, table_elems * sizeof(int32_t), &ptr))) return rc;
-        p->d_T = (int32_t*)ptr;
-        if ((rc = sr2_dev_reserve(ctx, DP_DTL_TAG, table_elems * sizeof(uint32_t), &ptr))) return rc;
-        p->d_tag = (uint32_t*)ptr;
-        if (p->need_decoded_cost) {
-            if ((rc = sr2_dev_reserve(ctx, DP_DTL_C, table_elems * sizeof(int32_t), &ptr))) return rc;
-            p->d_C = (int32_t*)ptr;
-        }
+    int64_t first_chunk_rows = 0;
+    p->two_streams = pipeline_chunks > 1 && !(flags & SR2_KEEP_TABLES) && hooks && hooks->on_chunk;
+    if (p->two_streams) rows_budget /= 2;  // two sets of tables
+    if (pipeline_chunks > 1 && !(flags & SR2_KEEP_TABLES)) {
+        int64_t rows_est = (N - B) / 2;
+        int64_t per_chunk = (rows_est + pipeline_chunks - 1) / pipeline_chunks;
+        // a chunk should still fill the machine's big-wave kernels
+        per_chunk = std::max<int64_t>(per_chunk, 64 * 8 * (int64_t)ctx->sm_count);
+        rows_budget = std::min(rows_budget, per_chunk);
+        first_chunk_rows = rows_budget / 2;
     }
+    RowHooks plan_only;
+    plan_only.user = ctx;
+    plan_only.on_plan = dtl_prepare;
+    int rc = sr2_build_rows(ctx, "sr2_dtl_upload", B, node_off, left, right, leaf_species, rows_budget,
+                            (flags & SR2_KEEP_TABLES) != 0, false, &p->rows, hooks ? hooks : &plan_only,
+                            first_chunk_rows);
+    if (rc) return rc;
     ctx->timing.upload_ms = (float)(now_ms() - t0);
     return SR2_OK;
+}
+
+extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
+                              const int32_t* left, const int32_t* right,
+                              const int32_t* leaf_species, const int32_t costs[5], uint32_t flags) {
+    return dtl_upload_impl(ctx, B, node_off, left, right, leaf_species, costs, flags, 1, nullptr);
 }
 
 static int dtl_configure_waves(sr2_ctx* ctx, DtlProblem* p) {
@@ -1112,12 +1164,6 @@ static int dtl_configure_waves(sr2_ctx* ctx, DtlProblem* p) {
                                            (int)p->wave_smem));
     }
     return SR2_OK;
-}
-
-static int ceil_log2(int v) {
-    int bits = 0;
-    while ((1 << bits) < v) ++bits;
-    return bits;
 }
 
 static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
@@ -1193,8 +1239,8 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
                            int64_t n_rows, const DtlCosts& cs) {
     if (n_rows <= 0) return SR2_OK;
     if (h == 1) {  // both children of a height-1 node are leaves
-        dtl_cherry_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, ctx->stream>>>(
-            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs);
+        dtl_cherry_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, p->cur_stream>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
@@ -1206,8 +1252,8 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         kp.dm = (1u << p->depth_bits) - 1;
         kp.inf32 = 1u << (32 - kp.sh - 1);
         kp.thresh = p->flat2_thresh;
-        p->flat2_fn<<<(unsigned)((n_rows + 7) / 8), 256, p->flat2_smem, ctx->stream>>>(
-            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs, kp);
+        p->flat2_fn<<<(unsigned)((n_rows + 7) / 8), 256, p->flat2_smem, p->cur_stream>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
@@ -1220,8 +1266,8 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         kp.inf32 = 1u << (32 - kp.sh - 1);
         kp.thresh = p->simd_thresh;
         if (p->flat) {
-            dtl_wave_flat_kernel<<<(unsigned)((n_rows + 7) / 8), 256, p->flat_smem, ctx->stream>>>(
-                ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
+            dtl_wave_flat_kernel<<<(unsigned)((n_rows + 7) / 8), 256, p->flat_smem, p->cur_stream>>>(
+                ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
                 p->flat_rs, kp);
             SR2_CUDA(ctx, cudaGetLastError());
             return SR2_OK;
@@ -1230,8 +1276,8 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             int rows_per_cta = 8 * p->multi_rpw;
             unsigned grid = (unsigned)((n_rows + rows_per_cta - 1) / rows_per_cta);
 #define SR2_LAUNCH_MULTI(R)                                                                              \
-    dtl_wave_multi_kernel<R><<<grid, 256, p->multi_smem, ctx->stream>>>(                                 \
-        ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, \
+    dtl_wave_multi_kernel<R><<<grid, 256, p->multi_smem, p->cur_stream>>>(                                 \
+        ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, \
         cs, p->multi_rs, kp)
             if (p->multi_rpw == 1) SR2_LAUNCH_MULTI(1);
             else if (p->multi_rpw == 2) SR2_LAUNCH_MULTI(2);
@@ -1241,95 +1287,124 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             SR2_CUDA(ctx, cudaGetLastError());
             return SR2_OK;
         }
-        dtl_wave_simd16_kernel<<<(unsigned)((n_rows + SIMD_ROWS - 1) / SIMD_ROWS), 512, p->simd_smem, ctx->stream>>>(
-            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
+        dtl_wave_simd16_kernel<<<(unsigned)((n_rows + SIMD_ROWS - 1) / SIMD_ROWS), 512, p->simd_smem, p->cur_stream>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
             p->simd_arr_words, kp);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
     if (!p->cta_per_row) {
         int64_t grid = (n_rows + p->wave_warps - 1) / p->wave_warps;
-        dtl_wave_kernel<32><<<(unsigned)grid, p->wave_warps * 32, p->wave_smem, ctx->stream>>>(
-            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
+        dtl_wave_kernel<32><<<(unsigned)grid, p->wave_warps * 32, p->wave_smem, p->cur_stream>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
             p->spad);
     } else {
-        dtl_wave_kernel<512><<<(unsigned)n_rows, 512, p->wave_smem, ctx->stream>>>(
-            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->d_T, p->d_tag, cs,
+        dtl_wave_kernel<512><<<(unsigned)n_rows, 512, p->wave_smem, p->cur_stream>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
             p->spad);
     }
     SR2_CUDA(ctx, cudaGetLastError());
     return SR2_OK;
 }
 
-extern "C" int sr2_dtl_solve(sr2_ctx* ctx) {
-    if (!ctx) return SR2_ERR_ARG;
-    DtlProblem* p = ctx->dtl;
-    if (!p) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_solve: nothing uploaded");
-    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
-    {
-        int rc = dtl_configure_waves(ctx, p);
-        if (rc) return rc;
-        rc = dtl_configure_simd(ctx, p);
-        if (rc) return rc;
-    }
-    cudaStream_t st = ctx->stream;
+static int dtl_configure(sr2_ctx* ctx, DtlProblem* p) {
+    int rc = dtl_configure_waves(ctx, p);
+    if (rc) return rc;
+    return dtl_configure_simd(ctx, p);
+}
+
+// All device work of one chunk, enqueued on the context's stream: one wave launch per height,
+// (decoded cost rows), selection, one traceback launch per height from the top down.
+static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
+    // pipelined runs alternate between two streams and two sets of tables, so that the
+    // latency-bound top waves and the traceback of one chunk overlap the big waves of the next
+    const int set = p->two_streams ? (ci & 1) : 0;
+    const size_t table_elems = (size_t)std::max<int64_t>(p->rows.max_chunk_rows, 1) * ctx->pitch;
+    p->cur_stream = set ? ctx->stream2 : ctx->stream;
+    p->cur_T = p->d_T + set * table_elems;
+    p->cur_tag = p->d_tag + set * table_elems;
+    p->cur_C = p->d_C ? p->d_C + set * table_elems : nullptr;
+    cudaStream_t st = p->cur_stream;
+    const RowChunk& c = p->rows.chunks[ci];
+    if (p->wait_rows) SR2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->chunk_events[ci], 0));  // its rows' H2D copies
     DtlCosts cs{p->costs[0], p->costs[1], p->costs[2], p->costs[3]};
-    int n_waves = 0, n_launch = 0;
-    float waves_ms = 0.f;
-    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-    for (const RowChunk& c : p->rows.chunks) {
-        const int H = (int)c.wave_off.size() - 2;  // highest wave
-        SR2_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    const int H = (int)c.wave_off.size() - 2;  // highest wave
+    SR2_CUDA(ctx, cudaEventRecord(p->ev_w0[ci], st));
+    for (int h = 1; h <= H; ++h) {
+        int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+        if (n <= 0) continue;
+        int rc = dtl_launch_wave(ctx, p, c, h, c.wave_off[h], n, cs);
+        if (rc) return rc;
+        ++p->n_waves;
+        ++p->n_launch;
+    }
+    SR2_CUDA(ctx, cudaEventRecord(p->ev_w1[ci], st));
+    if (p->need_decoded_cost) {
         for (int h = 1; h <= H; ++h) {
             int64_t n = c.wave_off[h + 1] - c.wave_off[h];
             if (n <= 0) continue;
-            int rc = dtl_launch_wave(ctx, p, c, h, c.wave_off[h], n, cs);
-            if (rc) return rc;
-            ++n_waves;
-            ++n_launch;
-        }
-        SR2_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-        if (p->need_decoded_cost) {
-            for (int h = 1; h <= H; ++h) {
-                int64_t n = c.wave_off[h + 1] - c.wave_off[h];
-                if (n <= 0) continue;
-                dtl_decoded_cost_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(
-                    ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->d_tag, p->d_C, cs);
-                ++n_launch;
-            }
-        }
-        int n_inst = c.inst_end - c.inst_begin;
-        if (n_inst > 0) {
-            dtl_select_kernel<<<(n_inst + 7) / 8, 256, 0, st>>>(
-                ctx->dsp, p->rows.d_root_row, p->rows.d_root_node, c.inst_begin, n_inst, c.row_begin, p->d_T,
-                p->need_decoded_cost ? p->d_C : nullptr, p->d_min_cost, p->d_root_species, p->d_map);
-            ++n_launch;
-        }
-        for (int h = H; h >= 1; --h) {
-            int64_t n = c.wave_off[h + 1] - c.wave_off[h];
-            if (n <= 0) continue;
-            dtl_traceback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-                ctx->dsp, p->rows.row_node, p->rows.row_left, p->rows.row_right, c.wave_off[h], c.row_begin, (int)n,
-                p->d_tag, p->d_map);
-            ++n_launch;
-        }
-        SR2_CUDA(ctx, cudaGetLastError());
-        if (p->rows.chunks.size() > 1) {
-            // the next chunk reuses the table buffers: account the wave time now
-            SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[3]));
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
-            waves_ms += ms;
+            dtl_decoded_cost_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(
+                ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_tag, p->cur_C, cs);
+            ++p->n_launch;
         }
     }
-    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
-    if (p->rows.chunks.size() == 1) cudaEventElapsedTime(&waves_ms, ctx->ev[2], ctx->ev[3]);
+    int n_inst = c.inst_end - c.inst_begin;
+    if (n_inst > 0) {
+        dtl_select_kernel<<<(n_inst + 7) / 8, 256, 0, st>>>(
+            ctx->dsp, p->rows.d_root_row, p->rows.d_root_node, c.inst_begin, n_inst, c.row_begin, p->cur_T,
+            p->need_decoded_cost ? p->cur_C : nullptr, p->d_min_cost, p->d_root_species, p->d_map);
+        ++p->n_launch;
+    }
+    for (int h = H; h >= 1; --h) {
+        int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+        if (n <= 0) continue;
+        dtl_traceback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+            ctx->dsp, p->rows.row_node, p->rows.row_left, p->rows.row_right, c.wave_off[h], c.row_begin, (int)n,
+            p->cur_tag, p->d_map);
+        ++p->n_launch;
+    }
+    SR2_CUDA(ctx, cudaGetLastError());
+    SR2_CUDA(ctx, cudaEventRecord(p->ev_done[ci], st));
+    return SR2_OK;
+}
+
+// after a stream synchronize: timings of the chunks that ran
+static void dtl_collect_timing(sr2_ctx* ctx, DtlProblem* p) {
+    float waves_ms = 0.f;
+    for (size_t ci = 0; ci < p->rows.chunks.size(); ++ci) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p->ev_w0[ci], p->ev_w1[ci]);
+        waves_ms += ms;
+    }
     cudaEventElapsedTime(&ctx->timing.solve_ms, ctx->ev[0], ctx->ev[1]);
+    if (getenv("SR2_TRACE"))
+        for (size_t ci = 0; ci < p->rows.chunks.size(); ++ci) {
+            float a = 0.f, b = 0.f, c = 0.f;
+            cudaEventElapsedTime(&a, ctx->ev[0], p->ev_w0[ci]);
+            cudaEventElapsedTime(&b, ctx->ev[0], p->ev_w1[ci]);
+            cudaEventElapsedTime(&c, ctx->ev[0], p->ev_done[ci]);
+            fprintf(stderr, "[sr2] chunk %zu on the device: waves %.2f .. %.2f ms, done %.2f ms\n", ci, a, b, c);
+        }
     ctx->timing.waves_ms = waves_ms;
-    ctx->timing.n_waves = n_waves;
-    ctx->timing.n_launches = n_launch;
+    ctx->timing.n_waves = p->n_waves;
+    ctx->timing.n_launches = p->n_launch;
     ctx->timing.n_cells = p->rows.R * (int64_t)ctx->S;
+}
+
+extern "C" int sr2_dtl_solve(sr2_ctx* ctx) {
+    if (!ctx) return SR2_ERR_ARG;
+    DtlProblem* p = ctx->dtl;
+    if (!p || !p->prepared) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_solve: nothing uploaded");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc = dtl_configure(ctx, p);
+    if (rc) return rc;
+    p->n_waves = p->n_launch = 0;
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    for (size_t ci = 0; ci < p->rows.chunks.size(); ++ci)
+        if ((rc = dtl_enqueue_chunk(ctx, p, (int)ci))) return rc;
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+    dtl_collect_timing(ctx, p);
     p->solved = true;
     return SR2_OK;
 }
@@ -1369,15 +1444,125 @@ extern "C" int sr2_dtl_results(sr2_ctx* ctx, int32_t* out_min_cost, int32_t* out
     return SR2_OK;
 }
 
+// sr2_dtl_run = upload + solve + results, pipelined over instance chunks: while the device solves
+// chunk k (stream-ordered behind its own H2D copies) the host validates and buckets chunk k+1,
+// and a second stream copies chunk k's results into pinned staging.
+struct DtlRunState {
+    sr2_ctx* ctx;
+    int32_t* stage;  // pinned: [B] min cost, [B] root species, [N] mapping
+    int32_t *out_cost, *out_root, *out_map;
+    bool started;
+    int delivered;   // chunks whose results already sit in the caller's buffers
+    std::vector<cudaEvent_t> copied;  // per chunk: its D2H copies finished
+};
+
+// staging -> caller's buffers for chunks [rs->delivered, upto) whose copies have finished
+// (wait == false: stop at the first chunk that is still in flight)
+static int dtl_deliver(DtlRunState* rs, int upto, bool wait) {
+    sr2_ctx* ctx = rs->ctx;
+    DtlProblem* p = ctx->dtl;
+    const size_t B = p->rows.B;
+    while (rs->delivered < upto) {
+        cudaEvent_t e = rs->copied[rs->delivered];
+        if (wait) SR2_CUDA(ctx, cudaEventSynchronize(e));
+        else if (cudaEventQuery(e) != cudaSuccess) break;
+        const RowChunk& c = p->rows.chunks[rs->delivered];
+        const size_t b0 = c.inst_begin, nb = c.inst_end - c.inst_begin;
+        const int64_t n0 = p->rows.node_off[c.inst_begin], nn = p->rows.node_off[c.inst_end] - n0;
+        if (rs->out_cost) memcpy(rs->out_cost + b0, rs->stage + b0, nb * 4);
+        if (rs->out_root) memcpy(rs->out_root + b0, rs->stage + B + b0, nb * 4);
+        if (rs->out_map) {
+            const int64_t block = 1 << 17;
+            const int64_t n_blocks = (nn + block - 1) / block;
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static)
+            for (int64_t k = 0; k < n_blocks; ++k) {
+                int64_t lo = n0 + k * block, hi = std::min<int64_t>(n0 + nn, lo + block);
+                memcpy(rs->out_map + lo, rs->stage + 2 * B + lo, (size_t)(hi - lo) * 4);
+            }
+        }
+        ++rs->delivered;
+    }
+    return SR2_OK;
+}
+
+static int dtl_run_on_plan(void* user) {
+    DtlRunState* rs = (DtlRunState*)user;
+    sr2_ctx* ctx = rs->ctx;
+    int rc = dtl_prepare(ctx);
+    if (rc) return rc;
+    DtlProblem* p = ctx->dtl;
+    if ((rc = dtl_configure(ctx, p))) return rc;
+    void* ptr = nullptr;
+    if ((rc = sr2_pin_reserve(ctx, HP_RESULTS, (2 * (size_t)p->rows.B + (size_t)p->rows.N + 16) * sizeof(int32_t), &ptr)))
+        return rc;
+    rs->stage = (int32_t*)ptr;
+    if (!ctx->copy_stream) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    while (rs->copied.size() < p->rows.chunks.size()) {
+        cudaEvent_t e;
+        SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        rs->copied.push_back(e);
+    }
+    p->n_waves = p->n_launch = 0;
+    p->wait_rows = true;
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    rs->started = true;
+    return SR2_OK;
+}
+
+static int dtl_run_on_chunk(void* user, int ci) {
+    DtlRunState* rs = (DtlRunState*)user;
+    sr2_ctx* ctx = rs->ctx;
+    DtlProblem* p = ctx->dtl;
+    int rc = dtl_enqueue_chunk(ctx, p, ci);
+    if (rc) return rc;
+    const RowChunk& c = p->rows.chunks[ci];
+    const size_t B = p->rows.B;
+    const size_t b0 = c.inst_begin, nb = c.inst_end - c.inst_begin;
+    const size_t n0 = p->rows.node_off[c.inst_begin], nn = p->rows.node_off[c.inst_end] - n0;
+    cudaStream_t cs = ctx->copy_stream;
+    SR2_CUDA(ctx, cudaStreamWaitEvent(cs, p->ev_done[ci], 0));
+    if (rs->out_cost && nb)
+        SR2_CUDA(ctx, cudaMemcpyAsync(rs->stage + b0, p->d_min_cost + b0, nb * 4, cudaMemcpyDeviceToHost, cs));
+    if (rs->out_root && nb)
+        SR2_CUDA(ctx, cudaMemcpyAsync(rs->stage + B + b0, p->d_root_species + b0, nb * 4, cudaMemcpyDeviceToHost, cs));
+    if (rs->out_map && nn)
+        SR2_CUDA(ctx, cudaMemcpyAsync(rs->stage + 2 * B + n0, p->d_map + n0, nn * 4, cudaMemcpyDeviceToHost, cs));
+    SR2_CUDA(ctx, cudaEventRecord(rs->copied[ci], cs));
+    return dtl_deliver(rs, ci, false);  // earlier chunks that are back already
+}
+
 extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, const int32_t* left,
                            const int32_t* right, const int32_t* leaf_species, const int32_t costs[5],
                            uint32_t flags, int32_t* out_min_cost, int32_t* out_root_species,
                            int32_t* out_map_species) {
-    int rc = sr2_dtl_upload(ctx, B, node_off, left, right, leaf_species, costs, flags);
+    if (!ctx) return SR2_ERR_ARG;
+    int pipeline_chunks = 3;
+    if (const char* v = getenv("SR2_PIPELINE_CHUNKS")) pipeline_chunks = std::max(1, atoi(v));
+    DtlRunState rs{ctx, nullptr, out_min_cost, out_root_species, out_map_species, false, 0, {}};
+    RowHooks hooks;
+    hooks.user = &rs;
+    hooks.on_plan = dtl_run_on_plan;
+    hooks.on_chunk = dtl_run_on_chunk;
+    double t0 = now_ms();
+    int rc = dtl_upload_impl(ctx, B, node_off, left, right, leaf_species, costs, flags, pipeline_chunks, &hooks);
+    double t1 = now_ms();  // the host side is done; sr2_build_rows waited for the compute stream
+    DtlProblem* p = ctx->dtl;
+    if (!rc) rc = dtl_deliver(&rs, (int)p->rows.chunks.size(), true);
+    if (rs.started) {
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
+        cudaStreamSynchronize(ctx->copy_stream);
+    }
+    for (cudaEvent_t e : rs.copied) cudaEventDestroy(e);
     if (rc) return rc;
-    rc = sr2_dtl_solve(ctx);
-    if (rc) return rc;
-    return sr2_dtl_results(ctx, out_min_cost, out_root_species, out_map_species);
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+    dtl_collect_timing(ctx, p);
+    p->solved = true;
+    p->wait_rows = false;
+    ctx->timing.upload_ms = (float)(t1 - t0);         // bucketing with the device work overlapped
+    ctx->timing.results_ms = (float)(now_ms() - t1);  // what was left of staging -> caller's buffers
+    return SR2_OK;
 }
 
 extern "C" int sr2_dtl_tables(sr2_ctx* ctx, int32_t instance, int32_t* out_value, int32_t* out_tag) {

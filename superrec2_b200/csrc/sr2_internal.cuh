@@ -83,6 +83,10 @@ struct sr2_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;    // device-to-host result copies of pipelined runs (lazy)
+    cudaStream_t stream2 = nullptr;        // second compute stream of pipelined runs (lazy)
+    cudaStream_t upload_stream = nullptr;  // host-to-device row copies of pipelined runs (lazy)
+    std::vector<cudaEvent_t> chunk_events; // "rows of chunk i are on the device"
     std::string err;
     int sm_count = 148;
     int host_threads = 1;  // OpenMP threads of the host-side bucketing (see sr2_create)

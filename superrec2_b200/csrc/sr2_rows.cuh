@@ -38,8 +38,20 @@ struct RowLayout {
     void release();  // forgets the pooled pointers (the context keeps the memory)
 };
 
-// Validates the batch (ABI numbering rules), computes heights, splits into chunks
-// of at most `rows_budget` rows, fills the row arrays and copies them to the device.
+// Optional callbacks of sr2_build_rows, so that a caller can overlap the host-side bucketing of
+// the next chunk with device work on the previous one: on_plan runs once chunks, sizes
+// (R, max_chunk_rows, max_nodes) and the device row arrays are known; on_chunk(i) runs after
+// chunk i's rows were bucketed and their host-to-device copies were enqueued on ctx->stream.
+struct RowHooks {
+    void* user = nullptr;
+    int (*on_plan)(void* user) = nullptr;
+    int (*on_chunk)(void* user, int chunk) = nullptr;
+};
+
+// Splits the batch into chunks of at most `rows_budget` rows, then chunk by chunk validates the
+// trees (ABI numbering rules), computes heights, fills the row arrays and copies them to the
+// device (asynchronously; the call returns after a stream synchronize).
 int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node_off,
                    const int32_t* left, const int32_t* right, const int32_t* leaf_species,
-                   int64_t rows_budget, bool keep_host, bool want_preorder, RowLayout* out);
+                   int64_t rows_budget, bool keep_host, bool want_preorder, RowLayout* out,
+                   const RowHooks* hooks = nullptr, int64_t first_chunk_rows = 0);
