@@ -264,15 +264,16 @@ def main():
         peak, peak_src = measured_peak()
         achieved = cells * args.steps * BYTES_PER_CELL / (wave_ms * 1e-3) / 1e9
         # DRAM traffic per wave launch, from the ncu --set full captures under profiles/
-        # (r1j: dtl_wave_flat_kernel 5.16 GB for 1,000,032 rows of 399 species = 12.9 B/cell;
-        #  r1a/r1b: the wave-1 cherry kernel only writes, 8 B/cell), scaled to this batch's rows
+        # (r1n: dtl_wave_flat2_kernel 5.41 GB for 1,000,032 rows of 399 species = 13.56 B/cell -- whole
+        #  416-column pitches are written; r1a/r1b: the wave-1 cherry kernel only writes, 8 B/cell),
+        #  scaled to this batch's rows
         internal = batch.left >= 0
         safe_l = np.where(internal, batch.left, 0) + np.repeat(batch.node_off[:-1], np.diff(batch.node_off))
         safe_r = np.where(internal, batch.right, 0) + np.repeat(batch.node_off[:-1], np.diff(batch.node_off))
         cherry = internal & ~internal[safe_l] & ~internal[safe_r]
         n_cherry, n_other = int(cherry.sum()), int(internal.sum() - cherry.sum())
         waves_per_step = max(1, ctx.timing().n_waves)
-        traffic = (n_other * batch.n_species * 12.93 + n_cherry * batch.n_species * 8.0) / waves_per_step
+        traffic = (n_other * batch.n_species * 13.56 + n_cherry * batch.n_species * 8.0) / waves_per_step
         line = {
             "metric": "dp_cells_per_s",
             "value": all_cells * args.steps / (elapsed_ms * 1e-3),
@@ -298,27 +299,28 @@ def main():
             "e2e": {"value": all_cells * e2e_steps / (e2e_ms * 1e-3), "unit": "cells/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                    "api": "sr2_dtl_run (upload + solve + results, host buffers)",
-                    "upload_ms": e2e_parts[0] / e2e_steps, "solve_ms": e2e_parts[1] / e2e_steps,
-                    "results_ms": e2e_parts[2] / e2e_steps},
+                    "api": "sr2_dtl_run (host buffers in, host buffers out; bucketing, H2D, solve and D2H pipelined "
+                           "over instance chunks)",
+                    "host_ms": e2e_parts[0] / e2e_steps, "device_span_ms": e2e_parts[1] / e2e_steps,
+                    "tail_ms": e2e_parts[2] / e2e_steps},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "dtl wave kernels: dtl_wave_flat_kernel (85 % of the step) + "
-                                   "dtl_cherry_kernel (wave 1, 10 %)",
+                         "kernel": "dtl wave kernels: dtl_wave_flat2_kernel (83 % of the step) + "
+                                   "dtl_cherry_kernel (wave 1, 13 %)",
                          "peak_source": peak_src,
                          "bytes_per_cell": BYTES_PER_CELL,
                          "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL / waves_per_step,
                          "wave_launches_per_step": waves_per_step,
                          "wave_ms_per_step": wave_ms / args.steps,
                          "traffic_source": "bytes per wave launch (average over the step's launches) from "
-                                           "ncu dram__bytes_read+write per row, profiles/r1j_flat_ncu_details.csv"},
+                                           "ncu dram__bytes_read+write per row, profiles/r1n_flat2_ncu_details.csv"},
             "checksum_min_costs": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            sample = min(n_trees, max(16, 2 * cores))
+            sample = min(n_trees, max(16, 6 * cores))  # about 20 core-seconds
             rate, seconds = time_cpu_port(batch, sample)
             line["cpu_baseline"] = {
                 "value": rate, "unit": "cells/s", "cores": cores, "kind": "port",
