@@ -63,6 +63,38 @@ struct DevSpecies {
 struct DtlProblem;
 struct SuperProblem;
 
+// Plan of a range of polytomy resolutions whose DP rows are shared (sr2_resolve.cu builds it,
+// sr2_superdtl.cu consumes it).  Two resolutions contain the same binary subtree below a joint
+// whenever they agree on the digits of the original nodes under it, so the table has one row
+// ("slot") per (original node v, variant of v's subtree, joint of v's arrangement) instead of one
+// per (resolution, internal node).  A variant of v is numbered var = (r / stride[v]) % count[v].
+struct SharedPlan {
+    // the multifurcating tree (original nodes), as the device-side unranking needs it
+    int n = 0;                                  // original nodes
+    int Gb = 0;                                 // nodes of one resolved (binary) tree
+    int64_t first = 0, count = 0;               // resolution numbers [first, first + count)
+    std::vector<int32_t> arity, base;           // [n] children / first id of the node's block in a resolved tree
+    std::vector<int64_t> ways, stride, cnt;     // [n] own arrangements, digit stride, variants of the subtree
+    std::vector<int64_t> var_first, raw_base;   // [n] first variant in the plan, first raw slot of the node
+    std::vector<int32_t> child_of;              // [n_edges] children, concatenated (child_off below)
+    std::vector<int32_t> child_off;             // [n+1]
+    std::vector<int32_t> arr_off;               // [n] offset of the node's arrangement table in arr
+    // arr[arr_off[v] + (j * (k-1) + q) * 2 + side]: child of joint q (preorder rank inside the block) in
+    // arrangement j: >= 0 item (child number), < 0 joint -1-q'
+    std::vector<int32_t> arr;
+    // slots, ordered by height: wave h = [wave_off[h], wave_off[h+1]), h = 1..H
+    int64_t n_slots = 0;
+    std::vector<int64_t> wave_off;
+    std::vector<int32_t> perm;                  // [n_slots] raw slot -> slot
+    std::vector<int32_t> slot_cl, slot_cr;      // [n_slots] table descriptors: child slot, or -1 - leaf species
+    std::vector<int32_t> dag_left, dag_right;   // [Gb + n_slots] children as dag ids (leaf: its id in a resolved
+                                                // tree; slot s: Gb + s), -1 for leaves
+    std::vector<int32_t> leaf_species;          // [Gb] species of the leaves of a resolved tree, -1 elsewhere
+    std::vector<uint32_t> leaf_bits;            // [Gb * W]
+};
+int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_words, const int32_t costs[5],
+                               uint32_t flags);
+
 // Grow-only buffer pools owned by the context: repeated uploads reuse device buffers and
 // pinned host staging instead of paying cudaMalloc/cudaFree and first-touch page faults.
 struct Sr2Pool {
@@ -74,7 +106,8 @@ enum Sr2DevPool {
     DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MINCOST, DP_DTL_ROOTSP, DP_DTL_MAP,
     DP_S_LEFT, DP_S_RIGHT, DP_S_NODEOFF, DP_S_BITS, DP_S_PRESENT, DP_S_OUTSIDE, DP_S_GAIN, DP_S_L, DP_S_FLAGS,
     DP_S_T, DP_S_TAG, DP_S_DEC, DP_S_ANC, DP_S_TAU, DP_S_TAUMIN, DP_S_COST, DP_S_MINCOST, DP_S_ROOTSP, DP_S_MAP,
-    DP_S_KIND, DP_S_SYN, DP_S_BEST, DP_S_ALLOWED, DP_COUNT
+    DP_S_KIND, DP_S_SYN, DP_S_BEST, DP_S_ALLOWED,
+    DP_S_NODESLOT, DP_S_NODEDAG, DP_S_NODEPRE, DP_S_NODEINST, DP_S_PLAN32, DP_S_PLAN64, DP_COUNT
 };
 enum Sr2PinPool { HP_ROWS_SLAB, HP_ROOT_ROW, HP_ROOT_NODE, HP_NODE_PRE, HP_NODE_INST, HP_RESULTS, HP_COUNT };
 enum Sr2HostPool { MP_HEIGHT, MP_NODE_ROW, MP_CNT, MP_COUNT };

@@ -54,6 +54,17 @@ struct SuperProblem {
     int spad = 0, wave_warps = 0;
     size_t wave_smem = 0;
     bool cta_per_row = false;
+    // shared-row mode (resolutions of one multifurcating tree, SharedPlan): the table has one row per
+    // distinct subtree ("slot"); per-node arrays still exist for every resolved tree
+    bool shared = false;
+    int Gb = 0;                     // nodes of one resolved tree
+    int64_t n_slots = 0;
+    std::vector<int64_t> slot_wave_off;
+    int32_t *d_node_slot = nullptr, *d_node_dag = nullptr;   // [N] table row / dag id of a node
+    int32_t *d_node_pre = nullptr, *d_node_inst = nullptr;   // [N]
+    int32_t *d_slot_cl = nullptr, *d_slot_cr = nullptr;      // [n_slots] table descriptors
+    int32_t *d_dag_left = nullptr, *d_dag_right = nullptr;   // [Gb + n_slots]
+    int32_t* d_slot_node = nullptr;                          // [n_slots] Gb + slot
 };
 
 void sr2_free_super(sr2_ctx* ctx) {
@@ -392,10 +403,11 @@ __global__ void sdecode_wave_kernel(DevSpecies sp, const int32_t* __restrict__ r
 
 // the synteny a node is labelled with at time `stamp`: clean lca-set of its owner plus
 // every family merged into that set at or before `stamp`
-__device__ __forceinline__ uint32_t syn_word(const uint32_t* __restrict__ L, const uint32_t* __restrict__ tau,
+__device__ __forceinline__ uint32_t syn_word(const uint32_t* __restrict__ L, size_t L_index,
+                                             const uint32_t* __restrict__ tau,
                                              const uint32_t* __restrict__ taumin, size_t owner, int W, int w,
                                              unsigned stamp) {
-    uint32_t bits = L[owner * W + w];
+    uint32_t bits = L[L_index * W + w];
     if (taumin[owner] <= stamp) {
         const uint32_t* t = tau + (owner * W + w) * 32;
         for (int f = 0; f < 32; ++f)
@@ -415,7 +427,7 @@ __global__ void scost_kernel(DevSpecies sp, const int64_t* __restrict__ node_off
                              int inst_begin, int n_inst, int W, const uint32_t* __restrict__ L,
                              const uint32_t* __restrict__ tau, const uint32_t* __restrict__ taumin,
                              const uint16_t* __restrict__ dec, const uint16_t* __restrict__ anc, SuperCosts cs,
-                             int32_t* __restrict__ cost) {
+                             int32_t* __restrict__ cost, const int32_t* __restrict__ node_dag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)n_inst * sp.S) return;
     int b = inst_begin + (int)(i / sp.S), k = (int)(i % sp.S);
@@ -437,10 +449,13 @@ __global__ void scost_kernel(DevSpecies sp, const int64_t* __restrict__ node_off
             unsigned su = ((unsigned)k << 16) | (unsigned)node_pre[u], sl = ((unsigned)k << 16) | (unsigned)node_pre[l],
                      sr = ((unsigned)k << 16) | (unsigned)node_pre[r];
             bool in_l = true, in_r = true;
+            // shared-row mode: the clean lca-sets live per dag node, the time stamps per tree node
+            size_t Lu = node_dag ? (size_t)node_dag[ou] : ou, Ll = node_dag ? (size_t)node_dag[ol] : ol,
+                   Lr = node_dag ? (size_t)node_dag[orr] : orr;
             for (int w = 0; w < W; ++w) {
-                uint32_t mine = syn_word(L, tau, taumin, ou, W, w, su);
-                in_l &= (mine & ~syn_word(L, tau, taumin, ol, W, w, sl)) == 0;
-                in_r &= (mine & ~syn_word(L, tau, taumin, orr, W, w, sr)) == 0;
+                uint32_t mine = syn_word(L, Lu, tau, taumin, ou, W, w, su);
+                in_l &= (mine & ~syn_word(L, Ll, tau, taumin, ol, W, w, sl)) == 0;
+                in_r &= (mine & ~syn_word(L, Lr, tau, taumin, orr, W, w, sr)) == 0;
             }
             int lc = in_l ? 0 : cs.sloss, rc = in_r ? 0 : cs.sloss;
             // event (model/reconciliation.py:273-365); decodes of finite entries are never INVALID
@@ -495,7 +510,8 @@ __global__ void smaterialise_kernel(DevSpecies sp, int64_t node_begin, int64_t n
                                     int W, const uint32_t* __restrict__ L, const uint32_t* __restrict__ tau,
                                     const uint32_t* __restrict__ taumin, const uint16_t* __restrict__ dec,
                                     const uint16_t* __restrict__ anc, int32_t* __restrict__ map,
-                                    int32_t* __restrict__ kind, uint32_t* __restrict__ syn) {
+                                    int32_t* __restrict__ kind, uint32_t* __restrict__ syn,
+                                    const int32_t* __restrict__ node_dag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_nodes) return;
     int64_t u = node_begin + i;
@@ -512,7 +528,136 @@ __global__ void smaterialise_kernel(DevSpecies sp, int64_t node_begin, int64_t n
     kind[u] = e & 1;
     size_t owner = (size_t)node_off[b] + anc[(size_t)u * sp.S + k];
     unsigned stamp = ((unsigned)k << 16) | (unsigned)node_pre[u];
-    for (int w = 0; w < W; ++w) syn[(size_t)u * W + w] = syn_word(L, tau, taumin, owner, W, w, stamp);
+    size_t L_index = node_dag ? (size_t)node_dag[owner] : owner;
+    for (int w = 0; w < W; ++w) syn[(size_t)u * W + w] = syn_word(L, L_index, tau, taumin, owner, W, w, stamp);
+}
+
+// ---------------------------------------------------------------------------
+// shared-row mode: resolved trees on the device, decode by walking each tree in id order
+// ---------------------------------------------------------------------------
+struct DevPlan {
+    int n, Gb;
+    int64_t first;
+    const int32_t *arity, *base, *child_off, *child_of, *arr_off, *arr, *perm;
+    const int64_t *ways, *stride, *cnt, *var_first, *raw_base;
+};
+
+// Resolution first + i of the plan, as global-id child arrays, table row and dag id of every node,
+// preorder positions and instance numbers.  One thread per resolution.
+__global__ void resolve_unrank_kernel(DevPlan P, int64_t count, int32_t* __restrict__ left,
+                                      int32_t* __restrict__ right, int32_t* __restrict__ node_slot,
+                                      int32_t* __restrict__ node_dag, int32_t* __restrict__ node_pre,
+                                      int32_t* __restrict__ node_inst) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const int64_t r = P.first + i;
+    const int64_t off = i * P.Gb;
+    for (int v = 0; v < P.n; ++v) {
+        const int k = P.arity[v];
+        const int id0 = P.base[v];
+        const int64_t g0 = off + id0;
+        if (k == 0) {
+            left[g0] = right[g0] = -1;
+            node_slot[g0] = -1;
+            node_dag[g0] = id0;
+            continue;
+        }
+        const int64_t var = (r / P.stride[v]) % P.cnt[v];
+        const int64_t j = var % P.ways[v];
+        const int64_t raw0 = P.raw_base[v] + (var - P.var_first[v]) * (k - 1);
+        const int32_t* codes = P.arr + P.arr_off[v] + j * (k - 1) * 2;
+        const int32_t* kids = P.child_of + P.child_off[v];
+        for (int q = 0; q < k - 1; ++q) {
+            int cl = codes[2 * q], cr = codes[2 * q + 1];
+            left[g0 + q] = (int32_t)(off + (cl >= 0 ? P.base[kids[cl]] : id0 + (-1 - cl)));
+            right[g0 + q] = (int32_t)(off + (cr >= 0 ? P.base[kids[cr]] : id0 + (-1 - cr)));
+            int s = P.perm[raw0 + q];
+            node_slot[g0 + q] = s;
+            node_dag[g0 + q] = P.Gb + s;
+        }
+    }
+    // preorder positions from subtree sizes (children have larger ids than their parent)
+    for (int u = P.Gb - 1; u >= 0; --u) {
+        int l = left[off + u];
+        node_inst[off + u] = l < 0 ? 1 : 1 + node_inst[l] + node_inst[right[off + u]];
+    }
+    node_pre[off] = 0;
+    for (int u = 0; u < P.Gb; ++u) {
+        int l = left[off + u];
+        if (l < 0) continue;
+        int mine = node_pre[off + u];
+        node_pre[l] = mine + 1;
+        node_pre[right[off + u]] = mine + 1 + node_inst[l];
+    }
+    for (int u = 0; u < P.Gb; ++u) node_inst[off + u] = (int32_t)i;
+}
+
+// sdecode_root_kernel + sdecode_wave_kernel for uniform trees whose nodes are numbered parents
+// first: thread (instance b, root species k) walks the tree in id order.
+__global__ void sdecode_walk_kernel(DevSpecies sp, int n_inst, int Gb, const int32_t* __restrict__ left,
+                                    const int32_t* __restrict__ right, const int32_t* __restrict__ node_slot,
+                                    const int32_t* __restrict__ node_dag, const int32_t* __restrict__ node_pre,
+                                    const uint32_t* __restrict__ tags, int W, const uint32_t* __restrict__ gain,
+                                    uint16_t* __restrict__ dec, uint16_t* __restrict__ anc,
+                                    uint32_t* __restrict__ tau, uint32_t* __restrict__ taumin) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)n_inst * sp.S) return;
+    const int b = (int)(i / sp.S), k = (int)(i % sp.S);
+    const int64_t off = (int64_t)b * Gb;
+    {
+        bool ok = tags[((size_t)node_slot[off] * 2 + 0) * sp.pitch + k] != SR2_NO_TAG;  // kind LCA (:487)
+        dec[(size_t)off * sp.S + k] = ok ? (uint16_t)(k << 1) : (uint16_t)DEC_NONE;
+        anc[(size_t)off * sp.S + k] = 0;
+    }
+    for (int u = 0; u < Gb; ++u) {
+        const int64_t node = off + u;
+        const int l = left[node];
+        if (l < 0) continue;
+        const int r = right[node];
+        unsigned e = dec[(size_t)node * sp.S + k];
+        unsigned el = DEC_NONE, er = DEC_NONE;
+        unsigned al = 0, ar = 0;
+        if (e != DEC_NONE) {
+            int x = e >> 1, kd = e & 1;
+            unsigned tag = tags[((size_t)node_slot[node] * 2 + kd) * sp.pitch + x];
+            if (tag != SR2_NO_TAG) {
+                el = tag & 0xffffu;
+                er = tag >> 16;
+                unsigned mine = anc[(size_t)node * sp.S + k];
+                al = (el & 1) ? mine : (unsigned)(l - off);
+                ar = (er & 1) ? mine : (unsigned)(r - off);
+                // kind INHERIT: see sdecode_wave_kernel
+#pragma unroll 1
+                for (int side = 0; side < 2; ++side) {
+                    unsigned ec = side ? er : el;
+                    if (!(ec & 1)) continue;
+                    int child = side ? r : l;
+                    unsigned owner = side ? ar : al;
+                    unsigned stamp = ((unsigned)k << 16) | (unsigned)node_pre[child];
+                    bool any = false;
+                    for (int w = 0; w < W; ++w) {
+                        uint32_t g = gain[(size_t)node_dag[child] * W + w];
+                        while (g) {
+                            int f = __ffs(g) - 1;
+                            g &= g - 1;
+                            atomicMin(&tau[((size_t)(off + owner) * W + w) * 32 + f], stamp);
+                            any = true;
+                        }
+                    }
+                    if (any) atomicMin(&taumin[off + owner], stamp);
+                }
+            }
+        }
+        dec[(size_t)l * sp.S + k] = (uint16_t)el;
+        dec[(size_t)r * sp.S + k] = (uint16_t)er;
+        anc[(size_t)l * sp.S + k] = (uint16_t)al;
+        anc[(size_t)r * sp.S + k] = (uint16_t)ar;
+    }
+}
+
+__global__ void iota_kernel(int32_t* __restrict__ out, int64_t n, int32_t start) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = start + (int32_t)i;
 }
 
 // lexicographic minimum of (cost, global instance number, root species) over the batch:
@@ -630,6 +775,155 @@ extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_
     return SR2_OK;
 }
 
+// Shared-row upload (SharedPlan, sr2_internal.cuh): plan arrays to the device, resolved trees by
+// resolve_unrank_kernel.  Replaces the per-resolution host unranking + bucketing of
+// sr2_resolutions_upload; results are read through the same calls as a plain batch.
+int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_words, const int32_t costs[5],
+                               uint32_t flags) {
+    double t0 = snow_ms();
+    if (ctx->S == 0) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_resolutions_upload: call sr2_set_species first");
+    if (ctx->S > 32767)
+        return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_resolutions_upload: more than 32767 species nodes");
+    if (plan.first + plan.count >= (1 << 24))
+        return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_resolutions_upload: instance numbers must stay below 2^24");
+    if (plan.Gb > 65535)
+        return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_resolutions_upload: more than 65535 nodes in one object tree");
+    if (flags & SR2_KEEP_TABLES)
+        return sr2_fail(ctx, SR2_ERR_ARG, "sr2_resolutions_upload: SR2_KEEP_TABLES is not available for shared rows "
+                                          "(set SR2_RESOLUTIONS_UNSHARED=1)");
+    int rc = sr2_check_costs(ctx, "sr2_resolutions_upload", costs, plan.Gb, nullptr);
+    if (rc) return rc;
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    sr2_free_super(ctx);
+    const int S = ctx->S, W = n_words, Gb = plan.Gb;
+    const int64_t B = plan.count, N = B * Gb, NS = plan.n_slots, D = Gb + NS;
+    SuperProblem* p = new SuperProblem();
+    ctx->super = p;
+    p->flags = flags;
+    p->W = W;
+    p->index_base = plan.first;
+    p->shared = true;
+    p->Gb = Gb;
+    p->n_slots = NS;
+    p->slot_wave_off = plan.wave_off;
+    memcpy(p->costs, costs, sizeof(p->costs));
+    p->rows.B = (int32_t)B;
+    p->rows.N = N;
+    p->rows.R = NS;
+    p->rows.node_off.resize(B + 1);
+    for (int64_t i = 0; i <= B; ++i) p->rows.node_off[i] = i * Gb;
+    p->rows.max_nodes = Gb;
+
+    // two slabs of plan arrays
+    std::vector<int32_t> h32;
+    std::vector<int64_t> h64;
+    auto add32 = [&](const std::vector<int32_t>& v) {
+        size_t at = h32.size();
+        h32.insert(h32.end(), v.begin(), v.end());
+        return at;
+    };
+    auto add64 = [&](const std::vector<int64_t>& v) {
+        size_t at = h64.size();
+        h64.insert(h64.end(), v.begin(), v.end());
+        return at;
+    };
+    size_t o_arity = add32(plan.arity), o_base = add32(plan.base), o_choff = add32(plan.child_off),
+           o_chof = add32(plan.child_of), o_arroff = add32(plan.arr_off), o_arr = add32(plan.arr),
+           o_perm = add32(plan.perm), o_scl = add32(plan.slot_cl), o_scr = add32(plan.slot_cr),
+           o_dl = add32(plan.dag_left), o_dr = add32(plan.dag_right);
+    size_t o_ways = add64(plan.ways), o_stride = add64(plan.stride), o_cnt = add64(plan.cnt),
+           o_vf = add64(plan.var_first), o_rb = add64(plan.raw_base), o_noff = add64(p->rows.node_off);
+
+    size_t free_b = 0, total_b = 0;
+    SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    for (int id = DP_S_LEFT; id < DP_COUNT; ++id) free_b += sr2_dev_pooled(ctx, id);
+    size_t need = (size_t)N * (4 * 8 + (size_t)W * 4 + (size_t)W * 128 + (size_t)S * 4) + (size_t)D * W * 4 * 5 +
+                  (size_t)NS * ((size_t)ctx->pitch * 16 + 8) + (size_t)B * ((size_t)S * 4 + 16) + h32.size() * 4 +
+                  h64.size() * 8 + (64u << 20);
+    if (free_b < need)
+        return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_resolutions_upload: range does not fit in device memory");
+    size_t dw = (size_t)D * W;
+#define SR2_RESERVE(id, field, bytes)                                   \
+    do {                                                                \
+        void* ptr__ = nullptr;                                          \
+        int rc__ = sr2_dev_reserve(ctx, id, (bytes), &ptr__);           \
+        if (rc__) return rc__;                                          \
+        p->field = (decltype(p->field))ptr__;                           \
+    } while (0)
+    int32_t* d32 = nullptr;
+    int64_t* d64 = nullptr;
+    {
+        void* ptr = nullptr;
+        if ((rc = sr2_dev_reserve(ctx, DP_S_PLAN32, (h32.size() + NS) * 4, &ptr))) return rc;
+        d32 = (int32_t*)ptr;
+        if ((rc = sr2_dev_reserve(ctx, DP_S_PLAN64, h64.size() * 8, &ptr))) return rc;
+        d64 = (int64_t*)ptr;
+    }
+    SR2_RESERVE(DP_S_LEFT, d_left, (size_t)N * 4);
+    SR2_RESERVE(DP_S_RIGHT, d_right, (size_t)N * 4);
+    SR2_RESERVE(DP_S_NODESLOT, d_node_slot, (size_t)N * 4);
+    SR2_RESERVE(DP_S_NODEDAG, d_node_dag, (size_t)N * 4);
+    SR2_RESERVE(DP_S_NODEPRE, d_node_pre, (size_t)N * 4);
+    SR2_RESERVE(DP_S_NODEINST, d_node_inst, (size_t)N * 4);
+    SR2_RESERVE(DP_S_BITS, d_bits, dw * 4);
+    SR2_RESERVE(DP_S_PRESENT, d_present, dw * 4);
+    SR2_RESERVE(DP_S_OUTSIDE, d_outside, dw * 4);
+    SR2_RESERVE(DP_S_GAIN, d_gain, dw * 4);
+    SR2_RESERVE(DP_S_L, d_L, dw * 4);
+    SR2_RESERVE(DP_S_FLAGS, d_row_flags, (size_t)std::max<int64_t>(NS, 1));
+    SR2_RESERVE(DP_S_T, d_T, (size_t)std::max<int64_t>(NS, 1) * 2 * ctx->pitch * 4);
+    SR2_RESERVE(DP_S_TAG, d_tag, (size_t)std::max<int64_t>(NS, 1) * 2 * ctx->pitch * 4);
+    SR2_RESERVE(DP_S_DEC, d_dec, (size_t)N * S * 2);
+    SR2_RESERVE(DP_S_ANC, d_anc, (size_t)N * S * 2);
+    SR2_RESERVE(DP_S_TAU, d_tau, (size_t)N * W * 32 * 4);
+    SR2_RESERVE(DP_S_TAUMIN, d_taumin, (size_t)N * 4);
+    SR2_RESERVE(DP_S_COST, d_cost, (size_t)B * S * 4);
+    SR2_RESERVE(DP_S_MINCOST, d_min_cost, (size_t)B * 4);
+    SR2_RESERVE(DP_S_ROOTSP, d_root_species, (size_t)B * 4);
+    SR2_RESERVE(DP_S_MAP, d_map, (size_t)N * 4);
+    SR2_RESERVE(DP_S_KIND, d_kind, (size_t)N * 4);
+    SR2_RESERVE(DP_S_SYN, d_syn, (size_t)N * W * 4);
+    SR2_RESERVE(DP_S_BEST, d_best, 8);
+#undef SR2_RESERVE
+    cudaStream_t st = ctx->stream;
+    SR2_CUDA(ctx, cudaMemcpyAsync(d32, h32.data(), h32.size() * 4, cudaMemcpyHostToDevice, st));
+    SR2_CUDA(ctx, cudaMemcpyAsync(d64, h64.data(), h64.size() * 8, cudaMemcpyHostToDevice, st));
+    // leaf bits of the dag: the leaves of a resolved tree sit at the same ids in every resolution
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_bits, 0, std::max<size_t>(dw * 4, 4), st));
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_bits, plan.leaf_bits.data(), (size_t)Gb * W * 4, cudaMemcpyHostToDevice, st));
+    p->d_slot_cl = d32 + o_scl;
+    p->d_slot_cr = d32 + o_scr;
+    p->d_dag_left = d32 + o_dl;
+    p->d_dag_right = d32 + o_dr;
+    p->d_slot_node = d32 + h32.size();
+    p->d_node_off = d64 + o_noff;
+    if (NS > 0) iota_kernel<<<(unsigned)((NS + 255) / 256), 256, 0, st>>>(p->d_slot_node, NS, Gb);
+    DevPlan P;
+    P.n = plan.n;
+    P.Gb = Gb;
+    P.first = plan.first;
+    P.arity = d32 + o_arity;
+    P.base = d32 + o_base;
+    P.child_off = d32 + o_choff;
+    P.child_of = d32 + o_chof;
+    P.arr_off = d32 + o_arroff;
+    P.arr = d32 + o_arr;
+    P.perm = d32 + o_perm;
+    P.ways = d64 + o_ways;
+    P.stride = d64 + o_stride;
+    P.cnt = d64 + o_cnt;
+    P.var_first = d64 + o_vf;
+    P.raw_base = d64 + o_rb;
+    if (B > 0)
+        resolve_unrank_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(P, B, p->d_left, p->d_right, p->d_node_slot,
+                                                                        p->d_node_dag, p->d_node_pre,
+                                                                        p->d_node_inst);
+    SR2_CUDA(ctx, cudaGetLastError());
+    SR2_CUDA(ctx, cudaStreamSynchronize(st));  // h32 / h64 / plan.leaf_bits are released on return
+    ctx->timing.upload_ms = (float)(snow_ms() - t0);
+    return SR2_OK;
+}
+
 static int super_configure(sr2_ctx* ctx, SuperProblem* p) {
     const int S = ctx->S;
     p->spad = (S + 1) & ~1;
@@ -653,6 +947,97 @@ static int super_configure(sr2_ctx* ctx, SuperProblem* p) {
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
 
+// Shared-row solve: synteny sets and the table over the distinct subtrees (dag), then decode,
+// cost() and selection per resolved tree.
+static int super_solve_shared(sr2_ctx* ctx, SuperProblem* p) {
+    cudaStream_t st = ctx->stream;
+    const int W = p->W, S = ctx->S, Gb = p->Gb;
+    const int64_t N = p->rows.N, NS = p->n_slots, D = Gb + NS;
+    const int B = p->rows.B;
+    const std::vector<int64_t>& wo = p->slot_wave_off;
+    const int H = (int)wo.size() - 2;
+    SuperCosts cs{p->costs[0], p->costs[1], p->costs[2], p->costs[3], p->costs[4]};
+    int n_launch = 0, n_waves = 0;
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
+    size_t dw = (size_t)D * W;
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_present, p->d_bits, dw * 4, cudaMemcpyDeviceToDevice, st));
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_L, p->d_bits, dw * 4, cudaMemcpyDeviceToDevice, st));
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_outside, 0, std::max<size_t>(dw * 4, 4), st));
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_tau, 0xff, std::max<size_t>((size_t)N * W * 128, 4), st));
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_taumin, 0xff, std::max<size_t>((size_t)N * 4, 4), st));
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_best, 0xff, 8, st));
+    const int32_t* s_left = p->d_dag_left + Gb;    // indexed by slot
+    const int32_t* s_right = p->d_dag_right + Gb;
+    for (int h = 1; h <= H; ++h) {
+        int64_t n = wo[h + 1] - wo[h];
+        if (n <= 0) continue;
+        syn_present_wave<<<grid_for(n * W, 256), 256, 0, st>>>(p->d_slot_node, s_left, s_right, wo[h], (int)n, W,
+                                                               p->d_present);
+        ++n_launch;
+    }
+    // a shared subtree has several parents, all of which give it the same "outside" set (the
+    // leaves outside a subtree do not depend on how they are arranged)
+    for (int h = H; h >= 1; --h) {
+        int64_t n = wo[h + 1] - wo[h];
+        if (n <= 0) continue;
+        syn_outside_wave<<<grid_for(n * W, 256), 256, 0, st>>>(p->d_slot_node, s_left, s_right, wo[h], (int)n, W,
+                                                               p->d_present, p->d_outside);
+        ++n_launch;
+    }
+    syn_gain_kernel<<<grid_for(D * W, 256), 256, 0, st>>>(p->d_dag_left, p->d_dag_right, D, W, p->d_present,
+                                                          p->d_outside, p->d_gain);
+    ++n_launch;
+    for (int h = 1; h <= H; ++h) {
+        int64_t n = wo[h + 1] - wo[h];
+        if (n <= 0) continue;
+        syn_lca_wave<<<grid_for(n, 256), 256, 0, st>>>(p->d_slot_node, s_left, s_right, wo[h], (int)n, W, p->d_gain,
+                                                       p->d_L, p->d_row_flags);
+        ++n_launch;
+    }
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    for (int h = 1; h <= H; ++h) {
+        int64_t n = wo[h + 1] - wo[h];
+        if (n <= 0) continue;
+        if (!p->cta_per_row) {
+            superdtl_wave_kernel<32><<<grid_for(n, p->wave_warps), p->wave_warps * 32, p->wave_smem, st>>>(
+                ctx->dsp, p->d_slot_cl, p->d_slot_cr, p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad);
+        } else {
+            superdtl_wave_kernel<256><<<(unsigned)n, 256, p->wave_smem, st>>>(
+                ctx->dsp, p->d_slot_cl, p->d_slot_cr, p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad);
+        }
+        ++n_launch;
+        ++n_waves;
+    }
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    SR2_CUDA(ctx, cudaGetLastError());
+    if (B > 0) {
+        sdecode_walk_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
+            ctx->dsp, B, Gb, p->d_left, p->d_right, p->d_node_slot, p->d_node_dag, p->d_node_pre, p->d_tag, W,
+            p->d_gain, p->d_dec, p->d_anc, p->d_tau, p->d_taumin);
+        scost_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
+            ctx->dsp, p->d_node_off, p->d_left, p->d_right, p->d_node_pre, 0, B, W, p->d_L, p->d_tau, p->d_taumin,
+            p->d_dec, p->d_anc, cs, p->d_cost, p->d_node_dag);
+        sselect_kernel<<<grid_for(B, 8), 256, 0, st>>>(ctx->dsp, 0, B, p->d_cost, p->d_dec, p->d_node_off,
+                                                       p->d_min_cost, p->d_root_species);
+        smaterialise_kernel<<<grid_for(N, 256), 256, 0, st>>>(
+            ctx->dsp, 0, N, p->d_node_inst, p->d_node_off, p->d_node_pre, p->d_root_species, W, p->d_L, p->d_tau,
+            p->d_taumin, p->d_dec, p->d_anc, p->d_map, p->d_kind, p->d_syn, p->d_node_dag);
+        sbest_kernel<<<grid_for(B, 256), 256, 0, st>>>(B, p->index_base, p->d_min_cost, p->d_root_species,
+                                                       p->d_best);
+        n_launch += 5;
+    }
+    SR2_CUDA(ctx, cudaGetLastError());
+    SR2_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
+    SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
+    cudaEventElapsedTime(&ctx->timing.waves_ms, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&ctx->timing.solve_ms, ctx->ev[0], ctx->ev[1]);
+    ctx->timing.n_waves = n_waves;
+    ctx->timing.n_launches = n_launch;
+    ctx->timing.n_cells = NS * (int64_t)S * 2;  // cell-kinds actually evaluated
+    p->solved = true;
+    return SR2_OK;
+}
+
 extern "C" int sr2_superdtl_solve(sr2_ctx* ctx) {
     if (!ctx) return SR2_ERR_ARG;
     SuperProblem* p = ctx->super;
@@ -660,6 +1045,7 @@ extern "C" int sr2_superdtl_solve(sr2_ctx* ctx) {
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
     int rc = super_configure(ctx, p);
     if (rc) return rc;
+    if (p->shared) return super_solve_shared(ctx, p);
     cudaStream_t st = ctx->stream;
     const RowLayout& rows = p->rows;
     const RowChunk& c = rows.chunks[0];
@@ -738,12 +1124,12 @@ extern "C" int sr2_superdtl_solve(sr2_ctx* ctx) {
         }
         scost_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
             ctx->dsp, p->d_node_off, p->d_left, p->d_right, rows.d_node_pre, 0, B, W, p->d_L, p->d_tau, p->d_taumin,
-            p->d_dec, p->d_anc, cs, p->d_cost);
+            p->d_dec, p->d_anc, cs, p->d_cost, nullptr);
         sselect_kernel<<<grid_for(B, 8), 256, 0, st>>>(ctx->dsp, 0, B, p->d_cost, p->d_dec, p->d_node_off,
                                                        p->d_min_cost, p->d_root_species);
         smaterialise_kernel<<<grid_for(N, 256), 256, 0, st>>>(
             ctx->dsp, 0, N, rows.d_node_inst, p->d_node_off, rows.d_node_pre, p->d_root_species, W, p->d_L,
-            p->d_tau, p->d_taumin, p->d_dec, p->d_anc, p->d_map, p->d_kind, p->d_syn);
+            p->d_tau, p->d_taumin, p->d_dec, p->d_anc, p->d_map, p->d_kind, p->d_syn, nullptr);
         sbest_kernel<<<grid_for(B, 256), 256, 0, st>>>(B, p->index_base, p->d_min_cost, p->d_root_species,
                                                        p->d_best);
         n_launch += 4;

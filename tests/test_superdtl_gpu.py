@@ -186,3 +186,32 @@ def test_config5_full_enumeration_properties(ctx):
         out = oracle.superdtl(*other.species_args, *other.object_args, other.leaf_bits, other.costs,
                               tables=False)
         assert out["min_cost"] >= best_cost
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [
+    (8, (5, 4), 2, 6, 77),     # binary root over a 5-ary and a 4-ary node, 2-leaf subtrees
+    (10, (4, 5), 2, 8, 5),
+    (6, (3, 6), 1, 5, 9),      # leaves directly under the polytomies
+    (12, (6, 2), 3, 40, 21),   # two 32-bit words of families
+])
+def test_shared_rows_equal_unshared_rows(ctx, monkeypatch, shape):
+    """Resolutions are solved with one table row per DISTINCT subtree and trees unranked on the
+    device (SharedPlan).  Every per-resolution result (cost, root, mapping, kinds, syntenies) must
+    equal what the plain per-resolution batch (host unranking, one row per node) gives, for the
+    whole enumeration and for a sub-range (the multi-GPU sharding case)."""
+    n_s, arities, sub, fam, seed = shape
+    data = synth.make_polytomy_input(n_s, arities, sub, fam, seed=seed)
+    srec_input, species, poly, bits, costs = _poly_setup(ctx, data)
+    total = srec_input.count_resolutions()
+    for lo, hi in ((0, total), (total // 3, total // 3 + max(1, total // 5))):
+        outs = []
+        for unshared in ("1", "0"):
+            monkeypatch.setenv("SR2_RESOLUTIONS_UNSHARED", unshared)
+            ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits, costs, lo, hi - lo)
+            ctx.superdtl_solve()
+            outs.append((ctx.superdtl_results(), ctx.superdtl_best()))
+        (plain, plain_best), (shared, shared_best) = outs
+        assert plain_best == shared_best
+        for a, b in zip(plain, shared):
+            assert (a == b).all()
