@@ -134,6 +134,11 @@ int sr2_superdtl_upload(sr2_ctx* ctx, int32_t n_instances, const int64_t* node_o
                         const int32_t* left, const int32_t* right, const int32_t* leaf_species,
                         int32_t n_words, const uint32_t* leaf_bits, const int32_t costs[5],
                         int64_t index_base, uint32_t flags);
+/* Optional, between upload and solve: restrict every object node to one species
+ * (node_species[node], -1 = any species) -- the `allowed_species` argument of
+ * _compute_uspfs_table (compute/unordered_super_reconciliation.py:300-358); with the LCA
+ * mapping this is usreconcile_base_uspfs (:500-520).  NULL lifts the restriction. */
+int sr2_superdtl_set_allowed(sr2_ctx* ctx, const int32_t* node_species);
 int sr2_superdtl_solve(sr2_ctx* ctx);
 int sr2_superdtl_results(sr2_ctx* ctx, int32_t* out_min_cost, int32_t* out_root_species,
                          int32_t* out_map_species, int32_t* out_map_kind, uint32_t* out_synteny_bits);

@@ -21,6 +21,9 @@ Fixtures:
   superdtl_reference.json.gz  data/example.in.json, the reference test instances
   crispr.json.gz           data/crispr-class1.in.json (superdtl, default costs)
   binarize.json.gz         enumeration order of ReconciliationInput.binarize()
+  base_uspfs.json.gz       binary instances solved by usreconcile_base_uspfs (superdtl table
+                           restricted to the LCA mapping) and by reconcile_lca, incl. the
+                           instances of tests/compute/test_unordered_super_reconciliation.py
 """
 import gzip
 import io
@@ -196,6 +199,24 @@ def superdtl_fixture(data, with_table):
     return fixture
 
 
+def base_uspfs_fixture(data):
+    """usreconcile_base_uspfs (:500-520) and reconcile_lca (compute/reconciliation.py:23-44)."""
+    fixture = {"kind": "base_uspfs", "input": data}
+    srec_input = SuperReconciliationInput.from_dict(data)
+    lca = ref_rec.reconcile_lca(srec_input)
+    fixture["lca"] = {node.name: species.name for node, species in lca.object_species.items()
+                      if node.name}
+    fixture["lca_cost"] = num(lca.cost())
+    results = list(quiet(ref_usr.usreconcile_base_uspfs, srec_input, RetentionPolicy.ANY))
+    if not results:
+        fixture["result"] = None
+        return fixture
+    assert len(results) == 1
+    fixture["min_cost"] = num(results[0].cost())
+    fixture["result"] = results[0].to_dict()
+    return fixture
+
+
 def binarize_fixture(newick):
     """Order of ReconciliationInput.binarize() on a multifurcating object tree."""
     from ete3 import Tree
@@ -225,6 +246,11 @@ def write(name, fixtures):
 
 
 def main():
+    only = set(sys.argv[1:])   # optional: names of the fixture files to (re)write
+    global write
+    if only:
+        real_write = write
+        write = lambda name, fixtures: real_write(name, fixtures) if name in only else None  # noqa: E731
     rng = random.Random(20261019)
 
     # ---- dtl ----------------------------------------------------------------
@@ -309,6 +335,35 @@ def main():
         binarize_fixture("((a,b,c)p,(d,e,f,g)q,h)r;"),
         binarize_fixture("((a,b)p,(c,d,e)q,(f,(g,h,i)s)t);"),
     ])
+
+    # ---- base_uspfs / lca (own generator: the fixtures above stay byte-identical) ------
+    rng2 = random.Random(20261020)
+    base = []
+    default = dict(zip(COST_NAMES, [0, 1, 1, 1, 1]))
+    # tests/compute/test_unordered_super_reconciliation.py:99-331
+    for tree, species, syn in [
+        ("((x_1,y_1)2,z_1)1;", "((X,Y)XY,Z)XYZ;", {"x_1": "a", "y_1": "a", "z_1": "ab"}),
+        ("((x_1,y_1)2,z_1)1;", "((X,Y)XY,Z)XYZ;", {"x_1": "ab", "y_1": "a", "z_1": "b"}),
+        ("((x_1,y_1)2,z_1)1;", "((X,Y)XY,Z)XYZ;", {"x_1": "abc", "y_1": "bd", "z_1": "ace"}),
+        ("((x_1,x_2)2,x_3)1;", "((X,Y)XY,Z)XYZ;", {"x_1": "ab", "x_2": "b", "x_3": "a"}),
+        ("((x_1,x_2)2,(x_3,y_1)3)1;", "((X,Y)XY,Z)XYZ;", {"x_1": "abc", "x_2": "ab", "x_3": "bc", "y_1": "abc"}),
+        ("((x_1,y_1)1,(x_2,y_2)2)3;", "(X,Y)XY;", {"x_1": "abc", "y_1": "ab", "x_2": "bc", "y_2": "abc"}),
+    ]:
+        leaves = [name for name in syn]
+        base.append(base_uspfs_fixture({
+            "object_tree": tree, "species_tree": species,
+            "leaf_object_species": {leaf: leaf.split("_")[0].upper() for leaf in leaves},
+            "leaf_syntenies": {leaf: list(fams) for leaf, fams in syn.items()},
+            "costs": default,
+        }))
+    for i in range(120):
+        n_s = rng2.randint(1, 6)
+        n_o = rng2.randint(1, 9)
+        mode = ["default", "zero", "spe", "random"][i % 4]
+        base.append(base_uspfs_fixture(
+            random_instance(rng2, n_s, n_o, i % 3 != 2, mode, families=rng2.randint(1, 6),
+                            name_internal=i % 2 == 0)))
+    write("base_uspfs.json.gz", base)
 
 
 if __name__ == "__main__":

@@ -61,6 +61,7 @@ SIGNATURES = {
     "sr2_dtl_tables": (c_int, [c_void_p, c_int32, _I32P, _I32P]),
     "sr2_superdtl_upload": (c_int, [c_void_p, c_int32, _I64P, _I32P, _I32P, _I32P, c_int32, _U32P, _I32P,
                                     c_int64, c_uint32]),
+    "sr2_superdtl_set_allowed": (c_int, [c_void_p, _I32P]),
     "sr2_superdtl_solve": (c_int, [c_void_p]),
     "sr2_superdtl_results": (c_int, [c_void_p, _I32P, _I32P, _I32P, _I32P, _U32P]),
     "sr2_superdtl_best": (c_int, [c_void_p, _I32P, _I64P, _I32P, POINTER(c_uint64)]),
@@ -208,6 +209,16 @@ class Context:
         self._check(self._lib.sr2_superdtl_upload(
             self._handle, len(node_off) - 1, p64(node_off), p32(left), p32(right), p32(leaf_species),
             leaf_bits.shape[1], leaf_bits.ctypes.data_as(_U32P), p32(costs), index_base, flags))
+
+    def superdtl_set_allowed(self, node_species):
+        """Restrict every object node of the uploaded batch to one species rank (-1 = any)."""
+        if node_species is None:
+            self._check(self._lib.sr2_superdtl_set_allowed(self._handle, None))
+            return
+        node_species = i32(node_species)
+        if len(node_species) != self._sbatch[1]:
+            raise ValueError("one entry per object node of the uploaded batch")
+        self._check(self._lib.sr2_superdtl_set_allowed(self._handle, p32(node_species)))
 
     def superdtl_solve(self):
         self._check(self._lib.sr2_superdtl_solve(self._handle))

@@ -5,8 +5,11 @@ import json
 import sys
 import textwrap
 
-from ..compute.reconciliation import reconcile_thl
-from ..compute.unordered_super_reconciliation import usreconcile_extended_uspfs
+from ..compute.reconciliation import reconcile_lca, reconcile_thl
+from ..compute.unordered_super_reconciliation import (
+    usreconcile_base_uspfs,
+    usreconcile_extended_uspfs,
+)
 from ..model.reconciliation import (
     EdgeEvent,
     NodeEvent,
@@ -18,10 +21,12 @@ from ..model.reconciliation import (
 from ..utils.dynamic_programming import RetentionPolicy
 
 # Same registry shape as /root/reference/src/superrec2/cli/reconcile.py:32-40, restricted to
-# the two algorithms this package implements; "dtl" is an alias of the reference's "thl".
+# the algorithms this package implements; "dtl" is an alias of the reference's "thl".
 algorithms = {
+    "lca": reconcile_lca,
     "thl": reconcile_thl,
     "dtl": reconcile_thl,
+    "base_uspfs": usreconcile_base_uspfs,
     "superdtl": usreconcile_extended_uspfs,
 }
 
@@ -63,7 +68,9 @@ def call_algorithm(args, rec_input):
             print(f"Error: '{args.algorithm}' is a super-reconciliation "
                   "algorithm: you need to provide leaf syntenies", file=sys.stderr)
             return None
-    if len(params) == 2 and params[1].annotation == RetentionPolicy:
+    if len(params) == 1:
+        output = algo(rec_input)
+    elif len(params) == 2 and params[1].annotation == RetentionPolicy:
         output = algo(rec_input, getattr(RetentionPolicy, args.solutions.upper()))
     else:
         return None

@@ -29,6 +29,38 @@ def cost_vector(costs) -> np.ndarray:
     return np.asarray(values, np.int32)
 
 
+def reconcile_lca(rec_input: ReconciliationInput) -> ReconciliationOutput:
+    """
+    Compute the minimum-cost reconciliation between two trees by mapping each
+    node of the object tree to the lowest common ancestor (LCA) of all species
+    that correspond to leaves of that node's subtree. This yields the only
+    optimal solution, provided only speciations, duplications, and losses are
+    allowed and duplications cost the same as losses.
+
+    Mirrors ``reconcile_lca`` of the reference
+    (``/root/reference/src/superrec2/compute/reconciliation.py:23-44``).  It is a
+    single bottom-up pass with no dynamic program behind it, so it stays on the
+    host; ``usreconcile_base_uspfs`` uses it to restrict the GPU table.
+
+    :param rec_input: input for the reconciliation
+    :returns: reconciliation result
+    """
+    rec = {}
+    stack = [(rec_input.object_tree, False)]
+    while stack:  # postorder, iteratively (deep trees)
+        node, done = stack.pop()
+        if not node.children:
+            rec[node] = rec_input.leaf_object_species[node]
+        elif done:
+            left, right = node.children
+            rec[node] = rec_input.species_lca(rec[left], rec[right])
+        else:
+            stack.append((node, True))
+            stack.extend((kid, False) for kid in reversed(node.children))
+    # the reference builds the dict in postorder; keep that key order
+    return ReconciliationOutput(rec_input, rec)
+
+
 def reconcile_thl(
     rec_input: ReconciliationInput,
     policy: RetentionPolicy,

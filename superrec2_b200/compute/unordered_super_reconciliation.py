@@ -96,6 +96,7 @@ def usreconcile_extended_uspfs_sharded(
     shard: int = 0,
     n_shards: int = 1,
     reduce_key=None,
+    allowed=None,
 ) -> Set[SuperReconciliationOutput]:
     """
     ``usreconcile_extended_uspfs`` restricted to one contiguous block of resolution
@@ -103,6 +104,10 @@ def usreconcile_extended_uspfs_sharded(
     is the cross-shard min-reduce of the packed ``(cost, resolution, root)`` key (an NCCL
     all-reduce in ``superrec2_b200.dist``); the shard that owns the winning resolution
     returns the solution, the others return an empty set.
+
+    ``allowed(bin_input, objects, species) -> int32[nodes]`` optionally restricts every object
+    node of a BINARY input to one species rank (-1 = any): the ``allowed_species`` argument of the
+    reference's ``_compute_uspfs_table`` (``:300-358``).
     """
     if policy is not RetentionPolicy.ANY:
         raise NotImplementedError(
@@ -127,6 +132,8 @@ def usreconcile_extended_uspfs_sharded(
                 _, objects, _, bits = flatten_super(srec_input, species, families)
                 ctx.superdtl_upload([0, len(objects.nodes)], objects.left, objects.right,
                                     objects.leaf_species, bits, costs)
+                if allowed is not None:
+                    ctx.superdtl_set_allowed(allowed(srec_input, objects, species))
                 ctx.superdtl_solve()
                 best_key = ctx.superdtl_best()[3]
         else:
@@ -169,11 +176,53 @@ def usreconcile_extended_uspfs_sharded(
     winner.label_internal()
     species, objects, _, bits = flatten_super(winner, None, families)
     ctx.set_species(species.parent, species.child0, species.child1)
-    min_cost, root, mapping, _, syn = ctx.superdtl_run(
-        [0, len(objects.nodes)], objects.left, objects.right, objects.leaf_species, bits, costs)
+    ctx.superdtl_upload([0, len(objects.nodes)], objects.left, objects.right, objects.leaf_species,
+                        bits, costs)
+    if allowed is not None:
+        ctx.superdtl_set_allowed(allowed(winner, objects, species))
+    ctx.superdtl_solve()
+    min_cost, root, mapping, _, syn = ctx.superdtl_results()
     if (int(min_cost[0]), int(root[0])) != (global_key >> 40, global_key & 0xFFFF):
         raise _lib.Sr2Error(-5, "winning resolution does not reproduce its key")
     object_species = {node: species.nodes[int(mapping[u])] for u, node in enumerate(objects.nodes)}
     syntenies = {node: bits_to_families(syn[u], names) for u, node in enumerate(objects.nodes)}
     return {SuperReconciliationOutput(
         input=winner, object_species=object_species, syntenies=syntenies, ordered=False)}
+
+
+def usreconcile_base_uspfs(
+    srec_input: SuperReconciliationInput,
+    policy: RetentionPolicy,
+) -> Set[SuperReconciliationOutput]:
+    """
+    Compute a minimum-cost unordered super-reconciliation using the original
+    Unordered Small-Phylogeny-for-Syntenies (USPFS) algorithm, on an NVIDIA
+    B200 GPU. This cannot generate horizontal gene transfer events and
+    assumes that the cost of duplications is equal to the cost of losses:
+    every object node is mapped to the LCA of the species below it and only
+    the synteny labelling is optimised.
+
+    Mirrors ``usreconcile_base_uspfs`` of the reference
+    (``compute/unordered_super_reconciliation.py:500-520``): the same table as
+    ``superdtl`` with ``allowed_species`` reduced to the LCA mapping.  Like the
+    reference it needs a binary object tree (``reconcile_lca`` unpacks two
+    children per node).
+
+    :param srec_input: objects of the super-reconciliation
+    :param policy: ``RetentionPolicy.ANY`` (one solution)
+    :returns: any minimum-cost super-reconciliation, if there is one
+    """
+    from ..utils.trees import is_binary
+    from .reconciliation import reconcile_lca
+    if not is_binary(srec_input.object_tree):
+        raise ValueError("base_uspfs needs a binary object tree (reconcile_lca maps two children per node)")
+
+    def lca_only(bin_input, objects, species):
+        mapping = reconcile_lca(bin_input).object_species
+        only = np.full(len(objects.nodes), -1, np.int32)
+        for u, node in enumerate(objects.nodes):
+            if node.children:
+                only[u] = species.rank[mapping[node]]
+        return only
+
+    return usreconcile_extended_uspfs_sharded(srec_input, policy, allowed=lca_only)

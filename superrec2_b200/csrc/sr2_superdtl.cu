@@ -50,6 +50,7 @@ struct SuperProblem {
     int32_t *d_map = nullptr, *d_kind = nullptr;         // [N]
     uint32_t* d_syn = nullptr;                           // [N*W]
     unsigned long long* d_best = nullptr;                // packed (cost, instance, root)
+    int32_t* d_allowed = nullptr;                        // [N] the only species a node may map to, -1 = any
     bool solved = false;
     int spad = 0, wave_warps = 0;
     size_t wave_smem = 0;
@@ -209,7 +210,8 @@ template <int TPR>
 __global__ void __launch_bounds__(TPR == 32 ? 256 : TPR)
 superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                      const uint8_t* __restrict__ row_flags, int64_t row_begin, int64_t chunk_row0, int n_rows,
-                     int32_t* __restrict__ T, uint32_t* __restrict__ tags, SuperCosts cs, int spad) {
+                     int32_t* __restrict__ T, uint32_t* __restrict__ tags, SuperCosts cs, int spad,
+                     const int32_t* __restrict__ row_node, const int32_t* __restrict__ allowed) {
     extern __shared__ u64 smem[];
     const int S = sp.S;
     int group, lane, groups_per_cta;
@@ -228,6 +230,9 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     const size_t slot = (size_t)(gr - chunk_row0);
     u64* base = smem + (size_t)group * 12 * spad;
     const int flags = row_flags[gr];
+    // allowed_species of _compute_uspfs_table (:340-356): every species (superdtl) or one species per
+    // object node (base_uspfs); cells of other species are never created
+    const int only = allowed ? allowed[row_node[gr]] : -1;
 
     // stage the child rows as the 12 key rows
     for (int i = 0; i < 2; ++i) {
@@ -278,12 +283,13 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
         int cx = __ldg(sp.child0);
         int best;
         unsigned tag;
+        const bool skip = only >= 0 && only != 0;
         super_cell(base, spad, 0, 0, 0, cx, true, SR2_KEY_NONE, SR2_KEY_NONE, cs, best, tag);
-        Tout0[0] = best;
-        Gout0[0] = tag;
+        Tout0[0] = skip ? SR2_INF : best;
+        Gout0[0] = skip ? SR2_NO_TAG : tag;
         super_cell(base, spad, 1, 0, 0, cx, true, SR2_KEY_NONE, SR2_KEY_NONE, cs, best, tag);
-        Tout1[0] = best;
-        Gout1[0] = tag;
+        Tout1[0] = skip ? SR2_INF : best;
+        Gout1[0] = skip ? SR2_NO_TAG : tag;
         for (int i = 0; i < 2; ++i)
             for (int K = 0; K < 2; ++K) SARR(base, spad, i, K, T_SEP)[0] = SR2_KEY_NONE;
     }
@@ -306,9 +312,11 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
                 int best;
                 unsigned tag;
                 super_cell(base, spad, K, c, d + 1, cx0, false, Pc_0, Pc_1, cs, best, tag);
+                if (only >= 0 && only != c) best = SR2_INF, tag = SR2_NO_TAG;
                 (K ? Tout1 : Tout0)[c] = best;
                 (K ? Gout1 : Gout0)[c] = tag;
                 super_cell(base, spad, K, c + 1, d + 1, cx1, false, Pd_0, Pd_1, cs, best, tag);
+                if (only >= 0 && only != c + 1) best = SR2_INF, tag = SR2_NO_TAG;
                 (K ? Tout1 : Tout0)[c + 1] = best;
                 (K ? Gout1 : Gout0)[c + 1] = tag;
                 E0[c] = Pc_0;
@@ -924,6 +932,31 @@ int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_w
     return SR2_OK;
 }
 
+extern "C" int sr2_superdtl_set_allowed(sr2_ctx* ctx, const int32_t* node_species) {
+    if (!ctx) return SR2_ERR_ARG;
+    SuperProblem* p = ctx->super;
+    if (!p) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_set_allowed: nothing uploaded");
+    if (p->shared)
+        return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_set_allowed: not available for resolution batches");
+    SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!node_species) {
+        p->d_allowed = nullptr;
+        return SR2_OK;
+    }
+    const size_t N = (size_t)p->rows.N;
+    for (size_t u = 0; u < N; ++u)
+        if (node_species[u] < -1 || node_species[u] >= ctx->S)
+            return sr2_fail(ctx, SR2_ERR_ARG, "sr2_superdtl_set_allowed: species out of range");
+    void* ptr = nullptr;
+    int rc = sr2_dev_reserve(ctx, DP_S_ALLOWED, std::max<size_t>(N, 1) * 4, &ptr);
+    if (rc) return rc;
+    p->d_allowed = (int32_t*)ptr;
+    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_allowed, node_species, N * 4, cudaMemcpyHostToDevice, ctx->stream));
+    SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    p->solved = false;
+    return SR2_OK;
+}
+
 static int super_configure(sr2_ctx* ctx, SuperProblem* p) {
     const int S = ctx->S;
     p->spad = (S + 1) & ~1;
@@ -1000,10 +1033,12 @@ static int super_solve_shared(sr2_ctx* ctx, SuperProblem* p) {
         if (n <= 0) continue;
         if (!p->cta_per_row) {
             superdtl_wave_kernel<32><<<grid_for(n, p->wave_warps), p->wave_warps * 32, p->wave_smem, st>>>(
-                ctx->dsp, p->d_slot_cl, p->d_slot_cr, p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad);
+                ctx->dsp, p->d_slot_cl, p->d_slot_cr, p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad,
+                nullptr, nullptr);
         } else {
             superdtl_wave_kernel<256><<<(unsigned)n, 256, p->wave_smem, st>>>(
-                ctx->dsp, p->d_slot_cl, p->d_slot_cr, p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad);
+                ctx->dsp, p->d_slot_cl, p->d_slot_cr, p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad,
+                nullptr, nullptr);
         }
         ++n_launch;
         ++n_waves;
@@ -1097,11 +1132,11 @@ extern "C" int sr2_superdtl_solve(sr2_ctx* ctx) {
         if (!p->cta_per_row) {
             superdtl_wave_kernel<32><<<grid_for(n, p->wave_warps), p->wave_warps * 32, p->wave_smem, st>>>(
                 ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, c.wave_off[h], c.row_begin, (int)n, p->d_T,
-                p->d_tag, cs, p->spad);
+                p->d_tag, cs, p->spad, rows.row_node, p->d_allowed);
         } else {
             superdtl_wave_kernel<256><<<(unsigned)n, 256, p->wave_smem, st>>>(
                 ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, c.wave_off[h], c.row_begin, (int)n, p->d_T,
-                p->d_tag, cs, p->spad);
+                p->d_tag, cs, p->spad, rows.row_node, p->d_allowed);
         }
         ++n_launch;
         ++n_waves;

@@ -152,3 +152,17 @@ def test_entry_point_signatures_satisfy_the_cli_introspection():
         assert len(params) == 2
         assert params[0].annotation is cls and params[1].annotation is RetentionPolicy
         assert fn.__doc__ and fn.__doc__.strip()
+
+
+def test_reconcile_lca_against_the_reference(golden):
+    """reconcile_lca (host only, reference compute/reconciliation.py:23-44): same mapping and
+    cost() as the reference on the base_uspfs fixtures."""
+    from superrec2_b200.compute.reconciliation import reconcile_lca
+    from superrec2_b200.model.reconciliation import SuperReconciliationInput
+    for fixture in golden("base_uspfs.json.gz"):
+        rec_input = SuperReconciliationInput.from_dict(fixture["input"])
+        output = reconcile_lca(rec_input)
+        got = {node.name: species.name for node, species in output.object_species.items() if node.name}
+        assert got == fixture["lca"]
+        cost = output.cost()
+        assert (None if cost == float("inf") else cost) == fixture["lca_cost"]

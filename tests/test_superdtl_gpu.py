@@ -215,3 +215,19 @@ def test_shared_rows_equal_unshared_rows(ctx, monkeypatch, shape):
         assert plain_best == shared_best
         for a, b in zip(plain, shared):
             assert (a == b).all()
+
+
+def test_base_uspfs_against_the_reference(golden):
+    """usreconcile_base_uspfs = the superdtl table restricted to the LCA mapping (`allowed_species`,
+    reference :500-520).  Outputs equal the reference's on its own test instances
+    (tests/compute/test_unordered_super_reconciliation.py:99-331) and on 120 random ones."""
+    from superrec2_b200.compute.unordered_super_reconciliation import usreconcile_base_uspfs
+    for fixture in golden("base_uspfs.json.gz"):
+        srec_input = SuperReconciliationInput.from_dict(fixture["input"])
+        results = usreconcile_base_uspfs(srec_input, RetentionPolicy.ANY)
+        if fixture["result"] is None:
+            assert not results
+            continue
+        (result,) = results
+        assert result.to_dict() == fixture["result"]
+        assert result.cost() == fixture["min_cost"]
