@@ -21,6 +21,7 @@ Fixtures:
   superdtl_reference.json.gz  data/example.in.json, the reference test instances
   crispr.json.gz           data/crispr-class1.in.json (superdtl, default costs)
   binarize.json.gz         enumeration order of ReconciliationInput.binarize()
+  thl_all.json.gz          dtl instances with the full RetentionPolicy.ALL solution set
   base_uspfs.json.gz       binary instances solved by usreconcile_base_uspfs (superdtl table
                            restricted to the LCA mapping) and by reconcile_lca, incl. the
                            instances of tests/compute/test_unordered_super_reconciliation.py
@@ -199,6 +200,22 @@ def superdtl_fixture(data, with_table):
     return fixture
 
 
+def thl_all_fixture(data):
+    """reconcile_thl with RetentionPolicy.ALL: the whole solution set (compared as a set)."""
+    rec_input = ReconciliationInput.from_dict(data)
+    fixture = {"kind": "thl_all", "input": data}
+    try:
+        results = list(ref_rec.reconcile_thl(rec_input, RetentionPolicy.ALL))
+    except KeyError:
+        fixture["error"] = "KeyError"
+        return fixture
+    fixture["min_cost"] = num(results[0].cost()) if results else None
+    fixture["solutions"] = sorted(
+        sorted((node.name, species.name) for node, species in out.object_species.items())
+        for out in results)
+    return fixture
+
+
 def base_uspfs_fixture(data):
     """usreconcile_base_uspfs (:500-520) and reconcile_lca (compute/reconciliation.py:23-44)."""
     fixture = {"kind": "base_uspfs", "input": data}
@@ -364,6 +381,24 @@ def main():
             random_instance(rng2, n_s, n_o, i % 3 != 2, mode, families=rng2.randint(1, 6),
                             name_internal=i % 2 == 0)))
     write("base_uspfs.json.gz", base)
+
+    # ---- dtl, every solution (--solutions all) ------------------------------------------
+    rng3 = random.Random(20261021)
+    every = [thl_all_fixture({
+        "object_tree": "((x_1,(x_2,(y_1,z_1)5)4)3,(y_2,z_2)2)1;",
+        "species_tree": "(X,(Y,Z)YZ)XYZ;",
+        "leaf_object_species": {"x_1": "X", "x_2": "X", "y_1": "Y", "z_1": "Z", "y_2": "Y", "z_2": "Z"},
+        "costs": dict(zip(COST_NAMES, [0, 1, 1, 1, 1])),
+    })]
+    while len(every) < 160:
+        i = len(every)
+        n_s = rng3.randint(1, 6)
+        n_o = max(n_s, rng3.randint(1, 8))
+        mode = ["default", "zero", "spe", "random"][i % 4]
+        fixture = thl_all_fixture(random_instance(rng3, n_s, n_o, True, mode))
+        if len(fixture.get("solutions", ())) <= 3000:
+            every.append(fixture)
+    write("thl_all.json.gz", every)
 
 
 if __name__ == "__main__":

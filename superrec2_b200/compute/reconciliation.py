@@ -74,11 +74,142 @@ def reconcile_thl(
     guaranteed to be time-consistent.
 
     :param rec_input: reconciliation input
-    :param policy: ``RetentionPolicy.ANY`` (one solution)
-    :returns: any minimum-cost reconciliation
+    :param policy: ``RetentionPolicy.ANY`` (one solution) or ``ALL`` (every solution the
+        reference enumerates; the table comes from the GPU, the enumeration runs on the host)
+    :returns: any minimum-cost reconciliation, or all of them
     """
+    if policy is RetentionPolicy.ALL:
+        return reconcile_thl_all(rec_input)
     outputs = reconcile_thl_batch([rec_input], policy)
     return outputs[0]
+
+
+def reconcile_thl_all(rec_input: ReconciliationInput, device: int = 0) -> Set[ReconciliationOutput]:
+    """
+    ``reconcile_thl(rec_input, RetentionPolicy.ALL)`` of the reference
+    (``compute/reconciliation.py:266-294`` with ``_decode_thl_table :228-263``): every
+    reconciliation reachable through ALL minimum-achieving tags, filtered to those of minimum
+    ``cost()``.
+
+    The O(|G||S|^2) part -- the value table -- is computed on the GPU (the values do not depend
+    on the retention policy: with non-negative loss cost the first candidate in level order is
+    also the cheapest).  The tag SETS are rebuilt on the host only for
+    the cells the enumeration actually visits, with the reference's rules
+    (``utils/dynamic_programming.py:215-260``: an equal value adds a tag; minima over a child
+    row keep every species that reaches the minimum), and checked against the GPU value.
+    The number of solutions can be exponential, exactly as in the reference.
+    """
+    species = flatten_species(rec_input.species_lca.tree)
+    layout = flatten_objects(rec_input.object_tree, rec_input.leaf_object_species, species.rank)
+    costs = cost_vector(rec_input.costs)
+    n, S = len(layout.nodes), len(species.nodes)
+    ctx = _lib.default_context(device)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    ctx.dtl_run(np.asarray([0, n], np.int64), layout.left, layout.right, layout.leaf_species, costs,
+                flags=_lib.SR2_KEEP_TABLES)
+    value, _ = ctx.dtl_tables(0, n)
+    INF = _lib.SR2_INF
+    T = value.astype(np.int64)
+
+    # species geometry by BFS rank
+    depth = np.zeros(S, np.int64)
+    for y in range(1, S):
+        depth[y] = depth[species.parent[y]] + 1
+    size = np.ones(S, np.int64)
+    for y in range(S - 1, 0, -1):
+        size[species.parent[y]] += size[y]
+    tin = np.zeros(S, np.int64)
+    for y in range(S):
+        if species.child0[y] >= 0:
+            tin[species.child0[y]] = tin[y] + 1
+            tin[species.child1[y]] = tin[y] + 1 + size[species.child0[y]]
+    tout = tin + size
+    ranks = np.arange(S)
+    _, dup, hgt, loss, _ = (int(c) for c in costs)
+
+    def below(x):            # species in the subtree of x (x included), level order
+        return ranks[(tin >= tin[x]) & (tin < tout[x])]
+
+    def separate(x):         # species neither below nor above x
+        return ranks[~((tin >= tin[x]) & (tin < tout[x])) & ~((tin <= tin[x]) & (tin[x] < tout))]
+
+    def minima(row, subset):
+        """(minimum, every species of `subset` reaching it) -- Entry.update under ALL."""
+        if len(subset) == 0:
+            return INF, subset
+        vals = row[subset]
+        low = vals.min()
+        return int(low), subset[vals == low]
+
+    tag_cache = {}
+
+    def tags(u, x):
+        """The MappingInfo set of table[u][x] under RetentionPolicy.ALL, as (left, right) ranks."""
+        key = (u, x)
+        if key in tag_cache:
+            return tag_cache[key]
+        l, r = layout.left[u], layout.right[u]
+        found = {}
+
+        def offer(left_min, right_min, extra):
+            (vl, sl), (vr, sr) = left_min, right_min
+            if vl >= INF or vr >= INF:
+                return
+            for a in sl:
+                for b in sr:
+                    found.setdefault(vl + vr + extra(int(a), int(b)), set()).add((int(a), int(b)))
+
+        dx = int(depth[x])
+        if species.child0[x] >= 0:
+            x0, x1 = int(species.child0[x]), int(species.child1[x])
+            spe = lambda a, b: loss * (int(depth[a]) + int(depth[b]) - 2 * dx - 2)  # noqa: E731
+            offer(minima(T[l], below(x0)), minima(T[r], below(x1)), spe)
+            offer(minima(T[l], below(x1)), minima(T[r], below(x0)), spe)
+        sub, sep = below(x), separate(x)
+        offer(minima(T[l], sub), minima(T[r], sub),
+              lambda a, b: dup + loss * (int(depth[a]) + int(depth[b]) - 2 * dx))
+        offer(minima(T[l], sep), minima(T[r], sub), lambda a, b: hgt + loss * (int(depth[b]) - dx))
+        offer(minima(T[l], sub), minima(T[r], sep), lambda a, b: hgt + loss * (int(depth[a]) - dx))
+        result = ()
+        if found:
+            best = min(found)
+            if best != T[u][x]:
+                raise _lib.Sr2Error(-5, f"host tag sets disagree with the device table at cell ({u}, {x})")
+            result = tuple(sorted(found[best]))
+        tag_cache[key] = result
+        return result
+
+    import sys
+    from itertools import product
+
+    def decode(u, x):
+        """_decode_thl_table: dicts in the reference's key order (node, left subtree, right subtree)."""
+        node = layout.nodes[u]
+        options = tags(u, x) if layout.left[u] >= 0 else ()
+        if not options:
+            yield {node: species.nodes[x]}
+            return
+        for a, b in options:
+            for left_map, right_map in product(decode(int(layout.left[u]), a), decode(int(layout.right[u]), b)):
+                yield {node: species.nodes[x], **left_map, **right_map}
+
+    best_cost, best = None, set()
+    old_limit = sys.getrecursionlimit()
+    sys.setrecursionlimit(max(old_limit, 4 * n + 1000))
+    try:
+        for x in range(S):
+            if layout.left[0] >= 0 and T[0][x] >= INF:
+                continue  # no entry: the reference raises KeyError here (SURVEY.md Hazard B); skipped
+            for mapping in decode(0, x):
+                output = ReconciliationOutput(rec_input, mapping)
+                cost = output.cost()
+                if best_cost is None or cost < best_cost:
+                    best_cost, best = cost, {output}
+                elif cost == best_cost:
+                    best.add(output)
+    finally:
+        sys.setrecursionlimit(old_limit)
+    return best
 
 
 def reconcile_thl_batch(
@@ -91,10 +222,10 @@ def reconcile_thl_batch(
     (all inputs must share ``species_lca`` and ``costs``).  Returns one result
     set per input, each identical to ``reconcile_thl(input, policy)``.
     """
+    if policy is RetentionPolicy.ALL:
+        return [reconcile_thl_all(item, device) for item in rec_inputs]
     if policy is not RetentionPolicy.ANY:
-        raise NotImplementedError(
-            "only RetentionPolicy.ANY is implemented on the GPU path so far "
-            "(SURVEY.md section 8f item 1)")
+        raise ValueError(f"unsupported retention policy {policy!r}")
     if not rec_inputs:
         return []
     first = rec_inputs[0]

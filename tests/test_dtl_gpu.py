@@ -206,3 +206,20 @@ def test_kernel_variants_agree_on_a_large_batch(ctx, monkeypatch):
     from tests.helpers import flat_cost
     for b in (0, 299, 599):
         assert flat_cost(batch, b, simd[2]) == simd[0][b]
+
+
+def test_all_solutions_against_the_reference(golden):
+    """reconcile_thl(..., RetentionPolicy.ALL) (`--solutions all`): the value
+    table comes from the GPU, the reference's ALL-retention tag sets are rebuilt on the host for
+    the visited cells.  Set equality with the reference's full solution sets on 160 instances
+    (up to 3,000 solutions each), incl. tests/compute/test_reconciliation.py:67-123."""
+    from superrec2_b200.compute.reconciliation import reconcile_thl
+    from superrec2_b200.model.reconciliation import ReconciliationInput
+    from superrec2_b200.utils.dynamic_programming import RetentionPolicy
+    for fixture in golden("thl_all.json.gz"):
+        rec_input = ReconciliationInput.from_dict(fixture["input"])
+        results = reconcile_thl(rec_input, RetentionPolicy.ALL)
+        got = sorted(sorted([node.name, species.name] for node, species in out.object_species.items())
+                     for out in results)
+        assert got == fixture["solutions"]
+        assert {out.cost() for out in results} == {fixture["min_cost"]}
