@@ -179,15 +179,23 @@ class Context:
         self._check(self._lib.sr2_dtl_results(self._handle, p32(min_cost), p32(root), p32(mapping)))
         return min_cost, root, mapping
 
-    def dtl_run(self, node_off, left, right, leaf_species, costs, flags=0):
-        """upload + solve + results with host buffers (the e2e path)."""
+    def dtl_run(self, node_off, left, right, leaf_species, costs, flags=0, out=None):
+        """upload + solve + results with host buffers (the e2e path).  ``out`` = optional
+        ``(min_cost[int32 n_inst], root[int32 n_inst], mapping[int32 n_nodes])`` arrays to fill
+        (a caller that solves batch after batch reuses its result buffers)."""
         node_off, left, right = i64(node_off), i32(left), i32(right)
         leaf_species, costs = i32(leaf_species), i32(costs)
         n_inst, n_nodes = len(node_off) - 1, int(node_off[-1])
         self._batch = (n_inst, n_nodes)
-        min_cost = np.empty(n_inst, np.int32)
-        root = np.empty(n_inst, np.int32)
-        mapping = np.empty(n_nodes, np.int32)
+        if out is not None:
+            min_cost, root, mapping = out
+            for arr, size in ((min_cost, n_inst), (root, n_inst), (mapping, n_nodes)):
+                if arr.dtype != np.int32 or arr.shape != (size,) or not arr.flags.c_contiguous:
+                    raise ValueError("out arrays must be contiguous int32 of the batch's sizes")
+        else:
+            min_cost = np.empty(n_inst, np.int32)
+            root = np.empty(n_inst, np.int32)
+            mapping = np.empty(n_nodes, np.int32)
         self._check(self._lib.sr2_dtl_run(
             self._handle, n_inst, p64(node_off), p32(left), p32(right), p32(leaf_species),
             p32(costs), flags, p32(min_cost), p32(root), p32(mapping)))

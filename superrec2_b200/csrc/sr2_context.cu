@@ -157,6 +157,7 @@ extern "C" void sr2_destroy(sr2_ctx* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    if (ctx->fill_stream) cudaStreamDestroy(ctx->fill_stream);
     for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

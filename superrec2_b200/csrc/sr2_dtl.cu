@@ -1130,6 +1130,25 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     RowHooks plan_only;
     plan_only.user = ctx;
     plan_only.on_plan = dtl_prepare;
+    // pipelined runs of big batches bucket their rows on the device (one thread per tree)
+    if (p->two_streams && B >= 1024) {
+        const char* dev_rows = getenv("SR2_DEVICE_ROWS");
+        if (!(dev_rows && dev_rows[0] == '0')) {
+            size_t raw = (size_t)N * 22 + (size_t)B * 520;  // raw arrays, heights, node rows, per-instance bases
+            int64_t budget = rows_budget;
+            if (free_b > fixed + raw + per_row * 8) {
+                budget = std::min(budget, (int64_t)(((free_b - fixed - raw) / 10 * 9) / per_row / 2));
+                if (getenv("SR2_TRACE")) fprintf(stderr, "[sr2] dtl upload: %.2f ms before the row builder\n", now_ms() - t0);
+                int rc = sr2_build_rows_device(ctx, "sr2_dtl_run", B, node_off, left, right, leaf_species, budget,
+                                               &p->rows, hooks, first_chunk_rows);
+                if (rc != SR2_ROWS_FALLBACK) {
+                    if (!rc) ctx->timing.upload_ms = (float)(now_ms() - t0);
+                    return rc;
+                }
+                p->prepared = false;  // a tree too high for the device tables: bucket on the host
+            }
+        }
+    }
     int rc = sr2_build_rows(ctx, "sr2_dtl_upload", B, node_off, left, right, leaf_species, rows_budget,
                             (flags & SR2_KEEP_TABLES) != 0, false, &p->rows, hooks ? hooks : &plan_only,
                             first_chunk_rows);
@@ -1488,6 +1507,10 @@ static int dtl_deliver(DtlRunState* rs, int upto, bool wait) {
 static int dtl_run_on_plan(void* user) {
     DtlRunState* rs = (DtlRunState*)user;
     sr2_ctx* ctx = rs->ctx;
+    if (rs->started) {  // a second plan: the device-side bucketing handed over to the host-side one
+        cudaStreamSynchronize(ctx->copy_stream);
+        rs->delivered = 0;
+    }
     int rc = dtl_prepare(ctx);
     if (rc) return rc;
     DtlProblem* p = ctx->dtl;
@@ -1546,6 +1569,7 @@ extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     double t0 = now_ms();
     int rc = dtl_upload_impl(ctx, B, node_off, left, right, leaf_species, costs, flags, pipeline_chunks, &hooks);
     double t1 = now_ms();  // the host side is done; sr2_build_rows waited for the compute stream
+    if (getenv("SR2_TRACE")) fprintf(stderr, "[sr2] dtl run: upload_impl returned after %.2f ms\n", t1 - t0);
     DtlProblem* p = ctx->dtl;
     if (!rc) rc = dtl_deliver(&rs, (int)p->rows.chunks.size(), true);
     if (rs.started) {
@@ -1560,6 +1584,7 @@ extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     dtl_collect_timing(ctx, p);
     p->solved = true;
     p->wait_rows = false;
+    if (getenv("SR2_TRACE")) fprintf(stderr, "[sr2] dtl run: done after %.2f ms\n", now_ms() - t0);
     ctx->timing.upload_ms = (float)(t1 - t0);         // bucketing with the device work overlapped
     ctx->timing.results_ms = (float)(now_ms() - t1);  // what was left of staging -> caller's buffers
     return SR2_OK;

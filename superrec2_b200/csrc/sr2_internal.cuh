@@ -107,9 +107,10 @@ enum Sr2DevPool {
     DP_S_LEFT, DP_S_RIGHT, DP_S_NODEOFF, DP_S_BITS, DP_S_PRESENT, DP_S_OUTSIDE, DP_S_GAIN, DP_S_L, DP_S_FLAGS,
     DP_S_T, DP_S_TAG, DP_S_DEC, DP_S_ANC, DP_S_TAU, DP_S_TAUMIN, DP_S_COST, DP_S_MINCOST, DP_S_ROOTSP, DP_S_MAP,
     DP_S_KIND, DP_S_SYN, DP_S_BEST, DP_S_ALLOWED,
-    DP_S_NODESLOT, DP_S_NODEDAG, DP_S_NODEPRE, DP_S_NODEINST, DP_S_PLAN32, DP_S_PLAN64, DP_COUNT
+    DP_S_NODESLOT, DP_S_NODEDAG, DP_S_NODEPRE, DP_S_NODEINST, DP_S_PLAN32, DP_S_PLAN64,
+    DP_RAW, DP_RAW_HEIGHT, DP_RAW_NODEROW, DP_RAW_INSTBASE, DP_RAW_COUNTS, DP_RAW_NODEOFF, DP_COUNT
 };
-enum Sr2PinPool { HP_ROWS_SLAB, HP_ROOT_ROW, HP_ROOT_NODE, HP_NODE_PRE, HP_NODE_INST, HP_RESULTS, HP_COUNT };
+enum Sr2PinPool { HP_ROWS_SLAB, HP_ROOT_ROW, HP_ROOT_NODE, HP_NODE_PRE, HP_NODE_INST, HP_RESULTS, HP_RAW, HP_COUNTS, HP_COUNT };
 enum Sr2HostPool { MP_HEIGHT, MP_NODE_ROW, MP_CNT, MP_COUNT };
 
 struct sr2_ctx {
@@ -118,6 +119,7 @@ struct sr2_ctx {
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;    // device-to-host result copies of pipelined runs (lazy)
     cudaStream_t stream2 = nullptr;        // second compute stream of pipelined runs (lazy)
+    cudaStream_t fill_stream = nullptr;    // device-side bucketing, second phase (lazy)
     cudaStream_t upload_stream = nullptr;  // host-to-device row copies of pipelined runs (lazy)
     std::vector<cudaEvent_t> chunk_events; // "rows of chunk i are on the device"
     std::string err;

@@ -55,3 +55,16 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
                    const int32_t* left, const int32_t* right, const int32_t* leaf_species,
                    int64_t rows_budget, bool keep_host, bool want_preorder, RowLayout* out,
                    const RowHooks* hooks = nullptr, int64_t first_chunk_rows = 0);
+
+// The same result as sr2_build_rows, with the bucketing done ON THE DEVICE (dtl pipelined runs):
+// the raw child / leaf arrays of a chunk are copied to the device (directly when the caller's arrays
+// are pinned, else through pinned staging), one thread per tree validates it, computes heights and
+// per-height counts (rows_height_kernel), the host turns the chunk's counts into wave offsets, and a
+// second kernel hands out rows bottom-up (rows_fill_kernel).  The host only plans chunks and waits
+// for a few hundred bytes per chunk.  Returns SR2_ROWS_FALLBACK (> 0, nothing launched for the
+// offending chunk) when a tree is higher than the per-thread tables allow; the caller then uses
+// sr2_build_rows.  hooks->on_chunk is required.
+#define SR2_ROWS_FALLBACK 1
+int sr2_build_rows_device(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node_off,
+                          const int32_t* left, const int32_t* right, const int32_t* leaf_species,
+                          int64_t rows_budget, RowLayout* out, const RowHooks* hooks, int64_t first_chunk_rows);

@@ -223,3 +223,45 @@ def test_all_solutions_against_the_reference(golden):
                      for out in results)
         assert got == fixture["solutions"]
         assert {out.cost() for out in results} == {fixture["min_cost"]}
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_device_side_bucketing_equals_host_side(ctx, monkeypatch, pinned):
+    """sr2_dtl_run buckets big batches on the device (rows_height_kernel / rows_fill_kernel, one
+    thread per tree).  Same costs, roots and mappings as the host-side bucketing, from pageable and
+    from pinned input arrays; a malformed tree is reported with its instance number; a tree higher
+    than the device tables falls back to the host path."""
+    batch = synth.make_batch(40, 90, 3000, seed=77)
+    ctx.set_species(batch.parent, batch.child0, batch.child1)
+    arrays = [batch.left, batch.right, batch.leaf_species]
+    if pinned:
+        import torch
+        arrays = [torch.from_numpy(a.copy()).pin_memory().numpy() for a in arrays]
+    monkeypatch.setenv("SR2_DEVICE_ROWS", "0")
+    host = ctx.dtl_run(batch.node_off, *arrays, batch.costs)
+    monkeypatch.setenv("SR2_DEVICE_ROWS", "1")
+    dev = ctx.dtl_run(batch.node_off, *arrays, batch.costs)
+    for a, b in zip(host, dev):
+        assert (a == b).all()
+    # malformed: a child numbered before its parent
+    bad = batch.left.copy()
+    off = int(batch.node_off[1234])
+    bad[off + 5], bad[off + 0] = bad[off + 0], 0
+    with pytest.raises(_lib.Sr2Error, match="instance 1234"):
+        ctx.dtl_run(batch.node_off, bad, batch.right, batch.leaf_species, batch.costs)
+    # caterpillar trees (height = leaves - 1 = 199 > 127): handled by the host path
+    n = 200
+    left = np.full(2 * n - 1, -1, np.int32)
+    right = np.full(2 * n - 1, -1, np.int32)
+    for u in range(n - 1):
+        left[u] = u + 1 if u + 1 < n - 1 else 2 * n - 2
+        right[u] = n - 1 + u
+    species_leaves = np.flatnonzero(batch.child0 < 0).astype(np.int32)
+    leaf = np.full(2 * n - 1, -1, np.int32)
+    leaf[n - 1:] = species_leaves[np.arange(n) % len(species_leaves)]
+    count = 1100
+    node_off = np.arange(count + 1, dtype=np.int64) * (2 * n - 1)
+    tall = ctx.dtl_run(node_off, np.tile(left, count), np.tile(right, count), np.tile(leaf, count), batch.costs)
+    ref = oracle.dtl(batch.parent, batch.child0, batch.child1, left, right, leaf, batch.costs, strict=False)
+    assert (tall[0] == ref["min_cost"]).all() and (tall[1] == ref["root_species"]).all()
+    assert (tall[2].reshape(count, -1) == ref["mapping"]).all()
