@@ -1471,6 +1471,7 @@ struct DtlRunState {
     int32_t* stage;  // pinned: [B] min cost, [B] root species, [N] mapping
     int32_t *out_cost, *out_root, *out_map;
     bool started;
+    bool direct;     // the caller's result arrays are pinned: copy straight into them
     int delivered;   // chunks whose results already sit in the caller's buffers
     std::vector<cudaEvent_t> copied;  // per chunk: its D2H copies finished
 };
@@ -1488,6 +1489,10 @@ static int dtl_deliver(DtlRunState* rs, int upto, bool wait) {
         const RowChunk& c = p->rows.chunks[rs->delivered];
         const size_t b0 = c.inst_begin, nb = c.inst_end - c.inst_begin;
         const int64_t n0 = p->rows.node_off[c.inst_begin], nn = p->rows.node_off[c.inst_end] - n0;
+        if (rs->direct) {
+            ++rs->delivered;
+            continue;
+        }
         if (rs->out_cost) memcpy(rs->out_cost + b0, rs->stage + b0, nb * 4);
         if (rs->out_root) memcpy(rs->out_root + b0, rs->stage + B + b0, nb * 4);
         if (rs->out_map) {
@@ -1519,6 +1524,18 @@ static int dtl_run_on_plan(void* user) {
     if ((rc = sr2_pin_reserve(ctx, HP_RESULTS, (2 * (size_t)p->rows.B + (size_t)p->rows.N + 16) * sizeof(int32_t), &ptr)))
         return rc;
     rs->stage = (int32_t*)ptr;
+    {
+        auto pinned = [](const void* q) {
+            if (!q) return true;
+            cudaPointerAttributes attr;
+            if (cudaPointerGetAttributes(&attr, q) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            return attr.type == cudaMemoryTypeHost;
+        };
+        rs->direct = pinned(rs->out_cost) && pinned(rs->out_root) && pinned(rs->out_map);
+    }
     if (!ctx->copy_stream) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     while (rs->copied.size() < p->rows.chunks.size()) {
         cudaEvent_t e;
@@ -1544,12 +1561,15 @@ static int dtl_run_on_chunk(void* user, int ci) {
     const size_t n0 = p->rows.node_off[c.inst_begin], nn = p->rows.node_off[c.inst_end] - n0;
     cudaStream_t cs = ctx->copy_stream;
     SR2_CUDA(ctx, cudaStreamWaitEvent(cs, p->ev_done[ci], 0));
+    int32_t* to_cost = rs->direct ? rs->out_cost : rs->stage;
+    int32_t* to_root = rs->direct ? rs->out_root : rs->stage + B;
+    int32_t* to_map = rs->direct ? rs->out_map : rs->stage + 2 * B;
     if (rs->out_cost && nb)
-        SR2_CUDA(ctx, cudaMemcpyAsync(rs->stage + b0, p->d_min_cost + b0, nb * 4, cudaMemcpyDeviceToHost, cs));
+        SR2_CUDA(ctx, cudaMemcpyAsync(to_cost + b0, p->d_min_cost + b0, nb * 4, cudaMemcpyDeviceToHost, cs));
     if (rs->out_root && nb)
-        SR2_CUDA(ctx, cudaMemcpyAsync(rs->stage + B + b0, p->d_root_species + b0, nb * 4, cudaMemcpyDeviceToHost, cs));
+        SR2_CUDA(ctx, cudaMemcpyAsync(to_root + b0, p->d_root_species + b0, nb * 4, cudaMemcpyDeviceToHost, cs));
     if (rs->out_map && nn)
-        SR2_CUDA(ctx, cudaMemcpyAsync(rs->stage + 2 * B + n0, p->d_map + n0, nn * 4, cudaMemcpyDeviceToHost, cs));
+        SR2_CUDA(ctx, cudaMemcpyAsync(to_map + n0, p->d_map + n0, nn * 4, cudaMemcpyDeviceToHost, cs));
     SR2_CUDA(ctx, cudaEventRecord(rs->copied[ci], cs));
     return dtl_deliver(rs, ci, false);  // earlier chunks that are back already
 }
@@ -1561,7 +1581,7 @@ extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     if (!ctx) return SR2_ERR_ARG;
     int pipeline_chunks = 3;
     if (const char* v = getenv("SR2_PIPELINE_CHUNKS")) pipeline_chunks = std::max(1, atoi(v));
-    DtlRunState rs{ctx, nullptr, out_min_cost, out_root_species, out_map_species, false, 0, {}};
+    DtlRunState rs{ctx, nullptr, out_min_cost, out_root_species, out_map_species, false, false, 0, {}};
     RowHooks hooks;
     hooks.user = &rs;
     hooks.on_plan = dtl_run_on_plan;
