@@ -17,7 +17,7 @@ SR2_INF = 0x3FFFFFFF
 SR2_KEEP_TABLES = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsr2.so")
+LIB_PATH = os.environ.get("SR2_LIBRARY", os.path.join(_HERE, "libsr2.so"))  # override for A/B builds
 
 
 class Sr2Error(RuntimeError):
