@@ -50,3 +50,36 @@ def test_superdtl_without_syntenies_is_an_error(tmp_path, golden):
     proc, dst = _run(tmp_path, data, "superdtl")
     assert proc.returncode == 1
     assert "you need to provide leaf syntenies" in proc.stderr
+
+
+def _cost_flags(costs):
+    return ["--cost-spe", str(costs["SPECIATION"]), "--cost-dup", str(costs["DUPLICATION"]),
+            "--cost-hgt", str(costs["HORIZONTAL_TRANSFER"]), "--cost-floss", str(costs["FULL_LOSS"]),
+            "--cost-sloss", str(costs["SEGMENTAL_LOSS"])]
+
+
+def test_lca_and_base_uspfs_commands(tmp_path, golden):
+    """`lca` (one-argument algorithm, syntenies ignored with a warning) and `base_uspfs`."""
+    fixture = next(f for f in golden("base_uspfs.json.gz")[6:] if f["result"] is not None)
+    data = {k: v for k, v in fixture["input"].items() if k != "costs"}
+    flags = _cost_flags(fixture["input"]["costs"])
+    proc, dst = _run(tmp_path, data, "base_uspfs", *flags)
+    assert proc.returncode == 0, proc.stderr
+    assert f"Minimum cost: {fixture['min_cost']}" in proc.stderr
+    assert json.loads(dst.read_text()) == fixture["result"]
+    proc, dst = _run(tmp_path, data, "lca", *flags)
+    assert proc.returncode == 0, proc.stderr
+    assert "declared leaf syntenies will be ignored" in proc.stderr
+    got = json.loads(dst.read_text())["object_species"]
+    assert {k: v for k, v in got.items()} == fixture["lca"]
+
+
+def test_all_solutions_flag(tmp_path, golden):
+    """`thl --solutions all` prints one JSON document per solution, the reference's set."""
+    fixture = next(f for f in golden("thl_all.json.gz") if 3 <= len(f["solutions"]) <= 40)
+    data = {k: v for k, v in fixture["input"].items() if k != "costs"}
+    proc, dst = _run(tmp_path, data, "thl", "--solutions", "all", *_cost_flags(fixture["input"]["costs"]))
+    assert proc.returncode == 0, proc.stderr
+    lines = [json.loads(line) for line in dst.read_text().splitlines()]
+    got = sorted(sorted([k, v] for k, v in doc["object_species"].items()) for doc in lines)
+    assert got == fixture["solutions"]

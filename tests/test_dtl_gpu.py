@@ -268,3 +268,27 @@ def test_device_side_bucketing_equals_host_side(ctx, monkeypatch, pinned):
     ref = oracle.dtl(batch.parent, batch.child0, batch.child1, left, right, leaf, batch.costs, strict=False)
     assert (tall[0] == ref["min_cost"]).all() and (tall[1] == ref["root_species"]).all()
     assert (tall[2].reshape(count, -1) == ref["mapping"]).all()
+
+
+def test_full_size_batch_pipelined_run_equals_stepwise(ctx):
+    """BASELINE config #2 at full size (10,000 x 500-leaf trees vs 200 leaves, 1.99e9 cells):
+    sr2_dtl_run (pipelined chunks, device-side bucketing, two compute streams) returns exactly what
+    upload + solve + results (one chunk, host-side bucketing) returns; the checksum of the minimum
+    costs is the one bench.py prints; a sample of trees is re-checked with the host cost()."""
+    from tests.helpers import flat_cost
+    batch = synth.make_batch(200, 500, 10000, seed=2000)
+    ctx.set_species(batch.parent, batch.child0, batch.child1)
+    args = (batch.node_off, batch.left, batch.right, batch.leaf_species, batch.costs)
+    ctx.dtl_upload(*args)
+    ctx.dtl_solve()
+    stepwise = ctx.dtl_results()
+    run = ctx.dtl_run(*args)
+    for a, b in zip(stepwise, run):
+        assert (a == b).all()
+    assert int(run[0].astype(np.int64).sum()) == 4774426
+    for b in (0, 4999, 9999):
+        assert flat_cost(batch, b, run[2]) == run[0][b]
+    # an empty batch is a valid call
+    empty = ctx.dtl_run(np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32),
+                        np.zeros(0, np.int32), batch.costs)
+    assert all(len(part) == 0 for part in empty)
