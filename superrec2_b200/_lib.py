@@ -231,10 +231,14 @@ class Context:
     def superdtl_solve(self):
         self._check(self._lib.sr2_superdtl_solve(self._handle))
 
-    def superdtl_results(self):
+    def superdtl_results(self, costs_only=False):
+        """(min cost, root species[, mapping, kind, synteny bits]) of every instance."""
         n_inst, n_nodes, words, _ = self._sbatch
         min_cost = np.empty(n_inst, np.int32)
         root = np.empty(n_inst, np.int32)
+        if costs_only:
+            self._check(self._lib.sr2_superdtl_results(self._handle, p32(min_cost), p32(root), None, None, None))
+            return min_cost, root
         mapping = np.empty(n_nodes, np.int32)
         kind = np.empty(n_nodes, np.int32)
         syn = np.empty((n_nodes, words), np.uint32)

@@ -58,6 +58,8 @@ struct SuperProblem {
     // shared-row mode (resolutions of one multifurcating tree, SharedPlan): the table has one row per
     // distinct subtree ("slot"); per-node arrays still exist for every resolved tree
     bool shared = false;
+    bool fused = false;             // the last solve used sfused_kernel
+    bool materialised = true;       // d_map / d_kind / d_syn hold the last solve's per-node results
     int Gb = 0;                     // nodes of one resolved tree
     int64_t n_slots = 0;
     std::vector<int64_t> slot_wave_off;
@@ -663,6 +665,146 @@ __global__ void sdecode_walk_kernel(DevSpecies sp, int n_inst, int Gb, const int
     }
 }
 
+// Decode + Hazard-A time stamps + cost() + selection of ONE resolved tree per CTA, all state in
+// shared memory: thread k decodes from root species k (sdecode_walk_kernel), the CTA synchronises
+// (the in-place synteny unions only travel between the decodes of one tree), thread k evaluates
+// cost() of its decode (scost_kernel), the CTA keeps the first strict minimum in level order
+// (sselect_kernel) and offers it to the batch's packed best key (sbest_kernel).  Nothing per
+// (node, root) goes to global memory.
+__global__ void sfused_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__ left,
+                              const int32_t* __restrict__ right, const int32_t* __restrict__ node_slot,
+                              const int32_t* __restrict__ node_dag, const int32_t* __restrict__ node_pre,
+                              const uint32_t* __restrict__ tags, int W, const uint32_t* __restrict__ gain,
+                              const uint32_t* __restrict__ L, SuperCosts cs, int64_t index_base,
+                              int32_t* __restrict__ min_cost, int32_t* __restrict__ root_species,
+                              unsigned long long* __restrict__ best_key) {
+    extern __shared__ uint32_t fused_smem[];
+    const int S = sp.S;
+    const int b = blockIdx.x, k = threadIdx.x;
+    const int64_t off = (int64_t)b * Gb;
+    uint32_t* tau = fused_smem;                       // [Gb * W * 32]
+    uint32_t* taumin = tau + (size_t)Gb * W * 32;     // [Gb]
+    uint16_t* dec = reinterpret_cast<uint16_t*>(taumin + Gb);  // [Gb * S]
+    uint16_t* anc = dec + (size_t)Gb * S;             // [Gb * S]
+    __shared__ unsigned long long warp_best[32];
+    for (int i = threadIdx.x; i < Gb * W * 32 + Gb; i += blockDim.x) tau[i] = 0xffffffffu;
+    __syncthreads();
+    if (k < S) {
+        bool ok = tags[((size_t)node_slot[off] * 2 + 0) * sp.pitch + k] != SR2_NO_TAG;  // kind LCA (:487)
+        dec[k] = ok ? (uint16_t)(k << 1) : (uint16_t)DEC_NONE;
+        anc[k] = 0;
+        for (int u = 0; u < Gb; ++u) {
+            const int64_t node = off + u;
+            const int lg = left[node];
+            if (lg < 0) continue;
+            const int l = lg - (int)off, r = right[node] - (int)off;
+            unsigned e = dec[u * S + k];
+            unsigned el = DEC_NONE, er = DEC_NONE;
+            unsigned al = 0, ar = 0;
+            if (e != DEC_NONE) {
+                int x = e >> 1, kd = e & 1;
+                unsigned tag = tags[((size_t)node_slot[node] * 2 + kd) * sp.pitch + x];
+                if (tag != SR2_NO_TAG) {
+                    el = tag & 0xffffu;
+                    er = tag >> 16;
+                    unsigned mine = anc[u * S + k];
+                    al = (el & 1) ? mine : (unsigned)l;
+                    ar = (er & 1) ? mine : (unsigned)r;
+#pragma unroll 1
+                    for (int side = 0; side < 2; ++side) {
+                        unsigned ec = side ? er : el;
+                        if (!(ec & 1)) continue;
+                        int child = side ? r : l;
+                        unsigned owner = side ? ar : al;
+                        unsigned stamp = ((unsigned)k << 16) | (unsigned)node_pre[off + child];
+                        bool any = false;
+                        for (int w = 0; w < W; ++w) {
+                            uint32_t g = gain[(size_t)node_dag[off + child] * W + w];
+                            while (g) {
+                                int f = __ffs(g) - 1;
+                                g &= g - 1;
+                                atomicMin(&tau[((size_t)owner * W + w) * 32 + f], stamp);
+                                any = true;
+                            }
+                        }
+                        if (any) atomicMin(&taumin[owner], stamp);
+                    }
+                }
+            }
+            dec[l * S + k] = (uint16_t)el;
+            dec[r * S + k] = (uint16_t)er;
+            anc[l * S + k] = (uint16_t)al;
+            anc[r * S + k] = (uint16_t)ar;
+        }
+    }
+    __syncthreads();
+    u64 key = SR2_KEY_NONE;
+    if (k < S && dec[k] != DEC_NONE) {
+        int total = 0;
+        auto word = [&](int owner, int w, unsigned stamp) {
+            uint32_t bits = L[(size_t)node_dag[off + owner] * W + w];
+            if (taumin[owner] <= stamp) {
+                const uint32_t* t = tau + ((size_t)owner * W + w) * 32;
+                for (int f = 0; f < 32; ++f)
+                    if (t[f] <= stamp) bits |= 1u << f;
+            }
+            return bits;
+        };
+        for (int u = 0; u < Gb; ++u) {
+            const int lg = left[off + u];
+            if (lg < 0) continue;
+            const int l = lg - (int)off, r = right[off + u] - (int)off;
+            unsigned eu = dec[u * S + k], el = dec[l * S + k], er = dec[r * S + k];
+            int p = eu >> 1, a = el >> 1, c = er >> 1;
+            int dp = __ldg(sp.depth + p), da = __ldg(sp.depth + a), dc = __ldg(sp.depth + c);
+            bool pa = sp_anc(sp, p, a), pc = sp_anc(sp, p, c);
+            int ou = anc[u * S + k], ol = anc[l * S + k], orr = anc[r * S + k];
+            unsigned su = ((unsigned)k << 16) | (unsigned)node_pre[off + u],
+                     sl = ((unsigned)k << 16) | (unsigned)node_pre[off + l],
+                     sr = ((unsigned)k << 16) | (unsigned)node_pre[off + r];
+            bool in_l = true, in_r = true;
+            for (int w = 0; w < W; ++w) {
+                uint32_t mine = word(ou, w, su);
+                in_l &= (mine & ~word(ol, w, sl)) == 0;
+                in_r &= (mine & ~word(orr, w, sr)) == 0;
+            }
+            int lc = in_l ? 0 : cs.sloss, rc = in_r ? 0 : cs.sloss;
+            if (pa && pc) {
+                int cx = __ldg(sp.child0 + p);
+                bool spec = false;
+                if (cx >= 0 && a != p && c != p) {
+                    int t1 = __ldg(sp.tin + cx + 1);
+                    spec = (__ldg(sp.tin + a) < t1) != (__ldg(sp.tin + c) < t1);
+                }
+                if (spec)
+                    total += cs.spe + cs.floss * (da + dc - 2 * dp - 2) + lc + rc;
+                else
+                    total += cs.dup + cs.floss * (da + dc - 2 * dp) + min(lc, rc);
+            } else if (pa) {
+                total += cs.hgt + cs.floss * (da - dp) + lc;
+            } else {
+                total += cs.hgt + cs.floss * (dc - dp) + (sp_anc(sp, a, p) ? lc : rc);
+            }
+        }
+        key = ((u64)(unsigned)total << 32) | (unsigned)k;
+    }
+    for (int o = 16; o; o >>= 1) key = key_min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if ((threadIdx.x & 31) == 0) warp_best[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        key = threadIdx.x < (blockDim.x >> 5) ? warp_best[threadIdx.x] : SR2_KEY_NONE;
+        for (int o = 16; o; o >>= 1) key = key_min(key, __shfl_xor_sync(0xffffffffu, key, o));
+        if (threadIdx.x == 0) {
+            bool none = key == SR2_KEY_NONE;
+            int cost = none ? SR2_INF : (int)(key >> 32), root = none ? -1 : (int)(key & 0xffffffffu);
+            min_cost[b] = cost;
+            root_species[b] = root;
+            if (!none)
+                atomicMin(best_key, ((u64)(unsigned)cost << 40) | ((u64)(index_base + b) << 16) | (unsigned)root);
+        }
+    }
+}
+
 __global__ void iota_kernel(int32_t* __restrict__ out, int64_t n, int32_t start) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = start + (int32_t)i;
@@ -980,12 +1122,40 @@ static int super_configure(sr2_ctx* ctx, SuperProblem* p) {
 
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::max<int64_t>(1, (n + block - 1) / block); }
 
+// Shared-row mode, per (node, root) state in global memory: decode, time stamps, cost(), selection
+// and the mapping / kind / synteny of every node of every instance.  Runs in the solve when the
+// fused kernel does not fit, and on demand when a caller asks for per-node results.
+static int super_decode_shared(sr2_ctx* ctx, SuperProblem* p, int* n_launch) {
+    cudaStream_t st = ctx->stream;
+    const int W = p->W, S = ctx->S, Gb = p->Gb;
+    const int64_t N = p->rows.N;
+    const int B = p->rows.B;
+    SuperCosts cs{p->costs[0], p->costs[1], p->costs[2], p->costs[3], p->costs[4]};
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_tau, 0xff, std::max<size_t>((size_t)N * W * 128, 4), st));
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_taumin, 0xff, std::max<size_t>((size_t)N * 4, 4), st));
+    sdecode_walk_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
+        ctx->dsp, B, Gb, p->d_left, p->d_right, p->d_node_slot, p->d_node_dag, p->d_node_pre, p->d_tag, W,
+        p->d_gain, p->d_dec, p->d_anc, p->d_tau, p->d_taumin);
+    scost_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
+        ctx->dsp, p->d_node_off, p->d_left, p->d_right, p->d_node_pre, 0, B, W, p->d_L, p->d_tau, p->d_taumin,
+        p->d_dec, p->d_anc, cs, p->d_cost, p->d_node_dag);
+    sselect_kernel<<<grid_for(B, 8), 256, 0, st>>>(ctx->dsp, 0, B, p->d_cost, p->d_dec, p->d_node_off,
+                                                   p->d_min_cost, p->d_root_species);
+    smaterialise_kernel<<<grid_for(N, 256), 256, 0, st>>>(
+        ctx->dsp, 0, N, p->d_node_inst, p->d_node_off, p->d_node_pre, p->d_root_species, W, p->d_L, p->d_tau,
+        p->d_taumin, p->d_dec, p->d_anc, p->d_map, p->d_kind, p->d_syn, p->d_node_dag);
+    SR2_CUDA(ctx, cudaGetLastError());
+    if (n_launch) *n_launch += 4;
+    p->materialised = true;
+    return SR2_OK;
+}
+
 // Shared-row solve: synteny sets and the table over the distinct subtrees (dag), then decode,
 // cost() and selection per resolved tree.
 static int super_solve_shared(sr2_ctx* ctx, SuperProblem* p) {
     cudaStream_t st = ctx->stream;
     const int W = p->W, S = ctx->S, Gb = p->Gb;
-    const int64_t N = p->rows.N, NS = p->n_slots, D = Gb + NS;
+    const int64_t NS = p->n_slots, D = Gb + NS;
     const int B = p->rows.B;
     const std::vector<int64_t>& wo = p->slot_wave_off;
     const int H = (int)wo.size() - 2;
@@ -996,8 +1166,6 @@ static int super_solve_shared(sr2_ctx* ctx, SuperProblem* p) {
     SR2_CUDA(ctx, cudaMemcpyAsync(p->d_present, p->d_bits, dw * 4, cudaMemcpyDeviceToDevice, st));
     SR2_CUDA(ctx, cudaMemcpyAsync(p->d_L, p->d_bits, dw * 4, cudaMemcpyDeviceToDevice, st));
     SR2_CUDA(ctx, cudaMemsetAsync(p->d_outside, 0, std::max<size_t>(dw * 4, 4), st));
-    SR2_CUDA(ctx, cudaMemsetAsync(p->d_tau, 0xff, std::max<size_t>((size_t)N * W * 128, 4), st));
-    SR2_CUDA(ctx, cudaMemsetAsync(p->d_taumin, 0xff, std::max<size_t>((size_t)N * 4, 4), st));
     SR2_CUDA(ctx, cudaMemsetAsync(p->d_best, 0xff, 8, st));
     const int32_t* s_left = p->d_dag_left + Gb;    // indexed by slot
     const int32_t* s_right = p->d_dag_right + Gb;
@@ -1046,20 +1214,26 @@ static int super_solve_shared(sr2_ctx* ctx, SuperProblem* p) {
     SR2_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
     SR2_CUDA(ctx, cudaGetLastError());
     if (B > 0) {
-        sdecode_walk_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
-            ctx->dsp, B, Gb, p->d_left, p->d_right, p->d_node_slot, p->d_node_dag, p->d_node_pre, p->d_tag, W,
-            p->d_gain, p->d_dec, p->d_anc, p->d_tau, p->d_taumin);
-        scost_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
-            ctx->dsp, p->d_node_off, p->d_left, p->d_right, p->d_node_pre, 0, B, W, p->d_L, p->d_tau, p->d_taumin,
-            p->d_dec, p->d_anc, cs, p->d_cost, p->d_node_dag);
-        sselect_kernel<<<grid_for(B, 8), 256, 0, st>>>(ctx->dsp, 0, B, p->d_cost, p->d_dec, p->d_node_off,
-                                                       p->d_min_cost, p->d_root_species);
-        smaterialise_kernel<<<grid_for(N, 256), 256, 0, st>>>(
-            ctx->dsp, 0, N, p->d_node_inst, p->d_node_off, p->d_node_pre, p->d_root_species, W, p->d_L, p->d_tau,
-            p->d_taumin, p->d_dec, p->d_anc, p->d_map, p->d_kind, p->d_syn, p->d_node_dag);
-        sbest_kernel<<<grid_for(B, 256), 256, 0, st>>>(B, p->index_base, p->d_min_cost, p->d_root_species,
-                                                       p->d_best);
-        n_launch += 5;
+        // one CTA per resolved tree with everything per (node, root) in shared memory, when it fits;
+        // mappings / syntenies of every instance are then produced on demand (super_materialise)
+        const size_t fused_smem = ((size_t)Gb * W * 32 + Gb) * 4 + (size_t)Gb * S * 4;
+        const char* unfused = getenv("SR2_SUPERDTL_UNFUSED");
+        p->fused = !(unfused && unfused[0] == '1') && S <= 1024 && fused_smem <= ctx->smem_optin;
+        if (p->fused) {
+            SR2_CUDA(ctx, cudaFuncSetAttribute(sfused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)fused_smem));
+            sfused_kernel<<<B, (S + 31) / 32 * 32, fused_smem, st>>>(
+                ctx->dsp, Gb, p->d_left, p->d_right, p->d_node_slot, p->d_node_dag, p->d_node_pre, p->d_tag, W,
+                p->d_gain, p->d_L, cs, p->index_base, p->d_min_cost, p->d_root_species, p->d_best);
+            n_launch += 1;
+            p->materialised = false;
+        } else {
+            int rc = super_decode_shared(ctx, p, &n_launch);
+            if (rc) return rc;
+            sbest_kernel<<<grid_for(B, 256), 256, 0, st>>>(B, p->index_base, p->d_min_cost, p->d_root_species,
+                                                           p->d_best);
+            n_launch += 1;
+        }
     }
     SR2_CUDA(ctx, cudaGetLastError());
     SR2_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
@@ -1188,6 +1362,10 @@ extern "C" int sr2_superdtl_results(sr2_ctx* ctx, int32_t* out_min_cost, int32_t
     if (!p || !p->solved) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_results: solve first");
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
     double t0 = snow_ms();
+    if (!p->materialised && (out_map_species || out_map_kind || out_synteny_bits)) {
+        int rc = super_decode_shared(ctx, p, nullptr);
+        if (rc) return rc;
+    }
     cudaStream_t st = ctx->stream;
     size_t B = p->rows.B, N = p->rows.N;
     if (out_min_cost) SR2_CUDA(ctx, cudaMemcpyAsync(out_min_cost, p->d_min_cost, B * 4, cudaMemcpyDeviceToHost, st));
@@ -1227,6 +1405,10 @@ extern "C" int sr2_superdtl_result_one(sr2_ctx* ctx, int32_t instance, int32_t* 
     if (instance < 0 || instance >= p->rows.B)
         return sr2_fail(ctx, SR2_ERR_ARG, "sr2_superdtl_result_one: bad instance");
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!p->materialised) {
+        int rc = super_decode_shared(ctx, p, nullptr);
+        if (rc) return rc;
+    }
     cudaStream_t st = ctx->stream;
     size_t off = p->rows.node_off[instance], G = p->rows.node_off[instance + 1] - off;
     if (out_map_species)

@@ -210,7 +210,9 @@ def test_shared_rows_equal_unshared_rows(ctx, monkeypatch, shape):
             monkeypatch.setenv("SR2_RESOLUTIONS_UNSHARED", unshared)
             ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits, costs, lo, hi - lo)
             ctx.superdtl_solve()
+            fused = ctx.superdtl_results(costs_only=True)   # straight from the fused decode kernel
             outs.append((ctx.superdtl_results(), ctx.superdtl_best()))
+            assert (fused[0] == outs[-1][0][0]).all() and (fused[1] == outs[-1][0][1]).all()
         (plain, plain_best), (shared, shared_best) = outs
         assert plain_best == shared_best
         for a, b in zip(plain, shared):
