@@ -42,24 +42,31 @@ def main():
     heads = [i for i, r in enumerate(rows) if r and r[0] == "Line No"]
     if not heads:
         return
-    s = heads[0]
-    e = heads[1] if len(heads) > 1 else len(rows)
-    head = rows[s]
-    i_src, i_adr = 1, head.index("Address")
-    i_smp, i_exe = head.index("# Samples"), head.index("Instructions Executed")
-    stall = [(i, n[6:]) for i, n in enumerate(head) if n.startswith("stall_") and "Not Issued" not in n]
     per = []
-    for r in rows[s + 1:e]:
-        if len(r) <= i_exe or not r[0].isdigit() or r[i_adr] != "-":
-            continue  # SASS rows repeat what their source line row aggregates
-        per.append((r[0], r[i_src].strip()[:86], int(r[i_smp] or 0), int(r[i_exe] or 0),
-                    collections.Counter({n: int(r[i] or 0) for i, n in stall})))
+    for n, s in enumerate(heads):   # one section per source file
+        e = heads[n + 1] if n + 1 < len(heads) else len(rows)
+        head = rows[s]
+        if "Address" not in head or "# Samples" not in head:
+            continue
+        fname = ""
+        for back in range(1, 4):
+            if s - back >= 0 and rows[s - back] and rows[s - back][0] in ("File Path", "File Name"):
+                fname = rows[s - back][1].rsplit("/", 1)[-1]
+                break
+        i_src, i_adr = 1, head.index("Address")
+        i_smp, i_exe = head.index("# Samples"), head.index("Instructions Executed")
+        stall = [(i, name[6:]) for i, name in enumerate(head) if name.startswith("stall_") and "Not Issued" not in name]
+        for r in rows[s + 1:e]:
+            if len(r) <= i_exe or not r[0].isdigit() or r[i_adr] != "-":
+                continue  # SASS rows repeat what their source line row aggregates
+            per.append((fname[:14] + ":" + r[0], r[i_src].strip()[:80], int(r[i_smp] or 0), int(r[i_exe] or 0),
+                        collections.Counter({name: int(r[i] or 0) for i, name in stall})))
     total = sum(p[2] for p in per) or 1
     tot_exe = sum(p[3] for p in per) or 1
     print(f"== stall samples by source line (total {total} samples, {tot_exe / 1e6:.1f} M warp instructions)")
     for line, src, smp, exe, st in sorted(per, key=lambda p: -p[2])[:top_n]:
         top = ", ".join(f"{n}={100 * v / max(smp, 1):.0f}%" for n, v in st.most_common(3))
-        print(f"  {100 * smp / total:5.1f}% smp {100 * exe / tot_exe:5.1f}% ins  L{line:>5s} {src:86s} {top}")
+        print(f"  {100 * smp / total:5.1f}% smp {100 * exe / tot_exe:5.1f}% ins  {line:>20s} {src:80s} {top}")
 
 
 if __name__ == "__main__":

@@ -684,26 +684,47 @@ __global__ void sfused_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__
     const int64_t off = (int64_t)b * Gb;
     uint32_t* tau = fused_smem;                       // [Gb * W * 32]
     uint32_t* taumin = tau + (size_t)Gb * W * 32;     // [Gb]
-    uint16_t* dec = reinterpret_cast<uint16_t*>(taumin + Gb);  // [Gb * S]
+    uint32_t* taumask = taumin + Gb;                  // [Gb * W] families ever merged into a set
+    // the tree itself: children (local ids, -1 for leaves), table row, preorder position, clean
+    // lca-set and gain set of every node
+    int32_t* sL = reinterpret_cast<int32_t*>(taumask + (size_t)Gb * W);  // [Gb] left child
+    int32_t* sR = sL + Gb;                            // [Gb] right child
+    int32_t* sSlot = sR + Gb;                         // [Gb]
+    int32_t* sPre = sSlot + Gb;                       // [Gb]
+    uint32_t* sLca = reinterpret_cast<uint32_t*>(sPre + Gb);  // [Gb * W]
+    uint32_t* sGain = sLca + (size_t)Gb * W;          // [Gb * W]
+    uint16_t* dec = reinterpret_cast<uint16_t*>(sGain + (size_t)Gb * W);  // [Gb * S]
     uint16_t* anc = dec + (size_t)Gb * S;             // [Gb * S]
     __shared__ unsigned long long warp_best[32];
     for (int i = threadIdx.x; i < Gb * W * 32 + Gb; i += blockDim.x) tau[i] = 0xffffffffu;
+    for (int u = threadIdx.x; u < Gb; u += blockDim.x) {
+        const int lg = left[off + u];
+        sL[u] = lg < 0 ? -1 : lg - (int)off;
+        sR[u] = lg < 0 ? -1 : right[off + u] - (int)off;
+        sSlot[u] = node_slot[off + u];
+        sPre[u] = node_pre[off + u];
+        const size_t dag = (size_t)node_dag[off + u] * W;
+        for (int w = 0; w < W; ++w) {
+            sLca[u * W + w] = L[dag + w];
+            sGain[u * W + w] = gain[dag + w];
+        }
+    }
     __syncthreads();
     if (k < S) {
-        bool ok = tags[((size_t)node_slot[off] * 2 + 0) * sp.pitch + k] != SR2_NO_TAG;  // kind LCA (:487)
+        bool ok = tags[((size_t)sSlot[0] * 2 + 0) * sp.pitch + k] != SR2_NO_TAG;  // kind LCA (:487)
         dec[k] = ok ? (uint16_t)(k << 1) : (uint16_t)DEC_NONE;
         anc[k] = 0;
+        const int32_t* Slot = sSlot;
         for (int u = 0; u < Gb; ++u) {
-            const int64_t node = off + u;
-            const int lg = left[node];
-            if (lg < 0) continue;
-            const int l = lg - (int)off, r = right[node] - (int)off;
+            const int l = sL[u];
+            if (l < 0) continue;
+            const int r = sR[u];
             unsigned e = dec[u * S + k];
             unsigned el = DEC_NONE, er = DEC_NONE;
             unsigned al = 0, ar = 0;
             if (e != DEC_NONE) {
                 int x = e >> 1, kd = e & 1;
-                unsigned tag = tags[((size_t)node_slot[node] * 2 + kd) * sp.pitch + x];
+                unsigned tag = tags[((size_t)Slot[u] * 2 + kd) * sp.pitch + x];
                 if (tag != SR2_NO_TAG) {
                     el = tag & 0xffffu;
                     er = tag >> 16;
@@ -716,10 +737,10 @@ __global__ void sfused_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__
                         if (!(ec & 1)) continue;
                         int child = side ? r : l;
                         unsigned owner = side ? ar : al;
-                        unsigned stamp = ((unsigned)k << 16) | (unsigned)node_pre[off + child];
+                        unsigned stamp = ((unsigned)k << 16) | (unsigned)sPre[child];
                         bool any = false;
                         for (int w = 0; w < W; ++w) {
-                            uint32_t g = gain[(size_t)node_dag[off + child] * W + w];
+                            uint32_t g = sGain[child * W + w];
                             while (g) {
                                 int f = __ffs(g) - 1;
                                 g &= g - 1;
@@ -738,44 +759,52 @@ __global__ void sfused_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__
         }
     }
     __syncthreads();
+    for (int i = threadIdx.x; i < Gb * W; i += blockDim.x) {
+        uint32_t mask = 0;
+        if (taumin[i / W] != 0xffffffffu)
+            for (int f = 0; f < 32; ++f) mask |= (tau[(size_t)i * 32 + f] != 0xffffffffu ? 1u : 0u) << f;
+        taumask[i] = mask;
+    }
+    __syncthreads();
     u64 key = SR2_KEY_NONE;
     if (k < S && dec[k] != DEC_NONE) {
         int total = 0;
+        const int32_t* Pre = sPre;
+        const unsigned kk = (unsigned)k << 16;
         auto word = [&](int owner, int w, unsigned stamp) {
-            uint32_t bits = L[(size_t)node_dag[off + owner] * W + w];
+            uint32_t bits = sLca[owner * W + w];
             if (taumin[owner] <= stamp) {
                 const uint32_t* t = tau + ((size_t)owner * W + w) * 32;
-                for (int f = 0; f < 32; ++f)
+                uint32_t cand = taumask[owner * W + w] & ~bits;  // only families that were merged at all
+                while (cand) {
+                    int f = __ffs(cand) - 1;
+                    cand &= cand - 1;
                     if (t[f] <= stamp) bits |= 1u << f;
+                }
             }
             return bits;
         };
         for (int u = 0; u < Gb; ++u) {
-            const int lg = left[off + u];
-            if (lg < 0) continue;
-            const int l = lg - (int)off, r = right[off + u] - (int)off;
-            unsigned eu = dec[u * S + k], el = dec[l * S + k], er = dec[r * S + k];
-            int p = eu >> 1, a = el >> 1, c = er >> 1;
-            int dp = __ldg(sp.depth + p), da = __ldg(sp.depth + a), dc = __ldg(sp.depth + c);
-            bool pa = sp_anc(sp, p, a), pc = sp_anc(sp, p, c);
-            int ou = anc[u * S + k], ol = anc[l * S + k], orr = anc[r * S + k];
-            unsigned su = ((unsigned)k << 16) | (unsigned)node_pre[off + u],
-                     sl = ((unsigned)k << 16) | (unsigned)node_pre[off + l],
-                     sr = ((unsigned)k << 16) | (unsigned)node_pre[off + r];
+            const int l = sL[u];
+            if (l < 0) continue;
+            const int r = sR[u];
+            const unsigned eu = dec[u * S + k], el = dec[l * S + k], er = dec[r * S + k];
+            const int p = eu >> 1, a = el >> 1, c = er >> 1;
+            // (tin, tout, (child0 + 1) << 16 | depth, tin of the second child) of the three species
+            const uint4 gp = __ldg(sp.span4 + p), ga = __ldg(sp.span4 + a), gc = __ldg(sp.span4 + c);
+            const int dp = (int)(gp.z & 0xffffu), da = (int)(ga.z & 0xffffu), dc = (int)(gc.z & 0xffffu);
+            const bool pa = gp.x <= ga.x && ga.x < gp.y, pc = gp.x <= gc.x && gc.x < gp.y;
+            const int ou = anc[u * S + k], ol = anc[l * S + k], orr = anc[r * S + k];
             bool in_l = true, in_r = true;
             for (int w = 0; w < W; ++w) {
-                uint32_t mine = word(ou, w, su);
-                in_l &= (mine & ~word(ol, w, sl)) == 0;
-                in_r &= (mine & ~word(orr, w, sr)) == 0;
+                uint32_t mine = word(ou, w, kk | (unsigned)Pre[u]);
+                in_l &= (mine & ~word(ol, w, kk | (unsigned)Pre[l])) == 0;
+                in_r &= (mine & ~word(orr, w, kk | (unsigned)Pre[r])) == 0;
             }
-            int lc = in_l ? 0 : cs.sloss, rc = in_r ? 0 : cs.sloss;
+            const int lc = in_l ? 0 : cs.sloss, rc = in_r ? 0 : cs.sloss;
             if (pa && pc) {
-                int cx = __ldg(sp.child0 + p);
-                bool spec = false;
-                if (cx >= 0 && a != p && c != p) {
-                    int t1 = __ldg(sp.tin + cx + 1);
-                    spec = (__ldg(sp.tin + a) < t1) != (__ldg(sp.tin + c) < t1);
-                }
+                // speciation iff a and c sit below different children of p
+                const bool spec = (gp.z >> 16) != 0 && a != p && c != p && ((ga.x < gp.w) != (gc.x < gp.w));
                 if (spec)
                     total += cs.spe + cs.floss * (da + dc - 2 * dp - 2) + lc + rc;
                 else
@@ -783,7 +812,8 @@ __global__ void sfused_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__
             } else if (pa) {
                 total += cs.hgt + cs.floss * (da - dp) + lc;
             } else {
-                total += cs.hgt + cs.floss * (dc - dp) + (sp_anc(sp, a, p) ? lc : rc);
+                const bool a_above_p = ga.x <= gp.x && gp.x < ga.y;
+                total += cs.hgt + cs.floss * (dc - dp) + (a_above_p ? lc : rc);
             }
         }
         key = ((u64)(unsigned)total << 32) | (unsigned)k;
@@ -1216,7 +1246,7 @@ static int super_solve_shared(sr2_ctx* ctx, SuperProblem* p) {
     if (B > 0) {
         // one CTA per resolved tree with everything per (node, root) in shared memory, when it fits;
         // mappings / syntenies of every instance are then produced on demand (super_materialise)
-        const size_t fused_smem = ((size_t)Gb * W * 32 + Gb) * 4 + (size_t)Gb * S * 4;
+        const size_t fused_smem = ((size_t)Gb * W * 35 + Gb * 5) * 4 + (size_t)Gb * S * 4;
         const char* unfused = getenv("SR2_SUPERDTL_UNFUSED");
         p->fused = !(unfused && unfused[0] == '1') && S <= 1024 && fused_smem <= ctx->smem_optin;
         if (p->fused) {
