@@ -278,8 +278,11 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
     std::vector<int32_t> sched2(std::max<size_t>(sched.size(), 32 * 32));  // padded to 32 steps with idle words
     for (size_t i = 0; i < sched2.size(); ++i) {
         uint32_t w = i < sched.size() ? (uint32_t)sched[i] : 0xffffffffu;
-        uint32_t p_idx = w == 0xffffffffu ? (uint32_t)ctx->pitch + 6 : (w & 0xffffu) + 1;
-        uint32_t c_idx = w == 0xffffffffu ? (uint32_t)ctx->pitch + 4 : (w >> 16) + 1;
+        if (w == 0xffffffffu) {
+            sched2[i] = 0;  // idle lane
+            continue;
+        }
+        uint32_t p_idx = (w & 0xffffu) + 1, c_idx = (w >> 16) + 1;
         sched2[i] = (int32_t)((c_idx * 8) << 16 | (p_idx * 8));
     }
     size_t total = (size_t)S * 7 + (n_int ? n_int : 1) + (size_t)ctx->D + 1 + std::max<size_t>(sched.size(), 32) + sched2.size() +

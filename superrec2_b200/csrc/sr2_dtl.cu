@@ -73,6 +73,7 @@ struct DtlProblem {
     size_t flat_smem = 0;
     bool flat2 = false;          // the default batched kernel when its preconditions hold
     size_t flat2_smem = 0;
+    int flat2_rows = 8;
     int flat2_sh = 0, flat2_thresh = 0;
     void (*flat2_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
                      Key32) = nullptr;
@@ -787,7 +788,7 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int pitch = sp.pitch, rs = sp.flat_rs, n_chunks = pitch >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int local = blockIdx.x * 8 + warp;
+    const int local = blockIdx.x * (blockDim.x >> 5) + warp;
     if (local >= n_rows) return;
     const int64_t gr = row_begin + local;
     const size_t slot = (size_t)(gr - chunk_row0);
@@ -813,7 +814,10 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     // (the table is padded to NS steps with idle words)
     unsigned sw[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) sw[i] = __ldg(sp.flat_sched + i * 32 + lane) + Mb * 0x10001u;
+    for (int i = 0; i < NS; ++i) {
+        const unsigned w = __ldg(sp.flat_sched + i * 32 + lane);
+        sw[i] = w ? w + Mb * 0x10001u : 0u;  // 0 = this lane idles in step i
+    }
     // per-species words of the cells this lane will evaluate
     unsigned meta[FLAT2_NCH];
 #pragma unroll
@@ -833,20 +837,26 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     // ---- up-sweep: SUBMIN in place, deepest level first ------------------------------------------
 #pragma unroll
     for (int i = NS - 1; i >= 0; --i) {
-        const unsigned pa = sw[i] & 0xffffu, ca = sw[i] >> 16;
-        const uint4 k = lds128(ca);
-        const uint2 own = lds64(pa);
-        sts64(pa, min(own.x, min(k.x, k.z)), min(own.y, min(k.y, k.w)));
+        // idle lanes stay out of the shared-memory pipe (the kernel's busiest unit): a level of w
+        // species costs ceil(w / 8) wavefronts for the child pairs instead of 4
+        if (sw[i]) {
+            const unsigned pa = sw[i] & 0xffffu, ca = sw[i] >> 16;
+            const uint4 k = lds128(ca);
+            const uint2 own = lds64(pa);
+            sts64(pa, min(own.x, min(k.x, k.z)), min(own.y, min(k.y, k.w)));
+        }
         __syncwarp();
     }
     // ---- top-down sweep: SEPMIN into P ------------------------------------------------------------
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-        const unsigned pa = sw[i] & 0xffffu, ca = sw[i] >> 16;
-        const uint4 k = lds128(ca);
-        const uint2 pp = lds64(pa + pofs);
-        // incomparable(c) = incomparable(p) + subtree(c+1), and the other way round
-        sts128(ca + pofs, min(pp.x, k.z), min(pp.y, k.w), min(pp.x, k.x), min(pp.y, k.y));
+        if (sw[i]) {
+            const unsigned pa = sw[i] & 0xffffu, ca = sw[i] >> 16;
+            const uint4 k = lds128(ca);
+            const uint2 pp = lds64(pa + pofs);
+            // incomparable(c) = incomparable(p) + subtree(c+1), and the other way round
+            sts128(ca + pofs, min(pp.x, k.z), min(pp.y, k.w), min(pp.x, k.x), min(pp.y, k.y));
+        }
         __syncwarp();
     }
 
@@ -1224,7 +1234,9 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
         int64_t inf = vb >= 2 ? (int64_t)1 << (vb - 1) : 0;
         p->flat2_sh = 32 - vb;
         p->flat2_thresh = (int)(inf - slack);
-        p->flat2_smem = (size_t)8 * 2 * ctx->dsp.flat_rs * sizeof(uint2);
+        p->flat2_rows = 8;  // rows (warps) per CTA
+        if (const char* rpc = getenv("SR2_FLAT2_ROWS")) p->flat2_rows = std::max(1, std::min(8, atoi(rpc)));
+        p->flat2_smem = (size_t)p->flat2_rows * 2 * ctx->dsp.flat_rs * sizeof(uint2);
         p->flat2 = (!v || strcmp(v, "flat2") == 0) && !(off && off[0] == '1') && S >= 2 && vb >= 8 &&
                    p->max_finite + slack < inf - slack && ctx->dsp.flat_rs > 0 && ctx->dsp.n_steps <= FLAT2_NS && ctx->pitch <= 32 * FLAT2_NCH &&
                    p->flat2_smem <= std::min<size_t>(ctx->smem_optin, 65535);
@@ -1271,7 +1283,8 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         kp.dm = (1u << p->depth_bits) - 1;
         kp.inf32 = 1u << (32 - kp.sh - 1);
         kp.thresh = p->flat2_thresh;
-        p->flat2_fn<<<(unsigned)((n_rows + 7) / 8), 256, p->flat2_smem, p->cur_stream>>>(
+        p->flat2_fn<<<(unsigned)((n_rows + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem,
+                      p->cur_stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
