@@ -255,9 +255,7 @@ dtl_cherry_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32
     const int a = -1 - row_cl[gr], b = -1 - row_cr[gr];
     const int ta = __ldg(sp.tin + a), oa = __ldg(sp.tout + a), da = __ldg(sp.depth + a);
     const int tb = __ldg(sp.tin + b), ob = __ldg(sp.tout + b), db = __ldg(sp.depth + b);
-    const unsigned tag_ab = (unsigned)a | ((unsigned)b << 16);
     int32_t* __restrict__ Tout = T + slot * sp.pitch;
-    uint32_t* __restrict__ Gout = tags + slot * sp.pitch;
     for (int x = lane; x < sp.S; x += 32) {
         const uint4 sx = __ldg(sp.span4 + x);
         const int tx = (int)sx.x, ox = (int)sx.y, dx = (int)(sx.z & 0xffffu), t1 = (int)sx.w;
@@ -281,7 +279,8 @@ dtl_cherry_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32
             if (v < best) best = v;
         }
         Tout[x] = best;
-        Gout[x] = best < SR2_INF ? tag_ab : SR2_NO_TAG;
+        // no tag row: every finite cell of a cherry has the tag (a, b), which its readers rebuild
+        // from the child descriptors (dtl_traceback_kernel, dtl_decoded_cost_kernel, sr2_dtl_tables)
     }
 }
 
@@ -947,15 +946,18 @@ __global__ void __launch_bounds__(256)
 dtl_decoded_cost_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
                         const int32_t* __restrict__ row_cr, int64_t row_begin, int64_t chunk_row0,
                         int n_rows, const uint32_t* __restrict__ tags, int32_t* __restrict__ C,
-                        DtlCosts cs) {
+                        DtlCosts cs, const int32_t* __restrict__ T) {
     int local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (local >= n_rows) return;
     const int64_t gr = row_begin + local;
     const size_t slot = (size_t)(gr - chunk_row0);
     const int cl = row_cl[gr], cr = row_cr[gr];
+    const bool cherry = cl < 0 && cr < 0;  // height-1 rows store no tags
     for (int x = lane; x < sp.S; x += 32) {
-        unsigned tag = tags[slot * sp.pitch + x];
+        unsigned tag = cherry ? (T[slot * sp.pitch + x] < SR2_INF ? (unsigned)(-1 - cl) | ((unsigned)(-1 - cr) << 16)
+                                                                   : SR2_NO_TAG)
+                              : tags[slot * sp.pitch + x];
         int out = SR2_INF;
         if (tag != SR2_NO_TAG) {
             int a = tag & 0xffffu, b = tag >> 16;
@@ -1015,18 +1017,27 @@ __global__ void __launch_bounds__(256)
 dtl_traceback_kernel(DevSpecies sp, const int32_t* __restrict__ row_node,
                      const int32_t* __restrict__ row_left, const int32_t* __restrict__ row_right,
                      int64_t row_begin, int64_t chunk_row0, int n_rows,
-                     const uint32_t* __restrict__ tags, int32_t* __restrict__ map) {
+                     const uint32_t* __restrict__ tags, int32_t* __restrict__ map,
+                     const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                     const int32_t* __restrict__ T) {
     int local = blockIdx.x * blockDim.x + threadIdx.x;
     if (local >= n_rows) return;
     int64_t gr = row_begin + local;
     size_t slot = (size_t)(gr - chunk_row0);
     int x = map[row_node[gr]];
     int a = -1, b = -1;
+    const int cl = row_cl[gr], cr = row_cr[gr];
     if (x >= 0) {
-        unsigned tag = tags[slot * sp.pitch + x];
-        if (tag != SR2_NO_TAG) {
-            a = tag & 0xffffu;
-            b = tag >> 16;
+        if (cl < 0 && cr < 0) {
+            // a cherry stores no tags: its parent only ever points at a finite cell, whose tag is
+            // the two leaf species
+            if (T[slot * sp.pitch + x] < SR2_INF) a = -1 - cl, b = -1 - cr;
+        } else {
+            unsigned tag = tags[slot * sp.pitch + x];
+            if (tag != SR2_NO_TAG) {
+                a = tag & 0xffffu;
+                b = tag >> 16;
+            }
         }
     }
     map[row_left[gr]] = a;
@@ -1376,7 +1387,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
             int64_t n = c.wave_off[h + 1] - c.wave_off[h];
             if (n <= 0) continue;
             dtl_decoded_cost_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(
-                ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_tag, p->cur_C, cs);
+                ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_tag, p->cur_C, cs, p->cur_T);
             ++p->n_launch;
         }
     }
@@ -1392,7 +1403,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         if (n <= 0) continue;
         dtl_traceback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
             ctx->dsp, p->rows.row_node, p->rows.row_left, p->rows.row_right, c.wave_off[h], c.row_begin, (int)n,
-            p->cur_tag, p->d_map);
+            p->cur_tag, p->d_map, p->rows.row_cl, p->rows.row_cr, p->cur_T);
         ++p->n_launch;
     }
     SR2_CUDA(ctx, cudaGetLastError());
@@ -1648,6 +1659,12 @@ extern "C" int sr2_dtl_tables(sr2_ctx* ctx, int32_t instance, int32_t* out_value
         }
         SR2_CUDA(ctx, cudaMemcpy(rowT.data(), p->d_T + (size_t)gr * pitch, (size_t)pitch * 4, cudaMemcpyDeviceToHost));
         SR2_CUDA(ctx, cudaMemcpy(rowG.data(), p->d_tag + (size_t)gr * pitch, (size_t)pitch * 4, cudaMemcpyDeviceToHost));
+        int32_t desc[2];
+        SR2_CUDA(ctx, cudaMemcpy(&desc[0], p->rows.row_cl + gr, 4, cudaMemcpyDeviceToHost));
+        SR2_CUDA(ctx, cudaMemcpy(&desc[1], p->rows.row_cr + gr, 4, cudaMemcpyDeviceToHost));
+        if (desc[0] < 0 && desc[1] < 0)  // a cherry stores no tags (dtl_cherry_kernel)
+            for (int x = 0; x < S; ++x)
+                rowG[x] = rowT[x] < SR2_INF ? (uint32_t)(-1 - desc[0]) | ((uint32_t)(-1 - desc[1]) << 16) : SR2_NO_TAG;
         for (int x = 0; x < S; ++x) {
             if (ov) ov[x] = rowT[x];
             if (ot) {
