@@ -154,6 +154,7 @@ extern "C" void sr2_destroy(sr2_ctx* ctx) {
     for (auto& pool : ctx->host) free(pool.ptr);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
+    if (ctx->d_anc_tab) cudaFree(ctx->d_anc_tab);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -347,6 +348,26 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
         ctx->dsp.span4 = (const uint4*)put(span, 4 * (size_t)S);
     }
     SR2_CUDA(ctx, cudaMemcpyAsync(d, h, total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    // ancestor table for the sparse cherry kernel
+    if (ctx->d_anc_tab) {
+        cudaFree(ctx->d_anc_tab);
+        ctx->d_anc_tab = nullptr;
+    }
+    ctx->dsp.anc_tab = nullptr;
+    ctx->dsp.anc_pitch = (ctx->D + 1) & ~1;
+    std::vector<uint16_t> anc;
+    if ((size_t)S * ctx->dsp.anc_pitch <= ((size_t)1 << 23)) {
+        anc.assign((size_t)S * ctx->dsp.anc_pitch, 0);
+        for (int y = 0; y < S; ++y) {
+            uint16_t* row = anc.data() + (size_t)y * ctx->dsp.anc_pitch;
+            if (y > 0) memcpy(row, anc.data() + (size_t)parent[y] * ctx->dsp.anc_pitch, sizeof(uint16_t) * ctx->h_depth[y]);
+            row[ctx->h_depth[y]] = (uint16_t)y;
+        }
+        SR2_CUDA(ctx, cudaMalloc(&ctx->d_anc_tab, anc.size() * sizeof(uint16_t)));
+        SR2_CUDA(ctx, cudaMemcpyAsync(ctx->d_anc_tab, anc.data(), anc.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
+                                      ctx->stream));
+        ctx->dsp.anc_tab = ctx->d_anc_tab;
+    }
     SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SR2_OK;
 }

@@ -284,6 +284,52 @@ dtl_cherry_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32
     }
 }
 
+// Wave 1, sparse form.  A cherry's row is infinite except on the two root paths of its leaf
+// species a and b (at most 2 x depth cells of |S|):
+//   x above both (depth d <= depth of lca(a, b)):  duplication  dup + loss (da + db - 2d),
+//                                                   at the lca itself (a != b) the speciation
+//                                                   loss (da + db - 2d - 2), offered first
+//   x above a only:  right child transferred        hgt + loss (da - d)
+//   x above b only:  left child transferred         hgt + loss (db - d)
+// (the same values as dtl_cherry_kernel's interval tests, which are kept for species trees whose
+// ancestor table would be too large).  One warp per row: 128-bit stores of the infinite row, then
+// the path cells from the ancestor table.  HBM-write-bound instead of ALU-bound.
+__global__ void __launch_bounds__(256)
+dtl_cherry_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                         int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T, DtlCosts cs) {
+    int local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int lane = threadIdx.x & 31;
+    if (local >= n_rows) return;
+    const int64_t gr = row_begin + local;
+    const size_t slot = (size_t)(gr - chunk_row0);
+    const int a = -1 - row_cl[gr], b = -1 - row_cr[gr];
+    const int da = __ldg(sp.depth + a), db = __ldg(sp.depth + b);
+    int32_t* __restrict__ Tout = T + slot * sp.pitch;
+    uint4* __restrict__ row4 = reinterpret_cast<uint4*>(Tout);
+    const uint4 inf4 = make_uint4(SR2_INF, SR2_INF, SR2_INF, SR2_INF);
+    for (int i = lane; i < (sp.pitch >> 2); i += 32) row4[i] = inf4;
+    const uint16_t* __restrict__ pa = sp.anc_tab + (size_t)a * sp.anc_pitch;
+    const uint16_t* __restrict__ pb = sp.anc_tab + (size_t)b * sp.anc_pitch;
+    // depths at which the two root paths coincide: 0 .. common - 1
+    int common = 0;
+    const int dmin = min(da, db);
+    for (int d0 = 0; d0 <= dmin; d0 += 32) {
+        const int d = d0 + lane;
+        const bool eq = d <= dmin && pa[d] == pb[d];
+        common += __popc(__ballot_sync(0xffffffffu, eq));
+    }
+    __syncwarp();  // the infinite row is written before its finite cells
+    for (int d = lane; d <= da; d += 32) {
+        int v;
+        if (d < common)
+            v = (d == common - 1 && a != b) ? cs.loss * (da + db - 2 * d - 2) : cs.dup + cs.loss * (da + db - 2 * d);
+        else
+            v = cs.hgt + cs.loss * (da - d);
+        Tout[pa[d]] = v;
+    }
+    for (int d = common + lane; d <= db; d += 32) Tout[pb[d]] = cs.hgt + cs.loss * (db - d);
+}
+
 // ---------------------------------------------------------------------------
 // Batched waves: SIMD across rows.  A CTA owns 16 rows of the wave; lane = (row j,
 // half h).  All lanes of a warp work on the SAME species node (two sibling cells, or the
@@ -1280,6 +1326,12 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
 static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h, int64_t row_begin,
                            int64_t n_rows, const DtlCosts& cs) {
     if (n_rows <= 0) return SR2_OK;
+    if (h == 1 && ctx->dsp.anc_tab && !getenv("SR2_DTL_DENSE_CHERRIES")) {
+        dtl_cherry_sparse_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, p->cur_stream>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, cs);
+        SR2_CUDA(ctx, cudaGetLastError());
+        return SR2_OK;
+    }
     if (h == 1) {  // both children of a height-1 node are leaves
         dtl_cherry_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, p->cur_stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs);

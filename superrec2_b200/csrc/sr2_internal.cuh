@@ -58,6 +58,10 @@ struct DevSpecies {
     // [S] x 4 words: tin, tout, (child0 + 1) << 16 | depth, tin of the second child (or tout):
     // everything the closed-form cherry cells need about a species in one 16-byte load
     const uint4* span4;
+    // anc_tab[s * anc_pitch + d] = ancestor of species s at depth d (d <= depth[s]); null when the
+    // table would be too large (S x D > 2^23 entries)
+    const uint16_t* anc_tab;
+    int anc_pitch;
 };
 
 struct DtlProblem;
@@ -131,6 +135,7 @@ struct sr2_ctx {
     int S = 0, pitch = 0, D = 0, n_internal = 0;
     std::vector<int32_t> h_parent, h_child0, h_depth, h_tin, h_tout, h_int_list, h_int_lvl_off;
     int32_t* d_species_slab = nullptr;
+    uint16_t* d_anc_tab = nullptr;
     DevSpecies dsp{};
 
     Sr2Pool dev[DP_COUNT], pin[HP_COUNT], host[MP_COUNT];

@@ -203,6 +203,12 @@ def test_kernel_variants_agree_on_a_large_batch(ctx, monkeypatch):
     simd = ctx.dtl_run(*args)
     for a, b in zip(plain, simd):
         assert (a == b).all()
+    # wave 1: the sparse cherry kernel (root paths from the ancestor table, default) against the
+    # dense closed-form kernel
+    monkeypatch.setenv("SR2_DTL_DENSE_CHERRIES", "1")
+    dense = ctx.dtl_run(*args)
+    for a, b in zip(simd, dense):
+        assert (a == b).all()
     from tests.helpers import flat_cost
     for b in (0, 299, 599):
         assert flat_cost(batch, b, simd[2]) == simd[0][b]
