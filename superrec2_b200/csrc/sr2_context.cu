@@ -287,7 +287,7 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
         sched2[i] = (int32_t)((c_idx * 8) << 16 | (p_idx * 8));
     }
     size_t total = (size_t)S * 7 + (n_int ? n_int : 1) + (size_t)ctx->D + 1 + std::max<size_t>(sched.size(), 32) + sched2.size() +
-                   (size_t)S * 4 + 2 * (size_t)ctx->pitch + 16;
+                   (size_t)S * 4 + 2 * (size_t)ctx->pitch + 16 + (size_t)S * (ctx->pitch / 32);
     SR2_CUDA(ctx, cudaMalloc(&ctx->d_species_slab, total * sizeof(int32_t)));
     std::vector<int32_t> slab(total, 0);
     int32_t* h = slab.data();
@@ -337,6 +337,17 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
         }
         ctx->dsp.keylow_p = (const uint32_t*)put(keylow_p, ctx->pitch);
         ctx->dsp.cmeta = (const uint32_t*)put(cmeta, ctx->pitch);
+        {
+            const int mw = ctx->pitch / 32;
+            std::vector<int32_t> pathmask((size_t)S * mw, 0);
+            for (int y = 0; y < S; ++y) {
+                int32_t* row = pathmask.data() + (size_t)y * mw;
+                if (y > 0) memcpy(row, pathmask.data() + (size_t)parent[y] * mw, sizeof(int32_t) * mw);
+                row[y >> 5] |= (int32_t)(1u << (y & 31));
+            }
+            ctx->dsp.mask_words = mw;
+            ctx->dsp.pathmask = (const uint32_t*)put(pathmask, pathmask.size());
+        }
         off = (off + 3) / 4 * 4;  // 16-byte alignment (the slab itself is 256-byte aligned)
         std::vector<int32_t> span(4 * (size_t)S);
         for (int y = 0; y < S; ++y) {

@@ -53,6 +53,8 @@ struct DtlProblem {
     int32_t* cur_T = nullptr;
     uint32_t* cur_tag = nullptr;
     int32_t* cur_C = nullptr;
+    uint32_t* d_mask = nullptr;      // [rows * pitch/32] root-path bit sets of the rows (flat2 only)
+    uint32_t* cur_mask = nullptr;
     std::vector<cudaEvent_t> ev_w0, ev_w1, ev_done;  // per chunk: waves begin / end, chunk finished
     int n_waves = 0, n_launch = 0;
     // wave launch configuration (fixed per upload)
@@ -76,7 +78,9 @@ struct DtlProblem {
     int flat2_rows = 8;
     int flat2_sh = 0, flat2_thresh = 0;
     void (*flat2_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
-                     Key32) = nullptr;
+                     Key32, uint32_t*, int, int, int) = nullptr;
+    int flat2_pf_near = 0, flat2_pf_far = 0;
+    int flat2_sparse_max = 0;        // rows with at most this many root-path species take the sparse cells path
 };
 
 void sr2_free_dtl(sr2_ctx* ctx) {
@@ -246,7 +250,7 @@ dtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
 __global__ void __launch_bounds__(256)
 dtl_cherry_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                   int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
-                  uint32_t* __restrict__ tags, DtlCosts cs) {
+                  uint32_t* __restrict__ tags, DtlCosts cs, uint32_t* __restrict__ rowmask) {
     int local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (local >= n_rows) return;
@@ -256,6 +260,9 @@ dtl_cherry_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32
     const int ta = __ldg(sp.tin + a), oa = __ldg(sp.tout + a), da = __ldg(sp.depth + a);
     const int tb = __ldg(sp.tin + b), ob = __ldg(sp.tout + b), db = __ldg(sp.depth + b);
     int32_t* __restrict__ Tout = T + slot * sp.pitch;
+    if (rowmask && lane < sp.mask_words)
+        rowmask[slot * sp.mask_words + lane] = __ldg(sp.pathmask + (size_t)a * sp.mask_words + lane) |
+                                               __ldg(sp.pathmask + (size_t)b * sp.mask_words + lane);
     for (int x = lane; x < sp.S; x += 32) {
         const uint4 sx = __ldg(sp.span4 + x);
         const int tx = (int)sx.x, ox = (int)sx.y, dx = (int)(sx.z & 0xffffu), t1 = (int)sx.w;
@@ -296,7 +303,8 @@ dtl_cherry_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32
 // the path cells from the ancestor table.  HBM-write-bound instead of ALU-bound.
 __global__ void __launch_bounds__(256)
 dtl_cherry_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
-                         int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T, DtlCosts cs) {
+                         int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T, DtlCosts cs,
+                         uint32_t* __restrict__ rowmask) {
     int local = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int lane = threadIdx.x & 31;
     if (local >= n_rows) return;
@@ -308,6 +316,9 @@ dtl_cherry_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, cons
     uint4* __restrict__ row4 = reinterpret_cast<uint4*>(Tout);
     const uint4 inf4 = make_uint4(SR2_INF, SR2_INF, SR2_INF, SR2_INF);
     for (int i = lane; i < (sp.pitch >> 2); i += 32) row4[i] = inf4;
+    if (rowmask && lane < sp.mask_words)
+        rowmask[slot * sp.mask_words + lane] = __ldg(sp.pathmask + (size_t)a * sp.mask_words + lane) |
+                                               __ldg(sp.pathmask + (size_t)b * sp.mask_words + lane);
     const uint16_t* __restrict__ pa = sp.anc_tab + (size_t)a * sp.anc_pitch;
     const uint16_t* __restrict__ pb = sp.anc_tab + (size_t)b * sp.anc_pitch;
     // depths at which the two root paths coincide: 0 .. common - 1
@@ -829,7 +840,8 @@ template <int NS>
 __global__ void __launch_bounds__(256, 4)
 dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                       int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
-                      uint32_t* __restrict__ tags, DtlCosts cs, Key32 kp) {
+                      uint32_t* __restrict__ tags, DtlCosts cs, Key32 kp, uint32_t* __restrict__ rowmask,
+                      int sparse_max, int pf_near, int pf_far) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int pitch = sp.pitch, rs = sp.flat_rs, n_chunks = pitch >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -855,6 +867,26 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
         else if (cr >= 0) flat2_load<false, true>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
         else flat2_load<false, false>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
     }
+    // The kernel is latency-bound (two dependent DRAM trips per row: descriptors, then child rows).
+    // Pull the descriptors of a row far ahead into L2, and read those of a nearer row (prefetched by
+    // an earlier CTA) to pull ITS child rows into L2; the prefetches are issued before the sweeps.
+    int cl2 = -1, cr2 = -1;
+    if (pf_far > 0 && local + pf_far < n_rows && lane < 2)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((lane ? row_cr : row_cl) + gr + pf_far));
+    if (pf_near > 0 && local + pf_near < n_rows) {
+        cl2 = row_cl[gr + pf_near];
+        cr2 = row_cr[gr + pf_near];
+    }
+    // the row's root-path bit set: one 32-species word per lane (lanes >= pitch / 32 hold 0)
+    unsigned mword = 0;
+    if (lane < n_chunks) {
+        const unsigned ml = cl >= 0 ? rowmask[(size_t)cl * n_chunks + lane]
+                                    : __ldg(sp.pathmask + (size_t)(-1 - cl) * n_chunks + lane);
+        const unsigned mr = cr >= 0 ? rowmask[(size_t)cr * n_chunks + lane]
+                                    : __ldg(sp.pathmask + (size_t)(-1 - cr) * n_chunks + lane);
+        mword = ml | mr;
+        rowmask[slot * n_chunks + lane] = mword;
+    }
     // sweep schedule -> registers, as absolute shared-memory addresses of this warp's row
     // (the table is padded to NS steps with idle words)
     unsigned sw[NS];
@@ -879,6 +911,10 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     }
     __syncwarp();
 
+    if (lane * 32 < pitch) {  // one 128-byte line per lane
+        if (cl2 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cl2 * pitch + lane * 32));
+        if (cr2 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cr2 * pitch + lane * 32));
+    }
     // ---- up-sweep: SUBMIN in place, deepest level first ------------------------------------------
 #pragma unroll
     for (int i = NS - 1; i >= 0; --i) {
@@ -905,50 +941,94 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
         __syncwarp();
     }
 
-    // ---- cells: element-wise over the pitch ----------------------------------------------------------
-    int32_t* __restrict__ Tout = T + slot * pitch + lane;
-    uint32_t* __restrict__ Gout = tags + slot * pitch + lane;
+    // ---- cells ---------------------------------------------------------------------------------------
+    int32_t* __restrict__ Trow = T + slot * pitch;
+    uint32_t* __restrict__ Grow = tags + slot * pitch;
     const unsigned char* Mbytes = reinterpret_cast<const unsigned char*>(Mrow);
-    const uint2* Mx = M + lane;
-    const uint2* Px = P + lane;
     const int loss = cs.loss, db = kp.db, thresh = kp.thresh;
     const unsigned dm = kp.dm, rm = kp.rm, hi_mul = 1u << (32 - kp.sh);
     const int c12 = -2 * loss, c3 = cs.dup, c45 = cs.hgt;
+    // one cell: species x, its word (child pair offset << 16 | depth); writes value and tag
+    auto cell = [&](int x, unsigned mx) {
+        const uint2 m = M[x], pq = P[x];
+        const uint4 k = *reinterpret_cast<const uint4*>(Mbytes + (mx >> 16));  // (l0, r0, l1, r1)
+        const int nld = -loss * (int)(mx & 0xffffu);
+        const int qMl = flat2_q(m.x, hi_mul, dm, loss), qMr = flat2_q(m.y, hi_mul, dm, loss);
+        const int ql0 = flat2_q(k.x, hi_mul, dm, loss), qr0 = flat2_q(k.y, hi_mul, dm, loss);
+        const int ql1 = flat2_q(k.z, hi_mul, dm, loss), qr1 = flat2_q(k.w, hi_mul, dm, loss);
+        const int pl = (int)__umulhi(pq.x, hi_mul), pr = (int)__umulhi(pq.y, hi_mul);
+        const int b12 = 2 * nld + c12, b3 = 2 * nld + c3, b45 = nld + c45;
+        const int w1 = flat2_pack(ql0 + qr1 + b12, 0);  // 1. speciation, left below x0, right below x1
+        const int w2 = flat2_pack(ql1 + qr0 + b12, 1);  // 2. the other way round
+        const int w3 = flat2_pack(qMl + qMr + b3, 2);   // 3. duplication
+        const int w4 = flat2_pack(pl + qMr + b45, 3);   // 4. transfer, left child away
+        const int w5 = flat2_pack(qMl + pr + b45, 4);   // 5. transfer, right child away
+        const int w = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
+        const int best = w >> 3, which = w & 7;
+        unsigned ka = m.x, kb = m.y;
+        ka = which == 0 ? k.x : ka;
+        ka = which == 1 ? k.z : ka;
+        ka = which == 3 ? pq.x : ka;
+        kb = which == 0 ? k.w : kb;
+        kb = which == 1 ? k.y : kb;
+        kb = which == 4 ? pq.y : kb;
+        const bool finite = best < thresh;
+        Trow[x] = finite ? best : SR2_INF;
+        Grow[x] = finite ? (((ka >> db) & rm) | (((kb >> db) & rm) << 16)) : SR2_NO_TAG;
+    };
+    // A cell can only be finite on the root path of a leaf species below the object node.  Rows whose
+    // path set is small (most rows: low in the object trees) write the infinite row with 128-bit
+    // stores and evaluate the cells of the set only, ceil(m / 32) passes instead of pitch / 32; cells
+    // outside the set get no tag (readers look at the value first).
+    const int cnt = __popc(mword);
+    int incl = cnt;
 #pragma unroll
-    for (int j = 0; j < FLAT2_NCH; ++j) {
-        if (j < n_chunks) {
-            const uint2 m = Mx[j * 32], pq = Px[j * 32];
-            const uint4 k = *reinterpret_cast<const uint4*>(Mbytes + (meta[j] >> 16));  // (l0, r0, l1, r1)
-            const int nld = -loss * (int)(meta[j] & 0xffffu);
-            const int qMl = flat2_q(m.x, hi_mul, dm, loss), qMr = flat2_q(m.y, hi_mul, dm, loss);
-            const int ql0 = flat2_q(k.x, hi_mul, dm, loss), qr0 = flat2_q(k.y, hi_mul, dm, loss);
-            const int ql1 = flat2_q(k.z, hi_mul, dm, loss), qr1 = flat2_q(k.w, hi_mul, dm, loss);
-            const int pl = (int)__umulhi(pq.x, hi_mul), pr = (int)__umulhi(pq.y, hi_mul);
-            const int b12 = 2 * nld + c12, b3 = 2 * nld + c3, b45 = nld + c45;
-            const int w1 = flat2_pack(ql0 + qr1 + b12, 0);  // 1. speciation, left below x0, right below x1
-            const int w2 = flat2_pack(ql1 + qr0 + b12, 1);  // 2. the other way round
-            const int w3 = flat2_pack(qMl + qMr + b3, 2);   // 3. duplication
-            const int w4 = flat2_pack(pl + qMr + b45, 3);   // 4. transfer, left child away
-            const int w5 = flat2_pack(qMl + pr + b45, 4);   // 5. transfer, right child away
-            const int w = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
-            const int best = w >> 3, which = w & 7;
-            unsigned ka = m.x, kb = m.y;
-            ka = which == 0 ? k.x : ka;
-            ka = which == 1 ? k.z : ka;
-            ka = which == 3 ? pq.x : ka;
-            kb = which == 0 ? k.w : kb;
-            kb = which == 1 ? k.y : kb;
-            kb = which == 4 ? pq.y : kb;
-            const bool finite = best < thresh;
-            Tout[j * 32] = finite ? best : SR2_INF;
-            Gout[j * 32] = finite ? (((ka >> db) & rm) | (((kb >> db) & rm) << 16)) : SR2_NO_TAG;
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
     }
+    const int m_set = __shfl_sync(0xffffffffu, incl, 31);
+    if (m_set <= sparse_max) {
+        uint4* __restrict__ row4 = reinterpret_cast<uint4*>(Trow);
+        const uint4 inf4 = make_uint4(SR2_INF, SR2_INF, SR2_INF, SR2_INF);
+        for (int i = lane; i < (pitch >> 2); i += 32) row4[i] = inf4;
+        __syncwarp();
+        const int excl = incl - cnt;
+        for (int i0 = 0; i0 < m_set; i0 += 32) {
+            const int i = min(i0 + lane, m_set - 1);
+            // the word that holds the i-th species of the set: the number of words that end at or before i
+            int w = 0;
+            for (int q = 0; q < n_chunks; ++q) w += __shfl_sync(0xffffffffu, incl, q) <= i ? 1 : 0;
+            const unsigned word = __shfl_sync(0xffffffffu, mword, w);
+            const int before = __shfl_sync(0xffffffffu, excl, w);
+            const int x = w * 32 + (int)__fns(word, 0, i - before + 1);
+            if (i0 + lane < m_set) cell(x, __ldg(sp.cmeta + x));
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < FLAT2_NCH; ++j)
+        if (j < n_chunks) cell(j * 32 + lane, meta[j]);
+}
+
+// Root-path bit set of every row of a wave computed by a kernel that does not maintain it itself:
+// mask(row) = mask(left child) | mask(right child), a leaf child contributing its species' path.
+__global__ void dtl_rowmask_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                                   int64_t row_begin, int64_t chunk_row0, int n_rows, uint32_t* __restrict__ rowmask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int mw = sp.mask_words;
+    if (i >= (int64_t)n_rows * mw) return;
+    const int64_t gr = row_begin + i / mw;
+    const int w = (int)(i % mw);
+    const int cl = row_cl[gr], cr = row_cr[gr];
+    const uint32_t a = cl >= 0 ? rowmask[(size_t)cl * mw + w] : __ldg(sp.pathmask + (size_t)(-1 - cl) * mw + w);
+    const uint32_t b = cr >= 0 ? rowmask[(size_t)cr * mw + w] : __ldg(sp.pathmask + (size_t)(-1 - cr) * mw + w);
+    rowmask[(size_t)(gr - chunk_row0) * mw + w] = a | b;
 }
 
 // the instantiation whose register-resident schedule is the shortest that holds n_steps
 typedef void (*Flat2Fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*,
-                        DtlCosts, Key32);
+                        DtlCosts, Key32, uint32_t*, int, int, int);
 static Flat2Fn flat2_pick(int n_steps) {
     if (n_steps <= 12) return dtl_wave_flat2_kernel<12>;
     if (n_steps <= 16) return dtl_wave_flat2_kernel<16>;
@@ -1001,9 +1081,11 @@ dtl_decoded_cost_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
     const int cl = row_cl[gr], cr = row_cr[gr];
     const bool cherry = cl < 0 && cr < 0;  // height-1 rows store no tags
     for (int x = lane; x < sp.S; x += 32) {
-        unsigned tag = cherry ? (T[slot * sp.pitch + x] < SR2_INF ? (unsigned)(-1 - cl) | ((unsigned)(-1 - cr) << 16)
-                                                                   : SR2_NO_TAG)
-                              : tags[slot * sp.pitch + x];
+        // an infinite cell has no tag (and its tag word may never have been written)
+        const bool finite = T[slot * sp.pitch + x] < SR2_INF;
+        unsigned tag = !finite ? SR2_NO_TAG
+                       : cherry ? (unsigned)(-1 - cl) | ((unsigned)(-1 - cr) << 16)
+                                : tags[slot * sp.pitch + x];
         int out = SR2_INF;
         if (tag != SR2_NO_TAG) {
             int a = tag & 0xffffu, b = tag >> 16;
@@ -1078,7 +1160,7 @@ dtl_traceback_kernel(DevSpecies sp, const int32_t* __restrict__ row_node,
             // a cherry stores no tags: its parent only ever points at a finite cell, whose tag is
             // the two leaf species
             if (T[slot * sp.pitch + x] < SR2_INF) a = -1 - cl, b = -1 - cr;
-        } else {
+        } else if (T[slot * sp.pitch + x] < SR2_INF) {  // infinite cells have no (defined) tag
             unsigned tag = tags[slot * sp.pitch + x];
             if (tag != SR2_NO_TAG) {
                 a = tag & 0xffffu;
@@ -1142,6 +1224,8 @@ static int dtl_prepare(void* user) {
         if ((rc = sr2_dev_reserve(ctx, DP_DTL_C, table_elems * sizeof(int32_t), &ptr))) return rc;
         p->d_C = (int32_t*)ptr;
     }
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_MASK, table_elems / 32 * sizeof(uint32_t) + 256, &ptr))) return rc;
+    p->d_mask = (uint32_t*)ptr;
     for (auto* list : {&p->ev_w0, &p->ev_w1, &p->ev_done})
         while (list->size() < p->rows.chunks.size()) {
             cudaEvent_t e;
@@ -1177,8 +1261,8 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     size_t free_b = 0, total_b = 0;
     SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
     // buffers this context already holds are reused, so they count as available
-    for (int id : {DP_ROWS_SLAB, DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MAP}) free_b += sr2_dev_pooled(ctx, id);
-    size_t per_row = (size_t)ctx->pitch * (p->need_decoded_cost ? 12 : 8);
+    for (int id : {DP_ROWS_SLAB, DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MAP, DP_DTL_MASK}) free_b += sr2_dev_pooled(ctx, id);
+    size_t per_row = (size_t)ctx->pitch * (p->need_decoded_cost ? 12 : 8) + ctx->pitch / 8;
     size_t fixed = (size_t)N * 4 * 7 + (size_t)B * 32 + (64u << 20);
     if (free_b < fixed + per_row * 4)
         return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: batch does not fit in device memory");
@@ -1299,6 +1383,16 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
                    p->flat2_smem <= std::min<size_t>(ctx->smem_optin, 65535);
         if (p->flat2) {
             p->flat2_fn = flat2_pick(ctx->dsp.n_steps);
+            // ceil(m / 32) sparse passes cost about as much as 2 dense chunks each (locating a lane's species)
+            p->flat2_sparse_max = std::min(S, ctx->pitch / 4);
+            if (const char* sm = getenv("SR2_FLAT2_SPARSE_MAX")) p->flat2_sparse_max = atoi(sm);
+            const int resident = 8 * 4 * ctx->sm_count;  // rows of the CTAs that run at one time
+            p->flat2_pf_near = resident;
+            p->flat2_pf_far = 3 * resident;
+            if (const char* pf = getenv("SR2_FLAT2_PREFETCH")) {
+                p->flat2_pf_near = atoi(pf) * resident / 4;
+                p->flat2_pf_far = 3 * p->flat2_pf_near;
+            }
             SR2_CUDA(ctx, cudaFuncSetAttribute((const void*)p->flat2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)p->flat2_smem));
         }
@@ -1328,13 +1422,15 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
     if (n_rows <= 0) return SR2_OK;
     if (h == 1 && ctx->dsp.anc_tab && !getenv("SR2_DTL_DENSE_CHERRIES")) {
         dtl_cherry_sparse_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, p->cur_stream>>>(
-            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, cs);
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, cs,
+            p->cur_mask);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
     if (h == 1) {  // both children of a height-1 node are leaves
         dtl_cherry_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, p->cur_stream>>>(
-            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs);
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
+            p->cur_mask);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
@@ -1348,9 +1444,18 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         kp.thresh = p->flat2_thresh;
         p->flat2_fn<<<(unsigned)((n_rows + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem,
                       p->cur_stream>>>(
-            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp);
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
+            p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
+    }
+    // every other wave kernel leaves the row masks to dtl_rowmask_kernel (the flat2 kernel of a
+    // later wave reads its children's masks)
+    if (p->flat2 && p->cur_mask) {
+        const int64_t words = n_rows * ctx->dsp.mask_words;
+        dtl_rowmask_kernel<<<(unsigned)((words + 255) / 256), 256, 0, p->cur_stream>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_mask);
+        SR2_CUDA(ctx, cudaGetLastError());
     }
     if (p->simd_ok && n_rows >= p->simd_min_rows) {
         Key32 kp;
@@ -1419,6 +1524,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     p->cur_T = p->d_T + set * table_elems;
     p->cur_tag = p->d_tag + set * table_elems;
     p->cur_C = p->d_C ? p->d_C + set * table_elems : nullptr;
+    p->cur_mask = p->d_mask + set * (table_elems / 32);
     cudaStream_t st = p->cur_stream;
     const RowChunk& c = p->rows.chunks[ci];
     if (p->wait_rows) SR2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->chunk_events[ci], 0));  // its rows' H2D copies
@@ -1720,7 +1826,7 @@ extern "C" int sr2_dtl_tables(sr2_ctx* ctx, int32_t instance, int32_t* out_value
         for (int x = 0; x < S; ++x) {
             if (ov) ov[x] = rowT[x];
             if (ot) {
-                bool none = rowG[x] == SR2_NO_TAG;
+                bool none = rowG[x] == SR2_NO_TAG || rowT[x] >= SR2_INF;  // infinite cells carry no tag
                 ot[2 * x] = none ? -1 : (int32_t)(rowG[x] & 0xffffu);
                 ot[2 * x + 1] = none ? -1 : (int32_t)(rowG[x] >> 16);
             }
