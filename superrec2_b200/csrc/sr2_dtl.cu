@@ -1276,7 +1276,9 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
         // a chunk should still fill the machine's big-wave kernels
         per_chunk = std::max<int64_t>(per_chunk, 64 * 8 * (int64_t)ctx->sm_count);
         rows_budget = std::min(rows_budget, per_chunk);
-        first_chunk_rows = rows_budget / 2;
+        int first_div = 2;
+        if (const char* fd = getenv("SR2_PIPELINE_FIRST")) first_div = std::max(1, atoi(fd));
+        first_chunk_rows = rows_budget / first_div;
     }
     RowHooks plan_only;
     plan_only.user = ctx;
@@ -1761,7 +1763,7 @@ extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
                            uint32_t flags, int32_t* out_min_cost, int32_t* out_root_species,
                            int32_t* out_map_species) {
     if (!ctx) return SR2_ERR_ARG;
-    int pipeline_chunks = 3;
+    int pipeline_chunks = 4;
     if (const char* v = getenv("SR2_PIPELINE_CHUNKS")) pipeline_chunks = std::max(1, atoi(v));
     DtlRunState rs{ctx, nullptr, out_min_cost, out_root_species, out_map_species, false, false, 0, {}};
     RowHooks hooks;
