@@ -61,15 +61,12 @@ struct DtlProblem {
     int spad = 0, wave_warps = 0;
     size_t wave_smem = 0;
     bool cta_per_row = false;
-    // SIMD-across-rows kernel for big waves (32-bit keys)
+    // batched wave kernels (32-bit keys)
     bool simd_ok = false;
-    size_t simd_smem = 0;
     int rank_bits = 0, depth_bits = 0;
     int64_t max_finite = 0;
     int64_t simd_min_rows = 0;
-    int simd_arr_words = 0, simd_thresh = 0;
-    int multi_rpw = 2, multi_rs = 0;
-    size_t multi_smem = 0;
+    int simd_thresh = 0;
     bool flat = true;
     int flat_rs = 0;
     size_t flat_smem = 0;
@@ -342,284 +339,19 @@ dtl_cherry_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, cons
 }
 
 // ---------------------------------------------------------------------------
-// Batched waves: SIMD across rows.  A CTA owns 16 rows of the wave; lane = (row j,
-// half h).  All lanes of a warp work on the SAME species node (two sibling cells, or the
-// l / r child row of one node), so species-tree look-ups are warp-uniform, every lane is
-// busy and no lane ever waits for another row.  The 16 x |S| slot arrays and the output
-// staging live in shared memory, transposed ([species][row], XOR-swizzled) so that both
-// the compute phase (fixed species, 16 rows) and the coalesced row loads / stores (fixed
-// row, 32 species) are free of bank conflicts.  Keys are 32 bits:
+// 32-bit arg-min keys of the batched wave kernels:
 //   value[31:sh] | rank[sh-1:db] | depth[db-1:0]
 // which the host only selects when every finite table value fits the value field.
 // ---------------------------------------------------------------------------
 struct Key32 {
-    int sh, db;            // value shift (= rank bits + depth bits), depth bits
+    int sh, db;            // value shift (>= rank bits + depth bits), depth bits
     unsigned rm, dm;       // rank mask (after >> db), depth mask
     unsigned inf32;        // the infinite value: top bit of the value field
     int thresh;            // sums below this are finite (inf32 minus the largest correction)
 };
 
-#define SIMD_ROWS 16
-#define SIMD_LD 17  // row stride in words: odd, so transposed row loads/stores hit 32 banks
-__device__ __forceinline__ int simd_at(int y, int j) { return y * SIMD_LD + j; }
-
-// value + loss * depth of a key: what a candidate adds for a child placed at that key
-__device__ __forceinline__ int key_q(unsigned k, int loss, const Key32& kp) {
-    return (int)(k >> kp.sh) + loss * (int)(k & kp.dm);
-}
-
-__global__ void __launch_bounds__(512, 2)
-dtl_wave_simd16_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
-                       int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
-                       uint32_t* __restrict__ tags, DtlCosts cs, int arr_words, Key32 kp) {
-    extern __shared__ unsigned smem32[];
-    const int S = sp.S;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int j = lane & 15, h = lane >> 4;
-    // four arrays of arr_words (a multiple of 32); SR and OG are shifted by 16 words so that the
-    // two halves of a warp (same species, other array) use opposite halves of the 32 banks
-    unsigned* SL = smem32;
-    unsigned* SR = smem32 + arr_words + 16;
-    unsigned* OT = smem32 + 2 * arr_words + 32;
-    unsigned* OG = smem32 + 3 * arr_words + 48;
-    const int row0 = blockIdx.x * SIMD_ROWS;
-    const int rows_here = min(SIMD_ROWS, n_rows - row0);
-
-    // ---- load: 32 (row, side) child rows, transposed into the slot arrays ----------------
-    for (int pair = warp; pair < 2 * SIMD_ROWS; pair += nwarps) {
-        int jj = pair >> 1, side = pair & 1;
-        int64_t gr = row_begin + row0 + min(jj, rows_here - 1);  // pad the last group with a copy
-        int c = side ? row_cr[gr] : row_cl[gr];
-        unsigned* dst = (side ? SR : SL) + jj;
-        const int32_t* __restrict__ src = c >= 0 ? T + (size_t)c * sp.pitch : nullptr;
-        for (int y = lane; y < S; y += 32) {
-            int v = src ? src[y] : (y == -1 - c ? 0 : SR2_INF);
-            unsigned val = v >= SR2_INF ? kp.inf32 : (unsigned)v;
-            dst[y * SIMD_LD] = (val << kp.sh) | ((unsigned)y << kp.db) | (unsigned)__ldg(sp.depth + y);
-        }
-    }
-    __syncthreads();
-
-    // ---- up-sweep: half 0 sweeps the left-child array, half 1 the right-child array -------
-    {
-        unsigned* arr = (h ? SR : SL) + j;
-        for (int d = sp.D - 2; d >= 0; --d) {
-            int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
-            for (int i = b + warp; i < e; i += nwarps) {
-                int p = __ldg(sp.int_list + i), c = 2 * i + 1;
-                unsigned k = min(arr[p * SIMD_LD], min(arr[c * SIMD_LD], arr[(c + 1) * SIMD_LD]));
-                arr[p * SIMD_LD] = k;
-            }
-            __syncthreads();
-        }
-    }
-
-    const int loss = cs.loss;
-    const int NONE = 0x7fffffff;
-    // ---- down-sweep: a warp takes one internal species p; its halves finish the two sibling
-    //      cells x = c + h and leave P[x] in the slots for the next level.  The root cell is
-    //      folded in as iteration -1 of level 0 (half 0 of warp 0). ----------------------------
-    for (int d = -1; d < sp.D - 1; ++d) {
-        int b = d < 0 ? 0 : __ldg(sp.int_lvl_off + d), e = d < 0 ? 1 : __ldg(sp.int_lvl_off + d + 1);
-        const int dx = d + 1;
-        for (int i = b + warp; i < e; i += nwarps) {
-            int x, cx;
-            unsigned Ml, Mr, Pl, Pr;
-            if (d < 0) {
-                if (h) break;  // only half 0 of warp 0 handles the root
-                x = 0;
-                Ml = SL[simd_at(0, j)];
-                Mr = SR[simd_at(0, j)];
-                Pl = Pr = 0xffffffffu;  // nothing is incomparable to the root
-            } else {
-                int p = __ldg(sp.int_list + i), c = 2 * i + 1;
-                x = c + h;
-                unsigned Ppl = SL[simd_at(p, j)], Ppr = SR[simd_at(p, j)];
-                Ml = SL[simd_at(x, j)];
-                Mr = SR[simd_at(x, j)];
-                unsigned sibl = SL[simd_at(c + 1 - h, j)], sibr = SR[simd_at(c + 1 - h, j)];
-                Pl = min(Ppl, sibl);
-                Pr = min(Ppr, sibr);
-            }
-            cx = __ldg(sp.child0 + x);
-            const int qMl = key_q(Ml, loss, kp), qMr = key_q(Mr, loss, kp);
-            int w1 = NONE, w2 = NONE, w4 = NONE, w5 = NONE;
-            unsigned l0 = 0, l1 = 0, r0 = 0, r1 = 0;
-            if (cx >= 0) {
-                l0 = SL[simd_at(cx, j)];
-                l1 = SL[simd_at(cx + 1, j)];
-                r0 = SR[simd_at(cx, j)];
-                r1 = SR[simd_at(cx + 1, j)];
-                int b12 = -2 * loss * (dx + 1);
-                w1 = ((key_q(l0, loss, kp) + key_q(r1, loss, kp) + b12) << 3) | 0;   // 1. spe, l|r
-                w2 = ((key_q(l1, loss, kp) + key_q(r0, loss, kp) + b12) << 3) | 1;   // 2. spe, r|l
-            }
-            int w3 = ((qMl + qMr + cs.dup - 2 * loss * dx) << 3) | 2;                  // 3. dup
-            if (d >= 0) {
-                w4 = (((int)(Pl >> kp.sh) + qMr + cs.hgt - loss * dx) << 3) | 3;       // 4. hgt, left away
-                w5 = ((qMl + (int)(Pr >> kp.sh) + cs.hgt - loss * dx) << 3) | 4;       // 5. hgt, right away
-            }
-            int w = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
-            int best = w >> 3, which = w & 7;
-            unsigned ka = which == 0 ? l0 : which == 1 ? l1 : which == 3 ? Pl : Ml;
-            unsigned kb = which == 0 ? r1 : which == 1 ? r0 : which == 4 ? Pr : Mr;
-            bool finite = best < kp.thresh;
-            OT[simd_at(x, j)] = finite ? (unsigned)best : (unsigned)SR2_INF;
-            OG[simd_at(x, j)] =
-                finite ? (((ka >> kp.db) & kp.rm) | (((kb >> kp.db) & kp.rm) << 16)) : SR2_NO_TAG;
-            SL[simd_at(x, j)] = Pl;
-            SR[simd_at(x, j)] = Pr;
-        }
-        __syncthreads();
-    }
-
-    // ---- store: rows back to global memory, coalesced -----------------------------------------
-    for (int pair = warp; pair < 2 * rows_here; pair += nwarps) {
-        int jj = pair >> 1, which = pair & 1;
-        size_t slot = (size_t)(row_begin + row0 + jj - chunk_row0);
-        const unsigned* src = (which ? OG : OT) + jj;
-        unsigned* dst = which ? tags + slot * sp.pitch : reinterpret_cast<unsigned*>(T) + slot * sp.pitch;
-        for (int y = lane; y < S; y += 32) dst[y] = src[y * SIMD_LD];
-    }
-}
-
 // ---------------------------------------------------------------------------
-// Batched waves, second form: several rows per warp.  A warp owns RPW rows and gives each
-// 32/RPW lanes, so thin levels of the species tree still fill the warp, while everything
-// stays warp-synchronous (no block barrier, rows are loaded and stored row-major and
-// coalesced).  32-bit keys as above; cells are written straight to global memory (the
-// lanes of one row cover consecutive species, i.e. whole 32-byte sectors).
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void cell32(int x, int dx, int cx, bool is_root, unsigned Ml, unsigned Mr,
-                                       unsigned Pl, unsigned Pr, const unsigned* sl, const unsigned* sr,
-                                       const DtlCosts& cs, const Key32& kp, int& out_t, unsigned& out_g) {
-    const int loss = cs.loss, NONE = 0x7fffffff;
-    const int qMl = key_q(Ml, loss, kp), qMr = key_q(Mr, loss, kp);
-    int w1 = NONE, w2 = NONE, w4 = NONE, w5 = NONE;
-    unsigned l0 = 0, l1 = 0, r0 = 0, r1 = 0;
-    if (cx >= 0) {
-        l0 = sl[cx];
-        l1 = sl[cx + 1];
-        r0 = sr[cx];
-        r1 = sr[cx + 1];
-        int b12 = -2 * loss * (dx + 1);
-        w1 = ((key_q(l0, loss, kp) + key_q(r1, loss, kp) + b12) << 3) | 0;
-        w2 = ((key_q(l1, loss, kp) + key_q(r0, loss, kp) + b12) << 3) | 1;
-    }
-    int w3 = ((qMl + qMr + cs.dup - 2 * loss * dx) << 3) | 2;
-    if (!is_root) {
-        w4 = (((int)(Pl >> kp.sh) + qMr + cs.hgt - loss * dx) << 3) | 3;
-        w5 = ((qMl + (int)(Pr >> kp.sh) + cs.hgt - loss * dx) << 3) | 4;
-    }
-    int w = min(min(min(w1, w2), w3), min(w4, w5));
-    int best = w >> 3, which = w & 7;
-    unsigned ka = Ml, kb = Mr;
-    ka = which == 0 ? l0 : ka;
-    ka = which == 1 ? l1 : ka;
-    ka = which == 3 ? Pl : ka;
-    kb = which == 0 ? r1 : kb;
-    kb = which == 1 ? r0 : kb;
-    kb = which == 4 ? Pr : kb;
-    bool finite = best < kp.thresh;
-    out_t = finite ? best : SR2_INF;
-    out_g = finite ? (((ka >> kp.db) & kp.rm) | (((kb >> kp.db) & kp.rm) << 16)) : SR2_NO_TAG;
-}
-
-template <int RPW>
-__global__ void __launch_bounds__(256)
-dtl_wave_multi_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
-                      int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
-                      uint32_t* __restrict__ tags, DtlCosts cs, int rs, Key32 kp) {
-    extern __shared__ unsigned smem32[];
-    constexpr int LPR = 32 / RPW;  // lanes per row
-    const int S = sp.S;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int g = lane / LPR, t = lane % LPR;
-    const int wrow0 = (blockIdx.x * nwarps + warp) * RPW;  // first row of this warp inside the wave
-    if (wrow0 >= n_rows) return;
-    const int rows_here = min(RPW, n_rows - wrow0);
-    unsigned* wbase = smem32 + (size_t)warp * RPW * 2 * rs;
-
-    // ---- load the 2*RPW child rows, row-major, whole warp per row ---------------------------
-#pragma unroll 1
-    for (int r = 0; r < RPW; ++r) {
-        int64_t gr = row_begin + wrow0 + min(r, rows_here - 1);
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            int c = side ? row_cr[gr] : row_cl[gr];
-            unsigned* dst = wbase + (size_t)(r * 2 + side) * rs;
-            const int32_t* __restrict__ src = c >= 0 ? T + (size_t)c * sp.pitch : nullptr;
-            for (int y = lane; y < S; y += 32) {
-                int v = src ? src[y] : (y == -1 - c ? 0 : SR2_INF);
-                unsigned val = v >= SR2_INF ? kp.inf32 : (unsigned)v;
-                dst[y] = (val << kp.sh) | ((unsigned)y << kp.db) | (unsigned)__ldg(sp.depth + y);
-            }
-        }
-    }
-    __syncwarp();
-
-    unsigned* sl = wbase + (size_t)(g * 2) * rs;
-    unsigned* sr = sl + rs;
-    // ---- up-sweep -----------------------------------------------------------------------------
-    for (int d = sp.D - 2; d >= 0; --d) {
-        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
-        for (int i = b + t; i < e; i += LPR) {
-            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
-            sl[p] = min(sl[p], min(sl[c], sl[c + 1]));
-            sr[p] = min(sr[p], min(sr[c], sr[c + 1]));
-        }
-        __syncwarp();
-    }
-
-    const bool live = g < rows_here;
-    const size_t slot = (size_t)(row_begin + wrow0 + min(g, rows_here - 1) - chunk_row0);
-    int32_t* __restrict__ Tout = T + slot * sp.pitch;
-    uint32_t* __restrict__ Gout = tags + slot * sp.pitch;
-
-    // ---- root cell ------------------------------------------------------------------------------
-    if (t == 0) {
-        int ot;
-        unsigned og;
-        cell32(0, 0, __ldg(sp.child0), true, sl[0], sr[0], 0xffffffffu, 0xffffffffu, sl, sr, cs, kp, ot, og);
-        if (live) {
-            Tout[0] = ot;
-            Gout[0] = og;
-        }
-        sl[0] = 0xffffffffu;  // nothing is incomparable to the root
-        sr[0] = 0xffffffffu;
-    }
-    __syncwarp();
-
-    // ---- down-sweep -------------------------------------------------------------------------------
-    for (int d = 0; d < sp.D - 1; ++d) {
-        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
-        for (int i = b + t; i < e; i += LPR) {
-            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
-            unsigned Ppl = sl[p], Ppr = sr[p];
-            unsigned m0l = sl[c], m1l = sl[c + 1], m0r = sr[c], m1r = sr[c + 1];
-            unsigned P0l = min(Ppl, m1l), P1l = min(Ppl, m0l);
-            unsigned P0r = min(Ppr, m1r), P1r = min(Ppr, m0r);
-            int t0, t1;
-            unsigned g0, g1;
-            cell32(c, d + 1, __ldg(sp.child0 + c), false, m0l, m0r, P0l, P0r, sl, sr, cs, kp, t0, g0);
-            cell32(c + 1, d + 1, __ldg(sp.child0 + c + 1), false, m1l, m1r, P1l, P1r, sl, sr, cs, kp, t1, g1);
-            if (live) {
-                Tout[c] = t0;
-                Tout[c + 1] = t1;
-                Gout[c] = g0;
-                Gout[c + 1] = g1;
-            }
-            sl[c] = P0l;
-            sl[c + 1] = P1l;
-            sr[c] = P0r;
-            sr[c + 1] = P1r;
-        }
-        __syncwarp();
-    }
-}
-
-// ---------------------------------------------------------------------------
-// Batched waves, third form ("flat"): one warp per row, 32-bit keys, and BOTH sweeps
+// Batched waves, first form ("flat", kept as a cross-check of flat2): one warp per row, 32-bit keys, and BOTH sweeps
 // materialised in shared memory before any cell is evaluated:
 //   ML/MR = SUBMIN of the two child rows (up-sweep, in place)
 //   PL/PR = SEPMIN of the two child rows (top-down sweep into two more arrays)
@@ -761,7 +493,7 @@ dtl_wave_flat_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
 }
 
 // ---------------------------------------------------------------------------
-// Batched waves, fourth form ("flat2"): the flat kernel with its three phases put on an
+// Batched waves, the form in use ("flat2"): the flat kernel with its three phases put on an
 // instruction diet (the flat kernel is issue-bound, profiles/README.md r1j):
 //   * everything runs over whole row pitches (multiples of 32 species) -- no bounds tests;
 //     pad cells hold garbage that nothing reads;
@@ -1343,30 +1075,24 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
     p->rank_bits = ctx->dsp.rank_bits;
     p->depth_bits = ctx->dsp.depth_bits;
     int value_bits = 32 - p->rank_bits - p->depth_bits;
-    p->simd_arr_words = (S * SIMD_LD + 31) / 32 * 32;
-    p->simd_smem = ((size_t)4 * p->simd_arr_words + 64) * sizeof(unsigned);
     // finite sums stay below inf32 minus the largest correction a candidate subtracts
     int64_t inf32 = value_bits >= 2 ? (int64_t)1 << (value_bits - 1) : 0;
     int64_t slack = 4 * (int64_t)p->costs[3] * (ctx->D + 2);
     const char* off = getenv("SR2_DTL_NO_SIMD");
     p->simd_ok = !(off && off[0] == '1') && S >= 2 && value_bits >= 8 && value_bits <= 27 &&
-                 p->max_finite + slack < inf32 - slack && p->simd_smem <= ctx->smem_optin;
+                 p->max_finite + slack < inf32 - slack;
     p->simd_thresh = (int)(inf32 - slack);
-    // small waves keep the row-per-warp kernel (more parallelism inside a row); the
-    // threshold can be overridden for tests (SR2_DTL_SIMD_MIN_ROWS)
-    p->simd_min_rows = SIMD_ROWS * (int64_t)ctx->sm_count;
+    // small waves keep the row-per-warp kernel with 64-bit keys (latency-bound tops of the trees);
+    // the threshold can be overridden for tests (SR2_DTL_SIMD_MIN_ROWS)
+    p->simd_min_rows = 16 * (int64_t)ctx->sm_count;
     if (const char* min_rows = getenv("SR2_DTL_SIMD_MIN_ROWS")) p->simd_min_rows = atoll(min_rows);
-    if (p->simd_ok)
-        SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_simd16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)p->simd_smem));
-    // default batched kernel: "flat" (element-wise cells); SR2_DTL_VARIANT=multi|simd16 selects
-    // the two earlier forms (kept for comparison and as cross-checks in the tests)
-    p->flat = true;
+    // "flat": the first batched form, selected with SR2_DTL_VARIANT=flat (a cross-check of flat2 in the tests)
+    p->flat = false;
     if (const char* v = getenv("SR2_DTL_VARIANT")) p->flat = strcmp(v, "flat") == 0;
     p->flat_rs = (S + 2 + 15) / 16 * 16 + 2;   // uint2 elements per array; even (aligned uint4 pairs)
     p->flat_smem = (size_t)8 * 2 * p->flat_rs * sizeof(uint2);
-    if (p->flat_smem > ctx->smem_optin) p->flat = false;
-    if (p->simd_ok && p->flat)
+    if (p->flat_smem > ctx->smem_optin || !p->simd_ok) p->flat = false;
+    if (p->flat)
         SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->flat_smem));
     // flat2 (default): needs the schedule in FLAT2_NS registers, 16-bit shared-memory addresses and
@@ -1398,23 +1124,6 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
             SR2_CUDA(ctx, cudaFuncSetAttribute((const void*)p->flat2_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)p->flat2_smem));
         }
-    }
-    // rows-per-warp variant: 0 = use the 16-rows-per-CTA kernel instead
-    p->multi_rpw = 2;  // measured best on B200 for |S| = 399 (profiles/README.md)
-    if (const char* v = getenv("SR2_DTL_ROWS_PER_WARP")) p->multi_rpw = atoi(v);
-    if (p->multi_rpw != 0 && p->multi_rpw != 1 && p->multi_rpw != 2 && p->multi_rpw != 4 && p->multi_rpw != 8)
-        p->multi_rpw = 2;
-    // row stride = 4 mod 32 words: the rows of one warp start in different banks
-    p->multi_rs = (S + 31) / 32 * 32 + 4;
-    while (p->multi_rpw > 1 && (size_t)8 * p->multi_rpw * 2 * p->multi_rs * 4 > ctx->smem_optin) p->multi_rpw /= 2;
-    p->multi_smem = (size_t)8 * std::max(p->multi_rpw, 1) * 2 * p->multi_rs * sizeof(unsigned);
-    if (p->multi_smem > ctx->smem_optin) p->multi_rpw = 0;
-    if (p->simd_ok && p->multi_rpw) {
-        const void* fn = p->multi_rpw == 1 ? (const void*)dtl_wave_multi_kernel<1>
-                         : p->multi_rpw == 2 ? (const void*)dtl_wave_multi_kernel<2>
-                         : p->multi_rpw == 4 ? (const void*)dtl_wave_multi_kernel<4>
-                                             : (const void*)dtl_wave_multi_kernel<8>;
-        SR2_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->multi_smem));
     }
     return SR2_OK;
 }
@@ -1459,7 +1168,7 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_mask);
         SR2_CUDA(ctx, cudaGetLastError());
     }
-    if (p->simd_ok && n_rows >= p->simd_min_rows) {
+    if (p->flat && n_rows >= p->simd_min_rows) {
         Key32 kp;
         kp.db = p->depth_bits;
         kp.sh = p->rank_bits + p->depth_bits;
@@ -1467,31 +1176,9 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         kp.dm = (1u << p->depth_bits) - 1;
         kp.inf32 = 1u << (32 - kp.sh - 1);
         kp.thresh = p->simd_thresh;
-        if (p->flat) {
-            dtl_wave_flat_kernel<<<(unsigned)((n_rows + 7) / 8), 256, p->flat_smem, p->cur_stream>>>(
-                ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
-                p->flat_rs, kp);
-            SR2_CUDA(ctx, cudaGetLastError());
-            return SR2_OK;
-        }
-        if (p->multi_rpw) {
-            int rows_per_cta = 8 * p->multi_rpw;
-            unsigned grid = (unsigned)((n_rows + rows_per_cta - 1) / rows_per_cta);
-#define SR2_LAUNCH_MULTI(R)                                                                              \
-    dtl_wave_multi_kernel<R><<<grid, 256, p->multi_smem, p->cur_stream>>>(                                 \
-        ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, \
-        cs, p->multi_rs, kp)
-            if (p->multi_rpw == 1) SR2_LAUNCH_MULTI(1);
-            else if (p->multi_rpw == 2) SR2_LAUNCH_MULTI(2);
-            else if (p->multi_rpw == 4) SR2_LAUNCH_MULTI(4);
-            else SR2_LAUNCH_MULTI(8);
-#undef SR2_LAUNCH_MULTI
-            SR2_CUDA(ctx, cudaGetLastError());
-            return SR2_OK;
-        }
-        dtl_wave_simd16_kernel<<<(unsigned)((n_rows + SIMD_ROWS - 1) / SIMD_ROWS), 512, p->simd_smem, p->cur_stream>>>(
+        dtl_wave_flat_kernel<<<(unsigned)((n_rows + 7) / 8), 256, p->flat_smem, p->cur_stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
-            p->simd_arr_words, kp);
+            p->flat_rs, kp);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }

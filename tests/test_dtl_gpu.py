@@ -163,17 +163,16 @@ def test_bad_input_is_rejected(ctx):
     (100, 130, 5, (0, 0, 0, 0, 0)),
     (200, 210, 3, (0, 1, 1, 1, 1)),
 ])
-@pytest.mark.parametrize("variant,rows_per_warp", [
-    ("flat2", 0), ("flat", 0), ("multi", 0), ("multi", 1), ("multi", 2), ("multi", 4), ("multi", 8)])
-def test_batched_wave_kernels_against_oracle(ctx, monkeypatch, n_s, n_o, n_trees, costs, variant,
-                                             rows_per_warp):
+@pytest.mark.parametrize("variant", ["flat2", "flat2-dense-cells", "flat"])
+def test_batched_wave_kernels_against_oracle(ctx, monkeypatch, n_s, n_o, n_trees, costs, variant):
     """Force the batched-wave kernels (32-bit keys) on small batches, including partial last
-    groups, and compare every cell and tag with the oracle: "flat" (the default: both sweeps in
-    shared memory, element-wise cells), and the two earlier forms kept as cross-checks
-    ("multi" with 1/2/4/8 rows per warp; rows_per_warp == 0 = 16 rows per CTA)."""
+    groups, and compare every cell and tag with the oracle: "flat2" (the default: sweep schedule in
+    registers, sparse cells pass for rows with few root-path species), the same with the sparse pass
+    switched off, and "flat", the first form, kept as a cross-check."""
     monkeypatch.setenv("SR2_DTL_SIMD_MIN_ROWS", "1")
-    monkeypatch.setenv("SR2_DTL_VARIANT", variant)
-    monkeypatch.setenv("SR2_DTL_ROWS_PER_WARP", str(rows_per_warp))
+    monkeypatch.setenv("SR2_DTL_VARIANT", variant.split("-")[0])
+    if variant.endswith("dense-cells"):
+        monkeypatch.setenv("SR2_FLAT2_SPARSE_MAX", "0")
     batch = synth.make_batch(n_s, n_o, n_trees, seed=31 + n_s, costs=costs)
     ctx.set_species(batch.parent, batch.child0, batch.child1)
     min_cost, root, mapping = ctx.dtl_run(batch.node_off, batch.left, batch.right,
