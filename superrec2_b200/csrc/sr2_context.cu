@@ -27,6 +27,7 @@ int sr2_dev_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out) {
     Sr2Pool& pool = ctx->dev[id];
     bytes = std::max<size_t>(bytes, 256);
     if (pool.cap < bytes) {
+        ctx->mem_dirty = true;
         if (pool.ptr) cudaFree(pool.ptr);
         pool.ptr = nullptr;
         pool.cap = 0;
@@ -76,6 +77,17 @@ int sr2_host_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out) {
 }
 
 size_t sr2_dev_pooled(const sr2_ctx* ctx, int id) { return ctx->dev[id].cap; }
+
+int sr2_mem_free(sr2_ctx* ctx, size_t* out_free) {
+    if (ctx->mem_dirty) {
+        size_t free_b = 0, total_b = 0;
+        SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        ctx->mem_free_cached = free_b;
+        ctx->mem_dirty = false;
+    }
+    *out_free = ctx->mem_free_cached;
+    return SR2_OK;
+}
 
 static std::string g_create_error;
 
@@ -160,6 +172,8 @@ extern "C" void sr2_destroy(sr2_ctx* ctx) {
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->fill_stream) cudaStreamDestroy(ctx->fill_stream);
     for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
+    for (auto* list : {&ctx->dtl_ev_w0, &ctx->dtl_ev_w1, &ctx->dtl_ev_done, &ctx->dtl_ev_copied})
+        for (cudaEvent_t e : *list) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -255,6 +269,7 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
     for (int d = 0; d < ctx->D; ++d) ctx->h_int_lvl_off[d + 1] += ctx->h_int_lvl_off[d];
 
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->mem_dirty = true;  // the species slab and the ancestor table are allocated below
     sr2_free_dtl(ctx);
     sr2_free_super(ctx);
     if (ctx->d_species_slab) {

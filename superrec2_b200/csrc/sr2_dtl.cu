@@ -55,7 +55,6 @@ struct DtlProblem {
     int32_t* cur_C = nullptr;
     uint32_t* d_mask = nullptr;      // [rows * pitch/32] root-path bit sets of the rows (flat2 only)
     uint32_t* cur_mask = nullptr;
-    std::vector<cudaEvent_t> ev_w0, ev_w1, ev_done;  // per chunk: waves begin / end, chunk finished
     int n_waves = 0, n_launch = 0;
     // wave launch configuration (fixed per upload)
     int spad = 0, wave_warps = 0;
@@ -83,8 +82,6 @@ struct DtlProblem {
 void sr2_free_dtl(sr2_ctx* ctx) {
     DtlProblem* p = ctx->dtl;
     if (!p) return;
-    for (auto* list : {&p->ev_w0, &p->ev_w1, &p->ev_done})
-        for (cudaEvent_t e : *list) cudaEventDestroy(e);
     delete p;  // device buffers live in the context's pools
     ctx->dtl = nullptr;
 }
@@ -958,12 +955,17 @@ static int dtl_prepare(void* user) {
     }
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_MASK, table_elems / 32 * sizeof(uint32_t) + 256, &ptr))) return rc;
     p->d_mask = (uint32_t*)ptr;
-    for (auto* list : {&p->ev_w0, &p->ev_w1, &p->ev_done})
+    for (auto* list : {&ctx->dtl_ev_w0, &ctx->dtl_ev_w1, &ctx->dtl_ev_done})
         while (list->size() < p->rows.chunks.size()) {
             cudaEvent_t e;
             SR2_CUDA(ctx, cudaEventCreate(&e));
             list->push_back(e);
         }
+    while (ctx->dtl_ev_copied.size() < p->rows.chunks.size()) {
+        cudaEvent_t e;
+        SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->dtl_ev_copied.push_back(e);
+    }
     p->prepared = true;
     return SR2_OK;
 }
@@ -990,8 +992,11 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     // speciation cost (reconciliation.py:97-108) but cost() does (DESIGN.md "selection").
     p->need_decoded_cost = costs[0] != 0;
 
-    size_t free_b = 0, total_b = 0;
-    SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t free_b = 0;
+    {
+        int rc_mem = sr2_mem_free(ctx, &free_b);
+        if (rc_mem) return rc_mem;
+    }
     // buffers this context already holds are reused, so they count as available
     for (int id : {DP_ROWS_SLAB, DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MAP, DP_DTL_MASK}) free_b += sr2_dev_pooled(ctx, id);
     size_t per_row = (size_t)ctx->pitch * (p->need_decoded_cost ? 12 : 8) + ctx->pitch / 8;
@@ -1219,7 +1224,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     if (p->wait_rows) SR2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->chunk_events[ci], 0));  // its rows' H2D copies
     DtlCosts cs{p->costs[0], p->costs[1], p->costs[2], p->costs[3]};
     const int H = (int)c.wave_off.size() - 2;  // highest wave
-    SR2_CUDA(ctx, cudaEventRecord(p->ev_w0[ci], st));
+    SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w0[ci], st));
     for (int h = 1; h <= H; ++h) {
         int64_t n = c.wave_off[h + 1] - c.wave_off[h];
         if (n <= 0) continue;
@@ -1228,7 +1233,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         ++p->n_waves;
         ++p->n_launch;
     }
-    SR2_CUDA(ctx, cudaEventRecord(p->ev_w1[ci], st));
+    SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w1[ci], st));
     if (p->need_decoded_cost) {
         for (int h = 1; h <= H; ++h) {
             int64_t n = c.wave_off[h + 1] - c.wave_off[h];
@@ -1254,7 +1259,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         ++p->n_launch;
     }
     SR2_CUDA(ctx, cudaGetLastError());
-    SR2_CUDA(ctx, cudaEventRecord(p->ev_done[ci], st));
+    SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_done[ci], st));
     return SR2_OK;
 }
 
@@ -1263,16 +1268,16 @@ static void dtl_collect_timing(sr2_ctx* ctx, DtlProblem* p) {
     float waves_ms = 0.f;
     for (size_t ci = 0; ci < p->rows.chunks.size(); ++ci) {
         float ms = 0.f;
-        cudaEventElapsedTime(&ms, p->ev_w0[ci], p->ev_w1[ci]);
+        cudaEventElapsedTime(&ms, ctx->dtl_ev_w0[ci], ctx->dtl_ev_w1[ci]);
         waves_ms += ms;
     }
     cudaEventElapsedTime(&ctx->timing.solve_ms, ctx->ev[0], ctx->ev[1]);
     if (getenv("SR2_TRACE"))
         for (size_t ci = 0; ci < p->rows.chunks.size(); ++ci) {
             float a = 0.f, b = 0.f, c = 0.f;
-            cudaEventElapsedTime(&a, ctx->ev[0], p->ev_w0[ci]);
-            cudaEventElapsedTime(&b, ctx->ev[0], p->ev_w1[ci]);
-            cudaEventElapsedTime(&c, ctx->ev[0], p->ev_done[ci]);
+            cudaEventElapsedTime(&a, ctx->ev[0], ctx->dtl_ev_w0[ci]);
+            cudaEventElapsedTime(&b, ctx->ev[0], ctx->dtl_ev_w1[ci]);
+            cudaEventElapsedTime(&c, ctx->ev[0], ctx->dtl_ev_done[ci]);
             fprintf(stderr, "[sr2] chunk %zu on the device: waves %.2f .. %.2f ms, done %.2f ms\n", ci, a, b, c);
         }
     ctx->timing.waves_ms = waves_ms;
@@ -1344,7 +1349,6 @@ struct DtlRunState {
     bool started;
     bool direct;     // the caller's result arrays are pinned: copy straight into them
     int delivered;   // chunks whose results already sit in the caller's buffers
-    std::vector<cudaEvent_t> copied;  // per chunk: its D2H copies finished
 };
 
 // staging -> caller's buffers for chunks [rs->delivered, upto) whose copies have finished
@@ -1354,7 +1358,7 @@ static int dtl_deliver(DtlRunState* rs, int upto, bool wait) {
     DtlProblem* p = ctx->dtl;
     const size_t B = p->rows.B;
     while (rs->delivered < upto) {
-        cudaEvent_t e = rs->copied[rs->delivered];
+        cudaEvent_t e = ctx->dtl_ev_copied[rs->delivered];
         if (wait) SR2_CUDA(ctx, cudaEventSynchronize(e));
         else if (cudaEventQuery(e) != cudaSuccess) break;
         const RowChunk& c = p->rows.chunks[rs->delivered];
@@ -1408,11 +1412,6 @@ static int dtl_run_on_plan(void* user) {
         rs->direct = pinned(rs->out_cost) && pinned(rs->out_root) && pinned(rs->out_map);
     }
     if (!ctx->copy_stream) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    while (rs->copied.size() < p->rows.chunks.size()) {
-        cudaEvent_t e;
-        SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        rs->copied.push_back(e);
-    }
     p->n_waves = p->n_launch = 0;
     p->wait_rows = true;
     SR2_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -1431,7 +1430,7 @@ static int dtl_run_on_chunk(void* user, int ci) {
     const size_t b0 = c.inst_begin, nb = c.inst_end - c.inst_begin;
     const size_t n0 = p->rows.node_off[c.inst_begin], nn = p->rows.node_off[c.inst_end] - n0;
     cudaStream_t cs = ctx->copy_stream;
-    SR2_CUDA(ctx, cudaStreamWaitEvent(cs, p->ev_done[ci], 0));
+    SR2_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->dtl_ev_done[ci], 0));
     int32_t* to_cost = rs->direct ? rs->out_cost : rs->stage;
     int32_t* to_root = rs->direct ? rs->out_root : rs->stage + B;
     int32_t* to_map = rs->direct ? rs->out_map : rs->stage + 2 * B;
@@ -1441,7 +1440,7 @@ static int dtl_run_on_chunk(void* user, int ci) {
         SR2_CUDA(ctx, cudaMemcpyAsync(to_root + b0, p->d_root_species + b0, nb * 4, cudaMemcpyDeviceToHost, cs));
     if (rs->out_map && nn)
         SR2_CUDA(ctx, cudaMemcpyAsync(to_map + n0, p->d_map + n0, nn * 4, cudaMemcpyDeviceToHost, cs));
-    SR2_CUDA(ctx, cudaEventRecord(rs->copied[ci], cs));
+    SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_copied[ci], cs));
     return dtl_deliver(rs, ci, false);  // earlier chunks that are back already
 }
 
@@ -1452,7 +1451,7 @@ extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     if (!ctx) return SR2_ERR_ARG;
     int pipeline_chunks = 4;
     if (const char* v = getenv("SR2_PIPELINE_CHUNKS")) pipeline_chunks = std::max(1, atoi(v));
-    DtlRunState rs{ctx, nullptr, out_min_cost, out_root_species, out_map_species, false, false, 0, {}};
+    DtlRunState rs{ctx, nullptr, out_min_cost, out_root_species, out_map_species, false, false, 0};
     RowHooks hooks;
     hooks.user = &rs;
     hooks.on_plan = dtl_run_on_plan;
@@ -1468,7 +1467,6 @@ extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
         if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
         cudaStreamSynchronize(ctx->copy_stream);
     }
-    for (cudaEvent_t e : rs.copied) cudaEventDestroy(e);
     if (rc) return rc;
     SR2_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));

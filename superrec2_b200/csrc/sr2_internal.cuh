@@ -131,6 +131,13 @@ struct sr2_ctx {
     cudaStream_t fill_stream = nullptr;    // device-side bucketing, second phase (lazy)
     cudaStream_t upload_stream = nullptr;  // host-to-device row copies of pipelined runs (lazy)
     std::vector<cudaEvent_t> chunk_events; // "rows of chunk i are on the device"
+    // per-chunk events of the dtl solves, pooled for the life of the context (creating and
+    // destroying events per call showed up as multi-millisecond stalls): waves begin / end,
+    // chunk finished (timing enabled), results copied back (no timing)
+    std::vector<cudaEvent_t> dtl_ev_w0, dtl_ev_w1, dtl_ev_done, dtl_ev_copied;
+    // free device memory as last reported by the driver; refreshed only after a pool grew
+    size_t mem_free_cached = 0;
+    bool mem_dirty = true;
     std::string err;
     int sm_count = 148;
     int host_threads = 1;  // OpenMP threads of the host-side bucketing (see sr2_create)
@@ -157,6 +164,7 @@ int sr2_dev_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out);   // device
 int sr2_pin_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out);   // pinned host memory
 int sr2_host_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out);  // plain host scratch
 size_t sr2_dev_pooled(const sr2_ctx* ctx, int id);
+int sr2_mem_free(sr2_ctx* ctx, size_t* out_free);  // cudaMemGetInfo, cached until a pool grows
 void sr2_free_dtl(sr2_ctx* ctx);
 void sr2_free_super(sr2_ctx* ctx);
 

@@ -884,8 +884,11 @@ extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_
     p->index_base = index_base;
     memcpy(p->costs, costs, sizeof(p->costs));
 
-    size_t free_b = 0, total_b = 0;
-    SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t free_b = 0;
+    {
+        int rc_mem = sr2_mem_free(ctx, &free_b);
+        if (rc_mem) return rc_mem;
+    }
     for (int id = DP_S_LEFT; id <= DP_S_BEST; ++id) free_b += sr2_dev_pooled(ctx, id);
     free_b += sr2_dev_pooled(ctx, DP_ROWS_SLAB);
     size_t per_row = (size_t)ctx->pitch * 16 + 1;
@@ -1014,8 +1017,11 @@ int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_w
     size_t o_ways = add64(plan.ways), o_stride = add64(plan.stride), o_cnt = add64(plan.cnt),
            o_vf = add64(plan.var_first), o_rb = add64(plan.raw_base), o_noff = add64(p->rows.node_off);
 
-    size_t free_b = 0, total_b = 0;
-    SR2_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+    size_t free_b = 0;
+    {
+        int rc_mem = sr2_mem_free(ctx, &free_b);
+        if (rc_mem) return rc_mem;
+    }
     for (int id = DP_S_LEFT; id < DP_COUNT; ++id) free_b += sr2_dev_pooled(ctx, id);
     size_t need = (size_t)N * (4 * 8 + (size_t)W * 4 + (size_t)W * 128 + (size_t)S * 4) + (size_t)D * W * 4 * 5 +
                   (size_t)NS * ((size_t)ctx->pitch * 16 + 8) + (size_t)B * ((size_t)S * 4 + 16) + h32.size() * 4 +
