@@ -171,6 +171,10 @@ extern "C" void sr2_destroy(sr2_ctx* ctx) {
     if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     if (ctx->fill_stream) cudaStreamDestroy(ctx->fill_stream);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->part_stream[k]) cudaStreamDestroy(ctx->part_stream[k]);
+        for (cudaEvent_t e : ctx->part_events[k]) cudaEventDestroy(e);
+    }
     for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
     for (auto* list : {&ctx->dtl_ev_w0, &ctx->dtl_ev_w1, &ctx->dtl_ev_done, &ctx->dtl_ev_copied})
         for (cudaEvent_t e : *list) cudaEventDestroy(e);

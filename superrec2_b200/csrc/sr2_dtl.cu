@@ -31,6 +31,7 @@
 // ---------------------------------------------------------------------------
 // device-resident problem
 // ---------------------------------------------------------------------------
+#define SPARSE_MAXM_DEFAULT 64
 struct DtlCosts;
 struct Key32;
 struct DtlProblem {
@@ -55,6 +56,16 @@ struct DtlProblem {
     int32_t* cur_C = nullptr;
     uint32_t* d_mask = nullptr;      // [rows * pitch/32] root-path bit sets of the rows (flat2 only)
     uint32_t* cur_mask = nullptr;
+    // Row lists of every wave, kept with the upload (they depend on the trees, not on the costs):
+    // d_lists[0 * R + row] / d_lists[1 * R + row] = sparse / dense rows of the wave that starts at `row`
+    // (wave-local indices), d_counts[(chunk * 65536 + wave) * 2 + {0, 1}] = their lengths.
+    int* d_lists = nullptr;
+    int* d_counts = nullptr;
+    int cur_chunk = 0;
+    cudaEvent_t cur_part_event = nullptr;  // set by dtl_enqueue_chunk for the wave being launched
+    int64_t list_pitch = 0;          // = R
+    std::vector<char> partitioned;   // per chunk: lists and path sets are on the device
+    int sparse_maxm = SPARSE_MAXM_DEFAULT;
     int n_waves = 0, n_launch = 0;
     // wave launch configuration (fixed per upload)
     int spad = 0, wave_warps = 0;
@@ -74,7 +85,7 @@ struct DtlProblem {
     int flat2_rows = 8;
     int flat2_sh = 0, flat2_thresh = 0;
     void (*flat2_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
-                     Key32, uint32_t*, int, int, int) = nullptr;
+                     Key32, const uint32_t*, int, int, int, const int*, const int*) = nullptr;
     int flat2_pf_near = 0, flat2_pf_far = 0;
     int flat2_sparse_max = 0;        // rows with at most this many root-path species take the sparse cells path
 };
@@ -569,13 +580,16 @@ template <int NS>
 __global__ void __launch_bounds__(256, 4)
 dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                       int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
-                      uint32_t* __restrict__ tags, DtlCosts cs, Key32 kp, uint32_t* __restrict__ rowmask,
-                      int sparse_max, int pf_near, int pf_far) {
+                      uint32_t* __restrict__ tags, DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask,
+                      int sparse_max, int pf_near, int pf_far, const int* __restrict__ row_list,
+                      const int* __restrict__ list_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int pitch = sp.pitch, rs = sp.flat_rs, n_chunks = pitch >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int local = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (local >= n_rows) return;
+    int local = blockIdx.x * (blockDim.x >> 5) + warp;
+    // the rows of this launch: the wave's "dense" list written by dtl_partition_kernel
+    if (local >= *list_count) return;
+    local = row_list[local];
     const int64_t gr = row_begin + local;
     const size_t slot = (size_t)(gr - chunk_row0);
     uint2* Mrow = reinterpret_cast<uint2*>(smem_raw) + (size_t)warp * 2 * rs;
@@ -600,22 +614,18 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     // Pull the descriptors of a row far ahead into L2, and read those of a nearer row (prefetched by
     // an earlier CTA) to pull ITS child rows into L2; the prefetches are issued before the sweeps.
     int cl2 = -1, cr2 = -1;
-    if (pf_far > 0 && local + pf_far < n_rows && lane < 2)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"((lane ? row_cr : row_cl) + gr + pf_far));
-    if (pf_near > 0 && local + pf_near < n_rows) {
-        cl2 = row_cl[gr + pf_near];
-        cr2 = row_cr[gr + pf_near];
+    {
+        const int pos = blockIdx.x * (blockDim.x >> 5) + warp, n_list = *list_count;
+        if (pf_far > 0 && pos + pf_far < n_list && lane < 2)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"((lane ? row_cr : row_cl) + row_begin + row_list[pos + pf_far]));
+        if (pf_near > 0 && pos + pf_near < n_list) {
+            const int64_t g2 = row_begin + row_list[pos + pf_near];
+            cl2 = row_cl[g2];
+            cr2 = row_cr[g2];
+        }
     }
-    // the row's root-path bit set: one 32-species word per lane (lanes >= pitch / 32 hold 0)
-    unsigned mword = 0;
-    if (lane < n_chunks) {
-        const unsigned ml = cl >= 0 ? rowmask[(size_t)cl * n_chunks + lane]
-                                    : __ldg(sp.pathmask + (size_t)(-1 - cl) * n_chunks + lane);
-        const unsigned mr = cr >= 0 ? rowmask[(size_t)cr * n_chunks + lane]
-                                    : __ldg(sp.pathmask + (size_t)(-1 - cr) * n_chunks + lane);
-        mword = ml | mr;
-        rowmask[slot * n_chunks + lane] = mword;
-    }
+    // the row's root-path bit set (dtl_partition_kernel): one 32-species word per lane
+    const unsigned mword = lane < n_chunks ? rowmask[slot * n_chunks + lane] : 0u;
     // sweep schedule -> registers, as absolute shared-memory addresses of this warp's row
     // (the table is padded to NS steps with idle words)
     unsigned sw[NS];
@@ -740,6 +750,268 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
         if (j < n_chunks) cell(j * 32 + lane, meta[j]);
 }
 
+// ---------------------------------------------------------------------------
+// Sparse rows.  A cell can only be finite on the root path of a leaf species below its object node
+// (88 % of config #2's cells are infinite), so low rows of the object trees hold a few dozen live
+// cells out of |S|.  dtl_partition_kernel computes every row's root-path bit set and splits the wave
+// into rows with at most SPARSE_MAXM path species ("sparse") and the rest ("dense", flat2).
+// dtl_wave_sparse_kernel gives a sparse row 4 lanes instead of a warp and works on the path set only:
+//   elements   = the path species in BFS order (non-decreasing depth), position e in [0, m)
+//   Mc / Pc    = SUBMIN / SEPMIN (left key, right key) pairs per element, in shared memory
+//   up-sweep   = one step per depth, deepest first: atomicMin of an element into its parent's slot
+//   down-sweep = one step per depth from the top: P[e] = min(P[parent], M[sibling] if on a path)
+//   cells      = element-wise, the same candidates and packing as flat2
+// 8 rows per warp, 1.5 KB of shared memory per row instead of 6.8 KB: 4 x as many rows in flight
+// and every lane busy where the dense sweeps leave 90 % of the lanes idle.
+// ---------------------------------------------------------------------------
+#define SPARSE_MAXM 64
+#define SPARSE_ROW_WORDS 392  // shared-memory words per row: Mc 128, Pc 128, el 64, mk/ml/mr/pre 16 each, and
+                              // 8 words of padding: the 4 rows of a half-warp start 8 banks apart
+
+__global__ void __launch_bounds__(256)
+dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                     int64_t row_begin, int64_t chunk_row0, int n_rows, uint32_t* __restrict__ rowmask,
+                     int max_sparse, int* __restrict__ lists, int list_pitch, int* __restrict__ counts) {
+    __shared__ int cta_cnt[2], cta_base[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int local = blockIdx.x * 8 + warp;
+    const int mw = sp.mask_words;
+    if (threadIdx.x < 2) cta_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    int cls = -1, my_off = 0;
+    if (local < n_rows) {
+        const int64_t gr = row_begin + local;
+        const int cl = row_cl[gr], cr = row_cr[gr];
+        int cnt = 0;
+        for (int w = lane; w < mw; w += 32) {
+            const uint32_t a = cl >= 0 ? rowmask[(size_t)cl * mw + w] : __ldg(sp.pathmask + (size_t)(-1 - cl) * mw + w);
+            const uint32_t b = cr >= 0 ? rowmask[(size_t)cr * mw + w] : __ldg(sp.pathmask + (size_t)(-1 - cr) * mw + w);
+            rowmask[(size_t)(gr - chunk_row0) * mw + w] = a | b;
+            cnt += __popc(a | b);
+        }
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        cls = cnt <= max_sparse ? 0 : 1;
+        if (lane == 0) my_off = atomicAdd(&cta_cnt[cls], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) cta_base[threadIdx.x] = cta_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], cta_cnt[threadIdx.x]) : 0;
+    __syncthreads();
+    if (cls >= 0 && lane == 0) lists[(size_t)cls * list_pitch + cta_base[cls] + my_off] = local;
+}
+
+__global__ void __launch_bounds__(128)
+dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                       int64_t row_begin, int64_t chunk_row0, int32_t* __restrict__ T, uint32_t* __restrict__ tags,
+                       DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask, const int* __restrict__ row_list,
+                       const int* __restrict__ list_count) {
+    extern __shared__ uint32_t sp_smem[];  // [4 warps][8 rows][SPARSE_ROW_WORDS]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, sub = lane & 3;
+    const int n_list = *list_count;
+    const int first = (blockIdx.x * 4 + warp) * 8;
+    if (first >= n_list) return;
+    const bool valid = first + g < n_list;
+    const int pitch = sp.pitch, mw = sp.mask_words;
+    uint32_t* base = sp_smem + (size_t)(warp * 8 + g) * SPARSE_ROW_WORDS;
+    uint2* Mc = reinterpret_cast<uint2*>(base);
+    uint2* Pc = Mc + SPARSE_MAXM;
+    uint32_t* el = base + 256;   // species | depth << 16
+    uint32_t* mk = el + 64;      // union of the children's path sets
+    uint32_t* ml = mk + 16;      // the left / right child's own path set
+    uint32_t* mr = ml + 16;
+    uint32_t* pre = mr + 16;     // pre[w] = path species in words < w; pre[mw] = m
+    int64_t gr = 0;
+    size_t slot = 0;
+    int cl = -1, cr = -1, m = 0;
+    if (valid) {
+        gr = row_begin + row_list[first + g];
+        slot = (size_t)(gr - chunk_row0);
+        cl = row_cl[gr];
+        cr = row_cr[gr];
+        for (int w = sub; w < mw; w += 4) {
+            const uint32_t a = cl >= 0 ? rowmask[(size_t)cl * mw + w] : __ldg(sp.pathmask + (size_t)(-1 - cl) * mw + w);
+            const uint32_t b = cr >= 0 ? rowmask[(size_t)cr * mw + w] : __ldg(sp.pathmask + (size_t)(-1 - cr) * mw + w);
+            ml[w] = a;
+            mr[w] = b;
+            mk[w] = a | b;
+        }
+    }
+    __syncwarp();
+    if (valid && sub == 0) {
+        int run = 0;
+        for (int w = 0; w < mw; ++w) {
+            pre[w] = run;
+            run += __popc(mk[w]);
+        }
+        pre[mw] = run;
+    }
+    __syncwarp();
+    if (valid) m = (int)pre[mw];
+    // position of a species of the path set
+    auto pos_of = [&](int s) { return (int)pre[s >> 5] + __popc(mk[s >> 5] & ((1u << (s & 31)) - 1u)); };
+    auto on_path = [&](int s) { return (mk[s >> 5] >> (s & 31)) & 1u; };
+
+    // ---- elements: the path species in BFS order ------------------------------------------------------
+    {
+        int w = 0;
+        for (int e = sub; e < m; e += 4) {
+            while ((int)pre[w + 1] <= e) ++w;
+            const int s = w * 32 + (int)__fns(mk[w], 0, e - (int)pre[w] + 1);
+            const unsigned low = __ldg(sp.keylow_p + s);
+            el[e] = (unsigned)s | ((low & kp.dm) << 16);
+            // positions of the parent, the sibling and the two children inside the path set (0xff = not
+            // on a path); parked in Pc until the bit sets are no longer needed
+            const int par = s ? __ldg(sp.parent + s) : 0, c0 = __ldg(sp.child0 + s);
+            const int sib = s ? ((s & 1) ? s + 1 : s - 1) : 0;
+            unsigned link = (unsigned)pos_of(par);
+            link |= (s && on_path(sib) ? (unsigned)pos_of(sib) : 0xffu) << 8;
+            link |= (c0 >= 0 && on_path(c0) ? (unsigned)pos_of(c0) : 0xffu) << 16;
+            link |= (c0 >= 0 && on_path(c0 + 1) ? (unsigned)pos_of(c0 + 1) : 0xffu) << 24;
+            Pc[e].x = link;
+        }
+    }
+    // ---- child values -> keys; the gathers of four elements per lane are in flight together ----------
+    const unsigned vmul = 1u << kp.sh, infkey = 0xffffffffu << kp.sh;
+    for (int e0 = sub; e0 < m; e0 += 16) {
+        unsigned va[4], vb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = e0 + 4 * q;
+            va[q] = vb[q] = 0xffffffffu;  // "not on the child's paths": infinite
+            if (e < m) {
+                const int s = (int)(el[e] & 0xffffu);
+                const unsigned bit = 1u << (s & 31);
+                if (cl >= 0) {
+                    if (ml[s >> 5] & bit) va[q] = (unsigned)T[(size_t)cl * pitch + s];
+                } else if (s == -1 - cl) {
+                    va[q] = 0u;
+                }
+                if (cr >= 0) {
+                    if (mr[s >> 5] & bit) vb[q] = (unsigned)T[(size_t)cr * pitch + s];
+                } else if (s == -1 - cr) {
+                    vb[q] = 0u;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = e0 + 4 * q;
+            if (e < m) {
+                const int s = (int)(el[e] & 0xffffu);
+                const unsigned low = ((unsigned)s << kp.db) | (el[e] >> 16);
+                Mc[e] = make_uint2(va[q] == 0xffffffffu ? infkey + low : va[q] * vmul + low,
+                                   vb[q] == 0xffffffffu ? infkey + low : vb[q] * vmul + low);
+            }
+        }
+    }
+    __syncwarp();
+    uint32_t* lk = mk;  // [64] links, over mk / ml / mr / pre (dead from here on)
+    {
+        unsigned mine[SPARSE_MAXM / 4];
+#pragma unroll
+        for (int q = 0; q < SPARSE_MAXM / 4; ++q) mine[q] = sub + 4 * q < m ? Pc[sub + 4 * q].x : 0u;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < SPARSE_MAXM / 4; ++q)
+            if (sub + 4 * q < m) lk[sub + 4 * q] = mine[q];
+    }
+    // the infinite value rows of the warp's 8 rows, all lanes together (before any finite cell)
+    {
+        const uint4 inf4 = make_uint4(SR2_INF, SR2_INF, SR2_INF, SR2_INF);
+        for (int r = 0; r < 8; ++r) {
+            const unsigned long long row_slot = __shfl_sync(0xffffffffu, (unsigned long long)slot, r * 4);
+            const int row_ok = __shfl_sync(0xffffffffu, (int)valid, r * 4);
+            if (!row_ok) continue;
+            uint4* row4 = reinterpret_cast<uint4*>(T + (size_t)row_slot * pitch);
+            for (int i = lane; i < (pitch >> 2); i += 32) row4[i] = inf4;
+        }
+    }
+    __syncwarp();
+    const int D = sp.D;
+    // ---- up-sweep: SUBMIN, one step per depth, deepest first ---------------------------------------
+    {
+        int e = m > sub ? sub + ((m - 1 - sub) >> 2) * 4 : -1;  // my last element
+        for (int d = D - 1; d >= 1; --d) {
+            while (e >= 0 && (int)(el[e] >> 16) == d) {
+                const int pp = (int)(lk[e] & 0xffu);
+                const uint2 k = Mc[e];
+                atomicMin(&Mc[pp].x, k.x);
+                atomicMin(&Mc[pp].y, k.y);
+                e -= 4;
+            }
+            __syncwarp();
+        }
+    }
+    // ---- down-sweep: SEPMIN, one step per depth from the top -----------------------------------------
+    {
+        int e = sub;
+        if (valid && sub == 0) {
+            Pc[0] = make_uint2(0xffffffffu, 0xffffffffu);  // element 0 is the root: nothing is incomparable
+            e = 4;
+        }
+        __syncwarp();
+        for (int d = 1; d < D; ++d) {
+            while (e < m && (int)(el[e] >> 16) == d) {
+                const unsigned link = lk[e];
+                const int pp = (int)(link & 0xffu), sp_ = (int)((link >> 8) & 0xffu);
+                uint2 q = Pc[pp];
+                if (sp_ != 0xff) {  // the sibling (ranks 2i+1, 2i+2 are siblings) is on a path
+                    const uint2 ms = Mc[sp_];
+                    q.x = min(q.x, ms.x);
+                    q.y = min(q.y, ms.y);
+                }
+                Pc[e] = q;
+                e += 4;
+            }
+            __syncwarp();
+        }
+    }
+    // ---- cells: the path species only ---------------------------------------------------------------
+    if (!valid) return;
+    int32_t* __restrict__ Trow = T + slot * pitch;
+    uint32_t* __restrict__ Grow = tags + slot * pitch;
+    const int loss = cs.loss, db = kp.db, thresh = kp.thresh;
+    const unsigned dm = kp.dm, rm = kp.rm, hi_mul = 1u << (32 - kp.sh);
+    const int c12 = -2 * loss, c3 = cs.dup, c45 = cs.hgt;
+    for (int e = sub; e < m; e += 4) {
+        const int x = (int)(el[e] & 0xffffu), dx = (int)(el[e] >> 16);
+        const uint2 mm = Mc[e], pq = Pc[e];
+        uint4 k = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);  // (l0, r0, l1, r1)
+        const int p0 = (int)((lk[e] >> 16) & 0xffu), p1 = (int)(lk[e] >> 24);
+        if (p0 != 0xff) {
+            const uint2 t = Mc[p0];
+            k.x = t.x, k.y = t.y;
+        }
+        if (p1 != 0xff) {
+            const uint2 t = Mc[p1];
+            k.z = t.x, k.w = t.y;
+        }
+        const int nld = -loss * dx;
+        const int qMl = flat2_q(mm.x, hi_mul, dm, loss), qMr = flat2_q(mm.y, hi_mul, dm, loss);
+        const int ql0 = flat2_q(k.x, hi_mul, dm, loss), qr0 = flat2_q(k.y, hi_mul, dm, loss);
+        const int ql1 = flat2_q(k.z, hi_mul, dm, loss), qr1 = flat2_q(k.w, hi_mul, dm, loss);
+        const int pl = (int)__umulhi(pq.x, hi_mul), pr = (int)__umulhi(pq.y, hi_mul);
+        const int b12 = 2 * nld + c12, b3 = 2 * nld + c3, b45 = nld + c45;
+        const int w1 = flat2_pack(ql0 + qr1 + b12, 0);  // 1. speciation, left below x0, right below x1
+        const int w2 = flat2_pack(ql1 + qr0 + b12, 1);  // 2. the other way round
+        const int w3 = flat2_pack(qMl + qMr + b3, 2);   // 3. duplication
+        const int w4 = flat2_pack(pl + qMr + b45, 3);   // 4. transfer, left child away
+        const int w5 = flat2_pack(qMl + pr + b45, 4);   // 5. transfer, right child away
+        const int w = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
+        const int best = w >> 3, which = w & 7;
+        unsigned ka = mm.x, kb = mm.y;
+        ka = which == 0 ? k.x : ka;
+        ka = which == 1 ? k.z : ka;
+        ka = which == 3 ? pq.x : ka;
+        kb = which == 0 ? k.w : kb;
+        kb = which == 1 ? k.y : kb;
+        kb = which == 4 ? pq.y : kb;
+        const bool finite = best < thresh;
+        Trow[x] = finite ? best : SR2_INF;
+        Grow[x] = finite ? (((ka >> db) & rm) | (((kb >> db) & rm) << 16)) : SR2_NO_TAG;
+    }
+}
+
 // Root-path bit set of every row of a wave computed by a kernel that does not maintain it itself:
 // mask(row) = mask(left child) | mask(right child), a leaf child contributing its species' path.
 __global__ void dtl_rowmask_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
@@ -757,7 +1029,7 @@ __global__ void dtl_rowmask_kernel(DevSpecies sp, const int32_t* __restrict__ ro
 
 // the instantiation whose register-resident schedule is the shortest that holds n_steps
 typedef void (*Flat2Fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*,
-                        DtlCosts, Key32, uint32_t*, int, int, int);
+                        DtlCosts, Key32, const uint32_t*, int, int, int, const int*, const int*);
 static Flat2Fn flat2_pick(int n_steps) {
     if (n_steps <= 12) return dtl_wave_flat2_kernel<12>;
     if (n_steps <= 16) return dtl_wave_flat2_kernel<16>;
@@ -955,6 +1227,12 @@ static int dtl_prepare(void* user) {
     }
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_MASK, table_elems / 32 * sizeof(uint32_t) + 256, &ptr))) return rc;
     p->d_mask = (uint32_t*)ptr;
+    p->list_pitch = std::max<int64_t>(p->rows.R, 1);
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_LISTS, (size_t)2 * p->list_pitch * sizeof(int), &ptr))) return rc;
+    p->d_lists = (int*)ptr;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_COUNTS, p->rows.chunks.size() * 2 * 65536 * sizeof(int), &ptr))) return rc;
+    p->d_counts = (int*)ptr;
+    p->partitioned.assign(p->rows.chunks.size(), 0);
     for (auto* list : {&ctx->dtl_ev_w0, &ctx->dtl_ev_w1, &ctx->dtl_ev_done})
         while (list->size() < p->rows.chunks.size()) {
             cudaEvent_t e;
@@ -1119,6 +1397,10 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
             // ceil(m / 32) sparse passes cost about as much as 2 dense chunks each (locating a lane's species)
             p->flat2_sparse_max = std::min(S, ctx->pitch / 4);
             if (const char* sm = getenv("SR2_FLAT2_SPARSE_MAX")) p->flat2_sparse_max = atoi(sm);
+            p->sparse_maxm = ctx->dsp.mask_words <= 15 ? SPARSE_MAXM : 0;
+            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)(4 * 8 * SPARSE_ROW_WORDS * sizeof(uint32_t))));
+            if (const char* sm = getenv("SR2_SPARSE_MAXM")) p->sparse_maxm = std::min(atoi(sm), SPARSE_MAXM);
             const int resident = 8 * 4 * ctx->sm_count;  // rows of the CTAs that run at one time
             p->flat2_pf_near = resident;
             p->flat2_pf_far = 3 * resident;
@@ -1139,14 +1421,14 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
     if (h == 1 && ctx->dsp.anc_tab && !getenv("SR2_DTL_DENSE_CHERRIES")) {
         dtl_cherry_sparse_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, p->cur_stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, cs,
-            p->cur_mask);
+            nullptr);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
     if (h == 1) {  // both children of a height-1 node are leaves
         dtl_cherry_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, p->cur_stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
-            p->cur_mask);
+            nullptr);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
@@ -1158,20 +1440,22 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         kp.dm = (1u << p->depth_bits) - 1;
         kp.inf32 = 1u << (32 - kp.sh - 1);
         kp.thresh = p->flat2_thresh;
+        // path sets + the wave's sparse / dense row lists, then one launch per list (grids sized for
+        // the whole wave: CTAs beyond a list's length return at once)
+        int* counts = p->d_counts + ((size_t)p->cur_chunk * 65536 + h) * 2;
+        int* lists = p->d_lists + row_begin;
+        if (p->cur_part_event) SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, p->cur_part_event, 0));
+        if (p->sparse_maxm > 0)
+            dtl_wave_sparse_kernel<<<(unsigned)((n_rows + 31) / 32), 128, 4 * 8 * SPARSE_ROW_WORDS * sizeof(uint32_t),
+                                     p->cur_stream>>>(
+                ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
+                p->cur_mask, lists, counts);
         p->flat2_fn<<<(unsigned)((n_rows + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem,
                       p->cur_stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
-            p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far);
+            p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + p->list_pitch, counts + 1);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
-    }
-    // every other wave kernel leaves the row masks to dtl_rowmask_kernel (the flat2 kernel of a
-    // later wave reads its children's masks)
-    if (p->flat2 && p->cur_mask) {
-        const int64_t words = n_rows * ctx->dsp.mask_words;
-        dtl_rowmask_kernel<<<(unsigned)((words + 255) / 256), 256, 0, p->cur_stream>>>(
-            ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_mask);
-        SR2_CUDA(ctx, cudaGetLastError());
     }
     if (p->flat && n_rows >= p->simd_min_rows) {
         Key32 kp;
@@ -1219,15 +1503,67 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     p->cur_tag = p->d_tag + set * table_elems;
     p->cur_C = p->d_C ? p->d_C + set * table_elems : nullptr;
     p->cur_mask = p->d_mask + set * (table_elems / 32);
+    p->cur_chunk = ci;
+    // the path sets live in the table set: they survive between solves only if no other chunk used it
+    if (p->rows.chunks.size() > 1) p->partitioned[ci] = 0;
     cudaStream_t st = p->cur_stream;
     const RowChunk& c = p->rows.chunks[ci];
     if (p->wait_rows) SR2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->chunk_events[ci], 0));  // its rows' H2D copies
     DtlCosts cs{p->costs[0], p->costs[1], p->costs[2], p->costs[3]};
     const int H = (int)c.wave_off.size() - 2;  // highest wave
+    // Path sets and sparse / dense row lists of every wave do not depend on DP values: they are
+    // computed on a side stream, wave after wave, ahead of the wave kernels, which wait for the
+    // event of their wave.  They stay valid for later solves of the same upload.
+    const bool chain = p->flat2 && !p->partitioned[ci];
+    cudaEvent_t chain_tail = nullptr;
+    std::vector<cudaEvent_t>& part_events = ctx->part_events[set];
+    if (chain) {
+        if (!ctx->part_stream[set]) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->part_stream[set], cudaStreamNonBlocking));
+        cudaStream_t ps = ctx->part_stream[set];
+        if (p->wait_rows) SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->chunk_events[ci], 0));
+        // the table set's path sets may still be read by the chunk that used the set before
+        if (ci >= (p->two_streams ? 2 : 1)) SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->dtl_ev_done[ci - (p->two_streams ? 2 : 1)], 0));
+        SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w0[ci], st));   // also orders the side stream after earlier
+        SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->dtl_ev_w0[ci], 0));  // work of this stream (uploads, solves)
+        SR2_CUDA(ctx, cudaMemsetAsync(p->d_counts + (size_t)ci * 2 * 65536, 0, (size_t)2 * (H + 2) * sizeof(int), ps));
+        size_t k = 0;
+        for (int h = 1; h <= H; ++h) {
+            int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+            if (n <= 0) continue;
+            const bool listed = h > 1 && n >= p->simd_min_rows;
+            if (listed) {
+                dtl_partition_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ps>>>(
+                    ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask,
+                    p->sparse_maxm, p->d_lists + c.wave_off[h], (int)p->list_pitch,
+                    p->d_counts + ((size_t)ci * 65536 + h) * 2);
+                if (part_events.size() <= k) {
+                    cudaEvent_t e;
+                    SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                    part_events.push_back(e);
+                }
+                SR2_CUDA(ctx, cudaEventRecord(part_events[k++], ps));
+            } else {
+                const int64_t words = n * ctx->dsp.mask_words;
+                dtl_rowmask_kernel<<<(unsigned)((words + 255) / 256), 256, 0, ps>>>(
+                    ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask);
+            }
+        }
+        // the chain's tail (path sets of the small top waves) joins the chunk's stream before it ends
+        if (part_events.size() <= k) {
+            cudaEvent_t e;
+            SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            part_events.push_back(e);
+        }
+        SR2_CUDA(ctx, cudaEventRecord(part_events[k], ps));
+        chain_tail = part_events[k];
+        SR2_CUDA(ctx, cudaGetLastError());
+    }
     SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w0[ci], st));
+    size_t part_k = 0;
     for (int h = 1; h <= H; ++h) {
         int64_t n = c.wave_off[h + 1] - c.wave_off[h];
         if (n <= 0) continue;
+        p->cur_part_event = (chain && h > 1 && n >= p->simd_min_rows) ? part_events[part_k++] : nullptr;
         int rc = dtl_launch_wave(ctx, p, c, h, c.wave_off[h], n, cs);
         if (rc) return rc;
         ++p->n_waves;
@@ -1259,7 +1595,9 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         ++p->n_launch;
     }
     SR2_CUDA(ctx, cudaGetLastError());
+    if (chain_tail) SR2_CUDA(ctx, cudaStreamWaitEvent(st, chain_tail, 0));
     SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_done[ci], st));
+    p->partitioned[ci] = 1;
     return SR2_OK;
 }
 

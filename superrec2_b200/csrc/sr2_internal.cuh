@@ -112,7 +112,7 @@ struct Sr2Pool {
 };
 enum Sr2DevPool {
     DP_ROWS_SLAB, DP_ROOT_ROW, DP_ROOT_NODE, DP_NODE_PRE, DP_NODE_INST,
-    DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MINCOST, DP_DTL_ROOTSP, DP_DTL_MAP, DP_DTL_MASK,
+    DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MINCOST, DP_DTL_ROOTSP, DP_DTL_MAP, DP_DTL_MASK, DP_DTL_LISTS, DP_DTL_COUNTS,
     DP_S_LEFT, DP_S_RIGHT, DP_S_NODEOFF, DP_S_BITS, DP_S_PRESENT, DP_S_OUTSIDE, DP_S_GAIN, DP_S_L, DP_S_FLAGS,
     DP_S_T, DP_S_TAG, DP_S_DEC, DP_S_ANC, DP_S_TAU, DP_S_TAUMIN, DP_S_COST, DP_S_MINCOST, DP_S_ROOTSP, DP_S_MAP,
     DP_S_KIND, DP_S_SYN, DP_S_BEST, DP_S_ALLOWED,
@@ -129,6 +129,8 @@ struct sr2_ctx {
     cudaStream_t copy_stream = nullptr;    // device-to-host result copies of pipelined runs (lazy)
     cudaStream_t stream2 = nullptr;        // second compute stream of pipelined runs (lazy)
     cudaStream_t fill_stream = nullptr;    // device-side bucketing, second phase (lazy)
+    cudaStream_t part_stream[2] = {nullptr, nullptr};  // path sets / row lists of the waves, ahead of the waves
+    std::vector<cudaEvent_t> part_events[2];           // "lists of wave k are ready", per table set
     cudaStream_t upload_stream = nullptr;  // host-to-device row copies of pipelined runs (lazy)
     std::vector<cudaEvent_t> chunk_events; // "rows of chunk i are on the device"
     // per-chunk events of the dtl solves, pooled for the life of the context (creating and
