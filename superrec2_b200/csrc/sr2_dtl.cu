@@ -86,7 +86,7 @@ struct DtlProblem {
     int flat2_sh = 0, flat2_thresh = 0;
     void (*flat2_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
                      Key32, const uint32_t*, int, int, int, const int*, const int*) = nullptr;
-    int flat2_pf_near = 0, flat2_pf_far = 0;
+    int flat2_pf_near = 0, flat2_pf_far = 0, sparse_pf_near = 0, sparse_pf_far = 0;
     int flat2_sparse_max = 0;        // rows with at most this many root-path species take the sparse cells path
 };
 
@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(128)
 dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                        int64_t row_begin, int64_t chunk_row0, int32_t* __restrict__ T, uint32_t* __restrict__ tags,
                        DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask, const int* __restrict__ row_list,
-                       const int* __restrict__ list_count) {
+                       const int* __restrict__ list_count, int pf_near, int pf_far) {
     extern __shared__ uint32_t sp_smem[];  // [4 warps][8 rows][SPARSE_ROW_WORDS]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, sub = lane & 3;
@@ -816,10 +816,8 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     uint2* Mc = reinterpret_cast<uint2*>(base);
     uint2* Pc = Mc + SPARSE_MAXM;
     uint32_t* el = base + 256;   // species | depth << 16
-    uint32_t* mk = el + 64;      // union of the children's path sets
-    uint32_t* ml = mk + 16;      // the left / right child's own path set
-    uint32_t* mr = ml + 16;
-    uint32_t* pre = mr + 16;     // pre[w] = path species in words < w; pre[mw] = m
+    uint32_t* mk = el + 64;      // the row's path set
+    uint32_t* pre = mk + 48;     // pre[w] = path species in words < w; pre[mw] = m
     int64_t gr = 0;
     size_t slot = 0;
     int cl = -1, cr = -1, m = 0;
@@ -828,14 +826,16 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         slot = (size_t)(gr - chunk_row0);
         cl = row_cl[gr];
         cr = row_cr[gr];
-        for (int w = sub; w < mw; w += 4) {
-            const uint32_t a = cl >= 0 ? rowmask[(size_t)cl * mw + w] : __ldg(sp.pathmask + (size_t)(-1 - cl) * mw + w);
-            const uint32_t b = cr >= 0 ? rowmask[(size_t)cr * mw + w] : __ldg(sp.pathmask + (size_t)(-1 - cr) * mw + w);
-            ml[w] = a;
-            mr[w] = b;
-            mk[w] = a | b;
-        }
+        // the row's own path set (dtl_partition_kernel); the children's rows are infinite outside
+        // their own sets, so their values are simply gathered at every species of this set
+        for (int w = sub; w < mw; w += 4) mk[w] = rowmask[slot * mw + w];
     }
+    // latency: list entry -> descriptors / path set -> child values are three dependent DRAM trips.
+    // Rows further down the list are pulled into L2 ahead of the CTAs that will work on them: the
+    // descriptors and path set of a far row, the child rows of a nearer one.
+    int r_far = -1, r_near = -1;
+    if (first + g + pf_far < n_list && pf_far > 0) r_far = row_list[first + g + pf_far];
+    if (first + g + pf_near < n_list && pf_near > 0) r_near = row_list[first + g + pf_near];
     __syncwarp();
     if (valid && sub == 0) {
         int run = 0;
@@ -870,6 +870,17 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             Pc[e].x = link;
         }
     }
+    int cl_near = -1, cr_near = -1;
+    if (r_near >= 0) {
+        cl_near = row_cl[row_begin + r_near];
+        cr_near = row_cr[row_begin + r_near];
+    }
+    if (r_far >= 0) {
+        const int64_t g_far = row_begin + r_far;
+        if (sub == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(row_cl + g_far));
+        if (sub == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(row_cr + g_far));
+        if (sub == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowmask + (size_t)(g_far - chunk_row0) * mw));
+    }
     // ---- child values -> keys; the gathers of four elements per lane are in flight together ----------
     const unsigned vmul = 1u << kp.sh, infkey = 0xffffffffu << kp.sh;
     for (int e0 = sub; e0 < m; e0 += 16) {
@@ -880,17 +891,14 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             va[q] = vb[q] = 0xffffffffu;  // "not on the child's paths": infinite
             if (e < m) {
                 const int s = (int)(el[e] & 0xffffu);
-                const unsigned bit = 1u << (s & 31);
-                if (cl >= 0) {
-                    if (ml[s >> 5] & bit) va[q] = (unsigned)T[(size_t)cl * pitch + s];
-                } else if (s == -1 - cl) {
+                if (cl >= 0)
+                    va[q] = (unsigned)T[(size_t)cl * pitch + s];
+                else if (s == -1 - cl)
                     va[q] = 0u;
-                }
-                if (cr >= 0) {
-                    if (mr[s >> 5] & bit) vb[q] = (unsigned)T[(size_t)cr * pitch + s];
-                } else if (s == -1 - cr) {
+                if (cr >= 0)
+                    vb[q] = (unsigned)T[(size_t)cr * pitch + s];
+                else if (s == -1 - cr)
                     vb[q] = 0u;
-                }
             }
         }
 #pragma unroll
@@ -899,6 +907,7 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             if (e < m) {
                 const int s = (int)(el[e] & 0xffffu);
                 const unsigned low = ((unsigned)s << kp.db) | (el[e] >> 16);
+                // a stored infinity (0x3fffffff) wraps to the all-ones value field, like the sentinel
                 Mc[e] = make_uint2(va[q] == 0xffffffffu ? infkey + low : va[q] * vmul + low,
                                    vb[q] == 0xffffffffu ? infkey + low : vb[q] * vmul + low);
             }
@@ -965,6 +974,10 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             }
             __syncwarp();
         }
+    }
+    for (int line = sub; line * 32 < pitch; line += 4) {  // 128-byte lines of the two child rows
+        if (cl_near >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cl_near * pitch + line * 32));
+        if (cr_near >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cr_near * pitch + line * 32));
     }
     // ---- cells: the path species only ---------------------------------------------------------------
     if (!valid) return;
@@ -1404,6 +1417,13 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
             const int resident = 8 * 4 * ctx->sm_count;  // rows of the CTAs that run at one time
             p->flat2_pf_near = resident;
             p->flat2_pf_far = 3 * resident;
+            const int sparse_resident = 32 * 4 * ctx->sm_count;  // rows of the sparse kernel's resident CTAs
+            p->sparse_pf_near = sparse_resident / 2;   // measured: 8.07 / 7.80 / 8.09 ms per step for 0 / 0.5 / 1 x resident
+            p->sparse_pf_far = 3 * p->sparse_pf_near;
+            if (const char* pf = getenv("SR2_SPARSE_PREFETCH")) {
+                p->sparse_pf_near = atoi(pf) * sparse_resident / 4;
+                p->sparse_pf_far = 3 * p->sparse_pf_near;
+            }
             if (const char* pf = getenv("SR2_FLAT2_PREFETCH")) {
                 p->flat2_pf_near = atoi(pf) * resident / 4;
                 p->flat2_pf_far = 3 * p->flat2_pf_near;
@@ -1449,7 +1469,7 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             dtl_wave_sparse_kernel<<<(unsigned)((n_rows + 31) / 32), 128, 4 * 8 * SPARSE_ROW_WORDS * sizeof(uint32_t),
                                      p->cur_stream>>>(
                 ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
-                p->cur_mask, lists, counts);
+                p->cur_mask, lists, counts, p->sparse_pf_near, p->sparse_pf_far);
         p->flat2_fn<<<(unsigned)((n_rows + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem,
                       p->cur_stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
