@@ -273,16 +273,16 @@ def main():
         peak, peak_src = measured_peak()
         achieved = cells * args.steps * BYTES_PER_CELL / (wave_ms * 1e-3) / 1e9
         # DRAM traffic per wave launch, from the ncu --set full captures under profiles/
-        # (r1y: dtl_wave_flat2_kernel 2.59 GB read + 2.24 GB written for 1,000,032 rows of 399 species =
-        #  12.1 B/cell -- tags are only written for the cells on a row's root paths; the wave-1 sparse
-        #  cherry kernel writes the value row only, 4.2 B/cell), scaled to this batch's rows
+        # (r2d: dtl_wave_sparse_kernel 1.93 GB read + 2.19 GB written for 1,000,032 rows of 399 species =
+        #  10.3 B/cell; r1y: dtl_wave_flat2_kernel 12.1 B/cell; the wave-1 sparse cherry kernel writes the
+        #  value row only, 4.2 B/cell), scaled to this batch's rows (3/4 of the other rows are sparse)
         internal = batch.left >= 0
         safe_l = np.where(internal, batch.left, 0) + np.repeat(batch.node_off[:-1], np.diff(batch.node_off))
         safe_r = np.where(internal, batch.right, 0) + np.repeat(batch.node_off[:-1], np.diff(batch.node_off))
         cherry = internal & ~internal[safe_l] & ~internal[safe_r]
         n_cherry, n_other = int(cherry.sum()), int(internal.sum() - cherry.sum())
         waves_per_step = max(1, ctx.timing().n_waves)
-        traffic = (n_other * batch.n_species * 12.1 + n_cherry * batch.n_species * 4.2) / waves_per_step
+        traffic = (n_other * batch.n_species * (0.74 * 10.3 + 0.26 * 12.1) + n_cherry * batch.n_species * 4.2) / waves_per_step
         line = {
             "metric": "dp_cells_per_s",
             "value": all_cells * args.steps / (elapsed_ms * 1e-3),
@@ -316,7 +316,8 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "dtl wave kernels: dtl_wave_flat2_kernel (87 % of the step) + "
+                         "kernel": "dtl wave kernels: dtl_wave_sparse_kernel (rows with <= 64 root-path species, 53 % "
+                                   "of the step), dtl_wave_flat2_kernel (the other rows, 33 %), "
                                    "dtl_cherry_sparse_kernel (wave 1, 6 %)",
                          "peak_source": peak_src,
                          "bytes_per_cell": BYTES_PER_CELL,
@@ -324,7 +325,7 @@ def main():
                          "wave_launches_per_step": waves_per_step,
                          "wave_ms_per_step": wave_ms / args.steps,
                          "traffic_source": "bytes per wave launch (average over the step's launches) from "
-                                           "ncu dram__bytes_read+write per row, profiles/r1y_flat2_ncu_details.csv"},
+                                           "ncu dram__bytes_read+write per row, profiles/r2d_sparse_ncu_details.csv, r1y_flat2_ncu_details.csv"},
             "checksum_min_costs": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
