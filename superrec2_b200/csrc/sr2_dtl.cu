@@ -914,16 +914,8 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         }
     }
     __syncwarp();
-    uint32_t* lk = mk;  // [64] links, over mk / ml / mr / pre (dead from here on)
-    {
-        unsigned mine[SPARSE_MAXM / 4];
-#pragma unroll
-        for (int q = 0; q < SPARSE_MAXM / 4; ++q) mine[q] = sub + 4 * q < m ? Pc[sub + 4 * q].x : 0u;
-        __syncwarp();
-#pragma unroll
-        for (int q = 0; q < SPARSE_MAXM / 4; ++q)
-            if (sub + 4 * q < m) lk[sub + 4 * q] = mine[q];
-    }
+    uint32_t* lk = mk;  // [64] links, over the bit set and its prefix counts (dead from here on)
+    for (int e = sub; e < m; e += 4) lk[e] = Pc[e].x;
     // the infinite value rows of the warp's 8 rows, all lanes together (before any finite cell)
     {
         const uint4 inf4 = make_uint4(SR2_INF, SR2_INF, SR2_INF, SR2_INF);
