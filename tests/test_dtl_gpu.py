@@ -162,6 +162,7 @@ def test_bad_input_is_rejected(ctx):
     (33, 50, 19, (0, 2, 1, 3, 1)),
     (100, 130, 5, (0, 0, 0, 0, 0)),
     (200, 210, 3, (0, 1, 1, 1, 1)),
+    (240, 250, 2, (0, 1, 2, 1, 1)),   # 479 species: the largest pitch (480) the batched kernels take
 ])
 @pytest.mark.parametrize("variant", ["flat2", "flat2-dense-cells", "flat"])
 def test_batched_wave_kernels_against_oracle(ctx, monkeypatch, n_s, n_o, n_trees, costs, variant):
@@ -297,3 +298,42 @@ def test_full_size_batch_pipelined_run_equals_stepwise(ctx):
     empty = ctx.dtl_run(np.zeros(1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.int32),
                         np.zeros(0, np.int32), batch.costs)
     assert all(len(part) == 0 for part in empty)
+
+
+def _caterpillar_species(n_leaves):
+    """A maximally unbalanced species tree in level-order numbering: node 2k is internal with
+    children 2k+1 (a leaf) and 2k+2."""
+    size = 2 * n_leaves - 1
+    parent = np.full(size, -1, np.int32)
+    child0 = np.full(size, -1, np.int32)
+    child1 = np.full(size, -1, np.int32)
+    for k in range(n_leaves - 1):
+        child0[2 * k], child1[2 * k] = 2 * k + 1, 2 * k + 2
+        parent[2 * k + 1] = parent[2 * k + 2] = 2 * k
+    return parent, child0, child1
+
+
+@pytest.mark.parametrize("n_species_leaves", [40, 120])
+def test_deep_species_tree_against_oracle(ctx, monkeypatch, n_species_leaves):
+    """A caterpillar species tree (depth = leaves - 1): more levels than the flat2 schedule holds
+    (the generic wave kernels take over), long root paths in the sparse cherry kernel and ancestor
+    table.  Every cell and tag against the oracle."""
+    monkeypatch.setenv("SR2_DTL_SIMD_MIN_ROWS", "1")
+    parent, child0, child1 = _caterpillar_species(n_species_leaves)
+    base = synth.make_batch(n_species_leaves, n_species_leaves + 12, 6, seed=5)
+    leaves = np.flatnonzero(child0 < 0).astype(np.int32)
+    rng = np.random.default_rng(3)
+    leaf_species = np.where(base.left < 0, leaves[rng.integers(0, len(leaves), len(base.left))], -1).astype(np.int32)
+    ctx.set_species(parent, child0, child1)
+    costs = np.asarray([0, 2, 3, 1, 1], np.int32)
+    min_cost, root, mapping = ctx.dtl_run(base.node_off, base.left, base.right, leaf_species, costs,
+                                          flags=_lib.SR2_KEEP_TABLES)
+    for b in range(base.n_instances):
+        lo, hi = int(base.node_off[b]), int(base.node_off[b + 1])
+        ref = oracle.dtl(parent, child0, child1, base.left[lo:hi], base.right[lo:hi], leaf_species[lo:hi], costs,
+                         strict=False)
+        value, tag = ctx.dtl_tables(b, hi - lo)
+        assert (value == ref["value"]).all()
+        assert (tag == ref["tag"]).all()
+        assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"]
+        assert (mapping[lo:hi] == ref["mapping"]).all()
