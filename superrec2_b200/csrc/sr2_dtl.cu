@@ -1457,6 +1457,7 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         int* counts = p->d_counts + ((size_t)p->cur_chunk * 65536 + h) * 2;
         int* lists = p->d_lists + row_begin;
         if (p->cur_part_event) SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, p->cur_part_event, 0));
+        if (p->sparse_maxm > 0) ++p->n_launch;  // two launches for this wave (the caller counts one)
         if (p->sparse_maxm > 0)
             dtl_wave_sparse_kernel<<<(unsigned)((n_rows + 31) / 32), 128, 4 * 8 * SPARSE_ROW_WORDS * sizeof(uint32_t),
                                      p->cur_stream>>>(
@@ -1554,10 +1555,12 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
                     part_events.push_back(e);
                 }
                 SR2_CUDA(ctx, cudaEventRecord(part_events[k++], ps));
+                ++p->n_launch;
             } else {
                 const int64_t words = n * ctx->dsp.mask_words;
                 dtl_rowmask_kernel<<<(unsigned)((words + 255) / 256), 256, 0, ps>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask);
+                ++p->n_launch;
             }
         }
         // the chain's tail (path sets of the small top waves) joins the chunk's stream before it ends
