@@ -22,6 +22,8 @@ Fixtures:
   crispr.json.gz           data/crispr-class1.in.json (superdtl, default costs)
   binarize.json.gz         enumeration order of ReconciliationInput.binarize()
   thl_all.json.gz          dtl instances with the full RetentionPolicy.ALL solution set
+  thl_internal_species.json.gz, superdtl_internal_species.json.gz
+                           instances whose object leaves sit at internal species nodes, full tables
   base_uspfs.json.gz       binary instances solved by usreconcile_base_uspfs (superdtl table
                            restricted to the LCA mapping) and by reconcile_lca, incl. the
                            instances of tests/compute/test_unordered_super_reconciliation.py
@@ -399,6 +401,25 @@ def main():
         if len(fixture.get("solutions", ())) <= 3000:
             every.append(fixture)
     write("thl_all.json.gz", every)
+
+    # ---- object leaves mapped to INTERNAL species nodes (allowed: the leaf map takes any named node) ----
+    rng4 = random.Random(20261022)
+    inner_thl, inner_super = [], []
+    for i in range(90):
+        n_s = rng4.randint(2, 7)
+        n_o = rng4.randint(2, 9)
+        mode = ["default", "zero", "spe", "random"][i % 4]
+        data = random_instance(rng4, n_s, n_o, False, mode, families=rng4.randint(1, 5) if i % 3 == 0 else 0)
+        internal_names = [f"s{k}" for k in range(n_s - 1)]
+        for leaf in list(data["leaf_object_species"]):
+            if rng4.random() < 0.4:
+                data["leaf_object_species"][leaf] = rng4.choice(internal_names)
+        if "leaf_syntenies" in data:
+            inner_super.append(superdtl_fixture(data, True))
+        else:
+            inner_thl.append(thl_fixture(data, True))
+    write("thl_internal_species.json.gz", inner_thl)
+    write("superdtl_internal_species.json.gz", inner_super)
 
 
 if __name__ == "__main__":

@@ -299,7 +299,7 @@ dtl_cherry_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32
 // Wave 1, sparse form.  A cherry's row is infinite except on the two root paths of its leaf
 // species a and b (at most 2 x depth cells of |S|):
 //   x above both (depth d <= depth of lca(a, b)):  duplication  dup + loss (da + db - 2d),
-//                                                   at the lca itself (a != b) the speciation
+//                                                   at the lca itself (if neither a nor b) the speciation
 //                                                   loss (da + db - 2d - 2), offered first
 //   x above a only:  right child transferred        hgt + loss (da - d)
 //   x above b only:  left child transferred         hgt + loss (db - d)
@@ -335,15 +335,24 @@ dtl_cherry_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, cons
         common += __popc(__ballot_sync(0xffffffffu, eq));
     }
     __syncwarp();  // the infinite row is written before its finite cells
+    // dl = depth of lca(a, b).  "Leaf species" may be internal nodes of the species tree (the
+    // reference maps leaves to any named node), so one of a, b can be the lca itself: then there is
+    // no speciation (both children must sit strictly below x) and no transfer below the lca on the
+    // other one's path (the species left behind would be an ancestor of x, not separated from it).
+    const int dl = common - 1;
+    const bool a_below = da > dl, b_below = db > dl;
     for (int d = lane; d <= da; d += 32) {
         int v;
-        if (d < common)
-            v = (d == common - 1 && a != b) ? cs.loss * (da + db - 2 * d - 2) : cs.dup + cs.loss * (da + db - 2 * d);
-        else
+        if (d <= dl)
+            v = (d == dl && a_below && b_below) ? cs.loss * (da + db - 2 * d - 2) : cs.dup + cs.loss * (da + db - 2 * d);
+        else if (b_below)
             v = cs.hgt + cs.loss * (da - d);
+        else
+            continue;
         Tout[pa[d]] = v;
     }
-    for (int d = common + lane; d <= db; d += 32) Tout[pb[d]] = cs.hgt + cs.loss * (db - d);
+    if (a_below)
+        for (int d = common + lane; d <= db; d += 32) Tout[pb[d]] = cs.hgt + cs.loss * (db - d);
 }
 
 // ---------------------------------------------------------------------------

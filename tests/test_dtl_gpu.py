@@ -31,7 +31,8 @@ def _gpu_tables(ctx, flat):
 
 def test_golden_small_tables(ctx, golden):
     """Cell by cell (value and tag) against the reference's own tables."""
-    for fixture in golden("thl_small.json.gz") + golden("thl_reference_tests.json.gz"):
+    for fixture in (golden("thl_small.json.gz") + golden("thl_reference_tests.json.gz") +
+                    golden("thl_internal_species.json.gz")):
         flat = FlatDtl(fixture["input"])
         min_cost, root, mapping, value, tag = _gpu_tables(ctx, flat)
         assert flat.table_by_name(value, tag) == fixture["table"]
@@ -175,6 +176,13 @@ def test_batched_wave_kernels_against_oracle(ctx, monkeypatch, n_s, n_o, n_trees
     if variant.endswith("dense-cells"):
         monkeypatch.setenv("SR2_FLAT2_SPARSE_MAX", "0")
     batch = synth.make_batch(n_s, n_o, n_trees, seed=31 + n_s, costs=costs)
+    if n_s in (9, 33, 240):
+        # the leaf map may name ANY species node: put a third of the object leaves at random
+        # (mostly internal) species
+        rng = np.random.default_rng(n_s)
+        leaves = np.flatnonzero(batch.left < 0)
+        moved = leaves[rng.random(len(leaves)) < 0.33]
+        batch.leaf_species[moved] = rng.integers(0, batch.n_species, len(moved))
     ctx.set_species(batch.parent, batch.child0, batch.child1)
     min_cost, root, mapping = ctx.dtl_run(batch.node_off, batch.left, batch.right,
                                           batch.leaf_species, batch.costs, flags=_lib.SR2_KEEP_TABLES)
@@ -337,3 +345,38 @@ def test_deep_species_tree_against_oracle(ctx, monkeypatch, n_species_leaves):
         assert (tag == ref["tag"]).all()
         assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"]
         assert (mapping[lo:hi] == ref["mapping"]).all()
+
+
+def test_device_bucketing_ragged_batch_with_single_leaf_trees(ctx, monkeypatch):
+    """More than 1024 instances of different sizes, one-node trees included: the pipelined run
+    (device-side bucketing, chunks, both compute streams) against the oracle, tree by tree."""
+    parts = [synth.make_batch(3, n_o, 400, seed=60 + n_o) for n_o in (3, 4, 6, 9)]
+    species = parts[0]
+    lefts, rights, leaves, sizes = [], [], [], []
+    rng = np.random.default_rng(1)
+    species_leaves = np.flatnonzero(species.child0 < 0).astype(np.int32)
+    for k in range(1600 + 300):
+        if k % 6 == 5:  # a one-node tree
+            lefts.append(np.array([-1], np.int32))
+            rights.append(np.array([-1], np.int32))
+            leaves.append(species_leaves[rng.integers(0, len(species_leaves), 1)])
+            sizes.append(1)
+            continue
+        part = parts[k % 4]
+        left, right, leaf = part.instance(k % 400)
+        lefts.append(left)
+        rights.append(right)
+        leaves.append(leaf)
+        sizes.append(len(left))
+    node_off = np.zeros(len(sizes) + 1, np.int64)
+    np.cumsum(sizes, out=node_off[1:])
+    left, right, leaf = np.concatenate(lefts), np.concatenate(rights), np.concatenate(leaves)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    monkeypatch.setenv("SR2_PIPELINE_CHUNKS", "5")
+    min_cost, root, mapping = ctx.dtl_run(node_off, left, right, leaf, species.costs)
+    for b in range(0, len(sizes), 7):
+        lo, hi = int(node_off[b]), int(node_off[b + 1])
+        ref = oracle.dtl(species.parent, species.child0, species.child1, left[lo:hi], right[lo:hi], leaf[lo:hi],
+                         species.costs, strict=False)
+        assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"], b
+        assert (mapping[lo:hi] == ref["mapping"]).all(), b

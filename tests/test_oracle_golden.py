@@ -23,7 +23,7 @@ def _check_thl(fixture, with_table):
 
 
 def test_thl_small_tables_and_results(golden):
-    fixtures = golden("thl_small.json.gz")
+    fixtures = golden("thl_small.json.gz") + golden("thl_internal_species.json.gz")
     assert len(fixtures) >= 100
     for fixture in fixtures:
         _check_thl(fixture, True)
@@ -51,7 +51,7 @@ def test_thl_non_strict_skips_missing_roots(golden):
     """Where the reference raises KeyError the oracle's non-strict mode (the product's
     documented behaviour) still returns the best root that has an entry."""
     seen = 0
-    for fixture in golden("thl_small.json.gz"):
+    for fixture in golden("thl_small.json.gz") + golden("thl_internal_species.json.gz"):
         if fixture.get("error") != "KeyError":
             continue
         flat = FlatDtl(fixture["input"])
@@ -86,7 +86,7 @@ def _check_superdtl_binary(fixture):
 
 
 def test_superdtl_small_tables_sets_and_results(golden):
-    fixtures = golden("superdtl_small.json.gz")
+    fixtures = golden("superdtl_small.json.gz") + golden("superdtl_internal_species.json.gz")
     assert len(fixtures) >= 100
     for fixture in fixtures:
         _check_superdtl_binary(fixture)

@@ -29,7 +29,8 @@ def _run_one(ctx, flat, keep=True):
 
 
 def test_golden_small_tables_sets_results(ctx, golden):
-    for fixture in golden("superdtl_small.json.gz") + golden("superdtl_reference.json.gz"):
+    for fixture in (golden("superdtl_small.json.gz") + golden("superdtl_reference.json.gz") +
+                    golden("superdtl_internal_species.json.gz")):
         flat = FlatSuper.from_dict(fixture["input"])
         min_cost, root, mapping, kind, syn = _run_one(ctx, flat)
         value, tag, gain, lca = ctx.superdtl_tables(0)
