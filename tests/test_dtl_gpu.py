@@ -380,3 +380,32 @@ def test_device_bucketing_ragged_batch_with_single_leaf_trees(ctx, monkeypatch):
                          species.costs, strict=False)
         assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"], b
         assert (mapping[lo:hi] == ref["mapping"]).all(), b
+
+
+def test_large_costs_leave_the_32_bit_kernels(ctx, monkeypatch):
+    """Costs too large for 32-bit (value, rank, depth) keys: the batched kernels step aside for the
+    64-bit row-per-warp kernel; tables and results still equal the oracle's."""
+    monkeypatch.setenv("SR2_DTL_SIMD_MIN_ROWS", "1")
+    costs = (0, 700000, 900000, 40000, 1)
+    batch = synth.make_batch(20, 30, 6, seed=12, costs=costs)
+    ctx.set_species(batch.parent, batch.child0, batch.child1)
+    min_cost, root, mapping = ctx.dtl_run(batch.node_off, batch.left, batch.right, batch.leaf_species,
+                                          batch.costs, flags=_lib.SR2_KEEP_TABLES)
+    for b in range(batch.n_instances):
+        left, right, leaf = batch.instance(b)
+        ref = oracle.dtl(batch.parent, batch.child0, batch.child1, left, right, leaf, batch.costs, strict=False)
+        value, tag = ctx.dtl_tables(b, len(left))
+        assert (value == ref["value"]).all() and (tag == ref["tag"]).all()
+        assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"]
+
+
+def test_batch_of_one_node_trees_only(ctx):
+    """No internal object node at all (zero DP rows), through the device-bucketing path."""
+    species = synth.make_batch(6, 6, 1, seed=2)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    count = 1500
+    leaves = np.flatnonzero(species.child0 < 0).astype(np.int32)
+    leaf = leaves[np.arange(count) % len(leaves)]
+    none = np.full(count, -1, np.int32)
+    min_cost, root, mapping = ctx.dtl_run(np.arange(count + 1, dtype=np.int64), none, none, leaf, species.costs)
+    assert (min_cost == 0).all() and (root == leaf).all() and (mapping == leaf).all()
