@@ -22,6 +22,7 @@ Fixtures:
   crispr.json.gz           data/crispr-class1.in.json (superdtl, default costs)
   binarize.json.gz         enumeration order of ReconciliationInput.binarize()
   thl_all.json.gz          dtl instances with the full RetentionPolicy.ALL solution set
+  superdtl_species_poly.json.gz  multifurcating species trees (and object trees), result only
   thl_internal_species.json.gz, superdtl_internal_species.json.gz
                            instances whose object leaves sit at internal species nodes, full tables
   base_uspfs.json.gz       binary instances solved by usreconcile_base_uspfs (superdtl table
@@ -418,6 +419,18 @@ def main():
             inner_super.append(superdtl_fixture(data, True))
         else:
             inner_thl.append(thl_fixture(data, True))
+    # ---- multifurcating SPECIES trees (every (object, species) resolution pair is tried, :171-174) ----
+    rng5 = random.Random(20261023)
+    species_poly = []
+    for i in range(24):
+        n_s = rng5.randint(3, 5)
+        n_o = rng5.randint(3, 6)
+        mode = ["default", "random", "spe"][i % 3]
+        data = random_instance(rng5, n_s, n_o, True, mode, families=rng5.randint(2, 4),
+                               polytomy=0.5 if i % 2 else 0.0, name_internal=i % 4 < 2)
+        data["species_tree"] = random_tree(rng5, [f"S{k}" for k in range(n_s)], "s", i % 4 < 2, polytomy=0.7)
+        species_poly.append(superdtl_fixture(data, False))
+    write("superdtl_species_poly.json.gz", species_poly)
     write("thl_internal_species.json.gz", inner_thl)
     write("superdtl_internal_species.json.gz", inner_super)
 

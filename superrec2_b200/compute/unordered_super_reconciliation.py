@@ -156,15 +156,45 @@ def usreconcile_extended_uspfs_sharded(
                 best_key = min(best_key, ctx.superdtl_best()[3])
                 start += count
     else:
-        # species polytomies: each (object, species) resolution pair has its own species tree
-        for index in range(lo, hi):
-            item = srec_input.resolution(index)
-            species, objects, _, bits = flatten_super(item, None, families)
+        # species polytomies: resolution number = object_number * n_species + species_number
+        # (reference model/reconciliation.py:171-174).  One batch of object resolutions per
+        # species resolution; the library orders a batch by (cost, object_number, root), which
+        # for a fixed species_number is the order of (cost, resolution number, root), so the
+        # key is renumbered here and the minimum over species resolutions taken on the host.
+        from ..utils.trees import unrank_resolution
+        from .flatten import flatten_polytomies
+        n_species = count_resolutions(srec_input.species_lca.tree)
+        leaf_species_nodes = set(srec_input.leaf_object_species.values())
+        for number in range(n_species):
+            first = (lo - number + n_species - 1) // n_species      # object numbers [first, last)
+            last = (hi - number + n_species - 1) // n_species
+            if last <= first:
+                continue
+            species = flatten_species(unrank_resolution(srec_input.species_lca.tree, number))
+            by_name = {node.name: rank for node, rank in species.rank.items()}
+            species_rank = {node: by_name[node.name] for node in leaf_species_nodes}
             ctx.set_species(species.parent, species.child0, species.child1)
-            ctx.superdtl_upload([0, len(objects.nodes)], objects.left, objects.right,
-                                objects.leaf_species, bits, costs, index_base=index)
-            ctx.superdtl_solve()
-            best_key = min(best_key, ctx.superdtl_best()[3])
+            poly = flatten_polytomies(srec_input.object_tree, srec_input.leaf_object_species,
+                                      species_rank)
+            bits = leaf_bitsets(poly.nodes, srec_input.leaf_syntenies, families)
+            start, step = first, last - first
+            while start < last:
+                count = min(step, last - start)
+                try:
+                    ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits,
+                                           costs, start, count)
+                except _lib.Sr2Error as err:
+                    if err.code != -4 or count == 1:   # SR2_ERR_NOMEM: halve the batch
+                        raise
+                    step = (count + 1) // 2
+                    continue
+                ctx.superdtl_solve()
+                key = ctx.superdtl_best()[3]
+                if key != no_key:
+                    resolution = ((key >> 16) & 0xFFFFFF) * n_species + number
+                    key = (key >> 40 << 40) | (resolution << 16) | (key & 0xFFFF)
+                    best_key = min(best_key, key)
+                start += count
 
     global_key = reduce_key(best_key) if reduce_key is not None else best_key
     if global_key == no_key or global_key != best_key:

@@ -116,7 +116,7 @@ def _solve_resolutions(data):
 
 
 def test_superdtl_polytomies(golden):
-    for fixture in golden("superdtl_poly.json.gz"):
+    for fixture in golden("superdtl_poly.json.gz") + golden("superdtl_species_poly.json.gz"):
         cost, result = _solve_resolutions(fixture["input"])
         assert cost == fixture["min_cost"]
         assert result == fixture["result"]

@@ -44,7 +44,8 @@ def test_golden_small_tables_sets_results(ctx, golden):
 def test_entry_point_polytomies_and_crispr(golden):
     """usreconcile_extended_uspfs(...).to_dict() equals the reference's output JSON, including
     the winning resolution's newick with O#/S# labels (BASELINE config #1 = crispr)."""
-    fixtures = golden("superdtl_poly.json.gz") + golden("crispr.json.gz") + golden("superdtl_small.json.gz")[:30]
+    fixtures = (golden("superdtl_poly.json.gz") + golden("crispr.json.gz") + golden("superdtl_small.json.gz")[:30]
+                + golden("superdtl_species_poly.json.gz"))
     for fixture in fixtures:
         srec_input = SuperReconciliationInput.from_dict(fixture["input"])
         (result,) = usreconcile_extended_uspfs(srec_input, RetentionPolicy.ANY)
@@ -164,6 +165,31 @@ def test_sharded_ranges_agree_with_single_range(ctx):
             ctx.superdtl_solve()
             keys.append(ctx.superdtl_best()[3])
         assert min(keys) == whole
+
+
+def test_species_polytomies_sharded_entry_point(golden):
+    """Species-tree polytomies: resolution number = object_number * n_species + species_number.
+    Shards of that numbering, reduced with min over the packed keys, return the reference's
+    solution from exactly one shard (2, 3 and 5 shards)."""
+    from superrec2_b200.compute.unordered_super_reconciliation import usreconcile_extended_uspfs_sharded
+    for fixture in golden("superdtl_species_poly.json.gz")[:12]:
+        srec_input = SuperReconciliationInput.from_dict(fixture["input"])
+        for world in (2, 3, 5):
+            keys = []
+            for rank in range(world):
+                usreconcile_extended_uspfs_sharded(
+                    srec_input, shard=rank, n_shards=world,
+                    reduce_key=lambda key: keys.append(key) or (1 << 64) - 1)
+            winner = min(keys)
+            found = []
+            for rank in range(world):
+                found += list(usreconcile_extended_uspfs_sharded(
+                    srec_input, shard=rank, n_shards=world, reduce_key=lambda key: winner))
+            if fixture["result"] is None:
+                assert not found
+                continue
+            (result,) = found
+            assert result.to_dict() == fixture["result"]
 
 
 def test_config5_full_enumeration_properties(ctx):
