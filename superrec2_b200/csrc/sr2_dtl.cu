@@ -85,7 +85,14 @@ struct DtlProblem {
     int flat2_rows = 8;
     int flat2_sh = 0, flat2_thresh = 0;
     void (*flat2_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
-                     Key32, const uint32_t*, int, int, int, const int*, const int*) = nullptr;
+                     Key32, const uint32_t*, int, int, int, const int*, const int*, int*) = nullptr;
+    // The small top waves of a chunk run as ONE launch (flat2, chained): a row starts when the "done"
+    // flags of its child rows are up, instead of one latency-bound launch per wave.
+    void (*flat2_chain_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
+                           Key32, const uint32_t*, int, int, int, const int*, const int*, int*) = nullptr;
+    size_t trace_smem_set = 0;       // dynamic shared memory opted in for dtl_select_trace_kernel
+    int64_t chain_rows = 0;          // waves with fewer rows than this join the chained launch (0 = off)
+    int* d_chain_sync = nullptr;     // per table set: [0] CTA ticket, [1 + i] done flag of chained row i
     int flat2_pf_near = 0, flat2_pf_far = 0, sparse_pf_near = 0, sparse_pf_far = 0;
     int flat2_sparse_max = 0;        // rows with at most this many root-path species take the sparse cells path
 };
@@ -547,7 +554,7 @@ __device__ __forceinline__ void sts128(unsigned a, unsigned x, unsigned y, unsig
 
 // Child rows -> keys.  Every global load of the row (up to 2 x n_chunks per lane) is issued
 // before the first one is consumed: one DRAM round trip per row.
-template <bool IL, bool IR>
+template <bool IL, bool IR, bool CG = false>
 __device__ __forceinline__ void flat2_load(const int32_t* __restrict__ Tl, const int32_t* __restrict__ Tr,
                                            const uint32_t* __restrict__ keylow, uint2* __restrict__ M,
                                            int n_chunks, unsigned vmul, unsigned infkey) {
@@ -556,8 +563,9 @@ __device__ __forceinline__ void flat2_load(const int32_t* __restrict__ Tl, const
     for (int j = 0; j < FLAT2_NCH; ++j) {
         vl[j] = vr[j] = 0u;
         if (j < n_chunks) {
-            if (IL) vl[j] = (unsigned)Tl[j * 32];
-            if (IR) vr[j] = (unsigned)Tr[j * 32];
+            // CG: the row may have been written by another SM during this launch (chained rows)
+            if (IL) vl[j] = (unsigned)(CG ? __ldcg(Tl + j * 32) : Tl[j * 32]);
+            if (IR) vr[j] = (unsigned)(CG ? __ldcg(Tr + j * 32) : Tr[j * 32]);
         }
     }
 #pragma unroll
@@ -585,20 +593,33 @@ __device__ __forceinline__ int flat2_pack(int sum, int idx) {  // sum * 8 + idx,
     return w;
 }
 
-template <int NS>
+// CHAIN = false: the rows of one wave's "dense" list.  CHAIN = true: rows [row_begin, row_begin + n_rows) of
+// SEVERAL consecutive waves in one launch; a row waits for the done flags of its child rows inside the
+// range (chain_sync[1 + i]) and raises its own after its cells are written.  CTAs take their 8 rows by
+// ticket (chain_sync[0]), so every row a CTA can wait for belongs to a CTA that is already running.
+template <int NS, bool CHAIN>
 __global__ void __launch_bounds__(256, 4)
 dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                       int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
                       uint32_t* __restrict__ tags, DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask,
                       int sparse_max, int pf_near, int pf_far, const int* __restrict__ row_list,
-                      const int* __restrict__ list_count) {
+                      const int* __restrict__ list_count, int* __restrict__ chain_sync) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int cta_ticket;
     const int pitch = sp.pitch, rs = sp.flat_rs, n_chunks = pitch >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int local = blockIdx.x * (blockDim.x >> 5) + warp;
-    // the rows of this launch: the wave's "dense" list written by dtl_partition_kernel
-    if (local >= *list_count) return;
-    local = row_list[local];
+    int local;
+    if (CHAIN) {
+        if (threadIdx.x == 0) cta_ticket = atomicAdd(chain_sync, 1);
+        __syncthreads();  // the only CTA-wide barrier: the warps are independent from here on
+        local = cta_ticket * (blockDim.x >> 5) + warp;
+        if (local >= n_rows) return;
+    } else {
+        local = blockIdx.x * (blockDim.x >> 5) + warp;
+        // the rows of this launch: the wave's "dense" list written by dtl_partition_kernel
+        if (local >= *list_count) return;
+        local = row_list[local];
+    }
     const int64_t gr = row_begin + local;
     const size_t slot = (size_t)(gr - chunk_row0);
     uint2* Mrow = reinterpret_cast<uint2*>(smem_raw) + (size_t)warp * 2 * rs;
@@ -610,20 +631,35 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     // ---- child rows -> keys ------------------------------------------------------------------
     const int cl = row_cl[gr], cr = row_cr[gr];
     const unsigned vmul = 1u << kp.sh, infkey = 0xffffffffu << kp.sh;
+    if (CHAIN) {
+        // child rows inside the chained range: wait for their flags (lanes 0 and 1 poll one child each)
+        const int first_slot = (int)(row_begin - chunk_row0);
+        const int c = lane == 0 ? cl : cr;
+        if (lane < 2 && c >= first_slot) {
+            const int* flag = chain_sync + 1 + (c - first_slot);
+            int up;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(up) : "l"(flag) : "memory");
+                if (up) break;
+                __nanosleep(100);
+            }
+        }
+        __syncwarp();
+    }
     {
         const int32_t* __restrict__ Tl = T + (size_t)(cl >= 0 ? cl : 0) * pitch + lane;
         const int32_t* __restrict__ Tr = T + (size_t)(cr >= 0 ? cr : 0) * pitch + lane;
         const uint32_t* __restrict__ kl = sp.keylow_p + lane;
-        if (cl >= 0 && cr >= 0) flat2_load<true, true>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
-        else if (cl >= 0) flat2_load<true, false>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
-        else if (cr >= 0) flat2_load<false, true>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
-        else flat2_load<false, false>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        if (cl >= 0 && cr >= 0) flat2_load<true, true, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        else if (cl >= 0) flat2_load<true, false, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        else if (cr >= 0) flat2_load<false, true, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        else flat2_load<false, false, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
     }
     // The kernel is latency-bound (two dependent DRAM trips per row: descriptors, then child rows).
     // Pull the descriptors of a row far ahead into L2, and read those of a nearer row (prefetched by
     // an earlier CTA) to pull ITS child rows into L2; the prefetches are issued before the sweeps.
     int cl2 = -1, cr2 = -1;
-    {
+    if (!CHAIN) {
         const int pos = blockIdx.x * (blockDim.x >> 5) + warp, n_list = *list_count;
         if (pf_far > 0 && pos + pf_far < n_list && lane < 2)
             asm volatile("prefetch.global.L2 [%0];" ::"l"((lane ? row_cr : row_cl) + row_begin + row_list[pos + pf_far]));
@@ -752,11 +788,19 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
             const int x = w * 32 + (int)__fns(word, 0, i - before + 1);
             if (i0 + lane < m_set) cell(x, __ldg(sp.cmeta + x));
         }
-        return;
-    }
+    } else {
 #pragma unroll
-    for (int j = 0; j < FLAT2_NCH; ++j)
-        if (j < n_chunks) cell(j * 32 + lane, meta[j]);
+        for (int j = 0; j < FLAT2_NCH; ++j)
+            if (j < n_chunks) cell(j * 32 + lane, meta[j]);
+    }
+    if (CHAIN) {  // the row (values and tags of every lane) is visible before its flag
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            int* flag = chain_sync + 1 + local;
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1043,14 +1087,15 @@ __global__ void dtl_rowmask_kernel(DevSpecies sp, const int32_t* __restrict__ ro
 
 // the instantiation whose register-resident schedule is the shortest that holds n_steps
 typedef void (*Flat2Fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*,
-                        DtlCosts, Key32, const uint32_t*, int, int, int, const int*, const int*);
+                        DtlCosts, Key32, const uint32_t*, int, int, int, const int*, const int*, int*);
+template <bool CHAIN>
 static Flat2Fn flat2_pick(int n_steps) {
-    if (n_steps <= 12) return dtl_wave_flat2_kernel<12>;
-    if (n_steps <= 16) return dtl_wave_flat2_kernel<16>;
-    if (n_steps <= 20) return dtl_wave_flat2_kernel<20>;
-    if (n_steps <= 24) return dtl_wave_flat2_kernel<24>;
-    if (n_steps <= 28) return dtl_wave_flat2_kernel<28>;
-    return dtl_wave_flat2_kernel<32>;
+    if (n_steps <= 12) return dtl_wave_flat2_kernel<12, CHAIN>;
+    if (n_steps <= 16) return dtl_wave_flat2_kernel<16, CHAIN>;
+    if (n_steps <= 20) return dtl_wave_flat2_kernel<20, CHAIN>;
+    if (n_steps <= 24) return dtl_wave_flat2_kernel<24, CHAIN>;
+    if (n_steps <= 28) return dtl_wave_flat2_kernel<28, CHAIN>;
+    return dtl_wave_flat2_kernel<32, CHAIN>;
 }
 
 // Event cost of node (x; children at a, b) as ReconciliationOutput.cost() sees it
@@ -1187,6 +1232,105 @@ dtl_traceback_kernel(DevSpecies sp, const int32_t* __restrict__ row_node,
     map[row_right[gr]] = b;
 }
 
+// Selection and traceback of a whole object tree in one CTA (the default): after the root is chosen
+// as in dtl_select_kernel, the tree is walked breadth-first with the frontier -- (row, species) pairs of
+// the internal nodes of one depth -- in shared memory, so a level costs one round trip to the tables
+// and a CTA barrier instead of a launch over the rows of one height of every tree.
+// Shared memory: 2 lists of `cap` pairs; cap >= the internal nodes of one depth (<= leaves / 2).
+__global__ void __launch_bounds__(1024)
+dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, const int32_t* __restrict__ root_node,
+                        int inst_begin, int64_t chunk_row0, const int32_t* __restrict__ T,
+                        const int32_t* __restrict__ C, const uint32_t* __restrict__ tags,
+                        const int32_t* __restrict__ row_left, const int32_t* __restrict__ row_right,
+                        const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr, int cap, int check_T,
+                        int32_t* __restrict__ min_cost, int32_t* __restrict__ root_species,
+                        int32_t* __restrict__ map) {
+    extern __shared__ int2 trace_lists[];  // [2][cap] of (row slot, species)
+    __shared__ u64 warp_best[32];
+    __shared__ int n_list[2];
+    const int b = inst_begin + blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const int64_t gr0 = root_row[b];
+    if (gr0 < 0) {  // single-leaf object tree: the leaf sits at its own species at cost 0
+        if (threadIdx.x == 0) {
+            const int s = (int)(-1 - gr0);
+            min_cost[b] = 0;
+            root_species[b] = s;
+            map[root_node[b]] = s;
+        }
+        return;
+    }
+    const int pitch = sp.pitch;
+    const size_t slot0 = (size_t)(gr0 - chunk_row0);
+    u64 best = SR2_KEY_NONE;
+    for (int x = threadIdx.x; x < sp.S; x += blockDim.x) {
+        const int t = T[slot0 * pitch + x];
+        if (t < SR2_INF) {  // roots without an entry are skipped (Hazard B)
+            const int c = C ? C[slot0 * pitch + x] : t;
+            best = key_min(best, ((u64)(unsigned)c << 32) | (unsigned)x);
+        }
+    }
+    for (int off = 16; off; off >>= 1) best = key_min(best, __shfl_xor_sync(0xffffffffu, best, off));
+    if (lane == 0) warp_best[warp] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < n_warps; ++w) best = key_min(best, warp_best[w]);
+        const bool none = best == SR2_KEY_NONE;
+        const int x = none ? -1 : (int)(best & 0xffffffffu);
+        min_cost[b] = none ? SR2_INF : (int)(best >> 32);
+        root_species[b] = x;
+        map[root_node[b]] = x;
+        trace_lists[0] = make_int2((int)slot0, x);
+        n_list[0] = 1;
+        n_list[1] = 0;
+    }
+    __syncthreads();
+    int cur = 0;
+    for (;;) {
+        const int n = min(n_list[cur], cap);
+        if (n == 0) break;
+        const int2* from = trace_lists + (size_t)cur * cap;
+        int2* to = trace_lists + (size_t)(cur ^ 1) * cap;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int slot = from[i].x, x = from[i].y;
+            const int64_t gr = chunk_row0 + slot;
+            const int cl = row_cl[gr], cr = row_cr[gr];
+            int a = -1, c = -1;
+            // infinite cells have no (defined) tag; a cherry stores none at all: its parent only ever
+            // points at a finite cell, whose tag is the two leaf species
+            // (a parent's tag only ever points at a finite cell of its child: the root is finite, and a
+            // finite value is a sum of the finite child values at the tagged species)
+            if (x >= 0) {
+                if (cl < 0 && cr < 0) {
+                    a = -1 - cl;
+                    c = -1 - cr;
+                } else if (!check_T || T[(size_t)slot * pitch + x] < SR2_INF) {
+                    const unsigned tag = tags[(size_t)slot * pitch + x];
+                    if (tag != SR2_NO_TAG) {
+                        a = tag & 0xffffu;
+                        c = tag >> 16;
+                    }
+                }
+            }
+            map[row_left[gr]] = a;
+            map[row_right[gr]] = c;
+            // (validated full binary trees never exceed cap; the guard keeps a bad tree out of other memory)
+            if (cl >= 0) {
+                const int k = atomicAdd(&n_list[cur ^ 1], 1);
+                if (k < cap) to[k] = make_int2(cl, a);
+            }
+            if (cr >= 0) {
+                const int k = atomicAdd(&n_list[cur ^ 1], 1);
+                if (k < cap) to[k] = make_int2(cr, c);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) n_list[cur] = 0;
+        cur ^= 1;
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------
@@ -1246,6 +1390,9 @@ static int dtl_prepare(void* user) {
     p->d_lists = (int*)ptr;
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_COUNTS, p->rows.chunks.size() * 2 * 65536 * sizeof(int), &ptr))) return rc;
     p->d_counts = (int*)ptr;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_CHAIN, (size_t)2 * (std::max<int64_t>(p->rows.max_chunk_rows, 1) + 1) * sizeof(int), &ptr)))
+        return rc;
+    p->d_chain_sync = (int*)ptr;
     p->partitioned.assign(p->rows.chunks.size(), 0);
     for (auto* list : {&ctx->dtl_ev_w0, &ctx->dtl_ev_w1, &ctx->dtl_ev_done})
         while (list->size() < p->rows.chunks.size()) {
@@ -1405,9 +1552,15 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
         p->flat2_smem = (size_t)p->flat2_rows * 2 * ctx->dsp.flat_rs * sizeof(uint2);
         p->flat2 = (!v || strcmp(v, "flat2") == 0) && !(off && off[0] == '1') && S >= 2 && vb >= 8 &&
                    p->max_finite + slack < inf - slack && ctx->dsp.flat_rs > 0 && ctx->dsp.n_steps <= FLAT2_NS && ctx->pitch <= 32 * FLAT2_NCH &&
-                   p->flat2_smem <= std::min<size_t>(ctx->smem_optin, 65535);
+                   p->flat2_smem <= std::min<size_t>(ctx->smem_optin, 65536 - 2048);  // 16-bit addresses: system + static words come first
         if (p->flat2) {
-            p->flat2_fn = flat2_pick(ctx->dsp.n_steps);
+            p->flat2_fn = flat2_pick<false>(ctx->dsp.n_steps);
+            p->flat2_chain_fn = flat2_pick<true>(ctx->dsp.n_steps);
+            // waves below 4 x the resident rows of the kernel are latency-bound as launches of their own
+            p->chain_rows = 4 * 8 * 4 * (int64_t)ctx->sm_count;
+            if (const char* cr = getenv("SR2_DTL_CHAIN_ROWS")) p->chain_rows = atoll(cr);
+            SR2_CUDA(ctx, cudaFuncSetAttribute((const void*)p->flat2_chain_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)p->flat2_smem));
             // ceil(m / 32) sparse passes cost about as much as 2 dense chunks each (locating a lane's species)
             p->flat2_sparse_max = std::min(S, ctx->pitch / 4);
             if (const char* sm = getenv("SR2_FLAT2_SPARSE_MAX")) p->flat2_sparse_max = atoi(sm);
@@ -1475,7 +1628,8 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         p->flat2_fn<<<(unsigned)((n_rows + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem,
                       p->cur_stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
-            p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + p->list_pitch, counts + 1);
+            p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + p->list_pitch, counts + 1,
+            nullptr);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
@@ -1538,6 +1692,16 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     // event of their wave.  They stay valid for later solves of the same upload.
     const bool chain = p->flat2 && !p->partitioned[ci];
     cudaEvent_t chain_tail = nullptr;
+    // the first wave of the chained launch: waves shrink with height, so every wave from the first
+    // one below the threshold on is small (H + 1 = no chained launch)
+    int h_chain = H + 1;
+    if (p->flat2 && p->chain_rows > 0)
+        for (int h = 2; h <= H; ++h)
+            if (c.wave_off[h + 1] - c.wave_off[h] < p->chain_rows) {
+                h_chain = h;
+                break;
+            }
+    if (h_chain >= H) h_chain = H + 1;  // a single wave gains nothing
     std::vector<cudaEvent_t>& part_events = ctx->part_events[set];
     if (chain) {
         if (!ctx->part_stream[set]) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->part_stream[set], cudaStreamNonBlocking));
@@ -1552,7 +1716,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         for (int h = 1; h <= H; ++h) {
             int64_t n = c.wave_off[h + 1] - c.wave_off[h];
             if (n <= 0) continue;
-            const bool listed = h > 1 && n >= p->simd_min_rows;
+            const bool listed = h > 1 && h < h_chain && n >= p->simd_min_rows;
             if (listed) {
                 dtl_partition_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ps>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask,
@@ -1584,12 +1748,34 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     }
     SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w0[ci], st));
     size_t part_k = 0;
-    for (int h = 1; h <= H; ++h) {
+    for (int h = 1; h <= H && h < h_chain; ++h) {
         int64_t n = c.wave_off[h + 1] - c.wave_off[h];
         if (n <= 0) continue;
         p->cur_part_event = (chain && h > 1 && n >= p->simd_min_rows) ? part_events[part_k++] : nullptr;
         int rc = dtl_launch_wave(ctx, p, c, h, c.wave_off[h], n, cs);
         if (rc) return rc;
+        ++p->n_waves;
+        ++p->n_launch;
+    }
+    if (h_chain <= H) {
+        const int64_t first = c.wave_off[h_chain], n = c.wave_off[H + 1] - first;
+        int* sync = p->d_chain_sync + (size_t)set * (std::max<int64_t>(p->rows.max_chunk_rows, 1) + 1);
+        SR2_CUDA(ctx, cudaMemsetAsync(sync, 0, (size_t)(n + 1) * sizeof(int), st));
+        if (chain_tail) {  // the path sets of all chained rows
+            SR2_CUDA(ctx, cudaStreamWaitEvent(st, chain_tail, 0));
+            chain_tail = nullptr;
+        }
+        Key32 kp;
+        kp.db = p->depth_bits;
+        kp.sh = p->flat2_sh;
+        kp.rm = (1u << p->rank_bits) - 1;
+        kp.dm = (1u << p->depth_bits) - 1;
+        kp.inf32 = 1u << (32 - kp.sh - 1);
+        kp.thresh = p->flat2_thresh;
+        p->flat2_chain_fn<<<(unsigned)((n + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem, st>>>(
+            ctx->dsp, p->rows.row_cl, p->rows.row_cr, first, c.row_begin, (int)n, p->cur_T, p->cur_tag, cs, kp,
+            p->cur_mask, p->flat2_sparse_max, 0, 0, nullptr, nullptr, sync);
+        SR2_CUDA(ctx, cudaGetLastError());
         ++p->n_waves;
         ++p->n_launch;
     }
@@ -1604,13 +1790,34 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         }
     }
     int n_inst = c.inst_end - c.inst_begin;
-    if (n_inst > 0) {
+    // one CTA per tree walks it top-down; frontier capacity from the largest tree of the chunk
+    int64_t max_nodes = 1;
+    for (int b = c.inst_begin; b < c.inst_end; ++b)
+        max_nodes = std::max<int64_t>(max_nodes, p->rows.node_off[b + 1] - p->rows.node_off[b]);
+    const int64_t cap = (max_nodes + 1) / 4 + 1;  // internal nodes of one depth <= leaves / 2
+    const size_t trace_smem = (size_t)2 * cap * sizeof(int2);
+    const bool per_tree = trace_smem + 1024 <= ctx->smem_optin && !getenv("SR2_DTL_TRACE_BY_WAVE");
+    if (n_inst > 0 && per_tree) {
+        int threads = 32;
+        while (threads < 1024 && threads * 2 < cap) threads *= 2;  // measured on config #2 (cap 251): 32 / 64 / 128 / 256 -> 336 / 309 / 272 / 393 us
+        if (const char* t = getenv("SR2_DTL_TRACE_THREADS")) threads = std::max(32, std::min(1024, atoi(t) / 32 * 32));
+        if (trace_smem > 48 * 1024 && trace_smem > p->trace_smem_set) {
+            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_select_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)trace_smem));
+            p->trace_smem_set = trace_smem;
+        }
+        dtl_select_trace_kernel<<<n_inst, threads, trace_smem, st>>>(
+            ctx->dsp, p->rows.d_root_row, p->rows.d_root_node, c.inst_begin, c.row_begin, p->cur_T,
+            p->need_decoded_cost ? p->cur_C : nullptr, p->cur_tag, p->rows.row_left, p->rows.row_right,
+            p->rows.row_cl, p->rows.row_cr, (int)cap, getenv("SR2_DTL_TRACE_CHECK") ? 1 : 0, p->d_min_cost, p->d_root_species, p->d_map);
+        ++p->n_launch;
+    } else if (n_inst > 0) {
         dtl_select_kernel<<<(n_inst + 7) / 8, 256, 0, st>>>(
             ctx->dsp, p->rows.d_root_row, p->rows.d_root_node, c.inst_begin, n_inst, c.row_begin, p->cur_T,
             p->need_decoded_cost ? p->cur_C : nullptr, p->d_min_cost, p->d_root_species, p->d_map);
         ++p->n_launch;
     }
-    for (int h = H; h >= 1; --h) {
+    for (int h = H; h >= 1 && !per_tree; --h) {
         int64_t n = c.wave_off[h + 1] - c.wave_off[h];
         if (n <= 0) continue;
         dtl_traceback_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(

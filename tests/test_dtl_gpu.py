@@ -165,16 +165,22 @@ def test_bad_input_is_rejected(ctx):
     (200, 210, 3, (0, 1, 1, 1, 1)),
     (240, 250, 2, (0, 1, 2, 1, 1)),   # 479 species: the largest pitch (480) the batched kernels take
 ])
-@pytest.mark.parametrize("variant", ["flat2", "flat2-dense-cells", "flat"])
+@pytest.mark.parametrize("variant", ["flat2", "flat2-waves", "flat2-dense-cells", "flat"])
 def test_batched_wave_kernels_against_oracle(ctx, monkeypatch, n_s, n_o, n_trees, costs, variant):
     """Force the batched-wave kernels (32-bit keys) on small batches, including partial last
     groups, and compare every cell and tag with the oracle: "flat2" (the default: sweep schedule in
-    registers, sparse cells pass for rows with few root-path species), the same with the sparse pass
-    switched off, and "flat", the first form, kept as a cross-check."""
+    registers, sparse cells pass for rows with few root-path species; at these sizes every wave above
+    the cherries joins the chained launch and the trees are traced back one CTA per tree),
+    "flat2-waves" (one launch per wave for the sparse / dense row lists, traceback one launch per
+    height), flat2 with the sparse pass switched off, and "flat", the first form, kept as a
+    cross-check."""
     monkeypatch.setenv("SR2_DTL_SIMD_MIN_ROWS", "1")
     monkeypatch.setenv("SR2_DTL_VARIANT", variant.split("-")[0])
     if variant.endswith("dense-cells"):
         monkeypatch.setenv("SR2_FLAT2_SPARSE_MAX", "0")
+    if variant.endswith("waves"):
+        monkeypatch.setenv("SR2_DTL_CHAIN_ROWS", "0")
+        monkeypatch.setenv("SR2_DTL_TRACE_BY_WAVE", "1")
     batch = synth.make_batch(n_s, n_o, n_trees, seed=31 + n_s, costs=costs)
     if n_s in (9, 33, 240):
         # the leaf map may name ANY species node: put a third of the object leaves at random
@@ -217,6 +223,16 @@ def test_kernel_variants_agree_on_a_large_batch(ctx, monkeypatch):
     dense = ctx.dtl_run(*args)
     for a, b in zip(simd, dense):
         assert (a == b).all()
+    monkeypatch.delenv("SR2_DTL_DENSE_CHERRIES")
+    # top waves: one chained launch for all waves above the cherries / one launch per wave;
+    # traceback: one launch per height instead of one CTA per tree
+    for chain_rows, by_wave in (("1000000000", "0"), ("0", "1")):
+        monkeypatch.setenv("SR2_DTL_CHAIN_ROWS", chain_rows)
+        if by_wave == "1":
+            monkeypatch.setenv("SR2_DTL_TRACE_BY_WAVE", "1")
+        other = ctx.dtl_run(*args)
+        for a, b in zip(simd, other):
+            assert (a == b).all()
     from tests.helpers import flat_cost
     for b in (0, 299, 599):
         assert flat_cost(batch, b, simd[2]) == simd[0][b]
@@ -397,6 +413,22 @@ def test_large_costs_leave_the_32_bit_kernels(ctx, monkeypatch):
         value, tag = ctx.dtl_tables(b, len(left))
         assert (value == ref["value"]).all() and (tag == ref["tag"]).all()
         assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"]
+
+
+def test_traceback_of_a_large_tree_per_tree_and_per_wave(ctx, monkeypatch):
+    """A 15,000-leaf object tree: the per-tree traceback needs a 120 KB frontier (opt-in shared
+    memory, 1,024 threads); same mapping as the launch-per-height traceback, and its cost() is
+    the reported minimum."""
+    batch = synth.make_batch(50, 15000, 1, seed=91)
+    ctx.set_species(batch.parent, batch.child0, batch.child1)
+    args = (batch.node_off, batch.left, batch.right, batch.leaf_species, batch.costs)
+    per_tree = ctx.dtl_run(*args)
+    monkeypatch.setenv("SR2_DTL_TRACE_BY_WAVE", "1")
+    per_wave = ctx.dtl_run(*args)
+    for a, b in zip(per_tree, per_wave):
+        assert (a == b).all()
+    from tests.helpers import flat_cost
+    assert flat_cost(batch, 0, per_tree[2]) == per_tree[0][0] < INF
 
 
 def test_batch_of_one_node_trees_only(ctx):
