@@ -306,7 +306,7 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
         sched2[i] = (int32_t)((c_idx * 8) << 16 | (p_idx * 8));
     }
     size_t total = (size_t)S * 7 + (n_int ? n_int : 1) + (size_t)ctx->D + 1 + std::max<size_t>(sched.size(), 32) + sched2.size() +
-                   (size_t)S * 4 + 2 * (size_t)ctx->pitch + 16 + (size_t)S * (ctx->pitch / 32);
+                   (size_t)S * 4 + 2 * (size_t)ctx->pitch + 24 + (size_t)S * ((ctx->pitch / 32 + 3) / 4 * 4);
     SR2_CUDA(ctx, cudaMalloc(&ctx->d_species_slab, total * sizeof(int32_t)));
     std::vector<int32_t> slab(total, 0);
     int32_t* h = slab.data();
@@ -357,14 +357,17 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
         ctx->dsp.keylow_p = (const uint32_t*)put(keylow_p, ctx->pitch);
         ctx->dsp.cmeta = (const uint32_t*)put(cmeta, ctx->pitch);
         {
-            const int mw = ctx->pitch / 32;
-            std::vector<int32_t> pathmask((size_t)S * mw, 0);
+            // rows of mask_stride words (a multiple of 4, zero padded): read and written as uint4
+            const int mw = ctx->pitch / 32, ms = (mw + 3) / 4 * 4;
+            std::vector<int32_t> pathmask((size_t)S * ms, 0);
             for (int y = 0; y < S; ++y) {
-                int32_t* row = pathmask.data() + (size_t)y * mw;
-                if (y > 0) memcpy(row, pathmask.data() + (size_t)parent[y] * mw, sizeof(int32_t) * mw);
+                int32_t* row = pathmask.data() + (size_t)y * ms;
+                if (y > 0) memcpy(row, pathmask.data() + (size_t)parent[y] * ms, sizeof(int32_t) * ms);
                 row[y >> 5] |= (int32_t)(1u << (y & 31));
             }
             ctx->dsp.mask_words = mw;
+            ctx->dsp.mask_stride = ms;
+            off = (off + 3) / 4 * 4;  // 16-byte alignment (the slab itself is 256-byte aligned)
             ctx->dsp.pathmask = (const uint32_t*)put(pathmask, pathmask.size());
         }
         off = (off + 3) / 4 * 4;  // 16-byte alignment (the slab itself is 256-byte aligned)

@@ -62,11 +62,12 @@ struct DevSpecies {
     // table would be too large (S x D > 2^23 entries)
     const uint16_t* anc_tab;
     int anc_pitch;
-    // pathmask[s * mask_words + w]: bit set of the species on the root path of s (s included), one
+    // pathmask[s * mask_stride + w]: bit set of the species on the root path of s (s included), one
     // bit per BFS rank, mask_words = pitch / 32.  The finite cells of a DP row are a subset of the
     // union of the root paths of the leaf species below its object node.
     const uint32_t* pathmask;
     int mask_words;
+    int mask_stride;  // words between two bit sets: mask_words rounded up to a multiple of 4 (uint4 access)
 };
 
 struct DtlProblem;
