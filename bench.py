@@ -316,16 +316,16 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "dtl wave kernels: dtl_wave_sparse_kernel (rows with <= 64 root-path species, 53 % "
-                                   "of the step), dtl_wave_flat2_kernel (the other rows, 33 %), "
-                                   "dtl_cherry_sparse_kernel (wave 1, 6 %)",
+                         "kernel": "dtl wave kernels: dtl_wave_sparse_kernel (rows with <= 64 root-path species, 50 % "
+                                   "of the step), dtl_wave_flat2_kernel (the other rows, 32 %, and the chained launch "
+                                   "of the small top waves, 5 %), dtl_cherry_sparse_kernel (wave 1, 7 %)",
                          "peak_source": peak_src,
                          "bytes_per_cell": BYTES_PER_CELL,
                          "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL / waves_per_step,
                          "wave_launches_per_step": waves_per_step,
                          "wave_ms_per_step": wave_ms / args.steps,
                          "traffic_source": "bytes per wave launch (average over the step's launches) from "
-                                           "ncu dram__bytes_read+write per row, profiles/r2d_sparse_ncu_details.csv, r1y_flat2_ncu_details.csv"},
+                                           "ncu dram__bytes_read+write per row, profiles/r2d_sparse_ncu_details.csv (r2h: same kernel, 4.8 KB per row), r1y_flat2_ncu_details.csv"},
             "checksum_min_costs": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:

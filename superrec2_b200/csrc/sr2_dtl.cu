@@ -56,7 +56,7 @@ struct DtlProblem {
     int32_t* cur_C = nullptr;
     uint32_t* d_mask = nullptr;      // [rows * pitch/32] root-path bit sets of the rows (flat2 only)
     uint32_t* cur_mask = nullptr;
-    // Row lists of every wave, kept with the upload (they depend on the trees, not on the costs):
+    // Row lists of every wave (rebuilt by every solve, on a side stream ahead of the wave kernels):
     // d_lists[0 * R + row] / d_lists[1 * R + row] = sparse / dense rows of the wave that starts at `row`
     // (wave-local indices), d_counts[(chunk * 65536 + wave) * 2 + {0, 1}] = their lengths.
     int* d_lists = nullptr;
@@ -64,7 +64,6 @@ struct DtlProblem {
     int cur_chunk = 0;
     cudaEvent_t cur_part_event = nullptr;  // set by dtl_enqueue_chunk for the wave being launched
     int64_t list_pitch = 0;          // = R
-    std::vector<char> partitioned;   // per chunk: lists and path sets are on the device
     int sparse_maxm = SPARSE_MAXM_DEFAULT;
     int n_waves = 0, n_launch = 0;
     // wave launch configuration (fixed per upload)
@@ -1401,7 +1400,6 @@ static int dtl_prepare(void* user) {
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_CHAIN, (size_t)2 * (std::max<int64_t>(p->rows.max_chunk_rows, 1) + 1) * sizeof(int), &ptr)))
         return rc;
     p->d_chain_sync = (int*)ptr;
-    p->partitioned.assign(p->rows.chunks.size(), 0);
     for (auto* list : {&ctx->dtl_ev_w0, &ctx->dtl_ev_w1, &ctx->dtl_ev_done})
         while (list->size() < p->rows.chunks.size()) {
             cudaEvent_t e;
@@ -1688,8 +1686,6 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     p->cur_C = p->d_C ? p->d_C + set * table_elems : nullptr;
     p->cur_mask = p->d_mask + set * (table_elems / ctx->pitch * ctx->dsp.mask_stride);
     p->cur_chunk = ci;
-    // the path sets live in the table set: they survive between solves only if no other chunk used it
-    if (p->rows.chunks.size() > 1) p->partitioned[ci] = 0;
     cudaStream_t st = p->cur_stream;
     const RowChunk& c = p->rows.chunks[ci];
     if (p->wait_rows) SR2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->chunk_events[ci], 0));  // its rows' H2D copies
@@ -1697,8 +1693,8 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     const int H = (int)c.wave_off.size() - 2;  // highest wave
     // Path sets and sparse / dense row lists of every wave do not depend on DP values: they are
     // computed on a side stream, wave after wave, ahead of the wave kernels, which wait for the
-    // event of their wave.  They stay valid for later solves of the same upload.
-    const bool chain = p->flat2 && !p->partitioned[ci];
+    // event of their wave.
+    const bool chain = p->flat2;
     cudaEvent_t chain_tail = nullptr;
     // the first wave of the chained launch: waves shrink with height, so every wave from the first
     // one below the threshold on is small (H + 1 = no chained launch)
@@ -1836,7 +1832,6 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     SR2_CUDA(ctx, cudaGetLastError());
     if (chain_tail) SR2_CUDA(ctx, cudaStreamWaitEvent(st, chain_tail, 0));
     SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_done[ci], st));
-    p->partitioned[ci] = 1;
     return SR2_OK;
 }
 
