@@ -273,16 +273,16 @@ def main():
         peak, peak_src = measured_peak()
         achieved = cells * args.steps * BYTES_PER_CELL / (wave_ms * 1e-3) / 1e9
         # DRAM traffic per wave launch, from the ncu --set full captures under profiles/
-        # (r2d: dtl_wave_sparse_kernel 1.93 GB read + 2.19 GB written for 1,000,032 rows of 399 species =
-        #  10.3 B/cell; r1y: dtl_wave_flat2_kernel 12.1 B/cell; the wave-1 sparse cherry kernel writes the
-        #  value row only, 4.2 B/cell), scaled to this batch's rows (3/4 of the other rows are sparse)
+        # (r2d / r2h: dtl_wave_sparse_kernel 4.8 KB per row of 399 species = 12.1 B/cell with the r2h figures;
+        #  r1y: dtl_wave_flat2_kernel 12.1 B/cell; cherry rows (wave 1) are never written: their readers
+        #  evaluate the closed form), scaled to this batch's rows
         internal = batch.left >= 0
         safe_l = np.where(internal, batch.left, 0) + np.repeat(batch.node_off[:-1], np.diff(batch.node_off))
         safe_r = np.where(internal, batch.right, 0) + np.repeat(batch.node_off[:-1], np.diff(batch.node_off))
         cherry = internal & ~internal[safe_l] & ~internal[safe_r]
         n_cherry, n_other = int(cherry.sum()), int(internal.sum() - cherry.sum())
         waves_per_step = max(1, ctx.timing().n_waves)
-        traffic = (n_other * batch.n_species * (0.74 * 10.3 + 0.26 * 12.1) + n_cherry * batch.n_species * 4.2) / waves_per_step
+        traffic = n_other * batch.n_species * 12.1 / waves_per_step
         line = {
             "metric": "dp_cells_per_s",
             "value": all_cells * args.steps / (elapsed_ms * 1e-3),

@@ -387,6 +387,7 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
         ctx->d_anc_tab = nullptr;
     }
     ctx->dsp.anc_tab = nullptr;
+    ctx->dsp.lca_depth = nullptr;
     ctx->dsp.anc_pitch = (ctx->D + 1) & ~1;
     std::vector<uint16_t> anc;
     if ((size_t)S * ctx->dsp.anc_pitch <= ((size_t)1 << 23)) {
@@ -396,10 +397,31 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
             if (y > 0) memcpy(row, anc.data() + (size_t)parent[y] * ctx->dsp.anc_pitch, sizeof(uint16_t) * ctx->h_depth[y]);
             row[ctx->h_depth[y]] = (uint16_t)y;
         }
-        SR2_CUDA(ctx, cudaMalloc(&ctx->d_anc_tab, anc.size() * sizeof(uint16_t)));
+        // depth of lca(a, b) for small species trees (S x S bytes behind the ancestor table): lets the
+        // consumers of a cherry row evaluate its closed form themselves (sr2_dtl.cu, "virtual cherries")
+        std::vector<uint8_t> lcad;
+        if (S <= 1024 && ctx->D <= 255) {
+            lcad.resize((size_t)S * S);
+            const int ap = ctx->dsp.anc_pitch;
+            for (int a = 0; a < S; ++a)
+                for (int b = a; b < S; ++b) {
+                    const uint16_t *ra = anc.data() + (size_t)a * ap, *rb = anc.data() + (size_t)b * ap;
+                    const int dmin = std::min(ctx->h_depth[a], ctx->h_depth[b]);
+                    int d = 0;
+                    while (d <= dmin && ra[d] == rb[d]) ++d;
+                    lcad[(size_t)a * S + b] = lcad[(size_t)b * S + a] = (uint8_t)(d - 1);
+                }
+        }
+        SR2_CUDA(ctx, cudaMalloc(&ctx->d_anc_tab, anc.size() * sizeof(uint16_t) + lcad.size()));
         SR2_CUDA(ctx, cudaMemcpyAsync(ctx->d_anc_tab, anc.data(), anc.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
                                       ctx->stream));
         ctx->dsp.anc_tab = ctx->d_anc_tab;
+        if (!lcad.empty()) {
+            uint8_t* d_lcad = reinterpret_cast<uint8_t*>(ctx->d_anc_tab + anc.size());
+            SR2_CUDA(ctx, cudaMemcpyAsync(d_lcad, lcad.data(), lcad.size(), cudaMemcpyHostToDevice, ctx->stream));
+            SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // lcad is a local
+            ctx->dsp.lca_depth = d_lcad;
+        }
     }
     SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SR2_OK;

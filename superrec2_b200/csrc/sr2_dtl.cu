@@ -84,11 +84,12 @@ struct DtlProblem {
     int flat2_rows = 8;
     int flat2_sh = 0, flat2_thresh = 0;
     void (*flat2_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
-                     Key32, const uint32_t*, int, int, int, const int*, const int*, int*) = nullptr;
+                     Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int) = nullptr;
     // The small top waves of a chunk run as ONE launch (flat2, chained): a row starts when the "done"
     // flags of its child rows are up, instead of one latency-bound launch per wave.
     void (*flat2_chain_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
-                           Key32, const uint32_t*, int, int, int, const int*, const int*, int*) = nullptr;
+                           Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int) = nullptr;
+    int cur_cherry_end = 0;          // chunk being enqueued: its wave-1 rows [0, cherry_end) are virtual (0 = materialised)
     size_t trace_smem_set = 0;       // dynamic shared memory opted in for dtl_select_trace_kernel
     int64_t chain_rows = 0;          // waves with fewer rows than this join the chained launch (0 = off)
     int* d_chain_sync = nullptr;     // per table set: [0] CTA ticket, [1 + i] done flag of chained row i
@@ -374,6 +375,44 @@ struct Key32 {
 };
 
 // ---------------------------------------------------------------------------
+// "Virtual cherries".  The row of a cherry (both children leaves, at species a and b) has a closed
+// form (dtl_cherry_sparse_kernel), so the batched kernels that read a cherry child evaluate it
+// themselves instead of reading a row from HBM, and wave 1 is not launched at all: no 1.6 KB row
+// written per cherry, no gather from it.  A child row slot below `cherry_end` (the chunk's wave-1
+// rows come first) is a cherry; its leaf species are its own descriptors.
+// ---------------------------------------------------------------------------
+struct CherryForm {
+    const uint16_t* pa;  // root paths of a and b by depth
+    const uint16_t* pb;
+    int da, db, dl;      // depths of a, b and lca(a, b)
+    bool a_below, b_below;
+};
+__device__ __forceinline__ CherryForm cherry_form(const DevSpecies& sp, int a, int b) {
+    CherryForm f;
+    f.pa = sp.anc_tab + (size_t)a * sp.anc_pitch;
+    f.pb = sp.anc_tab + (size_t)b * sp.anc_pitch;
+    f.da = __ldg(sp.depth + a);
+    f.db = __ldg(sp.depth + b);
+    f.dl = (int)__ldg(sp.lca_depth + (size_t)a * sp.S + b);
+    f.a_below = f.da > f.dl;
+    f.b_below = f.db > f.dl;
+    return f;
+}
+// The finite cells of the cherry sit on the two root paths: value of the cell at the depth-d species of
+// a's path (which = 0, d <= da) or of b's path below the lca (which = 1, dl < d <= db); 0xffffffff =
+// no candidate (see dtl_cherry_sparse_kernel for the cases).  Readers walk the paths by depth, so the
+// ancestor-table loads of a lane are independent of each other.
+__device__ __forceinline__ unsigned cherry_path_value(const CherryForm& f, int which, int d, const DtlCosts& cs) {
+    if (which == 0) {
+        if (d <= f.dl)
+            return (unsigned)((d == f.dl && f.a_below && f.b_below) ? cs.loss * (f.da + f.db - 2 * d - 2)
+                                                                     : cs.dup + cs.loss * (f.da + f.db - 2 * d));
+        return f.b_below ? (unsigned)(cs.hgt + cs.loss * (f.da - d)) : 0xffffffffu;
+    }
+    return (d > f.dl && f.a_below) ? (unsigned)(cs.hgt + cs.loss * (f.db - d)) : 0xffffffffu;
+}
+
+// ---------------------------------------------------------------------------
 // Batched waves, first form ("flat", kept as a cross-check of flat2): one warp per row, 32-bit keys, and BOTH sweeps
 // materialised in shared memory before any cell is evaluated:
 //   ML/MR = SUBMIN of the two child rows (up-sweep, in place)
@@ -602,7 +641,7 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
                       int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
                       uint32_t* __restrict__ tags, DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask,
                       int sparse_max, int pf_near, int pf_far, const int* __restrict__ row_list,
-                      const int* __restrict__ list_count, int* __restrict__ chain_sync) {
+                      const int* __restrict__ list_count, int* __restrict__ chain_sync, int cherry_end) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int cta_ticket;
     const int pitch = sp.pitch, rs = sp.flat_rs, n_chunks = pitch >> 5;
@@ -649,10 +688,33 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
         const int32_t* __restrict__ Tl = T + (size_t)(cl >= 0 ? cl : 0) * pitch + lane;
         const int32_t* __restrict__ Tr = T + (size_t)(cr >= 0 ? cr : 0) * pitch + lane;
         const uint32_t* __restrict__ kl = sp.keylow_p + lane;
-        if (cl >= 0 && cr >= 0) flat2_load<true, true, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
-        else if (cl >= 0) flat2_load<true, false, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
-        else if (cr >= 0) flat2_load<false, true, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        // rows to read: internal children that are not virtual cherries (slots below cherry_end)
+        const bool il = cl >= cherry_end, ir = cr >= cherry_end;
+        if (il && ir) flat2_load<true, true, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        else if (il) flat2_load<true, false, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        else if (ir) flat2_load<false, true, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
         else flat2_load<false, false, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
+        // a virtual cherry child: its closed form along the two root paths, lanes over depths
+        if (cherry_end > 0) __syncwarp();  // M of the whole row is written
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            const int c = side ? cr : cl;
+            if (c < 0 || c >= cherry_end) continue;
+            const CherryForm f = cherry_form(sp, -1 - row_cl[chunk_row0 + c], -1 - row_cr[chunk_row0 + c]);
+            for (int which = 0; which < 2; ++which) {
+                const uint16_t* path = which ? f.pb : f.pa;
+                const int last = which ? f.db : f.da;
+                for (int d = (which ? f.dl + 1 : 0) + lane; d <= last; d += 32) {
+                    const int y = (int)path[d];
+                    const unsigned v = cherry_path_value(f, which, d, cs);
+                    if (v != 0xffffffffu) {
+                        const unsigned key = v * vmul + __ldg(sp.keylow_p + y);
+                        if (side) M[y].y = key;
+                        else M[y].x = key;
+                    }
+                }
+            }
+        }
     }
     // The kernel is latency-bound (two dependent DRAM trips per row: descriptors, then child rows).
     // Pull the descriptors of a row far ahead into L2, and read those of a nearer row (prefetched by
@@ -695,8 +757,8 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     __syncwarp();
 
     if (lane * 32 < pitch) {  // one 128-byte line per lane
-        if (cl2 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cl2 * pitch + lane * 32));
-        if (cr2 >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cr2 * pitch + lane * 32));
+        if (cl2 >= cherry_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cl2 * pitch + lane * 32));
+        if (cr2 >= cherry_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cr2 * pitch + lane * 32));
     }
     // ---- up-sweep: SUBMIN in place, deepest level first ------------------------------------------
 #pragma unroll
@@ -862,7 +924,7 @@ __global__ void __launch_bounds__(128)
 dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                        int64_t row_begin, int64_t chunk_row0, int32_t* __restrict__ T, uint32_t* __restrict__ tags,
                        DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask, const int* __restrict__ row_list,
-                       const int* __restrict__ list_count, int pf_near, int pf_far) {
+                       const int* __restrict__ list_count, int pf_near, int pf_far, int cherry_end) {
     extern __shared__ uint32_t sp_smem[];  // [4 warps][8 rows][SPARSE_ROW_WORDS]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, sub = lane & 3;
@@ -880,11 +942,15 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     int64_t gr = 0;
     size_t slot = 0;
     int cl = -1, cr = -1, m = 0;
+    int2 cha = make_int2(-1, -1), chb = make_int2(-1, -1);
     if (valid) {
         gr = row_begin + row_list[first + g];
         slot = (size_t)(gr - chunk_row0);
         cl = row_cl[gr];
         cr = row_cr[gr];
+        // a virtual cherry child: its two leaf species (its own descriptors) instead of a row to read
+        if (cl >= 0 && cl < cherry_end) cha = make_int2(-1 - row_cl[chunk_row0 + cl], -1 - row_cr[chunk_row0 + cl]);
+        if (cr >= 0 && cr < cherry_end) chb = make_int2(-1 - row_cl[chunk_row0 + cr], -1 - row_cr[chunk_row0 + cr]);
         // the row's own path set (dtl_partition_kernel); the children's rows are infinite outside
         // their own sets, so their values are simply gathered at every species of this set
         // (word loads: one uint4 per lane measured 10 % slower for the whole kernel)
@@ -951,11 +1017,11 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             va[q] = vb[q] = 0xffffffffu;  // "not on the child's paths": infinite
             if (e < m) {
                 const int s = (int)(el[e] & 0xffffu);
-                if (cl >= 0)
+                if (cl >= cherry_end)
                     va[q] = (unsigned)T[(size_t)cl * pitch + s];
                 else if (s == -1 - cl)
                     va[q] = 0u;
-                if (cr >= 0)
+                if (cr >= cherry_end)
                     vb[q] = (unsigned)T[(size_t)cr * pitch + s];
                 else if (s == -1 - cr)
                     vb[q] = 0u;
@@ -970,6 +1036,36 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
                 // a stored infinity (0x3fffffff) wraps to the all-ones value field, like the sentinel
                 Mc[e] = make_uint2(va[q] == 0xffffffffu ? infkey + low : va[q] * vmul + low,
                                    vb[q] == 0xffffffffu ? infkey + low : vb[q] * vmul + low);
+            }
+        }
+    }
+    // virtual cherry children (left infinite above): the closed form along the two root paths, lanes
+    // over depths; a path species is always in this row's set
+    __syncwarp();  // Mc of the whole row is written
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        const int2 ch = side ? chb : cha;
+        if (ch.x < 0) continue;
+        const CherryForm f = cherry_form(sp, ch.x, ch.y);
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            const uint16_t* path = which ? f.pb : f.pa;
+            const int last = which ? f.db : f.da, d_first = (which ? f.dl + 1 : 0) + sub;
+            for (int d0 = d_first; d0 <= last; d0 += 16) {
+                int sd[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sd[q] = d0 + 4 * q <= last ? (int)path[d0 + 4 * q] : -1;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int d = d0 + 4 * q, y = sd[q];
+                    if (y < 0) continue;
+                    const unsigned v = cherry_path_value(f, which, d, cs);
+                    if (v == 0xffffffffu) continue;
+                    const unsigned key = v * vmul + (((unsigned)y << kp.db) | (unsigned)d);
+                    const int e = pos_of(y);
+                    if (side) Mc[e].y = key;
+                    else Mc[e].x = key;
+                }
             }
         }
     }
@@ -1028,9 +1124,14 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         }
     }
     for (int line = sub; line * 32 < pitch; line += 4) {  // 128-byte lines of the two child rows
-        if (cl_near >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cl_near * pitch + line * 32));
-        if (cr_near >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cr_near * pitch + line * 32));
+        if (cl_near >= cherry_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cl_near * pitch + line * 32));
+        if (cr_near >= cherry_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(T + (size_t)cr_near * pitch + line * 32));
     }
+    // ... and the descriptors of its virtual cherry children
+    if (cl_near >= 0 && cl_near < cherry_end && sub < 2)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((sub ? row_cr : row_cl) + chunk_row0 + cl_near));
+    if (cr_near >= 0 && cr_near < cherry_end && sub >= 2)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"((sub == 3 ? row_cr : row_cl) + chunk_row0 + cr_near));
     // ---- cells: the path species only ---------------------------------------------------------------
     if (!valid) return;
     int32_t* __restrict__ Trow = T + slot * pitch;
@@ -1094,7 +1195,7 @@ __global__ void dtl_rowmask_kernel(DevSpecies sp, const int32_t* __restrict__ ro
 
 // the instantiation whose register-resident schedule is the shortest that holds n_steps
 typedef void (*Flat2Fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*,
-                        DtlCosts, Key32, const uint32_t*, int, int, int, const int*, const int*, int*);
+                        DtlCosts, Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int);
 template <bool CHAIN>
 static Flat2Fn flat2_pick(int n_steps) {
     if (n_steps <= 12) return dtl_wave_flat2_kernel<12, CHAIN>;
@@ -1250,7 +1351,7 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
                         const int32_t* __restrict__ C, const uint32_t* __restrict__ tags,
                         const int32_t* __restrict__ row_left, const int32_t* __restrict__ row_right,
                         const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr, int cap, int check_T,
-                        int32_t* __restrict__ min_cost, int32_t* __restrict__ root_species,
+                        int cherry_end, DtlCosts cs, int32_t* __restrict__ min_cost, int32_t* __restrict__ root_species,
                         int32_t* __restrict__ map) {
     extern __shared__ int2 trace_lists[];  // [2][cap] of (row slot, species)
     __shared__ u64 warp_best[32];
@@ -1270,11 +1371,23 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
     const int pitch = sp.pitch;
     const size_t slot0 = (size_t)(gr0 - chunk_row0);
     u64 best = SR2_KEY_NONE;
-    for (int x = threadIdx.x; x < sp.S; x += blockDim.x) {
-        const int t = T[slot0 * pitch + x];
-        if (t < SR2_INF) {  // roots without an entry are skipped (Hazard B)
-            const int c = C ? C[slot0 * pitch + x] : t;
-            best = key_min(best, ((u64)(unsigned)c << 32) | (unsigned)x);
+    if ((int64_t)slot0 < cherry_end) {  // a two-leaf tree whose row was never written (virtual cherries)
+        const CherryForm f = cherry_form(sp, -1 - row_cl[gr0], -1 - row_cr[gr0]);
+        for (int which = 0; which < 2; ++which) {
+            const uint16_t* path = which ? f.pb : f.pa;
+            const int last = which ? f.db : f.da;
+            for (int d = (which ? f.dl + 1 : 0) + threadIdx.x; d <= last; d += blockDim.x) {
+                const unsigned t = cherry_path_value(f, which, d, cs);
+                if (t != 0xffffffffu) best = key_min(best, ((u64)t << 32) | (unsigned)path[d]);
+            }
+        }
+    } else {
+        for (int x = threadIdx.x; x < sp.S; x += blockDim.x) {
+            const int t = T[slot0 * pitch + x];
+            if (t < SR2_INF) {  // roots without an entry are skipped (Hazard B)
+                const int c = C ? C[slot0 * pitch + x] : t;
+                best = key_min(best, ((u64)(unsigned)c << 32) | (unsigned)x);
+            }
         }
     }
     for (int off = 16; off; off >>= 1) best = key_min(best, __shfl_xor_sync(0xffffffffu, best, off));
@@ -1630,12 +1743,12 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             dtl_wave_sparse_kernel<<<(unsigned)((n_rows + 31) / 32), 128, 4 * 8 * SPARSE_ROW_WORDS * sizeof(uint32_t),
                                      p->cur_stream>>>(
                 ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
-                p->cur_mask, lists, counts, p->sparse_pf_near, p->sparse_pf_far);
+                p->cur_mask, lists, counts, p->sparse_pf_near, p->sparse_pf_far, p->cur_cherry_end);
         p->flat2_fn<<<(unsigned)((n_rows + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem,
                       p->cur_stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
             p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + p->list_pitch, counts + 1,
-            nullptr);
+            nullptr, p->cur_cherry_end);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
@@ -1691,6 +1804,19 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     if (p->wait_rows) SR2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->chunk_events[ci], 0));  // its rows' H2D copies
     DtlCosts cs{p->costs[0], p->costs[1], p->costs[2], p->costs[3]};
     const int H = (int)c.wave_off.size() - 2;  // highest wave
+    int n_inst = c.inst_end - c.inst_begin;
+    // one CTA per tree walks it top-down; frontier capacity from the largest tree of the chunk
+    int64_t max_nodes = 1;
+    for (int b = c.inst_begin; b < c.inst_end; ++b)
+        max_nodes = std::max<int64_t>(max_nodes, p->rows.node_off[b + 1] - p->rows.node_off[b]);
+    const int64_t cap = (max_nodes + 1) / 4 + 1;  // internal nodes of one depth <= leaves / 2
+    const size_t trace_smem = (size_t)2 * cap * sizeof(int2);
+    const bool per_tree = trace_smem + 1024 <= ctx->smem_optin && !getenv("SR2_DTL_TRACE_BY_WAVE");
+    // Virtual cherries: wave 1 is not launched and its rows are never written when every reader of
+    // a cherry row is a kernel that evaluates the closed form itself (sparse / flat2 waves, the
+    // per-tree selection + traceback) and nobody asks for the tables.
+    bool virt = p->flat2 && per_tree && ctx->dsp.anc_tab && ctx->dsp.lca_depth && !(p->flags & SR2_KEEP_TABLES) &&
+                !p->need_decoded_cost && !getenv("SR2_DTL_DENSE_CHERRIES") && !getenv("SR2_DTL_REAL_CHERRIES");
     // Path sets and sparse / dense row lists of every wave do not depend on DP values: they are
     // computed on a side stream, wave after wave, ahead of the wave kernels, which wait for the
     // event of their wave.
@@ -1705,7 +1831,11 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
                 h_chain = h;
                 break;
             }
-    if (h_chain >= H) h_chain = H + 1;  // a single wave gains nothing
+    for (int h = 2; h <= H && h < h_chain; ++h) {
+        const int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+        if (n > 0 && n < p->simd_min_rows) virt = false;  // a wave of the row-per-warp kernel reads real rows
+    }
+    p->cur_cherry_end = virt ? (int)(c.wave_off[2] - c.row_begin) : 0;
     std::vector<cudaEvent_t>& part_events = ctx->part_events[set];
     if (chain) {
         if (!ctx->part_stream[set]) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->part_stream[set], cudaStreamNonBlocking));
@@ -1752,7 +1882,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     }
     SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w0[ci], st));
     size_t part_k = 0;
-    for (int h = 1; h <= H && h < h_chain; ++h) {
+    for (int h = virt ? 2 : 1; h <= H && h < h_chain; ++h) {
         int64_t n = c.wave_off[h + 1] - c.wave_off[h];
         if (n <= 0) continue;
         p->cur_part_event = (chain && h > 1 && n >= p->simd_min_rows) ? part_events[part_k++] : nullptr;
@@ -1778,7 +1908,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         kp.thresh = p->flat2_thresh;
         p->flat2_chain_fn<<<(unsigned)((n + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem, st>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, first, c.row_begin, (int)n, p->cur_T, p->cur_tag, cs, kp,
-            p->cur_mask, p->flat2_sparse_max, 0, 0, nullptr, nullptr, sync);
+            p->cur_mask, p->flat2_sparse_max, 0, 0, nullptr, nullptr, sync, p->cur_cherry_end);
         SR2_CUDA(ctx, cudaGetLastError());
         ++p->n_waves;
         ++p->n_launch;
@@ -1793,14 +1923,6 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
             ++p->n_launch;
         }
     }
-    int n_inst = c.inst_end - c.inst_begin;
-    // one CTA per tree walks it top-down; frontier capacity from the largest tree of the chunk
-    int64_t max_nodes = 1;
-    for (int b = c.inst_begin; b < c.inst_end; ++b)
-        max_nodes = std::max<int64_t>(max_nodes, p->rows.node_off[b + 1] - p->rows.node_off[b]);
-    const int64_t cap = (max_nodes + 1) / 4 + 1;  // internal nodes of one depth <= leaves / 2
-    const size_t trace_smem = (size_t)2 * cap * sizeof(int2);
-    const bool per_tree = trace_smem + 1024 <= ctx->smem_optin && !getenv("SR2_DTL_TRACE_BY_WAVE");
     if (n_inst > 0 && per_tree) {
         int threads = 32;
         while (threads < 1024 && threads * 2 < cap) threads *= 2;  // measured on config #2 (cap 251): 32 / 64 / 128 / 256 -> 336 / 309 / 272 / 393 us
@@ -1813,7 +1935,8 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         dtl_select_trace_kernel<<<n_inst, threads, trace_smem, st>>>(
             ctx->dsp, p->rows.d_root_row, p->rows.d_root_node, c.inst_begin, c.row_begin, p->cur_T,
             p->need_decoded_cost ? p->cur_C : nullptr, p->cur_tag, p->rows.row_left, p->rows.row_right,
-            p->rows.row_cl, p->rows.row_cr, (int)cap, getenv("SR2_DTL_TRACE_CHECK") ? 1 : 0, p->d_min_cost, p->d_root_species, p->d_map);
+            p->rows.row_cl, p->rows.row_cr, (int)cap, getenv("SR2_DTL_TRACE_CHECK") ? 1 : 0, p->cur_cherry_end, cs,
+            p->d_min_cost, p->d_root_species, p->d_map);
         ++p->n_launch;
     } else if (n_inst > 0) {
         dtl_select_kernel<<<(n_inst + 7) / 8, 256, 0, st>>>(

@@ -62,6 +62,7 @@ struct DevSpecies {
     // table would be too large (S x D > 2^23 entries)
     const uint16_t* anc_tab;
     int anc_pitch;
+    const uint8_t* lca_depth;  // [S * S] depth of lca(a, b); null for large species trees
     // pathmask[s * mask_stride + w]: bit set of the species on the root path of s (s included), one
     // bit per BFS rank, mask_words = pitch / 32.  The finite cells of a DP row are a subset of the
     // union of the root paths of the leaf species below its object node.

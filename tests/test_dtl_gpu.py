@@ -202,6 +202,43 @@ def test_batched_wave_kernels_against_oracle(ctx, monkeypatch, n_s, n_o, n_trees
         assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"]
         lo, hi = batch.node_off[b], batch.node_off[b + 1]
         assert (mapping[lo:hi] == ref["mapping"]).all()
+    # without SR2_KEEP_TABLES the cherry rows are never written: their readers evaluate the closed form
+    again = ctx.dtl_run(batch.node_off, batch.left, batch.right, batch.leaf_species, batch.costs)
+    for a, b in zip((min_cost, root, mapping), again):
+        assert (a == b).all()
+
+
+@pytest.mark.parametrize("mode", ["chained", "waves"])
+def test_virtual_cherries_with_two_leaf_trees(ctx, monkeypatch, mode):
+    """Cherry rows are not materialised (no SR2_KEEP_TABLES): trees that ARE a cherry (selection from
+    the closed form), trees with one and with two cherry children at the root, leaves mapped to
+    internal species (one leaf species an ancestor of the other); against the oracle."""
+    monkeypatch.setenv("SR2_DTL_SIMD_MIN_ROWS", "1")
+    if mode == "waves":
+        monkeypatch.setenv("SR2_DTL_CHAIN_ROWS", "0")
+    species = synth.make_batch(12, 12, 1, seed=3)
+    rng = np.random.default_rng(8)
+    shapes = {
+        2: ([1, -1, -1], [2, -1, -1]),
+        3: ([1, 2, -1, -1, -1], [4, 3, -1, -1, -1]),
+        4: ([1, 2, -1, -1, 5, -1, -1], [4, 3, -1, -1, 6, -1, -1]),
+    }
+    lefts, rights, leaves = [], [], []
+    for k in range(90):
+        left, right = (np.array(v, np.int32) for v in shapes[2 + k % 3])
+        leaf = np.where(left < 0, rng.integers(0, species.n_species, len(left)), -1).astype(np.int32)
+        lefts.append(left), rights.append(right), leaves.append(leaf)
+    node_off = np.cumsum([0] + [len(x) for x in lefts]).astype(np.int64)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    for costs in ((0, 1, 1, 1, 1), (0, 3, 2, 1, 1), (0, 0, 0, 0, 0)):
+        costs = np.array(costs, np.int32)
+        min_cost, root, mapping = ctx.dtl_run(node_off, np.concatenate(lefts), np.concatenate(rights),
+                                              np.concatenate(leaves), costs)
+        for b in range(len(lefts)):
+            ref = oracle.dtl(species.parent, species.child0, species.child1, lefts[b], rights[b], leaves[b],
+                             costs, strict=False, tables=False)
+            assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"], (b, costs)
+            assert (mapping[node_off[b]:node_off[b + 1]] == ref["mapping"]).all(), (b, costs)
 
 
 def test_kernel_variants_agree_on_a_large_batch(ctx, monkeypatch):
@@ -224,6 +261,12 @@ def test_kernel_variants_agree_on_a_large_batch(ctx, monkeypatch):
     for a, b in zip(simd, dense):
         assert (a == b).all()
     monkeypatch.delenv("SR2_DTL_DENSE_CHERRIES")
+    # cherry rows written by the wave-1 kernel instead of being evaluated by their readers
+    monkeypatch.setenv("SR2_DTL_REAL_CHERRIES", "1")
+    real = ctx.dtl_run(*args)
+    for a, b in zip(simd, real):
+        assert (a == b).all()
+    monkeypatch.delenv("SR2_DTL_REAL_CHERRIES")
     # top waves: one chained launch for all waves above the cherries / one launch per wave;
     # traceback: one launch per height instead of one CTA per tree
     for chain_rows, by_wave in (("1000000000", "0"), ("0", "1")):
