@@ -62,6 +62,8 @@ struct DtlProblem {
     int* d_lists = nullptr;
     int* d_counts = nullptr;
     int cur_chunk = 0;
+    int cur_set = 0;                 // table set / stream pair of the chunk being enqueued
+    bool split_waves = false;        // dense rows of a wave on a second stream, next to the sparse rows
     cudaEvent_t cur_part_event = nullptr;  // set by dtl_enqueue_chunk for the wave being launched
     int64_t list_pitch = 0;          // = R
     int sparse_maxm = SPARSE_MAXM_DEFAULT;
@@ -1676,6 +1678,8 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
             p->flat2_fn = flat2_pick<false>(ctx->dsp.n_steps);
             p->flat2_chain_fn = flat2_pick<true>(ctx->dsp.n_steps);
             // waves below 4 x the resident rows of the kernel are latency-bound as launches of their own
+            p->split_waves = true;  // measured on config #2: 7.33 -> 7.15 ms per step
+            if (const char* sw = getenv("SR2_DTL_SPLIT_WAVES")) p->split_waves = sw[0] != '0';
             p->chain_rows = 4 * 8 * 4 * (int64_t)ctx->sm_count;
             if (const char* cr = getenv("SR2_DTL_CHAIN_ROWS")) p->chain_rows = atoll(cr);
             SR2_CUDA(ctx, cudaFuncSetAttribute((const void*)p->flat2_chain_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1738,17 +1742,39 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         int* counts = p->d_counts + ((size_t)p->cur_chunk * 65536 + h) * 2;
         int* lists = p->d_lists + row_begin;
         if (p->cur_part_event) SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, p->cur_part_event, 0));
+        // the dense list runs next to the sparse one on a stream of its own (both depend on the
+        // previous wave only): the tail of one launch overlaps the other
+        cudaStream_t ds = p->cur_stream;
+        cudaEvent_t join = nullptr;
+        if (p->split_waves && p->sparse_maxm > 0) {
+            const int set = p->cur_set;
+            if (!ctx->dense_stream[set]) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->dense_stream[set], cudaStreamNonBlocking));
+            auto& pool = ctx->split_events[set];
+            while (pool.size() < ctx->split_used[set] + 2) {
+                cudaEvent_t e;
+                SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                pool.push_back(e);
+            }
+            cudaEvent_t fork = pool[ctx->split_used[set]++];
+            join = pool[ctx->split_used[set]++];
+            ds = ctx->dense_stream[set];
+            SR2_CUDA(ctx, cudaEventRecord(fork, p->cur_stream));  // the previous wave (and the lists) are done
+            SR2_CUDA(ctx, cudaStreamWaitEvent(ds, fork, 0));
+        }
         if (p->sparse_maxm > 0) ++p->n_launch;  // two launches for this wave (the caller counts one)
         if (p->sparse_maxm > 0)
             dtl_wave_sparse_kernel<<<(unsigned)((n_rows + 31) / 32), 128, 4 * 8 * SPARSE_ROW_WORDS * sizeof(uint32_t),
                                      p->cur_stream>>>(
                 ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
                 p->cur_mask, lists, counts, p->sparse_pf_near, p->sparse_pf_far, p->cur_cherry_end);
-        p->flat2_fn<<<(unsigned)((n_rows + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem,
-                      p->cur_stream>>>(
+        p->flat2_fn<<<(unsigned)((n_rows + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem, ds>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
             p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + p->list_pitch, counts + 1,
             nullptr, p->cur_cherry_end);
+        if (join) {
+            SR2_CUDA(ctx, cudaEventRecord(join, ds));
+            SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, join, 0));
+        }
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
@@ -1799,6 +1825,8 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     p->cur_C = p->d_C ? p->d_C + set * table_elems : nullptr;
     p->cur_mask = p->d_mask + set * (table_elems / ctx->pitch * ctx->dsp.mask_stride);
     p->cur_chunk = ci;
+    p->cur_set = set;
+    ctx->split_used[set] = 0;  // (re-recording an event does not disturb waits already enqueued on it)
     cudaStream_t st = p->cur_stream;
     const RowChunk& c = p->rows.chunks[ci];
     if (p->wait_rows) SR2_CUDA(ctx, cudaStreamWaitEvent(st, ctx->chunk_events[ci], 0));  // its rows' H2D copies

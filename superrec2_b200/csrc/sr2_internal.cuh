@@ -132,6 +132,9 @@ struct sr2_ctx {
     cudaStream_t stream2 = nullptr;        // second compute stream of pipelined runs (lazy)
     cudaStream_t fill_stream = nullptr;    // device-side bucketing, second phase (lazy)
     cudaStream_t part_stream[2] = {nullptr, nullptr};  // path sets / row lists of the waves, ahead of the waves
+    cudaStream_t dense_stream[2] = {nullptr, nullptr}; // the dense rows of a wave, next to its sparse rows
+    std::vector<cudaEvent_t> split_events[2];
+    size_t split_used[2] = {0, 0};
     std::vector<cudaEvent_t> part_events[2];           // "lists of wave k are ready", per table set
     cudaStream_t upload_stream = nullptr;  // host-to-device row copies of pipelined runs (lazy)
     std::vector<cudaEvent_t> chunk_events; // "rows of chunk i are on the device"
