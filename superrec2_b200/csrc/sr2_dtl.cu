@@ -57,8 +57,8 @@ struct DtlProblem {
     uint32_t* d_mask = nullptr;      // [rows * pitch/32] root-path bit sets of the rows (flat2 only)
     uint32_t* cur_mask = nullptr;
     // Row lists of every wave (rebuilt by every solve, on a side stream ahead of the wave kernels):
-    // d_lists[0 * R + row] / d_lists[1 * R + row] = sparse / dense rows of the wave that starts at `row`
-    // (wave-local indices), d_counts[(chunk * 65536 + wave) * 2 + {0, 1}] = their lengths.
+    // d_lists[cls * R + row] = rows of class cls (0 / 1 = the two sparse tiers, 2 = dense) of the wave that starts
+    // at `row` (wave-local indices), d_counts[(chunk * 65536 + wave) * 4 + cls] = their lengths.
     int* d_lists = nullptr;
     int* d_counts = nullptr;
     int cur_chunk = 0;
@@ -67,6 +67,7 @@ struct DtlProblem {
     cudaEvent_t cur_part_event = nullptr;  // set by dtl_enqueue_chunk for the wave being launched
     int64_t list_pitch = 0;          // = R
     int sparse_maxm = SPARSE_MAXM_DEFAULT;
+    int sparse_small = 0;            // rows with at most this many path species take the first tier (0 = one tier)
     int n_waves = 0, n_launch = 0;
     // wave launch configuration (fixed per upload)
     int spad = 0, wave_warps = 0;
@@ -880,20 +881,24 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
 // 8 rows per warp, 1.5 KB of shared memory per row instead of 6.8 KB: 4 x as many rows in flight
 // and every lane busy where the dense sweeps leave 90 % of the lanes idle.
 // ---------------------------------------------------------------------------
-#define SPARSE_MAXM 64
-#define SPARSE_ROW_WORDS 392  // shared-memory words per row: Mc 128, Pc 128, el 64, mk/ml/mr/pre 16 each, and
-                              // 8 words of padding: the 4 rows of a half-warp start 8 banks apart
+#define SPARSE_MAXM 64        // largest path set of a "sparse" row
+#define SPARSE_MAXM_SMALL 44  // ... of the first tier: 1,056 bytes of shared memory per row, 6 CTAs (24 warps) per SM
+// shared-memory words per row for a tier of MAXM species: Mc 2 MAXM, Pc 2 MAXM, el MAXM, mk + pre (later the
+// links) MAXM, padded to 8 mod 32 so that the 4 rows of a half-warp start 8 banks apart: 392 for 64, 264 for 44
+#define SPARSE_ROW_WORDS(MAXM) ((MAXM) == 64 ? 392 : 264)
 
 // 4 lanes per row, one uint4 (128 root-path bits) per lane and child: 64 rows per CTA in flight.
+// Classes: 0 = at most max_small path species, 1 = at most max_sparse, 2 = the others ("dense");
+// lists[cls * list_pitch + i], counts[cls].
 __global__ void __launch_bounds__(256)
 dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                      int64_t row_begin, int64_t chunk_row0, int n_rows, uint32_t* __restrict__ rowmask,
-                     int max_sparse, int* __restrict__ lists, int list_pitch, int* __restrict__ counts) {
-    __shared__ int cta_cnt[2], cta_base[2];
+                     int max_small, int max_sparse, int* __restrict__ lists, int list_pitch, int* __restrict__ counts) {
+    __shared__ int cta_cnt[3], cta_base[3];
     const int sub = threadIdx.x & 3;
     const int local = blockIdx.x * 64 + (threadIdx.x >> 2);
     const int ms = sp.mask_stride, quads = ms >> 2;
-    if (threadIdx.x < 2) cta_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 3) cta_cnt[threadIdx.x] = 0;
     __syncthreads();
     int cls = -1, my_off = 0, cnt = 0;
     const bool valid = local < n_rows;
@@ -913,21 +918,22 @@ dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
     if (valid) {
-        cls = cnt <= max_sparse ? 0 : 1;
+        cls = cnt <= max_small ? 0 : (cnt <= max_sparse ? 1 : 2);
         if (sub == 0) my_off = atomicAdd(&cta_cnt[cls], 1);
     }
     __syncthreads();
-    if (threadIdx.x < 2) cta_base[threadIdx.x] = cta_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], cta_cnt[threadIdx.x]) : 0;
+    if (threadIdx.x < 3) cta_base[threadIdx.x] = cta_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], cta_cnt[threadIdx.x]) : 0;
     __syncthreads();
     if (cls >= 0 && sub == 0) lists[(size_t)cls * list_pitch + cta_base[cls] + my_off] = local;
 }
 
+template <int MAXM>
 __global__ void __launch_bounds__(128)
 dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                        int64_t row_begin, int64_t chunk_row0, int32_t* __restrict__ T, uint32_t* __restrict__ tags,
                        DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask, const int* __restrict__ row_list,
                        const int* __restrict__ list_count, int pf_near, int pf_far, int cherry_end) {
-    extern __shared__ uint32_t sp_smem[];  // [4 warps][8 rows][SPARSE_ROW_WORDS]
+    extern __shared__ uint32_t sp_smem[];  // [4 warps][8 rows][SPARSE_ROW_WORDS(MAXM)]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, sub = lane & 3;
     const int n_list = *list_count;
@@ -935,12 +941,12 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     if (first >= n_list) return;
     const bool valid = first + g < n_list;
     const int pitch = sp.pitch, mw = sp.mask_words, ms = sp.mask_stride;
-    uint32_t* base = sp_smem + (size_t)(warp * 8 + g) * SPARSE_ROW_WORDS;
+    uint32_t* base = sp_smem + (size_t)(warp * 8 + g) * SPARSE_ROW_WORDS(MAXM);
     uint2* Mc = reinterpret_cast<uint2*>(base);
-    uint2* Pc = Mc + SPARSE_MAXM;
-    uint32_t* el = base + 256;   // species | depth << 16
-    uint32_t* mk = el + 64;      // the row's path set
-    uint32_t* pre = mk + 48;     // pre[w] = path species in words < w; pre[mw] = m
+    uint2* Pc = Mc + MAXM;
+    uint32_t* el = base + 4 * MAXM;  // species | depth << 16
+    uint32_t* mk = el + MAXM;        // the row's path set (<= 16 words)
+    uint32_t* pre = mk + 16;         // pre[w] = path species in words < w; pre[mw] = m (<= 17 words)
     int64_t gr = 0;
     size_t slot = 0;
     int cl = -1, cr = -1, m = 0;
@@ -1072,7 +1078,7 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         }
     }
     __syncwarp();
-    uint32_t* lk = mk;  // [64] links, over the bit set and its prefix counts (dead from here on)
+    uint32_t* lk = mk;  // [MAXM] links, over the bit set and its prefix counts (dead from here on)
     for (int e = sub; e < m; e += 4) lk[e] = Pc[e].x;
     // the infinite value rows of the warp's 8 rows, all lanes together (before any finite cell)
     {
@@ -1508,9 +1514,9 @@ static int dtl_prepare(void* user) {
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_MASK, table_elems / ctx->pitch * ctx->dsp.mask_stride * sizeof(uint32_t) + 256, &ptr))) return rc;
     p->d_mask = (uint32_t*)ptr;
     p->list_pitch = std::max<int64_t>(p->rows.R, 1);
-    if ((rc = sr2_dev_reserve(ctx, DP_DTL_LISTS, (size_t)2 * p->list_pitch * sizeof(int), &ptr))) return rc;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_LISTS, (size_t)3 * p->list_pitch * sizeof(int), &ptr))) return rc;
     p->d_lists = (int*)ptr;
-    if ((rc = sr2_dev_reserve(ctx, DP_DTL_COUNTS, p->rows.chunks.size() * 2 * 65536 * sizeof(int), &ptr))) return rc;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_COUNTS, p->rows.chunks.size() * 4 * 65536 * sizeof(int), &ptr))) return rc;
     p->d_counts = (int*)ptr;
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_CHAIN, (size_t)2 * (std::max<int64_t>(p->rows.max_chunk_rows, 1) + 1) * sizeof(int), &ptr)))
         return rc;
@@ -1687,9 +1693,14 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
             // ceil(m / 32) sparse passes cost about as much as 2 dense chunks each (locating a lane's species)
             p->flat2_sparse_max = std::min(S, ctx->pitch / 4);
             if (const char* sm = getenv("SR2_FLAT2_SPARSE_MAX")) p->flat2_sparse_max = atoi(sm);
-            p->sparse_maxm = ctx->dsp.mask_words <= 15 ? SPARSE_MAXM : 0;
-            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)(4 * 8 * SPARSE_ROW_WORDS * sizeof(uint32_t))));
+            p->sparse_maxm = ctx->dsp.mask_words <= 16 ? SPARSE_MAXM : 0;
+            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_sparse_kernel<SPARSE_MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)(4 * 8 * SPARSE_ROW_WORDS(SPARSE_MAXM) * sizeof(uint32_t))));
+            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_sparse_kernel<SPARSE_MAXM_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)(4 * 8 * SPARSE_ROW_WORDS(SPARSE_MAXM_SMALL) * sizeof(uint32_t))));
+            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_sparse_kernel<SPARSE_MAXM_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            p->sparse_small = SPARSE_MAXM_SMALL;
+            if (const char* sm = getenv("SR2_SPARSE_SMALL")) p->sparse_small = std::min(atoi(sm), SPARSE_MAXM_SMALL);
             if (const char* sm = getenv("SR2_SPARSE_MAXM")) p->sparse_maxm = std::min(atoi(sm), SPARSE_MAXM);
             const int resident = 8 * 4 * ctx->sm_count;  // rows of the CTAs that run at one time
             p->flat2_pf_near = resident;
@@ -1739,7 +1750,7 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         kp.thresh = p->flat2_thresh;
         // path sets + the wave's sparse / dense row lists, then one launch per list (grids sized for
         // the whole wave: CTAs beyond a list's length return at once)
-        int* counts = p->d_counts + ((size_t)p->cur_chunk * 65536 + h) * 2;
+        int* counts = p->d_counts + ((size_t)p->cur_chunk * 65536 + h) * 4;
         int* lists = p->d_lists + row_begin;
         if (p->cur_part_event) SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, p->cur_part_event, 0));
         // the dense list runs next to the sparse one on a stream of its own (both depend on the
@@ -1761,15 +1772,23 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             SR2_CUDA(ctx, cudaEventRecord(fork, p->cur_stream));  // the previous wave (and the lists) are done
             SR2_CUDA(ctx, cudaStreamWaitEvent(ds, fork, 0));
         }
-        if (p->sparse_maxm > 0) ++p->n_launch;  // two launches for this wave (the caller counts one)
-        if (p->sparse_maxm > 0)
-            dtl_wave_sparse_kernel<<<(unsigned)((n_rows + 31) / 32), 128, 4 * 8 * SPARSE_ROW_WORDS * sizeof(uint32_t),
-                                     p->cur_stream>>>(
+        if (p->sparse_maxm > 0) {  // the two sparse tiers (the caller counts one launch for this wave)
+            if (p->sparse_small > 0) {
+                ++p->n_launch;
+                dtl_wave_sparse_kernel<SPARSE_MAXM_SMALL><<<(unsigned)((n_rows + 31) / 32), 128,
+                                                            4 * 8 * SPARSE_ROW_WORDS(SPARSE_MAXM_SMALL) * sizeof(uint32_t), p->cur_stream>>>(
+                    ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
+                    p->cur_mask, lists, counts, p->sparse_pf_near * 3 / 2, p->sparse_pf_far * 3 / 2, p->cur_cherry_end);
+            }
+            ++p->n_launch;
+            dtl_wave_sparse_kernel<SPARSE_MAXM><<<(unsigned)((n_rows + 31) / 32), 128,
+                                                  4 * 8 * SPARSE_ROW_WORDS(SPARSE_MAXM) * sizeof(uint32_t), p->cur_stream>>>(
                 ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
-                p->cur_mask, lists, counts, p->sparse_pf_near, p->sparse_pf_far, p->cur_cherry_end);
+                p->cur_mask, lists + p->list_pitch, counts + 1, p->sparse_pf_near, p->sparse_pf_far, p->cur_cherry_end);
+        }
         p->flat2_fn<<<(unsigned)((n_rows + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem, ds>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
-            p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + p->list_pitch, counts + 1,
+            p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + 2 * p->list_pitch, counts + 2,
             nullptr, p->cur_cherry_end);
         if (join) {
             SR2_CUDA(ctx, cudaEventRecord(join, ds));
@@ -1873,7 +1892,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         if (ci >= (p->two_streams ? 2 : 1)) SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->dtl_ev_done[ci - (p->two_streams ? 2 : 1)], 0));
         SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w0[ci], st));   // also orders the side stream after earlier
         SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->dtl_ev_w0[ci], 0));  // work of this stream (uploads, solves)
-        SR2_CUDA(ctx, cudaMemsetAsync(p->d_counts + (size_t)ci * 2 * 65536, 0, (size_t)2 * (H + 2) * sizeof(int), ps));
+        SR2_CUDA(ctx, cudaMemsetAsync(p->d_counts + (size_t)ci * 4 * 65536, 0, (size_t)4 * (H + 2) * sizeof(int), ps));
         size_t k = 0;
         for (int h = 1; h <= H; ++h) {
             int64_t n = c.wave_off[h + 1] - c.wave_off[h];
@@ -1882,8 +1901,8 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
             if (listed) {
                 dtl_partition_kernel<<<(unsigned)((n + 63) / 64), 256, 0, ps>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask,
-                    p->sparse_maxm, p->d_lists + c.wave_off[h], (int)p->list_pitch,
-                    p->d_counts + ((size_t)ci * 65536 + h) * 2);
+                    p->sparse_maxm > 0 ? p->sparse_small : 0, p->sparse_maxm, p->d_lists + c.wave_off[h], (int)p->list_pitch,
+                    p->d_counts + ((size_t)ci * 65536 + h) * 4);
                 if (part_events.size() <= k) {
                     cudaEvent_t e;
                     SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
