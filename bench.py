@@ -316,7 +316,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "dtl wave kernels: dtl_wave_sparse_kernel (rows with <= 64 root-path species, 50 % "
+                         "kernel": "dtl wave kernels: dtl_wave_sparse_kernel<44|64> (rows with <= 64 root-path species, 55 % "
                                    "of the step), dtl_wave_flat2_kernel (the other rows, 32 %, and the chained launch "
                                    "of the small top waves, 5 %), dtl_cherry_sparse_kernel (wave 1, 7 %)",
                          "peak_source": peak_src,
