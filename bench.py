@@ -318,7 +318,7 @@ def main():
                          "frac": achieved / peak, "traffic": traffic,
                          "kernel": "dtl wave kernels: dtl_wave_sparse_kernel<44|64> (rows with <= 64 root-path species, 55 % "
                                    "of the step), dtl_wave_flat2_kernel (the other rows, 32 %, and the chained launch "
-                                   "of the small top waves, 5 %), dtl_cherry_sparse_kernel (wave 1, 7 %)",
+                                   "of the small top waves, 5 %); wave 1 is virtual (readers evaluate the closed form of a cherry row)",
                          "peak_source": peak_src,
                          "bytes_per_cell": BYTES_PER_CELL,
                          "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL / waves_per_step,
