@@ -2191,7 +2191,7 @@ extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
                            uint32_t flags, int32_t* out_min_cost, int32_t* out_root_species,
                            int32_t* out_map_species) {
     if (!ctx) return SR2_ERR_ARG;
-    int pipeline_chunks = 3;
+    int pipeline_chunks = 2;  // + a half-sized first chunk: quarter, half, quarter of the batch (measured: 8.74 ms against 8.84 for 3)
     if (const char* v = getenv("SR2_PIPELINE_CHUNKS")) pipeline_chunks = std::max(1, atoi(v));
     DtlRunState rs{ctx, nullptr, out_min_cost, out_root_species, out_map_species, false, false, 0};
     RowHooks hooks;
