@@ -1690,8 +1690,9 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
             if (const char* cr = getenv("SR2_DTL_CHAIN_ROWS")) p->chain_rows = atoll(cr);
             SR2_CUDA(ctx, cudaFuncSetAttribute((const void*)p->flat2_chain_fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)p->flat2_smem));
-            // ceil(m / 32) sparse passes cost about as much as 2 dense chunks each (locating a lane's species)
-            p->flat2_sparse_max = std::min(S, ctx->pitch / 4);
+            // ceil(m / 32) sparse passes cost about as much as 2 dense chunks each (locating a lane's species);
+            // measured on config #2 (pitch 416): 104 / 144 / 176 / 208 / 256 -> 6.84 / 6.78 / 6.79 / 6.80 / 6.86 ms
+            p->flat2_sparse_max = std::min(S, ctx->pitch * 3 / 8);
             if (const char* sm = getenv("SR2_FLAT2_SPARSE_MAX")) p->flat2_sparse_max = atoi(sm);
             p->sparse_maxm = ctx->dsp.mask_words <= 16 ? SPARSE_MAXM : 0;
             SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_sparse_kernel<SPARSE_MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
