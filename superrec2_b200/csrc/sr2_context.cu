@@ -174,6 +174,8 @@ extern "C" void sr2_destroy(sr2_ctx* ctx) {
     for (int k = 0; k < 2; ++k) {
         if (ctx->part_stream[k]) cudaStreamDestroy(ctx->part_stream[k]);
         for (cudaEvent_t e : ctx->part_events[k]) cudaEventDestroy(e);
+        if (ctx->dense_stream[k]) cudaStreamDestroy(ctx->dense_stream[k]);
+        for (cudaEvent_t e : ctx->split_events[k]) cudaEventDestroy(e);
     }
     for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);
     for (auto* list : {&ctx->dtl_ev_w0, &ctx->dtl_ev_w1, &ctx->dtl_ev_done, &ctx->dtl_ev_copied})
