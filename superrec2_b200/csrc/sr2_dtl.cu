@@ -1883,6 +1883,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         const int64_t n = c.wave_off[h + 1] - c.wave_off[h];
         if (n > 0 && n < p->simd_min_rows) virt = false;  // a wave of the row-per-warp kernel reads real rows
     }
+    if (H < 1) virt = false;  // one-node trees only: no rows at all
     p->cur_cherry_end = virt ? (int)(c.wave_off[2] - c.row_begin) : 0;
     std::vector<cudaEvent_t>& part_events = ctx->part_events[set];
     if (chain) {

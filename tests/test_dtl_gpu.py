@@ -241,6 +241,31 @@ def test_virtual_cherries_with_two_leaf_trees(ctx, monkeypatch, mode):
             assert (mapping[node_off[b]:node_off[b + 1]] == ref["mapping"]).all(), (b, costs)
 
 
+def test_batch_of_cherries_and_single_nodes_only(ctx):
+    """Every tree is a cherry or a single node: no wave kernel runs at all, selection and traceback
+    work from the closed form."""
+    species = synth.make_batch(9, 9, 1, seed=4)
+    rng = np.random.default_rng(2)
+    lefts, rights, leaves = [], [], []
+    for k in range(70):
+        if k % 5 == 4:
+            left, right = np.array([-1], np.int32), np.array([-1], np.int32)
+        else:
+            left, right = np.array([1, -1, -1], np.int32), np.array([2, -1, -1], np.int32)
+        leaf = np.where(left < 0, rng.integers(0, species.n_species, len(left)), -1).astype(np.int32)
+        lefts.append(left), rights.append(right), leaves.append(leaf)
+    node_off = np.cumsum([0] + [len(x) for x in lefts]).astype(np.int64)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    costs = np.array((0, 2, 3, 1, 1), np.int32)
+    min_cost, root, mapping = ctx.dtl_run(node_off, np.concatenate(lefts), np.concatenate(rights),
+                                          np.concatenate(leaves), costs)
+    for b in range(len(lefts)):
+        ref = oracle.dtl(species.parent, species.child0, species.child1, lefts[b], rights[b], leaves[b],
+                         costs, strict=False, tables=False)
+        assert min_cost[b] == ref["min_cost"] and root[b] == ref["root_species"], b
+        assert (mapping[node_off[b]:node_off[b + 1]] == ref["mapping"]).all(), b
+
+
 def test_kernel_variants_agree_on_a_large_batch(ctx, monkeypatch):
     """Size-independent property at bench scale (config #2 shape, 600 trees): the batched-wave
     kernel and the row-per-warp kernel produce identical costs, roots and mappings."""
