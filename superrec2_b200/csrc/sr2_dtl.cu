@@ -743,10 +743,6 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
         const unsigned w = __ldg(sp.flat_sched + i * 32 + lane);
         sw[i] = w ? w + Mb * 0x10001u : 0u;  // 0 = this lane idles in step i
     }
-    // per-species words of the cells this lane will evaluate
-    unsigned meta[FLAT2_NCH];
-#pragma unroll
-    for (int j = 0; j < FLAT2_NCH; ++j) meta[j] = j < n_chunks ? __ldg(sp.cmeta + j * 32 + lane) : 0u;
     __syncwarp();
     if (lane == 0) {
         // a leaf child: 0 at its own species
@@ -845,14 +841,21 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
         for (int i0 = 0; i0 < m_set; i0 += 32) {
             const int i = min(i0 + lane, m_set - 1);
             // the word that holds the i-th species of the set: the number of words that end at or before i
+            // (binary search over the non-decreasing prefix counts; lanes past n_chunks hold m_set > i)
             int w = 0;
-            for (int q = 0; q < n_chunks; ++q) w += __shfl_sync(0xffffffffu, incl, q) <= i ? 1 : 0;
+#pragma unroll
+            for (int step = FLAT2_NCH / 2; step; step >>= 1)
+                if (__shfl_sync(0xffffffffu, incl, w + step - 1) <= i) w += step;
             const unsigned word = __shfl_sync(0xffffffffu, mword, w);
             const int before = __shfl_sync(0xffffffffu, excl, w);
             const int x = w * 32 + (int)__fns(word, 0, i - before + 1);
             if (i0 + lane < m_set) cell(x, __ldg(sp.cmeta + x));
         }
     } else {
+        // per-species words of the cells this lane evaluates
+        unsigned meta[FLAT2_NCH];
+#pragma unroll
+        for (int j = 0; j < FLAT2_NCH; ++j) meta[j] = j < n_chunks ? __ldg(sp.cmeta + j * 32 + lane) : 0u;
 #pragma unroll
         for (int j = 0; j < FLAT2_NCH; ++j)
             if (j < n_chunks) cell(j * 32 + lane, meta[j]);
