@@ -85,6 +85,7 @@ struct DtlProblem {
     bool flat2 = false;          // the default batched kernel when its preconditions hold
     size_t flat2_smem = 0;
     int flat2_rows = 8;
+    int flat2_low_waves = 5;     // waves up to this height launch an eighth of the dense-list CTAs (measured: 0 / 4 / 6 / 99 -> 6.70 / 6.59 / 6.59 / 6.66 ms)
     int flat2_sh = 0, flat2_thresh = 0;
     void (*flat2_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
                      Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int) = nullptr;
@@ -649,17 +650,20 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     __shared__ int cta_ticket;
     const int pitch = sp.pitch, rs = sp.flat_rs, n_chunks = pitch >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int local;
+    int local = 0;
     if (CHAIN) {
         if (threadIdx.x == 0) cta_ticket = atomicAdd(chain_sync, 1);
         __syncthreads();  // the only CTA-wide barrier: the warps are independent from here on
         local = cta_ticket * (blockDim.x >> 5) + warp;
         if (local >= n_rows) return;
-    } else {
-        local = blockIdx.x * (blockDim.x >> 5) + warp;
-        // the rows of this launch: the wave's "dense" list written by dtl_partition_kernel
-        if (local >= *list_count) return;
-        local = row_list[local];
+    }
+    // CHAIN = false: the rows of this launch are the wave's "dense" list written by dtl_partition_kernel.  The
+    // grid may be smaller than the list (low waves have few dense rows and are launched with a fraction of the
+    // wave's rows): a warp then strides over the list.
+    for (int pos = blockIdx.x * (blockDim.x >> 5) + warp;; pos += gridDim.x * (blockDim.x >> 5)) {
+    if (!CHAIN) {
+        if (pos >= *list_count) return;
+        local = row_list[pos];
     }
     const int64_t gr = row_begin + local;
     const size_t slot = (size_t)(gr - chunk_row0);
@@ -724,7 +728,7 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     // an earlier CTA) to pull ITS child rows into L2; the prefetches are issued before the sweeps.
     int cl2 = -1, cr2 = -1;
     if (!CHAIN) {
-        const int pos = blockIdx.x * (blockDim.x >> 5) + warp, n_list = *list_count;
+        const int n_list = *list_count;
         if (pf_far > 0 && pos + pf_far < n_list && lane < 2)
             asm volatile("prefetch.global.L2 [%0];" ::"l"((lane ? row_cr : row_cl) + row_begin + row_list[pos + pf_far]));
         if (pf_near > 0 && pos + pf_near < n_list) {
@@ -867,6 +871,9 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
             int* flag = chain_sync + 1 + local;
             asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
         }
+        return;
+    }
+    __syncwarp();  // the warp's shared-memory row is reused by its next list entry
     }
 }
 
@@ -1687,6 +1694,7 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
             p->flat2_fn = flat2_pick<false>(ctx->dsp.n_steps);
             p->flat2_chain_fn = flat2_pick<true>(ctx->dsp.n_steps);
             // waves below 4 x the resident rows of the kernel are latency-bound as launches of their own
+            if (const char* lw = getenv("SR2_FLAT2_LOW_WAVES")) p->flat2_low_waves = atoi(lw);
             p->split_waves = true;  // measured on config #2: 7.33 -> 7.15 ms per step
             if (const char* sw = getenv("SR2_DTL_SPLIT_WAVES")) p->split_waves = sw[0] != '0';
             p->chain_rows = 4 * 8 * 4 * (int64_t)ctx->sm_count;
@@ -1790,7 +1798,10 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
                 ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
                 p->cur_mask, lists + p->list_pitch, counts + 1, p->sparse_pf_near, p->sparse_pf_far, p->cur_cherry_end);
         }
-        p->flat2_fn<<<(unsigned)((n_rows + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem, ds>>>(
+        // low waves hold few dense rows: a fraction of the wave's CTAs (the kernel strides if that is too few)
+        int64_t dense_ctas = (n_rows + p->flat2_rows - 1) / p->flat2_rows;
+        if (h <= p->flat2_low_waves) dense_ctas = std::max<int64_t>((dense_ctas + 7) / 8, std::min<int64_t>(dense_ctas, 4 * ctx->sm_count));
+        p->flat2_fn<<<(unsigned)dense_ctas, 32 * p->flat2_rows, p->flat2_smem, ds>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
             p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + 2 * p->list_pitch, counts + 2,
             nullptr, p->cur_cherry_end);
