@@ -903,7 +903,8 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
 __global__ void __launch_bounds__(256)
 dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                      int64_t row_begin, int64_t chunk_row0, int n_rows, uint32_t* __restrict__ rowmask,
-                     int max_small, int max_sparse, int* __restrict__ lists, int list_pitch, int* __restrict__ counts) {
+                     int max_small, int max_sparse, int* __restrict__ lists, int list_pitch, int* __restrict__ counts,
+                     int cherry_rows) {
     __shared__ int cta_cnt[3], cta_base[3];
     const int sub = threadIdx.x & 3;
     const int local = blockIdx.x * 64 + (threadIdx.x >> 2);
@@ -915,12 +916,25 @@ dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     if (valid) {
         const int64_t gr = row_begin + local;
         const int cl = row_cl[gr], cr = row_cr[gr];
+        // a child's set: its row's (internal child), the root path of its species (leaf child), or -- for a
+        // cherry child, a slot below cherry_rows, whose own set is never stored -- the paths of its two leaves
         const uint4* a4 = reinterpret_cast<const uint4*>(cl >= 0 ? rowmask + (size_t)cl * ms : sp.pathmask + (size_t)(-1 - cl) * ms);
         const uint4* b4 = reinterpret_cast<const uint4*>(cr >= 0 ? rowmask + (size_t)cr * ms : sp.pathmask + (size_t)(-1 - cr) * ms);
+        const uint4* a5 = a4;
+        const uint4* b5 = b4;
+        if (cl >= 0 && cl < cherry_rows) {
+            a4 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)(-1 - row_cl[chunk_row0 + cl]) * ms);
+            a5 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)(-1 - row_cr[chunk_row0 + cl]) * ms);
+        }
+        if (cr >= 0 && cr < cherry_rows) {
+            b4 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)(-1 - row_cl[chunk_row0 + cr]) * ms);
+            b5 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)(-1 - row_cr[chunk_row0 + cr]) * ms);
+        }
         uint4* o4 = reinterpret_cast<uint4*>(rowmask + (size_t)(gr - chunk_row0) * ms);
         for (int w = sub; w < quads; w += 4) {
-            const uint4 a = a4[w], b = b4[w];
-            const uint4 o = make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
+            const uint4 a = a4[w], b = b4[w], a2 = a5[w], b2 = b5[w];
+            const uint4 o = make_uint4(a.x | b.x | a2.x | b2.x, a.y | b.y | a2.y | b2.y, a.z | b.z | a2.z | b2.z,
+                                       a.w | b.w | a2.w | b2.w);
             o4[w] = o;
             cnt += __popc(o.x) + __popc(o.y) + __popc(o.z) + __popc(o.w);
         }
@@ -1199,16 +1213,29 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 // Root-path bit set of every row of a wave computed by a kernel that does not maintain it itself:
 // mask(row) = mask(left child) | mask(right child), a leaf child contributing its species' path.
 __global__ void dtl_rowmask_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
-                                   int64_t row_begin, int64_t chunk_row0, int n_rows, uint32_t* __restrict__ rowmask) {
+                                   int64_t row_begin, int64_t chunk_row0, int n_rows, uint32_t* __restrict__ rowmask,
+                                   int cherry_rows) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int ms = sp.mask_stride, quads = ms >> 2;  // one uint4 per thread
     if (i >= (int64_t)n_rows * quads) return;
     const int64_t gr = row_begin + i / quads;
     const int w = (int)(i % quads);
-    const int cl = row_cl[gr], cr = row_cr[gr];
-    const uint4 a = reinterpret_cast<const uint4*>(cl >= 0 ? rowmask + (size_t)cl * ms : sp.pathmask + (size_t)(-1 - cl) * ms)[w];
-    const uint4 b = reinterpret_cast<const uint4*>(cr >= 0 ? rowmask + (size_t)cr * ms : sp.pathmask + (size_t)(-1 - cr) * ms)[w];
-    reinterpret_cast<uint4*>(rowmask + (size_t)(gr - chunk_row0) * ms)[w] = make_uint4(a.x | b.x, a.y | b.y, a.z | b.z, a.w | b.w);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const int c = side ? row_cr[gr] : row_cl[gr];
+        if (c >= cherry_rows) {
+            const uint4 a = reinterpret_cast<const uint4*>(rowmask + (size_t)c * ms)[w];
+            o = make_uint4(o.x | a.x, o.y | a.y, o.z | a.z, o.w | a.w);
+        } else {  // a leaf, or a cherry (whose set is not stored): root paths of the species
+            const int s0 = c < 0 ? -1 - c : -1 - row_cl[chunk_row0 + c];
+            const int s1 = c < 0 ? s0 : -1 - row_cr[chunk_row0 + c];
+            const uint4 a = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)s0 * ms)[w];
+            const uint4 b = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)s1 * ms)[w];
+            o = make_uint4(o.x | a.x | b.x, o.y | a.y | b.y, o.z | a.z | b.z, o.w | a.w | b.w);
+        }
+    }
+    reinterpret_cast<uint4*>(rowmask + (size_t)(gr - chunk_row0) * ms)[w] = o;
 }
 
 // the instantiation whose register-resident schedule is the shortest that holds n_steps
@@ -1910,15 +1937,18 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->dtl_ev_w0[ci], 0));  // work of this stream (uploads, solves)
         SR2_CUDA(ctx, cudaMemsetAsync(p->d_counts + (size_t)ci * 4 * 65536, 0, (size_t)4 * (H + 2) * sizeof(int), ps));
         size_t k = 0;
-        for (int h = 1; h <= H; ++h) {
+        // (wave 1 has no stored sets: a cherry's set is the two root paths of its leaves, which its parent's
+        // kernel reads from the species tables)
+        const int cherry_rows = H >= 1 ? (int)(c.wave_off[2] - c.row_begin) : 0;
+        for (int h = 2; h <= H; ++h) {
             int64_t n = c.wave_off[h + 1] - c.wave_off[h];
             if (n <= 0) continue;
-            const bool listed = h > 1 && h < h_chain && n >= p->simd_min_rows;
+            const bool listed = h < h_chain && n >= p->simd_min_rows;
             if (listed) {
                 dtl_partition_kernel<<<(unsigned)((n + 63) / 64), 256, 0, ps>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask,
                     p->sparse_maxm > 0 ? p->sparse_small : 0, p->sparse_maxm, p->d_lists + c.wave_off[h], (int)p->list_pitch,
-                    p->d_counts + ((size_t)ci * 65536 + h) * 4);
+                    p->d_counts + ((size_t)ci * 65536 + h) * 4, cherry_rows);
                 if (part_events.size() <= k) {
                     cudaEvent_t e;
                     SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -1929,7 +1959,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
             } else {
                 const int64_t quads = n * (ctx->dsp.mask_stride / 4);
                 dtl_rowmask_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, ps>>>(
-                    ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask);
+                    ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask, cherry_rows);
                 ++p->n_launch;
             }
         }
