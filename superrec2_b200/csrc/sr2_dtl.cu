@@ -1927,21 +1927,27 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     if (H < 1) virt = false;  // one-node trees only: no rows at all
     p->cur_cherry_end = virt ? (int)(c.wave_off[2] - c.row_begin) : 0;
     std::vector<cudaEvent_t>& part_events = ctx->part_events[set];
+    cudaStream_t ps = nullptr;
     if (chain) {
         if (!ctx->part_stream[set]) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->part_stream[set], cudaStreamNonBlocking));
-        cudaStream_t ps = ctx->part_stream[set];
+        ps = ctx->part_stream[set];
         if (p->wait_rows) SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->chunk_events[ci], 0));
         // the table set's path sets may still be read by the chunk that used the set before
         if (ci >= (p->two_streams ? 2 : 1)) SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->dtl_ev_done[ci - (p->two_streams ? 2 : 1)], 0));
         SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w0[ci], st));   // also orders the side stream after earlier
         SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->dtl_ev_w0[ci], 0));  // work of this stream (uploads, solves)
         SR2_CUDA(ctx, cudaMemsetAsync(p->d_counts + (size_t)ci * 4 * 65536, 0, (size_t)4 * (H + 2) * sizeof(int), ps));
-        size_t k = 0;
-        // (wave 1 has no stored sets: a cherry's set is the two root paths of its leaves, which its parent's
-        // kernel reads from the species tables)
-        const int cherry_rows = H >= 1 ? (int)(c.wave_off[2] - c.row_begin) : 0;
-        for (int h = 2; h <= H; ++h) {
-            int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+    }
+    // (wave 1 has no stored sets: a cherry's set is the two root paths of its leaves, which its parent's
+    // kernel reads from the species tables)
+    const int cherry_rows = H >= 1 ? (int)(c.wave_off[2] - c.row_begin) : 0;
+    size_t events_used = 0;
+    int sets_done = 1;  // path sets (and lists) are enqueued for the waves up to this height
+    // enqueue the side-stream work of the waves up to `upto`; returns the event of wave h's lists through *ev
+    auto enqueue_sets = [&](int upto, int want, cudaEvent_t* ev) -> int {
+        for (int h = sets_done + 1; h <= std::min(upto, H); ++h) {
+            sets_done = h;
+            const int64_t n = c.wave_off[h + 1] - c.wave_off[h];
             if (n <= 0) continue;
             const bool listed = h < h_chain && n >= p->simd_min_rows;
             if (listed) {
@@ -1949,12 +1955,14 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask,
                     p->sparse_maxm > 0 ? p->sparse_small : 0, p->sparse_maxm, p->d_lists + c.wave_off[h], (int)p->list_pitch,
                     p->d_counts + ((size_t)ci * 65536 + h) * 4, cherry_rows);
-                if (part_events.size() <= k) {
+                if (part_events.size() <= events_used) {
                     cudaEvent_t e;
                     SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                     part_events.push_back(e);
                 }
-                SR2_CUDA(ctx, cudaEventRecord(part_events[k++], ps));
+                SR2_CUDA(ctx, cudaEventRecord(part_events[events_used], ps));
+                if (h == want && ev) *ev = part_events[events_used];
+                ++events_used;
                 ++p->n_launch;
             } else {
                 const int64_t quads = n * (ctx->dsp.mask_stride / 4);
@@ -1963,26 +1971,41 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
                 ++p->n_launch;
             }
         }
-        // the chain's tail (path sets of the small top waves) joins the chunk's stream before it ends
-        if (part_events.size() <= k) {
-            cudaEvent_t e;
-            SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            part_events.push_back(e);
-        }
-        SR2_CUDA(ctx, cudaEventRecord(part_events[k], ps));
-        chain_tail = part_events[k];
-        SR2_CUDA(ctx, cudaGetLastError());
-    }
+        return SR2_OK;
+    };
     SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w0[ci], st));
-    size_t part_k = 0;
+    // The side stream stays two waves ahead of the wave kernels; enqueueing all of it first would keep
+    // the first wave kernel waiting for ~30 launches of host time.
+    std::vector<cudaEvent_t> list_event(H + 2, nullptr);
     for (int h = virt ? 2 : 1; h <= H && h < h_chain; ++h) {
         int64_t n = c.wave_off[h + 1] - c.wave_off[h];
+        if (chain) {
+            for (int a2 = sets_done + 1; a2 <= std::min(h + 2, H); ++a2) {
+                cudaEvent_t e = nullptr;
+                int rc = enqueue_sets(a2, a2, &e);
+                if (rc) return rc;
+                list_event[a2] = e;
+            }
+        }
         if (n <= 0) continue;
-        p->cur_part_event = (chain && h > 1 && n >= p->simd_min_rows) ? part_events[part_k++] : nullptr;
+        p->cur_part_event = (chain && h > 1 && n >= p->simd_min_rows) ? list_event[h] : nullptr;
         int rc = dtl_launch_wave(ctx, p, c, h, c.wave_off[h], n, cs);
         if (rc) return rc;
         ++p->n_waves;
         ++p->n_launch;
+    }
+    if (chain) {
+        // the rest of the side stream (path sets of the chained top waves) joins the chunk's stream
+        int rc = enqueue_sets(H, -1, nullptr);
+        if (rc) return rc;
+        if (part_events.size() <= events_used) {
+            cudaEvent_t e;
+            SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            part_events.push_back(e);
+        }
+        SR2_CUDA(ctx, cudaEventRecord(part_events[events_used], ps));
+        chain_tail = part_events[events_used];
+        SR2_CUDA(ctx, cudaGetLastError());
     }
     if (h_chain <= H) {
         const int64_t first = c.wave_off[h_chain], n = c.wave_off[H + 1] - first;
