@@ -892,10 +892,11 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
 // and every lane busy where the dense sweeps leave 90 % of the lanes idle.
 // ---------------------------------------------------------------------------
 #define SPARSE_MAXM 64        // largest path set of a "sparse" row
-#define SPARSE_MAXM_SMALL 44  // ... of the first tier: 1,056 bytes of shared memory per row, 6 CTAs (24 warps) per SM
+#define SPARSE_MAXM_SMALL 48  // ... of the first tier: 1,184 bytes of shared memory per row, 6 CTAs (24 warps) per SM
+                              // (measured: 44 / 48 / 52 / 56 species -> 6.57 / 6.52 / 6.76 / 6.74 ms per step)
 // shared-memory words per row for a tier of MAXM species: Mc 2 MAXM, Pc 2 MAXM, el MAXM, mk + pre (later the
-// links) MAXM, padded to 8 mod 32 so that the 4 rows of a half-warp start 8 banks apart: 392 for 64, 264 for 44
-#define SPARSE_ROW_WORDS(MAXM) ((MAXM) == 64 ? 392 : 264)
+// links) MAXM, padded to 8 mod 32 so that the 4 rows of a half-warp start 8 banks apart: 392 for 64, 296 for 48
+#define SPARSE_ROW_WORDS(MAXM) ((MAXM) == 64 ? 392 : 296)
 
 // 4 lanes per row, one uint4 (128 root-path bits) per lane and child: 64 rows per CTA in flight.
 // Classes: 0 = at most max_small path species, 1 = at most max_sparse, 2 = the others ("dense");
