@@ -19,6 +19,19 @@
 // (utils/dynamic_programming.py:228-238) because candidates are offered in BFS
 // order.  The loss term is added AFTER the arg-min, as the reference does
 // (reconciliation.py:97-108,153-183), so cell values depend on that tie-break.
+//
+// What runs by default for a batch whose species tree fits the batched kernels (|S| <= ~480,
+// costs that fit 32-bit keys); DESIGN.md section 4 has the measurements behind each piece:
+//   wave 1 (cherries)      not launched: readers evaluate the closed form (cherry_form)
+//   side stream            dtl_partition_kernel / dtl_rowmask_kernel: root-path bit set of every row,
+//                          per wave the lists of rows with <= 48 / <= 64 path species and of the others
+//   big waves              dtl_wave_sparse_kernel<48>, <64> (4 lanes per row, path species only) and
+//                          dtl_wave_flat2_kernel<NS, false> (a warp per dense row) on two streams
+//   small top waves        dtl_wave_flat2_kernel<NS, true>: one launch, rows chained by done flags
+//   selection + traceback  dtl_select_trace_kernel: one CTA per tree
+// Everything else (dtl_wave_kernel, dtl_wave_flat_kernel, dtl_cherry_*_kernel, dtl_select_kernel,
+// dtl_traceback_kernel, dtl_decoded_cost_kernel) is the general path: large species trees, large
+// costs, tables kept for the caller, charged speciations, cross-checks in the tests.
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -1691,8 +1704,8 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
     p->simd_ok = !(off && off[0] == '1') && S >= 2 && value_bits >= 8 && value_bits <= 27 &&
                  p->max_finite + slack < inf32 - slack;
     p->simd_thresh = (int)(inf32 - slack);
-    // small waves keep the row-per-warp kernel with 64-bit keys (latency-bound tops of the trees);
-    // the threshold can be overridden for tests (SR2_DTL_SIMD_MIN_ROWS)
+    // waves below this size that are not part of the chained launch keep the row-per-warp kernel with
+    // 64-bit keys; the threshold can be overridden for tests (SR2_DTL_SIMD_MIN_ROWS)
     p->simd_min_rows = 2 * (int64_t)ctx->sm_count;  // measured: e2e 11.5 -> 11.0 ms against 16 x SMs, value unchanged
     if (const char* min_rows = getenv("SR2_DTL_SIMD_MIN_ROWS")) p->simd_min_rows = atoll(min_rows);
     // "flat": the first batched form, selected with SR2_DTL_VARIANT=flat (a cross-check of flat2 in the tests)
