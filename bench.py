@@ -273,16 +273,16 @@ def main():
         peak, peak_src = measured_peak()
         achieved = cells * args.steps * BYTES_PER_CELL / (wave_ms * 1e-3) / 1e9
         # DRAM traffic per wave launch, from the ncu --set full captures under profiles/
-        # (r2d / r2h: dtl_wave_sparse_kernel 4.8 KB per row of 399 species = 12.1 B/cell with the r2h figures;
-        #  r1y: dtl_wave_flat2_kernel 12.1 B/cell; cherry rows (wave 1) are never written: their readers
-        #  evaluate the closed form), scaled to this batch's rows
+        # (r2o: dtl_wave_sparse_kernel<48> 0.69 GB read + 2.25 GB written for 1,000,032 rows of 399 species =
+        #  7.4 B/cell; r1y / r2m: dtl_wave_flat2_kernel 12.1 B/cell; cherry rows (wave 1) are never written: their
+        #  readers evaluate the closed form), scaled to this batch's rows (74 % of the other rows are sparse)
         internal = batch.left >= 0
         safe_l = np.where(internal, batch.left, 0) + np.repeat(batch.node_off[:-1], np.diff(batch.node_off))
         safe_r = np.where(internal, batch.right, 0) + np.repeat(batch.node_off[:-1], np.diff(batch.node_off))
         cherry = internal & ~internal[safe_l] & ~internal[safe_r]
         n_cherry, n_other = int(cherry.sum()), int(internal.sum() - cherry.sum())
         waves_per_step = max(1, ctx.timing().n_waves)
-        traffic = n_other * batch.n_species * 12.1 / waves_per_step
+        traffic = n_other * batch.n_species * (0.74 * 7.4 + 0.26 * 12.1) / waves_per_step
         line = {
             "metric": "dp_cells_per_s",
             "value": all_cells * args.steps / (elapsed_ms * 1e-3),
@@ -325,7 +325,7 @@ def main():
                          "wave_launches_per_step": waves_per_step,
                          "wave_ms_per_step": wave_ms / args.steps,
                          "traffic_source": "bytes per wave launch (average over the step's launches) from "
-                                           "ncu dram__bytes_read+write per row, profiles/r2d_sparse_ncu_details.csv (r2h: same kernel, 4.8 KB per row), r1y_flat2_ncu_details.csv"},
+                                           "ncu dram__bytes_read+write per row, profiles/r2o_sparse44_ncu_details.csv, r1y_flat2_ncu_details.csv / r2m_flat2_ncu_details.csv"},
             "checksum_min_costs": checksum,
         }
         if world == 1 and not args.no_cpu_baseline:
