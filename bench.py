@@ -316,7 +316,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "dtl wave kernels: dtl_wave_sparse_kernel<48|64> (rows with <= 64 root-path species, 55 % "
+                         "kernel": "dtl wave kernels: dtl_wave_sparse_kernel<38|57> (rows with <= 57 root-path species, 55 % "
                                    "of the step), dtl_wave_flat2_kernel (the other rows, 32 %, and the chained launch "
                                    "of the small top waves, 5 %); wave 1 is virtual (readers evaluate the closed form of a cherry row)",
                          "peak_source": peak_src,

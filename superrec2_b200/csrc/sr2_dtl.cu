@@ -44,7 +44,7 @@
 // ---------------------------------------------------------------------------
 // device-resident problem
 // ---------------------------------------------------------------------------
-#define SPARSE_MAXM_DEFAULT 64
+#define SPARSE_MAXM_DEFAULT 57
 struct DtlCosts;
 struct Key32;
 struct DtlProblem {
@@ -904,12 +904,12 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
 // 8 rows per warp, 1.5 KB of shared memory per row instead of 6.8 KB: 4 x as many rows in flight
 // and every lane busy where the dense sweeps leave 90 % of the lanes idle.
 // ---------------------------------------------------------------------------
-#define SPARSE_MAXM 64        // largest path set of a "sparse" row
-#define SPARSE_MAXM_SMALL 48  // ... of the first tier: 1,184 bytes of shared memory per row, 6 CTAs (24 warps) per SM
-                              // (measured: 44 / 48 / 52 / 56 species -> 6.57 / 6.52 / 6.76 / 6.74 ms per step)
+#define SPARSE_MAXM 57        // largest path set of a "sparse" row: 1,376 bytes of shared memory per row, 5 CTAs (20 warps) per SM
+#define SPARSE_MAXM_SMALL 38  // ... of the first tier: 928 bytes per row, 7 CTAs (28 warps) per SM
+// (measured, small / large tier -> ms per step: 44 / 64 -> 6.57, 48 / 64 -> 6.52, 52 / 64 -> 6.76, 48 / 57 -> 6.43, 38 / 57 -> 6.39)
 // shared-memory words per row for a tier of MAXM species: Mc 2 MAXM, Pc 2 MAXM, el MAXM, mk + pre (later the
-// links) MAXM, padded to 8 mod 32 so that the 4 rows of a half-warp start 8 banks apart: 392 for 64, 296 for 48
-#define SPARSE_ROW_WORDS(MAXM) ((MAXM) == 64 ? 392 : 296)
+// links) MAXM, padded to 8 or 24 mod 32 so that the 4 rows of a half-warp start 8 banks apart
+#define SPARSE_ROW_WORDS(MAXM) ((MAXM) == 38 ? 232 : 344)
 
 // 4 lanes per row, one uint4 (128 root-path bits) per lane and child: 64 rows per CTA in flight.
 // Classes: 0 = at most max_small path species, 1 = at most max_sparse, 2 = the others ("dense");
@@ -1831,13 +1831,13 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
                 dtl_wave_sparse_kernel<SPARSE_MAXM_SMALL><<<(unsigned)((n_rows + 31) / 32), 128,
                                                             4 * 8 * SPARSE_ROW_WORDS(SPARSE_MAXM_SMALL) * sizeof(uint32_t), p->cur_stream>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
-                    p->cur_mask, lists, counts, p->sparse_pf_near * 3 / 2, p->sparse_pf_far * 3 / 2, p->cur_cherry_end);
+                    p->cur_mask, lists, counts, p->sparse_pf_near * 7 / 4, p->sparse_pf_far * 7 / 4, p->cur_cherry_end);
             }
             ++p->n_launch;
             dtl_wave_sparse_kernel<SPARSE_MAXM><<<(unsigned)((n_rows + 31) / 32), 128,
                                                   4 * 8 * SPARSE_ROW_WORDS(SPARSE_MAXM) * sizeof(uint32_t), p->cur_stream>>>(
                 ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
-                p->cur_mask, lists + p->list_pitch, counts + 1, p->sparse_pf_near, p->sparse_pf_far, p->cur_cherry_end);
+                p->cur_mask, lists + p->list_pitch, counts + 1, p->sparse_pf_near * 5 / 4, p->sparse_pf_far * 5 / 4, p->cur_cherry_end);
         }
         // low waves hold few dense rows: a fraction of the wave's CTAs (the kernel strides if that is too few)
         int64_t dense_ctas = (n_rows + p->flat2_rows - 1) / p->flat2_rows;
