@@ -119,7 +119,7 @@ def time_cpu_port(batch, n_trees):
     from oracle import binding as oracle
     args = cpu_sample(batch, n_trees)
     start = time.perf_counter()
-    oracle.dtl_batch(*args, want_map=True)
+    oracle.dtl_batch(*args, want_map=True, threads=os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     seconds = time.perf_counter() - start
     cells = int((args[4] >= 0).sum()) * batch.n_species
     return cells / seconds, seconds

@@ -56,8 +56,11 @@ def dtl(parent, child0, child1, left, right, leaf_species, costs, strict=True, t
                 mapping=mapping)
 
 
-def dtl_batch(parent, child0, child1, node_off, left, right, leaf_species, costs, want_map=True):
+def dtl_batch(parent, child0, child1, node_off, left, right, leaf_species, costs, want_map=True, threads=None):
+    """Independent instances over OpenMP threads; ``threads`` overrides OMP_NUM_THREADS (bench.py)."""
     lib = load()
+    if threads:
+        lib.oracle_set_threads(c_int(int(threads)))
     parent, child0, child1 = _a32(parent), _a32(child0), _a32(child1)
     left, right, leaf_species, costs = _a32(left), _a32(right), _a32(leaf_species), _a32(costs)
     node_off = np.ascontiguousarray(node_off, dtype=np.int64)

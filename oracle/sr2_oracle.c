@@ -20,6 +20,9 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #define INF 0x3fffffff
 #define ERR_KEYERROR (-100) /* the reference would raise KeyError (SURVEY Hazard B) */
@@ -304,6 +307,16 @@ int oracle_dtl(int S, const int* parent, const int* c0, const int* c1, int G, co
     free(T);
     species_free(&sp);
     return rc;
+}
+
+/* Threads of the batch driver below (bench.py: launchers such as torchrun export OMP_NUM_THREADS=1,
+ * and the CPU arm is to use all host threads). */
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
 }
 
 /* Batch driver used by bench.py's CPU baseline: independent instances over OpenMP
