@@ -103,3 +103,33 @@ def superdtl(parent, child0, child1, left, right, leaf_species, leaf_bits, costs
         _p(mapping), _p(kind), syn.ctypes.data_as(u32))
     return dict(rc=rc, gain=gain, lca=lca, value=value, tag=tag, min_cost=min_cost.value,
                 root_species=root.value, mapping=mapping, kind=kind, syn=syn)
+
+
+def superdtl_batch(parent, child0, child1, node_off, left, right, leaf_species, leaf_bits, costs,
+                   want_nodes=False, threads=None):
+    """Independent binary instances over OpenMP threads -> (min_cost[B], root[B][, mapping, kind, syn])."""
+    lib = load()
+    if threads:
+        lib.oracle_set_threads(c_int(int(threads)))
+    parent, child0, child1 = _a32(parent), _a32(child0), _a32(child1)
+    left, right, leaf_species, costs = _a32(left), _a32(right), _a32(leaf_species), _a32(costs)
+    node_off = np.ascontiguousarray(node_off, dtype=np.int64)
+    leaf_bits = np.ascontiguousarray(leaf_bits, dtype=np.uint32).reshape(len(left), -1)
+    B, W = len(node_off) - 1, leaf_bits.shape[1]
+    min_cost = np.empty(B, np.int32)
+    root = np.empty(B, np.int32)
+    mapping = np.empty(len(left), np.int32) if want_nodes else None
+    kind = np.empty(len(left), np.int32) if want_nodes else None
+    syn = np.empty((len(left), W), np.uint32) if want_nodes else None
+    u32 = POINTER(ctypes.c_uint32)
+    lib.oracle_superdtl_batch.restype = c_int
+    rc = lib.oracle_superdtl_batch(
+        c_int(len(parent)), _p(parent), _p(child0), _p(child1), c_int(B), node_off.ctypes.data_as(_P64),
+        _p(left), _p(right), _p(leaf_species), c_int(W), leaf_bits.ctypes.data_as(u32), _p(costs),
+        _p(min_cost), _p(root), _p(mapping), _p(kind),
+        syn.ctypes.data_as(u32) if syn is not None else None)
+    if rc:
+        raise RuntimeError(f"oracle_superdtl_batch failed with {rc}")
+    if want_nodes:
+        return min_cost, root, mapping, kind, syn
+    return min_cost, root

@@ -25,6 +25,8 @@ Fixtures:
   superdtl_species_poly.json.gz  multifurcating species trees (and object trees), result only
   thl_internal_species.json.gz, superdtl_internal_species.json.gz
                            instances whose object leaves sit at internal species nodes, full tables
+  superdtl_all.json.gz     superdtl instances with the full RetentionPolicy.ALL solution set, solved
+                           three times each (`stable`: the reference's answer did not depend on the run)
   base_uspfs.json.gz       binary instances solved by usreconcile_base_uspfs (superdtl table
                            restricted to the LCA mapping) and by reconcile_lca, incl. the
                            instances of tests/compute/test_unordered_super_reconciliation.py
@@ -216,6 +218,29 @@ def thl_all_fixture(data):
     fixture["solutions"] = sorted(
         sorted((node.name, species.name) for node, species in out.object_species.items())
         for out in results)
+    return fixture
+
+
+def superdtl_all_fixture(data, runs=3):
+    """usreconcile_extended_uspfs with RetentionPolicy.ALL.  Under ALL the reference iterates Python
+    sets of tuples of TreeNode objects (hashed by address) while unioning gain sets in place (Hazard A),
+    so its synteny labels -- and through cost() the kept solutions -- can depend on the run.  Every
+    instance is therefore solved `runs` times on freshly parsed inputs; `stable` says whether all
+    runs returned the same set of output JSON documents."""
+    fixture = {"kind": "superdtl_all", "input": data}
+    seen = []
+    for _ in range(runs):
+        srec_input = SuperReconciliationInput.from_dict(data)
+        results = list(quiet(ref_usr.usreconcile_extended_uspfs, srec_input, RetentionPolicy.ALL))
+        seen.append(sorted(json.dumps(out.to_dict(), sort_keys=True) for out in results))
+        cost = num(results[0].cost()) if results else None
+    fixture["min_cost"] = cost
+    fixture["stable"] = all(item == seen[0] for item in seen)
+    fixture["solutions"] = seen[0]
+    # the order-independent projection: which (resolution, object -> species) assignments are optimal
+    fixture["mappings"] = sorted({json.dumps([json.loads(doc)["input"]["object_tree"],
+                                              json.loads(doc)["object_species"]], sort_keys=True)
+                                  for doc in seen[0]})
     return fixture
 
 
@@ -431,6 +456,29 @@ def main():
         data["species_tree"] = random_tree(rng5, [f"S{k}" for k in range(n_s)], "s", i % 4 < 2, polytomy=0.7)
         species_poly.append(superdtl_fixture(data, False))
     write("superdtl_species_poly.json.gz", species_poly)
+    # ---- superdtl, every solution (--solutions all) ---------------------------------------------
+    rng6 = random.Random(20261024)
+    every_super = []
+    # tests/compute/test_unordered_super_reconciliation.py:294-355 (test_transfers) and data/example.in.json
+    every_super.append(superdtl_all_fixture({
+        "object_tree": "((x_1,y_1)1,(x_2,y_2)2)3;",
+        "species_tree": "(X,Y)XY;",
+        "leaf_object_species": {"x_1": "X", "y_1": "Y", "x_2": "X", "y_2": "Y"},
+        "leaf_syntenies": {"x_1": list("abc"), "y_1": list("ab"), "x_2": list("bc"), "y_2": list("abc")},
+        "costs": dict(zip(COST_NAMES, [0, 1, 1, 1, 1])),
+    }))
+    every_super.append(superdtl_all_fixture(example))
+    while len(every_super) < 90:
+        i = len(every_super)
+        n_s = rng6.randint(1, 5)
+        n_o = rng6.randint(1, 7)
+        mode = ["default", "zero", "spe", "random"][i % 4]
+        fixture = superdtl_all_fixture(random_instance(
+            rng6, n_s, n_o, i % 3 != 2, mode, families=rng6.randint(1, 5),
+            polytomy=0.5 if i % 5 == 0 else 0.0, name_internal=i % 2 == 0))
+        if len(fixture["solutions"]) <= 2000:
+            every_super.append(fixture)
+    write("superdtl_all.json.gz", every_super)
     write("thl_internal_species.json.gz", inner_thl)
     write("superdtl_internal_species.json.gz", inner_super)
 

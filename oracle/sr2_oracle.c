@@ -187,7 +187,11 @@ int oracle_dtl(int S, const int* parent, const int* c0, const int* c1, int G, co
         }
         const entry_t* Tl = T + (size_t)left[u] * S;
         const entry_t* Tr = T + (size_t)right[u] * S;
-        for (int x = S - 1; x >= 0; --x) { /* any order: cells of one node are independent */
+        /* any order: cells of one node are independent (threads only matter for the full-size
+         * fixtures of oracle/make_fullsize_golden.py; inside oracle_dtl_batch this region is nested
+         * and therefore serial) */
+#pragma omp parallel for schedule(dynamic, 16) if ((long long)S * S > 4000000)
+        for (int x = S - 1; x >= 0; --x) {
             entry_t* cell = &T[(size_t)u * S + x];
             int val[3], ta[3], tb[3];
             if (c0[x] >= 0) {
@@ -451,6 +455,7 @@ int oracle_superdtl(int S, const int* parent, const int* c0, const int* c1, int 
             CELL(u, leaf_species[u], K_LCA).value = 0; /* Candidate(0): value only */
             continue;
         }
+#pragma omp parallel for schedule(dynamic, 16) if ((long long)S * S > 250000)
         for (int x = 0; x < S; ++x) {
             /* _compute_uspfs_entry (:147-297) */
             entry_t sub[2][2][M_COUNT];
@@ -610,4 +615,28 @@ int oracle_superdtl(int S, const int* parent, const int* c0, const int* c1, int 
     free(opar), free(odep), free(gain), free(L), free(T);
     species_free(&sp);
     return rc;
+}
+
+/* Batch driver for bench.py's CPU baseline of the resolution workloads and for
+ * oracle/make_fullsize_golden.py: independent binary instances (concatenated, instance-local child
+ * indices, as in include/sr2.h) over OpenMP threads; results only (no tables). */
+int oracle_superdtl_batch(int S, const int* parent, const int* c0, const int* c1, int B, const int64_t* node_off,
+                          const int* left, const int* right, const int* leaf_species, int W,
+                          const uint32_t* leaf_bits, const int* costs, int* out_min_cost,
+                          int* out_root_species, int* out_map, int* out_kind, uint32_t* out_syn) {
+    int rc_all = 0;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int b = 0; b < B; ++b) {
+        int64_t off = node_off[b];
+        int G = (int)(node_off[b + 1] - off);
+        int rc = oracle_superdtl(S, parent, c0, c1, G, left + off, right + off, leaf_species + off, W,
+                                 leaf_bits + off * W, costs, NULL, NULL, NULL, NULL, out_min_cost + b,
+                                 out_root_species + b, out_map ? out_map + off : NULL,
+                                 out_kind ? out_kind + off : NULL, out_syn ? out_syn + off * W : NULL);
+        if (rc) {
+#pragma omp critical
+            rc_all = rc;
+        }
+    }
+    return rc_all;
 }

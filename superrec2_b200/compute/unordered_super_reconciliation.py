@@ -89,6 +89,130 @@ def usreconcile_extended_uspfs(
     return usreconcile_extended_uspfs_sharded(srec_input, policy)
 
 
+#: widths of the packed best key ``cost << 40 | resolution << 16 | root`` (one 8-byte word for the
+#: cross-GPU min-reduce): the library refuses uploads whose ``cost()`` bound reaches 2^23 and
+#: instance numbers from 2^24 on
+KEY_COST_BITS, KEY_RESOLUTION_BITS, KEY_ROOT_BITS = 23, 24, 16
+
+
+def _batches(ctx, upload, first, last):
+    """Solve resolutions [first, last) in as few batches as fit in device memory; yields the
+    (cost, object resolution number, root) of every batch that has a solution."""
+    start, step = first, max(1, last - first)
+    while start < last:
+        count = min(step, last - start)
+        try:
+            upload(start, count)
+        except _lib.Sr2Error as err:
+            if err.code != -4 or count == 1:   # SR2_ERR_NOMEM: halve the batch
+                raise
+            step = (count + 1) // 2
+            continue
+        ctx.superdtl_solve()
+        cost, number, root, key = ctx.superdtl_best()
+        if root >= 0:
+            yield cost, number, root
+        start += count
+
+
+def solve_resolution_range(srec_input: SuperReconciliationInput, lo: int, hi: int, device: int = 0,
+                           allowed=None, prepared=None):
+    """
+    First strict minimum of ``cost()`` over (resolution number, root species in level order) for
+    the resolutions ``[lo, hi)`` of ``srec_input`` -- the running ``Entry(MIN, ANY)`` of the
+    reference's ``_uspfs`` (``:454-497``) restricted to a block of its outer loop.  Returns
+    ``(cost, resolution number, root species rank)`` or ``None`` when no resolution of the block
+    has a solution.  The tuple is compared lexicographically across blocks / ranks.
+    """
+    from ..utils.trees import count_resolutions, is_binary
+    costs = cost_vector(srec_input.costs)
+    ctx = _lib.default_context(device)
+    families = family_index(srec_input.leaf_syntenies)
+    total = srec_input.count_resolutions()
+    best = None
+    if hi <= lo:
+        return None
+    if is_binary(srec_input.species_lca.tree):
+        # one species tree for every resolution: unranking happens inside the library
+        species = flatten_species(srec_input.species_lca.tree)
+        ctx.set_species(species.parent, species.child0, species.child1)
+        if total == 1:
+            _, objects, _, bits = flatten_super(srec_input, species, families)
+            ctx.superdtl_upload([0, len(objects.nodes)], objects.left, objects.right,
+                                objects.leaf_species, bits, costs)
+            if allowed is not None:
+                ctx.superdtl_set_allowed(allowed(srec_input, objects, species))
+            ctx.superdtl_solve()
+            cost, number, root, _ = ctx.superdtl_best()
+            return (cost, number, root) if root >= 0 else None
+        if allowed is not None:
+            raise ValueError("a per-node species restriction needs a binary object tree")
+        from .flatten import flatten_polytomies
+        poly = flatten_polytomies(srec_input.object_tree, srec_input.leaf_object_species, species.rank)
+        bits = leaf_bitsets(poly.nodes, srec_input.leaf_syntenies, families)
+        for found in _batches(ctx, lambda start, count: ctx.resolutions_upload(
+                poly.child_off, poly.child_idx, poly.leaf_species, bits, costs, start, count), lo, hi):
+            best = found if best is None else min(best, found)
+        return best
+    # species polytomies: resolution number = object_number * n_species + species_number
+    # (reference model/reconciliation.py:171-174).  One batch of object resolutions per species
+    # resolution; the library orders a batch by (cost, object_number, root), which for a fixed
+    # species_number is the order of (cost, resolution number, root); resolution numbers are
+    # Python integers here, so products of large polytomies cannot overflow a packed field.
+    if allowed is not None:
+        raise ValueError("a per-node species restriction needs binary trees")
+    from ..utils.trees import unrank_resolution
+    from .flatten import flatten_polytomies
+    n_species = count_resolutions(srec_input.species_lca.tree)
+    leaf_species_nodes = set(srec_input.leaf_object_species.values())
+    for number in range(n_species):
+        first = (lo - number + n_species - 1) // n_species      # object numbers [first, last)
+        last = (hi - number + n_species - 1) // n_species
+        if last <= first:
+            continue
+        species = flatten_species(unrank_resolution(srec_input.species_lca.tree, number))
+        by_name = {node.name: rank for node, rank in species.rank.items()}
+        species_rank = {node: by_name[node.name] for node in leaf_species_nodes}
+        ctx.set_species(species.parent, species.child0, species.child1)
+        poly = flatten_polytomies(srec_input.object_tree, srec_input.leaf_object_species, species_rank)
+        bits = leaf_bitsets(poly.nodes, srec_input.leaf_syntenies, families)
+        for cost, obj_number, root in _batches(ctx, lambda start, count: ctx.resolutions_upload(
+                poly.child_off, poly.child_idx, poly.leaf_species, bits, costs, start, count), first, last):
+            found = (cost, obj_number * n_species + number, root)
+            best = found if best is None else min(best, found)
+    return best
+
+
+def materialise_resolution(srec_input: SuperReconciliationInput, found, device: int = 0,
+                           allowed=None) -> SuperReconciliationOutput:
+    """
+    The solution behind ``found = (cost, resolution number, root)``: that one resolution is
+    rebuilt exactly as the reference does (re-parsed trees, ``O#``/``S#`` labels) and decoded in
+    its own preorder numbering; the device must reproduce the cost and the root it reported.
+    """
+    cost, index, root_rank = found
+    costs = cost_vector(srec_input.costs)
+    ctx = _lib.default_context(device)
+    families = family_index(srec_input.leaf_syntenies)
+    names = list(families)
+    winner = srec_input.resolution(index)
+    winner.label_internal()
+    species, objects, _, bits = flatten_super(winner, None, families)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    ctx.superdtl_upload([0, len(objects.nodes)], objects.left, objects.right, objects.leaf_species,
+                        bits, costs)
+    if allowed is not None:
+        ctx.superdtl_set_allowed(allowed(winner, objects, species))
+    ctx.superdtl_solve()
+    min_cost, root, mapping, _, syn = ctx.superdtl_results()
+    if (int(min_cost[0]), int(root[0])) != (cost, root_rank):
+        raise _lib.Sr2Error(-5, "winning resolution does not reproduce its key")
+    object_species = {node: species.nodes[int(mapping[u])] for u, node in enumerate(objects.nodes)}
+    syntenies = {node: bits_to_families(syn[u], names) for u, node in enumerate(objects.nodes)}
+    return SuperReconciliationOutput(
+        input=winner, object_species=object_species, syntenies=syntenies, ordered=False)
+
+
 def usreconcile_extended_uspfs_sharded(
     srec_input: SuperReconciliationInput,
     policy: RetentionPolicy = RetentionPolicy.ANY,
@@ -100,124 +224,30 @@ def usreconcile_extended_uspfs_sharded(
 ) -> Set[SuperReconciliationOutput]:
     """
     ``usreconcile_extended_uspfs`` restricted to one contiguous block of resolution
-    numbers: shard ``i`` of ``n`` handles ``[i*R/n, (i+1)*R/n)``.  ``reduce_key(key) -> key``
-    is the cross-shard min-reduce of the packed ``(cost, resolution, root)`` key (an NCCL
-    all-reduce in ``superrec2_b200.dist``); the shard that owns the winning resolution
-    returns the solution, the others return an empty set.
+    numbers: shard ``i`` of ``n`` handles ``[i*R/n, (i+1)*R/n)``.  ``reduce_key(found) -> found``
+    is the cross-shard lexicographic min-reduce of ``(cost, resolution, root)`` (``None`` = this
+    shard has no solution; an NCCL all-reduce of the packed 8-byte key in
+    ``superrec2_b200.dist``); the shard that owns the winning resolution returns the solution,
+    the others return an empty set.
 
     ``allowed(bin_input, objects, species) -> int32[nodes]`` optionally restricts every object
     node of a BINARY input to one species rank (-1 = any): the ``allowed_species`` argument of the
     reference's ``_compute_uspfs_table`` (``:300-358``).
     """
+    if policy is RetentionPolicy.ALL:
+        if n_shards != 1 or allowed is not None:
+            raise NotImplementedError("--solutions all runs on one GPU, without species restrictions")
+        from .unordered_super_all import usreconcile_extended_uspfs_all
+        return usreconcile_extended_uspfs_all(srec_input, device)
     if policy is not RetentionPolicy.ANY:
-        raise NotImplementedError(
-            "only RetentionPolicy.ANY is implemented on the GPU path so far "
-            "(SURVEY.md section 8f item 1)")
-    from ..utils.trees import count_resolutions, is_binary
+        raise ValueError(f"unsupported retention policy {policy!r}")
     total = srec_input.count_resolutions()
     lo, hi = total * shard // n_shards, total * (shard + 1) // n_shards
-    costs = cost_vector(srec_input.costs)
-    ctx = _lib.default_context(device)
-    families = family_index(srec_input.leaf_syntenies)
-    names = list(families)
-    no_key = (1 << 64) - 1
-    best_key = no_key
-
-    if is_binary(srec_input.species_lca.tree):
-        # one species tree for every resolution: unranking happens inside the library
-        species = flatten_species(srec_input.species_lca.tree)
-        ctx.set_species(species.parent, species.child0, species.child1)
-        if total == 1:
-            if hi > lo:
-                _, objects, _, bits = flatten_super(srec_input, species, families)
-                ctx.superdtl_upload([0, len(objects.nodes)], objects.left, objects.right,
-                                    objects.leaf_species, bits, costs)
-                if allowed is not None:
-                    ctx.superdtl_set_allowed(allowed(srec_input, objects, species))
-                ctx.superdtl_solve()
-                best_key = ctx.superdtl_best()[3]
-        else:
-            from .flatten import flatten_polytomies
-            poly = flatten_polytomies(srec_input.object_tree, srec_input.leaf_object_species,
-                                      species.rank)
-            bits = leaf_bitsets(poly.nodes, srec_input.leaf_syntenies, families)
-            start, step = lo, max(1, hi - lo)
-            while start < hi:
-                count = min(step, hi - start)
-                try:
-                    ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits,
-                                           costs, start, count)
-                except _lib.Sr2Error as err:
-                    if err.code != -4 or count == 1:   # SR2_ERR_NOMEM: halve the batch
-                        raise
-                    step = (count + 1) // 2
-                    continue
-                ctx.superdtl_solve()
-                best_key = min(best_key, ctx.superdtl_best()[3])
-                start += count
-    else:
-        # species polytomies: resolution number = object_number * n_species + species_number
-        # (reference model/reconciliation.py:171-174).  One batch of object resolutions per
-        # species resolution; the library orders a batch by (cost, object_number, root), which
-        # for a fixed species_number is the order of (cost, resolution number, root), so the
-        # key is renumbered here and the minimum over species resolutions taken on the host.
-        from ..utils.trees import unrank_resolution
-        from .flatten import flatten_polytomies
-        n_species = count_resolutions(srec_input.species_lca.tree)
-        leaf_species_nodes = set(srec_input.leaf_object_species.values())
-        for number in range(n_species):
-            first = (lo - number + n_species - 1) // n_species      # object numbers [first, last)
-            last = (hi - number + n_species - 1) // n_species
-            if last <= first:
-                continue
-            species = flatten_species(unrank_resolution(srec_input.species_lca.tree, number))
-            by_name = {node.name: rank for node, rank in species.rank.items()}
-            species_rank = {node: by_name[node.name] for node in leaf_species_nodes}
-            ctx.set_species(species.parent, species.child0, species.child1)
-            poly = flatten_polytomies(srec_input.object_tree, srec_input.leaf_object_species,
-                                      species_rank)
-            bits = leaf_bitsets(poly.nodes, srec_input.leaf_syntenies, families)
-            start, step = first, last - first
-            while start < last:
-                count = min(step, last - start)
-                try:
-                    ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits,
-                                           costs, start, count)
-                except _lib.Sr2Error as err:
-                    if err.code != -4 or count == 1:   # SR2_ERR_NOMEM: halve the batch
-                        raise
-                    step = (count + 1) // 2
-                    continue
-                ctx.superdtl_solve()
-                key = ctx.superdtl_best()[3]
-                if key != no_key:
-                    resolution = ((key >> 16) & 0xFFFFFF) * n_species + number
-                    key = (key >> 40 << 40) | (resolution << 16) | (key & 0xFFFF)
-                    best_key = min(best_key, key)
-                start += count
-
-    global_key = reduce_key(best_key) if reduce_key is not None else best_key
-    if global_key == no_key or global_key != best_key:
+    best = solve_resolution_range(srec_input, lo, hi, device, allowed)
+    winner = reduce_key(best) if reduce_key is not None else best
+    if winner is None or winner != best:
         return set()
-    # materialise the winner: rebuild that one resolution exactly as the reference does
-    # (re-parsed trees, O#/S# labels) and decode it in its own preorder numbering
-    index = (global_key >> 16) & 0xFFFFFF
-    winner = srec_input.resolution(index)
-    winner.label_internal()
-    species, objects, _, bits = flatten_super(winner, None, families)
-    ctx.set_species(species.parent, species.child0, species.child1)
-    ctx.superdtl_upload([0, len(objects.nodes)], objects.left, objects.right, objects.leaf_species,
-                        bits, costs)
-    if allowed is not None:
-        ctx.superdtl_set_allowed(allowed(winner, objects, species))
-    ctx.superdtl_solve()
-    min_cost, root, mapping, _, syn = ctx.superdtl_results()
-    if (int(min_cost[0]), int(root[0])) != (global_key >> 40, global_key & 0xFFFF):
-        raise _lib.Sr2Error(-5, "winning resolution does not reproduce its key")
-    object_species = {node: species.nodes[int(mapping[u])] for u, node in enumerate(objects.nodes)}
-    syntenies = {node: bits_to_families(syn[u], names) for u, node in enumerate(objects.nodes)}
-    return {SuperReconciliationOutput(
-        input=winner, object_species=object_species, syntenies=syntenies, ordered=False)}
+    return {materialise_resolution(srec_input, winner, device, allowed)}
 
 
 def usreconcile_base_uspfs(
@@ -244,8 +274,11 @@ def usreconcile_base_uspfs(
     """
     from ..utils.trees import is_binary
     from .reconciliation import reconcile_lca
-    if not is_binary(srec_input.object_tree):
-        raise ValueError("base_uspfs needs a binary object tree (reconcile_lca maps two children per node)")
+    if not is_binary(srec_input.object_tree) or not is_binary(srec_input.species_lca.tree):
+        # the reference needs both: reconcile_lca unpacks two children per object node, and its LCA
+        # mapping is keyed by the nodes of the ORIGINAL trees, which binarize() only keeps when
+        # there is nothing to resolve (model/reconciliation.py:167-169)
+        raise ValueError("base_uspfs needs binary object and species trees")
 
     def lca_only(bin_input, objects, species):
         mapping = reconcile_lca(bin_input).object_species

@@ -82,6 +82,10 @@ struct SuperCosts {
 };
 
 #define DEC_NONE 0xffffu
+// The packed best key is cost << 40 | instance << 16 | root; costs stay below 2^23 so that the key
+// also stays below 2^63 (it crosses GPUs as a signed 64-bit all-reduce(MIN)).  Uploads whose cost()
+// bound (nodes x largest event term) reaches the limit are refused instead of truncated.
+#define SUPER_KEY_COST_LIMIT ((int64_t)1 << 23)
 
 // ---------------------------------------------------------------------------
 // synteny bitsets (gain sets and LCA sets)
@@ -905,8 +909,13 @@ extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_
                         "sr2_superdtl_upload: batch does not fit in device memory (split it into smaller batches)");
     if (p->rows.max_nodes > 65535)
         return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_superdtl_upload: more than 65535 nodes in one object tree");
-    rc = sr2_check_costs(ctx, "sr2_superdtl_upload", costs, p->rows.max_nodes, nullptr);
+    int64_t cost_bound = 0;
+    rc = sr2_check_costs(ctx, "sr2_superdtl_upload", costs, p->rows.max_nodes, &cost_bound);
     if (rc) return rc;
+    if (cost_bound >= SUPER_KEY_COST_LIMIT)
+        return sr2_fail(ctx, SR2_ERR_RANGE,
+                        "sr2_superdtl_upload: costs x tree size may overflow the 23-bit cost field of the packed "
+                        "(cost, instance, root) key");
 
     const int64_t R = p->rows.R;
     // global-id child arrays for the per-instance kernels
@@ -974,8 +983,13 @@ int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_w
     if (flags & SR2_KEEP_TABLES)
         return sr2_fail(ctx, SR2_ERR_ARG, "sr2_resolutions_upload: SR2_KEEP_TABLES is not available for shared rows "
                                           "(set SR2_RESOLUTIONS_UNSHARED=1)");
-    int rc = sr2_check_costs(ctx, "sr2_resolutions_upload", costs, plan.Gb, nullptr);
+    int64_t cost_bound = 0;
+    int rc = sr2_check_costs(ctx, "sr2_resolutions_upload", costs, plan.Gb, &cost_bound);
     if (rc) return rc;
+    if (cost_bound >= SUPER_KEY_COST_LIMIT)
+        return sr2_fail(ctx, SR2_ERR_RANGE,
+                        "sr2_resolutions_upload: costs x tree size may overflow the 23-bit cost field of the packed "
+                        "(cost, instance, root) key");
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
     sr2_free_super(ctx);
     const int S = ctx->S, W = n_words, Gb = plan.Gb;

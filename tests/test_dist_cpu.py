@@ -26,31 +26,58 @@ def test_key_packing_is_lexicographic():
     assert sr2_dist.unpack_key(sorted(keys)[1]) == (5, 2, 3)
 
 
-def _worker(rank, world, port, keys, results):
+def test_packed_key_rejects_fields_that_do_not_fit():
+    """no silent truncation of the 23/24/16-bit fields."""
+    for bad in [(1 << 23, 0, 0), (0, 1 << 24, 0), (0, 0, 1 << 16), (-1, 0, 0)]:
+        assert not sr2_dist.fits_packed_key(bad)
+        with pytest.raises(OverflowError):
+            sr2_dist.pack_key(*bad)
+    assert sr2_dist.fits_packed_key(None) and sr2_dist.fits_packed_key(((1 << 23) - 1, (1 << 24) - 1, 65535))
+
+
+def _worker(rank, world, port, founds, failed, results):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        out = sr2_dist.allreduce_min_key(keys[rank])
-        results[rank] = out
+        winner, any_failed = sr2_dist.allreduce_min_found(founds[rank], failed=failed[rank])
+        results[rank] = (winner, any_failed)
         # ownership rule used by usreconcile_extended_uspfs_sharded
-        results[world + rank] = int(out == keys[rank])
+        results[world + rank] = int(winner is not None and winner == founds[rank])
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("keys", [
-    [sr2_dist.pack_key(16, 5, 8), sr2_dist.pack_key(16, 20, 0)],
-    [sr2_dist.NO_KEY, sr2_dist.pack_key(3, 1, 2)],
-    [sr2_dist.NO_KEY, sr2_dist.NO_KEY],
-])
-def test_allreduce_min_key_gloo_world2(keys):
+def _spawn(founds, failed=(False, False)):
     with socket.socket() as sock:
         sock.bind(("127.0.0.1", 0))
         port = sock.getsockname()[1]
     manager = mp.Manager()
     results = manager.dict()
-    mp.spawn(_worker, args=(2, port, keys, results), nprocs=2, join=True)
-    assert results[0] == results[1] == min(keys)
+    mp.spawn(_worker, args=(2, port, list(founds), list(failed), results), nprocs=2, join=True)
+    return results
+
+
+@pytest.mark.parametrize("founds", [
+    [(16, 5, 8), (16, 20, 0)],
+    [None, (3, 1, 2)],
+    [None, None],
+    [(7, 3, 1), (7, 3, 1)],
+    # resolution numbers beyond the 24-bit field (products of two large polytomies): the
+    # all-gather fallback must still return the lexicographic minimum
+    [(9, (1 << 24) + 5, 2), (9, 77, 40)],
+    [(9, (1 << 30) + 5, 2), (9, (1 << 30) + 4, 40)],
+])
+def test_allreduce_min_found_gloo_world2(founds):
+    results = _spawn(founds)
+    present = [item for item in founds if item is not None]
+    want = min(present) if present else None
+    assert results[0] == results[1] == (want, False)
     owners = results[2] + results[3]
-    assert owners == (2 if keys[0] == keys[1] else 1)
+    assert owners == (0 if want is None else 2 if founds[0] == founds[1] else 1)
+
+
+def test_a_failed_rank_does_not_hang_the_collective():
+    """a rank whose local solve raised still joins the reduce and everyone learns."""
+    results = _spawn([(5, 1, 1), None], failed=(False, True))
+    assert results[0] == results[1] == (None, True)

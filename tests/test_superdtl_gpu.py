@@ -113,6 +113,35 @@ def test_best_key_orders_by_cost_then_instance(ctx):
     assert key == (cost << 40) | (index << 16) | root_species
 
 
+def test_large_costs_are_exact_or_refused(ctx):
+    """the packed best key keeps 23 bits of cost.  Costs whose cost() bound stays
+    below 2^23 are exact (tables, best key and results against the oracle); beyond it the upload
+    is refused with SR2_ERR_RANGE instead of truncating the key."""
+    for costs in [(3000, 20000, 15000, 700, 9000), (0, 40000, 40000, 1000, 40000)]:
+        batch = synth.make_batch(8, 12, 6, seed=77, costs=costs, n_families=6)
+        ctx.set_species(batch.parent, batch.child0, batch.child1)
+        ctx.superdtl_upload(batch.node_off, batch.left, batch.right, batch.leaf_species,
+                            batch.leaf_family_bits, batch.costs, index_base=5)
+        ctx.superdtl_solve()
+        min_cost, root, mapping, kind, syn = ctx.superdtl_results()
+        for b in range(batch.n_instances):
+            lo, hi = int(batch.node_off[b]), int(batch.node_off[b + 1])
+            ref = oracle.superdtl(batch.parent, batch.child0, batch.child1, *batch.instance(b),
+                                  batch.leaf_family_bits[lo:hi], batch.costs, tables=False)
+            assert (min_cost[b], root[b]) == (ref["min_cost"], ref["root_species"])
+            assert (mapping[lo:hi] == ref["mapping"]).all() and (syn[lo:hi] == ref["syn"]).all()
+        cost, index, root_species, key = ctx.superdtl_best()
+        first = int(np.flatnonzero(min_cost == min_cost.min())[0])
+        assert (cost, index, root_species) == (int(min_cost.min()), 5 + first, int(root[first]))
+        assert cost > 0 and key == (cost << 40) | (index << 16) | root_species
+    batch = synth.make_batch(8, 12, 2, seed=77, costs=(0, 1 << 20, 1 << 20, 1 << 18, 1 << 20), n_families=6)
+    ctx.set_species(batch.parent, batch.child0, batch.child1)
+    with pytest.raises(_lib.Sr2Error) as err:
+        ctx.superdtl_upload(batch.node_off, batch.left, batch.right, batch.leaf_species,
+                            batch.leaf_family_bits, batch.costs)
+    assert err.value.code == -3 and "packed" in str(err.value)
+
+
 # ------------------------------------------------------------------ resolutions at scale
 def _poly_setup(ctx, data):
     from superrec2_b200.compute.flatten import flatten_polytomies, flatten_species
@@ -179,8 +208,9 @@ def test_species_polytomies_sharded_entry_point(golden):
             for rank in range(world):
                 usreconcile_extended_uspfs_sharded(
                     srec_input, shard=rank, n_shards=world,
-                    reduce_key=lambda key: keys.append(key) or (1 << 64) - 1)
-            winner = min(keys)
+                    reduce_key=lambda found: keys.append(found))
+            keys = [key for key in keys if key is not None]
+            winner = min(keys) if keys else None
             found = []
             for rank in range(world):
                 found += list(usreconcile_extended_uspfs_sharded(
