@@ -120,6 +120,15 @@ class TreeNode:
             return []
         return [n for n in self.up.children if n is not self]
 
+    def iter_ancestors(self):
+        node = self
+        while node.up is not None:
+            node = node.up
+            yield node
+
+    def get_ancestors(self):
+        return list(self.iter_ancestors())
+
     def get_tree_root(self):
         node = self
         while node.up is not None:

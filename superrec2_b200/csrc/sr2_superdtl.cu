@@ -43,6 +43,7 @@ struct SuperProblem {
     uint8_t* d_row_flags = nullptr;                      // [R]
     int32_t* d_T = nullptr;                              // [rows*2*pitch]
     uint32_t* d_tag = nullptr;                           // [rows*2*pitch]
+    uint32_t* d_ev = nullptr;                            // [rows*2*pitch] shared rows: super_event_word of every cell
     uint16_t *d_dec = nullptr, *d_anc = nullptr;         // [N*S] (species<<1|kind), local index of the set owner
     uint32_t *d_tau = nullptr, *d_taumin = nullptr;      // [N*W*32], [N]
     int32_t* d_cost = nullptr;                           // [B*S] cost() of the decode from each root
@@ -174,14 +175,24 @@ __device__ __forceinline__ void sgroup_sync() {
 
 // one candidate: children at keys a / b; da, db = depth the cons/seg value is relative to,
 // or -1 for a "separate" key (raw value, no distance term).
-__device__ __forceinline__ void super_offer(u64 a, int da, u64 b, int db, int event, int floss, int& best,
-                                            unsigned& tag) {
+struct SuperPick {
+    int best;       // value of the cell so far
+    unsigned tag;   // (species << 1 | kind) of the left child, the same of the right child << 16
+    int which;      // candidate that won (0..5, the order of :289-297)
+    u64 ka, kb;     // its two keys (value | rank | kind | depth)
+};
+
+__device__ __forceinline__ void super_offer(u64 a, int da, u64 b, int db, int event, int floss, int which,
+                                            SuperPick& pick) {
     unsigned va = (unsigned)(a >> 32), vb = (unsigned)(b >> 32);
     if (va < (unsigned)SR2_INF && vb < (unsigned)SR2_INF) {
         int v = event + (int)va + (int)vb - floss * ((da < 0 ? 0 : da) + (db < 0 ? 0 : db));
-        if (v < best) {
-            best = v;
-            tag = (unsigned)((a >> 15) & 0xffffu) | ((unsigned)((b >> 15) & 0xffffu) << 16);
+        if (v < pick.best) {
+            pick.best = v;
+            pick.tag = (unsigned)((a >> 15) & 0xffffu) | ((unsigned)((b >> 15) & 0xffffu) << 16);
+            pick.which = which;
+            pick.ka = a;
+            pick.kb = b;
         }
     }
 }
@@ -190,34 +201,80 @@ __device__ __forceinline__ void super_offer(u64 a, int da, u64 b, int db, int ev
 #define SARR(base, spad, i, K, t) ((base) + (size_t)((((i) * 2 + (K)) * 3) + (t)) * (spad))
 enum { T_CONS = 0, T_SEG = 1, T_SEP = 2 };
 
-// Cell (u, x, K).  P0/P1: SEPMIN keys of child 0/1 at x.  Candidate order = :289-297.
-__device__ __forceinline__ void super_cell(const u64* base, int spad, int K, int x, int dx, int cx, bool is_root,
-                                           u64 P0, u64 P1, const SuperCosts& cs, int& best, unsigned& tag) {
+// Cell (u, x, K).  P0/P1: SEPMIN keys of child 0/1 at x (none at the root).  Candidate order = :289-297.
+__device__ __forceinline__ void super_cell(const u64* base, int spad, int K, int x, int dx, int cx, u64 P0, u64 P1,
+                                           const SuperCosts& cs, SuperPick& pick) {
     const u64* C0 = SARR(base, spad, 0, K, T_CONS);
     const u64* C1 = SARR(base, spad, 1, K, T_CONS);
     const u64* G0 = SARR(base, spad, 0, K, T_SEG);
     const u64* G1 = SARR(base, spad, 1, K, T_SEG);
-    best = SR2_INF;
-    tag = SR2_NO_TAG;
+    pick.best = SR2_INF;
+    pick.tag = SR2_NO_TAG;
+    pick.which = 0;
+    pick.ka = pick.kb = 0;
     if (cx >= 0) {
-        super_offer(C0[cx], dx + 1, C1[cx + 1], dx + 1, cs.spe, cs.floss, best, tag);  // left x right
-        super_offer(C0[cx + 1], dx + 1, C1[cx], dx + 1, cs.spe, cs.floss, best, tag);  // right x left
+        super_offer(C0[cx], dx + 1, C1[cx + 1], dx + 1, cs.spe, cs.floss, 0, pick);  // left x right
+        super_offer(C0[cx + 1], dx + 1, C1[cx], dx + 1, cs.spe, cs.floss, 1, pick);  // right x left
     }
     u64 c0 = C0[x], c1 = C1[x];
-    super_offer(c0, dx, G1[x], dx, cs.dup, cs.floss, best, tag);  // conserved x segment
-    super_offer(G0[x], dx, c1, dx, cs.dup, cs.floss, best, tag);  // segment x conserved
-    if (!is_root) {
-        super_offer(c0, dx, P1, -1, cs.hgt, cs.floss, best, tag);  // conserved x separate
-        super_offer(P0, -1, c1, dx, cs.hgt, cs.floss, best, tag);  // separate x conserved
-    }
+    super_offer(c0, dx, G1[x], dx, cs.dup, cs.floss, 2, pick);  // conserved x segment
+    super_offer(G0[x], dx, c1, dx, cs.dup, cs.floss, 3, pick);  // segment x conserved
+    super_offer(c0, dx, P1, -1, cs.hgt, cs.floss, 4, pick);     // conserved x separate
+    super_offer(P0, -1, c1, dx, cs.hgt, cs.floss, 5, pick);     // separate x conserved
 }
 
+// What SuperReconciliationOutput.cost() (model/reconciliation.py:273-365, 511-543) charges for a
+// node decoded through this cell, as far as it only depends on the cell: the event term
+// (node_event of (x, a, c) + its loss distances) << 2 | which segmental-loss terms the labelling adds:
+//   0 speciation: lc + rc    1 duplication: min(lc, rc)    2 transfer, left child kept: lc
+//   3 transfer, right child kept: rc.
+// The candidate that won fixes the relation of a and c to x: 0-1 sit below different children of x
+// (speciation), 2-3 both below x (speciation iff neither is x and they sit below different
+// children, else duplication -- cost() classifies the decoded triple, not the candidate), 4 keeps the
+// left child below x, 5 the right one (its left child is incomparable with x, never above it).
+enum { EV_CLASS_SPE = 0, EV_CLASS_DUP = 1, EV_CLASS_HGT_L = 2, EV_CLASS_HGT_R = 3 };
+__device__ __forceinline__ uint32_t super_event_word(const DevSpecies& sp, int x, int dx, int cx,
+                                                     const SuperPick& pick, const SuperCosts& cs) {
+    const int a = (int)((pick.ka >> 16) & 0xffffu), c = (int)((pick.kb >> 16) & 0xffffu);
+    const int da = (int)(pick.ka & 0x7fffu), dc = (int)(pick.kb & 0x7fffu);
+    int cost, cls;
+    if (pick.which >= 4) {
+        cls = pick.which == 4 ? EV_CLASS_HGT_L : EV_CLASS_HGT_R;
+        cost = cs.hgt + cs.floss * ((pick.which == 4 ? da : dc) - dx);
+    } else {
+        bool spec = pick.which < 2;
+        if (!spec && cx >= 0 && a != x && c != x) {
+            const int t1 = __ldg(sp.tin + cx + 1);
+            spec = (__ldg(sp.tin + a) < t1) != (__ldg(sp.tin + c) < t1);
+        }
+        cls = spec ? EV_CLASS_SPE : EV_CLASS_DUP;
+        cost = (spec ? cs.spe - 2 * cs.floss : cs.dup) + cs.floss * (da + dc - 2 * dx);
+    }
+    return ((uint32_t)cost << 2) | (uint32_t)cls;
+}
+
+// Topology of the species tree staged once per CTA behind the key rows, so that the level loops of
+// the sweeps never wait for global memory (ncu r3b: two dependent __ldg per level made a wave of
+// config #4 cost 56 us, two thirds of it at the level barriers):
+//   s_meta[S]     (child0 + 1) << 16 | depth      (DevSpecies::meta)
+//   s_lvl[D + 1]  offsets into the list of internal nodes per depth
+//   s_int[n_int]  level-order rank of the i-th internal node (its children are 2i+1, 2i+2)
+__host__ __device__ __forceinline__ size_t super_topology_bytes(int S, int D, int n_int) {
+    return ((size_t)S + (size_t)D + 1) * 4 + (((size_t)n_int + 1) & ~(size_t)1) * 2;
+}
+
+// One row = both kinds of one object node.  Three phases over the 12 key rows of the node's children:
+//   1. up-sweep of all rows (SUBMIN), one step per species level;
+//   2. top-down sweep of the four "separate" rows only (SEPMIN, in place);
+//   3. the cells, element-wise over the species with every lane busy: 6 candidates per kind.
+// TPR = 32: one warp per row (small species trees); TPR = 256: one CTA per row.
 template <int TPR>
-__global__ void __launch_bounds__(TPR == 32 ? 256 : TPR)
+__global__ void __launch_bounds__(256)
 superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                      const uint8_t* __restrict__ row_flags, int64_t row_begin, int64_t chunk_row0, int n_rows,
                      int32_t* __restrict__ T, uint32_t* __restrict__ tags, SuperCosts cs, int spad,
-                     const int32_t* __restrict__ row_node, const int32_t* __restrict__ allowed) {
+                     const int32_t* __restrict__ row_node, const int32_t* __restrict__ allowed,
+                     uint32_t* __restrict__ evs) {
     extern __shared__ u64 smem[];
     const int S = sp.S;
     int group, lane, groups_per_cta;
@@ -230,6 +287,13 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
         lane = threadIdx.x;
         groups_per_cta = 1;
     }
+    uint32_t* s_meta = reinterpret_cast<uint32_t*>(smem + (size_t)groups_per_cta * 12 * spad);
+    int32_t* s_lvl = reinterpret_cast<int32_t*>(s_meta + S);
+    uint16_t* s_int = reinterpret_cast<uint16_t*>(s_lvl + sp.D + 1);
+    for (int i = threadIdx.x; i < S; i += blockDim.x) s_meta[i] = __ldg(sp.meta + i);
+    for (int i = threadIdx.x; i <= sp.D; i += blockDim.x) s_lvl[i] = __ldg(sp.int_lvl_off + i);
+    for (int i = threadIdx.x; i < sp.n_internal; i += blockDim.x) s_int[i] = (uint16_t)__ldg(sp.int_list + i);
+    __syncthreads();
     int local = blockIdx.x * groups_per_cta + group;
     if (local >= n_rows) return;
     const int64_t gr = row_begin + local;
@@ -249,7 +313,7 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
         const int32_t* __restrict__ TA = c >= 0 ? T + ((size_t)c * 2 + 0) * sp.pitch : nullptr;
         const int32_t* __restrict__ TB = c >= 0 ? T + ((size_t)c * 2 + 1) * sp.pitch : nullptr;
         for (int y = lane; y < S; y += TPR) {
-            int d = __ldg(sp.depth + y);
+            int d = (int)(s_meta[y] & 0xffffu);
             int Araw = TA ? TA[y] : (y == -1 - c ? 0 : SR2_INF);
             int Braw = TB ? TB[y] : SR2_INF;
             int A = sat_add(Araw, cs.floss * d), B = sat_add(Braw, cs.floss * d);
@@ -266,11 +330,11 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     }
     sgroup_sync<TPR>();
 
-    // up-sweep of all 12 rows
+    // 1. up-sweep of all 12 rows
     for (int d = sp.D - 2; d >= 0; --d) {
-        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
+        const int b = s_lvl[d], e = s_lvl[d + 1];
         for (int i = b + lane; i < e; i += TPR) {
-            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
+            const int p = s_int[i], c = 2 * i + 1;
 #pragma unroll
             for (int a = 0; a < 12; ++a) {
                 u64* arr = base + (size_t)a * spad;
@@ -280,58 +344,44 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
         sgroup_sync<TPR>();
     }
 
+    // 2. "separate" rows: SEPMIN[child] = min(SEPMIN[parent], SUBMIN[sibling]), nothing at the root
+    if (lane < 4) SARR(base, spad, lane >> 1, lane & 1, T_SEP)[0] = SR2_KEY_NONE;
+    sgroup_sync<TPR>();
+    for (int d = 0; d < sp.D - 1; ++d) {
+        const int b = s_lvl[d], e = s_lvl[d + 1];
+        for (int i = b + lane; i < e; i += TPR) {
+            const int p = s_int[i], c = 2 * i + 1;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                u64* E = SARR(base, spad, a >> 1, a & 1, T_SEP);
+                const u64 Pp = E[p], m0 = E[c], m1 = E[c + 1];
+                E[c] = key_min(Pp, m1);
+                E[c + 1] = key_min(Pp, m0);
+            }
+        }
+        sgroup_sync<TPR>();
+    }
+
+    // 3. the cells
     int32_t* __restrict__ Tout0 = T + (slot * 2 + 0) * sp.pitch;
     int32_t* __restrict__ Tout1 = T + (slot * 2 + 1) * sp.pitch;
     uint32_t* __restrict__ Gout0 = tags + (slot * 2 + 0) * sp.pitch;
     uint32_t* __restrict__ Gout1 = tags + (slot * 2 + 1) * sp.pitch;
-
-    if (lane == 0) {
-        int cx = __ldg(sp.child0);
-        int best;
-        unsigned tag;
-        const bool skip = only >= 0 && only != 0;
-        super_cell(base, spad, 0, 0, 0, cx, true, SR2_KEY_NONE, SR2_KEY_NONE, cs, best, tag);
-        Tout0[0] = skip ? SR2_INF : best;
-        Gout0[0] = skip ? SR2_NO_TAG : tag;
-        super_cell(base, spad, 1, 0, 0, cx, true, SR2_KEY_NONE, SR2_KEY_NONE, cs, best, tag);
-        Tout1[0] = skip ? SR2_INF : best;
-        Gout1[0] = skip ? SR2_NO_TAG : tag;
-        for (int i = 0; i < 2; ++i)
-            for (int K = 0; K < 2; ++K) SARR(base, spad, i, K, T_SEP)[0] = SR2_KEY_NONE;
-    }
-    sgroup_sync<TPR>();
-
-    for (int d = 0; d < sp.D - 1; ++d) {
-        int b = __ldg(sp.int_lvl_off + d), e = __ldg(sp.int_lvl_off + d + 1);
-        for (int i = b + lane; i < e; i += TPR) {
-            int p = __ldg(sp.int_list + i), c = 2 * i + 1;
-            int cx0 = __ldg(sp.child0 + c), cx1 = __ldg(sp.child0 + c + 1);
+    for (int x = lane; x < S; x += TPR) {
+        const uint32_t m = s_meta[x];
+        const int dx = (int)(m & 0xffffu), cx = (int)(m >> 16) - 1;
+        const bool skip = only >= 0 && only != x;
 #pragma unroll
-            for (int K = 0; K < 2; ++K) {
-                u64* E0 = SARR(base, spad, 0, K, T_SEP);
-                u64* E1 = SARR(base, spad, 1, K, T_SEP);
-                u64 Pp0 = E0[p], Pp1 = E1[p];
-                u64 m00 = E0[c], m01 = E0[c + 1], m10 = E1[c], m11 = E1[c + 1];
-                // species c: incomparable = parent's incomparable + subtree of the sibling c+1
-                u64 Pc_0 = key_min(Pp0, m01), Pc_1 = key_min(Pp1, m11);
-                u64 Pd_0 = key_min(Pp0, m00), Pd_1 = key_min(Pp1, m10);
-                int best;
-                unsigned tag;
-                super_cell(base, spad, K, c, d + 1, cx0, false, Pc_0, Pc_1, cs, best, tag);
-                if (only >= 0 && only != c) best = SR2_INF, tag = SR2_NO_TAG;
-                (K ? Tout1 : Tout0)[c] = best;
-                (K ? Gout1 : Gout0)[c] = tag;
-                super_cell(base, spad, K, c + 1, d + 1, cx1, false, Pd_0, Pd_1, cs, best, tag);
-                if (only >= 0 && only != c + 1) best = SR2_INF, tag = SR2_NO_TAG;
-                (K ? Tout1 : Tout0)[c + 1] = best;
-                (K ? Gout1 : Gout0)[c + 1] = tag;
-                E0[c] = Pc_0;
-                E0[c + 1] = Pd_0;
-                E1[c] = Pc_1;
-                E1[c + 1] = Pd_1;
-            }
+        for (int K = 0; K < 2; ++K) {
+            SuperPick pick;
+            super_cell(base, spad, K, x, dx, cx, SARR(base, spad, 0, K, T_SEP)[x], SARR(base, spad, 1, K, T_SEP)[x],
+                       cs, pick);
+            const bool none = skip || pick.tag == SR2_NO_TAG;
+            (K ? Tout1 : Tout0)[x] = skip ? SR2_INF : pick.best;
+            (K ? Gout1 : Gout0)[x] = none ? SR2_NO_TAG : pick.tag;
+            // the fused decode kernel reads what cost() charges for the cell next to its tag
+            if (evs) evs[(slot * 2 + K) * sp.pitch + x] = none ? 0u : super_event_word(sp, x, dx, cx, pick, cs);
         }
-        sgroup_sync<TPR>();
     }
 }
 
@@ -435,65 +485,76 @@ __device__ __forceinline__ bool sp_anc(const DevSpecies& sp, int a, int b) {  //
     return ta <= tb && tb < __ldg(sp.tout + a);
 }
 
-// cost() of the decode from root species k of instance b (one thread each)
-__global__ void scost_kernel(DevSpecies sp, const int64_t* __restrict__ node_off, const int32_t* __restrict__ left,
-                             const int32_t* __restrict__ right, const int32_t* __restrict__ node_pre,
-                             int inst_begin, int n_inst, int W, const uint32_t* __restrict__ L,
-                             const uint32_t* __restrict__ tau, const uint32_t* __restrict__ taumin,
-                             const uint16_t* __restrict__ dec, const uint16_t* __restrict__ anc, SuperCosts cs,
-                             int32_t* __restrict__ cost, const int32_t* __restrict__ node_dag) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)n_inst * sp.S) return;
-    int b = inst_begin + (int)(i / sp.S), k = (int)(i % sp.S);
-    int64_t off = node_off[b], end = node_off[b + 1];
-    int total = SR2_INF;
-    if (dec[(size_t)off * sp.S + k] != DEC_NONE) {
-        total = 0;
-        for (int64_t u = off; u < end; ++u) {
-            int l = left[u];
-            if (l < 0) continue;
-            int r = right[u];
-            unsigned eu = dec[(size_t)u * sp.S + k], el = dec[(size_t)l * sp.S + k], er = dec[(size_t)r * sp.S + k];
-            int p = eu >> 1, a = el >> 1, c = er >> 1;
-            int dp = __ldg(sp.depth + p), da = __ldg(sp.depth + a), dc = __ldg(sp.depth + c);
-            bool pa = sp_anc(sp, p, a), pc = sp_anc(sp, p, c);
-            // labelling cost (model/reconciliation.py:511-543)
-            size_t ou = (size_t)off + anc[(size_t)u * sp.S + k], ol = (size_t)off + anc[(size_t)l * sp.S + k],
-                   orr = (size_t)off + anc[(size_t)r * sp.S + k];
-            unsigned su = ((unsigned)k << 16) | (unsigned)node_pre[u], sl = ((unsigned)k << 16) | (unsigned)node_pre[l],
-                     sr = ((unsigned)k << 16) | (unsigned)node_pre[r];
-            bool in_l = true, in_r = true;
-            // shared-row mode: the clean lca-sets live per dag node, the time stamps per tree node
-            size_t Lu = node_dag ? (size_t)node_dag[ou] : ou, Ll = node_dag ? (size_t)node_dag[ol] : ol,
-                   Lr = node_dag ? (size_t)node_dag[orr] : orr;
-            for (int w = 0; w < W; ++w) {
-                uint32_t mine = syn_word(L, Lu, tau, taumin, ou, W, w, su);
-                in_l &= (mine & ~syn_word(L, Ll, tau, taumin, ol, W, w, sl)) == 0;
-                in_r &= (mine & ~syn_word(L, Lr, tau, taumin, orr, W, w, sr)) == 0;
+// cost() of every decode (model/reconciliation.py:511-554): thread = (chunk of SCOST_NODES consecutive
+// nodes, root species k) adds the terms of its internal nodes to cost[instance * S + k] (zeroed by the
+// caller).  One thread per root walking the whole tree took 1.5 ms for ONE 1,999-node instance.
+#define SCOST_NODES 16
+__global__ void __launch_bounds__(128)
+scost_kernel(DevSpecies sp, const int64_t* __restrict__ node_off, const int32_t* __restrict__ left,
+             const int32_t* __restrict__ right, const int32_t* __restrict__ node_pre,
+             const int32_t* __restrict__ node_inst, int64_t n_nodes, int W, const uint32_t* __restrict__ L,
+             const uint32_t* __restrict__ tau, const uint32_t* __restrict__ taumin,
+             const uint16_t* __restrict__ dec, const uint16_t* __restrict__ anc, SuperCosts cs,
+             int32_t* __restrict__ cost, const int32_t* __restrict__ node_dag) {
+    const int k = blockIdx.y * blockDim.x + threadIdx.x;
+    if (k >= sp.S) return;
+    const int64_t u0 = (int64_t)blockIdx.x * SCOST_NODES, u1 = min(u0 + (int64_t)SCOST_NODES, n_nodes);
+    int cur = -1, total = 0;
+    bool valid = false;
+    int64_t off = 0;
+    for (int64_t u = u0; u < u1; ++u) {
+        int l = left[u];
+        if (l < 0) continue;
+        const int b = node_inst[u];
+        if (b != cur) {
+            if (valid && total) atomicAdd(&cost[(size_t)cur * sp.S + k], total);
+            cur = b;
+            total = 0;
+            off = node_off[b];
+            valid = dec[(size_t)off * sp.S + k] != DEC_NONE;  // roots without an entry decode nothing
+        }
+        if (!valid) continue;
+        int r = right[u];
+        unsigned eu = dec[(size_t)u * sp.S + k], el = dec[(size_t)l * sp.S + k], er = dec[(size_t)r * sp.S + k];
+        int p = eu >> 1, a = el >> 1, c = er >> 1;
+        int dp = __ldg(sp.depth + p), da = __ldg(sp.depth + a), dc = __ldg(sp.depth + c);
+        bool pa = sp_anc(sp, p, a), pc = sp_anc(sp, p, c);
+        // labelling cost (model/reconciliation.py:511-543)
+        size_t ou = (size_t)off + anc[(size_t)u * sp.S + k], ol = (size_t)off + anc[(size_t)l * sp.S + k],
+               orr = (size_t)off + anc[(size_t)r * sp.S + k];
+        unsigned su = ((unsigned)k << 16) | (unsigned)node_pre[u], sl = ((unsigned)k << 16) | (unsigned)node_pre[l],
+                 sr = ((unsigned)k << 16) | (unsigned)node_pre[r];
+        bool in_l = true, in_r = true;
+        // shared-row mode: the clean lca-sets live per dag node, the time stamps per tree node
+        size_t Lu = node_dag ? (size_t)node_dag[ou] : ou, Ll = node_dag ? (size_t)node_dag[ol] : ol,
+               Lr = node_dag ? (size_t)node_dag[orr] : orr;
+        for (int w = 0; w < W; ++w) {
+            uint32_t mine = syn_word(L, Lu, tau, taumin, ou, W, w, su);
+            in_l &= (mine & ~syn_word(L, Ll, tau, taumin, ol, W, w, sl)) == 0;
+            in_r &= (mine & ~syn_word(L, Lr, tau, taumin, orr, W, w, sr)) == 0;
+        }
+        int lc = in_l ? 0 : cs.sloss, rc = in_r ? 0 : cs.sloss;
+        // event (model/reconciliation.py:273-365); decodes of finite entries are never INVALID
+        if (pa && pc) {
+            int cx = __ldg(sp.child0 + p);
+            bool spec = false;
+            if (cx >= 0 && a != p && c != p) {
+                int t1 = __ldg(sp.tin + cx + 1);
+                spec = (__ldg(sp.tin + a) < t1) != (__ldg(sp.tin + c) < t1);
             }
-            int lc = in_l ? 0 : cs.sloss, rc = in_r ? 0 : cs.sloss;
-            // event (model/reconciliation.py:273-365); decodes of finite entries are never INVALID
-            if (pa && pc) {
-                int cx = __ldg(sp.child0 + p);
-                bool spec = false;
-                if (cx >= 0 && a != p && c != p) {
-                    int t1 = __ldg(sp.tin + cx + 1);
-                    spec = (__ldg(sp.tin + a) < t1) != (__ldg(sp.tin + c) < t1);
-                }
-                if (spec)
-                    total += cs.spe + cs.floss * (da + dc - 2 * dp - 2) + lc + rc;
-                else
-                    total += cs.dup + cs.floss * (da + dc - 2 * dp) + min(lc, rc);
-            } else if (pa) {
-                total += cs.hgt + cs.floss * (da - dp) + lc;  // left child kept (comparable)
-            } else {
-                // transfer with the right child kept; the left child's species is comparable
-                // with p only if it is an ancestor of p, which a decode never produces
-                total += cs.hgt + cs.floss * (dc - dp) + (sp_anc(sp, a, p) ? lc : rc);
-            }
+            if (spec)
+                total += cs.spe + cs.floss * (da + dc - 2 * dp - 2) + lc + rc;
+            else
+                total += cs.dup + cs.floss * (da + dc - 2 * dp) + min(lc, rc);
+        } else if (pa) {
+            total += cs.hgt + cs.floss * (da - dp) + lc;  // left child kept (comparable)
+        } else {
+            // transfer with the right child kept; the left child's species is comparable
+            // with p only if it is an ancestor of p, which a decode never produces
+            total += cs.hgt + cs.floss * (dc - dp) + (sp_anc(sp, a, p) ? lc : rc);
         }
     }
-    cost[(size_t)b * sp.S + k] = total;
+    if (valid && total) atomicAdd(&cost[(size_t)cur * sp.S + k], total);
 }
 
 // first strict minimum over the root species in level order (_uspfs :474-495), one warp per instance
@@ -839,6 +900,202 @@ __global__ void sfused_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__
     }
 }
 
+// Compact form of sfused_kernel for species trees of at most 127 nodes and resolved trees of at
+// most 254 nodes (BASELINE config #5: 59 and 65).  Same result, a third of the instructions and
+// half the shared memory (ncu r3b: sfused_kernel issued 10.6 k warp-instructions per tree at 18
+// warps per SM):
+//   * what cost() charges for a node beyond the segmental losses is a function of the table cell the
+//     node was decoded through, so the wave kernel stores it next to the tag (super_event_word) and
+//     the decode adds it up: no species look-ups, no event classification per (tree, root, node);
+//   * per (node, root) state is ONE 16-bit word: owner << 8 | species << 1 | kind while the node
+//     waits to be decoded, then owner << 8 | class << 2 | kinds of the two children for the labelling;
+//   * a child labelled INHERIT is labelled from the same, only growing, set as its parent at a later
+//     time, so its segmental-loss term is 0 and only LCA-kind children are compared;
+//   * the time stamps of the in-place unions (SURVEY.md Hazard A) are kept per family: thread k
+//     notes into whose set it merged family f (a family is gained at one node, so at most once per
+//     decode), then one pass finds the first root that merged f into each set.  No atomics, 8-bit
+//     entries; tau[a][f] = (first root, preorder position of the gain node of f).
+struct FusedLayout {
+    int lca, gain, pmask, slot;     // 32-bit word offsets
+    int ent;                        // byte offsets from here on
+    int left, right, pre, fam, owner, first, inner;
+    int bytes;
+};
+__host__ __device__ __forceinline__ FusedLayout fused_layout(int Gb, int S, int W) {
+    FusedLayout f;
+    const int F = 32 * W, Gb4 = (Gb + 3) & ~3;
+    f.lca = 0;
+    f.gain = f.lca + Gb * W;
+    f.pmask = f.gain + Gb * W;
+    f.slot = f.pmask + Gb * W;
+    f.ent = (f.slot + Gb) * 4;
+    f.left = f.ent + ((Gb * S + 1) & ~1) * 2;
+    f.right = f.left + Gb4;
+    f.pre = f.right + Gb4;
+    f.fam = f.pre + Gb4;
+    f.owner = f.fam + F;
+    f.first = f.owner + ((F * S + 3) & ~3);
+    f.inner = f.first + Gb * F;
+    f.bytes = f.inner + Gb4;
+    return f;
+}
+
+__global__ void __launch_bounds__(128)
+sfused_compact_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+                      const int32_t* __restrict__ node_slot, const int32_t* __restrict__ node_dag,
+                      const int32_t* __restrict__ node_pre, const uint32_t* __restrict__ tags,
+                      const uint32_t* __restrict__ evs, int W, const uint32_t* __restrict__ gain,
+                      const uint32_t* __restrict__ L, SuperCosts cs, int64_t index_base,
+                      int32_t* __restrict__ min_cost, int32_t* __restrict__ root_species,
+                      unsigned long long* __restrict__ best_key) {
+    extern __shared__ uint32_t fsm[];
+    const int S = sp.S, F = 32 * W;
+    const int b = blockIdx.x, k = threadIdx.x;
+    const int64_t off = (int64_t)b * Gb;
+    const FusedLayout lay = fused_layout(Gb, S, W);
+    uint32_t* sLca = fsm + lay.lca;
+    uint32_t* sGain = fsm + lay.gain;
+    uint32_t* sPmask = fsm + lay.pmask;
+    const int32_t* sSlot = reinterpret_cast<int32_t*>(fsm + lay.slot);
+    uint8_t* bytes = reinterpret_cast<uint8_t*>(fsm);
+    uint16_t* ent = reinterpret_cast<uint16_t*>(bytes + lay.ent);
+    uint8_t* sL = bytes + lay.left;
+    uint8_t* sR = bytes + lay.right;
+    uint8_t* sPre = bytes + lay.pre;
+    uint8_t* sFam = bytes + lay.fam;
+    uint8_t* sOwner = bytes + lay.owner;
+    uint8_t* sFirst = bytes + lay.first;
+    uint8_t* sInt = bytes + lay.inner;
+    __shared__ unsigned long long warp_best[4];
+    __shared__ int s_n_int;
+
+    // ---- the tree, and "nothing merged yet" ---------------------------------------------------
+    for (int i = threadIdx.x; i < (lay.inner - lay.owner) / 4; i += blockDim.x)
+        reinterpret_cast<uint32_t*>(sOwner)[i] = 0xffffffffu;           // sOwner and sFirst
+    for (int u = threadIdx.x; u < Gb; u += blockDim.x) {
+        const int lg = left[off + u];
+        sL[u] = lg < 0 ? 0xff : (uint8_t)(lg - (int)off);
+        sR[u] = lg < 0 ? 0xff : (uint8_t)(right[off + u] - (int)off);
+        reinterpret_cast<int32_t*>(fsm + lay.slot)[u] = node_slot[off + u];
+        sPre[u] = (uint8_t)node_pre[off + u];
+        const size_t dag = (size_t)node_dag[off + u] * W;
+        for (int w = 0; w < W; ++w) {
+            sLca[u * W + w] = L[dag + w];
+            uint32_t g = gain[dag + w];
+            sGain[u * W + w] = g;
+            sPmask[u * W + w] = 0;
+            while (g) {                                                   // a family is gained at one node
+                const int f = __ffs(g) - 1;
+                g &= g - 1;
+                sFam[w * 32 + f] = (uint8_t)u;
+            }
+        }
+    }
+    if (threadIdx.x < 32) {   // ids of the internal nodes, in id order (parents before children)
+        int count = 0;
+        for (int base = 0; base < Gb; base += 32) {
+            const int u = base + threadIdx.x;
+            const bool inner = u < Gb && left[off + u] >= 0;
+            const unsigned m = __ballot_sync(0xffffffffu, inner);
+            if (inner) sInt[count + __popc(m & ((1u << threadIdx.x) - 1))] = (uint8_t)u;
+            count += __popc(m);
+        }
+        if (threadIdx.x == 0) s_n_int = count;
+    }
+    __syncthreads();
+    const int n_int = s_n_int;
+
+    // ---- decode from root species k (thread k), event terms added on the way -------------------
+    bool ok = false;
+    int total = 0;
+    if (k < S) {
+        ok = Gb == 1 ? false : tags[((size_t)sSlot[0] * 2 + 0) * sp.pitch + k] != SR2_NO_TAG;  // kind LCA (:487)
+        if (ok) {
+            ent[k] = (uint16_t)(k << 1);
+            for (int j = 0; j < n_int; ++j) {
+                const int u = sInt[j];
+                const unsigned e = ent[u * S + k];
+                const unsigned own = e >> 8;
+                const size_t at = ((size_t)sSlot[u] * 2 + (e & 1)) * sp.pitch + ((e >> 1) & 0x7f);
+                const unsigned tag = tags[at], ev = evs[at];
+                const unsigned el = tag & 0xffffu, er = tag >> 16;
+                const int l = sL[u], r = sR[u];
+                ent[l * S + k] = (uint16_t)((((el & 1) ? own : (unsigned)l) << 8) | el);
+                ent[r * S + k] = (uint16_t)((((er & 1) ? own : (unsigned)r) << 8) | er);
+                ent[u * S + k] = (uint16_t)((own << 8) | ((ev & 3) << 2) | ((el & 1) << 1) | (er & 1));
+                total += (int)(ev >> 2);
+                // kind INHERIT: the child's gains go, in place, into the set of its owner (:390)
+                if ((el | er) & 1) {
+                    for (int w = 0; w < W; ++w) {
+                        uint32_t g = ((el & 1) ? sGain[l * W + w] : 0u) | ((er & 1) ? sGain[r * W + w] : 0u);
+                        while (g) {
+                            const int f = __ffs(g) - 1;
+                            g &= g - 1;
+                            sOwner[(w * 32 + f) * S + k] = (uint8_t)own;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // ---- first root that merged family f into the set of node a ---------------------------------
+    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+        for (int kk = 0; kk < S; ++kk) {
+            const int a = sOwner[f * S + kk];
+            if (a != 0xff && sFirst[a * F + f] == 0xff) {
+                sFirst[a * F + f] = (uint8_t)kk;
+                atomicOr(&sPmask[a * W + (f >> 5)], 1u << (f & 31));
+            }
+        }
+    }
+    __syncthreads();
+    // ---- segmental-loss terms of cost() on the labels the reference would report ----------------
+    u64 key = SR2_KEY_NONE;
+    if (ok) {
+        auto word = [&](int a, int w, int pre_n) {
+            uint32_t bits = sLca[a * W + w];
+            uint32_t cand = sPmask[a * W + w] & ~bits;
+            while (cand) {
+                const int f = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const int k1 = sFirst[a * F + w * 32 + f];
+                if (k1 < k || (k1 == k && sPre[sFam[w * 32 + f]] <= pre_n)) bits |= 1u << f;
+            }
+            return bits;
+        };
+        for (int j = 0; j < n_int; ++j) {
+            const int u = sInt[j];
+            const unsigned rec = ent[u * S + k];
+            const int cls = (rec >> 2) & 3;
+            bool need_l = !(rec & 2) && cls != EV_CLASS_HGT_R, need_r = !(rec & 1) && cls != EV_CLASS_HGT_L;
+            if (cls == EV_CLASS_DUP && (rec & 3)) need_l = need_r = false;  // min(lc, rc) with a zero term
+            if (!(need_l || need_r)) continue;
+            const int own = rec >> 8, l = sL[u], r = sR[u];
+            bool in_l = true, in_r = true;
+            for (int w = 0; w < W; ++w) {
+                const uint32_t mine = word(own, w, sPre[u]);
+                if (need_l) in_l &= (mine & ~word(l, w, sPre[l])) == 0;
+                if (need_r) in_r &= (mine & ~word(r, w, sPre[r])) == 0;
+            }
+            const int lc = need_l && !in_l ? cs.sloss : 0, rc = need_r && !in_r ? cs.sloss : 0;
+            total += cls == EV_CLASS_DUP ? min(lc, rc) : lc + rc;
+        }
+        key = ((u64)(unsigned)total << 32) | (unsigned)k;
+    }
+    for (int o = 16; o; o >>= 1) key = key_min(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if ((threadIdx.x & 31) == 0) warp_best[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) key = key_min(key, warp_best[w]);
+        const bool none = key == SR2_KEY_NONE;
+        const int cost = none ? SR2_INF : (int)(key >> 32), root = none ? -1 : (int)(key & 0xffffffffu);
+        min_cost[b] = cost;
+        root_species[b] = root;
+        if (!none) atomicMin(best_key, ((u64)(unsigned)cost << 40) | ((u64)(index_base + b) << 16) | (unsigned)root);
+    }
+}
+
 __global__ void iota_kernel(int32_t* __restrict__ out, int64_t n, int32_t start) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = start + (int32_t)i;
@@ -1038,7 +1295,7 @@ int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_w
     }
     for (int id = DP_S_LEFT; id < DP_COUNT; ++id) free_b += sr2_dev_pooled(ctx, id);
     size_t need = (size_t)N * (4 * 8 + (size_t)W * 4 + (size_t)W * 128 + (size_t)S * 4) + (size_t)D * W * 4 * 5 +
-                  (size_t)NS * ((size_t)ctx->pitch * 16 + 8) + (size_t)B * ((size_t)S * 4 + 16) + h32.size() * 4 +
+                  (size_t)NS * ((size_t)ctx->pitch * 24 + 8) + (size_t)B * ((size_t)S * 4 + 16) + h32.size() * 4 +
                   h64.size() * 8 + (64u << 20);
     if (free_b < need)
         return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_resolutions_upload: range does not fit in device memory");
@@ -1073,6 +1330,7 @@ int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_w
     SR2_RESERVE(DP_S_FLAGS, d_row_flags, (size_t)std::max<int64_t>(NS, 1));
     SR2_RESERVE(DP_S_T, d_T, (size_t)std::max<int64_t>(NS, 1) * 2 * ctx->pitch * 4);
     SR2_RESERVE(DP_S_TAG, d_tag, (size_t)std::max<int64_t>(NS, 1) * 2 * ctx->pitch * 4);
+    SR2_RESERVE(DP_S_EV, d_ev, (size_t)std::max<int64_t>(NS, 1) * 2 * ctx->pitch * 4);
     SR2_RESERVE(DP_S_DEC, d_dec, (size_t)N * S * 2);
     SR2_RESERVE(DP_S_ANC, d_anc, (size_t)N * S * 2);
     SR2_RESERVE(DP_S_TAU, d_tau, (size_t)N * W * 32 * 4);
@@ -1153,17 +1411,18 @@ static int super_configure(sr2_ctx* ctx, SuperProblem* p) {
     const int S = ctx->S;
     p->spad = (S + 1) & ~1;
     const size_t per_row = (size_t)12 * p->spad * sizeof(u64);
-    if (per_row > ctx->smem_optin)
+    const size_t topology = super_topology_bytes(S, ctx->D, ctx->n_internal);
+    if (per_row + topology > ctx->smem_optin)
         return sr2_fail(ctx, SR2_ERR_RANGE, "superdtl: species tree too large for one CTA's shared memory");
     if (S <= 256) {
         p->cta_per_row = false;
-        p->wave_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx->smem_optin - 1024) / per_row));
-        p->wave_smem = per_row * p->wave_warps;
+        p->wave_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx->smem_optin - 1024 - topology) / per_row));
+        p->wave_smem = per_row * p->wave_warps + topology;
         SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->wave_smem));
     } else {
         p->cta_per_row = true;
-        p->wave_smem = per_row;
+        p->wave_smem = per_row + topology;
         SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->wave_smem));
     }
@@ -1186,9 +1445,10 @@ static int super_decode_shared(sr2_ctx* ctx, SuperProblem* p, int* n_launch) {
     sdecode_walk_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
         ctx->dsp, B, Gb, p->d_left, p->d_right, p->d_node_slot, p->d_node_dag, p->d_node_pre, p->d_tag, W,
         p->d_gain, p->d_dec, p->d_anc, p->d_tau, p->d_taumin);
-    scost_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
-        ctx->dsp, p->d_node_off, p->d_left, p->d_right, p->d_node_pre, 0, B, W, p->d_L, p->d_tau, p->d_taumin,
-        p->d_dec, p->d_anc, cs, p->d_cost, p->d_node_dag);
+    SR2_CUDA(ctx, cudaMemsetAsync(p->d_cost, 0, std::max<size_t>((size_t)B * S * 4, 4), st));
+    scost_kernel<<<dim3(grid_for(N, SCOST_NODES), grid_for(S, 128)), 128, 0, st>>>(
+        ctx->dsp, p->d_node_off, p->d_left, p->d_right, p->d_node_pre, p->d_node_inst, N, W, p->d_L, p->d_tau,
+        p->d_taumin, p->d_dec, p->d_anc, cs, p->d_cost, p->d_node_dag);
     sselect_kernel<<<grid_for(B, 8), 256, 0, st>>>(ctx->dsp, 0, B, p->d_cost, p->d_dec, p->d_node_off,
                                                    p->d_min_cost, p->d_root_species);
     smaterialise_kernel<<<grid_for(N, 256), 256, 0, st>>>(
@@ -1252,11 +1512,11 @@ static int super_solve_shared(sr2_ctx* ctx, SuperProblem* p) {
         if (!p->cta_per_row) {
             superdtl_wave_kernel<32><<<grid_for(n, p->wave_warps), p->wave_warps * 32, p->wave_smem, st>>>(
                 ctx->dsp, p->d_slot_cl, p->d_slot_cr, p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad,
-                nullptr, nullptr);
+                nullptr, nullptr, p->d_ev);
         } else {
             superdtl_wave_kernel<256><<<(unsigned)n, 256, p->wave_smem, st>>>(
                 ctx->dsp, p->d_slot_cl, p->d_slot_cr, p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad,
-                nullptr, nullptr);
+                nullptr, nullptr, p->d_ev);
         }
         ++n_launch;
         ++n_waves;
@@ -1269,7 +1529,18 @@ static int super_solve_shared(sr2_ctx* ctx, SuperProblem* p) {
         const size_t fused_smem = ((size_t)Gb * W * 35 + Gb * 5) * 4 + (size_t)Gb * S * 4;
         const char* unfused = getenv("SR2_SUPERDTL_UNFUSED");
         p->fused = !(unfused && unfused[0] == '1') && S <= 1024 && fused_smem <= ctx->smem_optin;
-        if (p->fused) {
+        const char* wide = getenv("SR2_SUPERDTL_FUSED_WIDE");   // cross-check: the general fused kernel
+        const FusedLayout lay = fused_layout(Gb, S, W);
+        if (p->fused && !(wide && wide[0] == '1') && S <= 127 && Gb >= 2 && Gb <= 254 &&
+            (size_t)lay.bytes <= ctx->smem_optin) {
+            SR2_CUDA(ctx, cudaFuncSetAttribute(sfused_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               lay.bytes));
+            sfused_compact_kernel<<<B, (S + 31) / 32 * 32, lay.bytes, st>>>(
+                ctx->dsp, Gb, p->d_left, p->d_right, p->d_node_slot, p->d_node_dag, p->d_node_pre, p->d_tag, p->d_ev,
+                W, p->d_gain, p->d_L, cs, p->index_base, p->d_min_cost, p->d_root_species, p->d_best);
+            n_launch += 1;
+            p->materialised = false;
+        } else if (p->fused) {
             SR2_CUDA(ctx, cudaFuncSetAttribute(sfused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)fused_smem));
             sfused_kernel<<<B, (S + 31) / 32 * 32, fused_smem, st>>>(
@@ -1356,11 +1627,11 @@ extern "C" int sr2_superdtl_solve(sr2_ctx* ctx) {
         if (!p->cta_per_row) {
             superdtl_wave_kernel<32><<<grid_for(n, p->wave_warps), p->wave_warps * 32, p->wave_smem, st>>>(
                 ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, c.wave_off[h], c.row_begin, (int)n, p->d_T,
-                p->d_tag, cs, p->spad, rows.row_node, p->d_allowed);
+                p->d_tag, cs, p->spad, rows.row_node, p->d_allowed, nullptr);
         } else {
             superdtl_wave_kernel<256><<<(unsigned)n, 256, p->wave_smem, st>>>(
                 ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, c.wave_off[h], c.row_begin, (int)n, p->d_T,
-                p->d_tag, cs, p->spad, rows.row_node, p->d_allowed);
+                p->d_tag, cs, p->spad, rows.row_node, p->d_allowed, nullptr);
         }
         ++n_launch;
         ++n_waves;
@@ -1381,9 +1652,10 @@ extern "C" int sr2_superdtl_solve(sr2_ctx* ctx) {
                 p->d_tau, p->d_taumin);
             ++n_launch;
         }
-        scost_kernel<<<grid_for((int64_t)B * S, 128), 128, 0, st>>>(
-            ctx->dsp, p->d_node_off, p->d_left, p->d_right, rows.d_node_pre, 0, B, W, p->d_L, p->d_tau, p->d_taumin,
-            p->d_dec, p->d_anc, cs, p->d_cost, nullptr);
+        SR2_CUDA(ctx, cudaMemsetAsync(p->d_cost, 0, std::max<size_t>((size_t)B * S * 4, 4), st));
+        scost_kernel<<<dim3(grid_for(N, SCOST_NODES), grid_for(S, 128)), 128, 0, st>>>(
+            ctx->dsp, p->d_node_off, p->d_left, p->d_right, rows.d_node_pre, rows.d_node_inst, N, W, p->d_L,
+            p->d_tau, p->d_taumin, p->d_dec, p->d_anc, cs, p->d_cost, nullptr);
         sselect_kernel<<<grid_for(B, 8), 256, 0, st>>>(ctx->dsp, 0, B, p->d_cost, p->d_dec, p->d_node_off,
                                                        p->d_min_cost, p->d_root_species);
         smaterialise_kernel<<<grid_for(N, 256), 256, 0, st>>>(

@@ -83,3 +83,14 @@ def test_all_solutions_flag(tmp_path, golden):
     lines = [json.loads(line) for line in dst.read_text().splitlines()]
     got = sorted(sorted([k, v] for k, v in doc["object_species"].items()) for doc in lines)
     assert got == fixture["solutions"]
+
+
+def test_superdtl_all_solutions_flag(tmp_path, golden):
+    """`superdtl --solutions all` prints one JSON document per solution: the reference's set."""
+    fixture = next(f for f in golden("superdtl_all.json.gz") if 3 <= len(f["solutions"]) <= 40)
+    data = {k: v for k, v in fixture["input"].items() if k != "costs"}
+    proc, dst = _run(tmp_path, data, "superdtl", "--solutions", "all", *_cost_flags(fixture["input"]["costs"]))
+    assert proc.returncode == 0, proc.stderr
+    assert f"Minimum cost: {fixture['min_cost']}" in proc.stderr
+    got = sorted(json.dumps(json.loads(line), sort_keys=True) for line in dst.read_text().splitlines())
+    assert got == fixture["solutions"]

@@ -1,6 +1,7 @@
 """Host-side model (no GPU): newick/JSON round trips, label_internal, resolution order,
 cost() -- against the fixtures produced by the unmodified reference."""
 import json
+import os
 
 import pytest
 
@@ -166,3 +167,54 @@ def test_reconcile_lca_against_the_reference(golden):
         assert got == fixture["lca"]
         cost = output.cost()
         assert (None if cost == float("inf") else cost) == fixture["lca_cost"]
+
+
+def _conforming_outputs(golden):
+    """(fixture result JSON, expected cost) of instances whose leaves follow the reference's
+    ``<species>_<suffix>`` naming, which its ``draw`` layout requires (render/layout.py:124)."""
+    fixtures = (golden("crispr.json.gz") + golden("superdtl_reference.json.gz") +
+                golden("thl_reference_tests.json.gz") + golden("base_uspfs.json.gz")[:6])
+    return [(f["result"], f["min_cost"]) for f in fixtures if f.get("result")]
+
+
+def test_emitted_json_round_trips_through_the_output_readers(golden):
+    """the documents this package writes are what ``superrec2 draw`` reads
+    (``cli/draw.py:18-29`` -> ``(Super)ReconciliationOutput.from_dict``): every key the reader needs is
+    there, the parsed object re-serialises to the same document and has the printed cost."""
+    from superrec2_b200.model.reconciliation import ReconciliationOutput, SuperReconciliationOutput
+    outputs = _conforming_outputs(golden) + [
+        (f["result"], f["min_cost"]) for f in golden("thl_medium.json.gz") + golden("superdtl_poly.json.gz")
+        if f.get("result")]
+    assert len(outputs) > 40
+    for document, cost in outputs:
+        assert {"input", "object_species"} <= set(document)
+        assert {"object_tree", "species_tree", "leaf_object_species", "costs"} <= set(document["input"])
+        cls = SuperReconciliationOutput if "syntenies" in document else ReconciliationOutput
+        parsed = cls.from_dict(json.loads(json.dumps(document)))
+        assert parsed.to_dict() == document
+        assert list(parsed.to_dict()["object_species"]) == list(document["object_species"])
+        assert parsed.cost() == cost
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src"), reason="the reference only exists in the build container")
+def test_emitted_json_is_drawn_by_the_reference(golden):
+    """The UNMODIFIED reference's ``draw`` pipeline (reader, layout, TikZ renderer; only the TeX call that
+    measures labels is stubbed, ``oracle/draw_check.py``) accepts documents serialised by THIS package's
+    output classes and sees the same solution and the same cost."""
+    import subprocess
+    import sys
+    from superrec2_b200.model.reconciliation import ReconciliationOutput, SuperReconciliationOutput
+    outputs = _conforming_outputs(golden)
+    lines = []
+    for document, _ in outputs:
+        cls = SuperReconciliationOutput if "syntenies" in document else ReconciliationOutput
+        lines.append(json.dumps(cls.from_dict(document).to_dict()))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, "oracle", "draw_check.py")],
+                          input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    reports = [json.loads(line) for line in proc.stdout.splitlines()]
+    assert len(reports) == len(outputs)
+    for report, (_, cost) in zip(reports, outputs):
+        assert report["cost"] == cost and report["same_solution"] and report["same_trees"]
+        assert report["tikz_chars"] > 500

@@ -290,3 +290,49 @@ def test_base_uspfs_against_the_reference(golden):
         (result,) = results
         assert result.to_dict() == fixture["result"]
         assert result.cost() == fixture["min_cost"]
+
+
+def test_all_solutions_against_the_reference(golden):
+    """``--solutions all`` (RetentionPolicy.ALL): the whole set of minimum-cost solutions -- winning
+    resolutions, mappings AND synteny labels -- equals the set the unmodified reference returned, on
+    90 instances (binary and multifurcating) whose reference answer was the same in three runs
+    (``stable``; see compute/unordered_super_all.py for what can depend on the run in the reference)."""
+    import json
+    fixtures = golden("superdtl_all.json.gz")
+    assert sum(len(fixture["solutions"]) > 1 for fixture in fixtures) >= 30
+    for fixture in fixtures:
+        srec_input = SuperReconciliationInput.from_dict(fixture["input"])
+        results = usreconcile_extended_uspfs(srec_input, RetentionPolicy.ALL)
+        got = sorted(json.dumps(out.to_dict(), sort_keys=True) for out in results)
+        mappings = sorted({json.dumps([json.loads(doc)["input"]["object_tree"], json.loads(doc)["object_species"]],
+                                      sort_keys=True) for doc in got})
+        assert mappings == fixture["mappings"]          # the order-independent projection
+        if fixture["stable"]:
+            assert got == fixture["solutions"]
+        if results:
+            assert {out.cost() for out in results} == {fixture["min_cost"]}
+        # ANY returns one of them
+        (one,) = usreconcile_extended_uspfs(srec_input, RetentionPolicy.ANY) or (None,)
+        if one is not None:
+            assert json.dumps(one.to_dict(), sort_keys=True) in fixture["solutions"]
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_fused_decode_kernels_agree_with_the_unfused_path(ctx, monkeypatch, wide):
+    """The compact fused kernel (event words from the table, per-family time stamps), the general fused
+    kernel and the per-(node, root) kernels in global memory return the same cost and root for every
+    resolution, also with costs that make cost() re-classify duplications as speciations."""
+    if wide:
+        monkeypatch.setenv("SR2_SUPERDTL_FUSED_WIDE", "1")
+    for seed, costs in [(5, (0, 1, 1, 1, 1)), (6, (3, 1, 2, 1, 2)), (7, (2, 0, 1, 0, 3)), (8, (1, 1, 0, 2, 0))]:
+        data = synth.make_polytomy_input(9, (4, 4), 2, 7, seed=seed, costs=costs)
+        srec_input, species, poly, bits, cvec = _poly_setup(ctx, data)
+        total = srec_input.count_resolutions()
+        outs = []
+        for unfused in ("0", "1"):
+            monkeypatch.setenv("SR2_SUPERDTL_UNFUSED", unfused)
+            ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits, cvec, 0, total)
+            ctx.superdtl_solve()
+            outs.append((ctx.superdtl_results(costs_only=True), ctx.superdtl_best()))
+        assert (outs[0][0][0] == outs[1][0][0]).all() and (outs[0][0][1] == outs[1][0][1]).all()
+        assert outs[0][1] == outs[1][1]
