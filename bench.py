@@ -237,7 +237,7 @@ def secondary_dtl_single(ctx, repeats, with_cpu):
                                    f"one instance: {waves} dependent wave launches, latency-bound "
                                    "(the tables are 160 MB; the HBM floor of 0.4 GB is 62 us)"),
     }
-    if with_cpu:
+    def cpu_leg():
         from oracle import binding as oracle
         oracle.load().oracle_set_threads(host_cores())
         start = time.perf_counter()
@@ -249,7 +249,7 @@ def secondary_dtl_single(ctx, repeats, with_cpu):
             "sample": f"the whole instance, OpenMP over the species of a node, {seconds:.1f} s wall",
             "parity": require_equal("config #3", (got[0][0], got[1][0], got[2]),
                                     (ref["min_cost"], ref["root_species"], ref["mapping"]))}
-    return entry
+    return entry, (cpu_leg if with_cpu else None)
 
 
 def secondary_superdtl_single(ctx, repeats, with_cpu):
@@ -276,7 +276,7 @@ def secondary_superdtl_single(ctx, repeats, with_cpu):
                                    f"one instance: {waves} dependent wave launches, latency-bound "
                                    "(HBM floor of 0.04 GB: 6 us)"),
     }
-    if with_cpu:
+    def cpu_leg():
         from oracle import binding as oracle
         oracle.load().oracle_set_threads(host_cores())
         start = time.perf_counter()
@@ -289,7 +289,7 @@ def secondary_superdtl_single(ctx, repeats, with_cpu):
             "parity": require_equal("config #4", (got[0][0], got[1][0], got[2], got[3], got[4]),
                                     (ref["min_cost"], ref["root_species"], ref["mapping"], ref["kind"], ref["syn"]))
             .replace("mapping)", "mapping, kinds, syntenies)")}
-    return entry
+    return entry, (cpu_leg if with_cpu else None)
 
 
 def resolution_workload(data):
@@ -346,12 +346,24 @@ def secondary_resolutions(ctx, name, data, number, repeats, with_cpu, cpu_count,
     upload_ms = ctx.timing().upload_ms
     solve_ms, waves_ms, launches, waves, evaluated = repeat_solve(ctx.superdtl_solve, ctx.timing, repeats)
     gpu_costs = ctx.superdtl_results(costs_only=True)
-    stats = torch.tensor([solve_ms, waves_ms, upload_ms], dtype=torch.float64, device="cuda")
+    # ---- the C ABI end to end: flat host arrays in, the packed best key out (+ the reduce over ranks) ----
+    device = torch.device("cuda", local_rank)
+    abi = []
+    for _ in range(repeats):
+        barrier()
+        start = time.perf_counter()
+        ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits, costs, lo, hi - lo)
+        ctx.superdtl_solve()
+        cost, number, root, _ = ctx.superdtl_best()
+        allreduce_min_found((cost, number, root) if root >= 0 else None, device)
+        abi.append((time.perf_counter() - start) * 1e3)
+    abi_ms = float(np.median(abi))
+    stats = torch.tensor([solve_ms, waves_ms, upload_ms, abi_ms], dtype=torch.float64, device="cuda")
     cells_t = torch.tensor([float(evaluated)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
         dist.all_reduce(cells_t, op=dist.ReduceOp.SUM)
-    solve_ms, waves_ms, upload_ms = (float(v) for v in stats.tolist())
+    solve_ms, waves_ms, upload_ms, abi_ms = (float(v) for v in stats.tolist())
     evaluated_all = int(cells_t.item())
 
     # ---- end to end through the Python entry point (every rank calls it with the same input) --
@@ -385,7 +397,12 @@ def secondary_resolutions(ctx, name, data, number, repeats, with_cpu, cpu_count,
         "e2e": {"ms": e2e_ms, "value": total / (e2e_ms * 1e-3), "unit": "resolutions/s",
                 "api": "usreconcile_extended_uspfs (Python entry point: host plan, unranking on the device, solve, "
                        "key reduce, winner rebuilt and decoded)" + (" sharded over ranks" if world > 1 else ""),
-                "solve_ms": part_solve, "reduce_ms": part_reduce, "materialise_ms": part_mat},
+                "solve_ms": part_solve, "reduce_ms": part_reduce, "materialise_ms": part_mat,
+                "abi_ms": abi_ms, "abi_value": total / (abi_ms * 1e-3),
+                "abi": "sr2_resolutions_upload + sr2_superdtl_solve + sr2_superdtl_best through ctypes: flat host "
+                       "arrays in, packed (cost, resolution, root) key out"
+                       + (", + the all-reduce(MIN) over ranks" if world > 1 else "")
+                       + "; the Python entry point adds tree flattening and the rebuilt winner (fixed cost per call)"},
         "roofline": roofline_entry(evaluated_all / world, waves_ms,
                                    "rows shared between resolutions: cells actually evaluated (reference-equivalent "
                                    "cells are reported separately); the solve is dominated by the per-resolution "
@@ -395,7 +412,6 @@ def secondary_resolutions(ctx, name, data, number, repeats, with_cpu, cpu_count,
     })
     if world > 1:
         # latency of the collective alone, and equality with the single-GPU answer
-        device = torch.device("cuda", local_rank)
         lat = []
         for _ in range(20):
             barrier()
@@ -411,7 +427,7 @@ def secondary_resolutions(ctx, name, data, number, repeats, with_cpu, cpu_count,
             entry["equals_single_gpu"] = bool(alone == winner)
             if alone != winner:
                 raise SystemExit(f"bench.py: {name}: sharded winner {winner} differs from the single-GPU {alone}")
-    if with_cpu and rank == 0:
+    def cpu_leg():
         count = min(cpu_count, hi - lo)
         seconds, cpu_cost, cpu_root = cpu_resolutions(data, lo, count)
         per_res = (n_leaves - 1) * S * 2
@@ -422,7 +438,7 @@ def secondary_resolutions(ctx, name, data, number, repeats, with_cpu, cpu_count,
                       f"OpenMP over resolutions, {seconds:.2f} s wall",
             "parity": require_equal(name, (gpu_costs[0][:count], gpu_costs[1][:count]), (cpu_cost, cpu_root))
             .replace("(min cost, root species, mapping)", "(min cost and root species of every sampled resolution)")}
-    return entry, result
+    return entry, result, (cpu_leg if with_cpu and rank == 0 else None)
 
 
 def secondary_crispr_check(entry, result):
@@ -634,7 +650,10 @@ def main():
                                            "r1y_flat2_ncu_details.csv / r2m_flat2_ncu_details.csv"},
             "checksum_min_costs": checksum,
         }
-        if world == 1 and not args.no_cpu_baseline:
+    cpu_legs = []   # every CPU leg runs after ALL GPU timing: a busy OpenMP team of another runtime in the
+                    # process adds milliseconds of jitter to host-side calls (profiles/README.md r3h)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        def primary_cpu_leg():
             cores = host_cores()
             sample = min(n_trees, max(16, 6 * cores))  # about 20 core-seconds
             rate, seconds, answers = time_cpu_port(batch, sample)
@@ -644,6 +663,7 @@ def main():
                 "sample": f"first {sample} trees of the batch, OpenMP over trees, {seconds:.1f} s wall; "
                           "plain-C port of the reference's O(|G||S|^2) algorithm",
                 "parity": require_equal("config #2", (min_cost[:sample], root[:sample], mapping[:hi]), answers)}
+        cpu_legs.append(primary_cpu_leg)
     ctx.close()
 
     # ---------------- the other BASELINE configurations ----------------------------------------
@@ -655,20 +675,34 @@ def main():
         if world == 1:
             with gzip.open(os.path.join(ROOT, "tests", "golden", "crispr.json.gz"), "rt") as handle:
                 crispr = json.load(handle)[0]["input"]
-            entry, result = secondary_resolutions(sctx, "config #1", crispr, 1, repeats, with_cpu, 27,
-                                                  rank, world, local_rank)
+            entry, result, leg = secondary_resolutions(sctx, "config #1", crispr, 1, repeats, with_cpu, 27,
+                                                       rank, world, local_rank)
             secondary_crispr_check(entry, result)
             secondary["superdtl_crispr_class1"] = entry
-            secondary["dtl_single_5000x2000"] = secondary_dtl_single(sctx, repeats, with_cpu)
-            secondary["superdtl_single_1000x500x32"] = secondary_superdtl_single(sctx, repeats, with_cpu)
-        entry, _ = secondary_resolutions(sctx, "config #5", synth.make_polytomy_input(), 5, repeats, with_cpu,
-                                         2048, rank, world, local_rank)
+            cpu_legs.append(leg)
+            secondary["dtl_single_5000x2000"], leg = secondary_dtl_single(sctx, repeats, with_cpu)
+            cpu_legs.append(leg)
+            secondary["superdtl_single_1000x500x32"], leg = secondary_superdtl_single(sctx, repeats, with_cpu)
+            cpu_legs.append(leg)
+        entry, _, leg = secondary_resolutions(sctx, "config #5", synth.make_polytomy_input(), 5, repeats, with_cpu,
+                                              2048, rank, world, local_rank)
         secondary["superdtl_resolutions_99225"] = entry
+        cpu_legs.append(leg)
+        # the same workload one size up (6-ary x 6-ary: 945 x 945 resolutions), where a GPU has ~50 ms of work
+        # per call and sharding the enumeration pays; not a BASELINE config, reported for the scaling curve
+        entry, _, leg = secondary_resolutions(sctx, "resolutions 6x6", synth.make_polytomy_input(arities=(6, 6)),
+                                              "5 (6-ary x 6-ary variant)", max(3, repeats // 2), with_cpu, 512,
+                                              rank, world, local_rank)
+        secondary["superdtl_resolutions_893025"] = entry
+        cpu_legs.append(leg)
         if line is not None:
             line["secondary"] = secondary
             if world > 1:
                 line["secondary_note"] = ("configs #1, #3 and #4 are single instances (replicas only, SURVEY 8e): "
                                           "measured at N=1; config #5 is strong-scaled over the ranks")
+    for leg in cpu_legs:
+        if leg is not None:
+            leg()
     if line is not None:
         print(json.dumps(line), flush=True)
     if world > 1:

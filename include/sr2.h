@@ -72,6 +72,21 @@ int sr2_synchronize(sr2_ctx* ctx);
 /* sizeof-style introspection used by the tests */
 int sr2_version(void);
 
+/* ---- retention policy ------------------------------------------------------
+ * RetentionPolicy of the reference (utils/dynamic_programming.py:89-101), the second argument of both
+ * compute entry points (compute/reconciliation.py:266-269, unordered_super_reconciliation.py:523-526).
+ *   SR2_POLICY_ANY (default): one solution per instance -- the one the reference returns under ANY
+ *       (first candidate that reaches the minimum, level-order tie-breaking); only the rows the
+ *       traceback needs stay on the device.
+ *   SR2_POLICY_ALL: the values of the DP table do not depend on the policy (they are minima), the SET of
+ *       optimal tags per cell does.  Under ALL every later upload keeps its whole table (as with
+ *       SR2_KEEP_TABLES) so that sr2_*_tables can serve the enumeration of all optimal solutions, which
+ *       the binding runs on the host (their number is exponential and each becomes a host object);
+ *       sr2_*_results still return the ANY solution.  Applies to uploads made after the call. */
+#define SR2_POLICY_ANY 0
+#define SR2_POLICY_ALL 1
+int sr2_set_policy(sr2_ctx* ctx, int policy);
+
 /* ---- species tree --------------------------------------------------------
  * parent[0] = -1; child0/child1 = -1 for leaves.  Replaces the per-input
  * LowestCommonAncestor oracle (/root/reference/src/superrec2/utils/trees.py:31-142):

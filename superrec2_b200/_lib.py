@@ -15,6 +15,7 @@ import numpy as np
 
 SR2_INF = 0x3FFFFFFF
 SR2_KEEP_TABLES = 1
+SR2_POLICY_ANY, SR2_POLICY_ALL = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SR2_LIBRARY", os.path.join(_HERE, "libsr2.so"))  # override for A/B builds
@@ -52,6 +53,7 @@ SIGNATURES = {
     "sr2_last_error": (c_char_p, [c_void_p]),
     "sr2_set_stream": (c_int, [c_void_p, c_void_p]),
     "sr2_synchronize": (c_int, [c_void_p]),
+    "sr2_set_policy": (c_int, [c_void_p, c_int]),
     "sr2_set_species": (c_int, [c_void_p, c_int32, _I32P, _I32P, _I32P]),
     "sr2_dtl_upload": (c_int, [c_void_p, c_int32, _I64P, _I32P, _I32P, _I32P, _I32P, c_uint32]),
     "sr2_dtl_solve": (c_int, [c_void_p]),
@@ -149,6 +151,11 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr: int):
         self._check(self._lib.sr2_set_stream(self._handle, c_void_p(cuda_stream_ptr)))
+
+    def set_policy(self, policy: int):
+        """RetentionPolicy of later uploads: SR2_POLICY_ALL keeps the whole table for the host-side
+        enumeration of all optimal solutions (include/sr2.h)."""
+        self._check(self._lib.sr2_set_policy(self._handle, int(policy)))
 
     def synchronize(self):
         self._check(self._lib.sr2_synchronize(self._handle))

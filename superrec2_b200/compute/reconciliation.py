@@ -105,9 +105,12 @@ def reconcile_thl_all(rec_input: ReconciliationInput, device: int = 0) -> Set[Re
     n, S = len(layout.nodes), len(species.nodes)
     ctx = _lib.default_context(device)
     ctx.set_species(species.parent, species.child0, species.child1)
-    ctx.dtl_run(np.asarray([0, n], np.int64), layout.left, layout.right, layout.leaf_species, costs,
-                flags=_lib.SR2_KEEP_TABLES)
-    value, _ = ctx.dtl_tables(0, n)
+    ctx.set_policy(_lib.SR2_POLICY_ALL)
+    try:
+        ctx.dtl_run(np.asarray([0, n], np.int64), layout.left, layout.right, layout.leaf_species, costs)
+        value, _ = ctx.dtl_tables(0, n)
+    finally:
+        ctx.set_policy(_lib.SR2_POLICY_ANY)
     INF = _lib.SR2_INF
     T = value.astype(np.int64)
 

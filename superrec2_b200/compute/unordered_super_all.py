@@ -53,9 +53,13 @@ class _Resolution:
         self.species, self.objects = species, objects
         ctx.set_species(species.parent, species.child0, species.child1)
         n = len(objects.nodes)
-        ctx.superdtl_run(np.asarray([0, n], np.int64), objects.left, objects.right, objects.leaf_species,
-                         bits, costs, flags=_lib.SR2_KEEP_TABLES)
-        value, _, gain, lca = ctx.superdtl_tables(0)
+        ctx.set_policy(_lib.SR2_POLICY_ALL)
+        try:
+            ctx.superdtl_run(np.asarray([0, n], np.int64), objects.left, objects.right, objects.leaf_species,
+                             bits, costs)
+            value, _, gain, lca = ctx.superdtl_tables(0)
+        finally:
+            ctx.set_policy(_lib.SR2_POLICY_ANY)
         table = value.astype(np.int64)
         table[value >= _lib.SR2_INF] = BIG
         self.T = table                                  # [node, species, kind]

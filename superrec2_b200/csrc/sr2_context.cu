@@ -31,13 +31,20 @@ int sr2_dev_reserve(sr2_ctx* ctx, int id, size_t bytes, void** out) {
         if (pool.ptr) cudaFree(pool.ptr);
         pool.ptr = nullptr;
         pool.cap = 0;
-        cudaError_t e = cudaMalloc(&pool.ptr, bytes);
+        // a little head-room: batches of similar size reuse the buffer instead of reallocating it
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&pool.ptr, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = cudaMalloc(&pool.ptr, want);
+        }
         if (e != cudaSuccess) {
             cudaGetLastError();
             return sr2_fail(ctx, SR2_ERR_NOMEM, std::string("device allocation of ") + std::to_string(bytes) +
                                                     " bytes failed: " + cudaGetErrorString(e));
         }
-        pool.cap = bytes;
+        pool.cap = want;
     }
     *out = pool.ptr;
     return SR2_OK;
@@ -158,7 +165,6 @@ extern "C" void sr2_destroy(sr2_ctx* ctx) {
     cudaSetDevice(ctx->device);
     sr2_free_dtl(ctx);
     sr2_free_super(ctx);
-    if (ctx->d_species_slab) cudaFree(ctx->d_species_slab);
     for (auto& pool : ctx->dev)
         if (pool.ptr) cudaFree(pool.ptr);
     for (auto& pool : ctx->pin)
@@ -166,7 +172,6 @@ extern "C" void sr2_destroy(sr2_ctx* ctx) {
     for (auto& pool : ctx->host) free(pool.ptr);
     for (auto& ev : ctx->ev)
         if (ev) cudaEventDestroy(ev);
-    if (ctx->d_anc_tab) cudaFree(ctx->d_anc_tab);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -212,6 +217,14 @@ extern "C" int sr2_last_timing(const sr2_ctx* ctx, sr2_timing* out) {
     return SR2_OK;
 }
 
+extern "C" int sr2_set_policy(sr2_ctx* ctx, int policy) {
+    if (!ctx) return SR2_ERR_ARG;
+    if (policy != SR2_POLICY_ANY && policy != SR2_POLICY_ALL)
+        return sr2_fail(ctx, SR2_ERR_ARG, "sr2_set_policy: policy must be SR2_POLICY_ANY or SR2_POLICY_ALL");
+    ctx->policy = policy;
+    return SR2_OK;
+}
+
 extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
                                const int32_t* child0, const int32_t* child1) {
     if (!ctx) return SR2_ERR_ARG;
@@ -244,6 +257,15 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
     if (next != S)
         return sr2_fail(ctx, SR2_ERR_ARG, "sr2_set_species: child arrays do not cover all nodes");
 
+    // The same tree again (the Python entry points set the species before every upload, and the winner
+    // of an enumeration is re-solved on a re-parsed copy of the same tree): everything on the device is
+    // still valid.  cudaMalloc / cudaFree are kept off this path altogether -- with peer access enabled
+    // (NCCL, one process per GPU) a single allocation was seen to take 200 ms (profiles/README.md r3k).
+    if (ctx->S == S && ctx->species_valid && ctx->h_parent.size() == (size_t)S &&
+        memcmp(ctx->h_parent.data(), parent, sizeof(int32_t) * S) == 0 &&
+        memcmp(ctx->h_child0.data(), child0, sizeof(int32_t) * S) == 0)
+        return SR2_OK;
+    ctx->species_valid = false;
     ctx->S = S;
     ctx->pitch = (S + 31) / 32 * 32;
     ctx->n_internal = (int)int_list.size();
@@ -275,13 +297,9 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
     for (int d = 0; d < ctx->D; ++d) ctx->h_int_lvl_off[d + 1] += ctx->h_int_lvl_off[d];
 
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
-    ctx->mem_dirty = true;  // the species slab and the ancestor table are allocated below
     sr2_free_dtl(ctx);
     sr2_free_super(ctx);
-    if (ctx->d_species_slab) {
-        cudaFree(ctx->d_species_slab);
-        ctx->d_species_slab = nullptr;
-    }
+    SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the pooled slab below may still be read
     size_t n_int = int_list.size();
     // sweep schedule (see DevSpecies::sweep_sched)
     std::vector<int32_t> sched;
@@ -309,7 +327,12 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
     }
     size_t total = (size_t)S * 7 + (n_int ? n_int : 1) + (size_t)ctx->D + 1 + std::max<size_t>(sched.size(), 32) + sched2.size() +
                    (size_t)S * 4 + 2 * (size_t)ctx->pitch + 24 + (size_t)S * ((ctx->pitch / 32 + 3) / 4 * 4);
-    SR2_CUDA(ctx, cudaMalloc(&ctx->d_species_slab, total * sizeof(int32_t)));
+    {
+        void* ptr = nullptr;
+        int rc = sr2_dev_reserve(ctx, DP_SPECIES_SLAB, total * sizeof(int32_t), &ptr);
+        if (rc) return rc;
+        ctx->d_species_slab = (int32_t*)ptr;
+    }
     std::vector<int32_t> slab(total, 0);
     int32_t* h = slab.data();
     int32_t* d = ctx->d_species_slab;
@@ -384,10 +407,7 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
     }
     SR2_CUDA(ctx, cudaMemcpyAsync(d, h, total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
     // ancestor table for the sparse cherry kernel
-    if (ctx->d_anc_tab) {
-        cudaFree(ctx->d_anc_tab);
-        ctx->d_anc_tab = nullptr;
-    }
+    ctx->d_anc_tab = nullptr;
     ctx->dsp.anc_tab = nullptr;
     ctx->dsp.lca_depth = nullptr;
     ctx->dsp.anc_pitch = (ctx->D + 1) & ~1;
@@ -414,7 +434,12 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
                     lcad[(size_t)a * S + b] = lcad[(size_t)b * S + a] = (uint8_t)(d - 1);
                 }
         }
-        SR2_CUDA(ctx, cudaMalloc(&ctx->d_anc_tab, anc.size() * sizeof(uint16_t) + lcad.size()));
+        {
+            void* ptr = nullptr;
+            int rc = sr2_dev_reserve(ctx, DP_SPECIES_ANC, anc.size() * sizeof(uint16_t) + lcad.size(), &ptr);
+            if (rc) return rc;
+            ctx->d_anc_tab = (uint16_t*)ptr;
+        }
         SR2_CUDA(ctx, cudaMemcpyAsync(ctx->d_anc_tab, anc.data(), anc.size() * sizeof(uint16_t), cudaMemcpyHostToDevice,
                                       ctx->stream));
         ctx->dsp.anc_tab = ctx->d_anc_tab;
@@ -426,5 +451,6 @@ extern "C" int sr2_set_species(sr2_ctx* ctx, int32_t S, const int32_t* parent,
         }
     }
     SR2_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->species_valid = true;
     return SR2_OK;
 }

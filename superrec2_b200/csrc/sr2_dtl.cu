@@ -1593,6 +1593,7 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
                            const int32_t* right, const int32_t* leaf_species, const int32_t costs[5],
                            uint32_t flags, int pipeline_chunks, const RowHooks* hooks) {
     if (!ctx) return SR2_ERR_ARG;
+    if (ctx->policy == SR2_POLICY_ALL) flags |= SR2_KEEP_TABLES;  // sr2_set_policy
     double t0 = now_ms();
     if (ctx->S == 0) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_upload: call sr2_set_species first");
     if (B < 0 || !node_off || !costs || (B > 0 && (!left || !right || !leaf_species)))
@@ -2154,7 +2155,7 @@ extern "C" int sr2_dtl_results(sr2_ctx* ctx, int32_t* out_min_cost, int32_t* out
     if (out_map_species) {
         const int64_t block = 1 << 18;
         const int64_t n_blocks = ((int64_t)N + block - 1) / block;
-#pragma omp parallel for num_threads(ctx->host_threads) schedule(static)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static) if (n_blocks > 1)
         for (int64_t k = 0; k < n_blocks; ++k) {
             int64_t lo = k * block, hi = std::min<int64_t>((int64_t)N, lo + block);
             memcpy(out_map_species + lo, stage + 2 * B + lo, (size_t)(hi - lo) * 4);
@@ -2198,7 +2199,7 @@ static int dtl_deliver(DtlRunState* rs, int upto, bool wait) {
         if (rs->out_map) {
             const int64_t block = 1 << 17;
             const int64_t n_blocks = (nn + block - 1) / block;
-#pragma omp parallel for num_threads(ctx->host_threads) schedule(static)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static) if (n_blocks > 1)
             for (int64_t k = 0; k < n_blocks; ++k) {
                 int64_t lo = n0 + k * block, hi = std::min<int64_t>(n0 + nn, lo + block);
                 memcpy(rs->out_map + lo, rs->stage + 2 * B + lo, (size_t)(hi - lo) * 4);

@@ -119,7 +119,8 @@ enum Sr2DevPool {
     DP_S_T, DP_S_TAG, DP_S_DEC, DP_S_ANC, DP_S_TAU, DP_S_TAUMIN, DP_S_COST, DP_S_MINCOST, DP_S_ROOTSP, DP_S_MAP,
     DP_S_KIND, DP_S_SYN, DP_S_BEST, DP_S_ALLOWED, DP_S_EV,
     DP_S_NODESLOT, DP_S_NODEDAG, DP_S_NODEPRE, DP_S_NODEINST, DP_S_PLAN32, DP_S_PLAN64,
-    DP_RAW, DP_RAW_HEIGHT, DP_RAW_NODEROW, DP_RAW_INSTBASE, DP_RAW_COUNTS, DP_RAW_NODEOFF, DP_COUNT
+    DP_RAW, DP_RAW_HEIGHT, DP_RAW_NODEROW, DP_RAW_INSTBASE, DP_RAW_COUNTS, DP_RAW_NODEOFF,
+    DP_SPECIES_SLAB, DP_SPECIES_ANC, DP_COUNT
 };
 enum Sr2PinPool { HP_ROWS_SLAB, HP_ROOT_ROW, HP_ROOT_NODE, HP_NODE_PRE, HP_NODE_INST, HP_RESULTS, HP_RAW, HP_COUNTS, HP_COUNT };
 enum Sr2HostPool { MP_HEIGHT, MP_NODE_ROW, MP_CNT, MP_COUNT };
@@ -145,6 +146,8 @@ struct sr2_ctx {
     // free device memory as last reported by the driver; refreshed only after a pool grew
     size_t mem_free_cached = 0;
     bool mem_dirty = true;
+    int policy = SR2_POLICY_ANY;   // sr2_set_policy: ALL keeps the whole table of later uploads
+    bool species_valid = false;   // the device copy of the species tree matches h_parent / h_child0
     std::string err;
     int sm_count = 148;
     int host_threads = 1;  // OpenMP threads of the host-side bucketing (see sr2_create)

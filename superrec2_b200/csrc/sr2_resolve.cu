@@ -275,7 +275,7 @@ bool plan_shared(const PolyTree& t, int64_t first, int64_t count, const int32_t*
         if (k == 0) continue;
         const int32_t* arr = P.arr.data() + P.arr_off[v];
         const int64_t rb = P.raw_base[v];
-#pragma omp parallel for num_threads(n_threads) schedule(static)
+#pragma omp parallel for num_threads(n_threads) schedule(static) if (n_var[v] >= 4096)
         for (int64_t i = 0; i < n_var[v]; ++i) {
             const int64_t var = P.var_first[v] + i;
             const int64_t j = var % t.ways[v];
@@ -326,7 +326,7 @@ bool plan_shared(const PolyTree& t, int64_t first, int64_t count, const int32_t*
             P.leaf_species[t.base[v]] = leaf_species[v];
             memcpy(&P.leaf_bits[(size_t)t.base[v] * W], leaf_bits + (size_t)v * W, sizeof(uint32_t) * W);
         }
-#pragma omp parallel for num_threads(n_threads) schedule(static)
+#pragma omp parallel for num_threads(n_threads) schedule(static) if (n_raw >= 16384)
     for (int64_t s = 0; s < n_raw; ++s) {
         const int32_t slot = P.perm[s];
         for (int side = 0; side < 2; ++side) {
@@ -410,7 +410,7 @@ extern "C" int sr2_resolutions_upload(sr2_ctx* ctx, int32_t n_nodes, const int32
             tmpl_leaf[t.base[v]] = leaf_species[v];
             memcpy(&tmpl_bits[(size_t)t.base[v] * W], leaf_bits + (size_t)v * W, sizeof(uint32_t) * W);
         }
-#pragma omp parallel for num_threads(ctx->host_threads) schedule(static)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static) if (count * Gb >= 65536)
     for (int64_t i = 0; i < count; ++i) {
         unrank(t, first + i, left.data() + i * Gb, right.data() + i * Gb, nullptr);
         memcpy(leaf.data() + i * Gb, tmpl_leaf.data(), sizeof(int32_t) * Gb);

@@ -142,7 +142,9 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
         }
     }
     if (keep_host) out->h_node_row.assign((size_t)N, -1);
-    const int T = std::max(1, ctx->host_threads);
+    // small batches stay on the calling thread: waking an OpenMP team costs more than the work, and
+    // under a busy host (other runtimes' teams spinning) it costs milliseconds (profiles/README.md r3h)
+    const int T = N < 65536 ? 1 : std::max(1, ctx->host_threads);
     std::vector<std::vector<int32_t>> counts(T);   // [thread][height] internal nodes, then row cursors
     std::vector<int> first_inst(T + 1);
     for (size_t ci = 0; ci < out->chunks.size(); ++ci) {
@@ -317,7 +319,7 @@ int sr2_build_rows(sr2_ctx* ctx, const char* who, int32_t B, const int64_t* node
             if (rc) return rc;
             out->d_node_inst = (int32_t*)ptr;
         }
-#pragma omp parallel for num_threads(ctx->host_threads) schedule(dynamic, 64)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(dynamic, 64) if (N >= 65536)
         for (int b = 0; b < B; ++b) {
             int64_t off = node_off[b];
             std::vector<int32_t> stack;
@@ -642,7 +644,7 @@ int sr2_build_rows_device(sr2_ctx* ctx, const char* who, int32_t B, const int64_
             if (!direct) {
                 int32_t* to = stage + (size_t)k * N + n0;
                 const int64_t block = 1 << 16, n_blocks = (nn + block - 1) / block;
-#pragma omp parallel for num_threads(ctx->host_threads) schedule(static)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static) if (n_blocks > 1)
                 for (int64_t q = 0; q < n_blocks; ++q) {
                     int64_t lo = q * block, hi = std::min(nn, lo + block);
                     memcpy(to + lo, from + lo, (size_t)(hi - lo) * sizeof(int32_t));

@@ -1126,6 +1126,7 @@ extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_
                                    const uint32_t* leaf_bits, const int32_t costs[5], int64_t index_base,
                                    uint32_t flags) {
     if (!ctx) return SR2_ERR_ARG;
+    if (ctx->policy == SR2_POLICY_ALL) flags |= SR2_KEEP_TABLES;  // sr2_set_policy
     double t0 = snow_ms();
     if (ctx->S == 0) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_superdtl_upload: call sr2_set_species first");
     if (B < 0 || !node_off || !costs || n_words < 1 || (B > 0 && (!left || !right || !leaf_species || !leaf_bits)))
@@ -1177,7 +1178,7 @@ extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_
     const int64_t R = p->rows.R;
     // global-id child arrays for the per-instance kernels
     std::vector<int32_t> gl(std::max<int64_t>(N, 1)), grt(std::max<int64_t>(N, 1));
-#pragma omp parallel for num_threads(ctx->host_threads) schedule(static)
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static) if (N >= 65536)
     for (int b = 0; b < B; ++b)
         for (int64_t u = node_off[b]; u < node_off[b + 1]; ++u) {
             gl[u] = left[u] < 0 ? -1 : (int32_t)(node_off[b] + left[u]);
