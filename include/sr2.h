@@ -115,6 +115,15 @@ int sr2_dtl_run(sr2_ctx* ctx, int32_t n_instances, const int64_t* node_off,
                 const int32_t* left, const int32_t* right, const int32_t* leaf_species,
                 const int32_t costs[5], uint32_t flags,
                 int32_t* out_min_cost, int32_t* out_root_species, int32_t* out_map_species);
+/* sr2_dtl_run with 16-bit node and species numbers, for batches whose trees have at most 32,767 nodes
+ * over at most 32,767 species nodes (the common case: BASELINE config #2 has 999 and 399): the three
+ * input arrays and the two per-node / per-instance species results cross PCIe at half the size and are
+ * widened / narrowed on the device.  Same results as sr2_dtl_run; SR2_ERR_RANGE when a tree or the
+ * species tree is too large. */
+int sr2_dtl_run16(sr2_ctx* ctx, int32_t n_instances, const int64_t* node_off,
+                  const int16_t* left, const int16_t* right, const int16_t* leaf_species,
+                  const int32_t costs[5], uint32_t flags,
+                  int32_t* out_min_cost, int16_t* out_root_species, int16_t* out_map_species);
 /* Test hook (needs SR2_KEEP_TABLES): full table of one instance.
  * out_value[u * n_species + x] = T[u][x] (leaf rows included), SR2_INF if absent;
  * out_tag[(u * n_species + x) * 2 + {0,1}] = species rank chosen for the

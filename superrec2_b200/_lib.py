@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import (POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_uint64,
+from ctypes import (POINTER, c_char_p, c_float, c_int, c_int16, c_int32, c_int64, c_uint32, c_uint64,
                     c_void_p)
 
 import numpy as np
@@ -43,6 +43,7 @@ class Timing(ctypes.Structure):
 
 _I32P = POINTER(c_int32)
 _I64P = POINTER(c_int64)
+_I16P = POINTER(c_int16)
 _U32P = POINTER(c_uint32)
 
 #: every symbol declared in include/sr2.h: name -> (restype, argtypes)
@@ -60,6 +61,8 @@ SIGNATURES = {
     "sr2_dtl_results": (c_int, [c_void_p, _I32P, _I32P, _I32P]),
     "sr2_dtl_run": (c_int, [c_void_p, c_int32, _I64P, _I32P, _I32P, _I32P, _I32P, c_uint32,
                             _I32P, _I32P, _I32P]),
+    "sr2_dtl_run16": (c_int, [c_void_p, c_int32, _I64P, _I16P, _I16P, _I16P, _I32P, c_uint32,
+                              _I32P, _I16P, _I16P]),
     "sr2_dtl_tables": (c_int, [c_void_p, c_int32, _I32P, _I32P]),
     "sr2_superdtl_upload": (c_int, [c_void_p, c_int32, _I64P, _I32P, _I32P, _I32P, c_int32, _U32P, _I32P,
                                     c_int64, c_uint32]),
@@ -206,6 +209,30 @@ class Context:
         self._check(self._lib.sr2_dtl_run(
             self._handle, n_inst, p64(node_off), p32(left), p32(right), p32(leaf_species),
             p32(costs), flags, p32(min_cost), p32(root), p32(mapping)))
+        return min_cost, root, mapping
+
+    def dtl_run16(self, node_off, left, right, leaf_species, costs, flags=0, out=None):
+        """``dtl_run`` with int16 child / leaf-species arrays in and int16 root / mapping arrays out
+        (``sr2_dtl_run16``: half the bytes over PCIe; trees and species tree of at most 32,767 nodes).
+        ``out`` = optional ``(min_cost[int32], root[int16], mapping[int16])`` arrays to fill."""
+        node_off = i64(node_off)
+        left, right, leaf_species = (np.ascontiguousarray(a, dtype=np.int16) for a in (left, right, leaf_species))
+        costs = i32(costs)
+        n_inst, n_nodes = len(node_off) - 1, int(node_off[-1])
+        self._batch = (n_inst, n_nodes)
+        if out is not None:
+            min_cost, root, mapping = out
+            for arr, size, dtype in ((min_cost, n_inst, np.int32), (root, n_inst, np.int16), (mapping, n_nodes, np.int16)):
+                if arr.dtype != dtype or arr.shape != (size,) or not arr.flags.c_contiguous:
+                    raise ValueError("out arrays must be contiguous (int32, int16, int16) of the batch's sizes")
+        else:
+            min_cost = np.empty(n_inst, np.int32)
+            root = np.empty(n_inst, np.int16)
+            mapping = np.empty(n_nodes, np.int16)
+        p16 = lambda a: a.ctypes.data_as(_I16P)  # noqa: E731
+        self._check(self._lib.sr2_dtl_run16(
+            self._handle, n_inst, p64(node_off), p16(left), p16(right), p16(leaf_species),
+            p32(costs), flags, p32(min_cost), p16(root), p16(mapping)))
         return min_cost, root, mapping
 
     def dtl_tables(self, instance: int, n_nodes: int):

@@ -1596,7 +1596,9 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     if (ctx->policy == SR2_POLICY_ALL) flags |= SR2_KEEP_TABLES;  // sr2_set_policy
     double t0 = now_ms();
     if (ctx->S == 0) return sr2_fail(ctx, SR2_ERR_STATE, "sr2_dtl_upload: call sr2_set_species first");
-    if (B < 0 || !node_off || !costs || (B > 0 && (!left || !right || !leaf_species)))
+    const bool raw16 = hooks && hooks->left16;
+    if (B < 0 || !node_off || !costs || (B > 0 && !raw16 && (!left || !right || !leaf_species)) ||
+        (B > 0 && raw16 && (!hooks->right16 || !hooks->leaf16)))
         return sr2_fail(ctx, SR2_ERR_ARG, "sr2_dtl_upload: null array");
     SR2_CUDA(ctx, cudaSetDevice(ctx->device));
     sr2_free_dtl(ctx);
@@ -1656,6 +1658,16 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
                 p->prepared = false;  // a tree too high for the device tables: bucket on the host
             }
         }
+    }
+    std::vector<int32_t> wide;   // sr2_dtl_run16 off the device path (small batches, very high trees)
+    if (hooks && hooks->left16) {
+        wide.resize((size_t)N * 3);
+        const int16_t* from[3] = {hooks->left16, hooks->right16, hooks->leaf16};
+        for (int k = 0; k < 3; ++k)
+            for (int64_t i = 0; i < N; ++i) wide[(size_t)k * N + i] = from[k][i];
+        left = wide.data();
+        right = wide.data() + N;
+        leaf_species = wide.data() + 2 * N;
     }
     int rc = sr2_build_rows(ctx, "sr2_dtl_upload", B, node_off, left, right, leaf_species, rows_budget,
                             (flags & SR2_KEEP_TABLES) != 0, false, &p->rows, hooks ? hooks : &plan_only,
@@ -2175,7 +2187,16 @@ struct DtlRunState {
     bool started;
     bool direct;     // the caller's result arrays are pinned: copy straight into them
     int delivered;   // chunks whose results already sit in the caller's buffers
+    // sr2_dtl_run16: root species and mapping leave the device as 16-bit integers
+    int16_t *out_root16 = nullptr, *out_map16 = nullptr;
+    int16_t *stage16 = nullptr, *d_narrow = nullptr;   // pinned [B + N]; device [B + N]
 };
+
+// results as 16-bit integers before they cross PCIe (species ranks fit: S <= 32767 is checked)
+__global__ void dtl_narrow_kernel(const int32_t* __restrict__ in, int16_t* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int16_t)in[i];
+}
 
 // staging -> caller's buffers for chunks [rs->delivered, upto) whose copies have finished
 // (wait == false: stop at the first chunk that is still in flight)
@@ -2195,6 +2216,16 @@ static int dtl_deliver(DtlRunState* rs, int upto, bool wait) {
             continue;
         }
         if (rs->out_cost) memcpy(rs->out_cost + b0, rs->stage + b0, nb * 4);
+        if (rs->out_root16) memcpy(rs->out_root16 + b0, rs->stage16 + b0, nb * 2);
+        if (rs->out_map16) {
+            const int64_t block = 1 << 18;
+            const int64_t n_blocks = (nn + block - 1) / block;
+#pragma omp parallel for num_threads(ctx->host_threads) schedule(static) if (n_blocks > 1)
+            for (int64_t k = 0; k < n_blocks; ++k) {
+                int64_t lo = n0 + k * block, hi = std::min<int64_t>(n0 + nn, lo + block);
+                memcpy(rs->out_map16 + lo, rs->stage16 + B + lo, (size_t)(hi - lo) * 2);
+            }
+        }
         if (rs->out_root) memcpy(rs->out_root + b0, rs->stage + B + b0, nb * 4);
         if (rs->out_map) {
             const int64_t block = 1 << 17;
@@ -2235,7 +2266,15 @@ static int dtl_run_on_plan(void* user) {
             }
             return attr.type == cudaMemoryTypeHost;
         };
-        rs->direct = pinned(rs->out_cost) && pinned(rs->out_root) && pinned(rs->out_map);
+        rs->direct = pinned(rs->out_cost) && pinned(rs->out_root) && pinned(rs->out_map) &&
+                     pinned(rs->out_root16) && pinned(rs->out_map16);
+    }
+    if (rs->out_root16 || rs->out_map16) {
+        const size_t n16 = (size_t)p->rows.B + (size_t)p->rows.N + 16;
+        if ((rc = sr2_pin_reserve(ctx, HP_RESULTS16, n16 * sizeof(int16_t), &ptr))) return rc;
+        rs->stage16 = (int16_t*)ptr;
+        if ((rc = sr2_dev_reserve(ctx, DP_DTL_MAP16, n16 * sizeof(int16_t), &ptr))) return rc;
+        rs->d_narrow = (int16_t*)ptr;
     }
     if (!ctx->copy_stream) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     p->n_waves = p->n_launch = 0;
@@ -2266,22 +2305,40 @@ static int dtl_run_on_chunk(void* user, int ci) {
         SR2_CUDA(ctx, cudaMemcpyAsync(to_root + b0, p->d_root_species + b0, nb * 4, cudaMemcpyDeviceToHost, cs));
     if (rs->out_map && nn)
         SR2_CUDA(ctx, cudaMemcpyAsync(to_map + n0, p->d_map + n0, nn * 4, cudaMemcpyDeviceToHost, cs));
+    if (rs->out_root16 && nb) {
+        int16_t* to = rs->direct ? rs->out_root16 : rs->stage16;
+        dtl_narrow_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, cs>>>(p->d_root_species + b0, rs->d_narrow + b0, (int64_t)nb);
+        SR2_CUDA(ctx, cudaMemcpyAsync(to + b0, rs->d_narrow + b0, nb * 2, cudaMemcpyDeviceToHost, cs));
+    }
+    if (rs->out_map16 && nn) {
+        int16_t* to = rs->direct ? rs->out_map16 : rs->stage16 + B;
+        dtl_narrow_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, cs>>>(p->d_map + n0, rs->d_narrow + B + n0, (int64_t)nn);
+        SR2_CUDA(ctx, cudaMemcpyAsync(to + n0, rs->d_narrow + B + n0, nn * 2, cudaMemcpyDeviceToHost, cs));
+    }
+    SR2_CUDA(ctx, cudaGetLastError());
     SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_copied[ci], cs));
     return dtl_deliver(rs, ci, false);  // earlier chunks that are back already
 }
 
-extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, const int32_t* left,
-                           const int32_t* right, const int32_t* leaf_species, const int32_t costs[5],
-                           uint32_t flags, int32_t* out_min_cost, int32_t* out_root_species,
-                           int32_t* out_map_species) {
+static int dtl_run_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, const int32_t* left, const int32_t* right,
+                        const int32_t* leaf_species, const int16_t* const raw16[3], const int32_t costs[5],
+                        uint32_t flags, int32_t* out_min_cost, int32_t* out_root_species, int32_t* out_map_species,
+                        int16_t* out_root16, int16_t* out_map16) {
     if (!ctx) return SR2_ERR_ARG;
     int pipeline_chunks = 2;  // + a half-sized first chunk: quarter, half, quarter of the batch (measured: 8.74 ms against 8.84 for 3)
     if (const char* v = getenv("SR2_PIPELINE_CHUNKS")) pipeline_chunks = std::max(1, atoi(v));
     DtlRunState rs{ctx, nullptr, out_min_cost, out_root_species, out_map_species, false, false, 0};
+    rs.out_root16 = out_root16;
+    rs.out_map16 = out_map16;
     RowHooks hooks;
     hooks.user = &rs;
     hooks.on_plan = dtl_run_on_plan;
     hooks.on_chunk = dtl_run_on_chunk;
+    if (raw16) {
+        hooks.left16 = raw16[0];
+        hooks.right16 = raw16[1];
+        hooks.leaf16 = raw16[2];
+    }
     double t0 = now_ms();
     int rc = dtl_upload_impl(ctx, B, node_off, left, right, leaf_species, costs, flags, pipeline_chunks, &hooks);
     double t1 = now_ms();  // the host side is done; sr2_build_rows waited for the compute stream
@@ -2303,6 +2360,31 @@ extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     ctx->timing.upload_ms = (float)(t1 - t0);         // bucketing with the device work overlapped
     ctx->timing.results_ms = (float)(now_ms() - t1);  // what was left of staging -> caller's buffers
     return SR2_OK;
+}
+
+extern "C" int sr2_dtl_run(sr2_ctx* ctx, int32_t B, const int64_t* node_off, const int32_t* left,
+                           const int32_t* right, const int32_t* leaf_species, const int32_t costs[5],
+                           uint32_t flags, int32_t* out_min_cost, int32_t* out_root_species,
+                           int32_t* out_map_species) {
+    return dtl_run_impl(ctx, B, node_off, left, right, leaf_species, nullptr, costs, flags, out_min_cost,
+                        out_root_species, out_map_species, nullptr, nullptr);
+}
+
+extern "C" int sr2_dtl_run16(sr2_ctx* ctx, int32_t B, const int64_t* node_off, const int16_t* left,
+                             const int16_t* right, const int16_t* leaf_species, const int32_t costs[5],
+                             uint32_t flags, int32_t* out_min_cost, int16_t* out_root_species,
+                             int16_t* out_map_species) {
+    if (!ctx) return SR2_ERR_ARG;
+    if (ctx->S > 32767)
+        return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_dtl_run16: more than 32767 species nodes (use sr2_dtl_run)");
+    if (B < 0 || !node_off) return sr2_fail(ctx, SR2_ERR_ARG, "sr2_dtl_run16: null array");
+    for (int b = 0; b < B; ++b)
+        if (node_off[b + 1] - node_off[b] > 32767)
+            return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_dtl_run16: instance " + std::to_string(b) +
+                                                    " has more than 32767 nodes (use sr2_dtl_run)");
+    const int16_t* raw16[3] = {left, right, leaf_species};
+    return dtl_run_impl(ctx, B, node_off, nullptr, nullptr, nullptr, raw16, costs, flags, out_min_cost, nullptr, nullptr,
+                        out_root_species, out_map_species);
 }
 
 extern "C" int sr2_dtl_tables(sr2_ctx* ctx, int32_t instance, int32_t* out_value, int32_t* out_tag) {

@@ -120,9 +120,9 @@ enum Sr2DevPool {
     DP_S_KIND, DP_S_SYN, DP_S_BEST, DP_S_ALLOWED, DP_S_EV,
     DP_S_NODESLOT, DP_S_NODEDAG, DP_S_NODEPRE, DP_S_NODEINST, DP_S_PLAN32, DP_S_PLAN64,
     DP_RAW, DP_RAW_HEIGHT, DP_RAW_NODEROW, DP_RAW_INSTBASE, DP_RAW_COUNTS, DP_RAW_NODEOFF,
-    DP_SPECIES_SLAB, DP_SPECIES_ANC, DP_COUNT
+    DP_SPECIES_SLAB, DP_SPECIES_ANC, DP_RAW16, DP_DTL_MAP16, DP_COUNT
 };
-enum Sr2PinPool { HP_ROWS_SLAB, HP_ROOT_ROW, HP_ROOT_NODE, HP_NODE_PRE, HP_NODE_INST, HP_RESULTS, HP_RAW, HP_COUNTS, HP_COUNT };
+enum Sr2PinPool { HP_ROWS_SLAB, HP_ROOT_ROW, HP_ROOT_NODE, HP_NODE_PRE, HP_NODE_INST, HP_RESULTS, HP_RAW, HP_COUNTS, HP_RESULTS16, HP_COUNT };
 enum Sr2HostPool { MP_HEIGHT, MP_NODE_ROW, MP_CNT, MP_COUNT };
 
 struct sr2_ctx {

@@ -496,6 +496,12 @@ rows_fill_kernel(int inst_begin, const int64_t* __restrict__ node_off, const int
     }
 }
 
+// 16-bit raw arrays (sr2_dtl_run16) to the 32-bit arrays the bucketing kernels read
+__global__ void rows_widen_kernel(const int16_t* __restrict__ in, int32_t* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
 static bool rows_is_pinned(const void* ptr) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
@@ -617,13 +623,25 @@ int sr2_build_rows_device(sr2_ctx* ctx, const char* who, int32_t B, const int64_
         if (rc) return rc;
     }
     // the caller's arrays go to the device directly when they are pinned, else through pinned staging
-    const bool direct = rows_is_pinned(left) && rows_is_pinned(right) && rows_is_pinned(leaf_species);
-    int32_t* stage = nullptr;
+    const bool narrow = hooks->left16 != nullptr;   // 16-bit raw arrays: half the bytes over PCIe
+    const size_t elem = narrow ? sizeof(int16_t) : sizeof(int32_t);
+    const char* src_all[3] = {narrow ? (const char*)hooks->left16 : (const char*)left,
+                              narrow ? (const char*)hooks->right16 : (const char*)right,
+                              narrow ? (const char*)hooks->leaf16 : (const char*)leaf_species};
+    const bool direct = rows_is_pinned(src_all[0]) && rows_is_pinned(src_all[1]) && rows_is_pinned(src_all[2]);
+    char* stage = nullptr;
     if (!direct) {
         void* ptr = nullptr;
-        int rc = sr2_pin_reserve(ctx, HP_RAW, (size_t)std::max<int64_t>(N, 1) * 3 * sizeof(int32_t), &ptr);
+        int rc = sr2_pin_reserve(ctx, HP_RAW, (size_t)std::max<int64_t>(N, 1) * 3 * elem, &ptr);
         if (rc) return rc;
-        stage = (int32_t*)ptr;
+        stage = (char*)ptr;
+    }
+    int16_t* d_raw16 = nullptr;
+    if (narrow) {
+        void* ptr = nullptr;
+        int rc = sr2_dev_reserve(ctx, DP_RAW16, (size_t)std::max<int64_t>(N, 1) * 3 * sizeof(int16_t), &ptr);
+        if (rc) return rc;
+        d_raw16 = (int16_t*)ptr;
     }
     cudaStream_t up = ctx->upload_stream;
     const bool trace = getenv("SR2_TRACE") != nullptr;
@@ -637,21 +655,26 @@ int sr2_build_rows_device(sr2_ctx* ctx, const char* who, int32_t B, const int64_
         const RowChunk& c = out->chunks[ci];
         const int nb = c.inst_end - c.inst_begin;
         const int64_t n0 = node_off[c.inst_begin], nn = node_off[c.inst_end] - n0;
-        const int32_t* src[3] = {left, right, leaf_species};
         int32_t* dst[3] = {d_left, d_right, d_leaf};
         for (int k = 0; k < 3; ++k) {
-            const int32_t* from = src[k] + n0;
+            const char* from = src_all[k] + (size_t)n0 * elem;
             if (!direct) {
-                int32_t* to = stage + (size_t)k * N + n0;
+                char* to = stage + ((size_t)k * N + n0) * elem;
                 const int64_t block = 1 << 16, n_blocks = (nn + block - 1) / block;
 #pragma omp parallel for num_threads(ctx->host_threads) schedule(static) if (n_blocks > 1)
                 for (int64_t q = 0; q < n_blocks; ++q) {
                     int64_t lo = q * block, hi = std::min(nn, lo + block);
-                    memcpy(to + lo, from + lo, (size_t)(hi - lo) * sizeof(int32_t));
+                    memcpy(to + lo * elem, from + lo * elem, (size_t)(hi - lo) * elem);
                 }
                 from = to;
             }
-            SR2_CUDA(ctx, cudaMemcpyAsync(dst[k] + n0, from, (size_t)nn * sizeof(int32_t), cudaMemcpyHostToDevice, up));
+            if (!narrow) {
+                SR2_CUDA(ctx, cudaMemcpyAsync(dst[k] + n0, from, (size_t)nn * elem, cudaMemcpyHostToDevice, up));
+            } else if (nn > 0) {
+                int16_t* d16 = d_raw16 + (size_t)k * N + n0;
+                SR2_CUDA(ctx, cudaMemcpyAsync(d16, from, (size_t)nn * elem, cudaMemcpyHostToDevice, up));
+                rows_widen_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, up>>>(d16, dst[k] + n0, nn);
+            }
         }
         unsigned* counts = d_counts + ci * (ROWS_HCAP + 4);
         int* status = (int*)(counts + ROWS_HCAP);

@@ -46,6 +46,9 @@ struct RowHooks {
     void* user = nullptr;
     int (*on_plan)(void* user) = nullptr;
     int (*on_chunk)(void* user, int chunk) = nullptr;
+    // sr2_build_rows_device only: the caller's raw arrays as 16-bit integers (sr2_dtl_run16); they
+    // cross PCIe at half the size and are widened on the device.  Null: the 32-bit arguments are used.
+    const int16_t *left16 = nullptr, *right16 = nullptr, *leaf16 = nullptr;
 };
 
 // Splits the batch into chunks of at most `rows_budget` rows, then chunk by chunk validates the

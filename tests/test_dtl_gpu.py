@@ -509,3 +509,31 @@ def test_batch_of_one_node_trees_only(ctx):
     none = np.full(count, -1, np.int32)
     min_cost, root, mapping = ctx.dtl_run(np.arange(count + 1, dtype=np.int64), none, none, leaf, species.costs)
     assert (min_cost == 0).all() and (root == leaf).all() and (mapping == leaf).all()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_sixteen_bit_run_equals_the_32_bit_run(ctx, pinned):
+    """sr2_dtl_run16 (int16 arrays over PCIe, widened / narrowed on the device) returns exactly what
+    sr2_dtl_run returns: on the device-bucketing path (big batch, pageable and pinned buffers), on the
+    host path (small batch), and it refuses trees that do not fit 16 bits."""
+    import torch
+    for n_s, n_o, n_trees in [(60, 90, 3000), (12, 20, 7)]:
+        batch = synth.make_batch(n_s, n_o, n_trees, seed=1600 + n_trees)
+        ctx.set_species(batch.parent, batch.child0, batch.child1)
+        want = ctx.dtl_run(batch.node_off, batch.left, batch.right, batch.leaf_species, batch.costs)
+        arrays = [np.ascontiguousarray(a, dtype=np.int16) for a in (batch.left, batch.right, batch.leaf_species)]
+        out = None
+        if pinned:
+            arrays = [torch.from_numpy(a).pin_memory().numpy() for a in arrays]
+            out = (torch.zeros(n_trees, dtype=torch.int32).pin_memory().numpy(),
+                   torch.zeros(n_trees, dtype=torch.int16).pin_memory().numpy(),
+                   torch.zeros(len(batch.left), dtype=torch.int16).pin_memory().numpy())
+        got = ctx.dtl_run16(batch.node_off, *arrays, batch.costs, out=out)
+        assert got[1].dtype == np.int16 and got[2].dtype == np.int16
+        for a, b in zip(got, want):
+            assert np.array_equal(a.astype(np.int32), b)
+    big = synth.make_batch(10, 20000, 1, seed=3)
+    ctx.set_species(big.parent, big.child0, big.child1)
+    with pytest.raises(_lib.Sr2Error) as err:
+        ctx.dtl_run16(big.node_off, big.left % 30000, big.right % 30000, big.leaf_species, big.costs)
+    assert err.value.code == -3
