@@ -688,17 +688,25 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
 
     // ---- child rows -> keys ------------------------------------------------------------------
     const int cl = row_cl[gr], cr = row_cr[gr];
+    SR2_DCHECK(local >= 0 && local < n_rows && cl < (int)slot && cr < (int)slot);
+    SR2_DCHECK(cl >= -sp.S && cr >= -sp.S);      // a leaf child is -1 - species
     const unsigned vmul = 1u << kp.sh, infkey = 0xffffffffu << kp.sh;
     if (CHAIN) {
         // child rows inside the chained range: wait for their flags (lanes 0 and 1 poll one child each)
         const int first_slot = (int)(row_begin - chunk_row0);
         const int c = lane == 0 ? cl : cr;
         if (lane < 2 && c >= first_slot) {
+            // Rows are handed out by ticket in row order and rows are sorted by height (sr2_build_rows*), so a
+            // child inside the chained range always belongs to a warp that already runs: the wait cannot
+            // deadlock.  A row layout that breaks the invariant (a child at or behind its parent) must not
+            // hang the GPU: it traps, and the host reports the failed launch (SR2_ERR_CUDA).
+            if (c - first_slot >= local) __trap();
             const int* flag = chain_sync + 1 + (c - first_slot);
             int up;
-            for (;;) {
+            for (unsigned spins = 0;; ++spins) {
                 asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(up) : "l"(flag) : "memory");
                 if (up) break;
+                if (spins > (1u << 24)) __trap();   // seconds of waiting: something upstream failed
                 __nanosleep(100);
             }
         }
@@ -1019,6 +1027,8 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     }
     __syncwarp();
     if (valid) m = (int)pre[mw];
+    SR2_DCHECK(m <= MAXM);                       // dtl_partition_kernel only lists rows that fit the tier
+    SR2_DCHECK(!valid || (cl < (int)slot && cr < (int)slot));   // children are rows of earlier waves
     // position of a species of the path set
     auto pos_of = [&](int s) { return (int)pre[s >> 5] + __popc(mk[s >> 5] & ((1u << (s & 31)) - 1u)); };
     auto on_path = [&](int s) { return (mk[s >> 5] >> (s & 31)) & 1u; };
@@ -1029,6 +1039,7 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         for (int e = sub; e < m; e += 4) {
             while ((int)pre[w + 1] <= e) ++w;
             const int s = w * 32 + (int)__fns(mk[w], 0, e - (int)pre[w] + 1);
+            SR2_DCHECK(s >= 0 && s < sp.S && w < mw);
             const unsigned low = __ldg(sp.keylow_p + s);
             el[e] = (unsigned)s | ((low & kp.dm) << 16);
             // positions of the parent, the sibling and the two children inside the path set (0xff = not
@@ -1039,6 +1050,7 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             link |= (s && on_path(sib) ? (unsigned)pos_of(sib) : 0xffu) << 8;
             link |= (c0 >= 0 && on_path(c0) ? (unsigned)pos_of(c0) : 0xffu) << 16;
             link |= (c0 >= 0 && on_path(c0 + 1) ? (unsigned)pos_of(c0 + 1) : 0xffu) << 24;
+            SR2_DCHECK(on_path(par) && (int)(link & 0xffu) <= e);   // root paths are closed under "parent"
             Pc[e].x = link;
         }
     }

@@ -20,6 +20,17 @@
 
 #define SR2_NO_TAG 0xffffffffu
 
+// Device-side invariant checks, compiled in with -DSR2_DEBUG_CHECKS (scripts/debug_checks.sh builds
+// libsr2_debug.so and runs the GPU tests against it).  compute-sanitizer is closed on this pool, so
+// index bounds and ordering invariants of the kernels are asserted by hand instead; a violated check
+// fails the launch loudly (cudaErrorAssert -> SR2_ERR_CUDA).
+#ifdef SR2_DEBUG_CHECKS
+#include <assert.h>
+#define SR2_DCHECK(cond) assert(cond)
+#else
+#define SR2_DCHECK(cond) ((void)0)
+#endif
+
 typedef unsigned long long u64;
 
 // Device view of the species tree (all pointers are device memory).

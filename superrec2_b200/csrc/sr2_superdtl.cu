@@ -53,7 +53,7 @@ struct SuperProblem {
     unsigned long long* d_best = nullptr;                // packed (cost, instance, root)
     int32_t* d_allowed = nullptr;                        // [N] the only species a node may map to, -1 = any
     bool solved = false;
-    int spad = 0, wave_warps = 0;
+    int spad = 0, wave_warps = 0, cta_threads = 256;
     size_t wave_smem = 0;
     bool cta_per_row = false;
     // shared-row mode (resolutions of one multifurcating tree, SharedPlan): the table has one row per
@@ -154,6 +154,78 @@ __global__ void syn_lca_wave(const int32_t* __restrict__ row_node, const int32_t
         sub1 &= (mine & ~Lr) == 0;
     }
     row_flags[gr] = (uint8_t)((sub0 ? 1 : 0) | (sub1 ? 2 : 0));
+}
+
+// All four passes above for ONE instance in one launch (one CTA, a barrier per wave): a single tree has
+// nothing to fill the machine with, so its 3 H + 1 launches were pure launch latency (config #4: 61
+// launches, 0.2 ms of a 0.86 ms solve).  Rows of wave h = [off[h], off[h+1]).
+#define SYN_SINGLE_MAXH 120
+struct SynWaves {
+    int H;
+    int32_t off[SYN_SINGLE_MAXH + 2];
+};
+__global__ void __launch_bounds__(1024)
+syn_single_kernel(SynWaves wo, const int32_t* __restrict__ row_node, const int32_t* __restrict__ row_left,
+                  const int32_t* __restrict__ row_right, const int32_t* __restrict__ left,
+                  const int32_t* __restrict__ right, int N, int W, const uint32_t* __restrict__ bits,
+                  uint32_t* __restrict__ present, uint32_t* __restrict__ outside, uint32_t* __restrict__ gain,
+                  uint32_t* __restrict__ L, uint8_t* __restrict__ row_flags) {
+    const int t = threadIdx.x, T = blockDim.x;
+    for (int i = t; i < N * W; i += T) {
+        const uint32_t b = bits[i];
+        present[i] = b;
+        L[i] = b;
+        outside[i] = 0;
+    }
+    __syncthreads();
+    for (int h = 1; h <= wo.H; ++h) {   // syn_present_wave
+        const int r0 = wo.off[h], n = wo.off[h + 1] - r0;
+        for (int i = t; i < n * W; i += T) {
+            const int gr = r0 + i / W, w = i % W;
+            present[(size_t)row_node[gr] * W + w] =
+                present[(size_t)row_left[gr] * W + w] | present[(size_t)row_right[gr] * W + w];
+        }
+        __syncthreads();
+    }
+    for (int h = wo.H; h >= 1; --h) {   // syn_outside_wave
+        const int r0 = wo.off[h], n = wo.off[h + 1] - r0;
+        for (int i = t; i < n * W; i += T) {
+            const int gr = r0 + i / W, w = i % W;
+            const uint32_t mine = outside[(size_t)row_node[gr] * W + w];
+            const size_t l = (size_t)row_left[gr] * W + w, r = (size_t)row_right[gr] * W + w;
+            outside[l] = mine | present[r];
+            outside[r] = mine | present[l];
+        }
+        __syncthreads();
+    }
+    for (int i = t; i < N * W; i += T) {   // syn_gain_kernel
+        const int u = i / W, w = i % W;
+        uint32_t full = present[i] & ~outside[i];
+        const int l = left[u];
+        if (l >= 0) {
+            const size_t li = (size_t)l * W + w, ri = (size_t)right[u] * W + w;
+            full &= ~((present[li] & ~outside[li]) | (present[ri] & ~outside[ri]));
+        }
+        gain[i] = full;
+    }
+    __syncthreads();
+    for (int h = 1; h <= wo.H; ++h) {   // syn_lca_wave
+        const int r0 = wo.off[h], n = wo.off[h + 1] - r0;
+        for (int i = t; i < n; i += T) {
+            const int gr = r0 + i;
+            const size_t u = (size_t)row_node[gr] * W, l = (size_t)row_left[gr] * W, r = (size_t)row_right[gr] * W;
+            bool sub0 = true, sub1 = true;
+            for (int w = 0; w < W; ++w) {
+                const uint32_t Ll = L[l + w], Lr = L[r + w];
+                const uint32_t mine = (Ll | Lr) & ~(gain[l + w] | gain[r + w]);
+                L[u + w] = mine;
+                sub0 &= (mine & ~Ll) == 0;
+                sub1 &= (mine & ~Lr) == 0;
+            }
+            row_flags[gr] = (uint8_t)((sub0 ? 1 : 0) | (sub1 ? 2 : 0));
+        }
+        __syncthreads();
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -269,7 +341,7 @@ __host__ __device__ __forceinline__ size_t super_topology_bytes(int S, int D, in
 //   3. the cells, element-wise over the species with every lane busy: 6 candidates per kind.
 // TPR = 32: one warp per row (small species trees); TPR = 256: one CTA per row.
 template <int TPR>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TPR == 32 ? 256 : TPR)
 superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                      const uint8_t* __restrict__ row_flags, int64_t row_begin, int64_t chunk_row0, int n_rows,
                      int32_t* __restrict__ T, uint32_t* __restrict__ tags, SuperCosts cs, int spad,
@@ -300,6 +372,8 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     const size_t slot = (size_t)(gr - chunk_row0);
     u64* base = smem + (size_t)group * 12 * spad;
     const int flags = row_flags[gr];
+    SR2_DCHECK(row_cl[gr] < (int)slot && row_cr[gr] < (int)slot && row_cl[gr] >= -S && row_cr[gr] >= -S);
+    SR2_DCHECK(flags >= 0 && flags < 4);
     // allowed_species of _compute_uspfs_table (:340-356): every species (superdtl) or one species per
     // object node (base_uspfs); cells of other species are never created
     const int only = allowed ? allowed[row_node[gr]] : -1;
@@ -330,16 +404,17 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     }
     sgroup_sync<TPR>();
 
-    // 1. up-sweep of all 12 rows
+    // 1. up-sweep of all 12 rows.  A work item is (internal species of the level, key row): the levels of a
+    // species tree are narrow (config #5: 3.6 internal species per level on average), so lanes over species
+    // alone left 7 of 8 lanes idle while the busy ones walked the 12 rows one after the other.
     for (int d = sp.D - 2; d >= 0; --d) {
-        const int b = s_lvl[d], e = s_lvl[d + 1];
-        for (int i = b + lane; i < e; i += TPR) {
+        const int b = s_lvl[d], items = (s_lvl[d + 1] - b) * 12;
+        for (int it = lane; it < items; it += TPR) {
+            const int i = b + it / 12, a = it % 12;
             const int p = s_int[i], c = 2 * i + 1;
-#pragma unroll
-            for (int a = 0; a < 12; ++a) {
-                u64* arr = base + (size_t)a * spad;
-                arr[p] = key_min(arr[p], key_min(arr[c], arr[c + 1]));
-            }
+            SR2_DCHECK(i < sp.n_internal && p < S && c + 1 < S && p < c);
+            u64* arr = base + (size_t)a * spad;
+            arr[p] = key_min(arr[p], key_min(arr[c], arr[c + 1]));
         }
         sgroup_sync<TPR>();
     }
@@ -348,16 +423,14 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     if (lane < 4) SARR(base, spad, lane >> 1, lane & 1, T_SEP)[0] = SR2_KEY_NONE;
     sgroup_sync<TPR>();
     for (int d = 0; d < sp.D - 1; ++d) {
-        const int b = s_lvl[d], e = s_lvl[d + 1];
-        for (int i = b + lane; i < e; i += TPR) {
+        const int b = s_lvl[d], items = (s_lvl[d + 1] - b) * 4;
+        for (int it = lane; it < items; it += TPR) {
+            const int i = b + (it >> 2), a = it & 3;
             const int p = s_int[i], c = 2 * i + 1;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                u64* E = SARR(base, spad, a >> 1, a & 1, T_SEP);
-                const u64 Pp = E[p], m0 = E[c], m1 = E[c + 1];
-                E[c] = key_min(Pp, m1);
-                E[c + 1] = key_min(Pp, m0);
-            }
+            u64* E = SARR(base, spad, a >> 1, a & 1, T_SEP);
+            const u64 Pp = E[p], m0 = E[c], m1 = E[c + 1];
+            E[c] = key_min(Pp, m1);
+            E[c + 1] = key_min(Pp, m0);
         }
         sgroup_sync<TPR>();
     }
@@ -517,6 +590,8 @@ scost_kernel(DevSpecies sp, const int64_t* __restrict__ node_off, const int32_t*
         int r = right[u];
         unsigned eu = dec[(size_t)u * sp.S + k], el = dec[(size_t)l * sp.S + k], er = dec[(size_t)r * sp.S + k];
         int p = eu >> 1, a = el >> 1, c = er >> 1;
+        SR2_DCHECK(l > u && r > u && r < n_nodes && eu != DEC_NONE && el != DEC_NONE && er != DEC_NONE);
+        SR2_DCHECK(p < sp.S && a < sp.S && c < sp.S);
         int dp = __ldg(sp.depth + p), da = __ldg(sp.depth + a), dc = __ldg(sp.depth + c);
         bool pa = sp_anc(sp, p, a), pc = sp_anc(sp, p, c);
         // labelling cost (model/reconciliation.py:511-543)
@@ -1020,6 +1095,9 @@ sfused_compact_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__ left, c
                 const unsigned tag = tags[at], ev = evs[at];
                 const unsigned el = tag & 0xffffu, er = tag >> 16;
                 const int l = sL[u], r = sR[u];
+                // a tag only ever points at finite child cells; children follow their parent in id order
+                SR2_DCHECK(tag != SR2_NO_TAG && (int)(el >> 1) < S && (int)(er >> 1) < S);
+                SR2_DCHECK(u < Gb && l > u && r > u && l < Gb && r < Gb && own < (unsigned)Gb);
                 ent[l * S + k] = (uint16_t)((((el & 1) ? own : (unsigned)l) << 8) | el);
                 ent[r * S + k] = (uint16_t)((((er & 1) ? own : (unsigned)r) << 8) | er);
                 ent[u * S + k] = (uint16_t)((own << 8) | ((ev & 3) << 2) | ((el & 1) << 1) | (er & 1));
@@ -1031,6 +1109,7 @@ sfused_compact_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__ left, c
                         while (g) {
                             const int f = __ffs(g) - 1;
                             g &= g - 1;
+                            SR2_DCHECK(sOwner[(w * 32 + f) * S + k] == 0xff);   // a family is gained at ONE node
                             sOwner[(w * 32 + f) * S + k] = (uint8_t)own;
                         }
                     }
@@ -1408,6 +1487,13 @@ extern "C" int sr2_superdtl_set_allowed(sr2_ctx* ctx, const int32_t* node_specie
     return SR2_OK;
 }
 
+#define SUPER_WAVE_CTA(threads, grid, smem, stream, ...)                                            \
+    do {                                                                                            \
+        if ((threads) == 1024) superdtl_wave_kernel<1024><<<grid, 1024, smem, stream>>>(__VA_ARGS__); \
+        else if ((threads) == 512) superdtl_wave_kernel<512><<<grid, 512, smem, stream>>>(__VA_ARGS__); \
+        else superdtl_wave_kernel<256><<<grid, 256, smem, stream>>>(__VA_ARGS__);                    \
+    } while (0)
+
 static int super_configure(sr2_ctx* ctx, SuperProblem* p) {
     const int S = ctx->S;
     p->spad = (S + 1) & ~1;
@@ -1424,7 +1510,15 @@ static int super_configure(sr2_ctx* ctx, SuperProblem* p) {
     } else {
         p->cta_per_row = true;
         p->wave_smem = per_row + topology;
+        // one CTA per row: the staging and the cells are throughput-bound inside the CTA (a wave of a single
+        // instance is a handful of CTAs on an empty machine), so large species trees get more threads
+        p->cta_threads = S > 384 ? 512 : 256;   // config #4 (S = 999): 256 / 512 / 1024 threads -> 0.434 / 0.395 / 0.413 ms of waves
+        if (const char* t = getenv("SR2_SUPERDTL_CTA_THREADS")) p->cta_threads = atoi(t) >= 1024 ? 1024 : (atoi(t) >= 512 ? 512 : 256);
         SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
+        SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
+        SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->wave_smem));
     }
     return SR2_OK;
@@ -1515,9 +1609,8 @@ static int super_solve_shared(sr2_ctx* ctx, SuperProblem* p) {
                 ctx->dsp, p->d_slot_cl, p->d_slot_cr, p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad,
                 nullptr, nullptr, p->d_ev);
         } else {
-            superdtl_wave_kernel<256><<<(unsigned)n, 256, p->wave_smem, st>>>(
-                ctx->dsp, p->d_slot_cl, p->d_slot_cr, p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad,
-                nullptr, nullptr, p->d_ev);
+            SUPER_WAVE_CTA(p->cta_threads, (unsigned)n, p->wave_smem, st, ctx->dsp, p->d_slot_cl, p->d_slot_cr,
+                           p->d_row_flags, wo[h], 0, (int)n, p->d_T, p->d_tag, cs, p->spad, nullptr, nullptr, p->d_ev);
         }
         ++n_launch;
         ++n_waves;
@@ -1588,32 +1681,44 @@ extern "C" int sr2_superdtl_solve(sr2_ctx* ctx) {
     SR2_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
     size_t nw = (size_t)N * W;
     // ---- gain sets and lca sets ------------------------------------------------------
-    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_present, p->d_bits, nw * 4, cudaMemcpyDeviceToDevice, st));
-    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_L, p->d_bits, nw * 4, cudaMemcpyDeviceToDevice, st));
-    SR2_CUDA(ctx, cudaMemsetAsync(p->d_outside, 0, std::max<size_t>(nw * 4, 4), st));
+    const bool syn_single = B == 1 && H >= 1 && H <= SYN_SINGLE_MAXH && N * W < (1 << 22);
+    if (!syn_single) {
+        SR2_CUDA(ctx, cudaMemcpyAsync(p->d_present, p->d_bits, nw * 4, cudaMemcpyDeviceToDevice, st));
+        SR2_CUDA(ctx, cudaMemcpyAsync(p->d_L, p->d_bits, nw * 4, cudaMemcpyDeviceToDevice, st));
+        SR2_CUDA(ctx, cudaMemsetAsync(p->d_outside, 0, std::max<size_t>(nw * 4, 4), st));
+    }
     SR2_CUDA(ctx, cudaMemsetAsync(p->d_tau, 0xff, std::max<size_t>(nw * 128, 4), st));
     SR2_CUDA(ctx, cudaMemsetAsync(p->d_taumin, 0xff, std::max<size_t>((size_t)N * 4, 4), st));
     SR2_CUDA(ctx, cudaMemsetAsync(p->d_best, 0xff, 8, st));
-    for (int h = 1; h <= H; ++h) {
+    if (syn_single) {
+        SynWaves wo;
+        wo.H = H;
+        for (int h = 0; h <= H + 1; ++h) wo.off[h] = (int32_t)c.wave_off[h];
+        syn_single_kernel<<<1, 1024, 0, st>>>(wo, rows.row_node, rows.row_left, rows.row_right, p->d_left, p->d_right,
+                                              (int)N, W, p->d_bits, p->d_present, p->d_outside, p->d_gain, p->d_L,
+                                              p->d_row_flags);
+        ++n_launch;
+    }
+    for (int h = 1; h <= H && !syn_single; ++h) {
         int64_t n = c.wave_off[h + 1] - c.wave_off[h];
         if (n <= 0) continue;
         syn_present_wave<<<grid_for(n * W, 256), 256, 0, st>>>(rows.row_node, rows.row_left, rows.row_right,
                                                                c.wave_off[h], (int)n, W, p->d_present);
         ++n_launch;
     }
-    for (int h = H; h >= 1; --h) {
+    for (int h = H; h >= 1 && !syn_single; --h) {
         int64_t n = c.wave_off[h + 1] - c.wave_off[h];
         if (n <= 0) continue;
         syn_outside_wave<<<grid_for(n * W, 256), 256, 0, st>>>(rows.row_node, rows.row_left, rows.row_right,
                                                                c.wave_off[h], (int)n, W, p->d_present, p->d_outside);
         ++n_launch;
     }
-    if (N > 0) {
+    if (N > 0 && !syn_single) {
         syn_gain_kernel<<<grid_for(N * W, 256), 256, 0, st>>>(p->d_left, p->d_right, N, W, p->d_present,
                                                               p->d_outside, p->d_gain);
         ++n_launch;
     }
-    for (int h = 1; h <= H; ++h) {
+    for (int h = 1; h <= H && !syn_single; ++h) {
         int64_t n = c.wave_off[h + 1] - c.wave_off[h];
         if (n <= 0) continue;
         syn_lca_wave<<<grid_for(n, 256), 256, 0, st>>>(rows.row_node, rows.row_left, rows.row_right, c.wave_off[h],
@@ -1630,9 +1735,9 @@ extern "C" int sr2_superdtl_solve(sr2_ctx* ctx) {
                 ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, c.wave_off[h], c.row_begin, (int)n, p->d_T,
                 p->d_tag, cs, p->spad, rows.row_node, p->d_allowed, nullptr);
         } else {
-            superdtl_wave_kernel<256><<<(unsigned)n, 256, p->wave_smem, st>>>(
-                ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, c.wave_off[h], c.row_begin, (int)n, p->d_T,
-                p->d_tag, cs, p->spad, rows.row_node, p->d_allowed, nullptr);
+            SUPER_WAVE_CTA(p->cta_threads, (unsigned)n, p->wave_smem, st, ctx->dsp, rows.row_cl, rows.row_cr,
+                           p->d_row_flags, c.wave_off[h], c.row_begin, (int)n, p->d_T, p->d_tag, cs, p->spad,
+                           rows.row_node, p->d_allowed, nullptr);
         }
         ++n_launch;
         ++n_waves;
