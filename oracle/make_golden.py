@@ -409,6 +409,16 @@ def main():
             random_instance(rng2, n_s, n_o, i % 3 != 2, mode, families=rng2.randint(1, 6),
                             name_internal=i % 2 == 0)))
     write("base_uspfs.json.gz", base)
+    # usreconcile_base_uspfs under RetentionPolicy.ALL (tests/compute/test_unordered_super_reconciliation.py:210-291
+    # has an instance with two solutions): the first 60 instances above, every solution
+    base_all = []
+    for fixture in base[:60]:
+        srec_input = SuperReconciliationInput.from_dict(fixture["input"])
+        results = list(quiet(ref_usr.usreconcile_base_uspfs, srec_input, RetentionPolicy.ALL))
+        base_all.append({"kind": "base_uspfs_all", "input": fixture["input"],
+                         "min_cost": num(results[0].cost()) if results else None,
+                         "solutions": sorted(json.dumps(out.to_dict(), sort_keys=True) for out in results)})
+    write("base_uspfs_all.json.gz", base_all)
 
     # ---- dtl, every solution (--solutions all) ------------------------------------------
     rng3 = random.Random(20261021)

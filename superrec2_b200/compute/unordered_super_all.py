@@ -48,15 +48,20 @@ LCA, INH = 0, 1
 class _Resolution:
     """One binary resolution: device value table + host-side ALL-retention tag sets."""
 
-    def __init__(self, ctx, bin_input, families, costs):
+    def __init__(self, ctx, bin_input, families, costs, allowed=None):
         species, objects, _, bits = flatten_super(bin_input, None, families)
         self.species, self.objects = species, objects
         ctx.set_species(species.parent, species.child0, species.child1)
         n = len(objects.nodes)
         ctx.set_policy(_lib.SR2_POLICY_ALL)
         try:
-            ctx.superdtl_run(np.asarray([0, n], np.int64), objects.left, objects.right, objects.leaf_species,
-                             bits, costs)
+            ctx.superdtl_upload(np.asarray([0, n], np.int64), objects.left, objects.right, objects.leaf_species,
+                                bits, costs)
+            if allowed is not None:
+                # cells of other species are never created (allowed_species of _compute_uspfs_table,
+                # :340-356): their values stay infinite, so neither a tag nor a root can reach them
+                ctx.superdtl_set_allowed(allowed(bin_input, objects, species))
+            ctx.superdtl_solve()
             value, _, gain, lca = ctx.superdtl_tables(0)
         finally:
             ctx.set_policy(_lib.SR2_POLICY_ANY)
@@ -155,12 +160,13 @@ class _Resolution:
         return result
 
 
-def usreconcile_extended_uspfs_all(srec_input: SuperReconciliationInput, device: int = 0
+def usreconcile_extended_uspfs_all(srec_input: SuperReconciliationInput, device: int = 0, allowed=None
                                    ) -> Set[SuperReconciliationOutput]:
     """
     All minimum-cost unordered super-reconciliations over every binary resolution of the input,
     as ``usreconcile_extended_uspfs(srec_input, RetentionPolicy.ALL)`` of the reference returns
-    them (module docstring: which part of that answer is well defined).
+    them (module docstring: which part of that answer is well defined).  ``allowed`` restricts every
+    object node to one species (``usreconcile_base_uspfs`` under ALL, binary inputs).
     """
     import sys
 
@@ -173,7 +179,7 @@ def usreconcile_extended_uspfs_all(srec_input: SuperReconciliationInput, device:
     for index in range(srec_input.count_resolutions()):
         bin_input = srec_input.resolution(index)
         bin_input.label_internal()
-        res = _Resolution(ctx, bin_input, families, costs)
+        res = _Resolution(ctx, bin_input, families, costs, allowed)
         nodes, sp_nodes = res.objects.nodes, res.species.nodes
         left, right = res.objects.left, res.objects.right
         live = list(res.clean)        # lca_sets: LIVE across the roots of this resolution (:463-464)

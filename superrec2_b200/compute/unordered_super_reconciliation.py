@@ -83,8 +83,9 @@ def usreconcile_extended_uspfs(
     implementation returns (same tie-breaking, same synteny labelling).
 
     :param srec_input: objects of the super-reconciliation
-    :param policy: ``RetentionPolicy.ANY`` (one solution)
-    :returns: any minimum-cost super-reconciliation, if there is one
+    :param policy: ``RetentionPolicy.ANY`` (one solution) or ``ALL`` (every minimum-cost solution; the value
+        tables come from the GPU, the enumeration runs on the host, ``compute/unordered_super_all.py``)
+    :returns: any minimum-cost super-reconciliation, if there is one, or all of them
     """
     return usreconcile_extended_uspfs_sharded(srec_input, policy)
 
@@ -235,10 +236,10 @@ def usreconcile_extended_uspfs_sharded(
     reference's ``_compute_uspfs_table`` (``:300-358``).
     """
     if policy is RetentionPolicy.ALL:
-        if n_shards != 1 or allowed is not None:
-            raise NotImplementedError("--solutions all runs on one GPU, without species restrictions")
+        if n_shards != 1:
+            raise NotImplementedError("--solutions all enumerates on the host: one GPU, no shards")
         from .unordered_super_all import usreconcile_extended_uspfs_all
-        return usreconcile_extended_uspfs_all(srec_input, device)
+        return usreconcile_extended_uspfs_all(srec_input, device, allowed)
     if policy is not RetentionPolicy.ANY:
         raise ValueError(f"unsupported retention policy {policy!r}")
     total = srec_input.count_resolutions()
@@ -269,8 +270,8 @@ def usreconcile_base_uspfs(
     children per node).
 
     :param srec_input: objects of the super-reconciliation
-    :param policy: ``RetentionPolicy.ANY`` (one solution)
-    :returns: any minimum-cost super-reconciliation, if there is one
+    :param policy: ``RetentionPolicy.ANY`` (one solution) or ``ALL`` (every minimum-cost solution)
+    :returns: any minimum-cost super-reconciliation, if there is one, or all of them
     """
     from ..utils.trees import is_binary
     from .reconciliation import reconcile_lca

@@ -86,6 +86,8 @@ struct DtlProblem {
     int spad = 0, wave_warps = 0;
     size_t wave_smem = 0;
     bool cta_per_row = false;
+    int wave_threads = 512;          // CTA size of the one-CTA-per-row kernel
+    bool wave_inplace = false;       // the two-row form of the CTA-per-row kernel (very large species trees)
     // batched wave kernels (32-bit keys)
     bool simd_ok = false;
     int rank_bits = 0, depth_bits = 0;
@@ -174,11 +176,119 @@ __device__ __forceinline__ void dtl_cell(int x, int dx, int cx, bool is_root, u6
     }
 }
 
-// TPR = threads per row: 32 (one warp per row, several rows per CTA) or the CTA
-// size (one row per CTA, for species trees too large for a warp's share of smem).
+// Species topology staged once per CTA behind the key rows (see superdtl_wave_kernel): per-species
+// (child0 + 1) << 16 | depth, level offsets of the internal species, their level-order ranks.
+__host__ __device__ __forceinline__ size_t dtl_topology_bytes(int S, int D, int n_int) {
+    return ((size_t)S + (size_t)D + 1) * 4 + (((size_t)n_int + 1) & ~(size_t)1) * 2;
+}
+
+// TPR = threads per row: 32 (one warp per row, several rows per CTA) or the CTA size (one row per
+// CTA, for species trees too large for a warp's share of shared memory: BASELINE config #3).
+// Four key rows per object node -- SUBMIN of the left / right child (Ml, Mr), SEPMIN (Pl, Pr) -- and
+// three phases: up-sweep of Ml / Mr, top-down sweep filling Pl / Pr, then the cells element-wise.
+// The sweeps take one step per species level; their work items are (internal species, key row) so
+// that narrow levels still use the lanes, and nothing in the level loops touches global memory
+// (ncu r3b on the superdtl twin of this kernel: the per-level __ldg of the first form cost more
+// than the arithmetic).
 template <int TPR>
 __global__ void __launch_bounds__(TPR == 32 ? 256 : TPR)
 dtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
+                const int32_t* __restrict__ row_cr, int64_t row_begin, int64_t chunk_row0,
+                int n_rows, int32_t* __restrict__ T, uint32_t* __restrict__ tags, DtlCosts cs,
+                int spad) {
+    extern __shared__ u64 smem[];
+    const int S = sp.S;
+    int group, lane, groups_per_cta;
+    if (TPR == 32) {
+        group = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        groups_per_cta = blockDim.x >> 5;
+    } else {
+        group = 0;
+        lane = threadIdx.x;
+        groups_per_cta = 1;
+    }
+    uint32_t* s_meta = reinterpret_cast<uint32_t*>(smem + (size_t)groups_per_cta * 4 * spad);
+    int32_t* s_lvl = reinterpret_cast<int32_t*>(s_meta + S);
+    uint16_t* s_int = reinterpret_cast<uint16_t*>(s_lvl + sp.D + 1);
+    for (int i = threadIdx.x; i < S; i += blockDim.x) s_meta[i] = __ldg(sp.meta + i);
+    for (int i = threadIdx.x; i <= sp.D; i += blockDim.x) s_lvl[i] = __ldg(sp.int_lvl_off + i);
+    for (int i = threadIdx.x; i < sp.n_internal; i += blockDim.x) s_int[i] = (uint16_t)__ldg(sp.int_list + i);
+    __syncthreads();
+    int local = blockIdx.x * groups_per_cta + group;
+    if (local >= n_rows) return;  // uniform per group
+    const int64_t gr = row_begin + local;              // global row
+    const size_t slot = (size_t)(gr - chunk_row0);     // row inside the chunk's tables
+    u64* base = smem + (size_t)group * 4 * spad;       // Ml, Mr, Pl, Pr
+    u64* Ml = base;
+    u64* Mr = base + spad;
+    const int cl = row_cl[gr], cr = row_cr[gr];
+    SR2_DCHECK(cl < (int)slot && cr < (int)slot && cl >= -S && cr >= -S);
+    const int32_t* __restrict__ Tl = cl >= 0 ? T + (size_t)cl * sp.pitch : nullptr;
+    const int32_t* __restrict__ Tr = cr >= 0 ? T + (size_t)cr * sp.pitch : nullptr;
+
+    // stage the two child rows as keys
+    for (int y = lane; y < S; y += TPR) {
+        const int d = (int)(s_meta[y] & 0xffffu);
+        const int vl = Tl ? Tl[y] : (y == -1 - cl ? 0 : SR2_INF);
+        const int vr = Tr ? Tr[y] : (y == -1 - cr ? 0 : SR2_INF);
+        Ml[y] = key_make(vl, y, d);
+        Mr[y] = key_make(vr, y, d);
+    }
+    group_sync<TPR>();
+
+    // 1. up-sweep: M[y] <- min over subtree(y); the deepest level has leaves only
+    for (int d = sp.D - 2; d >= 0; --d) {
+        const int b = s_lvl[d], items = (s_lvl[d + 1] - b) * 2;
+        for (int it = lane; it < items; it += TPR) {
+            const int i = b + (it >> 1);
+            const int p = s_int[i], c = 2 * i + 1;
+            u64* arr = base + (size_t)(it & 1) * spad;
+            arr[p] = key_min(arr[p], key_min(arr[c], arr[c + 1]));
+        }
+        group_sync<TPR>();
+    }
+
+    // 2. SEPMIN: nothing is incomparable to the root; P[child] = min(P[parent], M[sibling])
+    if (lane < 2) base[(size_t)(2 + lane) * spad] = SR2_KEY_NONE;
+    group_sync<TPR>();
+    for (int d = 0; d < sp.D - 1; ++d) {
+        const int b = s_lvl[d], items = (s_lvl[d + 1] - b) * 2;
+        for (int it = lane; it < items; it += TPR) {
+            const int i = b + (it >> 1);
+            const int p = s_int[i], c = 2 * i + 1;
+            const u64* M = base + (size_t)(it & 1) * spad;
+            u64* P = base + (size_t)(2 + (it & 1)) * spad;
+            const u64 Pp = P[p];
+            P[c] = key_min(Pp, M[c + 1]);
+            P[c + 1] = key_min(Pp, M[c]);
+        }
+        group_sync<TPR>();
+    }
+
+    // 3. the cells
+    int32_t* __restrict__ Tout = T + slot * sp.pitch;
+    uint32_t* __restrict__ Gout = tags + slot * sp.pitch;
+    const u64* Pl = base + (size_t)2 * spad;
+    const u64* Pr = base + (size_t)3 * spad;
+    for (int x = lane; x < S; x += TPR) {
+        const uint32_t m = s_meta[x];
+        int best;
+        unsigned tag;
+        dtl_cell(x, (int)(m & 0xffffu), (int)(m >> 16) - 1, x == 0, Ml[x], Mr[x], Pl[x], Pr[x], Ml, Mr, cs, best,
+                 tag);
+        Tout[x] = best;
+        Gout[x] = tag;
+    }
+}
+
+
+// The first form of the kernel above, kept for species trees whose four key rows do not fit one CTA's
+// shared memory (more than ~5,900 species nodes): two key rows, SEPMIN written in place over SUBMIN and
+// the cells computed inside the top-down sweep.
+template <int TPR>
+__global__ void __launch_bounds__(TPR == 32 ? 256 : TPR)
+dtl_wave_inplace_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
                 const int32_t* __restrict__ row_cr, int64_t row_begin, int64_t chunk_row0,
                 int n_rows, int32_t* __restrict__ T, uint32_t* __restrict__ tags, DtlCosts cs,
                 int spad) {
@@ -1698,20 +1808,32 @@ extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
 static int dtl_configure_waves(sr2_ctx* ctx, DtlProblem* p) {
     const int S = ctx->S;
     p->spad = (S + 1) & ~1;
-    const size_t per_row = (size_t)2 * p->spad * sizeof(u64);
+    const size_t per_row = (size_t)4 * p->spad * sizeof(u64);   // Ml, Mr, Pl, Pr
+    const size_t topology = dtl_topology_bytes(S, ctx->D, ctx->n_internal);
     if (S <= 1024) {
         p->cta_per_row = false;
-        p->wave_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx->smem_optin - 1024) / per_row));
-        p->wave_smem = per_row * p->wave_warps;
+        p->wave_warps = (int)std::max<size_t>(1, std::min<size_t>(8, (ctx->smem_optin - 1024 - topology) / per_row));
+        p->wave_smem = per_row * p->wave_warps + topology;
         SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->wave_smem));
     } else {
-        if (per_row > ctx->smem_optin)
-            return sr2_fail(ctx, SR2_ERR_RANGE, "dtl: species tree too large for one CTA's shared memory");
         p->cta_per_row = true;
         p->wave_warps = 16;
-        p->wave_smem = per_row;
+        p->wave_inplace = per_row + topology > ctx->smem_optin;
+        if (p->wave_inplace) {
+            if (per_row / 2 > ctx->smem_optin)
+                return sr2_fail(ctx, SR2_ERR_RANGE, "dtl: species tree too large for one CTA's shared memory");
+            p->wave_smem = per_row / 2;
+            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_inplace_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)p->wave_smem));
+            return SR2_OK;
+        }
+        p->wave_smem = per_row + topology;
+        p->wave_threads = S > 2048 ? 1024 : 512;
+        if (const char* t = getenv("SR2_DTL_CTA_THREADS")) p->wave_threads = atoi(t) >= 1024 ? 1024 : 512;
         SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
+        SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->wave_smem));
     }
     return SR2_OK;
@@ -1898,9 +2020,18 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
             p->spad);
     } else {
-        dtl_wave_kernel<512><<<(unsigned)n_rows, 512, p->wave_smem, p->cur_stream>>>(
+        if (p->wave_inplace)
+            dtl_wave_inplace_kernel<512><<<(unsigned)n_rows, 512, p->wave_smem, p->cur_stream>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
             p->spad);
+        else if (p->wave_threads == 1024)
+            dtl_wave_kernel<1024><<<(unsigned)n_rows, 1024, p->wave_smem, p->cur_stream>>>(
+                ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
+                p->spad);
+        else
+            dtl_wave_kernel<512><<<(unsigned)n_rows, 512, p->wave_smem, p->cur_stream>>>(
+                ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs,
+                p->spad);
     }
     SR2_CUDA(ctx, cudaGetLastError());
     return SR2_OK;

@@ -537,3 +537,23 @@ def test_sixteen_bit_run_equals_the_32_bit_run(ctx, pinned):
     with pytest.raises(_lib.Sr2Error) as err:
         ctx.dtl_run16(big.node_off, big.left % 30000, big.right % 30000, big.leaf_species, big.costs)
     assert err.value.code == -3
+
+
+def test_very_large_species_tree_uses_the_two_row_kernel(ctx):
+    """More than ~5,900 species nodes: the four key rows of dtl_wave_kernel no longer fit one CTA's shared
+    memory and the two-row in-place form runs instead.  6,399 species nodes, a 24-leaf object tree whose
+    leaves sit at random species leaves (not surjective: roots without an entry are skipped, as in the
+    oracle's non-strict mode); full table, tags, result against the oracle."""
+    species = synth.make_batch(3200, 3200, 1, seed=61)
+    small = synth.make_batch(24, 24, 1, seed=62)
+    rng = np.random.default_rng(63)
+    leaves = np.flatnonzero(species.child0 < 0)
+    leaf_species = np.where(small.left < 0, leaves[rng.integers(0, len(leaves), len(small.left))], -1).astype(np.int32)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    args = (small.node_off, small.left, small.right, leaf_species, small.costs)
+    min_cost, root, mapping = ctx.dtl_run(*args, flags=_lib.SR2_KEEP_TABLES)
+    ref = oracle.dtl(species.parent, species.child0, species.child1, small.left, small.right, leaf_species,
+                     small.costs, strict=False)
+    value, tag = ctx.dtl_tables(0, len(small.left))
+    assert (value == ref["value"]).all() and (tag == ref["tag"]).all()
+    assert min_cost[0] == ref["min_cost"] and root[0] == ref["root_species"] and (mapping == ref["mapping"]).all()

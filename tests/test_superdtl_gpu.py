@@ -336,3 +336,18 @@ def test_fused_decode_kernels_agree_with_the_unfused_path(ctx, monkeypatch, wide
             outs.append((ctx.superdtl_results(costs_only=True), ctx.superdtl_best()))
         assert (outs[0][0][0] == outs[1][0][0]).all() and (outs[0][0][1] == outs[1][0][1]).all()
         assert outs[0][1] == outs[1][1]
+
+
+def test_base_uspfs_all_solutions_against_the_reference(golden):
+    """usreconcile_base_uspfs under RetentionPolicy.ALL (the reference's own test has an instance with two
+    solutions, tests/compute/test_unordered_super_reconciliation.py:210-291): the exact solution set."""
+    import json
+    from superrec2_b200.compute.unordered_super_reconciliation import usreconcile_base_uspfs
+    fixtures = golden("base_uspfs_all.json.gz")
+    assert any(len(fixture["solutions"]) > 1 for fixture in fixtures)
+    for fixture in fixtures:
+        srec_input = SuperReconciliationInput.from_dict(fixture["input"])
+        results = usreconcile_base_uspfs(srec_input, RetentionPolicy.ALL)
+        assert sorted(json.dumps(out.to_dict(), sort_keys=True) for out in results) == fixture["solutions"]
+        if results:
+            assert {out.cost() for out in results} == {fixture["min_cost"]}
