@@ -13,7 +13,7 @@ if [ "$mode" = list ]; then
 else
   regex=$1; skip=$2; shift 2
   "$@" > gpurun_out/plain_${label}.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_${label}.log; exit 1; }
-  ncu --set full --clock-control none --import-source on -k regex:${regex} -s ${skip} -c 1 \
+  ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:${regex}" -s ${skip} -c 1 \
       -f -o gpurun_out/prof_${label} "$@" > gpurun_out/ncu_full_${label}.log 2>&1
   tail -2 gpurun_out/ncu_full_${label}.log
 fi

@@ -116,6 +116,9 @@ class _Resolution:
         key = (u, x, kind)
         if key in self._tags:
             return self._tags[key]
+        if self.T[u, x, kind] >= BIG:      # the entry was never created (no finite candidate, or a species the
+            self._tags[key] = ()           # node is not allowed at): nothing to decode
+            return ()
         spe, dup, hgt, floss, sloss = self.costs
         kids = (int(self.objects.left[u]), int(self.objects.right[u]))
         dx = int(self.depth[x])
