@@ -104,6 +104,12 @@ struct SharedPlan {
     // arr[arr_off[v] + (j * (k-1) + q) * 2 + side]: child of joint q (preorder rank inside the block) in
     // arrangement j: >= 0 item (child number), < 0 joint -1-q'
     std::vector<int32_t> arr;
+    // arr_pre[arr_pre_off[v] + j * (2k - 1) + i]: preorder position, relative to the root of v's block, of joint i
+    // (i < k - 1) or of the root of item i - (k - 1)'s subtree in arrangement j.  The subtree of an original
+    // node has the same size in every resolution, so these only depend on (v, j); with parent[] / child_pos[]
+    // a node finds its absolute preorder position by walking up the ORIGINAL tree, without any pass over
+    // the resolved tree.
+    std::vector<int32_t> arr_pre, arr_pre_off, parent, child_pos;
     // slots, ordered by height: wave h = [wave_off[h], wave_off[h+1]), h = 1..H
     int64_t n_slots = 0;
     std::vector<int64_t> wave_off;
@@ -113,6 +119,10 @@ struct SharedPlan {
                                                 // tree; slot s: Gb + s), -1 for leaves
     std::vector<int32_t> leaf_species;          // [Gb] species of the leaves of a resolved tree, -1 elsewhere
     std::vector<uint32_t> leaf_bits;            // [Gb * W]
+    // scratch of the planner (raw slots before the sort by height); kept with the plan so that a caller
+    // that plans range after range reuses the memory instead of faulting in fresh pages every time
+    std::vector<int32_t> raw_l, raw_r;
+    std::vector<uint16_t> height;
 };
 int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_words, const int32_t costs[5],
                                uint32_t flags);

@@ -16,6 +16,8 @@
 // 2*leaves(v)-1 ids; its k-1 joints come first (block root first, then preorder of the
 // arrangement), then the blocks of its children in order.  Parents precede children.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <omp.h>
@@ -232,6 +234,15 @@ bool plan_shared(const PolyTree& t, int64_t first, int64_t count, const int32_t*
     P.raw_base.assign(n, -1);
     P.arr_off.assign(n, 0);
     P.arr.clear();
+    P.arr_pre.clear();
+    P.arr_pre_off.assign(n, 0);
+    P.parent.assign(n, -1);
+    P.child_pos.assign(n, 0);
+    for (int v = 0; v < n; ++v)
+        for (int e = t.child_off[v]; e < t.child_off[v + 1]; ++e) {
+            P.parent[t.child_idx[e]] = v;
+            P.child_pos[t.child_idx[e]] = e - t.child_off[v];
+        }
     std::vector<int64_t> n_var(n, 0);
     for (int v = 0; v < n; ++v) {
         int k = t.child_off[v + 1] - t.child_off[v];
@@ -247,12 +258,31 @@ bool plan_shared(const PolyTree& t, int64_t first, int64_t count, const int32_t*
         }
         P.arr_off[v] = (int32_t)P.arr.size();
         P.arr.resize(P.arr.size() + (size_t)t.ways[v] * (k - 1) * 2);
+        P.arr_pre_off[v] = (int32_t)P.arr_pre.size();
+        P.arr_pre.resize(P.arr_pre.size() + (size_t)t.ways[v] * (2 * k - 1));
         for (int64_t j = 0; j < t.ways[v]; ++j) {
             int code_l[MAX_ARITY], code_r[MAX_ARITY];
             arrange(k, j, code_l, code_r);
             for (int q = 0; q < k - 1; ++q) {
                 P.arr[P.arr_off[v] + (j * (k - 1) + q) * 2 + 0] = code_l[q];
                 P.arr[P.arr_off[v] + (j * (k - 1) + q) * 2 + 1] = code_r[q];
+            }
+            // preorder walk of the block: a joint counts 1, an item the whole (resolution-independent) size
+            // of its resolved subtree
+            int32_t* rel = P.arr_pre.data() + P.arr_pre_off[v] + j * (2 * k - 1);
+            int stack[2 * MAX_ARITY], top = 0, pos = 0;
+            stack[top++] = -1;  // joint 0
+            while (top) {
+                const int code = stack[--top];
+                if (code >= 0) {
+                    rel[(k - 1) + code] = pos;
+                    pos += 2 * t.leaves[t.child_idx[t.child_off[v] + code]] - 1;
+                } else {
+                    const int q = -1 - code;
+                    rel[q] = pos++;
+                    stack[top++] = code_r[q];
+                    stack[top++] = code_l[q];
+                }
             }
         }
     }
@@ -268,8 +298,11 @@ bool plan_shared(const PolyTree& t, int64_t first, int64_t count, const int32_t*
     }
     P.n_slots = n_raw;
     // raw slots: children (as raw slots or leaves) and heights, children's blocks first
-    std::vector<int32_t> raw_l((size_t)n_raw), raw_r((size_t)n_raw);  // >= 0 raw slot, < 0: -1 - leaf's original node
-    std::vector<uint16_t> height((size_t)n_raw);
+    std::vector<int32_t>&raw_l = P.raw_l, &raw_r = P.raw_r;  // >= 0 raw slot, < 0: -1 - leaf's original node
+    std::vector<uint16_t>& height = P.height;
+    raw_l.resize((size_t)n_raw);
+    raw_r.resize((size_t)n_raw);
+    height.resize((size_t)n_raw);
     for (int v = n - 1; v >= 0; --v) {
         const int k = P.arity[v];
         if (k == 0) continue;
@@ -306,6 +339,7 @@ bool plan_shared(const PolyTree& t, int64_t first, int64_t count, const int32_t*
     }
     // slots = raw slots sorted by height (counting sort, stable)
     int H = 0;
+#pragma omp parallel for num_threads(n_threads) schedule(static) reduction(max : H) if (n_raw >= 65536)
     for (int64_t s = 0; s < n_raw; ++s) H = std::max(H, (int)height[s]);
     P.wave_off.assign(H + 2, 0);
     for (int64_t s = 0; s < n_raw; ++s) P.wave_off[height[s] + 1]++;
@@ -390,10 +424,15 @@ extern "C" int sr2_resolutions_upload(sr2_ctx* ctx, int32_t n_nodes, const int32
     const char* unshared = getenv("SR2_RESOLUTIONS_UNSHARED");
     if (!(unshared && unshared[0] == '1') && count > 0 && Gb > 1) {
         // one table row per distinct subtree, resolved trees built on the device
-        SharedPlan plan;
+        // one plan object per calling thread, reused: its vectors keep their capacity between calls
+        static thread_local SharedPlan plan;
         std::string error;
+        const auto t0 = std::chrono::steady_clock::now();
         if (!plan_shared(t, first, count, leaf_species, W, leaf_bits, ctx->host_threads, &plan, &error))
             return sr2_fail(ctx, SR2_ERR_RANGE, "sr2_resolutions_upload: " + error);
+        if (getenv("SR2_TRACE"))
+            fprintf(stderr, "[sr2] resolutions upload: host plan of %lld slots took %.2f ms\n", (long long)plan.n_slots,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         return sr2_superdtl_upload_shared(ctx, plan, W, costs, flags);
     }
     std::vector<int64_t> node_off(count + 1);

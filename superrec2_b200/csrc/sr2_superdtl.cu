@@ -22,6 +22,7 @@
 // `right` choices of the reference are cons at the two children of x.
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
 #include <cstring>
 
 #include "sr2_rows.cuh"
@@ -69,6 +70,11 @@ struct SuperProblem {
     int32_t *d_slot_cl = nullptr, *d_slot_cr = nullptr;      // [n_slots] table descriptors
     int32_t *d_dag_left = nullptr, *d_dag_right = nullptr;   // [Gb + n_slots]
     int32_t* d_slot_node = nullptr;                          // [n_slots] Gb + slot
+    // The resolved trees themselves (d_left ... d_node_inst and the per-(node, root) arrays) are only
+    // materialised when something needs them: the compact fused kernel unranks its tree itself.
+    bool trees_ready = true;
+    struct DevPlanStore* plan_store = nullptr;               // device plan of the upload (owned)
+    ~SuperProblem();
 };
 
 void sr2_free_super(sr2_ctx* ctx) {
@@ -689,8 +695,61 @@ struct DevPlan {
     int n, Gb;
     int64_t first;
     const int32_t *arity, *base, *child_off, *child_of, *arr_off, *arr, *perm;
+    const int32_t *arr_pre_off, *arr_pre, *parent, *child_pos;   // see SharedPlan::arr_pre
     const int64_t *ways, *stride, *cnt, *var_first, *raw_base;
 };
+
+struct DevPlanStore {
+    DevPlan plan;
+};
+SuperProblem::~SuperProblem() { delete plan_store; }
+
+// One original node v of resolution r: its block of k - 1 joints (local ids inside the resolved tree).
+// out_left / out_right / out_slot / out_dag are indexed by local id.
+// (r / stride) % cnt for resolution numbers below 2^24 (checked at upload) in 32-bit arithmetic: 64-bit
+// divisions are function calls on the device and every node of every tree does several of them
+__device__ __forceinline__ int64_t unrank_digit(int64_t r, int64_t stride, int64_t cnt) {
+    if (stride > r) return 0;
+    const uint32_t q = (uint32_t)r / (uint32_t)stride;
+    return cnt > (int64_t)q ? (int64_t)q : (int64_t)(q % (uint32_t)cnt);
+}
+
+__device__ __forceinline__ void unrank_node(const DevPlan& P, int64_t r, int v, int32_t* out_left, int32_t* out_right,
+                                            int32_t* out_slot, int32_t* out_dag, int32_t* out_pre, int32_t id_offset) {
+    const int k = P.arity[v];
+    const int id0 = P.base[v];
+    // preorder position of the root of v's block: up the original tree, adding where each ancestor's
+    // arrangement puts the item we came from
+    int abs_pre = 0;
+    for (int cur = v; cur != 0;) {
+        const int par = P.parent[cur], kp = P.arity[par];
+        const int64_t jp = (int64_t)((uint32_t)unrank_digit(r, P.stride[par], P.cnt[par]) % (uint32_t)P.ways[par]);
+        abs_pre += P.arr_pre[P.arr_pre_off[par] + jp * (2 * kp - 1) + (kp - 1) + P.child_pos[cur]];
+        cur = par;
+    }
+    if (k == 0) {
+        out_left[id0] = out_right[id0] = -1;
+        out_slot[id0] = -1;
+        out_dag[id0] = id0;
+        out_pre[id0] = abs_pre;
+        return;
+    }
+    const int64_t var = unrank_digit(r, P.stride[v], P.cnt[v]);
+    const int64_t j = (int64_t)((uint32_t)var % (uint32_t)P.ways[v]);
+    const int32_t* rel = P.arr_pre + P.arr_pre_off[v] + j * (2 * k - 1);
+    const int64_t raw0 = P.raw_base[v] + (var - P.var_first[v]) * (k - 1);
+    const int32_t* codes = P.arr + P.arr_off[v] + j * (k - 1) * 2;
+    const int32_t* kids = P.child_of + P.child_off[v];
+    for (int q = 0; q < k - 1; ++q) {
+        const int cl = codes[2 * q], cr = codes[2 * q + 1];
+        out_left[id0 + q] = id_offset + (cl >= 0 ? P.base[kids[cl]] : id0 + (-1 - cl));
+        out_right[id0 + q] = id_offset + (cr >= 0 ? P.base[kids[cr]] : id0 + (-1 - cr));
+        const int sl = P.perm[raw0 + q];
+        out_slot[id0 + q] = sl;
+        out_dag[id0 + q] = P.Gb + sl;
+        out_pre[id0 + q] = abs_pre + rel[q];
+    }
+}
 
 // Resolution first + i of the plan, as global-id child arrays, table row and dag id of every node,
 // preorder positions and instance numbers.  One thread per resolution.
@@ -1004,7 +1063,10 @@ __host__ __device__ __forceinline__ FusedLayout fused_layout(int Gb, int S, int 
     f.pmask = f.gain + Gb * W;
     f.slot = f.pmask + Gb * W;
     f.ent = (f.slot + Gb) * 4;
-    f.left = f.ent + ((Gb * S + 1) & ~1) * 2;
+    {
+        const int ent_bytes = ((Gb * S + 1) & ~1) * 2, scratch_bytes = 16 * Gb;   // unranking scratch lives here first
+        f.left = f.ent + ((ent_bytes > scratch_bytes ? ent_bytes : scratch_bytes) + 3) / 4 * 4;
+    }
     f.right = f.left + Gb4;
     f.pre = f.right + Gb4;
     f.fam = f.pre + Gb4;
@@ -1015,15 +1077,17 @@ __host__ __device__ __forceinline__ FusedLayout fused_layout(int Gb, int S, int 
     return f;
 }
 
+template <int WT>   // WT = 1: one synteny word (up to 32 families), loops over words disappear; WT = 0: W words
 __global__ void __launch_bounds__(128)
-sfused_compact_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
+sfused_compact_kernel(DevSpecies sp, DevPlan plan, int Gb, const int32_t* __restrict__ left, const int32_t* __restrict__ right,
                       const int32_t* __restrict__ node_slot, const int32_t* __restrict__ node_dag,
                       const int32_t* __restrict__ node_pre, const uint32_t* __restrict__ tags,
-                      const uint32_t* __restrict__ evs, int W, const uint32_t* __restrict__ gain,
+                      const uint32_t* __restrict__ evs, int W_runtime, const uint32_t* __restrict__ gain,
                       const uint32_t* __restrict__ L, SuperCosts cs, int64_t index_base,
                       int32_t* __restrict__ min_cost, int32_t* __restrict__ root_species,
                       unsigned long long* __restrict__ best_key) {
     extern __shared__ uint32_t fsm[];
+    const int W = WT ? WT : W_runtime;
     const int S = sp.S, F = 32 * W;
     const int b = blockIdx.x, k = threadIdx.x;
     const int64_t off = (int64_t)b * Gb;
@@ -1047,13 +1111,31 @@ sfused_compact_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__ left, c
     // ---- the tree, and "nothing merged yet" ---------------------------------------------------
     for (int i = threadIdx.x; i < (lay.inner - lay.owner) / 4; i += blockDim.x)
         reinterpret_cast<uint32_t*>(sOwner)[i] = 0xffffffffu;           // sOwner and sFirst
+    // The tree of this resolution.  left == nullptr: nobody materialised the resolved trees (the usual case);
+    // the CTA unranks its own from the plan, threads over the ORIGINAL nodes (children, table row, dag id and
+    // preorder position of every node of the node's block), into scratch that the decode state will overwrite.
+    int32_t* t_left = reinterpret_cast<int32_t*>(ent);          // [Gb] each (the ent region holds >= 16 Gb bytes)
+    int32_t* t_right = t_left + Gb;
+    int32_t* t_dag = t_right + Gb;
+    int32_t* t_pre = t_dag + Gb;
+    const bool unrank_here = left == nullptr;
+    if (unrank_here) {
+        int32_t* t_slot = reinterpret_cast<int32_t*>(fsm + lay.slot);
+        for (int v = threadIdx.x; v < plan.n; v += blockDim.x)
+            unrank_node(plan, plan.first + b, v, t_left, t_right, t_slot, t_dag, t_pre, 0);
+        __syncthreads();
+    }
     for (int u = threadIdx.x; u < Gb; u += blockDim.x) {
-        const int lg = left[off + u];
-        sL[u] = lg < 0 ? 0xff : (uint8_t)(lg - (int)off);
-        sR[u] = lg < 0 ? 0xff : (uint8_t)(right[off + u] - (int)off);
-        reinterpret_cast<int32_t*>(fsm + lay.slot)[u] = node_slot[off + u];
-        sPre[u] = (uint8_t)node_pre[off + u];
-        const size_t dag = (size_t)node_dag[off + u] * W;
+        const int lg = unrank_here ? t_left[u] : left[off + u];
+        const int rg = unrank_here ? t_right[u] : (lg < 0 ? -1 : right[off + u]);
+        const int base_id = unrank_here ? 0 : (int)off;
+        const uint8_t l8 = lg < 0 ? 0xff : (uint8_t)(lg - base_id), r8 = lg < 0 ? 0xff : (uint8_t)(rg - base_id);
+        const uint8_t pre8 = (uint8_t)(unrank_here ? t_pre[u] : node_pre[off + u]);
+        const size_t dag = (size_t)(unrank_here ? t_dag[u] : node_dag[off + u]) * W;
+        if (!unrank_here) reinterpret_cast<int32_t*>(fsm + lay.slot)[u] = node_slot[off + u];
+        sL[u] = l8;
+        sR[u] = r8;
+        sPre[u] = pre8;
         for (int w = 0; w < W; ++w) {
             sLca[u * W + w] = L[dag + w];
             uint32_t g = gain[dag + w];
@@ -1066,11 +1148,12 @@ sfused_compact_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__ left, c
             }
         }
     }
+    __syncthreads();
     if (threadIdx.x < 32) {   // ids of the internal nodes, in id order (parents before children)
         int count = 0;
         for (int base = 0; base < Gb; base += 32) {
             const int u = base + threadIdx.x;
-            const bool inner = u < Gb && left[off + u] >= 0;
+            const bool inner = u < Gb && sL[u] != 0xff;
             const unsigned m = __ballot_sync(0xffffffffu, inner);
             if (inner) sInt[count + __popc(m & ((1u << threadIdx.x) - 1))] = (uint8_t)u;
             count += __popc(m);
@@ -1091,7 +1174,8 @@ sfused_compact_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__ left, c
                 const int u = sInt[j];
                 const unsigned e = ent[u * S + k];
                 const unsigned own = e >> 8;
-                const size_t at = ((size_t)sSlot[u] * 2 + (e & 1)) * sp.pitch + ((e >> 1) & 0x7f);
+                // (the table has fewer than 2^31 cells: checked by the launcher)
+                const unsigned at = (unsigned)sSlot[u] * 2u * (unsigned)sp.pitch + (e & 1) * (unsigned)sp.pitch + ((e >> 1) & 0x7f);
                 const unsigned tag = tags[at], ev = evs[at];
                 const unsigned el = tag & 0xffffu, er = tag >> 16;
                 const int l = sL[u], r = sR[u];
@@ -1173,6 +1257,11 @@ sfused_compact_kernel(DevSpecies sp, int Gb, const int32_t* __restrict__ left, c
         root_species[b] = root;
         if (!none) atomicMin(best_key, ((u64)(unsigned)cost << 40) | ((u64)(index_base + b) << 16) | (unsigned)root);
     }
+}
+
+__global__ void iota64_kernel(int64_t* __restrict__ out, int64_t n, int64_t step) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i * step;
 }
 
 __global__ void iota_kernel(int32_t* __restrict__ out, int64_t n, int32_t start) {
@@ -1304,6 +1393,54 @@ extern "C" int sr2_superdtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_
     return SR2_OK;
 }
 
+// Can the compact fused kernel (which unranks its own tree) serve this upload?
+static bool super_compact_eligible(const sr2_ctx* ctx, int Gb, int S, int W) {
+    const char* unfused = getenv("SR2_SUPERDTL_UNFUSED");
+    const char* wide = getenv("SR2_SUPERDTL_FUSED_WIDE");
+    if ((unfused && unfused[0] == '1') || (wide && wide[0] == '1')) return false;
+    return S <= 127 && Gb >= 2 && Gb <= 254 && (size_t)fused_layout(Gb, S, W).bytes <= ctx->smem_optin;
+}
+static bool super_compact_table_fits(const sr2_ctx* ctx, int64_t n_slots) {   // 32-bit cell offsets in the kernel
+    return n_slots * 2 * (int64_t)ctx->pitch < ((int64_t)1 << 31);
+}
+
+// The resolved trees of a shared-row upload as arrays in global memory (child ids, table row, dag id,
+// preorder position, instance of every node) plus the per-(node, root) buffers of the unfused decode.
+// Only built when something reads them: the general fused kernel, the unfused kernels, per-node results.
+static int super_materialise_trees(sr2_ctx* ctx, SuperProblem* p) {
+    if (p->trees_ready) return SR2_OK;
+    const int S = ctx->S, W = p->W, Gb = p->Gb;
+    const int64_t B = p->rows.B, N = B * Gb;
+#define SR2_RESERVE(id, field, bytes)                                   \
+    do {                                                                \
+        void* ptr__ = nullptr;                                          \
+        int rc__ = sr2_dev_reserve(ctx, id, (bytes), &ptr__);           \
+        if (rc__) return rc__;                                          \
+        p->field = (decltype(p->field))ptr__;                           \
+    } while (0)
+    SR2_RESERVE(DP_S_LEFT, d_left, (size_t)N * 4);
+    SR2_RESERVE(DP_S_RIGHT, d_right, (size_t)N * 4);
+    SR2_RESERVE(DP_S_NODESLOT, d_node_slot, (size_t)N * 4);
+    SR2_RESERVE(DP_S_NODEDAG, d_node_dag, (size_t)N * 4);
+    SR2_RESERVE(DP_S_NODEPRE, d_node_pre, (size_t)N * 4);
+    SR2_RESERVE(DP_S_NODEINST, d_node_inst, (size_t)N * 4);
+    SR2_RESERVE(DP_S_DEC, d_dec, (size_t)N * S * 2);
+    SR2_RESERVE(DP_S_ANC, d_anc, (size_t)N * S * 2);
+    SR2_RESERVE(DP_S_TAU, d_tau, (size_t)N * W * 32 * 4);
+    SR2_RESERVE(DP_S_TAUMIN, d_taumin, (size_t)N * 4);
+    SR2_RESERVE(DP_S_COST, d_cost, (size_t)B * S * 4);
+    SR2_RESERVE(DP_S_MAP, d_map, (size_t)N * 4);
+    SR2_RESERVE(DP_S_KIND, d_kind, (size_t)N * 4);
+    SR2_RESERVE(DP_S_SYN, d_syn, (size_t)N * W * 4);
+#undef SR2_RESERVE
+    if (B > 0)
+        resolve_unrank_kernel<<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(
+            p->plan_store->plan, B, p->d_left, p->d_right, p->d_node_slot, p->d_node_dag, p->d_node_pre, p->d_node_inst);
+    SR2_CUDA(ctx, cudaGetLastError());
+    p->trees_ready = true;
+    return SR2_OK;
+}
+
 // Shared-row upload (SharedPlan, sr2_internal.cuh): plan arrays to the device, resolved trees by
 // resolve_unrank_kernel.  Replaces the per-resolution host unranking + bucketing of
 // sr2_resolutions_upload; results are read through the same calls as a plain batch.
@@ -1344,39 +1481,41 @@ int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_w
     p->rows.B = (int32_t)B;
     p->rows.N = N;
     p->rows.R = NS;
-    p->rows.node_off.resize(B + 1);
-    for (int64_t i = 0; i <= B; ++i) p->rows.node_off[i] = i * Gb;
+    p->rows.node_off.clear();   // uniform trees: instance i starts at node i * Gb (sr2_superdtl_result_one)
     p->rows.max_nodes = Gb;
 
-    // two slabs of plan arrays
-    std::vector<int32_t> h32;
-    std::vector<int64_t> h64;
-    auto add32 = [&](const std::vector<int32_t>& v) {
-        size_t at = h32.size();
-        h32.insert(h32.end(), v.begin(), v.end());
+    // two device slabs of plan arrays; every array is copied to its place on its own (no packing into a
+    // temporary: for the 893,025-resolution range packing 25 MB took longer than the solve)
+    size_t n32 = 0, n64 = 0;
+    auto place32 = [&](const std::vector<int32_t>& v) {
+        size_t at = n32;
+        n32 += (v.size() + 3) & ~(size_t)3;
         return at;
     };
-    auto add64 = [&](const std::vector<int64_t>& v) {
-        size_t at = h64.size();
-        h64.insert(h64.end(), v.begin(), v.end());
+    auto place64 = [&](const std::vector<int64_t>& v) {
+        size_t at = n64;
+        n64 += (v.size() + 1) & ~(size_t)1;
         return at;
     };
-    size_t o_arity = add32(plan.arity), o_base = add32(plan.base), o_choff = add32(plan.child_off),
-           o_chof = add32(plan.child_of), o_arroff = add32(plan.arr_off), o_arr = add32(plan.arr),
-           o_perm = add32(plan.perm), o_scl = add32(plan.slot_cl), o_scr = add32(plan.slot_cr),
-           o_dl = add32(plan.dag_left), o_dr = add32(plan.dag_right);
-    size_t o_ways = add64(plan.ways), o_stride = add64(plan.stride), o_cnt = add64(plan.cnt),
-           o_vf = add64(plan.var_first), o_rb = add64(plan.raw_base), o_noff = add64(p->rows.node_off);
-
+    const size_t o_arity = place32(plan.arity), o_base = place32(plan.base), o_choff = place32(plan.child_off),
+                 o_chof = place32(plan.child_of), o_arroff = place32(plan.arr_off), o_arr = place32(plan.arr),
+                 o_perm = place32(plan.perm), o_scl = place32(plan.slot_cl), o_scr = place32(plan.slot_cr),
+                 o_dl = place32(plan.dag_left), o_dr = place32(plan.dag_right), o_apo = place32(plan.arr_pre_off),
+                 o_ap = place32(plan.arr_pre), o_par = place32(plan.parent), o_cpos = place32(plan.child_pos);
+    const size_t o_ways = place64(plan.ways), o_stride = place64(plan.stride), o_cnt = place64(plan.cnt),
+                 o_vf = place64(plan.var_first), o_rb = place64(plan.raw_base);
+    const size_t o_noff = n64;       // node offsets: i * Gb, written by a kernel
+    n64 += (size_t)B + 2;
     size_t free_b = 0;
     {
         int rc_mem = sr2_mem_free(ctx, &free_b);
         if (rc_mem) return rc_mem;
     }
     for (int id = DP_S_LEFT; id < DP_COUNT; ++id) free_b += sr2_dev_pooled(ctx, id);
-    size_t need = (size_t)N * (4 * 8 + (size_t)W * 4 + (size_t)W * 128 + (size_t)S * 4) + (size_t)D * W * 4 * 5 +
-                  (size_t)NS * ((size_t)ctx->pitch * 24 + 8) + (size_t)B * ((size_t)S * 4 + 16) + h32.size() * 4 +
-                  h64.size() * 8 + (64u << 20);
+    const bool compact = super_compact_eligible(ctx, Gb, S, W) && super_compact_table_fits(ctx, NS);
+    size_t need = (compact ? 0 : (size_t)N * (4 * 8 + (size_t)W * 4 + (size_t)W * 128 + (size_t)S * 4)) + (size_t)D * W * 4 * 5 +
+                  (size_t)NS * ((size_t)ctx->pitch * 24 + 8) + (size_t)B * ((size_t)S * 4 + 16) + n32 * 4 +
+                  n64 * 8 + (64u << 20);
     if (free_b < need)
         return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_resolutions_upload: range does not fit in device memory");
     size_t dw = (size_t)D * W;
@@ -1391,17 +1530,11 @@ int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_w
     int64_t* d64 = nullptr;
     {
         void* ptr = nullptr;
-        if ((rc = sr2_dev_reserve(ctx, DP_S_PLAN32, (h32.size() + NS) * 4, &ptr))) return rc;
+        if ((rc = sr2_dev_reserve(ctx, DP_S_PLAN32, (n32 + NS) * 4, &ptr))) return rc;
         d32 = (int32_t*)ptr;
-        if ((rc = sr2_dev_reserve(ctx, DP_S_PLAN64, h64.size() * 8, &ptr))) return rc;
+        if ((rc = sr2_dev_reserve(ctx, DP_S_PLAN64, n64 * 8, &ptr))) return rc;
         d64 = (int64_t*)ptr;
     }
-    SR2_RESERVE(DP_S_LEFT, d_left, (size_t)N * 4);
-    SR2_RESERVE(DP_S_RIGHT, d_right, (size_t)N * 4);
-    SR2_RESERVE(DP_S_NODESLOT, d_node_slot, (size_t)N * 4);
-    SR2_RESERVE(DP_S_NODEDAG, d_node_dag, (size_t)N * 4);
-    SR2_RESERVE(DP_S_NODEPRE, d_node_pre, (size_t)N * 4);
-    SR2_RESERVE(DP_S_NODEINST, d_node_inst, (size_t)N * 4);
     SR2_RESERVE(DP_S_BITS, d_bits, dw * 4);
     SR2_RESERVE(DP_S_PRESENT, d_present, dw * 4);
     SR2_RESERVE(DP_S_OUTSIDE, d_outside, dw * 4);
@@ -1411,21 +1544,28 @@ int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_w
     SR2_RESERVE(DP_S_T, d_T, (size_t)std::max<int64_t>(NS, 1) * 2 * ctx->pitch * 4);
     SR2_RESERVE(DP_S_TAG, d_tag, (size_t)std::max<int64_t>(NS, 1) * 2 * ctx->pitch * 4);
     SR2_RESERVE(DP_S_EV, d_ev, (size_t)std::max<int64_t>(NS, 1) * 2 * ctx->pitch * 4);
-    SR2_RESERVE(DP_S_DEC, d_dec, (size_t)N * S * 2);
-    SR2_RESERVE(DP_S_ANC, d_anc, (size_t)N * S * 2);
-    SR2_RESERVE(DP_S_TAU, d_tau, (size_t)N * W * 32 * 4);
-    SR2_RESERVE(DP_S_TAUMIN, d_taumin, (size_t)N * 4);
-    SR2_RESERVE(DP_S_COST, d_cost, (size_t)B * S * 4);
     SR2_RESERVE(DP_S_MINCOST, d_min_cost, (size_t)B * 4);
     SR2_RESERVE(DP_S_ROOTSP, d_root_species, (size_t)B * 4);
-    SR2_RESERVE(DP_S_MAP, d_map, (size_t)N * 4);
-    SR2_RESERVE(DP_S_KIND, d_kind, (size_t)N * 4);
-    SR2_RESERVE(DP_S_SYN, d_syn, (size_t)N * W * 4);
     SR2_RESERVE(DP_S_BEST, d_best, 8);
 #undef SR2_RESERVE
     cudaStream_t st = ctx->stream;
-    SR2_CUDA(ctx, cudaMemcpyAsync(d32, h32.data(), h32.size() * 4, cudaMemcpyHostToDevice, st));
-    SR2_CUDA(ctx, cudaMemcpyAsync(d64, h64.data(), h64.size() * 8, cudaMemcpyHostToDevice, st));
+    const double t_packed = snow_ms();
+    {
+        const std::pair<size_t, const std::vector<int32_t>*> a32[] = {
+            {o_arity, &plan.arity}, {o_base, &plan.base},   {o_choff, &plan.child_off}, {o_chof, &plan.child_of},
+            {o_arroff, &plan.arr_off}, {o_arr, &plan.arr}, {o_perm, &plan.perm},       {o_scl, &plan.slot_cl},
+            {o_scr, &plan.slot_cr},  {o_dl, &plan.dag_left}, {o_dr, &plan.dag_right}, {o_apo, &plan.arr_pre_off},
+            {o_ap, &plan.arr_pre},   {o_par, &plan.parent},  {o_cpos, &plan.child_pos}};
+        for (const auto& a : a32)
+            if (!a.second->empty())
+                SR2_CUDA(ctx, cudaMemcpyAsync(d32 + a.first, a.second->data(), a.second->size() * 4, cudaMemcpyHostToDevice, st));
+        const std::pair<size_t, const std::vector<int64_t>*> a64[] = {
+            {o_ways, &plan.ways}, {o_stride, &plan.stride}, {o_cnt, &plan.cnt}, {o_vf, &plan.var_first}, {o_rb, &plan.raw_base}};
+        for (const auto& a : a64)
+            if (!a.second->empty())
+                SR2_CUDA(ctx, cudaMemcpyAsync(d64 + a.first, a.second->data(), a.second->size() * 8, cudaMemcpyHostToDevice, st));
+        iota64_kernel<<<(unsigned)((B + 1 + 255) / 256), 256, 0, st>>>(d64 + o_noff, B + 1, (int64_t)Gb);
+    }
     // leaf bits of the dag: the leaves of a resolved tree sit at the same ids in every resolution
     SR2_CUDA(ctx, cudaMemsetAsync(p->d_bits, 0, std::max<size_t>(dw * 4, 4), st));
     SR2_CUDA(ctx, cudaMemcpyAsync(p->d_bits, plan.leaf_bits.data(), (size_t)Gb * W * 4, cudaMemcpyHostToDevice, st));
@@ -1433,7 +1573,7 @@ int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_w
     p->d_slot_cr = d32 + o_scr;
     p->d_dag_left = d32 + o_dl;
     p->d_dag_right = d32 + o_dr;
-    p->d_slot_node = d32 + h32.size();
+    p->d_slot_node = d32 + n32;
     p->d_node_off = d64 + o_noff;
     if (NS > 0) iota_kernel<<<(unsigned)((NS + 255) / 256), 256, 0, st>>>(p->d_slot_node, NS, Gb);
     DevPlan P;
@@ -1447,18 +1587,28 @@ int sr2_superdtl_upload_shared(sr2_ctx* ctx, const SharedPlan& plan, int32_t n_w
     P.arr_off = d32 + o_arroff;
     P.arr = d32 + o_arr;
     P.perm = d32 + o_perm;
+    P.arr_pre_off = d32 + o_apo;
+    P.arr_pre = d32 + o_ap;
+    P.parent = d32 + o_par;
+    P.child_pos = d32 + o_cpos;
     P.ways = d64 + o_ways;
     P.stride = d64 + o_stride;
     P.cnt = d64 + o_cnt;
     P.var_first = d64 + o_vf;
     P.raw_base = d64 + o_rb;
-    if (B > 0)
-        resolve_unrank_kernel<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(P, B, p->d_left, p->d_right, p->d_node_slot,
-                                                                        p->d_node_dag, p->d_node_pre,
-                                                                        p->d_node_inst);
+    p->plan_store = new DevPlanStore{P};
+    p->trees_ready = false;
+    if (!compact) {   // the kernels that will run read the resolved trees from global memory
+        int rc_trees = super_materialise_trees(ctx, p);
+        if (rc_trees) return rc_trees;
+    }
     SR2_CUDA(ctx, cudaGetLastError());
-    SR2_CUDA(ctx, cudaStreamSynchronize(st));  // h32 / h64 / plan.leaf_bits are released on return
+    const double t_enqueued = snow_ms();
+    SR2_CUDA(ctx, cudaStreamSynchronize(st));  // the plan's vectors may be rewritten once this returns
     ctx->timing.upload_ms = (float)(snow_ms() - t0);
+    if (getenv("SR2_TRACE"))
+        fprintf(stderr, "[sr2] shared upload: packed + reserved %.2f ms, enqueued %.2f ms, device done %.2f ms (%zu + %zu plan bytes)\n",
+                t_packed - t0, t_enqueued - t0, snow_ms() - t0, n32 * 4, n64 * 8);
     return SR2_OK;
 }
 
@@ -1530,6 +1680,10 @@ static inline unsigned grid_for(int64_t n, int block) { return (unsigned)std::ma
 // and the mapping / kind / synteny of every node of every instance.  Runs in the solve when the
 // fused kernel does not fit, and on demand when a caller asks for per-node results.
 static int super_decode_shared(sr2_ctx* ctx, SuperProblem* p, int* n_launch) {
+    {
+        int rc_trees = super_materialise_trees(ctx, p);
+        if (rc_trees) return rc_trees;
+    }
     cudaStream_t st = ctx->stream;
     const int W = p->W, S = ctx->S, Gb = p->Gb;
     const int64_t N = p->rows.N;
@@ -1622,19 +1776,23 @@ static int super_solve_shared(sr2_ctx* ctx, SuperProblem* p) {
         // mappings / syntenies of every instance are then produced on demand (super_materialise)
         const size_t fused_smem = ((size_t)Gb * W * 35 + Gb * 5) * 4 + (size_t)Gb * S * 4;
         const char* unfused = getenv("SR2_SUPERDTL_UNFUSED");
-        p->fused = !(unfused && unfused[0] == '1') && S <= 1024 && fused_smem <= ctx->smem_optin;
-        const char* wide = getenv("SR2_SUPERDTL_FUSED_WIDE");   // cross-check: the general fused kernel
+        const bool compact = super_compact_eligible(ctx, Gb, S, W) &&   // (SR2_SUPERDTL_FUSED_WIDE=1: the general kernel)
+                             super_compact_table_fits(ctx, NS);
+        p->fused = compact || (!(unfused && unfused[0] == '1') && S <= 1024 && fused_smem <= ctx->smem_optin);
         const FusedLayout lay = fused_layout(Gb, S, W);
-        if (p->fused && !(wide && wide[0] == '1') && S <= 127 && Gb >= 2 && Gb <= 254 &&
-            (size_t)lay.bytes <= ctx->smem_optin) {
-            SR2_CUDA(ctx, cudaFuncSetAttribute(sfused_compact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               lay.bytes));
-            sfused_compact_kernel<<<B, (S + 31) / 32 * 32, lay.bytes, st>>>(
-                ctx->dsp, Gb, p->d_left, p->d_right, p->d_node_slot, p->d_node_dag, p->d_node_pre, p->d_tag, p->d_ev,
-                W, p->d_gain, p->d_L, cs, p->index_base, p->d_min_cost, p->d_root_species, p->d_best);
+        if (compact) {
+            auto kernel = W == 1 ? sfused_compact_kernel<1> : sfused_compact_kernel<0>;
+            SR2_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lay.bytes));
+            const bool in_memory = p->trees_ready;   // someone asked for per-node results earlier
+            kernel<<<B, (S + 31) / 32 * 32, lay.bytes, st>>>(
+                ctx->dsp, p->plan_store->plan, Gb, in_memory ? p->d_left : nullptr, p->d_right, p->d_node_slot,
+                p->d_node_dag, p->d_node_pre, p->d_tag, p->d_ev, W, p->d_gain, p->d_L, cs, p->index_base,
+                p->d_min_cost, p->d_root_species, p->d_best);
             n_launch += 1;
             p->materialised = false;
         } else if (p->fused) {
+            int rc_trees = super_materialise_trees(ctx, p);
+            if (rc_trees) return rc_trees;
             SR2_CUDA(ctx, cudaFuncSetAttribute(sfused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)fused_smem));
             sfused_kernel<<<B, (S + 31) / 32 * 32, fused_smem, st>>>(
@@ -1838,7 +1996,8 @@ extern "C" int sr2_superdtl_result_one(sr2_ctx* ctx, int32_t instance, int32_t* 
         if (rc) return rc;
     }
     cudaStream_t st = ctx->stream;
-    size_t off = p->rows.node_off[instance], G = p->rows.node_off[instance + 1] - off;
+    size_t off = p->shared ? (size_t)instance * p->Gb : (size_t)p->rows.node_off[instance];
+    size_t G = p->shared ? (size_t)p->Gb : (size_t)p->rows.node_off[instance + 1] - off;
     if (out_map_species)
         SR2_CUDA(ctx, cudaMemcpyAsync(out_map_species, p->d_map + off, G * 4, cudaMemcpyDeviceToHost, st));
     if (out_map_kind) SR2_CUDA(ctx, cudaMemcpyAsync(out_map_kind, p->d_kind + off, G * 4, cudaMemcpyDeviceToHost, st));

@@ -324,8 +324,9 @@ def test_fused_decode_kernels_agree_with_the_unfused_path(ctx, monkeypatch, wide
     resolution, also with costs that make cost() re-classify duplications as speciations."""
     if wide:
         monkeypatch.setenv("SR2_SUPERDTL_FUSED_WIDE", "1")
-    for seed, costs in [(5, (0, 1, 1, 1, 1)), (6, (3, 1, 2, 1, 2)), (7, (2, 0, 1, 0, 3)), (8, (1, 1, 0, 2, 0))]:
-        data = synth.make_polytomy_input(9, (4, 4), 2, 7, seed=seed, costs=costs)
+    for seed, costs, families in [(5, (0, 1, 1, 1, 1), 7), (6, (3, 1, 2, 1, 2), 7), (7, (2, 0, 1, 0, 3), 7),
+                                  (8, (1, 1, 0, 2, 0), 7), (9, (0, 1, 1, 1, 1), 40)]:   # 40 families: two synteny words
+        data = synth.make_polytomy_input(9, (4, 4), 2, families, seed=seed, costs=costs)
         srec_input, species, poly, bits, cvec = _poly_setup(ctx, data)
         total = srec_input.count_resolutions()
         outs = []
