@@ -49,9 +49,10 @@ WORKLOADS = {
     "dtl_batch_small": (50, 80, 512, 2000),
 }
 BYTES_PER_CELL = 20  # 2 x 4 B child reads + 4 B value + 8 B traceback
-# DRAM bytes per cell of the rows the wave kernels materialise, from the ncu --set full captures
-# under profiles/ (dram__bytes_read.sum + dram__bytes_write.sum per launch / cells of the launch)
-DRAM_B_PER_CELL_SPARSE, DRAM_B_PER_CELL_DENSE, SPARSE_SHARE = 7.4, 12.1, 0.74
+# DRAM bytes per evaluated cell, measured: ncu dram__bytes_read.sum + dram__bytes_write.sum of EVERY launch of
+# one step of the headline workload (profiles/r4g_dram_per_launch_config2.csv: 17.59 GB per step, 16.50 GB of
+# it in the 40 wave launches) / cells of the rows that are materialised (1,325,775,654 on rank 0's batch)
+DRAM_B_PER_CELL_STEP, DRAM_B_PER_CELL_WAVES = 17.59e9 / 1325775654, 16.50e9 / 1325775654
 
 
 def measured_peak():
@@ -605,8 +606,7 @@ def main():
         n_cherry, n_other = int(cherry.sum()), int(internal.sum() - cherry.sum())
         cells_evaluated = n_other * batch.n_species
         achieved_evaluated = cells_evaluated * args.steps * BYTES_PER_CELL / (wave_ms * 1e-3) / 1e9
-        dram_bytes_per_step = cells_evaluated * (SPARSE_SHARE * DRAM_B_PER_CELL_SPARSE +
-                                                 (1 - SPARSE_SHARE) * DRAM_B_PER_CELL_DENSE)
+        dram_bytes_per_step = cells_evaluated * DRAM_B_PER_CELL_WAVES     # the wave launches
         dram_gbs = dram_bytes_per_step * args.steps / (wave_ms * 1e-3) / 1e9
         line = {
             "metric": "dp_cells_per_s",
@@ -654,10 +654,11 @@ def main():
                          "frac": achieved / peak, "traffic": dram_bytes_per_step / waves_per_step,
                          "frac_evaluated": achieved_evaluated / peak,
                          "dram_frac": dram_gbs / peak,
+                         "dram_bytes_per_step_all_launches": cells_evaluated * DRAM_B_PER_CELL_STEP,
                          "reading": "frac: all cells x 20 B (the reference-equivalent figure, SURVEY 8d); "
                                     "frac_evaluated: only cells of rows that are materialised (cherry rows, a third of "
                                     "the rows, are evaluated by their readers and never stored); dram_frac: bytes that "
-                                    "really cross the HBM interface (ncu) / time / peak -- the kernels are bound by "
+                                    "really cross the HBM interface (ncu, every launch of a step) / time / peak -- the kernels are bound by "
                                     "instruction latency and issue slots, not by HBM",
                          "kernel": "dtl wave kernels: dtl_wave_sparse_kernel<38|57> (rows with <= 57 root-path species, 55 % "
                                    "of the step), dtl_wave_flat2_kernel (the other rows, 32 %, and the chained launch "
@@ -668,9 +669,10 @@ def main():
                          "wave_launches_per_step": waves_per_step,
                          "wave_ms_per_step": wave_ms / args.steps,
                          "cells_evaluated_per_step": cells_evaluated, "cherry_rows": n_cherry,
-                         "traffic_source": "bytes per wave launch (average over the step's launches) from "
-                                           "ncu dram__bytes_read+write per row, profiles/r2o_sparse44_ncu_details.csv, "
-                                           "r1y_flat2_ncu_details.csv / r2m_flat2_ncu_details.csv"},
+                         "traffic_source": "bytes per wave launch (average over the step's 40 wave launches) from ncu "
+                                           "dram__bytes_read.sum + dram__bytes_write.sum of every launch of one step, "
+                                           "profiles/r4g_dram_per_launch_config2.csv (cold caches, launches serialised), "
+                                           "scaled by the cells this batch evaluates"},
             "checksum_min_costs": checksum,
         }
     cpu_legs = []   # every CPU leg runs after ALL GPU timing: a busy OpenMP team of another runtime in the

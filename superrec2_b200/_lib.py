@@ -289,7 +289,7 @@ class Context:
 
     def superdtl_result_one(self, instance: int):
         _, _, words, node_off = self._sbatch
-        n_nodes = int(node_off[instance + 1] - node_off[instance])
+        n_nodes = node_off if isinstance(node_off, int) else int(node_off[instance + 1] - node_off[instance])
         mapping = np.empty(n_nodes, np.int32)
         kind = np.empty(n_nodes, np.int32)
         syn = np.empty((n_nodes, words), np.uint32)
@@ -321,8 +321,8 @@ class Context:
         leaf_species, costs = i32(leaf_species), i32(costs)
         leaf_bits = np.ascontiguousarray(leaf_bits, dtype=np.uint32).reshape(len(leaf_species), -1)
         _, binary_nodes = resolutions_count(child_off, child_idx)
-        node_off = np.arange(count + 1, dtype=np.int64) * binary_nodes
-        self._sbatch = (count, int(node_off[-1]), leaf_bits.shape[1], node_off)
+        # uniform trees: instance i starts at node i * binary_nodes (no offsets array for a million instances)
+        self._sbatch = (count, count * binary_nodes, leaf_bits.shape[1], binary_nodes)
         self._check(self._lib.sr2_resolutions_upload(
             self._handle, len(child_off) - 1, p32(child_off), p32(child_idx), p32(leaf_species),
             leaf_bits.shape[1], leaf_bits.ctypes.data_as(_U32P), p32(costs), first, count, flags))

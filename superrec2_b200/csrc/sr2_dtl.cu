@@ -24,12 +24,13 @@
 // costs that fit 32-bit keys); DESIGN.md section 4 has the measurements behind each piece:
 //   wave 1 (cherries)      not launched: readers evaluate the closed form (cherry_form)
 //   side stream            dtl_partition_kernel / dtl_rowmask_kernel: root-path bit set of every row,
-//                          per wave the lists of rows with <= 48 / <= 64 path species and of the others
-//   big waves              dtl_wave_sparse_kernel<48>, <64> (4 lanes per row, path species only) and
+//                          per wave the lists of rows with <= 38 / <= 57 path species and of the others
+//   big waves              dtl_wave_sparse_kernel<38>, <57> (4 lanes per row, path species only) and
 //                          dtl_wave_flat2_kernel<NS, false> (a warp per dense row) on two streams
 //   small top waves        dtl_wave_flat2_kernel<NS, true>: one launch, rows chained by done flags
 //   selection + traceback  dtl_select_trace_kernel: one CTA per tree
-// Everything else (dtl_wave_kernel, dtl_wave_flat_kernel, dtl_cherry_*_kernel, dtl_select_kernel,
+// Everything else (dtl_wave_kernel -- a warp or a CTA per row with 64-bit keys, BASELINE config #3 runs on
+// it --, dtl_wave_inplace_kernel, dtl_wave_flat_kernel, dtl_cherry_*_kernel, dtl_select_kernel,
 // dtl_traceback_kernel, dtl_decoded_cost_kernel) is the general path: large species trees, large
 // costs, tables kept for the caller, charged speciations, cross-checks in the tests.
 #include <algorithm>
