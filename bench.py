@@ -667,6 +667,9 @@ def main():
                          "bytes_per_cell": BYTES_PER_CELL,
                          "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL / waves_per_step,
                          "wave_launches_per_step": waves_per_step,
+                         "launch_definition": "a launch = one wave (one height of the whole batch): up to three concurrent "
+                                              "kernel launches (two sparse tiers + the dense rows), 40 kernel launches in "
+                                              "14 waves for this workload; achieved and traffic are per wave",
                          "wave_ms_per_step": wave_ms / args.steps,
                          "cells_evaluated_per_step": cells_evaluated, "cherry_rows": n_cherry,
                          "traffic_source": "bytes per wave launch (average over the step's 40 wave launches) from ncu "
