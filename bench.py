@@ -647,7 +647,8 @@ def main():
                                      "arrays out: the library stages through its own pinned pools",
                     "python_entry_point_note": "reconcile_thl_batch (tree objects in, ReconciliationOutput objects "
                                                "out) additionally flattens and rebuilds ~1e7 Python tree nodes, "
-                                               "which takes seconds; services that care call the flat-array API"},
+                                               "which takes seconds; callers that keep trees as arrays use "
+                                               "superrec2_b200.compute.reconciliation.reconcile_thl_flat"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -337,6 +337,27 @@ def test_fused_decode_kernels_agree_with_the_unfused_path(ctx, monkeypatch, wide
             outs.append((ctx.superdtl_results(costs_only=True), ctx.superdtl_best()))
         assert (outs[0][0][0] == outs[1][0][0]).all() and (outs[0][0][1] == outs[1][0][1]).all()
         assert outs[0][1] == outs[1][1]
+        # per-node results on demand materialise the resolved trees; a second solve then reads them from memory
+        # instead of unranking inside the kernel and must not change anything
+        monkeypatch.setenv("SR2_SUPERDTL_UNFUSED", "0")
+        ctx.resolutions_upload(poly.child_off, poly.child_idx, poly.leaf_species, bits, cvec, 0, total)
+        ctx.superdtl_solve()
+        first = (ctx.superdtl_results(), ctx.superdtl_best())
+        ctx.superdtl_solve()
+        again = (ctx.superdtl_results(), ctx.superdtl_best())
+        assert first[1] == again[1] == outs[0][1]
+        for a, b in zip(first[0], again[0]):
+            assert (a == b).all()
+        # the mapping / kinds / syntenies of every instance against the oracle on a few resolutions
+        from oracle.fullsize import ResolutionSet
+        res = ResolutionSet(data)
+        for index in (0, total // 3, total - 1):
+            node_off, left, right, leaf, rbits = res.batch(index, 1)
+            ref = oracle.superdtl(*res.species_args, left, right, leaf, rbits, res.costs, tables=False)
+            lo, hi = index * res.nodes_per_tree, (index + 1) * res.nodes_per_tree
+            assert first[0][0][index] == ref["min_cost"] and first[0][1][index] == ref["root_species"]
+            assert (first[0][2][lo:hi] == ref["mapping"]).all() and (first[0][3][lo:hi] == ref["kind"]).all()
+            assert (first[0][4][lo:hi] == ref["syn"]).all()
 
 
 def test_base_uspfs_all_solutions_against_the_reference(golden):
