@@ -373,3 +373,34 @@ def test_base_uspfs_all_solutions_against_the_reference(golden):
         assert sorted(json.dumps(out.to_dict(), sort_keys=True) for out in results) == fixture["solutions"]
         if results:
             assert {out.cost() for out in results} == {fixture["min_cost"]}
+
+
+def test_every_resolution_of_random_polytomies_against_the_oracle(ctx, golden):
+    """Nested polytomies, polytomies at the root, polytomies whose children are leaves (the 60 multifurcating
+    fixtures plus larger random trees): EVERY resolution's decoded minimum cost and root -- the device-side
+    unranking with its per-arrangement preorder tables, shared rows, Hazard-A time stamps -- against the oracle
+    run on the host-side unranking of the same resolution number."""
+    import random
+    from oracle.fullsize import ResolutionSet
+    from oracle.make_golden_inputs import random_polytomy_instance
+    inputs = [fixture["input"] for fixture in golden("superdtl_poly.json.gz")]
+    rng = random.Random(4242)
+    inputs += [random_polytomy_instance(rng, n_species=rng.randint(3, 9), n_objects=rng.randint(6, 11),
+                                        families=rng.randint(2, 9)) for _ in range(25)]
+    checked = 0
+    for data in inputs:
+        res = ResolutionSet(data)
+        if not 1 < res.total <= 20000:
+            continue
+        ctx.set_species(*res.species_args)
+        ctx.resolutions_upload(res.poly.child_off, res.poly.child_idx, res.poly.leaf_species, res.bits, res.costs,
+                               0, res.total)
+        ctx.superdtl_solve()
+        min_cost, root = ctx.superdtl_results(costs_only=True)
+        step = max(1, res.total // 400)            # every resolution of small inputs, a stride of large ones
+        picks = list(range(0, res.total, step))
+        for index in picks:
+            ref_cost, ref_root = oracle.superdtl_batch(*res.species_args, *res.batch(index, 1), res.costs)
+            assert (min_cost[index], root[index]) == (ref_cost[0], ref_root[0]), (res.total, index)
+        checked += len(picks)
+    assert checked > 3000
