@@ -1106,7 +1106,7 @@ sfused_compact_kernel(DevSpecies sp, DevPlan plan, int Gb, const int32_t* __rest
     uint8_t* sFirst = bytes + lay.first;
     uint8_t* sInt = bytes + lay.inner;
     __shared__ unsigned long long warp_best[4];
-    __shared__ int s_n_int;
+    __shared__ int s_n_int, s_any_merge;
 
     // ---- the tree, and "nothing merged yet" ---------------------------------------------------
     for (int i = threadIdx.x; i < (lay.inner - lay.owner) / 4; i += blockDim.x)
@@ -1158,14 +1158,22 @@ sfused_compact_kernel(DevSpecies sp, DevPlan plan, int Gb, const int32_t* __rest
             if (inner) sInt[count + __popc(m & ((1u << threadIdx.x) - 1))] = (uint8_t)u;
             count += __popc(m);
         }
-        if (threadIdx.x == 0) s_n_int = count;
+        if (threadIdx.x == 0) {
+            s_n_int = count;
+            s_any_merge = 0;
+        }
     }
     __syncthreads();
     const int n_int = s_n_int;
 
     // ---- decode from root species k (thread k), event terms added on the way -------------------
+    // Next to the event terms the decode adds the segmental-loss terms under the assumption that NO set of
+    // this tree is ever polluted (no INHERIT node with a non-empty gain set in any root's decode): then every
+    // label is the clean LCA set of its owner and needs no time stamps.  That is the common case (families
+    // shared by most leaves are gained at the root, which is never INHERIT: config #5 has no pollution at
+    // all); the exact passes below only run for trees where some thread merged something.
     bool ok = false;
-    int total = 0;
+    int total = 0, clean_labels = 0;
     if (k < S) {
         ok = Gb == 1 ? false : tags[((size_t)sSlot[0] * 2 + 0) * sp.pitch + k] != SR2_NO_TAG;  // kind LCA (:487)
         if (ok) {
@@ -1186,10 +1194,26 @@ sfused_compact_kernel(DevSpecies sp, DevPlan plan, int Gb, const int32_t* __rest
                 ent[r * S + k] = (uint16_t)((((er & 1) ? own : (unsigned)r) << 8) | er);
                 ent[u * S + k] = (uint16_t)((own << 8) | ((ev & 3) << 2) | ((el & 1) << 1) | (er & 1));
                 total += (int)(ev >> 2);
+                {   // clean labels: only LCA-kind children are compared (see the header of this kernel)
+                    const int cls = (int)(ev & 3);
+                    bool need_l = !(el & 1) && cls != EV_CLASS_HGT_R, need_r = !(er & 1) && cls != EV_CLASS_HGT_L;
+                    if (cls == EV_CLASS_DUP && ((el | er) & 1)) need_l = need_r = false;
+                    if (need_l || need_r) {
+                        bool in_l = true, in_r = true;
+                        for (int w = 0; w < W; ++w) {
+                            const uint32_t mine = sLca[own * W + w];
+                            if (need_l) in_l &= (mine & ~sLca[l * W + w]) == 0;
+                            if (need_r) in_r &= (mine & ~sLca[r * W + w]) == 0;
+                        }
+                        const int lc = need_l && !in_l ? cs.sloss : 0, rc = need_r && !in_r ? cs.sloss : 0;
+                        clean_labels += cls == EV_CLASS_DUP ? min(lc, rc) : lc + rc;
+                    }
+                }
                 // kind INHERIT: the child's gains go, in place, into the set of its owner (:390)
                 if ((el | er) & 1) {
                     for (int w = 0; w < W; ++w) {
                         uint32_t g = ((el & 1) ? sGain[l * W + w] : 0u) | ((er & 1) ? sGain[r * W + w] : 0u);
+                        if (g) s_any_merge = 1;
                         while (g) {
                             const int f = __ffs(g) - 1;
                             g &= g - 1;
@@ -1202,8 +1226,9 @@ sfused_compact_kernel(DevSpecies sp, DevPlan plan, int Gb, const int32_t* __rest
         }
     }
     __syncthreads();
+    const bool polluted = s_any_merge != 0;   // uniform: read after the barrier
     // ---- first root that merged family f into the set of node a ---------------------------------
-    for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    for (int f = threadIdx.x; f < F && polluted; f += blockDim.x) {
         for (int kk = 0; kk < S; ++kk) {
             const int a = sOwner[f * S + kk];
             if (a != 0xff && sFirst[a * F + f] == 0xff) {
@@ -1212,10 +1237,11 @@ sfused_compact_kernel(DevSpecies sp, DevPlan plan, int Gb, const int32_t* __rest
             }
         }
     }
-    __syncthreads();
+    if (polluted) __syncthreads();
     // ---- segmental-loss terms of cost() on the labels the reference would report ----------------
     u64 key = SR2_KEY_NONE;
-    if (ok) {
+    if (ok && !polluted) key = ((u64)(unsigned)(total + clean_labels) << 32) | (unsigned)k;
+    if (ok && polluted) {
         auto word = [&](int a, int w, int pre_n) {
             uint32_t bits = sLca[a * W + w];
             uint32_t cand = sPmask[a * W + w] & ~bits;
