@@ -155,6 +155,7 @@ struct sr2_ctx {
     cudaStream_t fill_stream = nullptr;    // device-side bucketing, second phase (lazy)
     cudaStream_t part_stream[2] = {nullptr, nullptr};  // path sets / row lists of the waves, ahead of the waves
     cudaStream_t dense_stream[2] = {nullptr, nullptr}; // the dense rows of a wave, next to its sparse rows
+    cudaStream_t tier_stream[2] = {nullptr, nullptr};  // the second sparse tier of a wave (SR2_DTL_SPLIT_TIERS)
     std::vector<cudaEvent_t> split_events[2];
     size_t split_used[2] = {0, 0};
     std::vector<cudaEvent_t> part_events[2];           // "lists of wave k are ready", per table set
