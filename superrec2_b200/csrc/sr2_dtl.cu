@@ -192,13 +192,19 @@ __host__ __device__ __forceinline__ size_t dtl_topology_bytes(int S, int D, int 
 // that narrow levels still use the lanes, and nothing in the level loops touches global memory
 // (ncu r3b on the superdtl twin of this kernel: the per-level __ldg of the first form cost more
 // than the arithmetic).
-template <int TPR>
+// CHAIN (one CTA per row only): every wave from the second one on in ONE launch.  CTAs take rows by ticket
+// (row order = height order), a CTA waits until the "done" flags of its two child rows are up, reads them
+// with L2-only loads and raises its own flag behind a fence.  A row can only wait for rows with smaller
+// tickets, which already run, so the launch cannot deadlock; and a row starts as soon as ITS children are
+// done instead of when the whole wave below is (a single instance has a handful of rows per top wave).
+template <int TPR, bool CHAIN = false>
 __global__ void __launch_bounds__(TPR == 32 ? 256 : TPR)
 dtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
                 const int32_t* __restrict__ row_cr, int64_t row_begin, int64_t chunk_row0,
                 int n_rows, int32_t* __restrict__ T, uint32_t* __restrict__ tags, DtlCosts cs,
-                int spad) {
+                int spad, int* __restrict__ chain_sync = nullptr) {
     extern __shared__ u64 smem[];
+    __shared__ int s_ticket;
     const int S = sp.S;
     int group, lane, groups_per_cta;
     if (TPR == 32) {
@@ -216,8 +222,9 @@ dtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
     for (int i = threadIdx.x; i < S; i += blockDim.x) s_meta[i] = __ldg(sp.meta + i);
     for (int i = threadIdx.x; i <= sp.D; i += blockDim.x) s_lvl[i] = __ldg(sp.int_lvl_off + i);
     for (int i = threadIdx.x; i < sp.n_internal; i += blockDim.x) s_int[i] = (uint16_t)__ldg(sp.int_list + i);
+    if (CHAIN && threadIdx.x == 0) s_ticket = atomicAdd(chain_sync, 1);
     __syncthreads();
-    int local = blockIdx.x * groups_per_cta + group;
+    int local = CHAIN ? s_ticket : blockIdx.x * groups_per_cta + group;
     if (local >= n_rows) return;  // uniform per group
     const int64_t gr = row_begin + local;              // global row
     const size_t slot = (size_t)(gr - chunk_row0);     // row inside the chunk's tables
@@ -226,14 +233,30 @@ dtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
     u64* Mr = base + spad;
     const int cl = row_cl[gr], cr = row_cr[gr];
     SR2_DCHECK(cl < (int)slot && cr < (int)slot && cl >= -S && cr >= -S);
+    if (CHAIN) {
+        const int first_slot = (int)(row_begin - chunk_row0);
+        const int c = threadIdx.x == 0 ? cl : cr;
+        if (threadIdx.x < 2 && c >= first_slot) {
+            if (c - first_slot >= local) __trap();   // rows are sorted by height: a child never follows its parent
+            const int* flag = chain_sync + 1 + (c - first_slot);
+            int up;
+            for (unsigned spins = 0;; ++spins) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(up) : "l"(flag) : "memory");
+                if (up) break;
+                if (spins > (1u << 24)) __trap();
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+    }
     const int32_t* __restrict__ Tl = cl >= 0 ? T + (size_t)cl * sp.pitch : nullptr;
     const int32_t* __restrict__ Tr = cr >= 0 ? T + (size_t)cr * sp.pitch : nullptr;
 
-    // stage the two child rows as keys
+    // stage the two child rows as keys (CHAIN: written by other CTAs of this launch, so past L1)
     for (int y = lane; y < S; y += TPR) {
         const int d = (int)(s_meta[y] & 0xffffu);
-        const int vl = Tl ? Tl[y] : (y == -1 - cl ? 0 : SR2_INF);
-        const int vr = Tr ? Tr[y] : (y == -1 - cr ? 0 : SR2_INF);
+        const int vl = Tl ? (CHAIN ? __ldcg(Tl + y) : Tl[y]) : (y == -1 - cl ? 0 : SR2_INF);
+        const int vr = Tr ? (CHAIN ? __ldcg(Tr + y) : Tr[y]) : (y == -1 - cr ? 0 : SR2_INF);
         Ml[y] = key_make(vl, y, d);
         Mr[y] = key_make(vr, y, d);
     }
@@ -281,6 +304,14 @@ dtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl,
                  tag);
         Tout[x] = best;
         Gout[x] = tag;
+    }
+    if (CHAIN) {   // the row is complete: every thread's stores, then the flag
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int* flag = chain_sync + 1 + local;
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+        }
     }
 }
 
@@ -1837,6 +1868,10 @@ static int dtl_configure_waves(sr2_ctx* ctx, DtlProblem* p) {
                                            (int)p->wave_smem));
         SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->wave_smem));
+        SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
+        SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
     }
     return SR2_OK;
 }
@@ -2098,6 +2133,10 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     // the first wave of the chained launch: waves shrink with height, so every wave from the first
     // one below the threshold on is small (H + 1 = no chained launch)
     int h_chain = H + 1;
+    // the generic one-CTA-per-row kernel (large species trees): every wave from the second one on is chained
+    const bool gen_chain = !p->flat2 && !p->flat && p->cta_per_row && !p->wave_inplace && H >= 2 &&
+                           !getenv("SR2_DTL_NO_GENERIC_CHAIN");
+    if (gen_chain) h_chain = 2;
     if (p->flat2 && p->chain_rows > 0)
         for (int h = 2; h <= H; ++h)
             if (c.wave_off[h + 1] - c.wave_off[h] < p->chain_rows) {
@@ -2191,7 +2230,20 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         chain_tail = part_events[events_used];
         SR2_CUDA(ctx, cudaGetLastError());
     }
-    if (h_chain <= H) {
+    if (h_chain <= H && gen_chain) {
+        const int64_t first = c.wave_off[h_chain], n = c.wave_off[H + 1] - first;
+        int* sync = p->d_chain_sync + (size_t)set * (std::max<int64_t>(p->rows.max_chunk_rows, 1) + 1);
+        SR2_CUDA(ctx, cudaMemsetAsync(sync, 0, (size_t)(n + 1) * sizeof(int), st));
+        if (p->wave_threads == 1024)
+            dtl_wave_kernel<1024, true><<<(unsigned)n, 1024, p->wave_smem, st>>>(
+                ctx->dsp, p->rows.row_cl, p->rows.row_cr, first, c.row_begin, (int)n, p->cur_T, p->cur_tag, cs, p->spad, sync);
+        else
+            dtl_wave_kernel<512, true><<<(unsigned)n, 512, p->wave_smem, st>>>(
+                ctx->dsp, p->rows.row_cl, p->rows.row_cr, first, c.row_begin, (int)n, p->cur_T, p->cur_tag, cs, p->spad, sync);
+        SR2_CUDA(ctx, cudaGetLastError());
+        ++p->n_waves;
+        ++p->n_launch;
+    } else if (h_chain <= H) {
         const int64_t first = c.wave_off[h_chain], n = c.wave_off[H + 1] - first;
         int* sync = p->d_chain_sync + (size_t)set * (std::max<int64_t>(p->rows.max_chunk_rows, 1) + 1);
         SR2_CUDA(ctx, cudaMemsetAsync(sync, 0, (size_t)(n + 1) * sizeof(int), st));

@@ -138,7 +138,7 @@ enum Sr2DevPool {
     DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MINCOST, DP_DTL_ROOTSP, DP_DTL_MAP, DP_DTL_MASK, DP_DTL_LISTS, DP_DTL_COUNTS, DP_DTL_CHAIN,
     DP_S_LEFT, DP_S_RIGHT, DP_S_NODEOFF, DP_S_BITS, DP_S_PRESENT, DP_S_OUTSIDE, DP_S_GAIN, DP_S_L, DP_S_FLAGS,
     DP_S_T, DP_S_TAG, DP_S_DEC, DP_S_ANC, DP_S_TAU, DP_S_TAUMIN, DP_S_COST, DP_S_MINCOST, DP_S_ROOTSP, DP_S_MAP,
-    DP_S_KIND, DP_S_SYN, DP_S_BEST, DP_S_ALLOWED, DP_S_EV,
+    DP_S_KIND, DP_S_SYN, DP_S_BEST, DP_S_ALLOWED, DP_S_EV, DP_S_CHAIN,
     DP_S_NODESLOT, DP_S_NODEDAG, DP_S_NODEPRE, DP_S_NODEINST, DP_S_PLAN32, DP_S_PLAN64,
     DP_RAW, DP_RAW_HEIGHT, DP_RAW_NODEROW, DP_RAW_INSTBASE, DP_RAW_COUNTS, DP_RAW_NODEOFF,
     DP_SPECIES_SLAB, DP_SPECIES_ANC, DP_RAW16, DP_DTL_MAP16, DP_COUNT

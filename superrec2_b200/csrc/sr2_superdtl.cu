@@ -346,14 +346,17 @@ __host__ __device__ __forceinline__ size_t super_topology_bytes(int S, int D, in
 //   2. top-down sweep of the four "separate" rows only (SEPMIN, in place);
 //   3. the cells, element-wise over the species with every lane busy: 6 candidates per kind.
 // TPR = 32: one warp per row (small species trees); TPR = 256: one CTA per row.
-template <int TPR>
+// CHAIN (one CTA per row only): all waves in ONE launch, rows handed out by ticket in height order, a row
+// waits for the "done" flags of its child rows and reads them past L1 (see dtl_wave_kernel in sr2_dtl.cu).
+template <int TPR, bool CHAIN = false>
 __global__ void __launch_bounds__(TPR == 32 ? 256 : TPR)
 superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                      const uint8_t* __restrict__ row_flags, int64_t row_begin, int64_t chunk_row0, int n_rows,
                      int32_t* __restrict__ T, uint32_t* __restrict__ tags, SuperCosts cs, int spad,
                      const int32_t* __restrict__ row_node, const int32_t* __restrict__ allowed,
-                     uint32_t* __restrict__ evs) {
+                     uint32_t* __restrict__ evs, int* __restrict__ chain_sync = nullptr) {
     extern __shared__ u64 smem[];
+    __shared__ int s_ticket;
     const int S = sp.S;
     int group, lane, groups_per_cta;
     if (TPR == 32) {
@@ -371,12 +374,29 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     for (int i = threadIdx.x; i < S; i += blockDim.x) s_meta[i] = __ldg(sp.meta + i);
     for (int i = threadIdx.x; i <= sp.D; i += blockDim.x) s_lvl[i] = __ldg(sp.int_lvl_off + i);
     for (int i = threadIdx.x; i < sp.n_internal; i += blockDim.x) s_int[i] = (uint16_t)__ldg(sp.int_list + i);
+    if (CHAIN && threadIdx.x == 0) s_ticket = atomicAdd(chain_sync, 1);
     __syncthreads();
-    int local = blockIdx.x * groups_per_cta + group;
+    int local = CHAIN ? s_ticket : blockIdx.x * groups_per_cta + group;
     if (local >= n_rows) return;
     const int64_t gr = row_begin + local;
     const size_t slot = (size_t)(gr - chunk_row0);
     u64* base = smem + (size_t)group * 12 * spad;
+    if (CHAIN) {
+        const int first_slot = (int)(row_begin - chunk_row0);
+        const int c = threadIdx.x == 0 ? row_cl[gr] : row_cr[gr];
+        if (threadIdx.x < 2 && c >= first_slot) {
+            if (c - first_slot >= local) __trap();   // rows are sorted by height: a child never follows its parent
+            const int* flag = chain_sync + 1 + (c - first_slot);
+            int up;
+            for (unsigned spins = 0;; ++spins) {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(up) : "l"(flag) : "memory");
+                if (up) break;
+                if (spins > (1u << 24)) __trap();
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+    }
     const int flags = row_flags[gr];
     SR2_DCHECK(row_cl[gr] < (int)slot && row_cr[gr] < (int)slot && row_cl[gr] >= -S && row_cr[gr] >= -S);
     SR2_DCHECK(flags >= 0 && flags < 4);
@@ -394,8 +414,8 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
         const int32_t* __restrict__ TB = c >= 0 ? T + ((size_t)c * 2 + 1) * sp.pitch : nullptr;
         for (int y = lane; y < S; y += TPR) {
             int d = (int)(s_meta[y] & 0xffffu);
-            int Araw = TA ? TA[y] : (y == -1 - c ? 0 : SR2_INF);
-            int Braw = TB ? TB[y] : SR2_INF;
+            int Araw = TA ? (CHAIN ? __ldcg(TA + y) : TA[y]) : (y == -1 - c ? 0 : SR2_INF);
+            int Braw = TB ? (CHAIN ? __ldcg(TB + y) : TB[y]) : SR2_INF;
             int A = sat_add(Araw, cs.floss * d), B = sat_add(Braw, cs.floss * d);
             // parent kind INHERIT: (sloss, 0, 0)
             SARR(base, spad, i, 1, T_CONS)[y] = key_min(skey(sat_add(A, cs.sloss), y, 0, d), skey(B, y, 1, d));
@@ -460,6 +480,14 @@ superdtl_wave_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
             (K ? Gout1 : Gout0)[x] = none ? SR2_NO_TAG : pick.tag;
             // the fused decode kernel reads what cost() charges for the cell next to its tag
             if (evs) evs[(slot * 2 + K) * sp.pitch + x] = none ? 0u : super_event_word(sp, x, dx, cx, pick, cs);
+        }
+    }
+    if (CHAIN) {   // the row is complete: every thread's stores, then the flag
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int* flag = chain_sync + 1 + local;
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
         }
     }
 }
@@ -1696,6 +1724,12 @@ static int super_configure(sr2_ctx* ctx, SuperProblem* p) {
                                            (int)p->wave_smem));
         SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)p->wave_smem));
+        SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
+        SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<512, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
+        SR2_CUDA(ctx, cudaFuncSetAttribute(superdtl_wave_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)p->wave_smem));
     }
     return SR2_OK;
 }
@@ -1911,7 +1945,31 @@ extern "C" int sr2_superdtl_solve(sr2_ctx* ctx) {
     }
     // ---- the table ---------------------------------------------------------------------
     SR2_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
-    for (int h = 1; h <= H; ++h) {
+    const bool chain_waves = p->cta_per_row && H >= 2 && !getenv("SR2_SUPERDTL_NO_CHAIN");
+    if (chain_waves) {
+        // one CTA per row: every wave in one launch, rows chained by done flags
+        const int64_t first = c.wave_off[1], n = c.wave_off[H + 1] - first;
+        void* ptr = nullptr;
+        int rc_sync = sr2_dev_reserve(ctx, DP_S_CHAIN, (size_t)(n + 1) * sizeof(int), &ptr);
+        if (rc_sync) return rc_sync;
+        int* sync = (int*)ptr;
+        SR2_CUDA(ctx, cudaMemsetAsync(sync, 0, (size_t)(n + 1) * sizeof(int), st));
+        if (p->cta_threads == 1024)
+            superdtl_wave_kernel<1024, true><<<(unsigned)n, 1024, p->wave_smem, st>>>(
+                ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, first, c.row_begin, (int)n, p->d_T, p->d_tag, cs,
+                p->spad, rows.row_node, p->d_allowed, nullptr, sync);
+        else if (p->cta_threads == 512)
+            superdtl_wave_kernel<512, true><<<(unsigned)n, 512, p->wave_smem, st>>>(
+                ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, first, c.row_begin, (int)n, p->d_T, p->d_tag, cs,
+                p->spad, rows.row_node, p->d_allowed, nullptr, sync);
+        else
+            superdtl_wave_kernel<256, true><<<(unsigned)n, 256, p->wave_smem, st>>>(
+                ctx->dsp, rows.row_cl, rows.row_cr, p->d_row_flags, first, c.row_begin, (int)n, p->d_T, p->d_tag, cs,
+                p->spad, rows.row_node, p->d_allowed, nullptr, sync);
+        ++n_launch;
+        ++n_waves;
+    }
+    for (int h = 1; h <= H && !chain_waves; ++h) {
         int64_t n = c.wave_off[h + 1] - c.wave_off[h];
         if (n <= 0) continue;
         if (!p->cta_per_row) {
