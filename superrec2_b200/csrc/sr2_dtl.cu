@@ -83,6 +83,10 @@ struct DtlProblem {
     int64_t list_pitch = 0;          // = R
     int sparse_maxm = SPARSE_MAXM_DEFAULT;
     int sparse_small = 0;            // rows with at most this many path species take the first tier (0 = one tier)
+    bool sparse_thread = false;      // the sparse tiers run on dtl_wave_thread_kernel (a thread per row, compact rows)
+    uint8_t* d_rowcnt = nullptr;     // [rows] per table set: entries of a compact row, 0 = dense
+    uint8_t* cur_rowcnt = nullptr;
+    bool cur_compact = false;        // chunk being enqueued: its sparse rows are stored compact
     int n_waves = 0, n_launch = 0;
     // wave launch configuration (fixed per upload)
     int spad = 0, wave_warps = 0;
@@ -105,11 +109,11 @@ struct DtlProblem {
     int flat2_low_waves = 5;     // waves up to this height launch an eighth of the dense-list CTAs (measured: 0 / 4 / 6 / 99 -> 6.70 / 6.59 / 6.59 / 6.66 ms)
     int flat2_sh = 0, flat2_thresh = 0;
     void (*flat2_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
-                     Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int) = nullptr;
+                     Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int, const uint8_t*) = nullptr;
     // The small top waves of a chunk run as ONE launch (flat2, chained): a row starts when the "done"
     // flags of its child rows are up, instead of one latency-bound launch per wave.
     void (*flat2_chain_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
-                           Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int) = nullptr;
+                           Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int, const uint8_t*) = nullptr;
     int cur_cherry_end = 0;          // chunk being enqueued: its wave-1 rows [0, cherry_end) are virtual (0 = materialised)
     size_t trace_smem_set = 0;       // dynamic shared memory opted in for dtl_select_trace_kernel
     int64_t chain_rows = 0;          // waves with fewer rows than this join the chained launch (0 = off)
@@ -527,6 +531,9 @@ dtl_cherry_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, cons
 //   value[31:sh] | rank[sh-1:db] | depth[db-1:0]
 // which the host only selects when every finite table value fits the value field.
 // ---------------------------------------------------------------------------
+// compact rows (dtl_wave_thread_kernel): entry = value | species << TH_VAL_BITS, TH_VAL_MASK = infinite
+#define TH_VAL_BITS 22
+#define TH_VAL_MASK 0x3fffffu
 struct Key32 {
     int sh, db;            // value shift (>= rank bits + depth bits), depth bits
     unsigned rm, dm;       // rank mask (after >> db), depth mask
@@ -801,7 +808,8 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
                       int64_t row_begin, int64_t chunk_row0, int n_rows, int32_t* __restrict__ T,
                       uint32_t* __restrict__ tags, DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask,
                       int sparse_max, int pf_near, int pf_far, const int* __restrict__ row_list,
-                      const int* __restrict__ list_count, int* __restrict__ chain_sync, int cherry_end) {
+                      const int* __restrict__ list_count, int* __restrict__ chain_sync, int cherry_end,
+                      const uint8_t* __restrict__ row_cnt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int cta_ticket;
     const int pitch = sp.pitch, rs = sp.flat_rs, n_chunks = pitch >> 5;
@@ -859,14 +867,31 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
         const int32_t* __restrict__ Tl = T + (size_t)(cl >= 0 ? cl : 0) * pitch + lane;
         const int32_t* __restrict__ Tr = T + (size_t)(cr >= 0 ? cr : 0) * pitch + lane;
         const uint32_t* __restrict__ kl = sp.keylow_p + lane;
-        // rows to read: internal children that are not virtual cherries (slots below cherry_end)
-        const bool il = cl >= cherry_end, ir = cr >= cherry_end;
+        // rows to read: internal children that are not virtual cherries (slots below cherry_end) and not
+        // compact rows (row_cnt != 0: the entries of a sparse row written by dtl_wave_thread_kernel)
+        const int ccl = (row_cnt && cl >= cherry_end) ? (int)row_cnt[cl] : 0;
+        const int ccr = (row_cnt && cr >= cherry_end) ? (int)row_cnt[cr] : 0;
+        const bool il = cl >= cherry_end && ccl == 0, ir = cr >= cherry_end && ccr == 0;
         if (il && ir) flat2_load<true, true, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
         else if (il) flat2_load<true, false, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
         else if (ir) flat2_load<false, true, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
         else flat2_load<false, false, CHAIN>(Tl, Tr, kl, M + lane, n_chunks, vmul, infkey);
         // a virtual cherry child: its closed form along the two root paths, lanes over depths
-        if (cherry_end > 0) __syncwarp();  // M of the whole row is written
+        if (cherry_end > 0 || row_cnt) __syncwarp();  // M of the whole row is written
+        // a compact child: its entries are scattered over the (infinite) key row
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side) {
+            const int cc = side ? ccr : ccl;
+            if (cc == 0) continue;
+            const uint32_t* __restrict__ Tc = reinterpret_cast<const uint32_t*>(T) + (size_t)(side ? cr : cl) * pitch;
+            for (int e = lane; e < cc; e += 32) {
+                const unsigned v = Tc[e], y = v >> TH_VAL_BITS, val = v & TH_VAL_MASK;
+                SR2_DCHECK((int)y < sp.S);
+                const unsigned key = (val == TH_VAL_MASK ? infkey : val * vmul) + __ldg(sp.keylow_p + y);
+                if (side) M[y].y = key;
+                else M[y].x = key;
+            }
+        }
 #pragma unroll 1
         for (int side = 0; side < 2; ++side) {
             const int c = side ? cr : cl;
@@ -1069,7 +1094,7 @@ __global__ void __launch_bounds__(256)
 dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                      int64_t row_begin, int64_t chunk_row0, int n_rows, uint32_t* __restrict__ rowmask,
                      int max_small, int max_sparse, int* __restrict__ lists, int list_pitch, int* __restrict__ counts,
-                     int cherry_rows) {
+                     int cherry_rows, uint8_t* __restrict__ row_cnt) {
     __shared__ int cta_cnt[3], cta_base[3];
     const int sub = threadIdx.x & 3;
     const int local = blockIdx.x * 64 + (threadIdx.x >> 2);
@@ -1109,6 +1134,8 @@ dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     if (valid) {
         cls = cnt <= max_small ? 0 : (cnt <= max_sparse ? 1 : 2);
         if (sub == 0) my_off = atomicAdd(&cta_cnt[cls], 1);
+        // compact rows (dtl_wave_thread_kernel): the size of the row's path set; 0 = a dense row
+        if (sub == 0 && row_cnt) row_cnt[row_begin + local - chunk_row0] = (uint8_t)(cls < 2 ? cnt : 0);
     }
     __syncthreads();
     if (threadIdx.x < 3) cta_base[threadIdx.x] = cta_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], cta_cnt[threadIdx.x]) : 0;
@@ -1379,6 +1406,275 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     }
 }
 
+// ---------------------------------------------------------------------------
+// Sparse rows, one THREAD per row, stored COMPACT.  The 4-lanes-per-row kernel above is bound by
+// instruction latency (a warp of 8 rows issues ~4,900 instructions, one every ~12 cycles, at 28 warps per SM)
+// and by its stores: a dense row is 1.6 KB of infinity plus m scattered 4-byte cells and tags, every one a
+// partial-sector write (measured with the stores compiled out: 1.7 -> 0.63 ms for wave 2).  Here
+//   * a lane owns a whole row and walks its path set serially, so a warp-instruction works on 32 rows; the
+//     row's state sits in shared memory as columns (word i of thread t at [i][t]: any per-thread index is
+//     conflict-free), 12 bytes per path species:
+//       el[e]  species | depth << 9 | parent position << 14 | first child position << 20 | child flags << 26
+//              | "on the root path of leaf la / lb / ra / rb" << 28..31      (elements are in BFS order)
+//       Mc[e]  (left key, right key): child values -> SUBMIN (up-sweep: e = m-1 .. 1 folds into its parent)
+//              -> SEPMIN, in place: siblings are adjacent in BFS order, an element's SUBMIN is last needed by
+//              the sibling after it (kept in registers for one step), its SEPMIN by its children further on;
+//   * the row is written compact: entry e of the row's slot in T is value | species << 22 (TH_VAL_MASK = the
+//     infinite value), entry e of its tag row the usual tag, e < m = row_cnt[slot] in BFS order -- nothing for
+//     the infinite cells.  Results go through a per-warp staging tile, 8 elements x 32 rows at a time, and
+//     leave as full 32-byte sectors (8 consecutive entries of one row);
+//   * readers: this kernel (a child's path set is a subset of its parent's, in the same order: a merge),
+//     dtl_wave_flat2_kernel (scatters a compact child into its dense key row), dtl_select_trace_kernel (the
+//     position of a species = number of path species before it, from the row's bit set).
+// The path set is generated top-down from the row's bit set (children of element p are appended in BFS
+// order, so the positions of parents / children / siblings fall out of the generation).  la, lb / ra, rb are
+// the leaf species of a leaf child (la only) or of a virtual cherry child: "species on the root path of
+// leaf a" is decided during the generation from preorder times (a sits below the first child of s iff
+// tin[a] < tin[second child]), so leaf rows and the closed form of cherry rows need no look-up per element.
+// Only used with virtual cherries (every stored child of a sparse row is then a compact row).
+// ---------------------------------------------------------------------------
+#ifndef TH_EXP
+#define TH_EXP 0
+#endif
+#define THREAD_ROWS 64   // rows (threads) per CTA
+#define TH_S_MASK 511u
+#define TH_D_SHIFT 9
+#define TH_PP_SHIFT 14
+#define TH_FC_SHIFT 20
+#define TH_C0_BIT 26
+#define TH_C1_BIT 27
+#define TH_FLAG_SHIFT 28
+// shared-memory words of a CTA: Mc [MAXM + 1] pairs and el [MAXM] per thread, and per warp the staging tile
+// (8 x 32 values, 8 x 32 tags), the rows' table offsets (32 x 2 words) and sizes (32)
+#define THREAD_SMEM_WORDS(MAXM) ((3 * (MAXM) + 2) * THREAD_ROWS + (THREAD_ROWS / 32) * (512 + 96))
+
+template <int MAXM>
+__global__ void __launch_bounds__(THREAD_ROWS)
+dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                       int64_t row_begin, int64_t chunk_row0, int32_t* __restrict__ T, uint32_t* __restrict__ tags,
+                       DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask, const int* __restrict__ row_list,
+                       const int* __restrict__ list_count, int cherry_end, const uint8_t* __restrict__ row_cnt) {
+    extern __shared__ __align__(16) uint32_t th_smem[];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int n_list = *list_count;
+    const int idx = blockIdx.x * THREAD_ROWS + t;
+    if (idx - lane >= n_list) return;  // the whole warp is beyond the list
+    const bool valid = idx < n_list;
+    const int pitch = sp.pitch, ms = sp.mask_stride;
+    uint2* Mc = reinterpret_cast<uint2*>(th_smem) + t;            // Mc[e * THREAD_ROWS]
+    uint32_t* el = th_smem + 2 * (MAXM + 1) * THREAD_ROWS + t;    // el[e * THREAD_ROWS]
+    uint32_t* stage = th_smem + (3 * MAXM + 2) * THREAD_ROWS + warp * (512 + 96);  // [2][8][32] values, tags
+    uint32_t* rowinfo = stage + 512;                              // [32] x (offset lo, offset hi), [32] sizes
+    // the row's bit set lives in the thread's own Mc words (two per element) until the keys are built
+    auto on_path = [&](int sx) {
+        const uint2 two = Mc[(sx >> 6) * THREAD_ROWS];
+        return (((sx >> 5) & 1 ? two.y : two.x) >> (sx & 31)) & 1u;
+    };
+    size_t slot = 0;
+    int cl = -1, cr = -1, m = 0;
+    // per side: 0 = leaf at species a, 1 = virtual cherry (a, b), 2 = stored (compact) row
+    int mode_l = 0, mode_r = 0, m_l = 0, m_r = 0;
+    CherryForm fl, fr;
+    fl.pa = fl.pb = fr.pa = fr.pb = nullptr;
+    fl.da = fl.db = fl.dl = fr.da = fr.db = fr.dl = 0;
+    fl.a_below = fl.b_below = fr.a_below = fr.b_below = false;
+    if (valid) {
+        const int64_t gr = row_begin + row_list[idx];
+        slot = (size_t)(gr - chunk_row0);
+        cl = row_cl[gr];
+        cr = row_cr[gr];
+        const uint4* m4 = reinterpret_cast<const uint4*>(rowmask + slot * ms);
+        for (int q = 0; q < (ms >> 2); ++q) {
+            const uint4 v = m4[q];
+            Mc[(2 * q) * THREAD_ROWS] = make_uint2(v.x, v.y);
+            Mc[(2 * q + 1) * THREAD_ROWS] = make_uint2(v.z, v.w);
+        }
+        mode_l = cl < 0 ? 0 : (cl < cherry_end ? 1 : 2);
+        mode_r = cr < 0 ? 0 : (cr < cherry_end ? 1 : 2);
+        if (mode_l == 2) m_l = (int)row_cnt[cl];
+        if (mode_r == 2) m_r = (int)row_cnt[cr];
+        SR2_DCHECK(mode_l != 2 || m_l > 0);  // a child's path set is a subset of this row's: it is a compact row
+        SR2_DCHECK(mode_r != 2 || m_r > 0);
+        // preorder times of the (up to) four leaf species whose root paths carry the children's finite cells
+        int la = cl < 0 ? -1 - cl : 0, lb = la, ra = cr < 0 ? -1 - cr : 0, rb = ra;
+        if (mode_l == 1) {
+            la = -1 - row_cl[chunk_row0 + cl];
+            lb = -1 - row_cr[chunk_row0 + cl];
+            fl.dl = (int)__ldg(sp.lca_depth + (size_t)la * sp.S + lb);
+        }
+        if (mode_r == 1) {
+            ra = -1 - row_cl[chunk_row0 + cr];
+            rb = -1 - row_cr[chunk_row0 + cr];
+            fr.dl = (int)__ldg(sp.lca_depth + (size_t)ra * sp.S + rb);
+        }
+        const int t_la = __ldg(sp.tin + la), t_lb = __ldg(sp.tin + lb), t_ra = __ldg(sp.tin + ra), t_rb = __ldg(sp.tin + rb);
+        fl.da = __ldg(sp.depth + la);
+        fl.db = __ldg(sp.depth + lb);
+        fr.da = __ldg(sp.depth + ra);
+        fr.db = __ldg(sp.depth + rb);
+        fl.a_below = fl.da > fl.dl, fl.b_below = fl.db > fl.dl;
+        fr.a_below = fr.da > fr.dl, fr.b_below = fr.db > fr.dl;
+        // ---- elements: top-down over the path set ----------------------------------------------------
+        el[0] = 0xfu << TH_FLAG_SHIFT;  // the root: species 0, depth 0, on every root path
+        m = 1;
+        for (int p = 0; p < m; ++p) {
+            const unsigned w = el[p * THREAD_ROWS];
+            const int s = (int)(w & TH_S_MASK), d = (int)((w >> TH_D_SHIFT) & 31u);
+            const uint4 span = __ldg(sp.span4 + s);  // tin, tout, (child0 + 1) << 16 | depth, tin of the second child
+            const int c0 = (int)(span.z >> 16) - 1;
+            if (c0 < 0) continue;
+            const unsigned b0 = on_path(c0), b1 = on_path(c0 + 1);
+            SR2_DCHECK(b0 | b1);                     // root paths end at leaf species
+            SR2_DCHECK(m + (int)(b0 + b1) <= MAXM);  // dtl_partition_kernel only lists rows that fit the tier
+            el[p * THREAD_ROWS] = w | ((unsigned)m << TH_FC_SHIFT) | (b0 << TH_C0_BIT) | (b1 << TH_C1_BIT);
+            const int split = (int)span.w;
+            const unsigned first = (unsigned)(t_la < split) | ((unsigned)(t_lb < split) << 1) |
+                                   ((unsigned)(t_ra < split) << 2) | ((unsigned)(t_rb < split) << 3);
+            const unsigned flags = w >> TH_FLAG_SHIFT;
+            const unsigned base = ((unsigned)(d + 1) << TH_D_SHIFT) | ((unsigned)p << TH_PP_SHIFT);
+            if (b0) el[(m++) * THREAD_ROWS] = (unsigned)c0 | base | ((flags & first) << TH_FLAG_SHIFT);
+            if (b1) el[(m++) * THREAD_ROWS] = (unsigned)(c0 + 1) | base | ((flags & ~first) << TH_FLAG_SHIFT);
+        }
+        SR2_DCHECK(m == (int)row_cnt[slot]);
+    }
+    // where the rows of this warp go (read by the flushes of the staging tile)
+    {
+        const unsigned long long off = (unsigned long long)slot * (unsigned)pitch;
+        rowinfo[2 * lane] = (unsigned)off;
+        rowinfo[2 * lane + 1] = (unsigned)(off >> 32);
+        rowinfo[64 + lane] = (unsigned)m;
+    }
+    // ---- child values -> keys ----------------------------------------------------------------------------
+    {
+        const unsigned vmul = 1u << kp.sh, infkey = 0xffffffffu << kp.sh;
+        const int db = kp.db;
+        // a compact child: its entries are a subsequence of this row's elements (same order)
+        const uint32_t* __restrict__ Tl = reinterpret_cast<const uint32_t*>(T) + (size_t)(mode_l == 2 ? cl : 0) * pitch;
+        const uint32_t* __restrict__ Tr = reinterpret_cast<const uint32_t*>(T) + (size_t)(mode_r == 2 ? cr : 0) * pitch;
+        int q_l = 0, q_r = 0;
+        unsigned next_l = m_l > 0 ? Tl[0] : 0xffffffffu, next_r = m_r > 0 ? Tr[0] : 0xffffffffu;
+        for (int e = 0; e < m; ++e) {
+            const unsigned w = el[e * THREAD_ROWS];
+            const unsigned s = w & TH_S_MASK;
+            const int d = (int)((w >> TH_D_SHIFT) & 31u);
+            const unsigned f = w >> TH_FLAG_SHIFT;
+            unsigned va = 0xffffffffu, vb = 0xffffffffu;
+            if (mode_l == 2) {
+                if ((next_l >> TH_VAL_BITS) == s) {
+                    va = next_l & TH_VAL_MASK;
+                    if (va == TH_VAL_MASK) va = 0xffffffffu;
+                    ++q_l;
+                    next_l = q_l < m_l ? Tl[q_l] : 0xffffffffu;
+                }
+            } else if (mode_l == 0) {
+                if ((f & 1u) && d == fl.da) va = 0u;
+            } else {
+                if ((f & 1u) && d <= fl.da) va = cherry_path_value(fl, 0, d, cs);
+                else if ((f & 2u) && d > fl.dl && d <= fl.db) va = cherry_path_value(fl, 1, d, cs);
+            }
+            if (mode_r == 2) {
+                if ((next_r >> TH_VAL_BITS) == s) {
+                    vb = next_r & TH_VAL_MASK;
+                    if (vb == TH_VAL_MASK) vb = 0xffffffffu;
+                    ++q_r;
+                    next_r = q_r < m_r ? Tr[q_r] : 0xffffffffu;
+                }
+            } else if (mode_r == 0) {
+                if ((f & 4u) && d == fr.da) vb = 0u;
+            } else {
+                if ((f & 4u) && d <= fr.da) vb = cherry_path_value(fr, 0, d, cs);
+                else if ((f & 8u) && d > fr.dl && d <= fr.db) vb = cherry_path_value(fr, 1, d, cs);
+            }
+            const unsigned low = (s << db) | (unsigned)d;
+            Mc[e * THREAD_ROWS] = make_uint2(va == 0xffffffffu ? infkey + low : va * vmul + low,
+                                             vb == 0xffffffffu ? infkey + low : vb * vmul + low);
+        }
+        SR2_DCHECK(q_l == m_l && q_r == m_r);  // every entry of a child found its element
+    }
+    // ---- up-sweep: SUBMIN ---------------------------------------------------------------------------------
+    for (int e = m - 1; e >= 1; --e) {
+        const int pp = (int)((el[e * THREAD_ROWS] >> TH_PP_SHIFT) & 63u);
+        const uint2 k = Mc[e * THREAD_ROWS], q = Mc[pp * THREAD_ROWS];
+        Mc[pp * THREAD_ROWS] = make_uint2(min(q.x, k.x), min(q.y, k.y));
+    }
+    // ---- top-down: SEPMIN in place, and the cells; the warp walks in step so that the results of 8 elements
+    //      x 32 rows leave through the staging tile as full sectors -------------------------------------------
+    const int loss = cs.loss, db = kp.db, thresh = kp.thresh;
+    const unsigned dm = kp.dm, rm = kp.rm, hi_mul = 1u << (32 - kp.sh);
+    const int c12 = -2 * loss, c3 = cs.dup, c45 = cs.hgt;
+    const uint2 inf2 = make_uint2(0xffffffffu, 0xffffffffu);
+    const int m_warp = __reduce_max_sync(0xffffffffu, m);
+    uint2 prevM = inf2;  // SUBMIN of the element before (its slot already holds its SEPMIN)
+    unsigned w = m > 0 ? el[0] : 0u;
+    for (int e = 0; e < m_warp; ++e) {
+        if (e < m) {
+            const unsigned wn = el[(e + 1 < MAXM ? e + 1 : e) * THREAD_ROWS];  // (garbage past m: unused)
+            const int pp = (int)((w >> TH_PP_SHIFT) & 63u);
+            const unsigned wp = el[pp * THREAD_ROWS];
+            const uint2 Pp = Mc[pp * THREAD_ROWS], mm = Mc[e * THREAD_ROWS], Mn = Mc[(e + 1) * THREAD_ROWS];
+            // the sibling is on a path iff the parent has both children; it is the next or the previous element
+            const bool both = ((wp >> TH_C0_BIT) & (wp >> TH_C1_BIT) & 1u) != 0u;
+            const bool is_first = (int)((wp >> TH_FC_SHIFT) & 63u) == e;
+            uint2 Ms = is_first ? Mn : prevM;
+            if (!both) Ms = inf2;
+            uint2 pq = make_uint2(min(Pp.x, Ms.x), min(Pp.y, Ms.y));
+            if (e == 0) pq = inf2;  // the root: nothing is incomparable to it
+            // the cell
+            const unsigned x = w & TH_S_MASK;
+            const int dx = (int)((w >> TH_D_SHIFT) & 31u);
+            const int fc = (int)((w >> TH_FC_SHIFT) & 63u);
+            const unsigned h0 = (w >> TH_C0_BIT) & 1u, h1 = (w >> TH_C1_BIT) & 1u;
+            uint2 k0 = inf2, k1 = inf2;  // SUBMIN at the two children of x
+            if (h0) k0 = Mc[fc * THREAD_ROWS];
+            if (h1) k1 = Mc[(fc + (int)h0) * THREAD_ROWS];
+            const int nld = -loss * dx;
+            const int qMl = flat2_q(mm.x, hi_mul, dm, loss), qMr = flat2_q(mm.y, hi_mul, dm, loss);
+            const int ql0 = flat2_q(k0.x, hi_mul, dm, loss), qr0 = flat2_q(k0.y, hi_mul, dm, loss);
+            const int ql1 = flat2_q(k1.x, hi_mul, dm, loss), qr1 = flat2_q(k1.y, hi_mul, dm, loss);
+            const int pl = (int)__umulhi(pq.x, hi_mul), pr = (int)__umulhi(pq.y, hi_mul);
+            const int b12 = 2 * nld + c12, b3 = 2 * nld + c3, b45 = nld + c45;
+            const int w1 = flat2_pack(ql0 + qr1 + b12, 0);  // 1. speciation, left below x0, right below x1
+            const int w2 = flat2_pack(ql1 + qr0 + b12, 1);  // 2. the other way round
+            const int w3 = flat2_pack(qMl + qMr + b3, 2);   // 3. duplication
+            const int w4 = flat2_pack(pl + qMr + b45, 3);   // 4. transfer, left child away
+            const int w5 = flat2_pack(qMl + pr + b45, 4);   // 5. transfer, right child away
+            const int wb = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
+            const int best = wb >> 3, which = wb & 7;
+            unsigned ka = mm.x, kb = mm.y;
+            ka = which == 0 ? k0.x : ka;
+            ka = which == 1 ? k1.x : ka;
+            ka = which == 3 ? pq.x : ka;
+            kb = which == 0 ? k1.y : kb;
+            kb = which == 1 ? k0.y : kb;
+            kb = which == 4 ? pq.y : kb;
+            const bool finite = best < thresh;
+            SR2_DCHECK(!finite || (unsigned)best < TH_VAL_MASK);
+            const int k = e & 7, col = (lane + 4 * k) & 31;  // tile layout: conflict-free for this store and for the flush
+            stage[k * 32 + col] = (finite ? (unsigned)best : TH_VAL_MASK) | (x << TH_VAL_BITS);
+            stage[256 + k * 32 + col] = finite ? (((ka >> db) & rm) | (((kb >> db) & rm) << 16)) : SR2_NO_TAG;
+            Mc[e * THREAD_ROWS] = pq;
+            prevM = mm;
+            w = wn;
+        }
+        if ((e & 7) == 7 || e == m_warp - 1) {
+            __syncwarp();
+            const int e0 = e & ~7, k = lane & 7;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int r = 4 * j + (lane >> 3);  // the lanes of a quarter-warp write 8 consecutive entries of row r
+                const int m_r2 = (int)rowinfo[64 + r];
+                if (e0 < m_r2) {   // (entries past the row's size, up to the sector's end, are never read)
+                    const size_t off = ((size_t)rowinfo[2 * r + 1] << 32 | rowinfo[2 * r]) + (size_t)(e0 + k);
+                    const int col = (r + 4 * k) & 31;
+                    reinterpret_cast<uint32_t*>(T)[off] = stage[k * 32 + col];
+                    tags[off] = stage[256 + k * 32 + col];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // Root-path bit set of every row of a wave computed by a kernel that does not maintain it itself:
 // mask(row) = mask(left child) | mask(right child), a leaf child contributing its species' path.
 __global__ void dtl_rowmask_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
@@ -1409,7 +1705,7 @@ __global__ void dtl_rowmask_kernel(DevSpecies sp, const int32_t* __restrict__ ro
 
 // the instantiation whose register-resident schedule is the shortest that holds n_steps
 typedef void (*Flat2Fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*,
-                        DtlCosts, Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int);
+                        DtlCosts, Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int, const uint8_t*);
 template <bool CHAIN>
 static Flat2Fn flat2_pick(int n_steps) {
     if (n_steps <= 12) return dtl_wave_flat2_kernel<12, CHAIN>;
@@ -1566,7 +1862,8 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
                         const int32_t* __restrict__ row_left, const int32_t* __restrict__ row_right,
                         const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr, int cap, int check_T,
                         int cherry_end, DtlCosts cs, int32_t* __restrict__ min_cost, int32_t* __restrict__ root_species,
-                        int32_t* __restrict__ map) {
+                        int32_t* __restrict__ map, const uint8_t* __restrict__ row_cnt,
+                        const uint32_t* __restrict__ rowmask) {
     extern __shared__ int2 trace_lists[];  // [2][cap] of (row slot, species)
     __shared__ u64 warp_best[32];
     __shared__ int n_list[2];
@@ -1594,6 +1891,12 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
                 const unsigned t = cherry_path_value(f, which, d, cs);
                 if (t != 0xffffffffu) best = key_min(best, ((u64)t << 32) | (unsigned)path[d]);
             }
+        }
+    } else if (row_cnt && row_cnt[slot0]) {  // a compact root row (small trees): entries = value | species << 22
+        const int m0 = (int)row_cnt[slot0];
+        for (int e = threadIdx.x; e < m0; e += blockDim.x) {
+            const unsigned v = (unsigned)T[slot0 * pitch + e], t = v & TH_VAL_MASK;
+            if (t != TH_VAL_MASK) best = key_min(best, ((u64)t << 32) | (v >> TH_VAL_BITS));
         }
     } else {
         for (int x = threadIdx.x; x < sp.S; x += blockDim.x) {
@@ -1638,6 +1941,30 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
                 if (cl < 0 && cr < 0) {
                     a = -1 - cl;
                     c = -1 - cr;
+                } else if (row_cnt && row_cnt[slot]) {
+                    // a compact row: the entry of species x is the number of path species before it
+                    const uint32_t* mk = rowmask + (size_t)slot * sp.mask_stride;
+                    const int xw = x >> 5;
+                    int pos = 0;
+                    for (int q = 0; q * 4 <= xw; ++q) {
+                        const uint4 v = reinterpret_cast<const uint4*>(mk)[q];
+                        const unsigned wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int wi = q * 4 + i;
+                            if (wi < xw) pos += __popc(wd[i]);
+                            else if (wi == xw) pos += __popc(wd[i] & ((1u << (x & 31)) - 1u));
+                        }
+                    }
+                    SR2_DCHECK(pos < (int)row_cnt[slot]);
+                    SR2_DCHECK(((unsigned)T[(size_t)slot * pitch + pos] >> TH_VAL_BITS) == (unsigned)x);
+                    if (!check_T || ((unsigned)T[(size_t)slot * pitch + pos] & TH_VAL_MASK) != TH_VAL_MASK) {
+                        const unsigned tag = tags[(size_t)slot * pitch + pos];
+                        if (tag != SR2_NO_TAG) {
+                            a = tag & 0xffffu;
+                            c = tag >> 16;
+                        }
+                    }
                 } else if (!check_T || T[(size_t)slot * pitch + x] < SR2_INF) {
                     const unsigned tag = tags[(size_t)slot * pitch + x];
                     if (tag != SR2_NO_TAG) {
@@ -1719,6 +2046,8 @@ static int dtl_prepare(void* user) {
     }
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_MASK, table_elems / ctx->pitch * ctx->dsp.mask_stride * sizeof(uint32_t) + 256, &ptr))) return rc;
     p->d_mask = (uint32_t*)ptr;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_ROWCNT, table_elems / ctx->pitch + 256, &ptr))) return rc;
+    p->d_rowcnt = (uint8_t*)ptr;
     p->list_pitch = std::max<int64_t>(p->rows.R, 1);
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_LISTS, (size_t)3 * p->list_pitch * sizeof(int), &ptr))) return rc;
     p->d_lists = (int*)ptr;
@@ -1939,6 +2268,15 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
                                                (int)(4 * 8 * SPARSE_ROW_WORDS(SPARSE_MAXM_SMALL) * sizeof(uint32_t))));
             SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_sparse_kernel<SPARSE_MAXM_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             p->sparse_small = SPARSE_MAXM_SMALL;
+            // a thread per sparse row (dtl_wave_thread_kernel) when species and depth fit its element word
+            p->sparse_thread = p->rank_bits <= 9 && p->depth_bits <= 5 && ctx->dsp.lca_depth && ctx->dsp.span4;
+            if (const char* th = getenv("SR2_SPARSE_THREAD")) p->sparse_thread = p->sparse_thread && th[0] != '0';
+            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<SPARSE_MAXM_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               4 * THREAD_SMEM_WORDS(SPARSE_MAXM_SMALL)));
+            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<SPARSE_MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               4 * THREAD_SMEM_WORDS(SPARSE_MAXM)));
+            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<SPARSE_MAXM_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<SPARSE_MAXM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             if (const char* sm = getenv("SR2_SPARSE_SMALL")) p->sparse_small = std::min(atoi(sm), SPARSE_MAXM_SMALL);
             if (const char* sm = getenv("SR2_SPARSE_MAXM")) p->sparse_maxm = std::min(atoi(sm), SPARSE_MAXM);
             const int resident = 8 * 4 * ctx->sm_count;  // rows of the CTAs that run at one time
@@ -2017,7 +2355,19 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
                 SR2_CUDA(ctx, cudaStreamWaitEvent(ts, fork, 0));
             }
         }
-        if (p->sparse_maxm > 0) {  // the two sparse tiers (the caller counts one launch for this wave)
+        if (p->sparse_maxm > 0 && p->cur_compact) {  // the two sparse tiers, a thread per row, compact rows
+            const unsigned ctas = (unsigned)((n_rows + THREAD_ROWS - 1) / THREAD_ROWS);
+            if (p->sparse_small > 0) {
+                ++p->n_launch;
+                dtl_wave_thread_kernel<SPARSE_MAXM_SMALL><<<ctas, THREAD_ROWS, 4 * THREAD_SMEM_WORDS(SPARSE_MAXM_SMALL), p->cur_stream>>>(
+                    ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
+                    p->cur_mask, lists, counts, p->cur_cherry_end, p->cur_rowcnt);
+            }
+            ++p->n_launch;
+            dtl_wave_thread_kernel<SPARSE_MAXM><<<ctas, THREAD_ROWS, 4 * THREAD_SMEM_WORDS(SPARSE_MAXM), ts>>>(
+                ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
+                p->cur_mask, lists + p->list_pitch, counts + 1, p->cur_cherry_end, p->cur_rowcnt);
+        } else if (p->sparse_maxm > 0) {  // the two sparse tiers (the caller counts one launch for this wave)
             if (p->sparse_small > 0) {
                 ++p->n_launch;
                 dtl_wave_sparse_kernel<SPARSE_MAXM_SMALL><<<(unsigned)((n_rows + 31) / 32), 128,
@@ -2037,7 +2387,7 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         p->flat2_fn<<<(unsigned)dense_ctas, 32 * p->flat2_rows, p->flat2_smem, ds>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
             p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + 2 * p->list_pitch, counts + 2,
-            nullptr, p->cur_cherry_end);
+            nullptr, p->cur_cherry_end, p->cur_compact ? p->cur_rowcnt : nullptr);
         if (join) {
             SR2_CUDA(ctx, cudaEventRecord(join, ds));
             SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, join, 0));
@@ -2104,6 +2454,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     p->cur_tag = p->d_tag + set * table_elems;
     p->cur_C = p->d_C ? p->d_C + set * table_elems : nullptr;
     p->cur_mask = p->d_mask + set * (table_elems / ctx->pitch * ctx->dsp.mask_stride);
+    p->cur_rowcnt = p->d_rowcnt + set * (table_elems / ctx->pitch);
     p->cur_chunk = ci;
     p->cur_set = set;
     ctx->split_used[set] = 0;  // (re-recording an event does not disturb waits already enqueued on it)
@@ -2149,6 +2500,9 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     }
     if (H < 1) virt = false;  // one-node trees only: no rows at all
     p->cur_cherry_end = virt ? (int)(c.wave_off[2] - c.row_begin) : 0;
+    // compact sparse rows need every reader to know the layout: the thread kernel itself (its stored children are
+    // then compact rows), flat2 and the per-tree traceback; nobody else may read the tables
+    p->cur_compact = virt && p->sparse_thread && p->sparse_maxm > 0 && p->max_finite < (int64_t)TH_VAL_MASK - 16;
     std::vector<cudaEvent_t>& part_events = ctx->part_events[set];
     cudaStream_t ps = nullptr;
     if (chain) {
@@ -2160,6 +2514,8 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w0[ci], st));   // also orders the side stream after earlier
         SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->dtl_ev_w0[ci], 0));  // work of this stream (uploads, solves)
         SR2_CUDA(ctx, cudaMemsetAsync(p->d_counts + (size_t)ci * 4 * 65536, 0, (size_t)4 * (H + 2) * sizeof(int), ps));
+        // rows of waves that are not listed (the chained top waves) are dense
+        if (p->cur_compact) SR2_CUDA(ctx, cudaMemsetAsync(p->cur_rowcnt, 0, (size_t)(c.row_end - c.row_begin), ps));
     }
     // (wave 1 has no stored sets: a cherry's set is the two root paths of its leaves, which its parent's
     // kernel reads from the species tables)
@@ -2177,7 +2533,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
                 dtl_partition_kernel<<<(unsigned)((n + 63) / 64), 256, 0, ps>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask,
                     p->sparse_maxm > 0 ? p->sparse_small : 0, p->sparse_maxm, p->d_lists + c.wave_off[h], (int)p->list_pitch,
-                    p->d_counts + ((size_t)ci * 65536 + h) * 4, cherry_rows);
+                    p->d_counts + ((size_t)ci * 65536 + h) * 4, cherry_rows, p->cur_compact ? p->cur_rowcnt : nullptr);
                 if (part_events.size() <= events_used) {
                     cudaEvent_t e;
                     SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -2260,7 +2616,8 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         kp.thresh = p->flat2_thresh;
         p->flat2_chain_fn<<<(unsigned)((n + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem, st>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, first, c.row_begin, (int)n, p->cur_T, p->cur_tag, cs, kp,
-            p->cur_mask, p->flat2_sparse_max, 0, 0, nullptr, nullptr, sync, p->cur_cherry_end);
+            p->cur_mask, p->flat2_sparse_max, 0, 0, nullptr, nullptr, sync, p->cur_cherry_end,
+            p->cur_compact ? p->cur_rowcnt : nullptr);
         SR2_CUDA(ctx, cudaGetLastError());
         ++p->n_waves;
         ++p->n_launch;
@@ -2288,7 +2645,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
             ctx->dsp, p->rows.d_root_row, p->rows.d_root_node, c.inst_begin, c.row_begin, p->cur_T,
             p->need_decoded_cost ? p->cur_C : nullptr, p->cur_tag, p->rows.row_left, p->rows.row_right,
             p->rows.row_cl, p->rows.row_cr, (int)cap, getenv("SR2_DTL_TRACE_CHECK") ? 1 : 0, p->cur_cherry_end, cs,
-            p->d_min_cost, p->d_root_species, p->d_map);
+            p->d_min_cost, p->d_root_species, p->d_map, p->cur_compact ? p->cur_rowcnt : nullptr, p->cur_mask);
         ++p->n_launch;
     } else if (n_inst > 0) {
         dtl_select_kernel<<<(n_inst + 7) / 8, 256, 0, st>>>(
