@@ -86,6 +86,8 @@ struct DtlProblem {
     bool sparse_thread = false;      // the sparse tiers run on dtl_wave_thread_kernel (a thread per row, compact rows)
     uint8_t* d_rowcnt = nullptr;     // [rows] per table set: entries of a compact row, 0 = dense
     uint8_t* cur_rowcnt = nullptr;
+    uint4* d_rowinfo = nullptr;      // [rows][2] per table set: dtl_partition_kernel's record of a listed row
+    uint4* cur_rowinfo = nullptr;
     bool cur_compact = false;        // chunk being enqueued: its sparse rows are stored compact
     int n_waves = 0, n_launch = 0;
     // wave launch configuration (fixed per upload)
@@ -1094,7 +1096,7 @@ __global__ void __launch_bounds__(256)
 dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                      int64_t row_begin, int64_t chunk_row0, int n_rows, uint32_t* __restrict__ rowmask,
                      int max_small, int max_sparse, int* __restrict__ lists, int list_pitch, int* __restrict__ counts,
-                     int cherry_rows, uint8_t* __restrict__ row_cnt) {
+                     int cherry_rows, uint8_t* __restrict__ row_cnt, uint4* __restrict__ row_info) {
     __shared__ int cta_cnt[3], cta_base[3];
     const int sub = threadIdx.x & 3;
     const int local = blockIdx.x * 64 + (threadIdx.x >> 2);
@@ -1112,13 +1114,32 @@ dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
         const uint4* b4 = reinterpret_cast<const uint4*>(cr >= 0 ? rowmask + (size_t)cr * ms : sp.pathmask + (size_t)(-1 - cr) * ms);
         const uint4* a5 = a4;
         const uint4* b5 = b4;
+        // leaf species behind the two children: of a leaf child (one), of a cherry child (two)
+        int la = cl < 0 ? -1 - cl : -1, lb = la, ra = cr < 0 ? -1 - cr : -1, rb = ra;
         if (cl >= 0 && cl < cherry_rows) {
-            a4 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)(-1 - row_cl[chunk_row0 + cl]) * ms);
-            a5 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)(-1 - row_cr[chunk_row0 + cl]) * ms);
+            la = -1 - row_cl[chunk_row0 + cl];
+            lb = -1 - row_cr[chunk_row0 + cl];
+            a4 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)la * ms);
+            a5 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)lb * ms);
         }
         if (cr >= 0 && cr < cherry_rows) {
-            b4 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)(-1 - row_cl[chunk_row0 + cr]) * ms);
-            b5 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)(-1 - row_cr[chunk_row0 + cr]) * ms);
+            ra = -1 - row_cl[chunk_row0 + cr];
+            rb = -1 - row_cr[chunk_row0 + cr];
+            b4 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)ra * ms);
+            b5 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)rb * ms);
+        }
+        // dtl_wave_thread_kernel's view of the row in two 16-byte words: child descriptors, preorder times of
+        // the four leaf species, and per side depth(a) | depth(b) << 8 | depth(lca(a, b)) << 16
+        if (row_info && sub < 2) {
+            const int a = sub ? ra : la, b = sub ? rb : lb;
+            unsigned ta = 0u, tb = 0u, dpack = 0u;
+            if (a >= 0) {
+                ta = (unsigned)__ldg(sp.tin + a);
+                tb = (unsigned)__ldg(sp.tin + b);
+                dpack = (unsigned)__ldg(sp.depth + a) | ((unsigned)__ldg(sp.depth + b) << 8) |
+                        ((unsigned)__ldg(sp.lca_depth + (size_t)a * sp.S + b) << 16);
+            }
+            row_info[(size_t)(gr - chunk_row0) * 2 + sub] = make_uint4((unsigned)(sub ? cr : cl), ta, tb, dpack);
         }
         uint4* o4 = reinterpret_cast<uint4*>(rowmask + (size_t)(gr - chunk_row0) * ms);
         for (int w = sub; w < quads; w += 4) {
@@ -1453,7 +1474,8 @@ __global__ void __launch_bounds__(THREAD_ROWS)
 dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                        int64_t row_begin, int64_t chunk_row0, int32_t* __restrict__ T, uint32_t* __restrict__ tags,
                        DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask, const int* __restrict__ row_list,
-                       const int* __restrict__ list_count, int cherry_end, const uint8_t* __restrict__ row_cnt) {
+                       const int* __restrict__ list_count, int cherry_end, const uint8_t* __restrict__ row_cnt,
+                       const uint4* __restrict__ row_info) {
     extern __shared__ __align__(16) uint32_t th_smem[];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int n_list = *list_count;
@@ -1474,46 +1496,30 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     int cl = -1, cr = -1, m = 0;
     // per side: 0 = leaf at species a, 1 = virtual cherry (a, b), 2 = stored (compact) row
     int mode_l = 0, mode_r = 0, m_l = 0, m_r = 0;
-    CherryForm fl, fr;
-    fl.pa = fl.pb = fr.pa = fr.pb = nullptr;
-    fl.da = fl.db = fl.dl = fr.da = fr.db = fr.dl = 0;
-    fl.a_below = fl.b_below = fr.a_below = fr.b_below = false;
+    // closed forms of the children that are leaves or virtual cherries (dtl_partition_kernel's record of the row):
+    // depths of the leaf species a, b and of lca(a, b) per side, preorder times of the four species
+    int l_da = 0, l_db = 0, l_dl = 0, r_da = 0, r_db = 0, r_dl = 0;
     if (valid) {
-        const int64_t gr = row_begin + row_list[idx];
-        slot = (size_t)(gr - chunk_row0);
-        cl = row_cl[gr];
-        cr = row_cr[gr];
+        slot = (size_t)(row_begin - chunk_row0) + (size_t)row_list[idx];
+        const uint4 il = row_info[slot * 2], ir = row_info[slot * 2 + 1];
         const uint4* m4 = reinterpret_cast<const uint4*>(rowmask + slot * ms);
         for (int q = 0; q < (ms >> 2); ++q) {
             const uint4 v = m4[q];
             Mc[(2 * q) * THREAD_ROWS] = make_uint2(v.x, v.y);
             Mc[(2 * q + 1) * THREAD_ROWS] = make_uint2(v.z, v.w);
         }
+        cl = (int)il.x;
+        cr = (int)ir.x;
+        SR2_DCHECK(cl == row_cl[chunk_row0 + slot] && cr == row_cr[chunk_row0 + slot]);
         mode_l = cl < 0 ? 0 : (cl < cherry_end ? 1 : 2);
         mode_r = cr < 0 ? 0 : (cr < cherry_end ? 1 : 2);
         if (mode_l == 2) m_l = (int)row_cnt[cl];
         if (mode_r == 2) m_r = (int)row_cnt[cr];
         SR2_DCHECK(mode_l != 2 || m_l > 0);  // a child's path set is a subset of this row's: it is a compact row
         SR2_DCHECK(mode_r != 2 || m_r > 0);
-        // preorder times of the (up to) four leaf species whose root paths carry the children's finite cells
-        int la = cl < 0 ? -1 - cl : 0, lb = la, ra = cr < 0 ? -1 - cr : 0, rb = ra;
-        if (mode_l == 1) {
-            la = -1 - row_cl[chunk_row0 + cl];
-            lb = -1 - row_cr[chunk_row0 + cl];
-            fl.dl = (int)__ldg(sp.lca_depth + (size_t)la * sp.S + lb);
-        }
-        if (mode_r == 1) {
-            ra = -1 - row_cl[chunk_row0 + cr];
-            rb = -1 - row_cr[chunk_row0 + cr];
-            fr.dl = (int)__ldg(sp.lca_depth + (size_t)ra * sp.S + rb);
-        }
-        const int t_la = __ldg(sp.tin + la), t_lb = __ldg(sp.tin + lb), t_ra = __ldg(sp.tin + ra), t_rb = __ldg(sp.tin + rb);
-        fl.da = __ldg(sp.depth + la);
-        fl.db = __ldg(sp.depth + lb);
-        fr.da = __ldg(sp.depth + ra);
-        fr.db = __ldg(sp.depth + rb);
-        fl.a_below = fl.da > fl.dl, fl.b_below = fl.db > fl.dl;
-        fr.a_below = fr.da > fr.dl, fr.b_below = fr.db > fr.dl;
+        const int t_la = (int)il.y, t_lb = (int)il.z, t_ra = (int)ir.y, t_rb = (int)ir.z;
+        l_da = (int)(il.w & 0xffu), l_db = (int)((il.w >> 8) & 0xffu), l_dl = (int)(il.w >> 16);
+        r_da = (int)(ir.w & 0xffu), r_db = (int)((ir.w >> 8) & 0xffu), r_dl = (int)(ir.w >> 16);
         // ---- elements: top-down over the path set ----------------------------------------------------
         el[0] = 0xfu << TH_FLAG_SHIFT;  // the root: species 0, depth 0, on every root path
         m = 1;
@@ -1553,37 +1559,58 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         const uint32_t* __restrict__ Tr = reinterpret_cast<const uint32_t*>(T) + (size_t)(mode_r == 2 ? cr : 0) * pitch;
         int q_l = 0, q_r = 0;
         unsigned next_l = m_l > 0 ? Tl[0] : 0xffffffffu, next_r = m_r > 0 ? Tr[0] : 0xffffffffu;
+        // Closed form of a cherry (a, b) at depth d of a's path: above the lca a duplication, at the lca a
+        // speciation when both leaves sit below it, below the lca a transfer of b (if b is below the lca);
+        // on b's path below the lca a transfer of a.  A leaf child is 0 at its own species.  All of it as
+        // selects on per-row constants: the lanes of a warp hold rows of every kind.
+        const int loss = cs.loss;
+        struct Side {
+            int k_top, k_lca, k_a, k_b, da, db, dl;
+            bool a_ok, b_ok, leaf, cherry;
+        };
+        auto make_side = [&](int mode, int da, int db_, int dl) {
+            Side z;
+            const bool a_below = da > dl, b_below = db_ > dl;
+            z.da = da, z.db = db_, z.dl = dl;
+            z.k_top = cs.dup + loss * (da + db_);                       // - 2 loss d
+            z.k_lca = (a_below && b_below) ? loss * (da + db_ - 2) : z.k_top;  // - 2 loss d, at d == dl
+            z.k_a = cs.hgt + loss * da;                                 // - loss d, a's path below the lca
+            z.k_b = cs.hgt + loss * db_;                                // - loss d, b's path below the lca
+            z.a_ok = b_below, z.b_ok = a_below;
+            z.leaf = mode == 0, z.cherry = mode == 1;
+            return z;
+        };
+        const Side zl = make_side(mode_l, l_da, l_db, l_dl), zr = make_side(mode_r, r_da, r_db, r_dl);
+        auto closed = [&](const Side& z, bool fa, bool fb, int d) {
+            const int ld = loss * d;
+            const bool on_a = fa && d <= z.da, on_b = fb && !on_a && d > z.dl && d <= z.db;
+            unsigned v = 0xffffffffu;
+            const unsigned top = (unsigned)((d == z.dl ? z.k_lca : z.k_top) - 2 * ld);
+            const unsigned va = d <= z.dl ? top : (z.a_ok ? (unsigned)(z.k_a - ld) : 0xffffffffu);
+            const unsigned vb = z.b_ok ? (unsigned)(z.k_b - ld) : 0xffffffffu;
+            v = on_a ? va : v;
+            v = on_b ? vb : v;
+            v = z.cherry ? v : 0xffffffffu;
+            v = (z.leaf && on_a && d == z.da) ? 0u : v;
+            return v;
+        };
         for (int e = 0; e < m; ++e) {
             const unsigned w = el[e * THREAD_ROWS];
             const unsigned s = w & TH_S_MASK;
             const int d = (int)((w >> TH_D_SHIFT) & 31u);
             const unsigned f = w >> TH_FLAG_SHIFT;
-            unsigned va = 0xffffffffu, vb = 0xffffffffu;
-            if (mode_l == 2) {
-                if ((next_l >> TH_VAL_BITS) == s) {
-                    va = next_l & TH_VAL_MASK;
-                    if (va == TH_VAL_MASK) va = 0xffffffffu;
-                    ++q_l;
-                    next_l = q_l < m_l ? Tl[q_l] : 0xffffffffu;
-                }
-            } else if (mode_l == 0) {
-                if ((f & 1u) && d == fl.da) va = 0u;
-            } else {
-                if ((f & 1u) && d <= fl.da) va = cherry_path_value(fl, 0, d, cs);
-                else if ((f & 2u) && d > fl.dl && d <= fl.db) va = cherry_path_value(fl, 1, d, cs);
+            unsigned va = closed(zl, f & 1u, f & 2u, d), vb = closed(zr, f & 4u, f & 8u, d);
+            if (mode_l == 2 && (next_l >> TH_VAL_BITS) == s) {
+                va = next_l & TH_VAL_MASK;
+                if (va == TH_VAL_MASK) va = 0xffffffffu;
+                ++q_l;
+                next_l = q_l < m_l ? Tl[q_l] : 0xffffffffu;
             }
-            if (mode_r == 2) {
-                if ((next_r >> TH_VAL_BITS) == s) {
-                    vb = next_r & TH_VAL_MASK;
-                    if (vb == TH_VAL_MASK) vb = 0xffffffffu;
-                    ++q_r;
-                    next_r = q_r < m_r ? Tr[q_r] : 0xffffffffu;
-                }
-            } else if (mode_r == 0) {
-                if ((f & 4u) && d == fr.da) vb = 0u;
-            } else {
-                if ((f & 4u) && d <= fr.da) vb = cherry_path_value(fr, 0, d, cs);
-                else if ((f & 8u) && d > fr.dl && d <= fr.db) vb = cherry_path_value(fr, 1, d, cs);
+            if (mode_r == 2 && (next_r >> TH_VAL_BITS) == s) {
+                vb = next_r & TH_VAL_MASK;
+                if (vb == TH_VAL_MASK) vb = 0xffffffffu;
+                ++q_r;
+                next_r = q_r < m_r ? Tr[q_r] : 0xffffffffu;
             }
             const unsigned low = (s << db) | (unsigned)d;
             Mc[e * THREAD_ROWS] = make_uint2(va == 0xffffffffu ? infkey + low : va * vmul + low,
@@ -1946,14 +1973,16 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
                     const uint32_t* mk = rowmask + (size_t)slot * sp.mask_stride;
                     const int xw = x >> 5;
                     int pos = 0;
-                    for (int q = 0; q * 4 <= xw; ++q) {
+                    const unsigned below = (1u << (x & 31)) - 1u;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {  // at most 16 words; the loads are independent
+                        if (q * 4 > xw) continue;
                         const uint4 v = reinterpret_cast<const uint4*>(mk)[q];
                         const unsigned wd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const int wi = q * 4 + i;
-                            if (wi < xw) pos += __popc(wd[i]);
-                            else if (wi == xw) pos += __popc(wd[i] & ((1u << (x & 31)) - 1u));
+                            pos += wi < xw ? __popc(wd[i]) : (wi == xw ? __popc(wd[i] & below) : 0);
                         }
                     }
                     SR2_DCHECK(pos < (int)row_cnt[slot]);
@@ -2048,6 +2077,8 @@ static int dtl_prepare(void* user) {
     p->d_mask = (uint32_t*)ptr;
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_ROWCNT, table_elems / ctx->pitch + 256, &ptr))) return rc;
     p->d_rowcnt = (uint8_t*)ptr;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_ROWINFO, (table_elems / ctx->pitch) * 2 * sizeof(uint4) + 256, &ptr))) return rc;
+    p->d_rowinfo = (uint4*)ptr;
     p->list_pitch = std::max<int64_t>(p->rows.R, 1);
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_LISTS, (size_t)3 * p->list_pitch * sizeof(int), &ptr))) return rc;
     p->d_lists = (int*)ptr;
@@ -2361,12 +2392,12 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
                 ++p->n_launch;
                 dtl_wave_thread_kernel<SPARSE_MAXM_SMALL><<<ctas, THREAD_ROWS, 4 * THREAD_SMEM_WORDS(SPARSE_MAXM_SMALL), p->cur_stream>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
-                    p->cur_mask, lists, counts, p->cur_cherry_end, p->cur_rowcnt);
+                    p->cur_mask, lists, counts, p->cur_cherry_end, p->cur_rowcnt, p->cur_rowinfo);
             }
             ++p->n_launch;
             dtl_wave_thread_kernel<SPARSE_MAXM><<<ctas, THREAD_ROWS, 4 * THREAD_SMEM_WORDS(SPARSE_MAXM), ts>>>(
                 ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
-                p->cur_mask, lists + p->list_pitch, counts + 1, p->cur_cherry_end, p->cur_rowcnt);
+                p->cur_mask, lists + p->list_pitch, counts + 1, p->cur_cherry_end, p->cur_rowcnt, p->cur_rowinfo);
         } else if (p->sparse_maxm > 0) {  // the two sparse tiers (the caller counts one launch for this wave)
             if (p->sparse_small > 0) {
                 ++p->n_launch;
@@ -2455,6 +2486,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     p->cur_C = p->d_C ? p->d_C + set * table_elems : nullptr;
     p->cur_mask = p->d_mask + set * (table_elems / ctx->pitch * ctx->dsp.mask_stride);
     p->cur_rowcnt = p->d_rowcnt + set * (table_elems / ctx->pitch);
+    p->cur_rowinfo = p->d_rowinfo + set * (table_elems / ctx->pitch) * 2;
     p->cur_chunk = ci;
     p->cur_set = set;
     ctx->split_used[set] = 0;  // (re-recording an event does not disturb waits already enqueued on it)
@@ -2533,7 +2565,8 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
                 dtl_partition_kernel<<<(unsigned)((n + 63) / 64), 256, 0, ps>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask,
                     p->sparse_maxm > 0 ? p->sparse_small : 0, p->sparse_maxm, p->d_lists + c.wave_off[h], (int)p->list_pitch,
-                    p->d_counts + ((size_t)ci * 65536 + h) * 4, cherry_rows, p->cur_compact ? p->cur_rowcnt : nullptr);
+                    p->d_counts + ((size_t)ci * 65536 + h) * 4, cherry_rows, p->cur_compact ? p->cur_rowcnt : nullptr,
+                    p->cur_compact ? p->cur_rowinfo : nullptr);
                 if (part_events.size() <= events_used) {
                     cudaEvent_t e;
                     SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
