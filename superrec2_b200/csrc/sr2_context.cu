@@ -180,7 +180,8 @@ extern "C" void sr2_destroy(sr2_ctx* ctx) {
         if (ctx->part_stream[k]) cudaStreamDestroy(ctx->part_stream[k]);
         for (cudaEvent_t e : ctx->part_events[k]) cudaEventDestroy(e);
         if (ctx->dense_stream[k]) cudaStreamDestroy(ctx->dense_stream[k]);
-        if (ctx->tier_stream[k]) cudaStreamDestroy(ctx->tier_stream[k]);
+        for (int j = 0; j < 8; ++j)
+            if (ctx->tier_streams[k][j]) cudaStreamDestroy(ctx->tier_streams[k][j]);
         for (cudaEvent_t e : ctx->split_events[k]) cudaEventDestroy(e);
     }
     for (cudaEvent_t e : ctx->chunk_events) cudaEventDestroy(e);

@@ -89,6 +89,14 @@ struct DtlProblem {
     uint4* d_rowinfo = nullptr;      // [rows][2] per table set: dtl_partition_kernel's record of a listed row
     uint4* cur_rowinfo = nullptr;
     bool cur_compact = false;        // chunk being enqueued: its sparse rows are stored compact
+    // classes of dtl_partition_kernel: table [0] without compact rows (two sparse tiers + dense), table [1] with
+    // (bins of path-set sizes grouped into the tiers of dtl_wave_thread_kernel + dense); device copies of 1024 bytes
+    uint8_t* d_class_of = nullptr;
+    std::vector<uint8_t> class_table;   // host copy of what d_class_of holds
+    int n_classes[2] = {3, 3};
+    int n_tiers = 0;                 // dtl_wave_thread_kernel launches per wave
+    int tier_maxm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int tier_cls0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // first class of a tier; [n_tiers] = the dense class
     int n_waves = 0, n_launch = 0;
     // wave launch configuration (fixed per upload)
     int spad = 0, wave_warps = 0;
@@ -1090,18 +1098,23 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
 #define SPARSE_ROW_WORDS(MAXM) ((MAXM) == 38 ? 232 : 344)
 
 // 4 lanes per row, one uint4 (128 root-path bits) per lane and child: 64 rows per CTA in flight.
-// Classes: 0 = at most max_small path species, 1 = at most max_sparse, 2 = the others ("dense");
+// class_of[size of the path set] = the row's class; the last class holds the "dense" rows (flat2).  Without
+// compact rows: 0 / 1 = the two tiers of dtl_wave_sparse_kernel.  With compact rows (dtl_wave_thread_kernel)
+// the classes below the last are narrow bins of path-set sizes, so that the 32 rows of a warp of that kernel
+// have sets of nearly the same size; rows of at most compact_max species are stored compact.
 // lists[cls * list_pitch + i], counts[cls].
+#define DTL_MAX_CLASSES 32
 __global__ void __launch_bounds__(256)
 dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                      int64_t row_begin, int64_t chunk_row0, int n_rows, uint32_t* __restrict__ rowmask,
-                     int max_small, int max_sparse, int* __restrict__ lists, int list_pitch, int* __restrict__ counts,
-                     int cherry_rows, uint8_t* __restrict__ row_cnt, uint4* __restrict__ row_info) {
-    __shared__ int cta_cnt[3], cta_base[3];
+                     const uint8_t* __restrict__ class_of, int compact_max, int* __restrict__ lists, int list_pitch,
+                     int* __restrict__ counts, int cherry_rows, uint8_t* __restrict__ row_cnt,
+                     uint4* __restrict__ row_info) {
+    __shared__ int cta_cnt[DTL_MAX_CLASSES], cta_base[DTL_MAX_CLASSES];
     const int sub = threadIdx.x & 3;
     const int local = blockIdx.x * 64 + (threadIdx.x >> 2);
     const int ms = sp.mask_stride, quads = ms >> 2;
-    if (threadIdx.x < 3) cta_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < DTL_MAX_CLASSES) cta_cnt[threadIdx.x] = 0;
     __syncthreads();
     int cls = -1, my_off = 0, cnt = 0;
     const bool valid = local < n_rows;
@@ -1153,13 +1166,14 @@ dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 1);
     cnt += __shfl_xor_sync(0xffffffffu, cnt, 2);
     if (valid) {
-        cls = cnt <= max_small ? 0 : (cnt <= max_sparse ? 1 : 2);
+        cls = (int)class_of[min(cnt, sp.S)];
         if (sub == 0) my_off = atomicAdd(&cta_cnt[cls], 1);
         // compact rows (dtl_wave_thread_kernel): the size of the row's path set; 0 = a dense row
-        if (sub == 0 && row_cnt) row_cnt[row_begin + local - chunk_row0] = (uint8_t)(cls < 2 ? cnt : 0);
+        if (sub == 0 && row_cnt) row_cnt[row_begin + local - chunk_row0] = (uint8_t)(cnt <= compact_max ? cnt : 0);
     }
     __syncthreads();
-    if (threadIdx.x < 3) cta_base[threadIdx.x] = cta_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], cta_cnt[threadIdx.x]) : 0;
+    if (threadIdx.x < DTL_MAX_CLASSES)
+        cta_base[threadIdx.x] = cta_cnt[threadIdx.x] ? atomicAdd(&counts[threadIdx.x], cta_cnt[threadIdx.x]) : 0;
     __syncthreads();
     if (cls >= 0 && sub == 0) lists[(size_t)cls * list_pitch + cta_base[cls] + my_off] = local;
 }
@@ -1469,19 +1483,27 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 // (8 x 32 values, 8 x 32 tags), the rows' table offsets (32 x 2 words) and sizes (32)
 #define THREAD_SMEM_WORDS(MAXM) ((3 * (MAXM) + 2) * THREAD_ROWS + (THREAD_ROWS / 32) * (512 + 96))
 
-template <int MAXM>
+// The rows of this launch: the classes [cls0, cls0 + n_cls) of the wave's lists, one after the other (a "tier":
+// the classes whose sets have at most maxm species); the shared memory of the launch is sized for maxm.
 __global__ void __launch_bounds__(THREAD_ROWS)
 dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                        int64_t row_begin, int64_t chunk_row0, int32_t* __restrict__ T, uint32_t* __restrict__ tags,
-                       DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask, const int* __restrict__ row_list,
-                       const int* __restrict__ list_count, int cherry_end, const uint8_t* __restrict__ row_cnt,
-                       const uint4* __restrict__ row_info) {
+                       DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask, const int* __restrict__ lists,
+                       int list_pitch, const int* __restrict__ counts, int cls0, int n_cls, int MAXM, int cherry_end,
+                       const uint8_t* __restrict__ row_cnt, const uint4* __restrict__ row_info) {
     extern __shared__ __align__(16) uint32_t th_smem[];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int n_list = *list_count;
     const int idx = blockIdx.x * THREAD_ROWS + t;
-    if (idx - lane >= n_list) return;  // the whole warp is beyond the list
+    // the class this thread's list position falls into
+    int n_list = 0, my_cls = -1, my_off = 0;
+    for (int b = 0; b < n_cls; ++b) {
+        const int c = counts[cls0 + b];
+        if (idx >= n_list && idx < n_list + c) my_cls = cls0 + b, my_off = idx - n_list;
+        n_list += c;
+    }
+    if (idx - lane >= n_list) return;  // the whole warp is beyond the lists
     const bool valid = idx < n_list;
+    const int* __restrict__ row_list = lists + (size_t)(valid ? my_cls : 0) * list_pitch + my_off;
     const int pitch = sp.pitch, ms = sp.mask_stride;
     uint2* Mc = reinterpret_cast<uint2*>(th_smem) + t;            // Mc[e * THREAD_ROWS]
     uint32_t* el = th_smem + 2 * (MAXM + 1) * THREAD_ROWS + t;    // el[e * THREAD_ROWS]
@@ -1500,7 +1522,7 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     // depths of the leaf species a, b and of lca(a, b) per side, preorder times of the four species
     int l_da = 0, l_db = 0, l_dl = 0, r_da = 0, r_db = 0, r_dl = 0;
     if (valid) {
-        slot = (size_t)(row_begin - chunk_row0) + (size_t)row_list[idx];
+        slot = (size_t)(row_begin - chunk_row0) + (size_t)row_list[0];
         const uint4 il = row_info[slot * 2], ir = row_info[slot * 2 + 1];
         const uint4* m4 = reinterpret_cast<const uint4*>(rowmask + slot * ms);
         for (int q = 0; q < (ms >> 2); ++q) {
@@ -2043,6 +2065,43 @@ int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64
     return SR2_OK;
 }
 
+// Tiers of dtl_wave_thread_kernel and the classes of dtl_partition_kernel (DtlProblem::tier_*, n_classes);
+// `table` (2 x 1024 bytes: class of a path-set size without / with compact rows) is filled when given.
+static void dtl_thread_tiers(DtlProblem* p, std::vector<uint8_t>* table) {
+    int tiers[8] = {28, 38, 48, 64}, nt = 4;
+    if (const char* tv = getenv("SR2_THREAD_TIERS")) {
+        nt = 0;
+        for (const char* q = tv; *q && nt < 8;) {
+            tiers[nt++] = std::max(1, std::min(64, atoi(q)));
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (nt == 0) tiers[nt++] = 64;
+    }
+    std::sort(tiers, tiers + nt);
+    nt = (int)(std::unique(tiers, tiers + nt) - tiers);
+    int cls = 0, k = 0;
+    p->n_tiers = nt;
+    p->tier_cls0[0] = 0;
+    for (int m = 0; m < 1024; ++m) {
+        if (table)
+            (*table)[m] = (uint8_t)(p->sparse_maxm <= 0 ? 2 : (m <= p->sparse_small ? 0 : (m <= p->sparse_maxm ? 1 : 2)));
+        if (k >= nt) {
+            if (table) (*table)[1024 + m] = (uint8_t)p->tier_cls0[nt];
+            continue;
+        }
+        if (table) (*table)[1024 + m] = (uint8_t)cls;
+        if (m == tiers[k]) {
+            p->tier_maxm[k] = tiers[k];
+            p->tier_cls0[++k] = ++cls;
+        } else if (m >= 16 && (m <= 40 ? m % 2 == 0 : m % 4 == 0) && cls + (nt - k) + 2 < DTL_MAX_CLASSES) {
+            ++cls;
+        }
+    }
+    p->n_classes[0] = 3;
+    p->n_classes[1] = p->tier_cls0[nt] + 1;
+}
+
 // Everything of an upload that needs the plan of the batch (chunks, sizes) but not its rows:
 // cost range check, table buffers.  Runs as the on_plan hook of sr2_build_rows.
 static int dtl_prepare(void* user) {
@@ -2080,9 +2139,10 @@ static int dtl_prepare(void* user) {
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_ROWINFO, (table_elems / ctx->pitch) * 2 * sizeof(uint4) + 256, &ptr))) return rc;
     p->d_rowinfo = (uint4*)ptr;
     p->list_pitch = std::max<int64_t>(p->rows.R, 1);
-    if ((rc = sr2_dev_reserve(ctx, DP_DTL_LISTS, (size_t)3 * p->list_pitch * sizeof(int), &ptr))) return rc;
+    dtl_thread_tiers(p, nullptr);
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_LISTS, (size_t)std::max(p->n_classes[0], p->n_classes[1]) * p->list_pitch * sizeof(int), &ptr))) return rc;
     p->d_lists = (int*)ptr;
-    if ((rc = sr2_dev_reserve(ctx, DP_DTL_COUNTS, p->rows.chunks.size() * 4 * 65536 * sizeof(int), &ptr))) return rc;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_COUNTS, p->rows.chunks.size() * DTL_MAX_CLASSES * 65536 * sizeof(int), &ptr))) return rc;
     p->d_counts = (int*)ptr;
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_CHAIN, (size_t)2 * (std::max<int64_t>(p->rows.max_chunk_rows, 1) + 1) * sizeof(int), &ptr)))
         return rc;
@@ -2134,7 +2194,7 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     }
     // buffers this context already holds are reused, so they count as available
     for (int id : {DP_ROWS_SLAB, DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MAP, DP_DTL_MASK}) free_b += sr2_dev_pooled(ctx, id);
-    size_t per_row = (size_t)ctx->pitch * (p->need_decoded_cost ? 12 : 8) + ctx->pitch / 8 + 16 + 12;  // tables, path set, lists and flags
+    size_t per_row = (size_t)ctx->pitch * (p->need_decoded_cost ? 12 : 8) + ctx->pitch / 8 + 16 + 4 * DTL_MAX_CLASSES + 40;  // tables, path set, lists, records and flags
     size_t fixed = (size_t)N * 4 * 7 + (size_t)B * 32 + (64u << 20);
     if (free_b < fixed + per_row * 4)
         return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: batch does not fit in device memory");
@@ -2302,14 +2362,26 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
             // a thread per sparse row (dtl_wave_thread_kernel) when species and depth fit its element word
             p->sparse_thread = p->rank_bits <= 9 && p->depth_bits <= 5 && ctx->dsp.lca_depth && ctx->dsp.span4;
             if (const char* th = getenv("SR2_SPARSE_THREAD")) p->sparse_thread = p->sparse_thread && th[0] != '0';
-            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<SPARSE_MAXM_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               4 * THREAD_SMEM_WORDS(SPARSE_MAXM_SMALL)));
-            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<SPARSE_MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               4 * THREAD_SMEM_WORDS(SPARSE_MAXM)));
-            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<SPARSE_MAXM_SMALL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<SPARSE_MAXM>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             if (const char* sm = getenv("SR2_SPARSE_SMALL")) p->sparse_small = std::min(atoi(sm), SPARSE_MAXM_SMALL);
             if (const char* sm = getenv("SR2_SPARSE_MAXM")) p->sparse_maxm = std::min(atoi(sm), SPARSE_MAXM);
+            // Tiers of the thread kernel: path-set limits, one launch (and shared-memory size) each, at most 64
+            // species (6-bit positions).  Classes of the partition = bins of path-set sizes (width 2 up to 40
+            // species, 4 above) cut at the tier limits; the class after the last tier is the dense one.
+            {
+                std::vector<uint8_t> table(2048, 0);
+                dtl_thread_tiers(p, &table);
+                void* ptr = nullptr;
+                int rc = sr2_dev_reserve(ctx, DP_DTL_CLASSES, table.size(), &ptr);
+                if (rc) return rc;
+                if (p->d_class_of != (uint8_t*)ptr || p->class_table != table) {  // (every solve configures: upload once)
+                    p->d_class_of = (uint8_t*)ptr;
+                    p->class_table = table;
+                    SR2_CUDA(ctx, cudaMemcpyAsync(p->d_class_of, p->class_table.data(), table.size(), cudaMemcpyHostToDevice, ctx->stream));
+                }
+                SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   4 * THREAD_SMEM_WORDS(64)));
+                SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            }
             const int resident = 8 * 4 * ctx->sm_count;  // rows of the CTAs that run at one time
             p->flat2_pf_near = resident;
             p->flat2_pf_far = 3 * resident;
@@ -2358,19 +2430,20 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         kp.thresh = p->flat2_thresh;
         // path sets + the wave's sparse / dense row lists, then one launch per list (grids sized for
         // the whole wave: CTAs beyond a list's length return at once)
-        int* counts = p->d_counts + ((size_t)p->cur_chunk * 65536 + h) * 4;
+        int* counts = p->d_counts + ((size_t)p->cur_chunk * 65536 + h) * DTL_MAX_CLASSES;
         int* lists = p->d_lists + row_begin;
         if (p->cur_part_event) SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, p->cur_part_event, 0));
         // the dense list runs next to the sparse one on a stream of its own (both depend on the
         // previous wave only): the tail of one launch overlaps the other
-        cudaStream_t ds = p->cur_stream, ts = p->cur_stream;
-        cudaEvent_t join = nullptr, join_tier = nullptr;
+        cudaStream_t ds = p->cur_stream, ts[8];
+        cudaEvent_t join = nullptr, join_tier[8];
+        for (int k = 0; k < 8; ++k) ts[k] = p->cur_stream, join_tier[k] = nullptr;
+        const int n_sparse = p->sparse_maxm <= 0 ? 0 : (p->cur_compact ? p->n_tiers : (p->sparse_small > 0 ? 2 : 1));
         if (p->split_waves && p->sparse_maxm > 0) {
             const int set = p->cur_set;
             if (!ctx->dense_stream[set]) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->dense_stream[set], cudaStreamNonBlocking));
-            if (!ctx->tier_stream[set]) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->tier_stream[set], cudaStreamNonBlocking));
             auto& pool = ctx->split_events[set];
-            while (pool.size() < ctx->split_used[set] + 3) {
+            while (pool.size() < ctx->split_used[set] + 10) {
                 cudaEvent_t e;
                 SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
                 pool.push_back(e);
@@ -2380,24 +2453,29 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             ds = ctx->dense_stream[set];
             SR2_CUDA(ctx, cudaEventRecord(fork, p->cur_stream));  // the previous wave (and the lists) are done
             SR2_CUDA(ctx, cudaStreamWaitEvent(ds, fork, 0));
-            if (p->split_tiers && p->sparse_small > 0) {  // the second sparse tier on a stream of its own as well
-                join_tier = pool[ctx->split_used[set]++];
-                ts = ctx->tier_stream[set];
-                SR2_CUDA(ctx, cudaStreamWaitEvent(ts, fork, 0));
+            if (p->split_tiers) {  // the sparse tiers after the first on streams of their own as well
+                for (int k = 1; k < n_sparse; ++k) {
+                    cudaStream_t& tk = ctx->tier_streams[set][k - 1];
+                    if (!tk) SR2_CUDA(ctx, cudaStreamCreateWithFlags(&tk, cudaStreamNonBlocking));
+                    join_tier[k] = pool[ctx->split_used[set]++];
+                    ts[k] = tk;
+                    SR2_CUDA(ctx, cudaStreamWaitEvent(tk, fork, 0));
+                }
             }
         }
-        if (p->sparse_maxm > 0 && p->cur_compact) {  // the two sparse tiers, a thread per row, compact rows
+        int dense_cls = 2;
+        if (p->sparse_maxm > 0 && p->cur_compact) {  // the sparse rows, a thread per row, compact rows: one launch per tier
+            // (grids sized for the whole wave: the warps beyond a tier's lists return at once)
             const unsigned ctas = (unsigned)((n_rows + THREAD_ROWS - 1) / THREAD_ROWS);
-            if (p->sparse_small > 0) {
+            for (int k = 0; k < p->n_tiers; ++k) {
                 ++p->n_launch;
-                dtl_wave_thread_kernel<SPARSE_MAXM_SMALL><<<ctas, THREAD_ROWS, 4 * THREAD_SMEM_WORDS(SPARSE_MAXM_SMALL), p->cur_stream>>>(
+                dtl_wave_thread_kernel<<<ctas, THREAD_ROWS, 4 * THREAD_SMEM_WORDS(p->tier_maxm[k]), ts[k]>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
-                    p->cur_mask, lists, counts, p->cur_cherry_end, p->cur_rowcnt, p->cur_rowinfo);
+                    p->cur_mask, lists, (int)p->list_pitch, counts, p->tier_cls0[k], p->tier_cls0[k + 1] - p->tier_cls0[k],
+                    p->tier_maxm[k], p->cur_cherry_end, p->cur_rowcnt, p->cur_rowinfo);
             }
-            ++p->n_launch;
-            dtl_wave_thread_kernel<SPARSE_MAXM><<<ctas, THREAD_ROWS, 4 * THREAD_SMEM_WORDS(SPARSE_MAXM), ts>>>(
-                ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
-                p->cur_mask, lists + p->list_pitch, counts + 1, p->cur_cherry_end, p->cur_rowcnt, p->cur_rowinfo);
+            --p->n_launch;  // (the caller counts one launch for this wave)
+            dense_cls = p->tier_cls0[p->n_tiers];
         } else if (p->sparse_maxm > 0) {  // the two sparse tiers (the caller counts one launch for this wave)
             if (p->sparse_small > 0) {
                 ++p->n_launch;
@@ -2408,7 +2486,7 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             }
             ++p->n_launch;
             dtl_wave_sparse_kernel<SPARSE_MAXM><<<(unsigned)((n_rows + 31) / 32), 128,
-                                                  4 * 8 * SPARSE_ROW_WORDS(SPARSE_MAXM) * sizeof(uint32_t), ts>>>(
+                                                  4 * 8 * SPARSE_ROW_WORDS(SPARSE_MAXM) * sizeof(uint32_t), ts[p->sparse_small > 0 ? 1 : 0]>>>(
                 ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
                 p->cur_mask, lists + p->list_pitch, counts + 1, p->sparse_pf_near * 5 / 4, p->sparse_pf_far * 5 / 4, p->cur_cherry_end);
         }
@@ -2417,16 +2495,17 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         if (h <= p->flat2_low_waves) dense_ctas = std::max<int64_t>((dense_ctas + 7) / 8, std::min<int64_t>(dense_ctas, 4 * ctx->sm_count));
         p->flat2_fn<<<(unsigned)dense_ctas, 32 * p->flat2_rows, p->flat2_smem, ds>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
-            p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + 2 * p->list_pitch, counts + 2,
-            nullptr, p->cur_cherry_end, p->cur_compact ? p->cur_rowcnt : nullptr);
+            p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + (size_t)dense_cls * p->list_pitch,
+            counts + dense_cls, nullptr, p->cur_cherry_end, p->cur_compact ? p->cur_rowcnt : nullptr);
         if (join) {
             SR2_CUDA(ctx, cudaEventRecord(join, ds));
             SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, join, 0));
         }
-        if (join_tier) {
-            SR2_CUDA(ctx, cudaEventRecord(join_tier, ts));
-            SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, join_tier, 0));
-        }
+        for (int k = 1; k < 8; ++k)
+            if (join_tier[k]) {
+                SR2_CUDA(ctx, cudaEventRecord(join_tier[k], ts[k]));
+                SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, join_tier[k], 0));
+            }
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
     }
@@ -2545,7 +2624,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         if (ci >= (p->two_streams ? 2 : 1)) SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->dtl_ev_done[ci - (p->two_streams ? 2 : 1)], 0));
         SR2_CUDA(ctx, cudaEventRecord(ctx->dtl_ev_w0[ci], st));   // also orders the side stream after earlier
         SR2_CUDA(ctx, cudaStreamWaitEvent(ps, ctx->dtl_ev_w0[ci], 0));  // work of this stream (uploads, solves)
-        SR2_CUDA(ctx, cudaMemsetAsync(p->d_counts + (size_t)ci * 4 * 65536, 0, (size_t)4 * (H + 2) * sizeof(int), ps));
+        SR2_CUDA(ctx, cudaMemsetAsync(p->d_counts + (size_t)ci * DTL_MAX_CLASSES * 65536, 0, (size_t)DTL_MAX_CLASSES * (H + 2) * sizeof(int), ps));
         // rows of waves that are not listed (the chained top waves) are dense
         if (p->cur_compact) SR2_CUDA(ctx, cudaMemsetAsync(p->cur_rowcnt, 0, (size_t)(c.row_end - c.row_begin), ps));
     }
@@ -2564,8 +2643,9 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
             if (listed) {
                 dtl_partition_kernel<<<(unsigned)((n + 63) / 64), 256, 0, ps>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask,
-                    p->sparse_maxm > 0 ? p->sparse_small : 0, p->sparse_maxm, p->d_lists + c.wave_off[h], (int)p->list_pitch,
-                    p->d_counts + ((size_t)ci * 65536 + h) * 4, cherry_rows, p->cur_compact ? p->cur_rowcnt : nullptr,
+                    p->d_class_of + (p->cur_compact ? 1024 : 0), p->cur_compact ? p->tier_maxm[p->n_tiers - 1] : 0,
+                    p->d_lists + c.wave_off[h], (int)p->list_pitch,
+                    p->d_counts + ((size_t)ci * 65536 + h) * DTL_MAX_CLASSES, cherry_rows, p->cur_compact ? p->cur_rowcnt : nullptr,
                     p->cur_compact ? p->cur_rowinfo : nullptr);
                 if (part_events.size() <= events_used) {
                     cudaEvent_t e;

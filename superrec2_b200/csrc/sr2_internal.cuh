@@ -135,7 +135,7 @@ struct Sr2Pool {
 };
 enum Sr2DevPool {
     DP_ROWS_SLAB, DP_ROOT_ROW, DP_ROOT_NODE, DP_NODE_PRE, DP_NODE_INST,
-    DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MINCOST, DP_DTL_ROOTSP, DP_DTL_MAP, DP_DTL_MASK, DP_DTL_LISTS, DP_DTL_COUNTS, DP_DTL_CHAIN, DP_DTL_ROWCNT, DP_DTL_ROWINFO,
+    DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MINCOST, DP_DTL_ROOTSP, DP_DTL_MAP, DP_DTL_MASK, DP_DTL_LISTS, DP_DTL_COUNTS, DP_DTL_CHAIN, DP_DTL_ROWCNT, DP_DTL_ROWINFO, DP_DTL_CLASSES,
     DP_S_LEFT, DP_S_RIGHT, DP_S_NODEOFF, DP_S_BITS, DP_S_PRESENT, DP_S_OUTSIDE, DP_S_GAIN, DP_S_L, DP_S_FLAGS,
     DP_S_T, DP_S_TAG, DP_S_DEC, DP_S_ANC, DP_S_TAU, DP_S_TAUMIN, DP_S_COST, DP_S_MINCOST, DP_S_ROOTSP, DP_S_MAP,
     DP_S_KIND, DP_S_SYN, DP_S_BEST, DP_S_ALLOWED, DP_S_EV, DP_S_CHAIN,
@@ -155,7 +155,7 @@ struct sr2_ctx {
     cudaStream_t fill_stream = nullptr;    // device-side bucketing, second phase (lazy)
     cudaStream_t part_stream[2] = {nullptr, nullptr};  // path sets / row lists of the waves, ahead of the waves
     cudaStream_t dense_stream[2] = {nullptr, nullptr}; // the dense rows of a wave, next to its sparse rows
-    cudaStream_t tier_stream[2] = {nullptr, nullptr};  // the second sparse tier of a wave (SR2_DTL_SPLIT_TIERS)
+    cudaStream_t tier_streams[2][8] = {};              // the sparse tiers of a wave after the first (SR2_DTL_SPLIT_TIERS)
     std::vector<cudaEvent_t> split_events[2];
     size_t split_used[2] = {0, 0};
     std::vector<cudaEvent_t> part_events[2];           // "lists of wave k are ready", per table set
