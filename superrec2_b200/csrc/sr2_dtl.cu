@@ -95,6 +95,7 @@ struct DtlProblem {
     std::vector<uint8_t> class_table;   // host copy of what d_class_of holds
     int n_classes[2] = {3, 3};
     int n_tiers = 0;                 // dtl_wave_thread_kernel launches per wave
+    int compact_max = 0;             // listed rows with at most this many path species are stored compact
     int tier_maxm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int tier_cls0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // first class of a tier; [n_tiers] = the dense class
     int n_waves = 0, n_launch = 0;
@@ -119,11 +120,11 @@ struct DtlProblem {
     int flat2_low_waves = 5;     // waves up to this height launch an eighth of the dense-list CTAs (measured: 0 / 4 / 6 / 99 -> 6.70 / 6.59 / 6.59 / 6.66 ms)
     int flat2_sh = 0, flat2_thresh = 0;
     void (*flat2_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
-                     Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int, const uint8_t*) = nullptr;
+                     Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int, const uint8_t*, int) = nullptr;
     // The small top waves of a chunk run as ONE launch (flat2, chained): a row starts when the "done"
     // flags of its child rows are up, instead of one latency-bound launch per wave.
     void (*flat2_chain_fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*, DtlCosts,
-                           Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int, const uint8_t*) = nullptr;
+                           Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int, const uint8_t*, int) = nullptr;
     int cur_cherry_end = 0;          // chunk being enqueued: its wave-1 rows [0, cherry_end) are virtual (0 = materialised)
     size_t trace_smem_set = 0;       // dynamic shared memory opted in for dtl_select_trace_kernel
     int64_t chain_rows = 0;          // waves with fewer rows than this join the chained launch (0 = off)
@@ -819,7 +820,7 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
                       uint32_t* __restrict__ tags, DtlCosts cs, Key32 kp, const uint32_t* __restrict__ rowmask,
                       int sparse_max, int pf_near, int pf_far, const int* __restrict__ row_list,
                       const int* __restrict__ list_count, int* __restrict__ chain_sync, int cherry_end,
-                      const uint8_t* __restrict__ row_cnt) {
+                      const uint8_t* __restrict__ row_cnt, int compact_max) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int cta_ticket;
     const int pitch = sp.pitch, rs = sp.flat_rs, n_chunks = pitch >> 5;
@@ -995,8 +996,9 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
     const int loss = cs.loss, db = kp.db, thresh = kp.thresh;
     const unsigned dm = kp.dm, rm = kp.rm, hi_mul = 1u << (32 - kp.sh);
     const int c12 = -2 * loss, c3 = cs.dup, c45 = cs.hgt;
-    // one cell: species x, its word (child pair offset << 16 | depth); writes value and tag
-    auto cell = [&](int x, unsigned mx) {
+    // one cell: species x, its word (child pair offset << 16 | depth); writes value and tag at entry `out` of the
+    // row: the species itself, or, for a compact row, the position of x in the path set (value | x << 22)
+    auto cell = [&](int x, unsigned mx, int out, bool compact) {
         const uint2 m = M[x], pq = P[x];
         const uint4 k = *reinterpret_cast<const uint4*>(Mbytes + (mx >> 16));  // (l0, r0, l1, r1)
         const int nld = -loss * (int)(mx & 0xffffu);
@@ -1020,8 +1022,8 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
         kb = which == 1 ? k.y : kb;
         kb = which == 4 ? pq.y : kb;
         const bool finite = best < thresh;
-        Trow[x] = finite ? best : SR2_INF;
-        Grow[x] = finite ? (((ka >> db) & rm) | (((kb >> db) & rm) << 16)) : SR2_NO_TAG;
+        Trow[out] = compact ? (int)((finite ? (unsigned)best : TH_VAL_MASK) | ((unsigned)x << TH_VAL_BITS)) : (finite ? best : SR2_INF);
+        Grow[out] = finite ? (((ka >> db) & rm) | (((kb >> db) & rm) << 16)) : SR2_NO_TAG;
     };
     // A cell can only be finite on the root path of a leaf species below the object node.  Rows whose
     // path set is small (most rows: low in the object trees) write the infinite row with 128-bit
@@ -1035,11 +1037,18 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
         if (lane >= o) incl += up;
     }
     const int m_set = __shfl_sync(0xffffffffu, incl, 31);
-    if (m_set <= sparse_max) {
-        uint4* __restrict__ row4 = reinterpret_cast<uint4*>(Trow);
-        const uint4 inf4 = make_uint4(SR2_INF, SR2_INF, SR2_INF, SR2_INF);
-        for (int i = lane; i < (pitch >> 2); i += 32) row4[i] = inf4;
-        __syncwarp();
+    // With compact rows (dtl_partition_kernel set row_cnt[slot] = m for the rows of its lists with m <= compact_max)
+    // the row is just its m entries in BFS order, written by consecutive lanes: no infinite row, no scattered
+    // 4-byte stores.
+    const bool compact = !CHAIN && m_set <= compact_max;
+    SR2_DCHECK(!row_cnt || CHAIN || (int)row_cnt[slot] == (compact ? m_set : 0));
+    if (m_set <= sparse_max || compact) {
+        if (!compact) {
+            uint4* __restrict__ row4 = reinterpret_cast<uint4*>(Trow);
+            const uint4 inf4 = make_uint4(SR2_INF, SR2_INF, SR2_INF, SR2_INF);
+            for (int i = lane; i < (pitch >> 2); i += 32) row4[i] = inf4;
+            __syncwarp();
+        }
         const int excl = incl - cnt;
         for (int i0 = 0; i0 < m_set; i0 += 32) {
             const int i = min(i0 + lane, m_set - 1);
@@ -1052,7 +1061,7 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
             const unsigned word = __shfl_sync(0xffffffffu, mword, w);
             const int before = __shfl_sync(0xffffffffu, excl, w);
             const int x = w * 32 + (int)__fns(word, 0, i - before + 1);
-            if (i0 + lane < m_set) cell(x, __ldg(sp.cmeta + x));
+            if (i0 + lane < m_set) cell(x, __ldg(sp.cmeta + x), compact ? i0 + lane : x, compact);
         }
     } else {
         // per-species words of the cells this lane evaluates
@@ -1061,7 +1070,7 @@ dtl_wave_flat2_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const i
         for (int j = 0; j < FLAT2_NCH; ++j) meta[j] = j < n_chunks ? __ldg(sp.cmeta + j * 32 + lane) : 0u;
 #pragma unroll
         for (int j = 0; j < FLAT2_NCH; ++j)
-            if (j < n_chunks) cell(j * 32 + lane, meta[j]);
+            if (j < n_chunks) cell(j * 32 + lane, meta[j], j * 32 + lane, false);
     }
     if (CHAIN) {  // the row (values and tags of every lane) is visible before its flag
         __threadfence();
@@ -1754,7 +1763,7 @@ __global__ void dtl_rowmask_kernel(DevSpecies sp, const int32_t* __restrict__ ro
 
 // the instantiation whose register-resident schedule is the shortest that holds n_steps
 typedef void (*Flat2Fn)(DevSpecies, const int32_t*, const int32_t*, int64_t, int64_t, int, int32_t*, uint32_t*,
-                        DtlCosts, Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int, const uint8_t*);
+                        DtlCosts, Key32, const uint32_t*, int, int, int, const int*, const int*, int*, int, const uint8_t*, int);
 template <bool CHAIN>
 static Flat2Fn flat2_pick(int n_steps) {
     if (n_steps <= 12) return dtl_wave_flat2_kernel<12, CHAIN>;
@@ -2381,6 +2390,9 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
                 SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                    4 * THREAD_SMEM_WORDS(64)));
                 SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                // compact rows: everything the thread kernel writes, and the rows of flat2's sparse cells pass (row_cnt is a byte)
+                p->compact_max = std::max(p->tier_maxm[p->n_tiers - 1], std::min(p->flat2_sparse_max, 255));
+                if (const char* cm = getenv("SR2_COMPACT_MAX")) p->compact_max = std::max(p->tier_maxm[p->n_tiers - 1], std::min(atoi(cm), 255));
             }
             const int resident = 8 * 4 * ctx->sm_count;  // rows of the CTAs that run at one time
             p->flat2_pf_near = resident;
@@ -2496,7 +2508,8 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
         p->flat2_fn<<<(unsigned)dense_ctas, 32 * p->flat2_rows, p->flat2_smem, ds>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, (int)n_rows, p->cur_T, p->cur_tag, cs, kp,
             p->cur_mask, p->flat2_sparse_max, p->flat2_pf_near, p->flat2_pf_far, lists + (size_t)dense_cls * p->list_pitch,
-            counts + dense_cls, nullptr, p->cur_cherry_end, p->cur_compact ? p->cur_rowcnt : nullptr);
+            counts + dense_cls, nullptr, p->cur_cherry_end, p->cur_compact ? p->cur_rowcnt : nullptr,
+            p->cur_compact ? p->compact_max : 0);
         if (join) {
             SR2_CUDA(ctx, cudaEventRecord(join, ds));
             SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, join, 0));
@@ -2643,7 +2656,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
             if (listed) {
                 dtl_partition_kernel<<<(unsigned)((n + 63) / 64), 256, 0, ps>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, c.wave_off[h], c.row_begin, (int)n, p->cur_mask,
-                    p->d_class_of + (p->cur_compact ? 1024 : 0), p->cur_compact ? p->tier_maxm[p->n_tiers - 1] : 0,
+                    p->d_class_of + (p->cur_compact ? 1024 : 0), p->cur_compact ? p->compact_max : 0,
                     p->d_lists + c.wave_off[h], (int)p->list_pitch,
                     p->d_counts + ((size_t)ci * 65536 + h) * DTL_MAX_CLASSES, cherry_rows, p->cur_compact ? p->cur_rowcnt : nullptr,
                     p->cur_compact ? p->cur_rowinfo : nullptr);
@@ -2730,7 +2743,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         p->flat2_chain_fn<<<(unsigned)((n + p->flat2_rows - 1) / p->flat2_rows), 32 * p->flat2_rows, p->flat2_smem, st>>>(
             ctx->dsp, p->rows.row_cl, p->rows.row_cr, first, c.row_begin, (int)n, p->cur_T, p->cur_tag, cs, kp,
             p->cur_mask, p->flat2_sparse_max, 0, 0, nullptr, nullptr, sync, p->cur_cherry_end,
-            p->cur_compact ? p->cur_rowcnt : nullptr);
+            p->cur_compact ? p->cur_rowcnt : nullptr, 0);
         SR2_CUDA(ctx, cudaGetLastError());
         ++p->n_waves;
         ++p->n_launch;
