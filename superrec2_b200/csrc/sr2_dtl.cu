@@ -96,6 +96,8 @@ struct DtlProblem {
     int n_classes[2] = {3, 3};
     int n_tiers = 0;                 // dtl_wave_thread_kernel launches per wave
     int compact_max = 0;             // listed rows with at most this many path species are stored compact
+    bool decouple_dense = true;      // the dense rows of a wave are not waited for by the sparse rows of the next
+    cudaEvent_t pending_dense = nullptr;   // last dense launch the chunk's stream has not joined yet
     int tier_maxm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int tier_cls0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};   // first class of a tier; [n_tiers] = the dense class
     int n_waves = 0, n_launch = 0;
@@ -2392,6 +2394,7 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
                 SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 // compact rows: everything the thread kernel writes, and the rows of flat2's sparse cells pass (row_cnt is a byte)
                 p->compact_max = std::max(p->tier_maxm[p->n_tiers - 1], std::min(p->flat2_sparse_max, 255));
+                if (const char* dd = getenv("SR2_DTL_DECOUPLE_DENSE")) p->decouple_dense = dd[0] != '0';
                 if (const char* cm = getenv("SR2_COMPACT_MAX")) p->compact_max = std::max(p->tier_maxm[p->n_tiers - 1], std::min(atoi(cm), 255));
             }
             const int resident = 8 * 4 * ctx->sm_count;  // rows of the CTAs that run at one time
@@ -2431,6 +2434,10 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             nullptr);
         SR2_CUDA(ctx, cudaGetLastError());
         return SR2_OK;
+    }
+    if (p->pending_dense && !(p->flat2 && n_rows >= p->simd_min_rows)) {
+        SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, p->pending_dense, 0));
+        p->pending_dense = nullptr;
     }
     if (p->flat2 && n_rows >= p->simd_min_rows) {
         Key32 kp;
@@ -2512,7 +2519,12 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             p->cur_compact ? p->compact_max : 0);
         if (join) {
             SR2_CUDA(ctx, cudaEventRecord(join, ds));
-            SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, join, 0));
+            // Compact rows: a row of the thread kernel only ever reads rows of the thread kernel (its children's
+            // path sets are subsets of its own), so the sparse rows of the next wave need not wait for the dense
+            // rows of this one: the dense stream runs as a pipeline of its own behind the sparse one (it waits for
+            // each wave's fork event) and joins before anything else reads the tables.
+            if (p->cur_compact && p->decouple_dense) p->pending_dense = join;
+            else SR2_CUDA(ctx, cudaStreamWaitEvent(p->cur_stream, join, 0));
         }
         for (int k = 1; k < 8; ++k)
             if (join_tier[k]) {
@@ -2581,6 +2593,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     p->cur_rowinfo = p->d_rowinfo + set * (table_elems / ctx->pitch) * 2;
     p->cur_chunk = ci;
     p->cur_set = set;
+    p->pending_dense = nullptr;
     ctx->split_used[set] = 0;  // (re-recording an event does not disturb waits already enqueued on it)
     cudaStream_t st = p->cur_stream;
     const RowChunk& c = p->rows.chunks[ci];
@@ -2698,6 +2711,10 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
         if (rc) return rc;
         ++p->n_waves;
         ++p->n_launch;
+    }
+    if (p->pending_dense) {  // the dense pipeline joins the chunk's stream
+        SR2_CUDA(ctx, cudaStreamWaitEvent(st, p->pending_dense, 0));
+        p->pending_dense = nullptr;
     }
     if (chain) {
         // the rest of the side stream (path sets of the chained top waves) joins the chunk's stream
