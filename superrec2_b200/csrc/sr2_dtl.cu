@@ -1482,7 +1482,9 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 #ifndef TH_EXP
 #define TH_EXP 0
 #endif
+#ifndef THREAD_ROWS
 #define THREAD_ROWS 64   // rows (threads) per CTA
+#endif
 #define TH_S_MASK 511u
 #define TH_D_SHIFT 9
 #define TH_PP_SHIFT 14
@@ -1556,23 +1558,38 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         // ---- elements: top-down over the path set ----------------------------------------------------
         el[0] = 0xfu << TH_FLAG_SHIFT;  // the root: species 0, depth 0, on every root path
         m = 1;
+        // (the species word of element p + 1 is requested while element p is worked on: the look-up is a trip to
+        // L2 -- the carve-out leaves little L1 -- and the loop is a dependent chain otherwise)
+        unsigned w_cur = el[0];
+        uint2 span_cur = __ldg(reinterpret_cast<const uint2*>(sp.span4) + 1);  // (child0 + 1) << 16 | depth, tin of the second child
         for (int p = 0; p < m; ++p) {
-            const unsigned w = el[p * THREAD_ROWS];
-            const int s = (int)(w & TH_S_MASK), d = (int)((w >> TH_D_SHIFT) & 31u);
-            const uint4 span = __ldg(sp.span4 + s);  // tin, tout, (child0 + 1) << 16 | depth, tin of the second child
-            const int c0 = (int)(span.z >> 16) - 1;
+            const unsigned w = w_cur;
+            const uint2 span = span_cur;
+            const bool have_next = p + 1 < m;
+            if (have_next) {
+                w_cur = el[(p + 1) * THREAD_ROWS];
+                span_cur = __ldg(reinterpret_cast<const uint2*>(sp.span4 + (w_cur & TH_S_MASK)) + 1);
+            }
+            const int d = (int)((w >> TH_D_SHIFT) & 31u);
+            const int c0 = (int)(span.x >> 16) - 1;
             if (c0 < 0) continue;
             const unsigned b0 = on_path(c0), b1 = on_path(c0 + 1);
             SR2_DCHECK(b0 | b1);                     // root paths end at leaf species
             SR2_DCHECK(m + (int)(b0 + b1) <= MAXM);  // dtl_partition_kernel only lists rows that fit the tier
             el[p * THREAD_ROWS] = w | ((unsigned)m << TH_FC_SHIFT) | (b0 << TH_C0_BIT) | (b1 << TH_C1_BIT);
-            const int split = (int)span.w;
+            const int split = (int)span.y;
             const unsigned first = (unsigned)(t_la < split) | ((unsigned)(t_lb < split) << 1) |
                                    ((unsigned)(t_ra < split) << 2) | ((unsigned)(t_rb < split) << 3);
             const unsigned flags = w >> TH_FLAG_SHIFT;
             const unsigned base = ((unsigned)(d + 1) << TH_D_SHIFT) | ((unsigned)p << TH_PP_SHIFT);
-            if (b0) el[(m++) * THREAD_ROWS] = (unsigned)c0 | base | ((flags & first) << TH_FLAG_SHIFT);
-            if (b1) el[(m++) * THREAD_ROWS] = (unsigned)(c0 + 1) | base | ((flags & ~first) << TH_FLAG_SHIFT);
+            const unsigned w0 = (unsigned)c0 | base | ((flags & first) << TH_FLAG_SHIFT);
+            const unsigned w1 = (unsigned)(c0 + 1) | base | ((flags & ~first) << TH_FLAG_SHIFT);
+            if (b0) el[(m++) * THREAD_ROWS] = w0;
+            if (b1) el[(m++) * THREAD_ROWS] = w1;
+            if (!have_next) {  // the queue held one element: the next one is the child just appended
+                w_cur = b0 ? w0 : w1;
+                span_cur = __ldg(reinterpret_cast<const uint2*>(sp.span4 + (w_cur & TH_S_MASK)) + 1);
+            }
         }
         SR2_DCHECK(m == (int)row_cnt[slot]);
     }
