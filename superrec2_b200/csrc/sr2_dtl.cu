@@ -1574,7 +1574,7 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             const int c0 = (int)(span.x >> 16) - 1;
             if (c0 < 0) continue;
             const unsigned b0 = on_path(c0), b1 = on_path(c0 + 1);
-            SR2_DCHECK(b0 | b1);                     // root paths end at leaf species
+            // (neither child on a path: an object leaf sits at this internal species)
             SR2_DCHECK(m + (int)(b0 + b1) <= MAXM);  // dtl_partition_kernel only lists rows that fit the tier
             el[p * THREAD_ROWS] = w | ((unsigned)m << TH_FC_SHIFT) | (b0 << TH_C0_BIT) | (b1 << TH_C1_BIT);
             const int split = (int)span.y;
