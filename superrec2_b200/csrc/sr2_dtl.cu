@@ -2063,6 +2063,21 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
                 const int k = atomicAdd(&n_list[cur ^ 1], 1);
                 if (k < cap) to[k] = make_int2(cr, c);
             }
+            // what the next level reads first about the two children, pulled towards the SM while this level
+            // finishes: descriptors, and for compact rows the size and the bit set (the entry's position)
+            if (row_cnt) {
+#pragma unroll
+                for (int side = 0; side < 2; ++side) {
+                    const int ch = side ? cr : cl, xs = side ? c : a;
+                    if (ch < 0 || xs < 0) continue;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row_cl + chunk_row0 + ch));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row_cr + chunk_row0 + ch));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row_cnt + ch));
+                    const uint32_t* mk2 = rowmask + (size_t)ch * sp.mask_stride;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(mk2));
+                    if ((xs >> 5) >= 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(mk2 + 8));
+                }
+            }
         }
         __syncthreads();
         if (threadIdx.x == 0) n_list[cur] = 0;
@@ -2228,7 +2243,8 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
         return sr2_fail(ctx, SR2_ERR_NOMEM, "sr2_dtl_upload: batch does not fit in device memory");
     int64_t rows_budget = (int64_t)(((free_b - fixed) / 10 * 9) / per_row);
     int64_t first_chunk_rows = 0;
-    p->two_streams = pipeline_chunks > 1 && !(flags & SR2_KEEP_TABLES) && hooks && hooks->on_chunk;
+    const bool resident_split = !hooks && pipeline_chunks > 1;
+    p->two_streams = pipeline_chunks > 1 && !(flags & SR2_KEEP_TABLES) && ((hooks && hooks->on_chunk) || resident_split);
     if (p->two_streams) rows_budget /= 2;  // two sets of tables
     if (pipeline_chunks > 1 && !(flags & SR2_KEEP_TABLES)) {
         int64_t rows_est = (N - B) / 2;
@@ -2236,7 +2252,7 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
         // a chunk should still fill the machine's big-wave kernels
         per_chunk = std::max<int64_t>(per_chunk, 64 * 8 * (int64_t)ctx->sm_count);
         rows_budget = std::min(rows_budget, per_chunk);
-        int first_div = 2;
+        int first_div = resident_split ? 1 : 2;
         if (const char* fd = getenv("SR2_PIPELINE_FIRST")) first_div = std::max(1, atoi(fd));
         first_chunk_rows = rows_budget / first_div;
     }
@@ -2244,7 +2260,7 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
     plan_only.user = ctx;
     plan_only.on_plan = dtl_prepare;
     // pipelined runs of big batches bucket their rows on the device (one thread per tree)
-    if (p->two_streams && B >= 1024) {
+    if (p->two_streams && B >= 1024 && hooks) {
         const char* dev_rows = getenv("SR2_DEVICE_ROWS");
         if (!(dev_rows && dev_rows[0] == '0')) {
             size_t raw = (size_t)N * 22 + (size_t)B * 520;  // raw arrays, heights, node rows, per-instance bases
@@ -2283,7 +2299,11 @@ static int dtl_upload_impl(sr2_ctx* ctx, int32_t B, const int64_t* node_off, con
 extern "C" int sr2_dtl_upload(sr2_ctx* ctx, int32_t B, const int64_t* node_off,
                               const int32_t* left, const int32_t* right,
                               const int32_t* leaf_species, const int32_t costs[5], uint32_t flags) {
-    return dtl_upload_impl(ctx, B, node_off, left, right, leaf_species, costs, flags, 1, nullptr);
+    // SR2_DTL_SOLVE_CHUNKS=n: a resident batch in n instance chunks that alternate between two streams and table
+    // sets, so that the latency-bound top waves and the traceback of one chunk overlap the big waves of the next
+    int chunks = 1;
+    if (const char* sc = getenv("SR2_DTL_SOLVE_CHUNKS")) chunks = std::max(1, atoi(sc));
+    return dtl_upload_impl(ctx, B, node_off, left, right, leaf_species, costs, flags, chunks, nullptr);
 }
 
 static int dtl_configure_waves(sr2_ctx* ctx, DtlProblem* p) {
@@ -2861,6 +2881,9 @@ extern "C" int sr2_dtl_solve(sr2_ctx* ctx) {
     SR2_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     for (size_t ci = 0; ci < p->rows.chunks.size(); ++ci)
         if ((rc = dtl_enqueue_chunk(ctx, p, (int)ci))) return rc;
+    if (p->two_streams)  // chunks on the second stream
+        for (size_t ci = 1; ci < p->rows.chunks.size(); ci += 2)
+            SR2_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->dtl_ev_done[ci], 0));
     SR2_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     SR2_CUDA(ctx, cudaEventSynchronize(ctx->ev[1]));
     dtl_collect_timing(ctx, p);
