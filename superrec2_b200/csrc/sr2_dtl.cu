@@ -1495,6 +1495,8 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 // shared-memory words of a CTA: Mc [MAXM + 1] pairs and el [MAXM] per thread, and per warp the staging tile
 // (8 x 32 values, 8 x 32 tags), the rows' table offsets (32 x 2 words) and sizes (32)
 #define THREAD_SMEM_WORDS(MAXM) ((3 * (MAXM) + 2) * THREAD_ROWS + (THREAD_ROWS / 32) * (512 + 96))
+// ... plus the species table of the generation, one word per species: (first child + 1) << 16 | preorder time of the second child
+#define THREAD_SMEM_BYTES(MAXM, S) (4 * (size_t)(THREAD_SMEM_WORDS(MAXM) + (((S) + 3) & ~3)))
 
 // The rows of this launch: the classes [cls0, cls0 + n_cls) of the wave's lists, one after the other (a "tier":
 // the classes whose sets have at most maxm species); the shared memory of the launch is sized for maxm.
@@ -1514,10 +1516,28 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         if (idx >= n_list && idx < n_list + c) my_cls = cls0 + b, my_off = idx - n_list;
         n_list += c;
     }
-    if (idx - lane >= n_list) return;  // the whole warp is beyond the lists
+    if (blockIdx.x * THREAD_ROWS >= n_list) return;  // the whole CTA is beyond the lists
     const bool valid = idx < n_list;
-    const int* __restrict__ row_list = lists + (size_t)(valid ? my_cls : 0) * list_pitch + my_off;
     const int pitch = sp.pitch, ms = sp.mask_stride;
+    // the row's record is requested before the species table is staged (one trip to memory instead of two)
+    size_t slot = 0;
+    uint4 il = make_uint4(0u, 0u, 0u, 0u), ir = il;
+    if (valid) {
+        slot = (size_t)(row_begin - chunk_row0) + (size_t)lists[(size_t)my_cls * list_pitch + my_off];
+        il = row_info[slot * 2];
+        ir = row_info[slot * 2 + 1];
+    }
+    // The generation below looks up every path species (first child, preorder time of the second child: which
+    // child a leaf species sits under).  From global memory that is a dependent trip to L2 per element (the
+    // carve-out leaves no L1 to speak of): 27 % of the kernel's stall samples in the r7a capture.  The table is
+    // staged per CTA instead, 4 bytes per species.
+    uint32_t* spt = th_smem + THREAD_SMEM_WORDS(MAXM);
+    for (int y = t; y < sp.S; y += THREAD_ROWS) {
+        const uint2 z = __ldg(reinterpret_cast<const uint2*>(sp.span4 + y) + 1);  // (child0 + 1) << 16 | depth, tin of the second child
+        spt[y] = (z.x & 0xffff0000u) | z.y;
+    }
+    __syncthreads();
+    if (idx - lane >= n_list) return;  // the whole warp is beyond the lists
     uint2* Mc = reinterpret_cast<uint2*>(th_smem) + t;            // Mc[e * THREAD_ROWS]
     uint32_t* el = th_smem + 2 * (MAXM + 1) * THREAD_ROWS + t;    // el[e * THREAD_ROWS]
     uint32_t* stage = th_smem + (3 * MAXM + 2) * THREAD_ROWS + warp * (512 + 96);  // [2][8][32] values, tags
@@ -1527,7 +1547,6 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         const uint2 two = Mc[(sx >> 6) * THREAD_ROWS];
         return (((sx >> 5) & 1 ? two.y : two.x) >> (sx & 31)) & 1u;
     };
-    size_t slot = 0;
     int cl = -1, cr = -1, m = 0;
     // per side: 0 = leaf at species a, 1 = virtual cherry (a, b), 2 = stored (compact) row
     int mode_l = 0, mode_r = 0, m_l = 0, m_r = 0;
@@ -1535,8 +1554,6 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     // depths of the leaf species a, b and of lca(a, b) per side, preorder times of the four species
     int l_da = 0, l_db = 0, l_dl = 0, r_da = 0, r_db = 0, r_dl = 0;
     if (valid) {
-        slot = (size_t)(row_begin - chunk_row0) + (size_t)row_list[0];
-        const uint4 il = row_info[slot * 2], ir = row_info[slot * 2 + 1];
         const uint4* m4 = reinterpret_cast<const uint4*>(rowmask + slot * ms);
         for (int q = 0; q < (ms >> 2); ++q) {
             const uint4 v = m4[q];
@@ -1558,26 +1575,17 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         // ---- elements: top-down over the path set ----------------------------------------------------
         el[0] = 0xfu << TH_FLAG_SHIFT;  // the root: species 0, depth 0, on every root path
         m = 1;
-        // (the species word of element p + 1 is requested while element p is worked on: the look-up is a trip to
-        // L2 -- the carve-out leaves little L1 -- and the loop is a dependent chain otherwise)
-        unsigned w_cur = el[0];
-        uint2 span_cur = __ldg(reinterpret_cast<const uint2*>(sp.span4) + 1);  // (child0 + 1) << 16 | depth, tin of the second child
         for (int p = 0; p < m; ++p) {
-            const unsigned w = w_cur;
-            const uint2 span = span_cur;
-            const bool have_next = p + 1 < m;
-            if (have_next) {
-                w_cur = el[(p + 1) * THREAD_ROWS];
-                span_cur = __ldg(reinterpret_cast<const uint2*>(sp.span4 + (w_cur & TH_S_MASK)) + 1);
-            }
+            const unsigned w = el[p * THREAD_ROWS];
+            const unsigned z = spt[w & TH_S_MASK];
             const int d = (int)((w >> TH_D_SHIFT) & 31u);
-            const int c0 = (int)(span.x >> 16) - 1;
+            const int c0 = (int)(z >> 16) - 1;
             if (c0 < 0) continue;
             const unsigned b0 = on_path(c0), b1 = on_path(c0 + 1);
             // (neither child on a path: an object leaf sits at this internal species)
             SR2_DCHECK(m + (int)(b0 + b1) <= MAXM);  // dtl_partition_kernel only lists rows that fit the tier
             el[p * THREAD_ROWS] = w | ((unsigned)m << TH_FC_SHIFT) | (b0 << TH_C0_BIT) | (b1 << TH_C1_BIT);
-            const int split = (int)span.y;
+            const int split = (int)(z & 0xffffu);
             const unsigned first = (unsigned)(t_la < split) | ((unsigned)(t_lb < split) << 1) |
                                    ((unsigned)(t_ra < split) << 2) | ((unsigned)(t_rb < split) << 3);
             const unsigned flags = w >> TH_FLAG_SHIFT;
@@ -1586,10 +1594,6 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             const unsigned w1 = (unsigned)(c0 + 1) | base | ((flags & ~first) << TH_FLAG_SHIFT);
             if (b0) el[(m++) * THREAD_ROWS] = w0;
             if (b1) el[(m++) * THREAD_ROWS] = w1;
-            if (!have_next) {  // the queue held one element: the next one is the child just appended
-                w_cur = b0 ? w0 : w1;
-                span_cur = __ldg(reinterpret_cast<const uint2*>(sp.span4 + (w_cur & TH_S_MASK)) + 1);
-            }
         }
         SR2_DCHECK(m == (int)row_cnt[slot]);
     }
@@ -1607,64 +1611,65 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         // a compact child: its entries are a subsequence of this row's elements (same order)
         const uint32_t* __restrict__ Tl = reinterpret_cast<const uint32_t*>(T) + (size_t)(mode_l == 2 ? cl : 0) * pitch;
         const uint32_t* __restrict__ Tr = reinterpret_cast<const uint32_t*>(T) + (size_t)(mode_r == 2 ? cr : 0) * pitch;
+        // (the entries of a stored child are requested two matches ahead: the loads are trips to L2 / DRAM)
         int q_l = 0, q_r = 0;
         unsigned next_l = m_l > 0 ? Tl[0] : 0xffffffffu, next_r = m_r > 0 ? Tr[0] : 0xffffffffu;
+        unsigned next2_l = m_l > 1 ? Tl[1] : 0xffffffffu, next2_r = m_r > 1 ? Tr[1] : 0xffffffffu;
         // Closed form of a cherry (a, b) at depth d of a's path: above the lca a duplication, at the lca a
         // speciation when both leaves sit below it, below the lca a transfer of b (if b is below the lca);
-        // on b's path below the lca a transfer of a.  A leaf child is 0 at its own species.  All of it as
-        // selects on per-row constants: the lanes of a warp hold rows of every kind.
+        // on b's path below the lca a transfer of a.  A leaf child is a cherry with a == b whose only finite
+        // cell is the one at the lca (= a), 0.  All of it as selects on per-row constants (the lanes of a warp hold
+        // rows of every kind); BIG stands for an infinite value: anything >= TH_VAL_MASK becomes the infinite key.
+        // A flag says "on a's root path" down to a itself only (a leaf may sit at an internal species, whose
+        // first-child chain inherits the flag): hence the depth tests.  On b's path but not on a's = below the lca.
         const int loss = cs.loss;
+        const unsigned BIG = 0x40000000u;
         struct Side {
-            int k_top, k_lca, k_a, k_b, da, db, dl;
-            bool a_ok, b_ok, leaf, cherry;
+            unsigned k_top, k_lca, k_a, k_b;
+            int dl, da, db;
         };
         auto make_side = [&](int mode, int da, int db_, int dl) {
             Side z;
             const bool a_below = da > dl, b_below = db_ > dl;
-            z.da = da, z.db = db_, z.dl = dl;
-            z.k_top = cs.dup + loss * (da + db_);                       // - 2 loss d
-            z.k_lca = (a_below && b_below) ? loss * (da + db_ - 2) : z.k_top;  // - 2 loss d, at d == dl
-            z.k_a = cs.hgt + loss * da;                                 // - loss d, a's path below the lca
-            z.k_b = cs.hgt + loss * db_;                                // - loss d, b's path below the lca
-            z.a_ok = b_below, z.b_ok = a_below;
-            z.leaf = mode == 0, z.cherry = mode == 1;
+            const unsigned dup_top = (unsigned)(cs.dup + loss * (da + db_));                  // - 2 loss d
+            z.dl = dl, z.da = da, z.db = db_;
+            z.k_top = mode == 1 ? dup_top : BIG;
+            z.k_lca = mode == 1 ? ((a_below && b_below) ? (unsigned)(loss * (da + db_ - 2)) : dup_top)
+                                : (mode == 0 ? (unsigned)(2 * loss * dl) : BIG);                // - 2 loss d, at d == dl
+            z.k_a = (mode == 1 && b_below) ? (unsigned)(cs.hgt + loss * da) : BIG;             // - loss d, a's path below the lca
+            z.k_b = (mode == 1 && a_below) ? (unsigned)(cs.hgt + loss * db_) : BIG;            // - loss d, b's path below the lca
             return z;
         };
         const Side zl = make_side(mode_l, l_da, l_db, l_dl), zr = make_side(mode_r, r_da, r_db, r_dl);
-        auto closed = [&](const Side& z, bool fa, bool fb, int d) {
-            const int ld = loss * d;
-            const bool on_a = fa && d <= z.da, on_b = fb && !on_a && d > z.dl && d <= z.db;
-            unsigned v = 0xffffffffu;
-            const unsigned top = (unsigned)((d == z.dl ? z.k_lca : z.k_top) - 2 * ld);
-            const unsigned va = d <= z.dl ? top : (z.a_ok ? (unsigned)(z.k_a - ld) : 0xffffffffu);
-            const unsigned vb = z.b_ok ? (unsigned)(z.k_b - ld) : 0xffffffffu;
-            v = on_a ? va : v;
-            v = on_b ? vb : v;
-            v = z.cherry ? v : 0xffffffffu;
-            v = (z.leaf && on_a && d == z.da) ? 0u : v;
-            return v;
+        auto closed = [&](const Side& z, unsigned fa, unsigned fb, int d, unsigned ld) {
+            const unsigned top = (d == z.dl ? z.k_lca : z.k_top) - 2u * ld;
+            const unsigned va = d <= z.dl ? top : z.k_a - ld;
+            const unsigned vb = z.k_b - ld;
+            const bool on_a = fa && d <= z.da, on_b = fb && d <= z.db;
+            return on_a ? va : (on_b ? vb : BIG);
         };
         for (int e = 0; e < m; ++e) {
             const unsigned w = el[e * THREAD_ROWS];
             const unsigned s = w & TH_S_MASK;
             const int d = (int)((w >> TH_D_SHIFT) & 31u);
             const unsigned f = w >> TH_FLAG_SHIFT;
-            unsigned va = closed(zl, f & 1u, f & 2u, d), vb = closed(zr, f & 4u, f & 8u, d);
-            if (mode_l == 2 && (next_l >> TH_VAL_BITS) == s) {
+            const unsigned ld = (unsigned)(loss * d);
+            unsigned va = closed(zl, f & 1u, f & 2u, d, ld), vb = closed(zr, f & 4u, f & 8u, d, ld);
+            if ((next_l >> TH_VAL_BITS) == s) {   // (0xffffffff >> 22 = 1023 is no species: rank_bits <= 9)
                 va = next_l & TH_VAL_MASK;
-                if (va == TH_VAL_MASK) va = 0xffffffffu;
-                ++q_l;
-                next_l = q_l < m_l ? Tl[q_l] : 0xffffffffu;
+                next_l = next2_l;
+                q_l += 1;
+                next2_l = q_l + 1 < m_l ? Tl[q_l + 1] : 0xffffffffu;
             }
-            if (mode_r == 2 && (next_r >> TH_VAL_BITS) == s) {
+            if ((next_r >> TH_VAL_BITS) == s) {
                 vb = next_r & TH_VAL_MASK;
-                if (vb == TH_VAL_MASK) vb = 0xffffffffu;
-                ++q_r;
-                next_r = q_r < m_r ? Tr[q_r] : 0xffffffffu;
+                next_r = next2_r;
+                q_r += 1;
+                next2_r = q_r + 1 < m_r ? Tr[q_r + 1] : 0xffffffffu;
             }
             const unsigned low = (s << db) | (unsigned)d;
-            Mc[e * THREAD_ROWS] = make_uint2(va == 0xffffffffu ? infkey + low : va * vmul + low,
-                                             vb == 0xffffffffu ? infkey + low : vb * vmul + low);
+            Mc[e * THREAD_ROWS] = make_uint2(va >= TH_VAL_MASK ? infkey + low : va * vmul + low,
+                                             vb >= TH_VAL_MASK ? infkey + low : vb * vmul + low);
         }
         SR2_DCHECK(q_l == m_l && q_r == m_r);  // every entry of a child found its element
     }
@@ -2111,7 +2116,7 @@ int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64
 // Tiers of dtl_wave_thread_kernel and the classes of dtl_partition_kernel (DtlProblem::tier_*, n_classes);
 // `table` (2 x 1024 bytes: class of a path-set size without / with compact rows) is filled when given.
 static void dtl_thread_tiers(DtlProblem* p, std::vector<uint8_t>* table) {
-    int tiers[8] = {28, 38, 48, 64}, nt = 4;
+    int tiers[8] = {27, 40, 50, 64}, nt = 4;  // 8 / 6 / 5 / 4 CTAs per SM with the 1.6 KB species table of config #2
     if (const char* tv = getenv("SR2_THREAD_TIERS")) {
         nt = 0;
         for (const char* q = tv; *q && nt < 8;) {
@@ -2427,7 +2432,7 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
                     SR2_CUDA(ctx, cudaMemcpyAsync(p->d_class_of, p->class_table.data(), table.size(), cudaMemcpyHostToDevice, ctx->stream));
                 }
                 SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   4 * THREAD_SMEM_WORDS(64)));
+                                                   (int)THREAD_SMEM_BYTES(64, ctx->S)));
                 SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 // compact rows: everything the thread kernel writes, and the rows of flat2's sparse cells pass (row_cnt is a byte)
                 p->compact_max = std::max(p->tier_maxm[p->n_tiers - 1], std::min(p->flat2_sparse_max, 255));
@@ -2525,7 +2530,7 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             const unsigned ctas = (unsigned)((n_rows + THREAD_ROWS - 1) / THREAD_ROWS);
             for (int k = 0; k < p->n_tiers; ++k) {
                 ++p->n_launch;
-                dtl_wave_thread_kernel<<<ctas, THREAD_ROWS, 4 * THREAD_SMEM_WORDS(p->tier_maxm[k]), ts[k]>>>(
+                dtl_wave_thread_kernel<<<ctas, THREAD_ROWS, THREAD_SMEM_BYTES(p->tier_maxm[k], ctx->S), ts[k]>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
                     p->cur_mask, lists, (int)p->list_pitch, counts, p->tier_cls0[k], p->tier_cls0[k + 1] - p->tier_cls0[k],
                     p->tier_maxm[k], p->cur_cherry_end, p->cur_rowcnt, p->cur_rowinfo);
@@ -2814,7 +2819,8 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     }
     if (n_inst > 0 && per_tree) {
         int threads = 32;
-        while (threads < 1024 && threads * 2 < cap) threads *= 2;  // measured on config #2 (cap 251): 32 / 64 / 128 / 256 -> 336 / 309 / 272 / 393 us
+        // measured on config #2 (cap 251; step time with compact rows): 32 / 64 / 128 / 256 threads -> 5.13 / 5.08 / 5.20 / 5.41 ms
+        while (threads < 1024 && threads * 4 < cap) threads *= 2;
         if (const char* t = getenv("SR2_DTL_TRACE_THREADS")) threads = std::max(32, std::min(1024, atoi(t) / 32 * 32));
         if (trace_smem > 48 * 1024 && trace_smem > p->trace_smem_set) {
             SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_select_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
