@@ -1153,7 +1153,8 @@ dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
             b5 = reinterpret_cast<const uint4*>(sp.pathmask + (size_t)rb * ms);
         }
         // dtl_wave_thread_kernel's view of the row in two 16-byte words: child descriptors, preorder times of
-        // the four leaf species, and per side depth(a) | depth(b) << 8 | depth(lca(a, b)) << 16
+        // the four leaf species, and per side depth(a) | depth(b) << 8 | depth(lca(a, b)) << 16 (a leaf or cherry
+        // child) or entries of the child's compact row << 24 (a stored child)
         if (row_info && sub < 2) {
             const int a = sub ? ra : la, b = sub ? rb : lb;
             unsigned ta = 0u, tb = 0u, dpack = 0u;
@@ -1162,6 +1163,10 @@ dtl_partition_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const in
                 tb = (unsigned)__ldg(sp.tin + b);
                 dpack = (unsigned)__ldg(sp.depth + a) | ((unsigned)__ldg(sp.depth + b) << 8) |
                         ((unsigned)__ldg(sp.lca_depth + (size_t)a * sp.S + b) << 16);
+            } else if (row_cnt) {
+                // a stored child: the size of its compact row (0 = dense), written by this kernel's launch for the
+                // child's wave (same stream) -- saves dtl_wave_thread_kernel a dependent trip to memory
+                dpack = (unsigned)row_cnt[sub ? cr : cl] << 24;
             }
             row_info[(size_t)(gr - chunk_row0) * 2 + sub] = make_uint4((unsigned)(sub ? cr : cl), ta, tb, dpack);
         }
@@ -1542,11 +1547,9 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     uint32_t* el = th_smem + 2 * (MAXM + 1) * THREAD_ROWS + t;    // el[e * THREAD_ROWS]
     uint32_t* stage = th_smem + (3 * MAXM + 2) * THREAD_ROWS + warp * (512 + 96);  // [2][8][32] values, tags
     uint32_t* rowinfo = stage + 512;                              // [32] x (offset lo, offset hi), [32] sizes
-    // the row's bit set lives in the thread's own Mc words (two per element) until the keys are built
-    auto on_path = [&](int sx) {
-        const uint2 two = Mc[(sx >> 6) * THREAD_ROWS];
-        return (((sx >> 5) & 1 ? two.y : two.x) >> (sx & 31)) & 1u;
-    };
+    // the row's bit set lives in the warp's staging tile (16 words per lane, [word][lane]) until the cells phase
+    uint32_t* bits = stage + lane;
+    auto on_path = [&](int sx) { return (bits[(sx >> 5) * 32] >> (sx & 31)) & 1u; };
     int cl = -1, cr = -1, m = 0;
     // per side: 0 = leaf at species a, 1 = virtual cherry (a, b), 2 = stored (compact) row
     int mode_l = 0, mode_r = 0, m_l = 0, m_r = 0;
@@ -1554,24 +1557,48 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     // depths of the leaf species a, b and of lca(a, b) per side, preorder times of the four species
     int l_da = 0, l_db = 0, l_dl = 0, r_da = 0, r_db = 0, r_dl = 0;
     if (valid) {
-        const uint4* m4 = reinterpret_cast<const uint4*>(rowmask + slot * ms);
-        for (int q = 0; q < (ms >> 2); ++q) {
-            const uint4 v = m4[q];
-            Mc[(2 * q) * THREAD_ROWS] = make_uint2(v.x, v.y);
-            Mc[(2 * q + 1) * THREAD_ROWS] = make_uint2(v.z, v.w);
-        }
         cl = (int)il.x;
         cr = (int)ir.x;
         SR2_DCHECK(cl == row_cl[chunk_row0 + slot] && cr == row_cr[chunk_row0 + slot]);
         mode_l = cl < 0 ? 0 : (cl < cherry_end ? 1 : 2);
         mode_r = cr < 0 ? 0 : (cr < cherry_end ? 1 : 2);
-        if (mode_l == 2) m_l = (int)row_cnt[cl];
-        if (mode_r == 2) m_r = (int)row_cnt[cr];
-        SR2_DCHECK(mode_l != 2 || m_l > 0);  // a child's path set is a subset of this row's: it is a compact row
-        SR2_DCHECK(mode_r != 2 || m_r > 0);
+        if (mode_l == 2) m_l = (int)(il.w >> 24);
+        if (mode_r == 2) m_r = (int)(ir.w >> 24);
+        SR2_DCHECK(mode_l != 2 || (m_l > 0 && m_l == (int)row_cnt[cl]));  // a child's path set is a subset of this
+        SR2_DCHECK(mode_r != 2 || (m_r > 0 && m_r == (int)row_cnt[cr]));  // row's: it is a compact row
+        // Everything the row reads from memory is requested here, in one go: its bit set and the entries of its
+        // stored children (a subsequence of this row's elements, so they fit the key slots Mc[0 .. m), left child
+        // in .x, right child in .y; the merge below walks backwards and overwrites them in place).  The r7b capture
+        // had 23 % of the kernel's stall samples at the per-entry loads of the merge.
+        const uint4* m4 = reinterpret_cast<const uint4*>(rowmask + slot * ms);
+        const uint4* Tl4 = reinterpret_cast<const uint4*>(T + (size_t)(mode_l == 2 ? cl : 0) * pitch);
+        const uint4* Tr4 = reinterpret_cast<const uint4*>(T + (size_t)(mode_r == 2 ? cr : 0) * pitch);
+        uint4 mk[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mk[q] = q < (ms >> 2) ? m4[q] : make_uint4(0u, 0u, 0u, 0u);
+        const int n4 = (max(m_l, m_r) + 3) >> 2;
+#pragma unroll 2
+        for (int j = 0; j < n4; ++j) {
+            // (a quad may reach past the child's entries, never past its row: m <= 64 < pitch)
+            uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+            if (4 * j < m_l) a = Tl4[j];
+            if (4 * j < m_r) b = Tr4[j];
+            // (Mc has MAXM + 1 slots; the last quad of a child with nearly MAXM entries must not spill into el)
+            Mc[(4 * j) * THREAD_ROWS] = make_uint2(a.x, b.x);
+            if (4 * j + 1 <= MAXM) Mc[(4 * j + 1) * THREAD_ROWS] = make_uint2(a.y, b.y);
+            if (4 * j + 2 <= MAXM) Mc[(4 * j + 2) * THREAD_ROWS] = make_uint2(a.z, b.z);
+            if (4 * j + 3 <= MAXM) Mc[(4 * j + 3) * THREAD_ROWS] = make_uint2(a.w, b.w);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            bits[(4 * q) * 32] = mk[q].x;
+            bits[(4 * q + 1) * 32] = mk[q].y;
+            bits[(4 * q + 2) * 32] = mk[q].z;
+            bits[(4 * q + 3) * 32] = mk[q].w;
+        }
         const int t_la = (int)il.y, t_lb = (int)il.z, t_ra = (int)ir.y, t_rb = (int)ir.z;
-        l_da = (int)(il.w & 0xffu), l_db = (int)((il.w >> 8) & 0xffu), l_dl = (int)(il.w >> 16);
-        r_da = (int)(ir.w & 0xffu), r_db = (int)((ir.w >> 8) & 0xffu), r_dl = (int)(ir.w >> 16);
+        l_da = (int)(il.w & 0xffu), l_db = (int)((il.w >> 8) & 0xffu), l_dl = (int)((il.w >> 16) & 0xffu);
+        r_da = (int)(ir.w & 0xffu), r_db = (int)((ir.w >> 8) & 0xffu), r_dl = (int)((ir.w >> 16) & 0xffu);
         // ---- elements: top-down over the path set ----------------------------------------------------
         el[0] = 0xfu << TH_FLAG_SHIFT;  // the root: species 0, depth 0, on every root path
         m = 1;
@@ -1608,13 +1635,12 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     {
         const unsigned vmul = 1u << kp.sh, infkey = 0xffffffffu << kp.sh;
         const int db = kp.db;
-        // a compact child: its entries are a subsequence of this row's elements (same order)
-        const uint32_t* __restrict__ Tl = reinterpret_cast<const uint32_t*>(T) + (size_t)(mode_l == 2 ? cl : 0) * pitch;
-        const uint32_t* __restrict__ Tr = reinterpret_cast<const uint32_t*>(T) + (size_t)(mode_r == 2 ? cr : 0) * pitch;
-        // (the entries of a stored child are requested two matches ahead: the loads are trips to L2 / DRAM)
-        int q_l = 0, q_r = 0;
-        unsigned next_l = m_l > 0 ? Tl[0] : 0xffffffffu, next_r = m_r > 0 ? Tr[0] : 0xffffffffu;
-        unsigned next2_l = m_l > 1 ? Tl[1] : 0xffffffffu, next2_r = m_r > 1 ? Tr[1] : 0xffffffffu;
+        // the entries of the stored children sit in Mc[0 .. m_l).x / Mc[0 .. m_r).y: walked backwards, like the
+        // elements, entry q of a child matches an element e >= q, so writing the keys of element e never hits an
+        // entry that is still to be read (the current entries are held in registers)
+        int q_l = m_l - 1, q_r = m_r - 1;
+        unsigned next_l = q_l >= 0 ? Mc[q_l * THREAD_ROWS].x : 0xffffffffu;
+        unsigned next_r = q_r >= 0 ? Mc[q_r * THREAD_ROWS].y : 0xffffffffu;
         // Closed form of a cherry (a, b) at depth d of a's path: above the lca a duplication, at the lca a
         // speciation when both leaves sit below it, below the lca a transfer of b (if b is below the lca);
         // on b's path below the lca a transfer of a.  A leaf child is a cherry with a == b whose only finite
@@ -1648,7 +1674,7 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             const bool on_a = fa && d <= z.da, on_b = fb && d <= z.db;
             return on_a ? va : (on_b ? vb : BIG);
         };
-        for (int e = 0; e < m; ++e) {
+        for (int e = m - 1; e >= 0; --e) {
             const unsigned w = el[e * THREAD_ROWS];
             const unsigned s = w & TH_S_MASK;
             const int d = (int)((w >> TH_D_SHIFT) & 31u);
@@ -1657,21 +1683,19 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             unsigned va = closed(zl, f & 1u, f & 2u, d, ld), vb = closed(zr, f & 4u, f & 8u, d, ld);
             if ((next_l >> TH_VAL_BITS) == s) {   // (0xffffffff >> 22 = 1023 is no species: rank_bits <= 9)
                 va = next_l & TH_VAL_MASK;
-                next_l = next2_l;
-                q_l += 1;
-                next2_l = q_l + 1 < m_l ? Tl[q_l + 1] : 0xffffffffu;
+                q_l -= 1;
+                next_l = q_l >= 0 ? Mc[q_l * THREAD_ROWS].x : 0xffffffffu;
             }
             if ((next_r >> TH_VAL_BITS) == s) {
                 vb = next_r & TH_VAL_MASK;
-                next_r = next2_r;
-                q_r += 1;
-                next2_r = q_r + 1 < m_r ? Tr[q_r + 1] : 0xffffffffu;
+                q_r -= 1;
+                next_r = q_r >= 0 ? Mc[q_r * THREAD_ROWS].y : 0xffffffffu;
             }
             const unsigned low = (s << db) | (unsigned)d;
             Mc[e * THREAD_ROWS] = make_uint2(va >= TH_VAL_MASK ? infkey + low : va * vmul + low,
                                              vb >= TH_VAL_MASK ? infkey + low : vb * vmul + low);
         }
-        SR2_DCHECK(q_l == m_l && q_r == m_r);  // every entry of a child found its element
+        SR2_DCHECK(q_l == -1 && q_r == -1);  // every entry of a child found its element
     }
     // ---- up-sweep: SUBMIN ---------------------------------------------------------------------------------
     for (int e = m - 1; e >= 1; --e) {
@@ -1686,6 +1710,7 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     const int c12 = -2 * loss, c3 = cs.dup, c45 = cs.hgt;
     const uint2 inf2 = make_uint2(0xffffffffu, 0xffffffffu);
     const int m_warp = __reduce_max_sync(0xffffffffu, m);
+    __syncwarp();  // the staging tile held the lanes' bit sets until here
     uint2 prevM = inf2;  // SUBMIN of the element before (its slot already holds its SEPMIN)
     unsigned w = m > 0 ? el[0] : 0u;
     for (int e = 0; e < m_warp; ++e) {
