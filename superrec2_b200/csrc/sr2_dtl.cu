@@ -88,6 +88,8 @@ struct DtlProblem {
     uint8_t* cur_rowcnt = nullptr;
     uint4* d_rowinfo = nullptr;      // [rows][2] per table set: dtl_partition_kernel's record of a listed row
     uint4* cur_rowinfo = nullptr;
+    int4* d_desc = nullptr;          // [rows] per table set: (left child, right child, node of the left child, of the right child),
+    int4* cur_desc = nullptr;        // the four row arrays packed for dtl_select_trace_kernel (dtl_desc_kernel)
     bool cur_compact = false;        // chunk being enqueued: its sparse rows are stored compact
     // classes of dtl_partition_kernel: table [0] without compact rows (two sparse tiers + dense), table [1] with
     // (bins of path-set sizes grouped into the tiers of dtl_wave_thread_kernel + dense); device copies of 1024 bytes
@@ -1957,6 +1959,19 @@ dtl_traceback_kernel(DevSpecies sp, const int32_t* __restrict__ row_node,
     map[row_right[gr]] = b;
 }
 
+// The traceback touches every row once, at random: read from four row arrays that is four 32-byte sectors per
+// node for 16 bytes of use (the kernel moves ~190 B per node and runs at the random-access rate of the HBM:
+// 0.94 GB in 0.36 ms for config #2).  This packs them, one 16-byte record per row (side stream, once per solve).
+__global__ void __launch_bounds__(256)
+dtl_desc_kernel(const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
+                const int32_t* __restrict__ row_left, const int32_t* __restrict__ row_right, int64_t chunk_row0,
+                int64_t n_rows, int4* __restrict__ desc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_rows) return;
+    const int64_t gr = chunk_row0 + i;
+    desc[i] = make_int4(row_cl[gr], row_cr[gr], row_left[gr], row_right[gr]);
+}
+
 // Selection and traceback of a whole object tree in one CTA (the default): after the root is chosen
 // as in dtl_select_kernel, the tree is walked breadth-first with the frontier -- (row, species) pairs of
 // the internal nodes of one depth -- in shared memory, so a level costs one round trip to the tables
@@ -1970,7 +1985,7 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
                         const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr, int cap, int check_T,
                         int cherry_end, DtlCosts cs, int32_t* __restrict__ min_cost, int32_t* __restrict__ root_species,
                         int32_t* __restrict__ map, const uint8_t* __restrict__ row_cnt,
-                        const uint32_t* __restrict__ rowmask) {
+                        const uint32_t* __restrict__ rowmask, const int4* __restrict__ desc) {
     extern __shared__ int2 trace_lists[];  // [2][cap] of (row slot, species)
     __shared__ u64 warp_best[32];
     __shared__ int n_list[2];
@@ -2038,7 +2053,13 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
         for (int i = threadIdx.x; i < n; i += blockDim.x) {
             const int slot = from[i].x, x = from[i].y;
             const int64_t gr = chunk_row0 + slot;
-            const int cl = row_cl[gr], cr = row_cr[gr];
+            int cl, cr, node_l, node_r;
+            if (desc) {
+                const int4 dd = desc[slot];
+                cl = dd.x, cr = dd.y, node_l = dd.z, node_r = dd.w;
+            } else {
+                cl = row_cl[gr], cr = row_cr[gr], node_l = row_left[gr], node_r = row_right[gr];
+            }
             int a = -1, c = -1;
             // infinite cells have no (defined) tag; a cherry stores none at all: its parent only ever
             // points at a finite cell, whose tag is the two leaf species
@@ -2082,8 +2103,8 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
                     }
                 }
             }
-            map[row_left[gr]] = a;
-            map[row_right[gr]] = c;
+            map[node_l] = a;
+            map[node_r] = c;
             // (validated full binary trees never exceed cap; the guard keeps a bad tree out of other memory)
             if (cl >= 0) {
                 const int k = atomicAdd(&n_list[cur ^ 1], 1);
@@ -2100,8 +2121,12 @@ dtl_select_trace_kernel(DevSpecies sp, const int64_t* __restrict__ root_row, con
                 for (int side = 0; side < 2; ++side) {
                     const int ch = side ? cr : cl, xs = side ? c : a;
                     if (ch < 0 || xs < 0) continue;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row_cl + chunk_row0 + ch));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row_cr + chunk_row0 + ch));
+                    if (desc) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(desc + ch));
+                    } else {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row_cl + chunk_row0 + ch));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row_cr + chunk_row0 + ch));
+                    }
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(row_cnt + ch));
                     const uint32_t* mk2 = rowmask + (size_t)ch * sp.mask_stride;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(mk2));
@@ -2211,6 +2236,8 @@ static int dtl_prepare(void* user) {
     p->d_rowcnt = (uint8_t*)ptr;
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_ROWINFO, (table_elems / ctx->pitch) * 2 * sizeof(uint4) + 256, &ptr))) return rc;
     p->d_rowinfo = (uint4*)ptr;
+    if ((rc = sr2_dev_reserve(ctx, DP_DTL_DESC, (table_elems / ctx->pitch) * sizeof(int4) + 256, &ptr))) return rc;
+    p->d_desc = (int4*)ptr;
     p->list_pitch = std::max<int64_t>(p->rows.R, 1);
     dtl_thread_tiers(p, nullptr);
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_LISTS, (size_t)std::max(p->n_classes[0], p->n_classes[1]) * p->list_pitch * sizeof(int), &ptr))) return rc;
@@ -2658,6 +2685,7 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
     p->cur_mask = p->d_mask + set * (table_elems / ctx->pitch * ctx->dsp.mask_stride);
     p->cur_rowcnt = p->d_rowcnt + set * (table_elems / ctx->pitch);
     p->cur_rowinfo = p->d_rowinfo + set * (table_elems / ctx->pitch) * 2;
+    p->cur_desc = p->d_desc + set * (table_elems / ctx->pitch);
     p->cur_chunk = ci;
     p->cur_set = set;
     p->pending_dense = nullptr;
@@ -2842,6 +2870,22 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
             ++p->n_launch;
         }
     }
+    // the packed row records of the traceback: on the side stream, behind the path sets (it has run dry by now)
+    const bool use_desc = ps && per_tree && n_inst > 0 && c.row_end > c.row_begin && !getenv("SR2_DTL_NO_DESC");
+    if (use_desc) {
+        const int64_t n = c.row_end - c.row_begin;
+        dtl_desc_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ps>>>(p->rows.row_cl, p->rows.row_cr, p->rows.row_left,
+                                                                    p->rows.row_right, c.row_begin, n, p->cur_desc);
+        if (part_events.size() <= events_used) {
+            cudaEvent_t e;
+            SR2_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            part_events.push_back(e);
+        }
+        SR2_CUDA(ctx, cudaEventRecord(part_events[events_used], ps));
+        SR2_CUDA(ctx, cudaStreamWaitEvent(st, part_events[events_used], 0));
+        ++events_used;
+        ++p->n_launch;
+    }
     if (n_inst > 0 && per_tree) {
         int threads = 32;
         // measured on config #2 (cap 251; step time with compact rows): 32 / 64 / 128 / 256 threads -> 5.13 / 5.08 / 5.20 / 5.41 ms
@@ -2856,7 +2900,8 @@ static int dtl_enqueue_chunk(sr2_ctx* ctx, DtlProblem* p, int ci) {
             ctx->dsp, p->rows.d_root_row, p->rows.d_root_node, c.inst_begin, c.row_begin, p->cur_T,
             p->need_decoded_cost ? p->cur_C : nullptr, p->cur_tag, p->rows.row_left, p->rows.row_right,
             p->rows.row_cl, p->rows.row_cr, (int)cap, getenv("SR2_DTL_TRACE_CHECK") ? 1 : 0, p->cur_cherry_end, cs,
-            p->d_min_cost, p->d_root_species, p->d_map, p->cur_compact ? p->cur_rowcnt : nullptr, p->cur_mask);
+            p->d_min_cost, p->d_root_species, p->d_map, p->cur_compact ? p->cur_rowcnt : nullptr, p->cur_mask,
+            use_desc ? p->cur_desc : nullptr);
         ++p->n_launch;
     } else if (n_inst > 0) {
         dtl_select_kernel<<<(n_inst + 7) / 8, 256, 0, st>>>(

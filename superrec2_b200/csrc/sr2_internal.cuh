@@ -135,7 +135,7 @@ struct Sr2Pool {
 };
 enum Sr2DevPool {
     DP_ROWS_SLAB, DP_ROOT_ROW, DP_ROOT_NODE, DP_NODE_PRE, DP_NODE_INST,
-    DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MINCOST, DP_DTL_ROOTSP, DP_DTL_MAP, DP_DTL_MASK, DP_DTL_LISTS, DP_DTL_COUNTS, DP_DTL_CHAIN, DP_DTL_ROWCNT, DP_DTL_ROWINFO, DP_DTL_CLASSES,
+    DP_DTL_T, DP_DTL_TAG, DP_DTL_C, DP_DTL_MINCOST, DP_DTL_ROOTSP, DP_DTL_MAP, DP_DTL_MASK, DP_DTL_LISTS, DP_DTL_COUNTS, DP_DTL_CHAIN, DP_DTL_ROWCNT, DP_DTL_ROWINFO, DP_DTL_CLASSES, DP_DTL_DESC,
     DP_S_LEFT, DP_S_RIGHT, DP_S_NODEOFF, DP_S_BITS, DP_S_PRESENT, DP_S_OUTSIDE, DP_S_GAIN, DP_S_L, DP_S_FLAGS,
     DP_S_T, DP_S_TAG, DP_S_DEC, DP_S_ANC, DP_S_TAU, DP_S_TAUMIN, DP_S_COST, DP_S_MINCOST, DP_S_ROOTSP, DP_S_MAP,
     DP_S_KIND, DP_S_SYN, DP_S_BEST, DP_S_ALLOWED, DP_S_EV, DP_S_CHAIN,
