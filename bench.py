@@ -50,9 +50,10 @@ WORKLOADS = {
 }
 BYTES_PER_CELL = 20  # 2 x 4 B child reads + 4 B value + 8 B traceback
 # DRAM bytes per evaluated cell, measured: ncu dram__bytes_read.sum + dram__bytes_write.sum of EVERY launch of
-# one step of the headline workload (profiles/r4g_dram_per_launch_config2.csv: 17.59 GB per step, 16.50 GB of
-# it in the 40 wave launches) / cells of the rows that are materialised (1,325,775,654 on rank 0's batch)
-DRAM_B_PER_CELL_STEP, DRAM_B_PER_CELL_WAVES = 17.59e9 / 1325775654, 16.50e9 / 1325775654
+# one step of the headline workload (profiles/r7d_dram_per_launch_config2.csv: 6.53 GB per step, 4.53 GB of
+# it in the 66 wave launches; 17.59 GB before the sparse rows were stored compact, r4g) / cells of the rows that
+# are materialised (1,325,775,654 on rank 0's batch)
+DRAM_B_PER_CELL_STEP, DRAM_B_PER_CELL_WAVES = 6.531e9 / 1325775654, 4.525e9 / 1325775654
 
 
 def measured_peak():
@@ -661,21 +662,22 @@ def main():
                                     "the rows, are evaluated by their readers and never stored); dram_frac: bytes that "
                                     "really cross the HBM interface (ncu, every launch of a step) / time / peak -- the kernels are bound by "
                                     "instruction latency and issue slots, not by HBM",
-                         "kernel": "dtl wave kernels: dtl_wave_sparse_kernel<38|57> (rows with <= 57 root-path species, 55 % "
-                                   "of the step), dtl_wave_flat2_kernel (the other rows, 32 %, and the chained launch "
-                                   "of the small top waves, 5 %); wave 1 is virtual (readers evaluate the closed form of a cherry row)",
+                         "kernel": "dtl wave kernels: dtl_wave_thread_kernel (rows with <= 64 root-path species: a thread "
+                                   "per row, rows stored compact; 40 % of the serialised kernel time of a step), "
+                                   "dtl_wave_flat2_kernel (the other rows, a warp per row, 38 %, and the chained launch "
+                                   "of the small top waves, 7 %); wave 1 is virtual (readers evaluate the closed form of a cherry row)",
                          "peak_source": peak_src,
                          "bytes_per_cell": BYTES_PER_CELL,
                          "algorithmic_bytes_per_launch": cells * BYTES_PER_CELL / waves_per_step,
                          "wave_launches_per_step": waves_per_step,
-                         "launch_definition": "a launch = one wave (one height of the whole batch): up to three concurrent "
-                                              "kernel launches (two sparse tiers + the dense rows), 40 kernel launches in "
-                                              "14 waves for this workload; achieved and traffic are per wave",
+                         "launch_definition": "a launch = one wave (one height of the whole batch): up to five concurrent "
+                                              "kernel launches (four tiers of the thread kernel + the dense rows), 66 kernel "
+                                              "launches in 14 waves for this workload; achieved and traffic are per wave",
                          "wave_ms_per_step": wave_ms / args.steps,
                          "cells_evaluated_per_step": cells_evaluated, "cherry_rows": n_cherry,
-                         "traffic_source": "bytes per wave launch (average over the step's 40 wave launches) from ncu "
+                         "traffic_source": "bytes per wave (average over the step's 14 waves) from ncu "
                                            "dram__bytes_read.sum + dram__bytes_write.sum of every launch of one step, "
-                                           "profiles/r4g_dram_per_launch_config2.csv (cold caches, launches serialised), "
+                                           "profiles/r7d_dram_per_launch_config2.csv (cold caches, launches serialised), "
                                            "scaled by the cells this batch evaluates"},
             "checksum_min_costs": checksum,
         }
