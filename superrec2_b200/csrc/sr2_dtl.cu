@@ -1579,17 +1579,27 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 #pragma unroll
         for (int q = 0; q < 4; ++q) mk[q] = q < (ms >> 2) ? m4[q] : make_uint4(0u, 0u, 0u, 0u);
         const int n4 = (max(m_l, m_r) + 3) >> 2;
-#pragma unroll 2
-        for (int j = 0; j < n4; ++j) {
-            // (a quad may reach past the child's entries, never past its row: m <= 64 < pitch)
-            uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
-            if (4 * j < m_l) a = Tl4[j];
-            if (4 * j < m_r) b = Tr4[j];
-            // (Mc has MAXM + 1 slots; the last quad of a child with nearly MAXM entries must not spill into el)
-            Mc[(4 * j) * THREAD_ROWS] = make_uint2(a.x, b.x);
-            if (4 * j + 1 <= MAXM) Mc[(4 * j + 1) * THREAD_ROWS] = make_uint2(a.y, b.y);
-            if (4 * j + 2 <= MAXM) Mc[(4 * j + 2) * THREAD_ROWS] = make_uint2(a.z, b.z);
-            if (4 * j + 3 <= MAXM) Mc[(4 * j + 3) * THREAD_ROWS] = make_uint2(a.w, b.w);
+        // (four quads per child in flight: a row of 64 entries costs 4 round trips, not 16)
+        for (int j0 = 0; j0 < n4; j0 += 4) {
+            uint4 a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                // (a quad may reach past the child's entries, never past its row: m <= 64 < pitch)
+                a[u] = b[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (4 * (j0 + u) < m_l) a[u] = Tl4[j0 + u];
+                if (4 * (j0 + u) < m_r) b[u] = Tr4[j0 + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = j0 + u;
+                // (Mc has MAXM + 1 slots; the last quad of a child with nearly MAXM entries must not spill into el)
+                if (j < n4) {
+                    Mc[(4 * j) * THREAD_ROWS] = make_uint2(a[u].x, b[u].x);
+                    if (4 * j + 1 <= MAXM) Mc[(4 * j + 1) * THREAD_ROWS] = make_uint2(a[u].y, b[u].y);
+                    if (4 * j + 2 <= MAXM) Mc[(4 * j + 2) * THREAD_ROWS] = make_uint2(a[u].z, b[u].z);
+                    if (4 * j + 3 <= MAXM) Mc[(4 * j + 3) * THREAD_ROWS] = make_uint2(a[u].w, b[u].w);
+                }
+            }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
