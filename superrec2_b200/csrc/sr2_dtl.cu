@@ -22,14 +22,20 @@
 //
 // What runs by default for a batch whose species tree fits the batched kernels (|S| <= ~480,
 // costs that fit 32-bit keys); DESIGN.md section 4 has the measurements behind each piece:
-//   wave 1 (cherries)      not launched: readers evaluate the closed form (cherry_form)
-//   side stream            dtl_partition_kernel / dtl_rowmask_kernel: root-path bit set of every row,
-//                          per wave the lists of rows with <= 38 / <= 57 path species and of the others
-//   big waves              dtl_wave_sparse_kernel<38>, <57> (4 lanes per row, path species only) and
-//                          dtl_wave_flat2_kernel<NS, false> (a warp per dense row) on two streams
+//   wave 1 (cherries)      not launched: readers evaluate the closed form (cherry_form / the per-row constants
+//                          of dtl_wave_thread_kernel)
+//   side stream            dtl_partition_kernel / dtl_rowmask_kernel: root-path bit set of every row, per wave the
+//                          lists of rows by path-set size (bins grouped into the tiers of the thread kernel, and
+//                          the dense rows), per row the record the thread kernel starts from; dtl_desc_kernel
+//   big waves              dtl_wave_thread_kernel (rows with <= 64 path species: one THREAD per row, tiers of
+//                          27 / 40 / 50 / 64 species, rows stored compact: value | species << 22 and the tag per
+//                          path species, nothing for the infinite cells) and dtl_wave_flat2_kernel<NS, false>
+//                          (a warp per dense row; rows of up to 3/8 pitch path species stored compact too), on
+//                          up to five streams
 //   small top waves        dtl_wave_flat2_kernel<NS, true>: one launch, rows chained by done flags
 //   selection + traceback  dtl_select_trace_kernel: one CTA per tree
-// Everything else (dtl_wave_kernel -- a warp or a CTA per row with 64-bit keys, BASELINE config #3 runs on
+// Everything else (dtl_wave_sparse_kernel -- 4 lanes per sparse row, dense storage: the path when the tables are
+// kept for the caller --, dtl_wave_kernel -- a warp or a CTA per row with 64-bit keys, BASELINE config #3 runs on
 // it --, dtl_wave_inplace_kernel, dtl_wave_flat_kernel, dtl_cherry_*_kernel, dtl_select_kernel,
 // dtl_traceback_kernel, dtl_decoded_cost_kernel) is the general path: large species trees, large
 // costs, tables kept for the caller, charged speciations, cross-checks in the tests.

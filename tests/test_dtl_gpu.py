@@ -582,3 +582,33 @@ def test_flat_entry_point_and_empty_sixteen_bit_batch(ctx):
     empty = ctx.dtl_run16(np.zeros(1, np.int64), np.zeros(0, np.int16), np.zeros(0, np.int16),
                           np.zeros(0, np.int16), batch.costs)
     assert all(len(part) == 0 for part in empty)
+
+
+@pytest.mark.parametrize("tiers", [None, "6,13,64", "64", "9,10,11,12,40"])
+@pytest.mark.parametrize("costs", [(0, 1, 1, 1, 1), (0, 5, 2, 3, 1), (0, 0, 4, 0, 2)])
+def test_thread_per_row_kernel_against_oracle(ctx, monkeypatch, tiers, costs):
+    """dtl_wave_thread_kernel (a thread per sparse row, rows stored compact) with its readers (itself, flat2's
+    scatter of a compact child, the per-tree traceback): 700 trees of 40 leaves over 150 species leaves, a third
+    of the object leaves at random -- mostly internal -- species (a leaf species that is an ancestor of its
+    sibling's: the flags of the generation are not exact there), tier limits that put the cuts at odd sizes and
+    a child with exactly as many entries as the tier holds.  Costs, roots and mappings of every tree against
+    the oracle (no SR2_KEEP_TABLES: compact rows and virtual cherries are only used when nobody reads the tables)."""
+    monkeypatch.setenv("SR2_DTL_SIMD_MIN_ROWS", "1")
+    if tiers:
+        monkeypatch.setenv("SR2_THREAD_TIERS", tiers)
+    batch = synth.make_batch(150, 40, 700, seed=77, costs=costs)
+    rng = np.random.default_rng(5)
+    leaves = np.flatnonzero(batch.left < 0)
+    moved = leaves[rng.random(len(leaves)) < 0.33]
+    batch.leaf_species[moved] = rng.integers(0, batch.n_species, len(moved))
+    ctx.set_species(batch.parent, batch.child0, batch.child1)
+    args = (batch.node_off, batch.left, batch.right, batch.leaf_species, batch.costs)
+    got = ctx.dtl_run(*args)
+    assert ctx.timing().n_launches > 0
+    want = oracle.dtl_batch(batch.parent, batch.child0, batch.child1, *args)
+    for g, w in zip(got, want):
+        assert np.array_equal(np.asarray(g), np.asarray(w))
+    # the 4-lanes-per-row kernel with dense rows (the path before compact rows) gives the same answers
+    monkeypatch.setenv("SR2_SPARSE_THREAD", "0")
+    for g, w in zip(ctx.dtl_run(*args), want):
+        assert np.array_equal(np.asarray(g), np.asarray(w))
