@@ -34,12 +34,22 @@ def main():
             n_o = n_s + int(rng.integers(0, 60))
             n_trees = int(rng.choice([1, 3, 40, 1200, 2500]))
             batch = synth.make_batch(n_s, n_o, n_trees, seed, costs=costs)
+            if rng.random() < 0.5:   # object leaves at internal species too (the reference allows any species node)
+                leaves = np.flatnonzero(batch.left < 0)
+                moved = leaves[rng.random(len(leaves)) < 0.3]
+                batch.leaf_species[moved] = rng.integers(0, batch.n_species, len(moved))
+            # tier limits of the thread-per-row kernel: the default, or cuts at odd sizes
+            tiers = str(rng.choice(["", "5,9,14,64", "64", "7,8,30,31,50"]))
+            os.environ.pop("SR2_THREAD_TIERS", None)
+            if tiers:
+                os.environ["SR2_THREAD_TIERS"] = tiers
+            os.environ["SR2_DTL_CHAIN_ROWS"] = str(rng.choice(["300", "19000"]))
             ctx.set_species(batch.parent, batch.child0, batch.child1)
             args = (batch.node_off, batch.left, batch.right, batch.leaf_species, batch.costs)
             got = ctx.dtl_run16(*args) if kind == "dtl16" else ctx.dtl_run(*args)
             want = oracle.dtl_batch(batch.parent, batch.child0, batch.child1, *args, threads=os.cpu_count())
             ok = all(np.array_equal(np.asarray(g, np.int32), w) for g, w in zip(got, want))
-            what = f"{kind} n_s={n_s} n_o={n_o} trees={n_trees} costs={costs} seed={seed}"
+            what = f"{kind} n_s={n_s} n_o={n_o} trees={n_trees} costs={costs} seed={seed} tiers={tiers!r}"
         elif kind == "superdtl":
             n_s = int(rng.integers(1, 40))
             n_o = n_s + int(rng.integers(0, 30))
