@@ -1490,11 +1490,13 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 // the leaf species of a leaf child (la only) or of a virtual cherry child: "species on the root path of
 // leaf a" is decided during the generation from preorder times (a sits below the first child of s iff
 // tin[a] < tin[second child]), so leaf rows and the closed form of cherry rows need no look-up per element.
+// Where the time went and what was done about it (profiles/README.md, r7a-r7c): the per-element look-up of the
+// species word (an L2 trip each) -> the table is staged per CTA, 4 bytes per species; the entries of the stored
+// children read one by one inside the merge -> everything the row reads (record, bit set, children) is requested
+// up front, the bit set parked in the staging tile, the children's entries in the key slots (left .x, right .y)
+// and merged BACKWARDS in place (entry q of a child matches an element e >= q).
 // Only used with virtual cherries (every stored child of a sparse row is then a compact row).
 // ---------------------------------------------------------------------------
-#ifndef TH_EXP
-#define TH_EXP 0
-#endif
 #ifndef THREAD_ROWS
 #define THREAD_ROWS 64   // rows (threads) per CTA
 #endif
