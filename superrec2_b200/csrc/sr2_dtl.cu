@@ -1473,8 +1473,10 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 //   * a lane owns a whole row and walks its path set serially, so a warp-instruction works on 32 rows; the
 //     row's state sits in shared memory as columns (word i of thread t at [i][t]: any per-thread index is
 //     conflict-free), 12 bytes per path species:
-//       el[e]  species | depth << 9 | parent position << 14 | first child position << 20 | child flags << 26
-//              | "on the root path of leaf la / lb / ra / rb" << 28..31      (elements are in BFS order)
+//       el[e]  species | depth << 9 | parent position << 14 | first-child / has-sibling << 22 | which of its
+//              children are on a path << 26 | "on the root path of leaf la / lb / ra / rb" << 28..31
+//              (elements are in BFS order: the children of the elements follow one another, so the position of
+//              an element's first child is a running count in a forward pass and needs no field)
 //       Mc[e]  (left key, right key): child values -> SUBMIN (up-sweep: e = m-1 .. 1 folds into its parent)
 //              -> SEPMIN, in place: siblings are adjacent in BFS order, an element's SUBMIN is last needed by
 //              the sibling after it (kept in registers for one step), its SEPMIN by its children further on;
@@ -1502,10 +1504,13 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 #endif
 #define TH_S_MASK 511u
 #define TH_D_SHIFT 9
-#define TH_PP_SHIFT 14
-#define TH_FC_SHIFT 20
+#define TH_PP_SHIFT 14   // 8 bits: a path set of the thread kernel has at most THREAD_MAXM species
+#define TH_PP_MASK 255u
+#define TH_FIRST_BIT 22  // the first of its parent's children that are on a path
+#define TH_SIB_BIT 23    // its sibling is on a path too (then it is the element next to it)
 #define TH_C0_BIT 26
 #define TH_C1_BIT 27
+#define THREAD_MAXM 128   // largest tier (row_cnt is a byte, compact rows reach 255 entries)
 #define TH_FLAG_SHIFT 28
 // shared-memory words of a CTA: Mc [MAXM + 1] pairs and el [MAXM] per thread, and per warp the staging tile
 // (8 x 32 values, 8 x 32 tags), the rows' table offsets (32 x 2 words) and sizes (32)
@@ -1631,14 +1636,15 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             const unsigned b0 = on_path(c0), b1 = on_path(c0 + 1);
             // (neither child on a path: an object leaf sits at this internal species)
             SR2_DCHECK(m + (int)(b0 + b1) <= MAXM);  // dtl_partition_kernel only lists rows that fit the tier
-            el[p * THREAD_ROWS] = w | ((unsigned)m << TH_FC_SHIFT) | (b0 << TH_C0_BIT) | (b1 << TH_C1_BIT);
+            el[p * THREAD_ROWS] = w | (b0 << TH_C0_BIT) | (b1 << TH_C1_BIT);
             const int split = (int)(z & 0xffffu);
             const unsigned first = (unsigned)(t_la < split) | ((unsigned)(t_lb < split) << 1) |
                                    ((unsigned)(t_ra < split) << 2) | ((unsigned)(t_rb < split) << 3);
             const unsigned flags = w >> TH_FLAG_SHIFT;
             const unsigned base = ((unsigned)(d + 1) << TH_D_SHIFT) | ((unsigned)p << TH_PP_SHIFT);
-            const unsigned w0 = (unsigned)c0 | base | ((flags & first) << TH_FLAG_SHIFT);
-            const unsigned w1 = (unsigned)(c0 + 1) | base | ((flags & ~first) << TH_FLAG_SHIFT);
+            const unsigned w0 = (unsigned)c0 | base | ((flags & first) << TH_FLAG_SHIFT) | (1u << TH_FIRST_BIT) | (b1 << TH_SIB_BIT);
+            const unsigned w1 = (unsigned)(c0 + 1) | base | ((flags & ~first) << TH_FLAG_SHIFT) | ((b0 ^ 1u) << TH_FIRST_BIT) |
+                                (b0 << TH_SIB_BIT);
             if (b0) el[(m++) * THREAD_ROWS] = w0;
             if (b1) el[(m++) * THREAD_ROWS] = w1;
         }
@@ -1719,7 +1725,7 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     }
     // ---- up-sweep: SUBMIN ---------------------------------------------------------------------------------
     for (int e = m - 1; e >= 1; --e) {
-        const int pp = (int)((el[e * THREAD_ROWS] >> TH_PP_SHIFT) & 63u);
+        const int pp = (int)((el[e * THREAD_ROWS] >> TH_PP_SHIFT) & TH_PP_MASK);
         const uint2 k = Mc[e * THREAD_ROWS], q = Mc[pp * THREAD_ROWS];
         Mc[pp * THREAD_ROWS] = make_uint2(min(q.x, k.x), min(q.y, k.y));
     }
@@ -1733,15 +1739,15 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     __syncwarp();  // the staging tile held the lanes' bit sets until here
     uint2 prevM = inf2;  // SUBMIN of the element before (its slot already holds its SEPMIN)
     unsigned w = m > 0 ? el[0] : 0u;
+    int fc = 1;  // position of the first on-path child of the element at hand: a running count in BFS order
     for (int e = 0; e < m_warp; ++e) {
         if (e < m) {
             const unsigned wn = el[(e + 1 < MAXM ? e + 1 : e) * THREAD_ROWS];  // (garbage past m: unused)
-            const int pp = (int)((w >> TH_PP_SHIFT) & 63u);
-            const unsigned wp = el[pp * THREAD_ROWS];
+            const int pp = (int)((w >> TH_PP_SHIFT) & TH_PP_MASK);
             const uint2 Pp = Mc[pp * THREAD_ROWS], mm = Mc[e * THREAD_ROWS], Mn = Mc[(e + 1) * THREAD_ROWS];
-            // the sibling is on a path iff the parent has both children; it is the next or the previous element
-            const bool both = ((wp >> TH_C0_BIT) & (wp >> TH_C1_BIT) & 1u) != 0u;
-            const bool is_first = (int)((wp >> TH_FC_SHIFT) & 63u) == e;
+            // a sibling on a path is the next element (this one is the first child) or the previous one
+            const bool both = ((w >> TH_SIB_BIT) & 1u) != 0u;
+            const bool is_first = ((w >> TH_FIRST_BIT) & 1u) != 0u;
             uint2 Ms = is_first ? Mn : prevM;
             if (!both) Ms = inf2;
             uint2 pq = make_uint2(min(Pp.x, Ms.x), min(Pp.y, Ms.y));
@@ -1749,11 +1755,11 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             // the cell
             const unsigned x = w & TH_S_MASK;
             const int dx = (int)((w >> TH_D_SHIFT) & 31u);
-            const int fc = (int)((w >> TH_FC_SHIFT) & 63u);
             const unsigned h0 = (w >> TH_C0_BIT) & 1u, h1 = (w >> TH_C1_BIT) & 1u;
             uint2 k0 = inf2, k1 = inf2;  // SUBMIN at the two children of x
             if (h0) k0 = Mc[fc * THREAD_ROWS];
             if (h1) k1 = Mc[(fc + (int)h0) * THREAD_ROWS];
+            fc += (int)(h0 + h1);
             const int nld = -loss * dx;
             const int qMl = flat2_q(mm.x, hi_mul, dm, loss), qMr = flat2_q(mm.y, hi_mul, dm, loss);
             const int ql0 = flat2_q(k0.x, hi_mul, dm, loss), qr0 = flat2_q(k0.y, hi_mul, dm, loss);
@@ -2188,7 +2194,7 @@ static void dtl_thread_tiers(DtlProblem* p, std::vector<uint8_t>* table) {
     if (const char* tv = getenv("SR2_THREAD_TIERS")) {
         nt = 0;
         for (const char* q = tv; *q && nt < 8;) {
-            tiers[nt++] = std::max(1, std::min(64, atoi(q)));
+            tiers[nt++] = std::max(1, std::min(THREAD_MAXM, atoi(q)));
             while (*q && *q != ',') ++q;
             if (*q == ',') ++q;
         }
@@ -2502,7 +2508,7 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
                     SR2_CUDA(ctx, cudaMemcpyAsync(p->d_class_of, p->class_table.data(), table.size(), cudaMemcpyHostToDevice, ctx->stream));
                 }
                 SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)THREAD_SMEM_BYTES(64, ctx->S)));
+                                                   (int)THREAD_SMEM_BYTES(p->tier_maxm[p->n_tiers - 1], ctx->S)));
                 SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 // compact rows: everything the thread kernel writes, and the rows of flat2's sparse cells pass (row_cnt is a byte)
                 p->compact_max = std::max(p->tier_maxm[p->n_tiers - 1], std::min(p->flat2_sparse_max, 255));
