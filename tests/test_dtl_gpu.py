@@ -624,3 +624,31 @@ def test_thread_per_row_kernel_against_oracle(ctx, monkeypatch, tiers, costs):
     # (one launch per tier and wave against two: the first run did go through the thread kernel)
     n_tiers = len(tiers.split(",")) if tiers else 4
     assert n_tiers in (2, 3) or ctx.timing().n_launches != launches
+
+
+@pytest.mark.parametrize("dup", [40000, 52000])
+def test_compact_rows_next_to_their_value_limit(ctx, monkeypatch, dup):
+    """A compact entry holds a 22-bit value.  With a 15-node species tree the 32-bit keys leave 25 bits for
+    values, so the bound of the table values (nodes x largest event term) can sit on either side of 2^22:
+    79 x (40,000 + ...) = 3.2 M keeps compact rows (table values in the millions go through the entries),
+    79 x (52,000 + ...) = 4.1 M+ makes the library store dense rows.  Every tree against the oracle either way."""
+    monkeypatch.setenv("SR2_DTL_SIMD_MIN_ROWS", "1")
+    monkeypatch.setenv("SR2_DTL_CHAIN_ROWS", "300")
+    species = synth.make_batch(8, 8, 1, seed=12)
+    batch = synth.make_batch(40, 40, 500, seed=13)
+    rng = np.random.default_rng(14)
+    leaf_species = np.where(batch.left < 0, rng.integers(0, species.n_species, len(batch.left)), -1).astype(np.int32)
+    costs = np.asarray((0, dup, 30000, 100, 1), np.int32)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    args = (batch.node_off, batch.left, batch.right, leaf_species, costs)
+    got = ctx.dtl_run(*args)
+    launches = ctx.timing().n_launches
+    want = oracle.dtl_batch(species.parent, species.child0, species.child1, *args)
+    assert int(np.asarray(want[0]).max()) > 200000   # values far beyond what config #2 ever holds
+    for g, w in zip(got, want):
+        assert np.array_equal(np.asarray(g), np.asarray(w))
+    monkeypatch.setenv("SR2_SPARSE_THREAD", "0")
+    for g, w in zip(ctx.dtl_run(*args), want):
+        assert np.array_equal(np.asarray(g), np.asarray(w))
+    # below the limit the first run went through the thread kernel (four tiers per wave, not two)
+    assert (ctx.timing().n_launches != launches) == (dup == 40000)
