@@ -652,3 +652,28 @@ def test_compact_rows_next_to_their_value_limit(ctx, monkeypatch, dup):
         assert np.array_equal(np.asarray(g), np.asarray(w))
     # below the limit the first run went through the thread kernel (four tiers per wave, not two)
     assert (ctx.timing().n_launches != launches) == (dup == 40000)
+
+
+def test_thread_per_row_kernel_largest_species_tree(ctx, monkeypatch):
+    """479 species nodes (the largest pitch, 480, of the batched kernels; 9-bit ranks, 15 words of path set): the
+    thread-per-row kernel, flat2 reading its compact rows and the traceback, 300 trees of 70 leaves against the oracle."""
+    monkeypatch.setenv("SR2_DTL_SIMD_MIN_ROWS", "1")
+    monkeypatch.setenv("SR2_DTL_CHAIN_ROWS", "200")
+    species = synth.make_batch(240, 240, 1, seed=90)
+    batch = synth.make_batch(70, 70, 300, seed=91)
+    rng = np.random.default_rng(92)
+    species_leaves = np.flatnonzero(species.child0 < 0)
+    n_nodes = len(batch.left)
+    leaf_species = np.where(rng.random(n_nodes) < 0.2, rng.integers(0, species.n_species, n_nodes),
+                            species_leaves[rng.integers(0, len(species_leaves), n_nodes)])
+    leaf_species = np.where(batch.left < 0, leaf_species, -1).astype(np.int32)
+    costs = np.asarray((0, 2, 3, 1, 1), np.int32)
+    ctx.set_species(species.parent, species.child0, species.child1)
+    args = (batch.node_off, batch.left, batch.right, leaf_species, costs)
+    got = ctx.dtl_run(*args)
+    want = oracle.dtl_batch(species.parent, species.child0, species.child1, *args)
+    for g, w in zip(got, want):
+        assert np.array_equal(np.asarray(g), np.asarray(w))
+    got16 = ctx.dtl_run16(*args)
+    for g, w in zip(got16, want):
+        assert np.array_equal(np.asarray(g, np.int32), np.asarray(w))
