@@ -677,3 +677,23 @@ def test_thread_per_row_kernel_largest_species_tree(ctx, monkeypatch):
     got16 = ctx.dtl_run16(*args)
     for g, w in zip(got16, want):
         assert np.array_equal(np.asarray(g, np.int32), np.asarray(w))
+
+
+@pytest.mark.parametrize("n_species_leaves", [17, 31])
+def test_thread_per_row_kernel_on_a_caterpillar(ctx, monkeypatch, n_species_leaves):
+    """A caterpillar species tree with 17 / 31 leaves (depths up to 16 / 30: the deepest a 5-bit depth field holds):
+    path sets are long chains with one leaf hanging off every element, siblings alternate between "next element" and
+    "previous element".  600 trees of 45 leaves, leaves at any species node, against the oracle."""
+    monkeypatch.setenv("SR2_DTL_SIMD_MIN_ROWS", "1")
+    monkeypatch.setenv("SR2_DTL_CHAIN_ROWS", "300")
+    parent, child0, child1 = _caterpillar_species(n_species_leaves)
+    batch = synth.make_batch(45, 45, 600, seed=101)
+    rng = np.random.default_rng(102)
+    leaf_species = np.where(batch.left < 0, rng.integers(0, len(parent), len(batch.left)), -1).astype(np.int32)
+    ctx.set_species(parent, child0, child1)
+    for costs in ((0, 1, 1, 1, 1), (0, 3, 2, 2, 0)):
+        args = (batch.node_off, batch.left, batch.right, leaf_species, np.asarray(costs, np.int32))
+        got = ctx.dtl_run(*args)
+        want = oracle.dtl_batch(parent, child0, child1, *args)
+        for g, w in zip(got, want):
+            assert np.array_equal(np.asarray(g), np.asarray(w))
