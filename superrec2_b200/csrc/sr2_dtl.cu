@@ -1482,8 +1482,9 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 //              the sibling after it (kept in registers for one step), its SEPMIN by its children further on;
 //   * the row is written compact: entry e of the row's slot in T is value | species << 22 (TH_VAL_MASK = the
 //     infinite value), entry e of its tag row the usual tag, e < m = row_cnt[slot] in BFS order -- nothing for
-//     the infinite cells.  Results go through a per-warp staging tile, 8 elements x 32 rows at a time, and
-//     leave as full 32-byte sectors (8 consecutive entries of one row);
+//     the infinite cells.  A lane writes four entries of its row at a time, 16 bytes of values and 16 of tags (the
+//     two halves of a sector follow each other within a few dozen instructions and merge in L2; a per-warp staging
+//     tile that made full 32-byte sectors of them cost more instructions than it saved: 4.73 -> 4.66 ms per step);
 //   * readers: this kernel (a child's path set is a subset of its parent's, in the same order: a merge),
 //     dtl_wave_flat2_kernel (scatters a compact child into its dense key row), dtl_select_trace_kernel (the
 //     position of a species = number of path species before it, from the row's bit set).
@@ -1512,11 +1513,10 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 #define TH_C1_BIT 27
 #define THREAD_MAXM 128   // largest tier (row_cnt is a byte, compact rows reach 255 entries)
 #define TH_FLAG_SHIFT 28
-// shared-memory words of a CTA: Mc [MAXM + 1] pairs and el [MAXM] per thread, and per warp the staging tile
-// (8 x 32 values, 8 x 32 tags), the rows' table offsets (32 x 2 words) and sizes (32)
-#define THREAD_SMEM_WORDS(MAXM) ((3 * (MAXM) + 2) * THREAD_ROWS + (THREAD_ROWS / 32) * (512 + 96))
+// shared-memory words of a CTA: Mc [MAXM + 1] pairs, el [MAXM] and the bit set [MW = mask words] per thread
+#define THREAD_SMEM_WORDS(MAXM, MW) ((3 * (MAXM) + 2 + (MW)) * THREAD_ROWS)
 // ... plus the species table of the generation, one word per species: (first child + 1) << 16 | preorder time of the second child
-#define THREAD_SMEM_BYTES(MAXM, S) (4 * (size_t)(THREAD_SMEM_WORDS(MAXM) + (((S) + 3) & ~3)))
+#define THREAD_SMEM_BYTES(MAXM, MW, S) (4 * (size_t)(THREAD_SMEM_WORDS(MAXM, MW) + (((S) + 3) & ~3)))
 
 // The rows of this launch: the classes [cls0, cls0 + n_cls) of the wave's lists, one after the other (a "tier":
 // the classes whose sets have at most maxm species); the shared memory of the launch is sized for maxm.
@@ -1527,7 +1527,7 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
                        int list_pitch, const int* __restrict__ counts, int cls0, int n_cls, int MAXM, int cherry_end,
                        const uint8_t* __restrict__ row_cnt, const uint4* __restrict__ row_info) {
     extern __shared__ __align__(16) uint32_t th_smem[];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = threadIdx.x, lane = t & 31;
     const int idx = blockIdx.x * THREAD_ROWS + t;
     // the class this thread's list position falls into
     int n_list = 0, my_cls = -1, my_off = 0;
@@ -1551,7 +1551,7 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     // child a leaf species sits under).  From global memory that is a dependent trip to L2 per element (the
     // carve-out leaves no L1 to speak of): 27 % of the kernel's stall samples in the r7a capture.  The table is
     // staged per CTA instead, 4 bytes per species.
-    uint32_t* spt = th_smem + THREAD_SMEM_WORDS(MAXM);
+    uint32_t* spt = th_smem + THREAD_SMEM_WORDS(MAXM, sp.mask_words);
     for (int y = t; y < sp.S; y += THREAD_ROWS) {
         const uint2 z = __ldg(reinterpret_cast<const uint2*>(sp.span4 + y) + 1);  // (child0 + 1) << 16 | depth, tin of the second child
         spt[y] = (z.x & 0xffff0000u) | z.y;
@@ -1560,11 +1560,9 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     if (idx - lane >= n_list) return;  // the whole warp is beyond the lists
     uint2* Mc = reinterpret_cast<uint2*>(th_smem) + t;            // Mc[e * THREAD_ROWS]
     uint32_t* el = th_smem + 2 * (MAXM + 1) * THREAD_ROWS + t;    // el[e * THREAD_ROWS]
-    uint32_t* stage = th_smem + (3 * MAXM + 2) * THREAD_ROWS + warp * (512 + 96);  // [2][8][32] values, tags
-    uint32_t* rowinfo = stage + 512;                              // [32] x (offset lo, offset hi), [32] sizes
-    // the row's bit set lives in the warp's staging tile (16 words per lane, [word][lane]) until the cells phase
-    uint32_t* bits = stage + lane;
-    auto on_path = [&](int sx) { return (bits[(sx >> 5) * 32] >> (sx & 31)) & 1u; };
+    // the row's bit set: mask_words words per thread, [word][thread]
+    uint32_t* bits = th_smem + (3 * MAXM + 2) * THREAD_ROWS + t;
+    auto on_path = [&](int sx) { return (bits[(sx >> 5) * THREAD_ROWS] >> (sx & 31)) & 1u; };
     int cl = -1, cr = -1, m = 0;
     // per side: 0 = leaf at species a, 1 = virtual cherry (a, b), 2 = stored (compact) row
     int mode_l = 0, mode_r = 0, m_l = 0, m_r = 0;
@@ -1614,12 +1612,13 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
                 }
             }
         }
+        const int mw = sp.mask_words;   // (the words past it are padding)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            bits[(4 * q) * 32] = mk[q].x;
-            bits[(4 * q + 1) * 32] = mk[q].y;
-            bits[(4 * q + 2) * 32] = mk[q].z;
-            bits[(4 * q + 3) * 32] = mk[q].w;
+            if (4 * q < mw) bits[(4 * q) * THREAD_ROWS] = mk[q].x;
+            if (4 * q + 1 < mw) bits[(4 * q + 1) * THREAD_ROWS] = mk[q].y;
+            if (4 * q + 2 < mw) bits[(4 * q + 2) * THREAD_ROWS] = mk[q].z;
+            if (4 * q + 3 < mw) bits[(4 * q + 3) * THREAD_ROWS] = mk[q].w;
         }
         const int t_la = (int)il.y, t_lb = (int)il.z, t_ra = (int)ir.y, t_rb = (int)ir.z;
         l_da = (int)(il.w & 0xffu), l_db = (int)((il.w >> 8) & 0xffu), l_dl = (int)((il.w >> 16) & 0xffu);
@@ -1649,13 +1648,6 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             if (b1) el[(m++) * THREAD_ROWS] = w1;
         }
         SR2_DCHECK(m == (int)row_cnt[slot]);
-    }
-    // where the rows of this warp go (read by the flushes of the staging tile)
-    {
-        const unsigned long long off = (unsigned long long)slot * (unsigned)pitch;
-        rowinfo[2 * lane] = (unsigned)off;
-        rowinfo[2 * lane + 1] = (unsigned)(off >> 32);
-        rowinfo[64 + lane] = (unsigned)m;
     }
     // ---- child values -> keys ----------------------------------------------------------------------------
     {
@@ -1735,76 +1727,69 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     const unsigned dm = kp.dm, rm = kp.rm, hi_mul = 1u << (32 - kp.sh);
     const int c12 = -2 * loss, c3 = cs.dup, c45 = cs.hgt;
     const uint2 inf2 = make_uint2(0xffffffffu, 0xffffffffu);
-    const int m_warp = __reduce_max_sync(0xffffffffu, m);
-    __syncwarp();  // the staging tile held the lanes' bit sets until here
+    // Results leave as 16-byte stores, four entries of the lane's own row at a time (the two halves of a sector
+    // are written a few dozen instructions apart and merge in L2): no staging tile, no flush.
+    uint32_t* __restrict__ Tq = reinterpret_cast<uint32_t*>(T) + slot * (size_t)pitch;
+    uint32_t* __restrict__ Gq = tags + slot * (size_t)pitch;
     uint2 prevM = inf2;  // SUBMIN of the element before (its slot already holds its SEPMIN)
     unsigned w = m > 0 ? el[0] : 0u;
     int fc = 1;  // position of the first on-path child of the element at hand: a running count in BFS order
-    for (int e = 0; e < m_warp; ++e) {
-        if (e < m) {
-            const unsigned wn = el[(e + 1 < MAXM ? e + 1 : e) * THREAD_ROWS];  // (garbage past m: unused)
-            const int pp = (int)((w >> TH_PP_SHIFT) & TH_PP_MASK);
-            const uint2 Pp = Mc[pp * THREAD_ROWS], mm = Mc[e * THREAD_ROWS], Mn = Mc[(e + 1) * THREAD_ROWS];
-            // a sibling on a path is the next element (this one is the first child) or the previous one
-            const bool both = ((w >> TH_SIB_BIT) & 1u) != 0u;
-            const bool is_first = ((w >> TH_FIRST_BIT) & 1u) != 0u;
-            uint2 Ms = is_first ? Mn : prevM;
-            if (!both) Ms = inf2;
-            uint2 pq = make_uint2(min(Pp.x, Ms.x), min(Pp.y, Ms.y));
-            if (e == 0) pq = inf2;  // the root: nothing is incomparable to it
-            // the cell
-            const unsigned x = w & TH_S_MASK;
-            const int dx = (int)((w >> TH_D_SHIFT) & 31u);
-            const unsigned h0 = (w >> TH_C0_BIT) & 1u, h1 = (w >> TH_C1_BIT) & 1u;
-            uint2 k0 = inf2, k1 = inf2;  // SUBMIN at the two children of x
-            if (h0) k0 = Mc[fc * THREAD_ROWS];
-            if (h1) k1 = Mc[(fc + (int)h0) * THREAD_ROWS];
-            fc += (int)(h0 + h1);
-            const int nld = -loss * dx;
-            const int qMl = flat2_q(mm.x, hi_mul, dm, loss), qMr = flat2_q(mm.y, hi_mul, dm, loss);
-            const int ql0 = flat2_q(k0.x, hi_mul, dm, loss), qr0 = flat2_q(k0.y, hi_mul, dm, loss);
-            const int ql1 = flat2_q(k1.x, hi_mul, dm, loss), qr1 = flat2_q(k1.y, hi_mul, dm, loss);
-            const int pl = (int)__umulhi(pq.x, hi_mul), pr = (int)__umulhi(pq.y, hi_mul);
-            const int b12 = 2 * nld + c12, b3 = 2 * nld + c3, b45 = nld + c45;
-            const int w1 = flat2_pack(ql0 + qr1 + b12, 0);  // 1. speciation, left below x0, right below x1
-            const int w2 = flat2_pack(ql1 + qr0 + b12, 1);  // 2. the other way round
-            const int w3 = flat2_pack(qMl + qMr + b3, 2);   // 3. duplication
-            const int w4 = flat2_pack(pl + qMr + b45, 3);   // 4. transfer, left child away
-            const int w5 = flat2_pack(qMl + pr + b45, 4);   // 5. transfer, right child away
-            const int wb = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
-            const int best = wb >> 3, which = wb & 7;
-            unsigned ka = mm.x, kb = mm.y;
-            ka = which == 0 ? k0.x : ka;
-            ka = which == 1 ? k1.x : ka;
-            ka = which == 3 ? pq.x : ka;
-            kb = which == 0 ? k1.y : kb;
-            kb = which == 1 ? k0.y : kb;
-            kb = which == 4 ? pq.y : kb;
-            const bool finite = best < thresh;
-            SR2_DCHECK(!finite || (unsigned)best < TH_VAL_MASK);
-            const int k = e & 7, col = (lane + 4 * k) & 31;  // tile layout: conflict-free for this store and for the flush
-            stage[k * 32 + col] = (finite ? (unsigned)best : TH_VAL_MASK) | (x << TH_VAL_BITS);
-            stage[256 + k * 32 + col] = finite ? (((ka >> db) & rm) | (((kb >> db) & rm) << 16)) : SR2_NO_TAG;
-            Mc[e * THREAD_ROWS] = pq;
-            prevM = mm;
-            w = wn;
-        }
-        if ((e & 7) == 7 || e == m_warp - 1) {
-            __syncwarp();
-            const int e0 = e & ~7, k = lane & 7;
+    for (int e0 = 0; e0 < m; e0 += 4) {
+        unsigned vq[4] = {0u, 0u, 0u, 0u}, gq[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int r = 4 * j + (lane >> 3);  // the lanes of a quarter-warp write 8 consecutive entries of row r
-                const int m_r2 = (int)rowinfo[64 + r];
-                if (e0 < m_r2) {   // (entries past the row's size, up to the sector's end, are never read)
-                    const size_t off = ((size_t)rowinfo[2 * r + 1] << 32 | rowinfo[2 * r]) + (size_t)(e0 + k);
-                    const int col = (r + 4 * k) & 31;
-                    reinterpret_cast<uint32_t*>(T)[off] = stage[k * 32 + col];
-                    tags[off] = stage[256 + k * 32 + col];
-                }
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u;
+            if (e < m) {
+                const unsigned wn = el[(e + 1 < MAXM ? e + 1 : e) * THREAD_ROWS];  // (garbage past m: unused)
+                const int pp = (int)((w >> TH_PP_SHIFT) & TH_PP_MASK);
+                const uint2 Pp = Mc[pp * THREAD_ROWS], mm = Mc[e * THREAD_ROWS], Mn = Mc[(e + 1) * THREAD_ROWS];
+                // a sibling on a path is the next element (this one is the first child) or the previous one
+                const bool both = ((w >> TH_SIB_BIT) & 1u) != 0u;
+                const bool is_first = ((w >> TH_FIRST_BIT) & 1u) != 0u;
+                uint2 Ms = is_first ? Mn : prevM;
+                if (!both) Ms = inf2;
+                uint2 pq = make_uint2(min(Pp.x, Ms.x), min(Pp.y, Ms.y));
+                if (e == 0) pq = inf2;  // the root: nothing is incomparable to it
+                // the cell
+                const unsigned x = w & TH_S_MASK;
+                const int dx = (int)((w >> TH_D_SHIFT) & 31u);
+                const unsigned h0 = (w >> TH_C0_BIT) & 1u, h1 = (w >> TH_C1_BIT) & 1u;
+                uint2 k0 = inf2, k1 = inf2;  // SUBMIN at the two children of x
+                if (h0) k0 = Mc[fc * THREAD_ROWS];
+                if (h1) k1 = Mc[(fc + (int)h0) * THREAD_ROWS];
+                fc += (int)(h0 + h1);
+                const int nld = -loss * dx;
+                const int qMl = flat2_q(mm.x, hi_mul, dm, loss), qMr = flat2_q(mm.y, hi_mul, dm, loss);
+                const int ql0 = flat2_q(k0.x, hi_mul, dm, loss), qr0 = flat2_q(k0.y, hi_mul, dm, loss);
+                const int ql1 = flat2_q(k1.x, hi_mul, dm, loss), qr1 = flat2_q(k1.y, hi_mul, dm, loss);
+                const int pl = (int)__umulhi(pq.x, hi_mul), pr = (int)__umulhi(pq.y, hi_mul);
+                const int b12 = 2 * nld + c12, b3 = 2 * nld + c3, b45 = nld + c45;
+                const int w1 = flat2_pack(ql0 + qr1 + b12, 0);  // 1. speciation, left below x0, right below x1
+                const int w2 = flat2_pack(ql1 + qr0 + b12, 1);  // 2. the other way round
+                const int w3 = flat2_pack(qMl + qMr + b3, 2);   // 3. duplication
+                const int w4 = flat2_pack(pl + qMr + b45, 3);   // 4. transfer, left child away
+                const int w5 = flat2_pack(qMl + pr + b45, 4);   // 5. transfer, right child away
+                const int wb = min(min(min(w1, w2), w3), min(w4, w5));  // smallest value, then first candidate
+                const int best = wb >> 3, which = wb & 7;
+                unsigned ka = mm.x, kb = mm.y;
+                ka = which == 0 ? k0.x : ka;
+                ka = which == 1 ? k1.x : ka;
+                ka = which == 3 ? pq.x : ka;
+                kb = which == 0 ? k1.y : kb;
+                kb = which == 1 ? k0.y : kb;
+                kb = which == 4 ? pq.y : kb;
+                const bool finite = best < thresh;
+                SR2_DCHECK(!finite || (unsigned)best < TH_VAL_MASK);
+                vq[u] = (finite ? (unsigned)best : TH_VAL_MASK) | (x << TH_VAL_BITS);
+                gq[u] = finite ? (((ka >> db) & rm) | (((kb >> db) & rm) << 16)) : SR2_NO_TAG;
+                Mc[e * THREAD_ROWS] = pq;
+                prevM = mm;
+                w = wn;
             }
-            __syncwarp();
         }
+        // (entries past the row's size, up to the quad's end, are never read)
+        *reinterpret_cast<uint4*>(Tq + e0) = make_uint4(vq[0], vq[1], vq[2], vq[3]);
+        *reinterpret_cast<uint4*>(Gq + e0) = make_uint4(gq[0], gq[1], gq[2], gq[3]);
     }
 }
 
@@ -2189,19 +2174,28 @@ int sr2_check_costs(sr2_ctx* ctx, const char* who, const int32_t costs[5], int64
 
 // Tiers of dtl_wave_thread_kernel and the classes of dtl_partition_kernel (DtlProblem::tier_*, n_classes);
 // `table` (2 x 1024 bytes: class of a path-set size without / with compact rows) is filled when given.
-static void dtl_thread_tiers(DtlProblem* p, std::vector<uint8_t>* table) {
-    int tiers[8] = {27, 40, 50, 64}, nt = 4;  // 8 / 6 / 5 / 4 CTAs per SM with the 1.6 KB species table of config #2
+static void dtl_thread_tiers(sr2_ctx* ctx, DtlProblem* p, std::vector<uint8_t>* table) {
+    // Default tiers: the largest path sets that still fit 8 / 6 / 5 / 4 CTAs of the thread kernel on an SM (228 KB
+    // of shared memory, 1 KB of it reserved per CTA): 29 / 42 / 52 / 64 species for config #2 (399 species: 13 words
+    // of bit set per row, 1.6 KB of species table per CTA).  Below 4 CTAs per SM the kernel loses to flat2.
+    std::vector<int> tiers;
+    for (int k : {8, 6, 5, 4}) {
+        const long fixed = 1024 + (long)THREAD_SMEM_BYTES(0, ctx->dsp.mask_words, ctx->S);
+        const long fit = ((long)(228 * 1024) / k - fixed) / (long)(3 * THREAD_ROWS * sizeof(uint32_t));
+        tiers.push_back((int)std::max<long>(8, std::min<long>(64, fit)));
+    }
     if (const char* tv = getenv("SR2_THREAD_TIERS")) {
-        nt = 0;
-        for (const char* q = tv; *q && nt < 8;) {
-            tiers[nt++] = std::max(1, std::min(THREAD_MAXM, atoi(q)));
+        tiers.clear();
+        for (const char* q = tv; *q && tiers.size() < 8;) {
+            tiers.push_back(std::max(1, std::min(THREAD_MAXM, atoi(q))));
             while (*q && *q != ',') ++q;
             if (*q == ',') ++q;
         }
-        if (nt == 0) tiers[nt++] = 64;
+        if (tiers.empty()) tiers.push_back(64);
     }
-    std::sort(tiers, tiers + nt);
-    nt = (int)(std::unique(tiers, tiers + nt) - tiers);
+    std::sort(tiers.begin(), tiers.end());
+    tiers.erase(std::unique(tiers.begin(), tiers.end()), tiers.end());
+    const int nt = (int)tiers.size();
     int cls = 0, k = 0;
     p->n_tiers = nt;
     p->tier_cls0[0] = 0;
@@ -2263,7 +2257,7 @@ static int dtl_prepare(void* user) {
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_DESC, (table_elems / ctx->pitch) * sizeof(int4) + 256, &ptr))) return rc;
     p->d_desc = (int4*)ptr;
     p->list_pitch = std::max<int64_t>(p->rows.R, 1);
-    dtl_thread_tiers(p, nullptr);
+    dtl_thread_tiers(ctx, p, nullptr);
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_LISTS, (size_t)std::max(p->n_classes[0], p->n_classes[1]) * p->list_pitch * sizeof(int), &ptr))) return rc;
     p->d_lists = (int*)ptr;
     if ((rc = sr2_dev_reserve(ctx, DP_DTL_COUNTS, p->rows.chunks.size() * DTL_MAX_CLASSES * 65536 * sizeof(int), &ptr))) return rc;
@@ -2498,7 +2492,7 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
             // species, 4 above) cut at the tier limits; the class after the last tier is the dense one.
             {
                 std::vector<uint8_t> table(2048, 0);
-                dtl_thread_tiers(p, &table);
+                dtl_thread_tiers(ctx, p, &table);
                 void* ptr = nullptr;
                 int rc = sr2_dev_reserve(ctx, DP_DTL_CLASSES, table.size(), &ptr);
                 if (rc) return rc;
@@ -2508,7 +2502,7 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
                     SR2_CUDA(ctx, cudaMemcpyAsync(p->d_class_of, p->class_table.data(), table.size(), cudaMemcpyHostToDevice, ctx->stream));
                 }
                 SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)THREAD_SMEM_BYTES(p->tier_maxm[p->n_tiers - 1], ctx->S)));
+                                                   (int)THREAD_SMEM_BYTES(p->tier_maxm[p->n_tiers - 1], ctx->dsp.mask_words, ctx->S)));
                 SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 // compact rows: everything the thread kernel writes, and the rows of flat2's sparse cells pass (row_cnt is a byte)
                 p->compact_max = std::max(p->tier_maxm[p->n_tiers - 1], std::min(p->flat2_sparse_max, 255));
@@ -2606,7 +2600,7 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             const unsigned ctas = (unsigned)((n_rows + THREAD_ROWS - 1) / THREAD_ROWS);
             for (int k = 0; k < p->n_tiers; ++k) {
                 ++p->n_launch;
-                dtl_wave_thread_kernel<<<ctas, THREAD_ROWS, THREAD_SMEM_BYTES(p->tier_maxm[k], ctx->S), ts[k]>>>(
+                dtl_wave_thread_kernel<<<ctas, THREAD_ROWS, THREAD_SMEM_BYTES(p->tier_maxm[k], ctx->dsp.mask_words, ctx->S), ts[k]>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
                     p->cur_mask, lists, (int)p->list_pitch, counts, p->tier_cls0[k], p->tier_cls0[k + 1] - p->tier_cls0[k],
                     p->tier_maxm[k], p->cur_cherry_end, p->cur_rowcnt, p->cur_rowinfo);
