@@ -1624,7 +1624,9 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         l_da = (int)(il.w & 0xffu), l_db = (int)((il.w >> 8) & 0xffu), l_dl = (int)((il.w >> 16) & 0xffu);
         r_da = (int)(ir.w & 0xffu), r_db = (int)((ir.w >> 8) & 0xffu), r_dl = (int)((ir.w >> 16) & 0xffu);
         // ---- elements: top-down over the path set ----------------------------------------------------
-        el[0] = 0xfu << TH_FLAG_SHIFT;  // the root: species 0, depth 0, on every root path
+        // the root: species 0, depth 0, on every root path; its "parent" is slot MAXM, which holds the infinite pair
+        // during the cells pass (nothing is incomparable to the root)
+        el[0] = (0xfu << TH_FLAG_SHIFT) | ((unsigned)MAXM << TH_PP_SHIFT);
         m = 1;
         for (int p = 0; p < m; ++p) {
             const unsigned w = el[p * THREAD_ROWS];
@@ -1734,13 +1736,14 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     uint2 prevM = inf2;  // SUBMIN of the element before (its slot already holds its SEPMIN)
     unsigned w = m > 0 ? el[0] : 0u;
     int fc = 1;  // position of the first on-path child of the element at hand: a running count in BFS order
+    Mc[MAXM * THREAD_ROWS] = inf2;  // the root's "parent"
     for (int e0 = 0; e0 < m; e0 += 4) {
         unsigned vq[4] = {0u, 0u, 0u, 0u}, gq[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int e = e0 + u;
             if (e < m) {
-                const unsigned wn = el[(e + 1 < MAXM ? e + 1 : e) * THREAD_ROWS];  // (garbage past m: unused)
+                const unsigned wn = el[(e + 1) * THREAD_ROWS];  // (past m, or past el into the bit set: unused)
                 const int pp = (int)((w >> TH_PP_SHIFT) & TH_PP_MASK);
                 const uint2 Pp = Mc[pp * THREAD_ROWS], mm = Mc[e * THREAD_ROWS], Mn = Mc[(e + 1) * THREAD_ROWS];
                 // a sibling on a path is the next element (this one is the first child) or the previous one
@@ -1748,8 +1751,7 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
                 const bool is_first = ((w >> TH_FIRST_BIT) & 1u) != 0u;
                 uint2 Ms = is_first ? Mn : prevM;
                 if (!both) Ms = inf2;
-                uint2 pq = make_uint2(min(Pp.x, Ms.x), min(Pp.y, Ms.y));
-                if (e == 0) pq = inf2;  // the root: nothing is incomparable to it
+                const uint2 pq = make_uint2(min(Pp.x, Ms.x), min(Pp.y, Ms.y));
                 // the cell
                 const unsigned x = w & TH_S_MASK;
                 const int dx = (int)((w >> TH_D_SHIFT) & 31u);
