@@ -1560,9 +1560,14 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
     if (idx - lane >= n_list) return;  // the whole warp is beyond the lists
     uint2* Mc = reinterpret_cast<uint2*>(th_smem) + t;            // Mc[e * THREAD_ROWS]
     uint32_t* el = th_smem + 2 * (MAXM + 1) * THREAD_ROWS + t;    // el[e * THREAD_ROWS]
-    // the row's bit set: mask_words words per thread, [word][thread]
+    // the row's bit set, shifted down by one bit: mask_words words per thread, [word][thread].  In BFS numbering the
+    // children of a species are 2i + 1 and 2i + 2, so after the shift their two bits sit in one word at an even
+    // position: one look-up answers "which of the children are on a path".
     uint32_t* bits = th_smem + (3 * MAXM + 2) * THREAD_ROWS + t;
-    auto on_path = [&](int sx) { return (bits[(sx >> 5) * THREAD_ROWS] >> (sx & 31)) & 1u; };
+    auto children_on_path = [&](int c0) {   // bit 0: c0, bit 1: c0 + 1
+        SR2_DCHECK((c0 & 1) == 1);
+        return (bits[((c0 - 1) >> 5) * THREAD_ROWS] >> ((c0 - 1) & 31)) & 3u;
+    };
     int cl = -1, cr = -1, m = 0;
     // per side: 0 = leaf at species a, 1 = virtual cherry (a, b), 2 = stored (compact) row
     int mode_l = 0, mode_r = 0, m_l = 0, m_r = 0;
@@ -1612,13 +1617,13 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
                 }
             }
         }
-        const int mw = sp.mask_words;   // (the words past it are padding)
+        const int mw = sp.mask_words;   // (the words past it are padding: zero)
+        {
+            const unsigned wd[17] = {mk[0].x, mk[0].y, mk[0].z, mk[0].w, mk[1].x, mk[1].y, mk[1].z, mk[1].w, mk[2].x,
+                                     mk[2].y, mk[2].z, mk[2].w, mk[3].x, mk[3].y, mk[3].z, mk[3].w, 0u};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (4 * q < mw) bits[(4 * q) * THREAD_ROWS] = mk[q].x;
-            if (4 * q + 1 < mw) bits[(4 * q + 1) * THREAD_ROWS] = mk[q].y;
-            if (4 * q + 2 < mw) bits[(4 * q + 2) * THREAD_ROWS] = mk[q].z;
-            if (4 * q + 3 < mw) bits[(4 * q + 3) * THREAD_ROWS] = mk[q].w;
+            for (int j = 0; j < 16; ++j)
+                if (j < mw) bits[j * THREAD_ROWS] = __funnelshift_r(wd[j], j + 1 < mw ? wd[j + 1] : 0u, 1);
         }
         const int t_la = (int)il.y, t_lb = (int)il.z, t_ra = (int)ir.y, t_rb = (int)ir.z;
         l_da = (int)(il.w & 0xffu), l_db = (int)((il.w >> 8) & 0xffu), l_dl = (int)((il.w >> 16) & 0xffu);
@@ -1634,7 +1639,7 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             const int d = (int)((w >> TH_D_SHIFT) & 31u);
             const int c0 = (int)(z >> 16) - 1;
             if (c0 < 0) continue;
-            const unsigned b0 = on_path(c0), b1 = on_path(c0 + 1);
+            const unsigned pair = children_on_path(c0), b0 = pair & 1u, b1 = pair >> 1;
             // (neither child on a path: an object leaf sits at this internal species)
             SR2_DCHECK(m + (int)(b0 + b1) <= MAXM);  // dtl_partition_kernel only lists rows that fit the tier
             el[p * THREAD_ROWS] = w | (b0 << TH_C0_BIT) | (b1 << TH_C1_BIT);
