@@ -50,10 +50,10 @@ WORKLOADS = {
 }
 BYTES_PER_CELL = 20  # 2 x 4 B child reads + 4 B value + 8 B traceback
 # DRAM bytes per evaluated cell, measured: ncu dram__bytes_read.sum + dram__bytes_write.sum of EVERY launch of
-# one step of the headline workload (profiles/r7d_dram_per_launch_config2.csv: 6.53 GB per step, 4.53 GB of
+# one step of the headline workload (profiles/r7h_dram_per_launch_config2.csv: 6.57 GB per step, 4.59 GB of
 # it in the 66 wave launches; 17.59 GB before the sparse rows were stored compact, r4g) / cells of the rows that
 # are materialised (1,325,775,654 on rank 0's batch)
-DRAM_B_PER_CELL_STEP, DRAM_B_PER_CELL_WAVES = 6.531e9 / 1325775654, 4.525e9 / 1325775654
+DRAM_B_PER_CELL_STEP, DRAM_B_PER_CELL_WAVES = 6.572e9 / 1325775654, 4.586e9 / 1325775654
 
 
 def measured_peak():
@@ -663,8 +663,8 @@ def main():
                                     "really cross the HBM interface (ncu, every launch of a step) / time / peak -- the kernels are bound by "
                                     "instruction latency and issue slots, not by HBM",
                          "kernel": "dtl wave kernels: dtl_wave_thread_kernel (rows with <= 64 root-path species: a thread "
-                                   "per row, rows stored compact; 40 % of the serialised kernel time of a step), "
-                                   "dtl_wave_flat2_kernel (the other rows, a warp per row, 38 %, and the chained launch "
+                                   "per row, rows stored compact; 38 % of the serialised kernel time of a step), "
+                                   "dtl_wave_flat2_kernel (the other rows, a warp per row, 39 %, and the chained launch "
                                    "of the small top waves, 7 %); wave 1 is virtual (readers evaluate the closed form of a cherry row)",
                          "peak_source": peak_src,
                          "bytes_per_cell": BYTES_PER_CELL,
@@ -677,7 +677,7 @@ def main():
                          "cells_evaluated_per_step": cells_evaluated, "cherry_rows": n_cherry,
                          "traffic_source": "bytes per wave (average over the step's 14 waves) from ncu "
                                            "dram__bytes_read.sum + dram__bytes_write.sum of every launch of one step, "
-                                           "profiles/r7d_dram_per_launch_config2.csv (cold caches, launches serialised), "
+                                           "profiles/r7h_dram_per_launch_config2.csv (cold caches, launches serialised), "
                                            "scaled by the cells this batch evaluates"},
             "checksum_min_costs": checksum,
         }
