@@ -28,7 +28,7 @@
 //                          lists of rows by path-set size (bins grouped into the tiers of the thread kernel, and
 //                          the dense rows), per row the record the thread kernel starts from; dtl_desc_kernel
 //   big waves              dtl_wave_thread_kernel (rows with <= 64 path species: one THREAD per row, tiers of
-//                          27 / 40 / 50 / 64 species, rows stored compact: value | species << 22 and the tag per
+//                          29 / 42 / 52 / 64 species for config #2, rows stored compact: value | species << 22 and the tag per
 //                          path species, nothing for the infinite cells) and dtl_wave_flat2_kernel<NS, false>
 //                          (a warp per dense row; rows of up to 3/8 pitch path species stored compact too), on
 //                          up to five streams
