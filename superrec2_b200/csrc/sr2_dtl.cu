@@ -1520,6 +1520,8 @@ dtl_wave_sparse_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
 
 // The rows of this launch: the classes [cls0, cls0 + n_cls) of the wave's lists, one after the other (a "tier":
 // the classes whose sets have at most maxm species); the shared memory of the launch is sized for maxm.
+// STORED = false: the rows of wave 2, whose children are leaves and (virtual) cherries only -- no child rows to load or merge.
+template <bool STORED>
 __global__ void __launch_bounds__(THREAD_ROWS)
 dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const int32_t* __restrict__ row_cr,
                        int64_t row_begin, int64_t chunk_row0, int32_t* __restrict__ T, uint32_t* __restrict__ tags,
@@ -1580,8 +1582,9 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
         SR2_DCHECK(cl == row_cl[chunk_row0 + slot] && cr == row_cr[chunk_row0 + slot]);
         mode_l = cl < 0 ? 0 : (cl < cherry_end ? 1 : 2);
         mode_r = cr < 0 ? 0 : (cr < cherry_end ? 1 : 2);
-        if (mode_l == 2) m_l = (int)(il.w >> 24);
-        if (mode_r == 2) m_r = (int)(ir.w >> 24);
+        SR2_DCHECK(STORED || (mode_l != 2 && mode_r != 2));
+        if (STORED && mode_l == 2) m_l = (int)(il.w >> 24);
+        if (STORED && mode_r == 2) m_r = (int)(ir.w >> 24);
         SR2_DCHECK(mode_l != 2 || (m_l > 0 && m_l == (int)row_cnt[cl]));  // a child's path set is a subset of this
         SR2_DCHECK(mode_r != 2 || (m_r > 0 && m_r == (int)row_cnt[cr]));  // row's: it is a compact row
         // Everything the row reads from memory is requested here, in one go: its bit set and the entries of its
@@ -1706,12 +1709,12 @@ dtl_wave_thread_kernel(DevSpecies sp, const int32_t* __restrict__ row_cl, const 
             const unsigned f = w >> TH_FLAG_SHIFT;
             const unsigned ld = (unsigned)(loss * d);
             unsigned va = closed(zl, f & 1u, f & 2u, d, ld), vb = closed(zr, f & 4u, f & 8u, d, ld);
-            if ((next_l >> TH_VAL_BITS) == s) {   // (0xffffffff >> 22 = 1023 is no species: rank_bits <= 9)
+            if (STORED && (next_l >> TH_VAL_BITS) == s) {   // (0xffffffff >> 22 = 1023 is no species: rank_bits <= 9)
                 va = next_l & TH_VAL_MASK;
                 q_l -= 1;
                 next_l = q_l >= 0 ? Mc[q_l * THREAD_ROWS].x : 0xffffffffu;
             }
-            if ((next_r >> TH_VAL_BITS) == s) {
+            if (STORED && (next_r >> TH_VAL_BITS) == s) {
                 vb = next_r & TH_VAL_MASK;
                 q_r -= 1;
                 next_r = q_r >= 0 ? Mc[q_r * THREAD_ROWS].y : 0xffffffffu;
@@ -2508,9 +2511,11 @@ static int dtl_configure_simd(sr2_ctx* ctx, DtlProblem* p) {
                     p->class_table = table;
                     SR2_CUDA(ctx, cudaMemcpyAsync(p->d_class_of, p->class_table.data(), table.size(), cudaMemcpyHostToDevice, ctx->stream));
                 }
-                SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   (int)THREAD_SMEM_BYTES(p->tier_maxm[p->n_tiers - 1], ctx->dsp.mask_words, ctx->S)));
-                SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                const int th_smem_max = (int)THREAD_SMEM_BYTES(p->tier_maxm[p->n_tiers - 1], ctx->dsp.mask_words, ctx->S);
+                SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, th_smem_max));
+                SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+                SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, th_smem_max));
+                SR2_CUDA(ctx, cudaFuncSetAttribute(dtl_wave_thread_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
                 // compact rows: everything the thread kernel writes, and the rows of flat2's sparse cells pass (row_cnt is a byte)
                 p->compact_max = std::max(p->tier_maxm[p->n_tiers - 1], std::min(p->flat2_sparse_max, 255));
                 if (const char* dd = getenv("SR2_DTL_DECOUPLE_DENSE")) p->decouple_dense = dd[0] != '0';
@@ -2607,7 +2612,9 @@ static int dtl_launch_wave(sr2_ctx* ctx, DtlProblem* p, const RowChunk& c, int h
             const unsigned ctas = (unsigned)((n_rows + THREAD_ROWS - 1) / THREAD_ROWS);
             for (int k = 0; k < p->n_tiers; ++k) {
                 ++p->n_launch;
-                dtl_wave_thread_kernel<<<ctas, THREAD_ROWS, THREAD_SMEM_BYTES(p->tier_maxm[k], ctx->dsp.mask_words, ctx->S), ts[k]>>>(
+                // (wave 2 with virtual cherries: no row has a stored child)
+                auto fn = (h == 2 && p->cur_cherry_end > 0) ? dtl_wave_thread_kernel<false> : dtl_wave_thread_kernel<true>;
+                fn<<<ctas, THREAD_ROWS, THREAD_SMEM_BYTES(p->tier_maxm[k], ctx->dsp.mask_words, ctx->S), ts[k]>>>(
                     ctx->dsp, p->rows.row_cl, p->rows.row_cr, row_begin, c.row_begin, p->cur_T, p->cur_tag, cs, kp,
                     p->cur_mask, lists, (int)p->list_pitch, counts, p->tier_cls0[k], p->tier_cls0[k + 1] - p->tier_cls0[k],
                     p->tier_maxm[k], p->cur_cherry_end, p->cur_rowcnt, p->cur_rowinfo);
